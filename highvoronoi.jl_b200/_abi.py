@@ -1,0 +1,83 @@
+"""ctypes binding of include/hvb200.h.  The library is required: importing this module without a built
+libhvb200.so raises, and every compute call fails with HVB_ENOGPU when no CUDA device is present."""
+import ctypes
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "libhvb200.so")
+
+HVB_OK, HVB_EINVAL, HVB_ECUDA, HVB_ENOGPU, HVB_ENOMEM, HVB_EDEGENERATE, HVB_ESTATE, HVB_EINCOMPLETE = 0, -1, -2, -3, -4, -5, -6, -7
+ERROR_NAMES = {-1: "HVB_EINVAL", -2: "HVB_ECUDA", -3: "HVB_ENOGPU", -4: "HVB_ENOMEM", -5: "HVB_EDEGENERATE",
+               -6: "HVB_ESTATE", -7: "HVB_EINCOMPLETE"}
+
+EXPORTS = ("hvb_default_params", "hvb_create", "hvb_search", "hvb_counts", "hvb_fetch_vertices", "hvb_fetch_rays",
+           "hvb_neighbor_count", "hvb_fetch_neighbors", "hvb_view_vertices", "hvb_export_device", "hvb_merge_device",
+           "hvb_stats", "hvb_last_error", "hvb_destroy", "hvb_version")
+
+
+class hvb_params(ctypes.Structure):
+    _fields_ = [("variance_tol", ctypes.c_double), ("break_tol", ctypes.c_double), ("b_nodes_tol", ctypes.c_double),
+                ("plane_tolerance", ctypes.c_double), ("ray_tol", ctypes.c_double),
+                ("method", ctypes.c_int32), ("device", ctypes.c_int32), ("rank", ctypes.c_int32), ("world", ctypes.c_int32),
+                ("fp32_filter", ctypes.c_int32), ("on_degenerate", ctypes.c_int32), ("points_per_cell", ctypes.c_int32),
+                ("seed_stride", ctypes.c_int32), ("sort_output", ctypes.c_int32), ("tile_size", ctypes.c_int32),
+                ("vertex_capacity", ctypes.c_int64), ("probe_scale", ctypes.c_double)]
+
+
+class hvb_stats_t(ctypes.Structure):
+    _fields_ = [(k, ctypes.c_int64) for k in
+                ("vertices", "rays", "raycasts", "duplicate_hits", "closed_skips", "candidates_fp32", "candidates_fp64",
+                 "rows_scanned", "probe_stages", "rounds", "seeds", "degenerate", "kernel_launches", "capacity_retries")] + \
+               [(k, ctypes.c_double) for k in ("ms_build", "ms_search", "ms_finalize", "ms_expand_kernel")] + \
+               [("expand_launches", ctypes.c_int64), ("expand_items", ctypes.c_int64)]
+
+    def as_dict(self):
+        return {k: getattr(self, k) for k, _ in self._fields_}
+
+
+class HVBError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__("%s: %s" % (ERROR_NAMES.get(code, str(code)), msg))
+        self.code = code
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise ImportError("libhvb200.so is not built (%s); run `python highvoronoi.jl_b200/build.py` -- there is no "
+                              "fallback implementation" % LIB_PATH)
+        L = ctypes.CDLL(LIB_PATH)
+        vp, i64, i32 = ctypes.c_void_p, ctypes.c_int64, ctypes.c_int
+        L.hvb_default_params.argtypes = [ctypes.POINTER(hvb_params)]
+        L.hvb_default_params.restype = None
+        L.hvb_create.argtypes = [ctypes.POINTER(vp), i32, i64, vp, i32, vp, vp, ctypes.POINTER(hvb_params)]
+        L.hvb_search.argtypes = [vp, vp, i64, vp, vp, i64, i32]
+        L.hvb_counts.argtypes = [vp, ctypes.POINTER(i64), ctypes.POINTER(i64), ctypes.POINTER(i64)]
+        L.hvb_fetch_vertices.argtypes = [vp, vp, vp]
+        L.hvb_fetch_rays.argtypes = [vp, vp, vp, vp, vp]
+        L.hvb_neighbor_count.argtypes = [vp, ctypes.POINTER(i64)]
+        L.hvb_fetch_neighbors.argtypes = [vp, vp, vp]
+        L.hvb_view_vertices.argtypes = [vp, ctypes.POINTER(vp), ctypes.POINTER(vp), ctypes.POINTER(i64)]
+        L.hvb_export_device.argtypes = [vp, vp, vp, i64, ctypes.POINTER(i64)]
+        L.hvb_merge_device.argtypes = [vp, vp, vp, i64]
+        L.hvb_stats.argtypes = [vp, ctypes.POINTER(hvb_stats_t)]
+        L.hvb_last_error.argtypes = [vp]
+        L.hvb_last_error.restype = ctypes.c_char_p
+        L.hvb_destroy.argtypes = [vp]
+        L.hvb_destroy.restype = None
+        L.hvb_version.restype = ctypes.c_char_p
+        for name in ("hvb_create", "hvb_search", "hvb_counts", "hvb_fetch_vertices", "hvb_fetch_rays", "hvb_neighbor_count",
+                     "hvb_fetch_neighbors", "hvb_view_vertices", "hvb_export_device", "hvb_merge_device", "hvb_stats"):
+            getattr(L, name).restype = i32
+        _lib = L
+    return _lib
+
+
+def check(rc, ctx=None):
+    if rc != HVB_OK:
+        msg = lib().hvb_last_error(ctx)
+        raise HVBError(rc, msg.decode() if msg else "")

@@ -1,0 +1,225 @@
+"""Host-side mirror of the reference interface for the raycast vertex-search path.
+
+Julia is not available in the build environment, so this Python layer plays the role of the Julia shim
+(julia/HighVoronoiB200.jl): same names, argument meaning and error behaviour as the reference for this path --
+VoronoiNodes (voronoinodes.jl:14), Boundary / cuboid (boundary.jl:22-29, 510-534), RaycastParameter
+(raycast-types.jl:312-324), Raycast (raycast.jl:26), voronoi (sysvoronoi.jl:21), VoronoiGeometry (geometry.jl:139),
+VoronoiData (voronoidata.jl:621).  All computation happens in libhvb200.so on the GPU.
+"""
+import ctypes
+
+import numpy as np
+
+from . import _abi
+from ._abi import HVBError  # noqa: F401
+
+
+def VoronoiNodes(x):
+    """VoronoiNodes(x::Matrix) (voronoinodes.jl:14-20): columns are points.  Accepts (d, N) like the reference;
+    an (N, d) array is accepted when it cannot be confused (N > 6 >= d)."""
+    x = np.asarray(x, dtype=np.float64)
+    if x.ndim != 2:
+        raise ValueError("VoronoiNodes expects a matrix")
+    if x.shape[0] <= 6 < x.shape[1]:
+        x = x.T
+    return np.ascontiguousarray(x)
+
+
+class Boundary:
+    """Boundary(planes...) (boundary.jl:78-85): convex domain {y : normal_p . (y - base_p) <= 0}."""
+
+    def __init__(self, base=None, normal=None, periodic=()):
+        self.base = np.zeros((0, 0)) if base is None else np.ascontiguousarray(base, dtype=np.float64)
+        self.normal = np.zeros((0, 0)) if normal is None else np.ascontiguousarray(normal, dtype=np.float64)
+        self.periodic = tuple(periodic)
+
+    def __len__(self):
+        return self.base.shape[0]
+
+
+def cuboid(dim, dimensions=None, periodic=None, neumann=(), offset=None):
+    """cuboid(dim; dimensions, periodic, neumann, offset) (boundary.jl:510-534).  Plane 2i-1 is the upper face of
+    axis i, plane 2i the lower one.  NOTE the reference's default is periodic=1:dim; the search itself treats every
+    plane as a mirror (geometry.jl:156), periodisation is host orchestration outside this path."""
+    dimensions = np.ones(dim) if dimensions is None else np.asarray(dimensions, dtype=np.float64)
+    offset = np.zeros(dim) if offset is None else np.asarray(offset, dtype=np.float64)
+    periodic = tuple(range(1, dim + 1)) if periodic is None else tuple(periodic)
+    base = np.zeros((2 * dim, dim))
+    normal = np.zeros((2 * dim, dim))
+    for i in range(dim):
+        base[2 * i] = offset
+        base[2 * i, i] += dimensions[i]
+        normal[2 * i, i] = 1.0
+        base[2 * i + 1] = offset
+        normal[2 * i + 1, i] = -1.0
+    return Boundary(base, normal, periodic)
+
+
+# method / threading singletons (raycast-types.jl:244-284, HighVoronoi.jl:60-81)
+RCStandard = RCNonGeneral = RCNonGeneralHP = 0
+RCOriginal = 1
+RCCombined = 2
+RCNonGeneralFast = 3
+
+
+class SingleThread:
+    pass
+
+
+class B200Thread:
+    """The new `threading` singleton the Julia shim adds: run the search on GPU `device`,
+    as slab `rank` of `world` GPUs."""
+
+    def __init__(self, device=0, rank=0, world=1):
+        self.device, self.rank, self.world = device, rank, world
+
+
+def RaycastParameter(variance_tol=1e-15, break_tol=1e-5, b_nodes_tol=1e-7, plane_tolerance=1e-12, ray_tol=1e-12,
+                     method=RCStandard, threading=None, **backend):
+    """RaycastParameter{Float64}(; ...) (raycast-types.jl:312-324) plus backend knobs (fp32_filter, on_degenerate,
+    points_per_cell, seed_stride, sort_output, vertex_capacity, probe_scale)."""
+    p = _abi.hvb_params()
+    _abi.lib().hvb_default_params(ctypes.byref(p))
+    p.variance_tol, p.break_tol, p.b_nodes_tol, p.plane_tolerance, p.ray_tol = variance_tol, break_tol, b_nodes_tol, plane_tolerance, ray_tol
+    p.method = int(method)
+    if threading is not None and isinstance(threading, B200Thread):
+        p.device, p.rank, p.world = threading.device, threading.rank, threading.world
+    for k, v in backend.items():
+        if not hasattr(p, k):
+            raise TypeError("unknown search setting %r" % k)
+        setattr(p, k, v)
+    return p
+
+
+class Raycast:
+    """Raycast(xs; domain=Boundary(), options=RaycastParameter()) (raycast.jl:26): owns the device context
+    (generators + spatial index)."""
+
+    def __init__(self, xs, domain=None, options=None):
+        self.xs = VoronoiNodes(xs) if not (isinstance(xs, np.ndarray) and xs.flags.c_contiguous and xs.dtype == np.float64 and xs.ndim == 2 and xs.shape[0] > xs.shape[1]) else xs
+        self.domain = domain if domain is not None else Boundary()
+        self.parameters = options if options is not None else RaycastParameter()
+        n, d = self.xs.shape
+        self.n, self.dim = n, d
+        L = _abi.lib()
+        self._ctx = ctypes.c_void_p()
+        P = len(self.domain)
+        base = self.domain.base.ctypes.data_as(ctypes.c_void_p) if P else None
+        normal = self.domain.normal.ctypes.data_as(ctypes.c_void_p) if P else None
+        rc = L.hvb_create(ctypes.byref(self._ctx), d, n, self.xs.ctypes.data_as(ctypes.c_void_p), P, base, normal,
+                          ctypes.byref(self.parameters))
+        if rc != _abi.HVB_OK:
+            self._ctx = None
+            _abi.check(rc, None)
+
+    def close(self):
+        if getattr(self, "_ctx", None):
+            _abi.lib().hvb_destroy(self._ctx)
+            self._ctx = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def stats(self):
+        s = _abi.hvb_stats_t()
+        _abi.check(_abi.lib().hvb_stats(self._ctx, ctypes.byref(s)), self._ctx)
+        return s.as_dict()
+
+
+class VoronoiMesh:
+    """Result of voronoi(): the vertex database in the reference's external numbering (1-based ids, plane p = n+p)."""
+
+    def __init__(self, searcher):
+        self.searcher = searcher
+        self.n, self.dim = searcher.n, searcher.dim
+        L, ctx = _abi.lib(), searcher._ctx
+        nv, nr, ml = ctypes.c_int64(), ctypes.c_int64(), ctypes.c_int64()
+        _abi.check(L.hvb_counts(ctx, ctypes.byref(nv), ctypes.byref(nr), ctypes.byref(ml)), ctx)
+        d = self.dim
+        self.sig = np.empty((nv.value, d + 1), dtype=np.int64)
+        self.r = np.empty((nv.value, d), dtype=np.float64)
+        _abi.check(L.hvb_fetch_vertices(ctx, self.sig.ctypes.data_as(ctypes.c_void_p), self.r.ctypes.data_as(ctypes.c_void_p)), ctx)
+        self.ray_edge = np.empty((nr.value, d), dtype=np.int64)
+        self.ray_base = np.empty((nr.value, d))
+        self.ray_dir = np.empty((nr.value, d))
+        self.ray_node = np.empty((nr.value,), dtype=np.int64)
+        if nr.value:
+            P = lambda a: a.ctypes.data_as(ctypes.c_void_p)
+            _abi.check(L.hvb_fetch_rays(ctx, P(self.ray_edge), P(self.ray_base), P(self.ray_dir), P(self.ray_node)), ctx)
+        self._nb = None
+        self._cell_index = None
+
+    def neighbors(self):
+        """CSR (offsets[n+1], ids) of neighbors_of_cell for every cell (neighbors.jl:214-262)."""
+        if self._nb is None:
+            L, ctx = _abi.lib(), self.searcher._ctx
+            tot = ctypes.c_int64()
+            _abi.check(L.hvb_neighbor_count(ctx, ctypes.byref(tot)), ctx)
+            off = np.empty((self.n + 1,), dtype=np.int64)
+            ids = np.empty((tot.value,), dtype=np.int64)
+            _abi.check(L.hvb_fetch_neighbors(ctx, off.ctypes.data_as(ctypes.c_void_p), ids.ctypes.data_as(ctypes.c_void_p)), ctx)
+            self._nb = (off, ids)
+        return self._nb
+
+    def neighbors_of_cell(self, i):
+        off, ids = self.neighbors()
+        return ids[off[i - 1]:off[i]]
+
+    def vertices_iterator(self, i):
+        """all (sig, r) of cell i (1-based), like vertices_iterator(mesh, i) (abstractmesh.jl:179)."""
+        if self._cell_index is None:
+            real = self.sig <= self.n
+            rows = np.repeat(np.arange(self.sig.shape[0]), self.dim + 1)[real.ravel()]
+            cells = self.sig.ravel()[real.ravel()]
+            order = np.argsort(cells, kind="stable")
+            self._cell_index = (np.searchsorted(cells[order], np.arange(1, self.n + 2)), rows[order])
+        starts, rows = self._cell_index
+        for v in rows[starts[i - 1]:starts[i]]:
+            yield self.sig[v], self.r[v]
+
+    def number_of_vertices(self):
+        return self.sig.shape[0]
+
+
+def voronoi(xs, searcher=None, Iter=None, **_ignored):
+    """voronoi(xs; searcher=Raycast(xs), Iter=1:length(xs)) (sysvoronoi.jl:7-39) -> (mesh, searcher)."""
+    if searcher is None:
+        searcher = Raycast(xs)
+    L, ctx = _abi.lib(), searcher._ctx
+    if Iter is None:
+        rc = L.hvb_search(ctx, None, 0, None, None, 0, 0)
+    else:
+        cells = np.ascontiguousarray(np.asarray(list(Iter), dtype=np.int64))
+        rc = L.hvb_search(ctx, cells.ctypes.data_as(ctypes.c_void_p), cells.shape[0], None, None, 0, 0)
+    _abi.check(rc, ctx)
+    return VoronoiMesh(searcher), searcher
+
+
+class VoronoiGeometry:
+    """VoronoiGeometry(xs, b; search_settings=(...)) (geometry.jl:139-201), restricted to what this path produces:
+    the vertex database and the neighbour lists (integrate=false)."""
+
+    def __init__(self, xs, b=None, search_settings=None, **_ignored):
+        xs = VoronoiNodes(xs)
+        b = b if b is not None else Boundary()
+        opts = RaycastParameter(**(search_settings or {}))
+        self.searcher = Raycast(xs, domain=b, options=opts)
+        self.mesh, _ = voronoi(xs, searcher=self.searcher)
+        self.nodes = xs
+        self.domain = b
+
+
+class VoronoiData:
+    """VoronoiData(VG; getvertices, getneighbors) (voronoidata.jl:545-703), vertex / neighbour fields only."""
+
+    def __init__(self, VG, getvertices=False, getneighbors=False, **_ignored):
+        self.nodes = VG.nodes
+        m = VG.mesh
+        if getvertices:
+            self.vertices = [list(m.vertices_iterator(i)) for i in range(1, m.n + 1)]
+        if getneighbors:
+            off, ids = m.neighbors()
+            self.neighbors = [ids[off[i]:off[i + 1]] for i in range(m.n)]

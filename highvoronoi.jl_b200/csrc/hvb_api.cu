@@ -1,0 +1,655 @@
+// hvb_api.cu -- C ABI (include/hvb200.h) and host orchestration of the B200 raycast vertex search.
+//
+// One context = one GPU.  hvb_create uploads the generators and builds the uniform-grid index; hvb_search seeds
+// the frontier (descents), runs frontier rounds until no open edge is left, re-seeds cells that are still empty,
+// then finalizes (caller numbering, canonical coordinates, lexicographic order) and stages the result in
+// page-locked host memory.  There is no host compute path: if CUDA is unavailable every entry fails.
+#include <cuda_runtime.h>
+#include <cub/device/device_radix_sort.cuh>
+#include <cub/device/device_scan.cuh>
+
+#include <algorithm>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/hvb200.h"
+#include "hvb_host.hpp"
+#include "hvb_kernels.cuh"
+
+using namespace hvb;
+
+static std::string g_create_error;
+
+#define CK(call)                                                                                         \
+    do {                                                                                                 \
+        cudaError_t e_ = (call);                                                                         \
+        if (e_ != cudaSuccess) {                                                                         \
+            char buf_[512];                                                                              \
+            snprintf(buf_, sizeof(buf_), "%s failed at %s:%d: %s", #call, __FILE__, __LINE__, cudaGetErrorString(e_)); \
+            this->err = buf_;                                                                            \
+            return (e_ == cudaErrorMemoryAllocation) ? HVB_ENOMEM : HVB_ECUDA;                           \
+        }                                                                                                \
+    } while (0)
+
+template <class T>
+struct DBuf {
+    T* p = nullptr;
+    size_t cap = 0;
+    cudaError_t ensure(size_t n) {
+        if (n <= cap) return cudaSuccess;
+        if (p) cudaFree(p);
+        p = nullptr; cap = 0;
+        cudaError_t e = cudaMalloc((void**)&p, std::max<size_t>(n, 1) * sizeof(T));
+        if (e == cudaSuccess) cap = n;
+        return e;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+};
+template <class T>
+struct HBuf {   // page-locked host memory
+    T* p = nullptr;
+    size_t cap = 0;
+    cudaError_t ensure(size_t n) {
+        if (n <= cap) return cudaSuccess;
+        if (p) cudaFreeHost(p);
+        p = nullptr; cap = 0;
+        size_t want = std::max<size_t>(n + n / 4, 1);
+        cudaError_t e = cudaHostAlloc((void**)&p, want * sizeof(T), cudaHostAllocDefault);
+        if (e == cudaSuccess) cap = want;
+        return e;
+    }
+    void release() { if (p) cudaFreeHost(p); p = nullptr; cap = 0; }
+};
+
+struct Scalars {            // small device-side words, mirrored into pinned host memory after every round
+    u32 qcount[2];
+    u32 vcount;
+    u32 ray_count;
+    u32 unseeded;
+    u32 out_count;
+    u32 pflags;
+    u32 pad;
+    double max_var;
+};
+
+struct hvb_ctx {
+    int dim = 0; int64_t n = 0; int P = 0;
+    hvb_params prm;
+    std::string err;
+    hvb_stats_t st;
+    virtual ~hvb_ctx() {}
+    virtual int init(const double* xs, const double* pbase, const double* pnormal) = 0;
+    virtual int search(const int64_t* cells, int64_t ncells, const int64_t* seed_sig, const double* seed_r, int64_t nseed, int stride) = 0;
+    virtual int counts(int64_t* nv, int64_t* nr, int64_t* msl) = 0;
+    virtual int fetch_vertices(int64_t* sig, double* r) = 0;
+    virtual int view_vertices(const int64_t** sig, const double** r, int64_t* nv) = 0;
+    virtual int fetch_rays(int64_t* edge, double* base, double* dir, int64_t* node) = 0;
+    virtual int neighbor_count(int64_t* total) = 0;
+    virtual int fetch_neighbors(int64_t* off, int64_t* ids) = 0;
+    virtual int export_device(void* sig, void* r, int64_t cap, int64_t* count) = 0;
+    virtual int merge_device(const void* sig, const void* r, int64_t count) = 0;
+};
+
+template <int D>
+struct Ctx : hvb_ctx {
+    int G = (D == 2) ? 4 : (D == 3) ? 8 : (D == 4) ? 16 : 32;       // lanes per frontier entry (prm.tile_size overrides)
+    bool debug = false;
+    cudaStream_t stream = nullptr;
+    int sms = 148;
+    Dev<D> dv;
+    int64_t ncells = 0;
+    // index
+    DBuf<double> xs_in, x64;
+    DBuf<float> x32;
+    DBuf<int> perm, inv, cell_of, cell_start, cell_cur, unseeded_list;
+    DBuf<PlaneSet> planes;
+    DBuf<unsigned char> active, has_vertex;
+    DBuf<char> cub_tmp;
+    // search state
+    int64_t vcap = 0;
+    DBuf<int> vsig;
+    DBuf<double> vr;
+    DBuf<u64> vtab, etab;
+    DBuf<u32> q[2];
+    u32 qcap = 0;
+    DBuf<u32> ray_item;
+    DBuf<double> ray_u;
+    u32 ray_cap = 0;
+    DBuf<Counters> ctr;
+    DBuf<Scalars> sc;
+    HBuf<Scalars> h_sc;
+    HBuf<Counters> h_ctr;
+    DBuf<long long> cells_dev;
+    // results
+    DBuf<long long> out_sig[2];
+    DBuf<double> out_r[2];
+    DBuf<u64> key_hi, key_lo, key_tmp;
+    DBuf<u32> idx[2];
+    int res = 0;                     // which of out_sig/out_r holds the final rows
+    int64_t nvert = 0, nrays = 0;
+    DBuf<long long> ray_edge, ray_node;
+    DBuf<double> ray_base, ray_dir;
+    HBuf<long long> h_sig;
+    HBuf<double> h_r;
+    bool have_result = false, staged = false;
+    // neighbours
+    DBuf<u64> ptab;
+    DBuf<u32> deg, ncur;
+    DBuf<long long> nb_off, nb_ids;
+    int64_t nb_total = -1;
+    std::vector<cudaEvent_t> ev_pool;
+    cudaEvent_t ev_a = nullptr, ev_b = nullptr, ev_c = nullptr, ev_d = nullptr;
+    int64_t launches = 0;
+
+    ~Ctx() override {
+        cudaSetDevice(prm.device);
+        if (stream) cudaStreamSynchronize(stream);
+        xs_in.release(); x64.release(); x32.release(); perm.release(); inv.release(); cell_of.release(); cell_start.release();
+        cell_cur.release(); unseeded_list.release(); planes.release(); active.release(); has_vertex.release(); cub_tmp.release();
+        vsig.release(); vr.release(); vtab.release(); etab.release(); q[0].release(); q[1].release(); ray_item.release(); ray_u.release();
+        ctr.release(); sc.release(); h_sc.release(); h_ctr.release(); cells_dev.release();
+        out_sig[0].release(); out_sig[1].release(); out_r[0].release(); out_r[1].release(); key_hi.release(); key_lo.release(); key_tmp.release();
+        idx[0].release(); idx[1].release(); ray_edge.release(); ray_node.release(); ray_base.release(); ray_dir.release();
+        h_sig.release(); h_r.release(); ptab.release(); deg.release(); ncur.release(); nb_off.release(); nb_ids.release();
+        for (cudaEvent_t e : ev_pool) cudaEventDestroy(e);
+        if (ev_a) cudaEventDestroy(ev_a);
+        if (ev_b) cudaEventDestroy(ev_b);
+        if (ev_c) cudaEventDestroy(ev_c);
+        if (ev_d) cudaEventDestroy(ev_d);
+        if (stream) cudaStreamDestroy(stream);
+    }
+
+    static int blocks_for(int64_t items, int per_block) { return (int)std::max<int64_t>(1, (items + per_block - 1) / per_block); }
+
+    int init(const double* xs, const double* pbase, const double* pnormal) override {
+        memset(&dv, 0, sizeof(dv));
+        memset(&st, 0, sizeof(st));
+        CK(cudaSetDevice(prm.device));
+        cudaDeviceProp prop;
+        CK(cudaGetDeviceProperties(&prop, prm.device));
+        sms = prop.multiProcessorCount;
+        CK(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
+        CK(cudaEventCreate(&ev_a)); CK(cudaEventCreate(&ev_b)); CK(cudaEventCreate(&ev_c)); CK(cudaEventCreate(&ev_d));
+        CK(cudaEventRecord(ev_a, stream));
+        dv.n = (int)n;
+        // planes: unit outward normals, offsets
+        PlaneSet ps;
+        memset(&ps, 0, sizeof(ps));
+        ps.P = P;
+        for (int p = 0; p < P; ++p) {
+            double nr = 0;
+            for (int k = 0; k < D; ++k) nr += pnormal[p * D + k] * pnormal[p * D + k];
+            nr = sqrt(nr);
+            if (!(nr > 0)) { err = "boundary plane with zero normal"; return HVB_EINVAL; }
+            double off = 0;
+            for (int k = 0; k < D; ++k) { ps.normal[p * 6 + k] = pnormal[p * D + k] / nr; off += ps.normal[p * 6 + k] * pbase[p * D + k]; }
+            ps.off[p] = off;
+        }
+        // bounding box + domain check (check_boundary, boundary.jl:437)
+        double blo[D], bhi[D];
+        for (int k = 0; k < D; ++k) { blo[k] = 1e300; bhi[k] = -1e300; }
+        for (int64_t i = 0; i < n; ++i) {
+            const double* x = xs + i * D;
+            for (int k = 0; k < D; ++k) {
+                if (!(x[k] == x[k]) || fabs(x[k]) > 1e150) { err = "non-finite generator coordinate"; return HVB_EINVAL; }
+                blo[k] = std::min(blo[k], x[k]); bhi[k] = std::max(bhi[k], x[k]);
+            }
+            for (int p = 0; p < P; ++p) {
+                double s = 0;
+                for (int k = 0; k < D; ++k) s += ps.normal[p * 6 + k] * x[k];
+                if (s > ps.off[p]) {
+                    char b[160]; snprintf(b, sizeof(b), "generator %lld does not lie in the domain (plane %d)", (long long)(i + 1), p + 1);
+                    err = b; return HVB_EINVAL;
+                }
+            }
+        }
+        int ppc = prm.points_per_cell > 0 ? prm.points_per_cell : default_points_per_cell(D);
+        ncells = setup_grid<D>(dv, blo, bhi, n, ppc);
+        dv.plane_tol = prm.plane_tolerance;
+        dv.probe_scale = prm.probe_scale > 1.0 ? prm.probe_scale : 1.3;
+        dv.fp32_filter = prm.fp32_filter;
+        if (prm.tile_size == 4 || prm.tile_size == 8 || prm.tile_size == 16 || prm.tile_size == 32) G = prm.tile_size;
+        debug = getenv("HVB_DEBUG") != nullptr;
+        CK(xs_in.ensure((size_t)n * D)); CK(x64.ensure((size_t)n * D)); CK(x32.ensure((size_t)n * D));
+        CK(perm.ensure(n)); CK(inv.ensure(n)); CK(cell_of.ensure(n)); CK(unseeded_list.ensure(n));
+        CK(cell_start.ensure(ncells + 1)); CK(cell_cur.ensure(ncells + 1));
+        CK(planes.ensure(1)); CK(active.ensure(n)); CK(has_vertex.ensure(n));
+        CK(ctr.ensure(1)); CK(sc.ensure(1)); CK(h_sc.ensure(1)); CK(h_ctr.ensure(1));
+        CK(cudaMemcpyAsync(planes.p, &ps, sizeof(ps), cudaMemcpyHostToDevice, stream));
+        CK(cudaMemcpyAsync(xs_in.p, xs, (size_t)n * D * sizeof(double), cudaMemcpyHostToDevice, stream));
+        dv.cell_start = cell_start.p; dv.x32 = x32.p; dv.x64 = x64.p; dv.planes = planes.p; dv.active = active.p;
+        dv.has_vertex = has_vertex.p; dv.ctr = ctr.p;
+        // counting sort into cells
+        CK(cudaMemsetAsync(cell_cur.p, 0, (size_t)(ncells + 1) * sizeof(int), stream));
+        k_cell_count<D><<<blocks_for(n, 256), 256, 0, stream>>>(dv, xs_in.p, cell_of.p, cell_cur.p); ++launches;
+        size_t tmp_bytes = 0;
+        CK(cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, cell_cur.p, cell_start.p, (int)(ncells + 1), stream));
+        CK(cub_tmp.ensure(tmp_bytes));
+        CK(cub::DeviceScan::ExclusiveSum(cub_tmp.p, tmp_bytes, cell_cur.p, cell_start.p, (int)(ncells + 1), stream));
+        CK(cudaMemsetAsync(cell_cur.p, 0, (size_t)(ncells + 1) * sizeof(int), stream));
+        k_scatter<D><<<blocks_for(n, 256), 256, 0, stream>>>(dv, xs_in.p, cell_of.p, cell_start.p, cell_cur.p, x64.p, x32.p, perm.p); ++launches;
+        k_cell_sort<D><<<blocks_for(ncells, 256), 256, 0, stream>>>(dv, xs_in.p, cell_start.p, (int)ncells, x64.p, x32.p, perm.p); ++launches;
+        k_inverse_perm<<<blocks_for(n, 256), 256, 0, stream>>>(perm.p, inv.p, (int)n); ++launches;
+        CK(cudaEventRecord(ev_b, stream));
+        CK(cudaStreamSynchronize(stream));
+        CK(cudaGetLastError());
+        float ms = 0;
+        cudaEventElapsedTime(&ms, ev_a, ev_b);
+        st.ms_build = ms;
+        return HVB_OK;
+    }
+
+    template <int GG>
+    void launch_seed_g(const int* seeds, int nseeds, int stride, int cur) {
+        k_seed<D, GG><<<std::min(blocks_for((int64_t)nseeds * GG, 128), sms * 16), 128, 0, stream>>>(
+            dv, seeds, nseeds, stride, q[cur].p, &sc.p->qcount[cur], qcap);
+        ++launches;
+    }
+    void launch_seed(const int* seeds, int nseeds, int stride, int cur) {
+        switch (G) {
+            case 4: launch_seed_g<4>(seeds, nseeds, stride, cur); break;
+            case 8: launch_seed_g<8>(seeds, nseeds, stride, cur); break;
+            case 16: launch_seed_g<16>(seeds, nseeds, stride, cur); break;
+            default: launch_seed_g<32>(seeds, nseeds, stride, cur); break;
+        }
+    }
+    template <int GG>
+    void launch_expand_g(u32 cnt, int cur, int nxt) {
+        k_expand<D, GG><<<std::min(blocks_for((int64_t)cnt * GG, 128), sms * 16), 128, 0, stream>>>(
+            dv, q[cur].p, &sc.p->qcount[cur], q[nxt].p, &sc.p->qcount[nxt], qcap);
+    }
+    void launch_expand(u32 cnt, int cur, int nxt) {
+        switch (G) {
+            case 4: launch_expand_g<4>(cnt, cur, nxt); break;
+            case 8: launch_expand_g<8>(cnt, cur, nxt); break;
+            case 16: launch_expand_g<16>(cnt, cur, nxt); break;
+            default: launch_expand_g<32>(cnt, cur, nxt); break;
+        }
+    }
+
+    int alloc_tables(int64_t cap) {
+        if (cap > 0x7ffffff0LL) { err = "vertex capacity beyond 2^31"; return HVB_ENOMEM; }
+        vcap = cap;
+        CK(vsig.ensure((size_t)cap * (D + 1))); CK(vr.ensure((size_t)cap * D));
+        u64 vts = next_pow2((u64)cap * 2);
+        u64 ecap = (u64)cap * (D + 1) / 2 + 1024;
+        u64 ets = next_pow2(ecap * 2);
+        if (ets > (1ULL << 32)) ets = 1ULL << 32;
+        CK(vtab.ensure(vts)); CK(etab.ensure(ets));
+        dv.vmask = vts - 1; dv.emask = ets - 1;
+        qcap = (u32)std::min<u64>(ecap, 0xfffffff0ULL);
+        CK(q[0].ensure(qcap)); CK(q[1].ensure(qcap));
+        ray_cap = (u32)((P > 0) ? std::max<int64_t>(4096, cap / 16) : cap);
+        CK(ray_item.ensure(ray_cap)); CK(ray_u.ensure((size_t)ray_cap * D));
+        dv.vsig = vsig.p; dv.vr = vr.p; dv.vcap = (u32)cap; dv.vtab = vtab.p; dv.etab = etab.p;
+        dv.ray_item = ray_item.p; dv.ray_u = ray_u.p; dv.ray_cap = ray_cap;
+        dv.vcount = &sc.p->vcount; dv.ray_count = &sc.p->ray_count;
+        return HVB_OK;
+    }
+
+    int read_scalars() {
+        CK(cudaMemcpyAsync(h_sc.p, sc.p, sizeof(Scalars), cudaMemcpyDeviceToHost, stream));
+        CK(cudaMemcpyAsync(h_ctr.p, ctr.p, sizeof(Counters), cudaMemcpyDeviceToHost, stream));
+        CK(cudaStreamSynchronize(stream));
+        return HVB_OK;
+    }
+
+    cudaEvent_t pool_event(size_t i) {
+        while (ev_pool.size() <= i) { cudaEvent_t e; cudaEventCreate(&e); ev_pool.push_back(e); }
+        return ev_pool[i];
+    }
+
+    int search(const int64_t* cells, int64_t ncells_in, const int64_t* seed_sig, const double* seed_r, int64_t nseed, int stride) override {
+        (void)seed_sig; (void)seed_r; (void)stride;
+        if (nseed > 0) { err = "pre-existing vertices (nseed > 0) are not supported yet"; return HVB_EINVAL; }
+        CK(cudaSetDevice(prm.device));
+        have_result = false; staged = false; nb_total = -1;
+        int64_t cap = prm.vertex_capacity > 0 ? prm.vertex_capacity : estimate_vertices(D, n, P);
+        if (vcap >= cap) cap = vcap;
+        int retries = 0;
+        const int world = std::max(1, prm.world), rank = std::min(std::max(0, prm.rank), world - 1);
+        launches = 0;
+        size_t n_ev = 0;
+        int64_t rounds = 0, items = 0, expand_launches = 0;
+        CK(cudaEventRecord(ev_a, stream));
+        for (;;) {
+            if (cap != vcap || !vsig.p) { int rc = alloc_tables(cap); if (rc) return rc; }
+            CK(cudaMemsetAsync(vtab.p, 0, (dv.vmask + 1) * sizeof(u64), stream));
+            CK(cudaMemsetAsync(etab.p, 0, (dv.emask + 1) * sizeof(u64), stream));
+            CK(cudaMemsetAsync(has_vertex.p, 0, n, stream));
+            CK(cudaMemsetAsync(ctr.p, 0, sizeof(Counters), stream));
+            CK(cudaMemsetAsync(sc.p, 0, sizeof(Scalars), stream));
+            if (cells == nullptr) {
+                int lo = (int)(n * rank / world), hi = (int)(n * (rank + 1) / world);
+                k_fill_active_range<<<blocks_for(n, 256), 256, 0, stream>>>(active.p, (int)n, lo, hi); ++launches;
+            } else {
+                CK(cells_dev.ensure(ncells_in));
+                CK(cudaMemcpyAsync(cells_dev.p, cells, ncells_in * sizeof(long long), cudaMemcpyHostToDevice, stream));
+                CK(cudaMemsetAsync(active.p, 0, n, stream));
+                k_mark_cells<<<blocks_for(ncells_in, 256), 256, 0, stream>>>(cells_dev.p, ncells_in, inv.p, active.p, (int)n); ++launches;
+            }
+            // seeds: one descent every `stride` generators of the sorted order
+            int sstride = prm.seed_stride;
+            if (sstride <= 0) {
+                int64_t want = std::min<int64_t>(std::max<int64_t>(n / 16, 2048), 65536);
+                sstride = (int)std::max<int64_t>(1, n / want);
+            }
+            int nseeds = (int)((n + sstride - 1) / sstride);
+            int cur = 0;
+            launch_seed(nullptr, nseeds, sstride, cur);
+            if (debug) fprintf(stderr, "[hvb] seeds=%d stride=%d G=%d vcap=%lld ncells=%lld\n", nseeds, sstride, G, (long long)vcap, (long long)ncells);
+            bool overflow = false;
+            u32 last_uns = 0xffffffffu, last_vcount = 0;
+            for (;;) {
+                int rc = read_scalars(); if (rc) return rc;
+                if (h_sc.p->pflags || h_ctr.p->flags) { overflow = true; break; }
+                u32 cnt = h_sc.p->qcount[cur];
+                if (cnt > 0) {
+                    int nxt = 1 - cur;
+                    CK(cudaMemsetAsync(&sc.p->qcount[nxt], 0, sizeof(u32), stream));
+                    cudaEvent_t e0 = pool_event(n_ev++), e1 = pool_event(n_ev++);
+                    CK(cudaEventRecord(e0, stream));
+                    if (debug) fprintf(stderr, "[hvb] round %lld frontier=%u vertices=%u\n", (long long)rounds, cnt, h_sc.p->vcount);
+                    launch_expand(cnt, cur, nxt);
+                    CK(cudaEventRecord(e1, stream));
+                    ++launches; ++expand_launches; ++rounds; items += cnt;
+                    cur = nxt;
+                    continue;
+                }
+                // frontier drained: cells of this context without a vertex get their own descent
+                CK(cudaMemsetAsync(&sc.p->unseeded, 0, sizeof(u32), stream));
+                k_unseeded<D><<<blocks_for(n, 256), 256, 0, stream>>>(dv, unseeded_list.p, &sc.p->unseeded); ++launches;
+                rc = read_scalars(); if (rc) return rc;
+                u32 uns = h_sc.p->unseeded;
+                if (uns == 0) break;
+                if (uns == last_uns && h_sc.p->vcount == last_vcount) break;   // descents keep failing: give up (HVB_EINCOMPLETE)
+                last_uns = uns; last_vcount = h_sc.p->vcount;
+                CK(cudaMemsetAsync(&sc.p->qcount[cur], 0, sizeof(u32), stream));
+                if (debug) fprintf(stderr, "[hvb] reseeding %u empty cells\n", uns);
+                launch_seed(unseeded_list.p, (int)uns, 1, cur);
+                ++rounds;
+                if (rounds > 100000) { err = "search does not terminate"; return HVB_EINCOMPLETE; }
+            }
+            if (!overflow) break;
+            if (++retries > 6) { err = "capacity exhausted after 6 retries"; return HVB_ENOMEM; }
+            cap = vcap * 2;
+        }
+        CK(cudaEventRecord(ev_b, stream));
+        int rc = finalize(); if (rc) return rc;
+        CK(cudaEventRecord(ev_c, stream));
+        rc = stage(); if (rc) return rc;
+        CK(cudaEventRecord(ev_d, stream));
+        CK(cudaStreamSynchronize(stream));
+        CK(cudaGetLastError());
+        float ms = 0;
+        cudaEventElapsedTime(&ms, ev_a, ev_b); st.ms_search = ms;
+        cudaEventElapsedTime(&ms, ev_b, ev_d); st.ms_finalize = ms;
+        double kms = 0;
+        for (size_t i = 0; i + 1 < n_ev; i += 2) { cudaEventElapsedTime(&ms, ev_pool[i], ev_pool[i + 1]); kms += ms; }
+        st.ms_expand_kernel = kms; st.expand_launches = expand_launches; st.expand_items = items;
+        const Counters& c = *h_ctr.p;
+        st.vertices = nvert; st.rays = nrays; st.raycasts = (int64_t)c.raycasts; st.duplicate_hits = (int64_t)c.dup_hits;
+        st.closed_skips = (int64_t)c.closed_skips; st.candidates_fp32 = (int64_t)c.cand32; st.candidates_fp64 = (int64_t)c.cand64;
+        st.rows_scanned = (int64_t)c.rows; st.probe_stages = (int64_t)c.stages; st.rounds = rounds; st.seeds = (int64_t)c.seeds;
+        st.degenerate = (int64_t)c.degenerate; st.kernel_launches = launches; st.capacity_retries = retries;
+        have_result = true;
+        if (c.seed_fail > 0 && h_sc.p->unseeded > 0) { err = "descent failed for some cells"; return HVB_EINCOMPLETE; }
+        if (c.degenerate > 0 && !prm.on_degenerate) {
+            err = "non-general position: a vertex with more than dim+1 cospherical generators was met"; return HVB_EDEGENERATE;
+        }
+        return HVB_OK;
+    }
+
+    int id_bits() const { int b = 1; while ((1LL << b) < n + P + 1) ++b; return b; }
+
+    // sorts `count` rows held in out_sig[0]/out_r[0] (keys in key_hi/key_lo) into out_sig[1]/out_r[1]
+    int sort_rows(u32 count, int bits) {
+        res = 0;
+        if (!prm.sort_output || count == 0) return HVB_OK;
+        if ((D + 1) * bits > 128) return HVB_OK;            // keys do not fit 128 bits: leave unsorted
+        CK(idx[0].ensure(count)); CK(idx[1].ensure(count)); CK(key_tmp.ensure(count));
+        k_iota<<<blocks_for(count, 256), 256, 0, stream>>>(idx[0].p, count); ++launches;
+        size_t tmp_bytes = 0;
+        int lo_bits = std::min(64, (D + 1) * bits), hi_bits = (D + 1) * bits - lo_bits;
+        CK(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, key_lo.p, key_tmp.p, idx[0].p, idx[1].p, (int)count, 0, lo_bits, stream));
+        CK(cub_tmp.ensure(tmp_bytes));
+        CK(cub::DeviceRadixSort::SortPairs(cub_tmp.p, tmp_bytes, key_lo.p, key_tmp.p, idx[0].p, idx[1].p, (int)count, 0, lo_bits, stream));
+        int fin = 1;
+        if (hi_bits > 0) {
+            k_gather_u64<<<blocks_for(count, 256), 256, 0, stream>>>(key_hi.p, idx[1].p, key_lo.p, count); ++launches;
+            CK(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, key_lo.p, key_tmp.p, idx[1].p, idx[0].p, (int)count, 0, hi_bits, stream));
+            CK(cub_tmp.ensure(tmp_bytes));
+            CK(cub::DeviceRadixSort::SortPairs(cub_tmp.p, tmp_bytes, key_lo.p, key_tmp.p, idx[1].p, idx[0].p, (int)count, 0, hi_bits, stream));
+            fin = 0;
+        }
+        k_gather_rows<D><<<blocks_for(count, 256), 256, 0, stream>>>(out_sig[0].p, out_r[0].p, idx[fin].p, out_sig[1].p, out_r[1].p, count); ++launches;
+        res = 1;
+        return HVB_OK;
+    }
+
+    int finalize() {
+        u32 nrec = std::min<u32>(h_sc.p->vcount, (u32)vcap);
+        nrays = std::min<u32>(h_sc.p->ray_count, ray_cap);
+        for (int i = 0; i < 2; ++i) { CK(out_sig[i].ensure((size_t)std::max<u32>(nrec, 1) * (D + 1))); CK(out_r[i].ensure((size_t)std::max<u32>(nrec, 1) * D)); }
+        CK(key_hi.ensure(std::max<u32>(nrec, 1))); CK(key_lo.ensure(std::max<u32>(nrec, 1)));
+        int bits = id_bits();
+        if (nrec > 0) {
+            k_final_rows<D><<<blocks_for(nrec, 128), 128, 0, stream>>>(dv, perm.p, nrec, bits, out_sig[0].p, out_r[0].p, key_hi.p, key_lo.p,
+                                                                     &sc.p->out_count, &sc.p->max_var);
+            ++launches;
+        }
+        if (nrays > 0) {
+            CK(ray_edge.ensure((size_t)nrays * D)); CK(ray_base.ensure((size_t)nrays * D)); CK(ray_dir.ensure((size_t)nrays * D)); CK(ray_node.ensure(nrays));
+            k_final_rays<D><<<blocks_for(nrays, 128), 128, 0, stream>>>(dv, perm.p, (u32)nrays, ray_edge.p, ray_base.p, ray_dir.p, ray_node.p);
+            ++launches;
+        }
+        int rc = read_scalars(); if (rc) return rc;
+        nvert = h_sc.p->out_count;
+        return sort_rows((u32)nvert, bits);
+    }
+
+    // device -> page-locked host staging (asynchronous; the fetch calls wait for it)
+    int stage() {
+        CK(h_sig.ensure((size_t)std::max<int64_t>(nvert, 1) * (D + 1))); CK(h_r.ensure((size_t)std::max<int64_t>(nvert, 1) * D));
+        if (nvert > 0) {
+            CK(cudaMemcpyAsync(h_sig.p, out_sig[res].p, (size_t)nvert * (D + 1) * sizeof(long long), cudaMemcpyDeviceToHost, stream));
+            CK(cudaMemcpyAsync(h_r.p, out_r[res].p, (size_t)nvert * D * sizeof(double), cudaMemcpyDeviceToHost, stream));
+        }
+        staged = true;
+        return HVB_OK;
+    }
+
+    int counts(int64_t* nv, int64_t* nr, int64_t* msl) override {
+        if (!have_result) { err = "no search result"; return HVB_ESTATE; }
+        if (nv) *nv = nvert;
+        if (nr) *nr = nrays;
+        if (msl) *msl = D + 1;
+        return HVB_OK;
+    }
+    int view_vertices(const int64_t** sig, const double** r, int64_t* nv) override {
+        if (!have_result) { err = "no search result"; return HVB_ESTATE; }
+        CK(cudaSetDevice(prm.device));
+        if (!staged) { int rc = stage(); if (rc) return rc; }
+        CK(cudaStreamSynchronize(stream));
+        *sig = (const int64_t*)h_sig.p; *r = h_r.p; *nv = nvert;
+        return HVB_OK;
+    }
+    int fetch_vertices(int64_t* sig, double* r) override {
+        const int64_t* s; const double* rr; int64_t nv;
+        int rc = view_vertices(&s, &rr, &nv); if (rc) return rc;
+        if (sig) memcpy(sig, s, (size_t)nv * (D + 1) * sizeof(int64_t));
+        if (r) memcpy(r, rr, (size_t)nv * D * sizeof(double));
+        return HVB_OK;
+    }
+    int fetch_rays(int64_t* edge, double* base, double* dir, int64_t* node) override {
+        if (!have_result) { err = "no search result"; return HVB_ESTATE; }
+        CK(cudaSetDevice(prm.device));
+        if (nrays == 0) return HVB_OK;
+        if (edge) CK(cudaMemcpyAsync(edge, ray_edge.p, (size_t)nrays * D * 8, cudaMemcpyDeviceToHost, stream));
+        if (base) CK(cudaMemcpyAsync(base, ray_base.p, (size_t)nrays * D * 8, cudaMemcpyDeviceToHost, stream));
+        if (dir) CK(cudaMemcpyAsync(dir, ray_dir.p, (size_t)nrays * D * 8, cudaMemcpyDeviceToHost, stream));
+        if (node) CK(cudaMemcpyAsync(node, ray_node.p, (size_t)nrays * 8, cudaMemcpyDeviceToHost, stream));
+        CK(cudaStreamSynchronize(stream));
+        return HVB_OK;
+    }
+
+    int build_neighbors() {
+        if (nb_total >= 0) return HVB_OK;
+        CK(cudaSetDevice(prm.device));
+        CK(deg.ensure(n)); CK(ncur.ensure(n)); CK(nb_off.ensure(n + 1));
+        static const double nb_est[7] = {0, 0, 8, 20, 48, 120, 320};
+        u64 want = next_pow2((u64)(std::min((double)nvert * D * (D + 1) / 2.0, (double)n * nb_est[D]) * 2.0) + 1024);
+        for (int attempt = 0; attempt < 8; ++attempt) {
+            CK(ptab.ensure(want));
+            CK(cudaMemsetAsync(ptab.p, 0, want * sizeof(u64), stream));
+            CK(cudaMemsetAsync(deg.p, 0, n * sizeof(u32), stream));
+            CK(cudaMemsetAsync(&sc.p->pflags, 0, sizeof(u32), stream));
+            if (nvert > 0) { k_pairs<D><<<blocks_for(nvert, 128), 128, 0, stream>>>(out_sig[res].p, (u32)nvert, n, ptab.p, want - 1, deg.p, &sc.p->pflags); ++launches; }
+            int rc = read_scalars(); if (rc) return rc;
+            if (!(h_sc.p->pflags & 8u)) break;
+            want *= 4;
+            if (attempt == 7) { err = "neighbour pair table overflow"; return HVB_ENOMEM; }
+        }
+        // offsets = exclusive scan of the degrees (as int64)
+        k_u32_to_i64<<<blocks_for(n, 256), 256, 0, stream>>>(deg.p, nb_off.p, n); ++launches;
+        CK(cudaMemsetAsync(nb_off.p + n, 0, sizeof(long long), stream));
+        size_t tmp_bytes = 0;
+        CK(cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, nb_off.p, nb_off.p, (int)(n + 1), stream));
+        CK(cub_tmp.ensure(tmp_bytes));
+        CK(cub::DeviceScan::ExclusiveSum(cub_tmp.p, tmp_bytes, nb_off.p, nb_off.p, (int)(n + 1), stream));
+        long long total = 0;
+        CK(cudaMemcpyAsync(&total, nb_off.p + n, sizeof(long long), cudaMemcpyDeviceToHost, stream));
+        CK(cudaStreamSynchronize(stream));
+        CK(nb_ids.ensure(std::max<long long>(total, 1)));
+        CK(cudaMemsetAsync(ncur.p, 0, n * sizeof(u32), stream));
+        k_pair_fill<<<blocks_for((int64_t)want, 256), 256, 0, stream>>>(ptab.p, want, n, nb_off.p, ncur.p, nb_ids.p); ++launches;
+        k_sort_lists<<<blocks_for(n, 128), 128, 0, stream>>>(nb_off.p, nb_ids.p, n); ++launches;
+        CK(cudaStreamSynchronize(stream));
+        CK(cudaGetLastError());
+        nb_total = total;
+        st.kernel_launches = launches;
+        return HVB_OK;
+    }
+    int neighbor_count(int64_t* total) override {
+        if (!have_result) { err = "no search result"; return HVB_ESTATE; }
+        int rc = build_neighbors(); if (rc) return rc;
+        *total = nb_total;
+        return HVB_OK;
+    }
+    int fetch_neighbors(int64_t* off, int64_t* ids) override {
+        if (!have_result) { err = "no search result"; return HVB_ESTATE; }
+        int rc = build_neighbors(); if (rc) return rc;
+        if (off) CK(cudaMemcpyAsync(off, nb_off.p, (size_t)(n + 1) * 8, cudaMemcpyDeviceToHost, stream));
+        if (ids && nb_total > 0) CK(cudaMemcpyAsync(ids, nb_ids.p, (size_t)nb_total * 8, cudaMemcpyDeviceToHost, stream));
+        CK(cudaStreamSynchronize(stream));
+        return HVB_OK;
+    }
+
+    int export_device(void* sig, void* r, int64_t cap, int64_t* count) override {
+        if (!have_result) { err = "no search result"; return HVB_ESTATE; }
+        CK(cudaSetDevice(prm.device));
+        if (count) *count = nvert;
+        if (cap < nvert) { err = "export buffer too small"; return HVB_EINVAL; }
+        if (nvert > 0) {
+            CK(cudaMemcpyAsync(sig, out_sig[res].p, (size_t)nvert * (D + 1) * 8, cudaMemcpyDeviceToDevice, stream));
+            CK(cudaMemcpyAsync(r, out_r[res].p, (size_t)nvert * D * 8, cudaMemcpyDeviceToDevice, stream));
+        }
+        CK(cudaStreamSynchronize(stream));
+        return HVB_OK;
+    }
+    int merge_device(const void* sig, const void* r, int64_t count) override {
+        CK(cudaSetDevice(prm.device));
+        for (int i = 0; i < 2; ++i) { CK(out_sig[i].ensure((size_t)std::max<int64_t>(count, 1) * (D + 1))); CK(out_r[i].ensure((size_t)std::max<int64_t>(count, 1) * D)); }
+        CK(key_hi.ensure(std::max<int64_t>(count, 1))); CK(key_lo.ensure(std::max<int64_t>(count, 1)));
+        u64 ts = next_pow2((u64)count * 2 + 16);
+        CK(ptab.ensure(ts));
+        CK(cudaMemsetAsync(ptab.p, 0, ts * sizeof(u64), stream));
+        CK(cudaMemsetAsync(&sc.p->out_count, 0, sizeof(u32), stream));
+        int bits = id_bits();
+        if (count > 0) {
+            k_merge_rows<D><<<blocks_for(count, 128), 128, 0, stream>>>((const long long*)sig, (const double*)r, (u64)count, bits, ptab.p, ts - 1,
+                                                                      out_sig[0].p, out_r[0].p, key_hi.p, key_lo.p, &sc.p->out_count);
+            ++launches;
+        }
+        int rc = read_scalars(); if (rc) return rc;
+        nvert = h_sc.p->out_count;
+        rc = sort_rows((u32)nvert, bits); if (rc) return rc;
+        nb_total = -1;
+        rc = stage(); if (rc) return rc;
+        CK(cudaStreamSynchronize(stream));
+        CK(cudaGetLastError());
+        st.vertices = nvert; st.kernel_launches = launches;
+        have_result = true;
+        return HVB_OK;
+    }
+};
+
+// ------------------------------------------------------------------------------------------------------------
+// C ABI
+// ------------------------------------------------------------------------------------------------------------
+extern "C" {
+
+void hvb_default_params(hvb_params* p) {
+    memset(p, 0, sizeof(*p));
+    p->variance_tol = 1e-15; p->break_tol = 1e-5; p->b_nodes_tol = 1e-7; p->plane_tolerance = 1e-12; p->ray_tol = 1e-12;
+    p->method = 0; p->device = 0; p->rank = 0; p->world = 1; p->fp32_filter = 1; p->on_degenerate = 0;
+    p->points_per_cell = 0; p->seed_stride = 0; p->sort_output = 1; p->vertex_capacity = 0; p->probe_scale = 0.0;
+}
+
+int hvb_create(hvb_ctx** out, int dim, int64_t n, const double* xs, int nplanes, const double* plane_base,
+               const double* plane_normal, const hvb_params* params) {
+    if (!out) return HVB_EINVAL;
+    *out = nullptr;
+    hvb_params prm;
+    if (params) prm = *params; else hvb_default_params(&prm);
+    if (dim < 2 || dim > HVB_MAX_DIM) { g_create_error = "dimension must be 2..6"; return HVB_EINVAL; }
+    if (n <= dim || !xs) { g_create_error = "There are not enough points to create a Voronoi tessellation"; return HVB_EINVAL; }   // sysvoronoi.jl:25-27
+    if (n > 0x7ff00000LL) { g_create_error = "too many generators"; return HVB_EINVAL; }
+    if (nplanes < 0 || nplanes > HVB_MAX_PLANES || (nplanes > 0 && (!plane_base || !plane_normal))) { g_create_error = "bad boundary planes"; return HVB_EINVAL; }
+    int ndev = 0;
+    cudaError_t ce = cudaGetDeviceCount(&ndev);
+    if (ce != cudaSuccess || ndev == 0) {
+        g_create_error = std::string("no CUDA device available (") + cudaGetErrorString(ce) + "); libhvb200 has no host fallback";
+        return HVB_ENOGPU;
+    }
+    if (prm.device < 0 || prm.device >= ndev) { g_create_error = "bad device ordinal"; return HVB_EINVAL; }
+    hvb_ctx* c = nullptr;
+    switch (dim) {
+        case 2: c = new Ctx<2>(); break;
+        case 3: c = new Ctx<3>(); break;
+        case 4: c = new Ctx<4>(); break;
+        case 5: c = new Ctx<5>(); break;
+        case 6: c = new Ctx<6>(); break;
+    }
+    c->dim = dim; c->n = n; c->P = nplanes; c->prm = prm;
+    int rc = c->init(xs, plane_base, plane_normal);
+    if (rc != HVB_OK) { g_create_error = c->err; delete c; return rc; }
+    *out = c;
+    return HVB_OK;
+}
+
+int hvb_search(hvb_ctx* ctx, const int64_t* cells, int64_t ncells, const int64_t* seed_sig, const double* seed_r, int64_t nseed, int sig_stride) {
+    if (!ctx) return HVB_EINVAL;
+    return ctx->search(cells, ncells, seed_sig, seed_r, nseed, sig_stride);
+}
+int hvb_counts(hvb_ctx* ctx, int64_t* nvert, int64_t* nrays, int64_t* max_siglen) { return ctx ? ctx->counts(nvert, nrays, max_siglen) : HVB_EINVAL; }
+int hvb_fetch_vertices(hvb_ctx* ctx, int64_t* sig, double* r) { return ctx ? ctx->fetch_vertices(sig, r) : HVB_EINVAL; }
+int hvb_view_vertices(hvb_ctx* ctx, const int64_t** sig, const double** r, int64_t* nvert) { return (ctx && sig && r && nvert) ? ctx->view_vertices(sig, r, nvert) : HVB_EINVAL; }
+int hvb_fetch_rays(hvb_ctx* ctx, int64_t* edge, double* base, double* dir, int64_t* node) { return ctx ? ctx->fetch_rays(edge, base, dir, node) : HVB_EINVAL; }
+int hvb_neighbor_count(hvb_ctx* ctx, int64_t* total) { return (ctx && total) ? ctx->neighbor_count(total) : HVB_EINVAL; }
+int hvb_fetch_neighbors(hvb_ctx* ctx, int64_t* offsets, int64_t* ids) { return ctx ? ctx->fetch_neighbors(offsets, ids) : HVB_EINVAL; }
+int hvb_export_device(hvb_ctx* ctx, void* sig_dev, void* r_dev, int64_t cap, int64_t* count) { return ctx ? ctx->export_device(sig_dev, r_dev, cap, count) : HVB_EINVAL; }
+int hvb_merge_device(hvb_ctx* ctx, const void* sig_dev, const void* r_dev, int64_t count) { return ctx ? ctx->merge_device(sig_dev, r_dev, count) : HVB_EINVAL; }
+int hvb_stats(hvb_ctx* ctx, hvb_stats_t* out) {
+    if (!ctx || !out) return HVB_EINVAL;
+    *out = ctx->st;
+    return HVB_OK;
+}
+const char* hvb_last_error(hvb_ctx* ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
+void hvb_destroy(hvb_ctx* ctx) { delete ctx; }
+const char* hvb_version(void) { return "hvb200 0.1.0 sm_100a"; }
+
+}  // extern "C"

@@ -1,0 +1,976 @@
+// hvb_core.cuh -- the raycast vertex search, written once for the device (sm_100a) and, for debugging in a
+// container without a GPU, compilable as plain host C++ (tests/hostsim).  Nothing here is a port of the Julia
+// code: the reference's cell-ordered, pointer-chasing walk (sysvoronoi.jl:384-525) is re-designed as an
+// edge frontier whose entries are solved by a tile of G cooperating lanes.
+//
+//   reference                                        here
+//   ---------------------------------------------    ---------------------------------------------------------
+//   u_qr (tools.jl:773-790)                          ortho_direction(): MGS2 in registers, sign by construction
+//   raycast_des2(::HPUnion) (raycast.jl:794-970)     min_t_query(): staged probe balls over a uniform grid,
+//     = 2.6 KD nn + 1 inrange                          FP32 filter with an explicit error bound + FP64 verify
+//   mirrors via ExtendedNodes (extended.jl,          analytic plane candidates t = (off - n.r)/(n.u), id N+p
+//     raycast.jl:354-375)
+//   EdgeHashTable per cell (edgehashing.jl:66-111)   one global edge table (64-bit slots, CAS), closed bit
+//   HeapDataBase + QueueHashTable (hvdatabase.jl)    vertex set: 64-bit slots {fingerprint, index} + SoA records
+//   descent (raycast.jl:45-109)                      seed_item(): d successive min-t queries
+#pragma once
+#include <stdint.h>
+#include <math.h>
+#include <float.h>
+
+#if defined(__CUDACC__)
+#define HVB_HD __host__ __device__ __forceinline__
+#define HVB_D __device__ __forceinline__
+#else
+#define HVB_HD inline
+#define HVB_D inline
+#endif
+
+#ifndef HVB_MAX_PLANES
+#define HVB_MAX_PLANES 32
+#endif
+
+namespace hvb {
+
+typedef unsigned long long u64;
+typedef unsigned int u32;
+
+// ------------------------------------------------------------------------------------------------------------
+// memory helpers: every structure that is written during a launch is read with ld.global.cg (L1 is not coherent)
+// ------------------------------------------------------------------------------------------------------------
+HVB_HD u64 ld_cg(const u64* p) {
+#if defined(__CUDA_ARCH__)
+    return __ldcg(p);
+#else
+    return *p;
+#endif
+}
+HVB_HD int ld_cg(const int* p) {
+#if defined(__CUDA_ARCH__)
+    return __ldcg(p);
+#else
+    return *p;
+#endif
+}
+HVB_HD double ld_cg(const double* p) {
+#if defined(__CUDA_ARCH__)
+    return __ldcg(p);
+#else
+    return *p;
+#endif
+}
+HVB_HD u64 atom_cas(u64* p, u64 cmp, u64 val) {
+#if defined(__CUDA_ARCH__)
+    return atomicCAS(p, cmp, val);
+#else
+    u64 old = *p; if (old == cmp) *p = val; return old;
+#endif
+}
+HVB_HD u32 atom_add(u32* p, u32 v) {
+#if defined(__CUDA_ARCH__)
+    return atomicAdd(p, v);
+#else
+    u32 old = *p; *p += v; return old;
+#endif
+}
+HVB_HD void atom_or(u64* p, u64 v) {
+#if defined(__CUDA_ARCH__)
+    atomicOr(p, v);
+#else
+    *p |= v;
+#endif
+}
+HVB_HD void atom_or(u32* p, u32 v) {
+#if defined(__CUDA_ARCH__)
+    atomicOr(p, v);
+#else
+    *p |= v;
+#endif
+}
+HVB_HD void mem_fence() {
+#if defined(__CUDA_ARCH__)
+    __threadfence();
+#endif
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// tiles: G lanes that solve one frontier entry together.  TileHost (G = 1) is the debugging stand-in.
+// ------------------------------------------------------------------------------------------------------------
+struct TileHost {
+    static const int SIZE = 1;
+    HVB_HD int lane() const { return 0; }
+    HVB_HD double shfl_xor(double v, int) const { return v; }
+    HVB_HD int shfl_xor(int v, int) const { return v; }
+    HVB_HD int shfl(int v, int) const { return v; }
+    HVB_HD u32 shfl(u32 v, int) const { return v; }
+    HVB_HD u64 shfl(u64 v, int) const { return v; }
+    HVB_HD u32 ballot(bool p) const { return p ? 1u : 0u; }
+    HVB_HD void sync() const {}
+};
+#if defined(__CUDACC__)
+template <int G>
+struct TileDev {
+    static const int SIZE = G;
+    unsigned mask;
+    int ln;
+    __device__ __forceinline__ TileDev() {
+        int wl = threadIdx.x & 31;
+        ln = wl & (G - 1);
+        mask = (G == 32) ? 0xffffffffu : (((1u << G) - 1u) << (wl & ~(G - 1)));
+    }
+    __device__ __forceinline__ int lane() const { return ln; }
+    __device__ __forceinline__ double shfl_xor(double v, int m) const { return __shfl_xor_sync(mask, v, m, G); }
+    __device__ __forceinline__ int shfl_xor(int v, int m) const { return __shfl_xor_sync(mask, v, m, G); }
+    __device__ __forceinline__ int shfl(int v, int src) const { return __shfl_sync(mask, v, src, G); }
+    __device__ __forceinline__ u32 shfl(u32 v, int src) const { return __shfl_sync(mask, v, src, G); }
+    __device__ __forceinline__ u64 shfl(u64 v, int src) const { return __shfl_sync(mask, v, src, G); }
+    // reconverges the lanes of this tile (they may still be split after lane-dependent work)
+    __device__ __forceinline__ void sync() const { __syncwarp(mask); }
+    // ballot restricted to this tile, bit i = lane i of the tile
+    __device__ __forceinline__ u32 ballot(bool p) const {
+        u32 b = __ballot_sync(mask, p);
+        return (G == 32) ? b : ((b & mask) >> ((threadIdx.x & 31) & ~(G - 1)));
+    }
+};
+#endif
+
+// ------------------------------------------------------------------------------------------------------------
+// device-resident problem description
+// ------------------------------------------------------------------------------------------------------------
+struct PlaneSet {                      // boundary.jl:22-29 : outward unit normal n, offset = n.base ; inside: n.y <= off
+    int P;
+    int pad;
+    double normal[HVB_MAX_PLANES * 6];
+    double off[HVB_MAX_PLANES];
+};
+
+struct Counters {
+    u64 raycasts, dup_hits, closed_skips, cand32, cand64, rows, stages, seeds, degenerate, seed_fail, dead;
+    u32 flags;                         // bit0 vertex store full, bit1 frontier full, bit2 ray list full
+    u32 pad;
+};
+enum { FLAG_VFULL = 1, FLAG_QFULL = 2, FLAG_RFULL = 4 };
+
+template <int D>
+struct Dev {
+    // ---- read-only during the search -----------------------------------------------------------------
+    int n;                             // generators
+    double lo[D], h[D], inv_h[D];      // uniform grid: origin, cell size, 1/cell size
+    int g[D];                          // cells per axis (linear index: axis D-1 fastest)
+    double hmin, diag;                 // smallest cell edge, diagonal of the bounding box
+    double ext;                        // largest bounding-box extent: scale of the FP32 coordinate error
+    const int* cell_start;             // [ncells + 1]
+    const float* x32;                  // [n][D]  coordinates minus lo, FP32 (filter)
+    const double* x64;                 // [n][D]  coordinates, FP64 (verification)
+    const PlaneSet* planes;
+    const unsigned char* active;       // [n] 1 = this context walks the edges of that cell (slab / Iter)
+    double plane_tol;                  // raycast-types.jl:229
+    double probe_scale;
+    int fp32_filter;
+    // ---- written during the search -------------------------------------------------------------------
+    int* vsig;                         // [vcap][D+1] sorted internal ids; vsig[v][0] = -1 marks a dead record
+    double* vr;                        // [vcap][D]
+    u32* vcount; u32 vcap;
+    u64* vtab; u64 vmask;              // vertex set: slot = fingerprint << 32 | (index + 1)
+    u64* etab; u64 emask;              // edge table: see edge_slot()
+    unsigned char* has_vertex;         // [n]
+    u32* ray_item; double* ray_u; u32* ray_count; u32 ray_cap;   // unbounded edges: v << 3 | k, direction
+    Counters* ctr;
+};
+
+// linear grid cell of a point (axis D-1 fastest); the same expression is used when the index is built
+template <int D>
+HVB_HD int cell_index(const Dev<D>& dv, const double* x) {
+    int idx = 0;
+#pragma unroll
+    for (int k = 0; k < D; ++k) {
+        double v = fmin(fmax((x[k] - dv.lo[k]) * dv.inv_h[k], 0.0), (double)(dv.g[k] - 1));
+        idx = idx * dv.g[k] + (int)floor(v);
+    }
+    return idx;
+}
+
+struct LocalStats {
+    u32 raycasts, dup_hits, closed_skips, cand32, cand64, rows, stages, seeds, degenerate, seed_fail, dead;
+};
+
+// ------------------------------------------------------------------------------------------------------------
+// hashing of sorted id tuples (replaces fnv1a_hash, tools.jl:11-28; full keys are always compared)
+// ------------------------------------------------------------------------------------------------------------
+HVB_HD u64 mix64(u64 x) {
+    x ^= x >> 33; x *= 0xff51afd7ed558ccdULL; x ^= x >> 33; x *= 0xc4ceb9fe1a85ec53ULL; x ^= x >> 33;
+    return x;
+}
+template <int D>
+HVB_HD u64 hash_ids(const int* ids, int count, int skip) {
+    u64 h = 0x9e3779b97f4a7c15ULL;
+#pragma unroll
+    for (int i = 0; i < D + 1; ++i)
+        if (i < count && i != skip) h = (h ^ (u64)(u32)ids[i]) * 0x100000001b3ULL + 0x632be59bd9b4e019ULL;
+    return mix64(h);
+}
+
+// edge slot: [63] valid, [62:36] fingerprint, [35] closed, [34:3] vertex index, [2:0] dropped position
+HVB_HD u64 edge_slot(u64 hash, u32 v, int k) {
+    return (1ULL << 63) | (((hash >> 37) & 0x7ffffffULL) << 36) | ((u64)v << 3) | (u64)k;
+}
+const u64 EDGE_CLOSED = 1ULL << 35;
+const u64 EDGE_FPMASK = (0x7ffffffULL << 36) | (1ULL << 63);
+
+// ------------------------------------------------------------------------------------------------------------
+// geometry
+// ------------------------------------------------------------------------------------------------------------
+template <int D>
+HVB_HD double dotD(const double* a, const double* b) {
+    double s = 0;
+#pragma unroll
+    for (int k = 0; k < D; ++k) s += a[k] * b[k];
+    return s;
+}
+
+// Unit vector orthogonal to the rows of V selected by `mask` (overwritten by an orthonormal basis), obtained by
+// projecting `v` off them (modified Gram-Schmidt, two passes).  Replaces u_qr (tools.jl:773-790): with
+// v = -(x_dropped - x0) the orientation "away from the dropped generator" holds by construction.  Rows are
+// addressed statically (mask predicates) so that V stays in registers.
+template <int D>
+HVB_HD bool ortho_direction(double (&V)[D + 1][D], unsigned mask, double (&v)[D]) {
+    bool ok = true;
+#pragma unroll
+    for (int i = 0; i < D + 1; ++i) {
+        if ((mask >> i) & 1u) {
+#pragma unroll
+            for (int rep = 0; rep < 2; ++rep) {
+#pragma unroll
+                for (int j = 0; j < D + 1; ++j)
+                    if (j < i && ((mask >> j) & 1u)) {
+                        double s = dotD<D>(V[i], V[j]);
+#pragma unroll
+                        for (int k = 0; k < D; ++k) V[i][k] -= s * V[j][k];
+                    }
+                double nr = sqrt(dotD<D>(V[i], V[i]));
+                ok &= (nr > 0);
+                double inv = 1.0 / nr;
+#pragma unroll
+                for (int k = 0; k < D; ++k) V[i][k] *= inv;
+            }
+        }
+    }
+#pragma unroll
+    for (int rep = 0; rep < 2; ++rep) {
+#pragma unroll
+        for (int j = 0; j < D + 1; ++j)
+            if ((mask >> j) & 1u) {
+                double s = dotD<D>(v, V[j]);
+#pragma unroll
+                for (int k = 0; k < D; ++k) v[k] -= s * V[j][k];
+            }
+        double nr = sqrt(dotD<D>(v, v));
+        ok &= (nr > 0);
+        double inv = 1.0 / nr;
+#pragma unroll
+        for (int k = 0; k < D; ++k) v[k] *= inv;
+    }
+    return ok;
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// the min-t query
+// ------------------------------------------------------------------------------------------------------------
+template <int D>
+struct RayQ {
+    double r[D], u[D], x0[D];
+    double c;          // half-space threshold on u.x : candidates need u.x > c   (raycast.jl:802-805, myskips :385)
+    double R0sq;       // |x0 - r|^2
+    double a;          // u.(x0 - r)
+    int excl[D + 1];   // ids that may not win (the origin vertex's generators)
+    int nexcl;
+};
+
+struct Best {
+    double t;          // smallest ray parameter so far
+    int id;            // its generator (>= n : boundary plane id - n), -1 none
+    double t2;         // runner-up, for the general-position check
+};
+
+HVB_HD void best_offer(Best& b, double t, int id) {
+    if (t < b.t || (t == b.t && id < b.id)) { b.t2 = b.t; b.t = t; b.id = id; }
+    else if (id != b.id && t < b.t2) b.t2 = t;
+}
+HVB_HD void best_merge(Best& b, double t, int id, double t2) {
+    if (t < b.t || (t == b.t && id < b.id)) {
+        double o = (id != b.id) ? b.t : b.t2;
+        b.t2 = fmin(o, fmin(b.t2, t2)); b.t = t; b.id = id;
+    } else {
+        double o = (id != b.id) ? t : t2;
+        b.t2 = fmin(b.t2, fmin(o, t2));
+    }
+}
+template <class T>
+HVB_HD void best_reduce(const T& tile, Best& b) {
+#pragma unroll
+    for (int m = T::SIZE / 2; m >= 1; m >>= 1) {
+        double ot = tile.shfl_xor(b.t, m);
+        int oid = tile.shfl_xor(b.id, m);
+        double ot2 = tile.shfl_xor(b.t2, m);
+        best_merge(b, ot, oid, ot2);
+    }
+}
+
+// FP64 evaluation of one generator: get_t_hp (raycast.jl:427-432) under the predicate of myskips (:385)
+template <int D>
+HVB_HD void verify64(const Dev<D>& dv, const RayQ<D>& q, int j, Best& best, LocalStats& ls) {
+#pragma unroll
+    for (int e = 0; e < D + 1; ++e)
+        if (e < q.nexcl && q.excl[e] == j) return;
+    const double* x = dv.x64 + (size_t)j * D;
+    double ux = 0, num = 0, den = 0;
+#pragma unroll
+    for (int k = 0; k < D; ++k) {
+        double xk = x[k];
+        double dx = xk - q.x0[k];
+        ux += q.u[k] * xk;
+        num += dx * (q.x0[k] + xk - 2.0 * q.r[k]);
+        den += q.u[k] * dx;
+    }
+    ls.cand64++;
+    if (!(ux > q.c) || !(den > 0)) return;
+    double t = num / (2.0 * den);
+    if (!(t >= dv.plane_tol)) return;                 // raycast.jl:887-889
+    best_offer(best, t, j);
+}
+
+// per-stage FP32 filter constants
+struct Filt {
+    float tb2;      // 2 * t_best, rounded up
+    float en;       // bound on |num32 - num|
+    float ed;       // bound on |den32 - den/2|
+};
+template <int D>
+HVB_HD Filt make_filter(double t_best, double rho, double R0, double ext) {
+    // coordinates are stored as fl32(x - lo) in [0, ext]: |q32 - q| <= eta per component
+    const double eps = 5.9604644775390625e-08;        // 2^-24
+    double eta = 3.0 * eps * ext;
+    double Q = 2.0 * fmax(rho, R0), W = R0;
+    double en = D * (2.0 * eta * (Q + W) + 2.0 * eps * Q * W + eta * eta) + (D + 3) * eps * D * Q * (Q + 2.0 * W);
+    double ed = D * eta + (D + 2.0) * D * eps * Q;
+    Filt f;
+    double tb2 = 2.0 * t_best * (1.0 + 8.0 * eps);
+    f.tb2 = (tb2 < 3.0e38) ? (float)tb2 * 1.0000005f : INFINITY;
+    en *= 2.0; ed *= 2.0;
+    f.en = (en < 3.0e38) ? (float)en * 1.0000005f : INFINITY;
+    f.ed = (ed < 3.0e38) ? (float)ed * 1.0000005f : INFINITY;
+    return f;
+}
+
+// Smallest t > 0 at which the ball centred at r + t u through x0 touches another generator or boundary plane.
+// All lanes of the tile call this with identical q; all return the same Best.
+template <int D, class T>
+HVB_HD Best min_t_query(const Dev<D>& dv, const T& tile, const RayQ<D>& q, LocalStats& ls) {
+    Best best;
+    best.t = INFINITY; best.id = -1; best.t2 = INFINITY;
+    const int lane = tile.lane();
+    ls.raycasts += (lane == 0);
+
+    // ---- boundary planes: mirror images of x0 (raycast.jl:354-375, extended.jl:131-140), analytically ----
+    const PlaneSet* ps = dv.planes;
+    const int P = ps->P;
+    {
+        double ux0 = dotD<D>(q.u, q.x0);
+        for (int p = 0; p < P; ++p) {
+            bool ex = false;
+#pragma unroll
+            for (int e = 0; e < D + 1; ++e) ex |= (e < q.nexcl && q.excl[e] == dv.n + p);
+            if (ex) continue;
+            const double* nrm = ps->normal + p * 6;
+            double nu = 0, nx0 = 0, nr = 0;
+#pragma unroll
+            for (int k = 0; k < D; ++k) { nu += nrm[k] * q.u[k]; nx0 += nrm[k] * q.x0[k]; nr += nrm[k] * q.r[k]; }
+            double s = ps->off[p] - nx0;                       // distance of x0 to the plane (> 0 inside)
+            if (!(ux0 + 2.0 * s * nu > q.c) || !(nu > 0)) continue;
+            double t = (ps->off[p] - nr) / nu;
+            if (!(t >= dv.plane_tol)) continue;
+            best_offer(best, t, dv.n + p);
+        }
+    }
+
+    // ---- FP32 copies of the ray ---------------------------------------------------------------------------
+    float uf[D], w2f[D], x0f[D];
+#pragma unroll
+    for (int k = 0; k < D; ++k) {
+        uf[k] = (float)q.u[k];
+        w2f[k] = (float)(2.0 * (q.r[k] - q.x0[k]));
+        x0f[k] = (float)(q.x0[k] - dv.lo[k]);
+    }
+    const double R0 = sqrt(q.R0sq);
+    const double R0p = fmax(R0, 0.5 * dv.hmin);
+    const double perp2 = fmax(q.R0sq - q.a * q.a, 0.0);       // squared distance of x0 to the ray's line
+    double scale = dv.probe_scale;
+
+    for (int stage = 0; stage < 64; ++stage) {
+        ls.stages += (lane == 0);
+        double rho_t = scale * R0p;
+        double Tst = (rho_t > 1e4 * dv.diag) ? INFINITY : q.a + sqrt(fmax(rho_t * rho_t - perp2, 0.0));
+        double Ts = fmin(Tst, best.t);
+        bool halfspace_mode = !(Ts < INFINITY);
+        // current search ball
+        double cen[D], rho2, rho;
+        if (halfspace_mode) {
+#pragma unroll
+            for (int k = 0; k < D; ++k) cen[k] = q.r[k];
+            rho = 1e150; rho2 = 1e300;
+        } else {
+#pragma unroll
+            for (int k = 0; k < D; ++k) cen[k] = q.r[k] + Ts * q.u[k];
+            rho2 = (q.R0sq - 2.0 * Ts * q.a + Ts * Ts) * (1.0 + 1e-12) + 1e-300;
+            rho = sqrt(rho2);
+        }
+        // cell box of the ball
+        int clo[D], chi[D];
+        int nrows = 1;
+        bool empty = false;
+#pragma unroll
+        for (int k = 0; k < D; ++k) {
+            double gk = (double)dv.g[k];
+            double vlo = fmin(fmax((cen[k] - rho - dv.lo[k]) * dv.inv_h[k] - 1e-9, 0.0), gk - 1.0);
+            double vhi = fmin(fmax((cen[k] + rho - dv.lo[k]) * dv.inv_h[k] + 1e-9, -1.0), gk - 1.0);
+            clo[k] = (int)floor(vlo); chi[k] = (int)floor(vhi);
+            if (chi[k] < clo[k]) empty = true;
+            if (k < D - 1) nrows *= (chi[k] - clo[k] + 1);
+        }
+        if (empty) nrows = 0;
+        Filt flt = make_filter<D>(halfspace_mode ? INFINITY : Ts, rho, R0, dv.ext);
+        double t_seen = best.t;
+
+        const int niter = (nrows + T::SIZE - 1) / T::SIZE;
+        for (int it = 0; it < niter; ++it) {
+            int j = it * T::SIZE + lane;
+            if (j < nrows) {
+                // decode the row
+                int base = 0;
+                double d2 = 0, umax = 0;
+                int rem = j;
+                int cc[D];
+#pragma unroll
+                for (int k = D - 2; k >= 0; --k) {
+                    int e = chi[k] - clo[k] + 1;
+                    cc[k] = clo[k] + rem % e;
+                    rem /= e;
+                }
+#pragma unroll
+                for (int k = 0; k < D - 1; ++k) {
+                    double blo = dv.lo[k] + cc[k] * dv.h[k] - 1e-9 * dv.h[k];
+                    double bhi = blo + dv.h[k] * (1.0 + 2e-9);
+                    double dd = fmax(0.0, fmax(blo - cen[k], cen[k] - bhi));
+                    d2 += dd * dd;
+                    umax += fmax(q.u[k] * (blo - q.x0[k]), q.u[k] * (bhi - q.x0[k]));
+                    base = base * dv.g[k] + cc[k];
+                }
+                if (d2 <= rho2) {
+                    const int L = D - 1;
+                    double s = sqrt(rho2 - d2);
+                    double zlo = cen[L] - s, zhi = cen[L] + s;
+                    bool skip = false;
+                    double ul = q.u[L];
+                    double slack = 1e-9 * (dv.h[L] + fabs(umax));
+                    if (ul > 1e-300) zlo = fmax(zlo, q.x0[L] - (umax + slack) / ul);
+                    else if (ul < -1e-300) zhi = fmin(zhi, q.x0[L] - (umax + slack) / ul);
+                    else if (umax + slack <= 0) skip = true;
+                    if (!skip) {
+                        double gl = (double)dv.g[L];
+                        double vlo = fmin(fmax((zlo - dv.lo[L]) * dv.inv_h[L] - 1e-9, 0.0), gl - 1.0);
+                        double vhi = fmin(fmax((zhi - dv.lo[L]) * dv.inv_h[L] + 1e-9, -1.0), gl - 1.0);
+                        int z0 = (int)floor(vlo), z1 = (int)floor(vhi);
+                        if (z1 >= z0) {
+                            ls.rows++;
+                            const int* cs = dv.cell_start + (size_t)base * dv.g[L];
+                            int pa = cs[z0], pb = cs[z1 + 1];
+                            ls.cand32 += (u32)(pb - pa);
+                            if (dv.fp32_filter) {
+                                const float* xp = dv.x32 + (size_t)pa * D;
+                                for (int p = pa; p < pb; ++p, xp += D) {
+                                    float den = 0.f, num = 0.f;
+#pragma unroll
+                                    for (int k = 0; k < D; ++k) {
+                                        float qk = xp[k] - x0f[k];
+                                        den = fmaf(uf[k], qk, den);
+                                        num = fmaf(qk, qk - w2f[k], num);
+                                    }
+                                    float dh = den + flt.ed;
+                                    if (dh > 0.f && (num - flt.en) <= flt.tb2 * dh) {
+                                        verify64<D>(dv, q, p, best, ls);
+                                        if (best.t < t_seen) {
+                                            t_seen = best.t;
+                                            flt.tb2 = (float)(2.0 * best.t * (1.0 + 4.8e-7)) * 1.0000005f;
+                                        }
+                                    }
+                                }
+                            } else {
+                                for (int p = pa; p < pb; ++p) verify64<D>(dv, q, p, best, ls);
+                            }
+                        }
+                    }
+                }
+            }
+            // share the best bound and shrink the ball
+            if (T::SIZE > 1) best_reduce(tile, best);
+            if (best.t < Ts) {
+                Ts = best.t;
+#pragma unroll
+                for (int k = 0; k < D; ++k) cen[k] = q.r[k] + Ts * q.u[k];
+                rho2 = (q.R0sq - 2.0 * Ts * q.a + Ts * Ts) * (1.0 + 1e-12) + 1e-300;
+                rho = sqrt(rho2);
+                flt = make_filter<D>(Ts, rho, R0, dv.ext);
+                t_seen = best.t;
+            }
+        }
+        if (best.t <= fmin(Tst, Ts) || !(Tst < INFINITY)) break;
+        scale *= 2.0;
+    }
+    return best;
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// vertex set + edge table
+// ------------------------------------------------------------------------------------------------------------
+template <int D>
+HVB_HD bool sig_equal(const Dev<D>& dv, u32 v, const int* sig) {
+    const int* p = dv.vsig + (size_t)v * (D + 1);
+    bool eq = true;
+#pragma unroll
+    for (int k = 0; k < D + 1; ++k) eq &= (ld_cg(p + k) == sig[k]);
+    return eq;
+}
+
+// Inserts (sig, r) unless present.  Returns the new index, or 0xffffffff if it was known / the store is full.
+// Replaces haskey + push! (abstractmesh.jl:111-153 -> hvdatabase.jl:94-116).
+template <int D>
+HVB_HD u32 vertex_insert(const Dev<D>& dv, const int* sig, const double* r, LocalStats& ls) {
+    u64 h = hash_ids<D>(sig, D + 1, -1);
+    u64 fp = (h >> 32) << 32;
+    if (fp == 0) fp = 1ULL << 32;
+    u64 slot = h & dv.vmask;
+    u32 mine = 0xffffffffu;
+    for (;;) {
+        u64 s = ld_cg(dv.vtab + slot);
+        if (s == 0) {
+            if (mine == 0xffffffffu) {
+                mine = atom_add(dv.vcount, 1u);
+                if (mine >= dv.vcap) { atom_or(&dv.ctr->flags, (u32)FLAG_VFULL); return 0xffffffffu; }
+                int* ps = dv.vsig + (size_t)mine * (D + 1);
+                double* pr = dv.vr + (size_t)mine * D;
+#pragma unroll
+                for (int k = 0; k < D + 1; ++k) ps[k] = sig[k];
+#pragma unroll
+                for (int k = 0; k < D; ++k) pr[k] = r[k];
+                mem_fence();
+            }
+            s = atom_cas(dv.vtab + slot, 0ULL, fp | (u64)(mine + 1u));
+            if (s == 0) return mine;
+        }
+        if ((s >> 32) == (fp >> 32) && sig_equal<D>(dv, (u32)(s & 0xffffffffu) - 1u, sig)) {
+            if (mine != 0xffffffffu) { dv.vsig[(size_t)mine * (D + 1)] = -1; ls.dead++; }   // lost a race: dead record
+            ls.dup_hits++;
+            return 0xffffffffu;
+        }
+        slot = (slot + 1) & dv.vmask;
+    }
+}
+
+// does the edge stored in slot value s equal (sig minus position k)?
+template <int D>
+HVB_HD bool edge_equal(const Dev<D>& dv, u64 s, const int* sig, int k) {
+    u32 v2 = (u32)((s >> 3) & 0xffffffffULL);
+    int k2 = (int)(s & 7);
+    const int* p = dv.vsig + (size_t)v2 * (D + 1);
+    bool eq = true;
+    int i2 = 0;
+#pragma unroll
+    for (int i = 0; i < D + 1; ++i) {
+        if (i == k) continue;
+        if (i2 == k2) ++i2;
+        eq &= (ld_cg(p + i2) == sig[i]);
+        ++i2;
+    }
+    return eq;
+}
+
+// Registers the sub-facet (sig minus position k) of vertex v.  First endpoint: the edge becomes an open frontier
+// entry (returns its slot); second endpoint: the edge is closed (returns ~0).  Replaces pushedge!
+// (edgehashing.jl:66-111) and queue_edges_OnFind (edgeiteratebase.jl:128-149).
+template <int D>
+HVB_HD u64 edge_register(const Dev<D>& dv, const int* sig, u32 v, int k) {
+    u64 h = hash_ids<D>(sig, D + 1, k);
+    u64 mine = edge_slot(h, v, k);
+    u64 slot = h & dv.emask;
+    for (;;) {
+        u64 s = ld_cg(dv.etab + slot);
+        if (s == 0) {
+            s = atom_cas(dv.etab + slot, 0ULL, mine);
+            if (s == 0) return slot;
+        }
+        if (((s ^ mine) & EDGE_FPMASK) == 0 && edge_equal<D>(dv, s, sig, k)) {
+            if (!(s & EDGE_CLOSED)) atom_or(dv.etab + slot, EDGE_CLOSED);
+            return ~0ULL;
+        }
+        slot = (slot + 1) & dv.emask;
+    }
+}
+
+// Shared tail of a walk / a descent: store the vertex, register its d+1 sub-facets, append the open ones to the
+// next frontier.  sig sorted.  All lanes call; lane 0 inserts, lanes 0..D register one sub-facet each.
+template <int D, class T>
+HVB_HD void commit_vertex(const Dev<D>& dv, const T& tile, const int* sig, const double* r,
+                          u32* q_out, u32* q_count, u32 q_cap, LocalStats& ls) {
+    const int lane = tile.lane();
+    u32 v = 0xffffffffu;
+    if (lane == 0) v = vertex_insert<D>(dv, sig, r, ls);
+    if (T::SIZE > 1) v = tile.shfl(v, 0);
+    if (v == 0xffffffffu) return;
+    if (lane == 0) {
+#pragma unroll
+        for (int k = 0; k < D + 1; ++k)
+            if (sig[k] < dv.n) dv.has_vertex[sig[k]] = 1;
+    }
+    for (int k = lane; k < D + 1; k += T::SIZE) {
+        // the sub-facet must keep a real generator whose cell this context explores
+        bool act = false;
+#pragma unroll
+        for (int i = 0; i < D + 1; ++i)
+            if (i != k && sig[i] < dv.n) act |= (dv.active[sig[i]] != 0);
+        if (!act) continue;
+        u64 slot = edge_register<D>(dv, sig, v, k);
+        if (slot != ~0ULL) {
+            u32 pos = atom_add(q_count, 1u);
+            if (pos < q_cap) q_out[pos] = (u32)slot;
+            else atom_or(&dv.ctr->flags, (u32)FLAG_QFULL);
+        }
+    }
+    tile.sync();
+}
+
+// insertion of g into the sorted list sig[0..cnt)
+HVB_HD void sorted_insert(int* sig, int cnt, int g) {
+    int i = cnt;
+    while (i > 0 && sig[i - 1] > g) { sig[i] = sig[i - 1]; --i; }
+    sig[i] = g;
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// one frontier entry: walk the open edge from its known endpoint (walkray raycast.jl:125-164 +
+// systematic_explore_vertex sysvoronoi.jl:490-525, one edge at a time)
+// ------------------------------------------------------------------------------------------------------------
+template <int D, class T>
+HVB_HD void expand_item(const Dev<D>& dv, const T& tile, u32 eslot, u32* q_out, u32* q_count, u32 q_cap, LocalStats& ls) {
+    const int lane = tile.lane();
+    // The closed bit is mutable: every lane must act on the SAME snapshot of the slot, otherwise part of the tile
+    // leaves while the rest waits in a shuffle.  Lane 0 reads, the tile converges on the broadcast.
+    tile.sync();
+    u64 s = 0;
+    if (lane == 0) s = ld_cg(dv.etab + eslot);
+    if (T::SIZE > 1) s = tile.shfl(s, 0);
+    if (s & EDGE_CLOSED) { ls.closed_skips += (lane == 0); return; }
+    const u32 v = (u32)((s >> 3) & 0xffffffffULL);
+    const int kd = (int)(s & 7);
+    int sig[D + 1];
+    RayQ<D> q;
+#pragma unroll
+    for (int k = 0; k < D + 1; ++k) { sig[k] = ld_cg(dv.vsig + (size_t)v * (D + 1) + k); q.excl[k] = sig[k]; }
+    q.nexcl = D + 1;
+#pragma unroll
+    for (int k = 0; k < D; ++k) q.r[k] = ld_cg(dv.vr + (size_t)v * D + k);
+    // x0 = first generator of the edge (always a real one: plane ids sort last)
+    const int id0 = (kd == 0) ? sig[1] : sig[0];
+    const int i0 = (kd == 0) ? 1 : 0;
+#pragma unroll
+    for (int k = 0; k < D; ++k) q.x0[k] = dv.x64[(size_t)id0 * D + k];
+    const PlaneSet* ps = dv.planes;
+    // direction: orthogonal to the edge's difference vectors / plane normals, away from the dropped generator
+    double V[D + 1][D];
+    double xd[D];
+#pragma unroll
+    for (int i = 0; i < D + 1; ++i) {
+        int id = sig[i];
+        if (id < dv.n) {
+#pragma unroll
+            for (int k = 0; k < D; ++k) V[i][k] = dv.x64[(size_t)id * D + k] - q.x0[k];
+        } else {
+#pragma unroll
+            for (int k = 0; k < D; ++k) V[i][k] = ps->normal[(id - dv.n) * 6 + k];
+        }
+        if (i == kd) {
+#pragma unroll
+            for (int k = 0; k < D; ++k) xd[k] = -V[i][k];
+        }
+    }
+    const unsigned emask = ((1u << (D + 1)) - 1u) & ~(1u << kd) & ~(1u << i0);
+    if (!ortho_direction<D>(V, emask, xd)) { ls.seed_fail += (lane == 0); return; }
+#pragma unroll
+    for (int k = 0; k < D; ++k) q.u[k] = xd[k];
+    // half-space threshold: c = max_{g in edge} u.x_g, c += |c| * plane_tol   (raycast.jl:802-804)
+    {
+        double cm = -INFINITY;
+        double ux0 = dotD<D>(q.u, q.x0);
+#pragma unroll
+        for (int i = 0; i < D + 1; ++i) {
+            if (i == kd) continue;
+            int id = sig[i];
+            double ux;
+            if (id < dv.n) ux = dotD<D>(q.u, dv.x64 + (size_t)id * D);
+            else {   // mirror image of x0 in the plane
+                const double* nrm = ps->normal + (id - dv.n) * 6;
+                double nu = 0, nx0 = 0;
+#pragma unroll
+                for (int k = 0; k < D; ++k) { nu += nrm[k] * q.u[k]; nx0 += nrm[k] * q.x0[k]; }
+                ux = ux0 + 2.0 * (ps->off[id - dv.n] - nx0) * nu;
+            }
+            cm = fmax(cm, ux);
+        }
+        q.c = cm + fabs(cm) * dv.plane_tol;
+    }
+    {
+        double w[D];
+#pragma unroll
+        for (int k = 0; k < D; ++k) w[k] = q.x0[k] - q.r[k];
+        q.R0sq = dotD<D>(w, w);
+        q.a = dotD<D>(q.u, w);
+    }
+    Best best = min_t_query<D, T>(dv, tile, q, ls);
+    if (best.id < 0) {                       // unbounded edge (sysvoronoi.jl:504-511)
+        if (lane == 0) {
+            u32 pos = atom_add(dv.ray_count, 1u);
+            if (pos < dv.ray_cap) {
+                dv.ray_item[pos] = (v << 3) | (u32)kd;
+#pragma unroll
+                for (int k = 0; k < D; ++k) dv.ray_u[(size_t)pos * D + k] = q.u[k];
+            } else atom_or(&dv.ctr->flags, (u32)FLAG_RFULL);
+        }
+        return;
+    }
+    if (best.t2 - best.t <= 1e-12 * fmax(best.t, sqrt(q.R0sq))) ls.degenerate += (lane == 0);
+    // new vertex: (sig minus position kd) plus the winner, kept sorted with static indexing
+    int sig2[D + 1];
+    {
+        int e[D];
+        int pos = 0;
+#pragma unroll
+        for (int j = 0; j < D; ++j) {
+            e[j] = (j < kd) ? sig[j] : sig[j + 1];
+            pos += (e[j] < best.id) ? 1 : 0;
+        }
+#pragma unroll
+        for (int i = 0; i < D + 1; ++i) {
+            int lo_ = (i < D) ? e[i] : 0;
+            int hi_ = (i > 0) ? e[i - 1] : 0;
+            sig2[i] = (i < pos) ? lo_ : ((i == pos) ? best.id : hi_);
+        }
+    }
+    double r2[D];
+#pragma unroll
+    for (int k = 0; k < D; ++k) r2[k] = q.r[k] + best.t * q.u[k];
+    commit_vertex<D, T>(dv, tile, sig2, r2, q_out, q_count, q_cap, ls);
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// seeding: descent (raycast.jl:45-109) from generator `start`
+// ------------------------------------------------------------------------------------------------------------
+// out-of-line copy for the (cold) descent, which would otherwise inline the query 2 d times
+template <int D, class T>
+#if defined(__CUDACC__)
+__host__ __device__ __noinline__
+#endif
+Best min_t_query_call(const Dev<D>& dv, const T& tile, const RayQ<D>& q, LocalStats& ls) {
+    return min_t_query<D, T>(dv, tile, q, ls);
+}
+
+HVB_HD double unit_hash(u64& s) {          // deterministic stand-in for randn (raycast.jl:228)
+    s = mix64(s + 0x9e3779b97f4a7c15ULL);
+    return ((double)(s >> 11) + 0.5) * (1.0 / 9007199254740992.0) * 2.0 - 1.0;
+}
+
+template <int D, class T>
+HVB_HD void seed_item(const Dev<D>& dv, const T& tile, int start, u32* q_out, u32* q_count, u32 q_cap, LocalStats& ls) {
+    const int lane = tile.lane();
+    tile.sync();
+    ls.seeds += (lane == 0);
+    const PlaneSet* ps = dv.planes;
+    for (int attempt = 0; attempt < 8; ++attempt) {
+        int sig[D + 1];          // in order of discovery; sig[0] = start
+        int cnt = 1;
+        sig[0] = start;
+        RayQ<D> q;
+#pragma unroll
+        for (int k = 0; k < D; ++k) { q.x0[k] = dv.x64[(size_t)start * D + k]; q.r[k] = q.x0[k]; }
+        u64 rs = mix64(((u64)(u32)start << 8) ^ (u64)attempt ^ 0x51ed270b1f2cULL);
+        bool ok = true;
+        for (int step = 0; step < D && ok; ++step) {
+            double V[D + 1][D];
+            unsigned vmask_ = 0;
+#pragma unroll
+            for (int i = 0; i < D + 1; ++i) {
+#pragma unroll
+                for (int k = 0; k < D; ++k) V[i][k] = 0.0;
+                if (i >= 1 && i < cnt) {
+                    int id = sig[i];
+                    if (id < dv.n) {
+#pragma unroll
+                        for (int k = 0; k < D; ++k) V[i][k] = dv.x64[(size_t)id * D + k] - q.x0[k];
+                    } else {
+#pragma unroll
+                        for (int k = 0; k < D; ++k) V[i][k] = ps->normal[(id - dv.n) * 6 + k];
+                    }
+                    vmask_ |= 1u << i;
+                }
+            }
+            double v[D];
+#pragma unroll
+            for (int k = 0; k < D; ++k) v[k] = unit_hash(rs);
+            if (!ortho_direction<D>(V, vmask_, v)) { ok = false; break; }
+            Best best;
+            best.id = -1; best.t = INFINITY; best.t2 = INFINITY;
+            for (int dir = 0; dir < 2 && best.id < 0; ++dir) {
+#pragma unroll
+                for (int k = 0; k < D; ++k) q.u[k] = dir ? -v[k] : v[k];
+                double cm = -INFINITY;
+                double ux0 = dotD<D>(q.u, q.x0);
+#pragma unroll
+                for (int i = 0; i < D + 1; ++i) {
+                    if (i < cnt) {
+                        int id = sig[i];
+                        double ux;
+                        if (id < dv.n) ux = dotD<D>(q.u, dv.x64 + (size_t)id * D);
+                        else {
+                            const double* nrm = ps->normal + (id - dv.n) * 6;
+                            double nu = 0, nx0 = 0;
+#pragma unroll
+                            for (int k = 0; k < D; ++k) { nu += nrm[k] * q.u[k]; nx0 += nrm[k] * q.x0[k]; }
+                            ux = ux0 + 2.0 * (ps->off[id - dv.n] - nx0) * nu;
+                        }
+                        cm = fmax(cm, ux);
+                    }
+                }
+                q.c = cm + fabs(cm) * dv.plane_tol;
+                double w[D];
+#pragma unroll
+                for (int k = 0; k < D; ++k) w[k] = q.x0[k] - q.r[k];
+                q.R0sq = dotD<D>(w, w);
+                q.a = dotD<D>(q.u, w);
+#pragma unroll
+                for (int i = 0; i < D + 1; ++i) q.excl[i] = (i < cnt) ? sig[i] : -1;
+                q.nexcl = cnt;
+                best = min_t_query_call<D, T>(dv, tile, q, ls);
+            }
+            if (best.id < 0) { ok = false; break; }
+#pragma unroll
+            for (int k = 0; k < D; ++k) q.r[k] += best.t * q.u[k];
+            sig[cnt++] = best.id;
+        }
+        if (!ok) continue;
+        int ssig[D + 1];
+        for (int i = 0; i < D + 1; ++i) sorted_insert(ssig, i, sig[i]);
+        commit_vertex<D, T>(dv, tile, ssig, q.r, q_out, q_count, q_cap, ls);
+        return;
+    }
+    ls.seed_fail += (lane == 0);
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// canonical coordinates: the point equidistant to the generators / on the planes of sig, solved from the
+// generators alone so that the output does not depend on the walk that found the vertex (sig is passed in the
+// caller's canonical order: ascending ORIGINAL ids).  Replaces
+// walkray_correct_vertex / _correct_vertex (raycast.jl:242-318).  Returns the relative variance of the squared
+// radii over the real generators (vertex_variance, raycast.jl:320-329).
+// ------------------------------------------------------------------------------------------------------------
+template <int D>
+HVB_HD double canonical_vertex(const Dev<D>& dv, const int* sig, double* r) {
+    const PlaneSet* ps = dv.planes;
+    double x0[D];
+#pragma unroll
+    for (int k = 0; k < D; ++k) x0[k] = dv.x64[(size_t)sig[0] * D + k];
+    double A[D][D], b[D], z[D];
+#pragma unroll
+    for (int i = 0; i < D; ++i) {
+        int id = sig[i + 1];
+        if (id < dv.n) {
+            double s = 0;
+#pragma unroll
+            for (int k = 0; k < D; ++k) { A[i][k] = dv.x64[(size_t)id * D + k] - x0[k]; s += A[i][k] * A[i][k]; }
+            b[i] = 0.5 * s;
+        } else {
+            double s = 0;
+#pragma unroll
+            for (int k = 0; k < D; ++k) { A[i][k] = ps->normal[(id - dv.n) * 6 + k]; s += A[i][k] * x0[k]; }
+            b[i] = ps->off[id - dv.n] - s;
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < D; ++k) z[k] = 0.0;
+    // direct solve of A z = b plus one step of iterative refinement (Gaussian elimination with partial pivoting);
+    // the walked coordinates are deliberately not used, so the result depends on sig alone
+    for (int rep = 0; rep < 2; ++rep) {
+        double M[D][D + 1];
+#pragma unroll
+        for (int i = 0; i < D; ++i) {
+            double res = b[i];
+#pragma unroll
+            for (int k = 0; k < D; ++k) { M[i][k] = A[i][k]; res -= A[i][k] * z[k]; }
+            M[i][D] = res;
+        }
+#pragma unroll
+        for (int c = 0; c < D; ++c) {
+            int pv = c;
+            double mx = fabs(M[c][c]);
+#pragma unroll
+            for (int i = 0; i < D; ++i)
+                if (i > c && fabs(M[i][c]) > mx) { mx = fabs(M[i][c]); pv = i; }
+#pragma unroll
+            for (int i = 0; i < D; ++i)
+                if (i == pv && pv != c) {
+#pragma unroll
+                    for (int k = 0; k < D + 1; ++k) { double tmp = M[c][k]; M[c][k] = M[i][k]; M[i][k] = tmp; }
+                }
+            double inv = (M[c][c] != 0.0) ? 1.0 / M[c][c] : 0.0;
+#pragma unroll
+            for (int i = 0; i < D; ++i)
+                if (i > c) {
+                    double f = M[i][c] * inv;
+#pragma unroll
+                    for (int k = 0; k < D + 1; ++k)
+                        if (k >= c) M[i][k] -= f * M[c][k];
+                }
+        }
+        double dz[D];
+#pragma unroll
+        for (int c = D - 1; c >= 0; --c) {
+            double s = M[c][D];
+#pragma unroll
+            for (int k = 0; k < D; ++k)
+                if (k > c) s -= M[c][k] * dz[k];
+            dz[c] = (M[c][c] != 0.0) ? s / M[c][c] : 0.0;
+        }
+#pragma unroll
+        for (int k = 0; k < D; ++k) z[k] += dz[k];
+    }
+#pragma unroll
+    for (int k = 0; k < D; ++k) r[k] = x0[k] + z[k];
+    // variance over the real generators
+    double dist[D + 1], mean = 0;
+    int cnt = 0;
+#pragma unroll
+    for (int i = 0; i < D + 1; ++i) {
+        dist[i] = 0;
+        if (sig[i] < dv.n) {
+            double s = 0;
+#pragma unroll
+            for (int k = 0; k < D; ++k) { double t = dv.x64[(size_t)sig[i] * D + k] - r[k]; s += t * t; }
+            dist[i] = s; mean += s; ++cnt;
+        }
+    }
+    mean /= cnt;
+    double var = 0;
+#pragma unroll
+    for (int i = 0; i < D + 1; ++i)
+        if (sig[i] < dv.n) var += (dist[i] - mean) * (dist[i] - mean);
+    return var / (mean * mean);
+}
+
+}  // namespace hvb

@@ -1,0 +1,329 @@
+// hvb_kernels.cuh -- __global__ wrappers around hvb_core.cuh plus the index-build and finalize kernels.
+// sm_100a only.  Launch shapes: tiles of G lanes per frontier entry, grid-stride over entries, grids sized in
+// multiples of the SM count.
+#pragma once
+#include <cuda_runtime.h>
+#include "hvb_core.cuh"
+
+namespace hvb {
+
+// ------------------------------------------------------------------------------------------------------------
+// statistics: per-thread registers -> one atomic per warp at kernel end
+// ------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void flush_stats(const LocalStats& ls, Counters* c) {
+    const u32* src = reinterpret_cast<const u32*>(&ls);
+    u64* dst = reinterpret_cast<u64*>(c);
+#pragma unroll
+    for (int i = 0; i < (int)(sizeof(LocalStats) / sizeof(u32)); ++i) {
+        u32 v = src[i];
+#pragma unroll
+        for (int m = 16; m >= 1; m >>= 1) v += __shfl_xor_sync(0xffffffffu, v, m);
+        if ((threadIdx.x & 31) == 0 && v) atomicAdd(dst + i, (u64)v);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// spatial index: counting sort of the generators into grid cells (replaces the KD-tree build, kd_tree.jl:27-158)
+// ------------------------------------------------------------------------------------------------------------
+template <int D>
+__global__ void k_cell_count(Dev<D> dv, const double* __restrict__ xs, int* __restrict__ cell_of, int* __restrict__ cell_cnt) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= dv.n) return;
+    double x[D];
+#pragma unroll
+    for (int k = 0; k < D; ++k) x[k] = xs[(size_t)i * D + k];
+    int c = cell_index<D>(dv, x);
+    cell_of[i] = c;
+    atomicAdd(cell_cnt + c, 1);
+}
+
+template <int D>
+__global__ void k_scatter(Dev<D> dv, const double* __restrict__ xs, const int* __restrict__ cell_of,
+                          const int* __restrict__ cell_start, int* __restrict__ cursor,
+                          double* __restrict__ x64, float* __restrict__ x32, int* __restrict__ perm) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= dv.n) return;
+    int c = cell_of[i];
+    int pos = cell_start[c] + atomicAdd(cursor + c, 1);
+    perm[pos] = i;
+#pragma unroll
+    for (int k = 0; k < D; ++k) {
+        double v = xs[(size_t)i * D + k];
+        x64[(size_t)pos * D + k] = v;
+        x32[(size_t)pos * D + k] = (float)(v - dv.lo[k]);
+    }
+}
+
+// deterministic order inside a cell: sort each cell's entries by caller id (cells hold a handful of points)
+template <int D>
+__global__ void k_cell_sort(Dev<D> dv, const double* __restrict__ xs, const int* __restrict__ cell_start, int ncells,
+                            double* __restrict__ x64, float* __restrict__ x32, int* __restrict__ perm) {
+    int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= ncells) return;
+    int a = cell_start[c], b = cell_start[c + 1];
+    for (int i = a + 1; i < b; ++i) {
+        int key = perm[i];
+        int j = i - 1;
+        while (j >= a && perm[j] > key) { perm[j + 1] = perm[j]; --j; }
+        perm[j + 1] = key;
+    }
+    for (int i = a; i < b; ++i) {
+        int o = perm[i];
+#pragma unroll
+        for (int k = 0; k < D; ++k) {
+            double v = xs[(size_t)o * D + k];
+            x64[(size_t)i * D + k] = v;
+            x32[(size_t)i * D + k] = (float)(v - dv.lo[k]);
+        }
+    }
+}
+
+// active[g] = 1 for the sorted positions of this context's slab (parallelmesh.jl:52-87) or of the Iter cells
+__global__ void k_fill_active_range(unsigned char* active, int n, int lo, int hi) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) active[i] = (i >= lo && i < hi) ? 1 : 0;
+}
+__global__ void k_inverse_perm(const int* __restrict__ perm, int* __restrict__ inv, int n) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) inv[perm[i]] = i;
+}
+__global__ void k_mark_cells(const long long* __restrict__ cells, long long ncells, const int* __restrict__ inv,
+                             unsigned char* active, int n) {
+    long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (i < ncells) { long long c = cells[i] - 1; if (c >= 0 && c < n) active[inv[c]] = 1; }
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// seeding and frontier rounds
+// ------------------------------------------------------------------------------------------------------------
+template <int D, int G>
+__global__ void __launch_bounds__(128) k_seed(Dev<D> dv, const int* __restrict__ seeds, int nseeds, int stride,
+                                              u32* q_out, u32* q_count, u32 q_cap) {
+    TileDev<G> tile;
+    LocalStats ls = {};
+    const int tiles_per_block = blockDim.x / G;
+    const int ntiles = gridDim.x * tiles_per_block;
+    for (int it = blockIdx.x * tiles_per_block + threadIdx.x / G; it < nseeds; it += ntiles) {
+        int start = seeds ? seeds[it] : it * stride;
+        if (start < dv.n && dv.active[start]) seed_item<D, TileDev<G> >(dv, tile, start, q_out, q_count, q_cap, ls);
+    }
+    flush_stats(ls, dv.ctr);
+}
+
+template <int D, int G>
+__global__ void __launch_bounds__(128) k_expand(Dev<D> dv, const u32* __restrict__ q_in, const u32* __restrict__ n_in_ptr,
+                                                u32* q_out, u32* q_count, u32 q_cap) {
+    TileDev<G> tile;
+    LocalStats ls = {};
+    const u32 n_in = min(*n_in_ptr, q_cap);
+    const u32 tiles_per_block = blockDim.x / G;
+    const u32 ntiles = gridDim.x * tiles_per_block;
+    for (u32 it = blockIdx.x * tiles_per_block + threadIdx.x / G; it < n_in; it += ntiles)
+        expand_item<D, TileDev<G> >(dv, tile, q_in[it], q_out, q_count, q_cap, ls);
+    flush_stats(ls, dv.ctr);
+}
+
+// cells of this context that still have no vertex (sysvoronoi.jl:416-429: they get their own descent)
+template <int D>
+__global__ void k_unseeded(Dev<D> dv, int* list, u32* count) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= dv.n) return;
+    if (dv.active[i] && !dv.has_vertex[i]) list[atomicAdd(count, 1u)] = i;
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// finalize: caller numbering, canonical coordinates, packed sort keys
+// ------------------------------------------------------------------------------------------------------------
+// one thread per stored record; dead records (lost insertion races) are skipped
+template <int D>
+__global__ void k_final_rows(Dev<D> dv, const int* __restrict__ perm, u32 nrec, int bits,
+                             long long* __restrict__ out_sig, double* __restrict__ out_r,
+                             u64* __restrict__ key_hi, u64* __restrict__ key_lo, u32* __restrict__ out_count,
+                             double* __restrict__ max_var) {
+    u32 v = blockIdx.x * blockDim.x + threadIdx.x;
+    if (v >= nrec) return;
+    const int* s = dv.vsig + (size_t)v * (D + 1);
+    if (s[0] < 0) return;
+    int in[D + 1];
+    long long og[D + 1];
+#pragma unroll
+    for (int k = 0; k < D + 1; ++k) { in[k] = s[k]; og[k] = (in[k] < dv.n) ? (long long)perm[in[k]] : (long long)in[k]; }
+    // sort by caller id (insertion sort network, D + 1 <= 7)
+#pragma unroll
+    for (int i = 1; i < D + 1; ++i) {
+#pragma unroll
+        for (int j = i; j > 0; --j) {
+            if (og[j - 1] > og[j]) {
+                long long t = og[j]; og[j] = og[j - 1]; og[j - 1] = t;
+                int ti = in[j]; in[j] = in[j - 1]; in[j - 1] = ti;
+            }
+        }
+    }
+    double r[D];
+    double var = canonical_vertex<D>(dv, in, r);
+    u32 pos = atomicAdd(out_count, 1u);
+    u64 hi = 0, lo = 0;
+#pragma unroll
+    for (int k = 0; k < D + 1; ++k) {
+        out_sig[(size_t)pos * (D + 1) + k] = og[k] + 1;
+        // 128-bit key = concatenation of the ids, first id most significant
+        hi = (hi << bits) | (lo >> (64 - bits));
+        lo = (lo << bits) | (u64)og[k];
+    }
+#pragma unroll
+    for (int k = 0; k < D; ++k) out_r[(size_t)pos * D + k] = r[k];
+    key_hi[pos] = hi; key_lo[pos] = lo;
+    if (var > 1e-18) atomicMax(reinterpret_cast<unsigned long long*>(max_var), (unsigned long long)__double_as_longlong(var));
+}
+
+__global__ void k_iota(u32* a, u32 n) {
+    u32 i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) a[i] = i;
+}
+__global__ void k_gather_u64(const u64* __restrict__ src, const u32* __restrict__ idx, u64* __restrict__ dst, u32 n) {
+    u32 i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) dst[i] = src[idx[i]];
+}
+template <int D>
+__global__ void k_gather_rows(const long long* __restrict__ sig_in, const double* __restrict__ r_in, const u32* __restrict__ idx,
+                              long long* __restrict__ sig_out, double* __restrict__ r_out, u32 n) {
+    u32 i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    u32 s = idx[i];
+#pragma unroll
+    for (int k = 0; k < D + 1; ++k) sig_out[(size_t)i * (D + 1) + k] = sig_in[(size_t)s * (D + 1) + k];
+#pragma unroll
+    for (int k = 0; k < D; ++k) r_out[(size_t)i * D + k] = r_in[(size_t)s * D + k];
+}
+
+// unbounded edges in caller numbering (pushray!, abstractmesh.jl:191; node = exploring cell = smallest id of the edge)
+template <int D>
+__global__ void k_final_rays(Dev<D> dv, const int* __restrict__ perm, u32 nrays,
+                             long long* __restrict__ edge, double* __restrict__ base, double* __restrict__ dir, long long* __restrict__ node) {
+    u32 i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nrays) return;
+    u32 it = dv.ray_item[i];
+    u32 v = it >> 3; int kd = it & 7;
+    long long e[D];
+    int c = 0;
+    for (int k = 0; k < D + 1; ++k) {
+        if (k == kd) continue;
+        int id = dv.vsig[(size_t)v * (D + 1) + k];
+        e[c++] = ((id < dv.n) ? (long long)perm[id] : (long long)id) + 1;
+    }
+    for (int a = 1; a < D; ++a) { long long key = e[a]; int b = a - 1; while (b >= 0 && e[b] > key) { e[b + 1] = e[b]; --b; } e[b + 1] = key; }
+    for (int k = 0; k < D; ++k) {
+        edge[(size_t)i * D + k] = e[k];
+        base[(size_t)i * D + k] = dv.vr[(size_t)v * D + k];
+        dir[(size_t)i * D + k] = dv.ray_u[(size_t)i * D + k];
+    }
+    node[i] = e[0];
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// neighbour lists (neighbors_of_cell_new, neighbors.jl:219-262): set of unordered id pairs -> CSR
+// ------------------------------------------------------------------------------------------------------------
+template <int D>
+__global__ void k_pairs(const long long* __restrict__ sig, u32 nv, long long n, u64* __restrict__ ptab, u64 pmask,
+                        u32* __restrict__ deg, u32* __restrict__ flags) {
+    u32 v = blockIdx.x * blockDim.x + threadIdx.x;
+    if (v >= nv) return;
+    long long s[D + 1];
+#pragma unroll
+    for (int k = 0; k < D + 1; ++k) s[k] = sig[(size_t)v * (D + 1) + k];
+#pragma unroll
+    for (int i = 0; i < D + 1; ++i) {
+#pragma unroll
+        for (int j = i + 1; j < D + 1; ++j) {
+            if (s[i] > n) continue;                       // both are planes
+            u64 key = ((u64)s[i] << 32) | (u64)s[j];      // 1-based ids: key != 0
+            u64 slot = mix64(key) & pmask;
+            for (u32 probe = 0;; ++probe) {
+                u64 cur = __ldcg(ptab + slot);
+                if (cur == key) break;
+                if (cur == 0) {
+                    cur = atomicCAS(ptab + slot, 0ULL, key);
+                    if (cur == 0) {
+                        atomicAdd(deg + (s[i] - 1), 1u);
+                        if (s[j] <= n) atomicAdd(deg + (s[j] - 1), 1u);
+                        break;
+                    }
+                    if (cur == key) break;
+                }
+                slot = (slot + 1) & pmask;
+                if (probe > pmask) { atomicOr(flags, 8u); break; }
+            }
+        }
+    }
+}
+
+__global__ void k_pair_fill(const u64* __restrict__ ptab, u64 nslots, long long n, const long long* __restrict__ off,
+                            u32* __restrict__ cursor, long long* __restrict__ ids) {
+    u64 i = blockIdx.x * (u64)blockDim.x + threadIdx.x;
+    if (i >= nslots) return;
+    u64 key = ptab[i];
+    if (key == 0) return;
+    long long a = (long long)(key >> 32), b = (long long)(key & 0xffffffffULL);
+    ids[off[a - 1] + atomicAdd(cursor + (a - 1), 1u)] = b;
+    if (b <= n) ids[off[b - 1] + atomicAdd(cursor + (b - 1), 1u)] = a;
+}
+
+__global__ void k_sort_lists(const long long* __restrict__ off, long long* __restrict__ ids, long long n) {
+    long long c = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (c >= n) return;
+    long long a = off[c], b = off[c + 1];
+    for (long long i = a + 1; i < b; ++i) {
+        long long key = ids[i];
+        long long j = i - 1;
+        while (j >= a && ids[j] > key) { ids[j + 1] = ids[j]; --j; }
+        ids[j + 1] = key;
+    }
+}
+
+__global__ void k_u32_to_i64(const u32* __restrict__ a, long long* __restrict__ b, long long n) {
+    long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (i < n) b[i] = a[i];
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// multi-GPU merge: dedup of gathered rows (sorted caller ids, 1-based) by a row hash set
+// ------------------------------------------------------------------------------------------------------------
+template <int D>
+__global__ void k_merge_rows(const long long* __restrict__ sig_in, const double* __restrict__ r_in, u64 count, int bits,
+                             u64* __restrict__ tab, u64 mask, long long* __restrict__ sig_out, double* __restrict__ r_out,
+                             u64* __restrict__ key_hi, u64* __restrict__ key_lo, u32* __restrict__ out_count) {
+    u64 i = blockIdx.x * (u64)blockDim.x + threadIdx.x;
+    if (i >= count) return;
+    long long s[D + 1];
+    u64 h = 0x9e3779b97f4a7c15ULL;
+#pragma unroll
+    for (int k = 0; k < D + 1; ++k) { s[k] = sig_in[i * (D + 1) + k]; h = (h ^ (u64)s[k]) * 0x100000001b3ULL + 0x632be59bd9b4e019ULL; }
+    h = mix64(h);
+    u64 slot = h & mask;
+    for (;;) {
+        u64 cur = __ldcg(tab + slot);
+        if (cur == 0) {
+            cur = atomicCAS(tab + slot, 0ULL, i + 1);
+            if (cur == 0) break;                          // this row represents its signature
+        }
+        const long long* o = sig_in + (cur - 1) * (D + 1);
+        bool eq = true;
+#pragma unroll
+        for (int k = 0; k < D + 1; ++k) eq &= (o[k] == s[k]);
+        if (eq) return;                                   // duplicate found by another rank
+        slot = (slot + 1) & mask;
+    }
+    u32 pos = atomicAdd(out_count, 1u);
+    u64 hi = 0, lo = 0;
+#pragma unroll
+    for (int k = 0; k < D + 1; ++k) {
+        sig_out[(size_t)pos * (D + 1) + k] = s[k];
+        hi = (hi << bits) | (lo >> (64 - bits));
+        lo = (lo << bits) | (u64)(s[k] - 1);
+    }
+#pragma unroll
+    for (int k = 0; k < D; ++k) r_out[(size_t)pos * D + k] = r_in[i * D + k];
+    key_hi[pos] = hi; key_lo[pos] = lo;
+}
+
+}  // namespace hvb

@@ -1,0 +1,143 @@
+/* hvb200.h -- C ABI of libhvb200.so, the B200 (sm_100a) raycast vertex-search backend.
+ *
+ * This is the drop-in boundary for ONE path of HighVoronoi.jl: voronoi(mesh; Iter, searcher)
+ * (src/sysvoronoi.jl:21), i.e. the edge walk that grows the Voronoi vertex set.  The reference is pure Julia
+ * and has no FFI today; the entry points below are what a Julia `ccall` shim binds (julia/HighVoronoiB200.jl,
+ * INTEGRATION.md).  Each entry point names the reference interface it replaces.
+ *
+ * Conventions
+ *  - plain pointers and sizes only; no C++ types, no exceptions, no callbacks cross this boundary;
+ *  - generator ids are 1-based Int64 like the reference; boundary plane p (1-based) appears in a vertex
+ *    signature as n+p (docs/src/man/short.md:41-42);
+ *  - every call returns 0 or a negative HVB_E* code; hvb_last_error() gives the message;
+ *  - there is NO CPU fallback: without a usable CUDA device hvb_create fails with HVB_ENOGPU;
+ *  - a context is single-caller; distinct contexts are independent.
+ */
+#ifndef HVB200_H
+#define HVB200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define HVB_OK            0
+#define HVB_EINVAL       -1   /* bad argument (dimension, sizes, points outside the domain, ...) */
+#define HVB_ECUDA        -2   /* CUDA runtime error */
+#define HVB_ENOGPU       -3   /* no CUDA device: the library never computes on the host */
+#define HVB_ENOMEM       -4   /* device allocation failed / capacity exhausted after retries */
+#define HVB_EDEGENERATE  -5   /* a vertex with more than dim+1 cospherical generators was met (edgeiterate.jl path) */
+#define HVB_ESTATE       -6   /* call sequence error (fetch before search, ...) */
+#define HVB_EINCOMPLETE  -7   /* a descent failed: some cell has no vertex (raycast.jl:54-59 analogue) */
+
+#define HVB_MAX_DIM     6
+#define HVB_MAX_PLANES  32
+
+typedef struct hvb_ctx hvb_ctx;
+
+/* Search settings: RaycastParameter (src/raycast-types.jl:312-324) plus backend knobs. */
+typedef struct hvb_params {
+    /* the five tolerances of the reference, defaults raycast-types.jl:226-230 */
+    double variance_tol;      /* 1e-15 : accepted relative variance of the d+1 squared radii */
+    double break_tol;         /* 1e-5  : above this a vertex is rejected                    */
+    double b_nodes_tol;       /* 1e-7                                                       */
+    double plane_tolerance;   /* 1e-12 : half-space slack  c = c1 + |c1| * plane_tolerance (raycast.jl:802-804) */
+    double ray_tol;           /* 1e-12                                                      */
+    int32_t method;           /* 0 RCStandard/RCNonGeneralHP, 1 RCOriginal, 2 RCCombined, 3 RCNonGeneralFast
+                                 (raycast-types.jl:244-284): every value runs the same exact min-t kernel */
+    int32_t device;           /* CUDA device ordinal */
+    /* slab sharding (parallelmesh.jl:52-87): this context explores slab `rank` of `world` contiguous slabs of
+       the spatially sorted generator order; rank=0, world=1 explores everything */
+    int32_t rank;
+    int32_t world;
+    int32_t fp32_filter;      /* 1: FP32 candidate filter + FP64 verification (default); 0: FP64 only */
+    int32_t on_degenerate;    /* 0: hvb_search returns HVB_EDEGENERATE (default); 1: count and continue */
+    int32_t points_per_cell;  /* target occupancy of a uniform-grid cell; 0 = auto */
+    int32_t seed_stride;      /* one descent seed every `seed_stride` generators; 0 = auto */
+    int32_t sort_output;      /* 1: vertices are returned in lexicographic order of their signature (default) */
+    int32_t tile_size;        /* lanes cooperating on one frontier entry: 4, 8, 16 or 32; 0 = auto by dimension */
+    int64_t vertex_capacity;  /* 0 = estimate from lowerbound(d,d) (edgeiteratebase.jl:151); grows on demand */
+    double probe_scale;       /* first probe ball radius / circumradius of the origin vertex; 0 = auto */
+} hvb_params;
+
+typedef struct hvb_stats_t {
+    int64_t vertices;         /* distinct vertices found                                  */
+    int64_t rays;             /* unbounded edges (Boundary() without planes)              */
+    int64_t raycasts;         /* min-t queries issued (walks + descent steps)             */
+    int64_t duplicate_hits;   /* walks that re-found a known vertex                       */
+    int64_t closed_skips;     /* frontier entries dropped because the edge was closed     */
+    int64_t candidates_fp32;  /* generators run through the FP32 filter                   */
+    int64_t candidates_fp64;  /* generators re-evaluated in FP64                          */
+    int64_t rows_scanned;     /* grid rows visited                                        */
+    int64_t probe_stages;     /* probe balls grown                                        */
+    int64_t rounds;           /* frontier rounds                                          */
+    int64_t seeds;            /* descents                                                 */
+    int64_t degenerate;       /* near-tie winners (non-general position)                  */
+    int64_t kernel_launches;  /* kernels of this library launched by the last hvb_search  */
+    int64_t capacity_retries;
+    double  ms_build;         /* H2D + grid build                                         */
+    double  ms_search;        /* seeding + frontier rounds                                */
+    double  ms_finalize;      /* canonical coordinates, sort, neighbour lists             */
+    double  ms_expand_kernel; /* device time of the dominant kernel (walk/expand), summed */
+    int64_t expand_launches;
+    int64_t expand_items;     /* frontier entries processed by it                         */
+} hvb_stats_t;
+
+/* fills *p with the reference's defaults (RaycastParameter(Float64), raycast-types.jl:312-324) */
+void hvb_default_params(hvb_params* p);
+
+/* Replaces Raycast(xs; domain, options) (src/raycast.jl:26 -> RaycastIncircleSkip raycast-types.jl:412) together
+ * with the ExtendedTree / HVKDTree build (extended.jl:92, kd_tree.jl:27-158): copies the generators
+ * (n x dim, row-major = Vector{SVector{dim,Float64}}, voronoinodes.jl:14) and the boundary planes
+ * (boundary.jl:22-29: base point and outward normal per plane) to the device and builds the spatial index. */
+int hvb_create(hvb_ctx** out, int dim, int64_t n, const double* xs,
+               int nplanes, const double* plane_base, const double* plane_normal,
+               const hvb_params* params);
+
+/* Replaces voronoi(mesh; Iter, searcher) (src/sysvoronoi.jl:21 -> _voronoi :41/:50 -> __voronoi :152):
+ * cells = Iter (1-based, NULL = all cells); seed_sig/seed_r = vertices the mesh already holds
+ * (nseed rows of sig_stride ids, unused entries 0; the refinement callers meshrefine.jl:199-215 pass a
+ * non-empty mesh).  Blocks until the results are complete on the device. */
+int hvb_search(hvb_ctx* ctx, const int64_t* cells, int64_t ncells,
+               const int64_t* seed_sig, const double* seed_r, int64_t nseed, int sig_stride);
+
+/* sizes for the fetch calls; max_siglen is dim+1 (general position) */
+int hvb_counts(hvb_ctx* ctx, int64_t* nvert, int64_t* nrays, int64_t* max_siglen);
+
+/* Replaces the replay target push!(mesh, sig=>r) (src/abstractmesh.jl:111): sig = nvert x (dim+1) sorted
+ * 1-based ids, r = nvert x dim. */
+int hvb_fetch_vertices(hvb_ctx* ctx, int64_t* sig, double* r);
+
+/* Replaces pushray!(mesh, full_edge, r, u, _Cell) (src/abstractmesh.jl:191, sysvoronoi.jl:504-511). */
+int hvb_fetch_rays(hvb_ctx* ctx, int64_t* edge, double* base, double* dir, int64_t* node);
+
+/* Replaces neighbors_of_cell (src/neighbors.jl:214-262) for every cell: CSR, offsets has n+1 entries. */
+int hvb_neighbor_count(hvb_ctx* ctx, int64_t* total);
+int hvb_fetch_neighbors(hvb_ctx* ctx, int64_t* offsets, int64_t* ids);
+
+/* Zero-copy variants: pointers into page-locked host memory owned by the context, valid until the next
+ * hvb_search / hvb_destroy.  Layout as in hvb_fetch_vertices. */
+int hvb_view_vertices(hvb_ctx* ctx, const int64_t** sig, const double** r, int64_t* nvert);
+
+/* Multi-GPU exchange step (parallelmesh.jl's shared store becomes: local search -> all-gather -> merge).
+ * hvb_export_device copies this rank's vertices (int32 sig rows of dim+1 0-based caller ids, double r rows)
+ * into caller-provided DEVICE buffers of capacity `cap` rows; hvb_merge_device replaces the context's result
+ * by the deduplicated, sorted union of `count` gathered rows (device pointers).  The collective itself
+ * (NCCL all-gather) is issued by the host language between the two calls. */
+int hvb_export_device(hvb_ctx* ctx, void* sig_dev, void* r_dev, int64_t cap, int64_t* count);
+int hvb_merge_device(hvb_ctx* ctx, const void* sig_dev, const void* r_dev, int64_t count);
+
+/* rare_events / statistics.jl:132-143 analogue */
+int hvb_stats(hvb_ctx* ctx, hvb_stats_t* out);
+
+const char* hvb_last_error(hvb_ctx* ctx);   /* ctx may be NULL: message of the last failed hvb_create */
+void hvb_destroy(hvb_ctx* ctx);
+
+/* library build info: "hvb200 <version> sm_100a" */
+const char* hvb_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* HVB200_H */

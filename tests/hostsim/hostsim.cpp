@@ -1,0 +1,135 @@
+// hostsim.cpp -- DEBUGGING HARNESS (test infrastructure, never shipped, never a fallback).
+// Compiles the device algorithm of highvoronoi.jl_b200/csrc/hvb_core.cuh as plain host C++ with a one-lane
+// tile and drives it sequentially, so that its logic (grid traversal, FP32 filter bound, probe stages,
+// vertex/edge tables, descent) can be checked against the oracle in a container that has no GPU.
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <vector>
+#include <algorithm>
+#include "../../highvoronoi.jl_b200/csrc/hvb_host.hpp"
+
+using namespace hvb;
+
+struct SimResult {
+    int d; int64_t nv, nr;
+    std::vector<int64_t> sig; std::vector<double> r;
+    std::vector<int64_t> ray_edge;
+    Counters ctr;
+    int rounds;
+};
+
+template <int D>
+static SimResult* run(int64_t n, const double* xs, int P, const double* base, const double* normal,
+                      int ppc, double probe_scale, int fp32, int seed_stride) {
+    Dev<D> dv;
+    memset(&dv, 0, sizeof(dv));
+    dv.n = (int)n;
+    double blo[D], bhi[D];
+    for (int k = 0; k < D; ++k) { blo[k] = 1e300; bhi[k] = -1e300; }
+    for (int64_t i = 0; i < n; ++i)
+        for (int k = 0; k < D; ++k) { blo[k] = std::min(blo[k], xs[i * D + k]); bhi[k] = std::max(bhi[k], xs[i * D + k]); }
+    int64_t ncell = setup_grid<D>(dv, blo, bhi, n, ppc > 0 ? ppc : default_points_per_cell(D));
+    std::vector<int> cell(n), cstart(ncell + 1, 0), perm(n);
+    for (int64_t i = 0; i < n; ++i) { cell[i] = cell_index<D>(dv, xs + i * D); cstart[cell[i] + 1]++; }
+    for (int64_t c = 0; c < ncell; ++c) cstart[c + 1] += cstart[c];
+    { std::vector<int> cur(cstart.begin(), cstart.end() - 1); for (int64_t i = 0; i < n; ++i) perm[cur[cell[i]]++] = (int)i; }
+    std::vector<double> x64(n * D); std::vector<float> x32(n * D);
+    for (int64_t i = 0; i < n; ++i)
+        for (int k = 0; k < D; ++k) { x64[i * D + k] = xs[(int64_t)perm[i] * D + k]; x32[i * D + k] = (float)(x64[i * D + k] - dv.lo[k]); }
+    PlaneSet ps; memset(&ps, 0, sizeof(ps)); ps.P = P;
+    for (int p = 0; p < P; ++p) {
+        double nr = 0; for (int k = 0; k < D; ++k) nr += normal[p * D + k] * normal[p * D + k];
+        nr = sqrt(nr); double off = 0;
+        for (int k = 0; k < D; ++k) { ps.normal[p * 6 + k] = normal[p * D + k] / nr; off += ps.normal[p * 6 + k] * base[p * D + k]; }
+        ps.off[p] = off;
+    }
+    std::vector<unsigned char> active(n, 1), hasv(n, 0);
+    dv.cell_start = cstart.data(); dv.x32 = x32.data(); dv.x64 = x64.data(); dv.planes = &ps; dv.active = active.data();
+    dv.plane_tol = 1e-12; dv.probe_scale = probe_scale > 1.0 ? probe_scale : 1.3; dv.fp32_filter = fp32;
+    int64_t vcap = estimate_vertices(D, n, P) * 2;
+    std::vector<int> vsig(vcap * (D + 1)); std::vector<double> vr(vcap * D);
+    u32 vcount = 0;
+    u64 vts = next_pow2(2 * vcap), ets = next_pow2((u64)(vcap * (D + 1)));
+    std::vector<u64> vtab(vts, 0), etab(ets, 0);
+    u32 rcount = 0; u32 rcap = (u32)vcap;
+    std::vector<u32> ritem(rcap); std::vector<double> ru((size_t)rcap * D);
+    Counters ctr; memset(&ctr, 0, sizeof(ctr));
+    dv.vsig = vsig.data(); dv.vr = vr.data(); dv.vcount = &vcount; dv.vcap = (u32)vcap; dv.vtab = vtab.data(); dv.vmask = vts - 1;
+    dv.etab = etab.data(); dv.emask = ets - 1; dv.has_vertex = hasv.data();
+    dv.ray_item = ritem.data(); dv.ray_u = ru.data(); dv.ray_count = &rcount; dv.ray_cap = rcap; dv.ctr = &ctr;
+    u32 qcap = (u32)std::min<u64>(ets, 0xfffffff0u);
+    std::vector<u32> qa(qcap), qb(qcap);
+    u32 na = 0, nb = 0;
+    TileHost tile; LocalStats ls; memset(&ls, 0, sizeof(ls));
+    if (seed_stride <= 0) seed_stride = 16;
+    for (int64_t i = 0; i < n; i += seed_stride) seed_item<D, TileHost>(dv, tile, (int)i, qa.data(), &na, qcap, ls);
+    int rounds = 0;
+    for (;;) {
+        while (na > 0) {
+            nb = 0;
+            for (u32 i = 0; i < na; ++i) expand_item<D, TileHost>(dv, tile, qa[i], qb.data(), &nb, qcap, ls);
+            qa.swap(qb); na = nb; ++rounds;
+        }
+        // cells without any vertex get their own descent (sysvoronoi.jl:416-429)
+        for (int64_t i = 0; i < n; ++i) if (!hasv[i]) seed_item<D, TileHost>(dv, tile, (int)i, qa.data(), &na, qcap, ls);
+        if (na == 0) break;
+    }
+    SimResult* R = new SimResult(); R->d = D; R->rounds = rounds;
+    ctr.raycasts = ls.raycasts; ctr.dup_hits = ls.dup_hits; ctr.closed_skips = ls.closed_skips; ctr.cand32 = ls.cand32; ctr.cand64 = ls.cand64;
+    ctr.rows = ls.rows; ctr.stages = ls.stages; ctr.seeds = ls.seeds; ctr.degenerate = ls.degenerate; ctr.seed_fail = ls.seed_fail; ctr.dead = ls.dead;
+    R->ctr = ctr;
+    // finalize: caller ids, canonical order, canonical coordinates
+    struct Row { int64_t sig[7]; double r[6]; };
+    std::vector<Row> rows;
+    for (u32 v = 0; v < vcount; ++v) {
+        const int* s = &vsig[(size_t)v * (D + 1)];
+        if (s[0] < 0) continue;
+        std::pair<int64_t, int> o[D + 1];
+        for (int k = 0; k <= D; ++k) o[k] = std::make_pair(s[k] < n ? (int64_t)perm[s[k]] : (int64_t)s[k], s[k]);
+        std::sort(o, o + D + 1);
+        int cs[D + 1]; Row row;
+        for (int k = 0; k <= D; ++k) { cs[k] = o[k].second; row.sig[k] = o[k].first + 1; }
+        canonical_vertex<D>(dv, cs, row.r);
+        rows.push_back(row);
+    }
+    std::sort(rows.begin(), rows.end(), [](const Row& a, const Row& b) { return std::lexicographical_compare(a.sig, a.sig + D + 1, b.sig, b.sig + D + 1); });
+    R->nv = (int64_t)rows.size();
+    for (auto& row : rows) { for (int k = 0; k <= D; ++k) R->sig.push_back(row.sig[k]); for (int k = 0; k < D; ++k) R->r.push_back(row.r[k]); }
+    R->nr = rcount;
+    for (u32 i = 0; i < rcount; ++i) {
+        u32 v = ritem[i] >> 3; int kd = ritem[i] & 7;
+        std::vector<int64_t> e;
+        for (int k = 0; k <= D; ++k) if (k != kd) { int id = vsig[(size_t)v * (D + 1) + k]; e.push_back((id < n ? perm[id] : id) + 1); }
+        std::sort(e.begin(), e.end());
+        R->ray_edge.insert(R->ray_edge.end(), e.begin(), e.end());
+    }
+    return R;
+}
+
+extern "C" {
+void* hostsim_run(int dim, int64_t n, const double* xs, int P, const double* base, const double* normal,
+                  int ppc, double probe_scale, int fp32, int seed_stride) {
+    switch (dim) {
+        case 2: return run<2>(n, xs, P, base, normal, ppc, probe_scale, fp32, seed_stride);
+        case 3: return run<3>(n, xs, P, base, normal, ppc, probe_scale, fp32, seed_stride);
+        case 4: return run<4>(n, xs, P, base, normal, ppc, probe_scale, fp32, seed_stride);
+        case 5: return run<5>(n, xs, P, base, normal, ppc, probe_scale, fp32, seed_stride);
+        case 6: return run<6>(n, xs, P, base, normal, ppc, probe_scale, fp32, seed_stride);
+    }
+    return 0;
+}
+void hostsim_counts(void* h, int64_t* nv, int64_t* nr, int64_t* ctr /*12*/) {
+    SimResult* R = (SimResult*)h; *nv = R->nv; *nr = R->nr;
+    const Counters& c = R->ctr;
+    int64_t v[12] = {(int64_t)c.raycasts, (int64_t)c.dup_hits, (int64_t)c.closed_skips, (int64_t)c.cand32, (int64_t)c.cand64, (int64_t)c.rows,
+                     (int64_t)c.stages, (int64_t)c.seeds, (int64_t)c.degenerate, (int64_t)c.seed_fail, (int64_t)c.dead, (int64_t)R->rounds};
+    memcpy(ctr, v, sizeof(v));
+}
+void hostsim_fetch(void* h, int64_t* sig, double* r, int64_t* ray_edge) {
+    SimResult* R = (SimResult*)h;
+    memcpy(sig, R->sig.data(), R->sig.size() * 8); memcpy(r, R->r.data(), R->r.size() * 8);
+    memcpy(ray_edge, R->ray_edge.data(), R->ray_edge.size() * 8);
+}
+void hostsim_free(void* h) { delete (SimResult*)h; }
+}

@@ -1,0 +1,43 @@
+"""ctypes wrapper of the CPU debugging harness (tests/hostsim/hostsim.cpp).  Test infrastructure only."""
+import ctypes, os, subprocess
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_SO = os.path.join(_HERE, "libhostsim.so")
+CTR = ("raycasts", "dup_hits", "closed_skips", "cand32", "cand64", "rows", "stages", "seeds", "degenerate", "seed_fail", "dead", "rounds")
+
+
+def build():
+    src = os.path.join(_HERE, "hostsim.cpp")
+    core = os.path.join(_HERE, "..", "..", "highvoronoi.jl_b200", "csrc", "hvb_core.cuh")
+    host = os.path.join(_HERE, "..", "..", "highvoronoi.jl_b200", "csrc", "hvb_host.hpp")
+    newest = max(os.path.getmtime(f) for f in (src, core, host))
+    if not os.path.exists(_SO) or os.path.getmtime(_SO) < newest:
+        subprocess.check_call(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-Wno-unknown-pragmas", "-o", _SO, src])
+    return _SO
+
+
+def run(xs, base=None, normal=None, ppc=0, probe_scale=0.0, fp32=1, seed_stride=0):
+    L = ctypes.CDLL(build())
+    L.hostsim_run.restype = ctypes.c_void_p
+    L.hostsim_run.argtypes = [ctypes.c_int, ctypes.c_int64, ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p,
+                              ctypes.c_int, ctypes.c_double, ctypes.c_int, ctypes.c_int]
+    for f in ("hostsim_counts", "hostsim_fetch", "hostsim_free"):
+        getattr(L, f).restype = None
+    L.hostsim_counts.argtypes = [ctypes.c_void_p] * 4
+    L.hostsim_fetch.argtypes = [ctypes.c_void_p] * 4
+    L.hostsim_free.argtypes = [ctypes.c_void_p]
+    xs = np.ascontiguousarray(xs, dtype=np.float64)
+    n, d = xs.shape
+    if base is None:
+        base = np.zeros((0, d)); normal = np.zeros((0, d))
+    base = np.ascontiguousarray(base, dtype=np.float64); normal = np.ascontiguousarray(normal, dtype=np.float64)
+    P = lambda a: a.ctypes.data_as(ctypes.c_void_p)
+    h = L.hostsim_run(d, n, P(xs), base.shape[0], P(base), P(normal), ppc, probe_scale, fp32, seed_stride)
+    nv, nr = ctypes.c_int64(), ctypes.c_int64()
+    ctr = np.zeros(12, dtype=np.int64)
+    L.hostsim_counts(h, ctypes.byref(nv), ctypes.byref(nr), P(ctr))
+    sig = np.empty((nv.value, d + 1), dtype=np.int64); r = np.empty((nv.value, d)); re = np.empty((nr.value, d), dtype=np.int64)
+    L.hostsim_fetch(h, P(sig), P(r), P(re))
+    L.hostsim_free(h)
+    return dict(sig=sig, r=r, ray_edge=re, stats=dict(zip(CTR, ctr.tolist())))

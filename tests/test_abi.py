@@ -1,0 +1,71 @@
+"""CPU tests of the drop-in boundary: the library loads, exports every declared symbol, and never computes on the host."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+from conftest import ROOT, cuda_available
+
+
+def declared_symbols():
+    src = open(os.path.join(ROOT, "include", "hvb200.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(hvb_[a-z_]+)\s*\(", src)))
+
+
+def test_library_exports_every_declared_symbol(hvb):
+    L = hvb._abi.lib()
+    names = declared_symbols()
+    assert len(names) >= 15
+    for name in names:
+        assert hasattr(L, name), name
+    assert set(hvb._abi.EXPORTS) == set(names)
+    assert b"sm_100a" in L.hvb_version()
+
+
+def test_default_params_match_reference(hvb):
+    p = hvb.RaycastParameter()
+    # raycast-types.jl:226-230
+    assert (p.variance_tol, p.break_tol, p.b_nodes_tol, p.plane_tolerance, p.ray_tol) == (1e-15, 1e-5, 1e-7, 1e-12, 1e-12)
+    assert p.method == hvb.RCStandard == hvb.RCNonGeneralHP and p.world == 1 and p.fp32_filter == 1 and p.sort_output == 1
+    assert ctypes.sizeof(hvb._abi.hvb_params) == 5 * 8 + 10 * 4 + 8 + 8
+    assert ctypes.sizeof(hvb._abi.hvb_stats_t) == 20 * 8
+
+
+def test_argument_errors(hvb):
+    L = hvb._abi.lib()
+    ctx = ctypes.c_void_p()
+    xs = np.random.default_rng(0).random((3, 3))
+    # sysvoronoi.jl:25-27: "There are not enough points to create a Voronoi tessellation"
+    rc = L.hvb_create(ctypes.byref(ctx), 3, 3, xs.ctypes.data_as(ctypes.c_void_p), 0, None, None, None)
+    assert rc == hvb._abi.HVB_EINVAL and b"not enough points" in L.hvb_last_error(None)
+    rc = L.hvb_create(ctypes.byref(ctx), 7, 100, xs.ctypes.data_as(ctypes.c_void_p), 0, None, None, None)
+    assert rc == hvb._abi.HVB_EINVAL
+    assert L.hvb_search(None, None, 0, None, None, 0, 0) == hvb._abi.HVB_EINVAL
+
+
+def test_cuboid_planes_match_reference_layout(hvb):
+    # boundary.jl:510-534: plane 2i-1 = upper face (normal +e_i, base offset + dim_i e_i), plane 2i = lower face
+    b = hvb.cuboid(3, periodic=[])
+    assert len(b) == 6
+    assert np.array_equal(b.normal[0], [1, 0, 0]) and np.array_equal(b.base[0], [1, 0, 0])
+    assert np.array_equal(b.normal[1], [-1, 0, 0]) and np.array_equal(b.base[1], [0, 0, 0])
+    assert hvb.cuboid(2).periodic == (1, 2)
+
+
+@pytest.mark.skipif(cuda_available(), reason="a CUDA device is present")
+def test_no_cpu_fallback(hvb):
+    with pytest.raises(hvb.HVBError) as e:
+        hvb.Raycast(np.random.default_rng(0).random((50, 3)))
+    assert e.value.code == hvb._abi.HVB_ENOGPU
+
+
+def test_product_does_not_touch_the_oracle():
+    pkg = os.path.join(ROOT, "highvoronoi.jl_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".hpp", ".h")):
+                text = open(os.path.join(dirpath, f)).read()
+                assert "hv_oracle" not in text and "qhull_oracle" not in text and "hostsim" not in text.replace("tests/hostsim", ""), f

@@ -1,0 +1,158 @@
+"""GPU parity tests: the CUDA path, called through the C ABI (ctypes), against the oracle on the same seeded
+inputs, against the committed golden vectors, and -- at BASELINE.json's full sizes -- through size-independent
+properties.  Bar: bit-exact signatures and neighbour lists, coordinates within 1e-10 relative."""
+import glob
+import os
+
+import numpy as np
+import pytest
+
+import qhull_oracle
+from util import assert_same_mesh, empty_ball_violations, neighbors_from_sig, points
+
+pytestmark = pytest.mark.gpu
+COORD_TOL = 1e-10          # north_star: "Vertex coordinates must agree within 1e-10 relative"
+GOLDEN = sorted(glob.glob(os.path.join(os.path.dirname(__file__), "golden", "*.npz")))
+
+
+def run_gpu(hvb, xs, bounded=True, **settings):
+    d = xs.shape[1]
+    dom = hvb.cuboid(d, periodic=[]) if bounded else hvb.Boundary()
+    s = hvb.Raycast(xs, domain=dom, options=hvb.RaycastParameter(**settings))
+    mesh, _ = hvb.voronoi(xs, searcher=s)
+    return mesh, s
+
+
+@pytest.mark.parametrize("path", GOLDEN, ids=[os.path.basename(p)[:-4] for p in GOLDEN])
+def test_golden_vectors(hvb, path):
+    g = np.load(path)
+    dom = hvb.Boundary(g["base"], g["normal"]) if g["base"].shape[0] else hvb.Boundary()
+    s = hvb.Raycast(g["xs"], domain=dom)
+    mesh, _ = hvb.voronoi(g["xs"], searcher=s)
+    assert_same_mesh(mesh.sig, mesh.r, g["sig"], g["r"], g["xs"], COORD_TOL)
+    assert sorted(map(tuple, mesh.ray_edge.tolist())) == sorted(map(tuple, g["ray_edge"].tolist()))
+    off, ids = mesh.neighbors()
+    assert np.array_equal(off, g["nb_off"]) and np.array_equal(ids, g["nb_ids"])
+
+
+# configs[0] of BASELINE.json (C1) and reduced sizes of C3/C4/C5 that the oracle finishes in seconds
+@pytest.mark.parametrize("d,n,bounded", [(3, 1000, True), (3, 1000, False), (2, 20000, True), (2, 5000, False),
+                                          (4, 2000, True), (4, 500, False), (5, 1000, True), (5, 300, False),
+                                          (6, 300, True), (6, 120, False), (3, 20000, True)])
+def test_matches_oracle(hvb, oracle, d, n, bounded):
+    xs = points(n, d, 1000 + 10 * d + int(bounded))
+    if bounded:
+        base, normal = qhull_oracle.cuboid(d)
+        o = oracle.run(xs, base, normal)
+    else:
+        o = oracle.run(xs)
+    mesh, s = run_gpu(hvb, xs, bounded)
+    assert_same_mesh(mesh.sig, mesh.r, o["sig"], o["r"], xs, COORD_TOL)
+    assert sorted(map(tuple, mesh.ray_edge.tolist())) == sorted(map(tuple, o["ray_edge"].tolist()))
+    off, ids = mesh.neighbors()
+    assert np.array_equal(off, o["nb_off"]) and np.array_equal(ids, o["nb_ids"])
+    st = s.stats()
+    assert st["degenerate"] == 0 and st["vertices"] == len(o["sig"])
+
+
+@pytest.mark.parametrize("seed", [0, 1, 2])
+def test_c1_seeds(hvb, oracle, seed):
+    xs = points(1000, 3, seed)
+    base, normal = qhull_oracle.cuboid(3)
+    o = oracle.run(xs, base, normal)
+    mesh, _ = run_gpu(hvb, xs, True)
+    assert_same_mesh(mesh.sig, mesh.r, o["sig"], o["r"], xs, COORD_TOL)
+
+
+def test_matches_qhull_directly(hvb):
+    """independent of the restatement: Delaunay circumcentres + per-cell half-space intersection"""
+    xs = points(600, 3, 77)
+    base, normal = qhull_oracle.cuboid(3)
+    q = qhull_oracle.bounded(xs, base, normal)
+    mesh, _ = run_gpu(hvb, xs, True)
+    got = [tuple(s) for s in mesh.sig.tolist()]
+    assert set(got) == set(q) and len(got) == len(q)
+    assert max(np.abs(mesh.r[k] - q[s]).max() for k, s in enumerate(got)) < 1e-11
+
+
+def test_fp32_filter_equals_fp64_only(hvb):
+    xs = points(30000, 3, 3)
+    a, sa = run_gpu(hvb, xs, True, fp32_filter=1)
+    b, sb = run_gpu(hvb, xs, True, fp32_filter=0)
+    assert np.array_equal(a.sig, b.sig) and np.array_equal(a.r, b.r)
+    assert sa.stats()["candidates_fp64"] < sb.stats()["candidates_fp64"]
+
+
+def test_deterministic_and_knob_independent(hvb):
+    xs = points(20000, 3, 4)
+    a, _ = run_gpu(hvb, xs, True)
+    b, _ = run_gpu(hvb, xs, True)
+    c, _ = run_gpu(hvb, xs, True, points_per_cell=6, seed_stride=3, probe_scale=2.0)
+    assert np.array_equal(a.sig, b.sig) and np.array_equal(a.r, b.r)       # bitwise, run to run
+    assert np.array_equal(a.sig, c.sig) and np.array_equal(a.r, c.r)       # canonical coordinates
+
+
+def test_iter_subset_finds_all_vertices_of_the_cells(hvb, oracle):
+    xs = points(3000, 3, 8)
+    base, normal = qhull_oracle.cuboid(3)
+    o = oracle.run(xs, base, normal)
+    cells = np.arange(1, 301)
+    s = hvb.Raycast(xs, domain=hvb.cuboid(3, periodic=[]))
+    mesh, _ = hvb.voronoi(xs, searcher=s, Iter=cells)
+    want = {tuple(r) for r in o["sig"].tolist() if any(1 <= g <= 300 for g in r)}
+    got = {tuple(r) for r in mesh.sig.tolist()}
+    assert want <= got <= {tuple(r) for r in o["sig"].tolist()}
+
+
+def test_slab_union_equals_full(hvb, oracle):
+    """the multi-GPU decomposition on one device: the union of the slab searches is the full vertex set"""
+    xs = points(6000, 3, 10)
+    base, normal = qhull_oracle.cuboid(3)
+    o = oracle.run(xs, base, normal)
+    rows = set()
+    for rank in range(4):
+        s = hvb.Raycast(xs, domain=hvb.cuboid(3, periodic=[]), options=hvb.RaycastParameter(threading=hvb.B200Thread(0, rank, 4)))
+        mesh, _ = hvb.voronoi(xs, searcher=s)
+        rows |= {tuple(r) for r in mesh.sig.tolist()}
+    assert rows == {tuple(r) for r in o["sig"].tolist()}
+
+
+def test_points_outside_domain_are_rejected(hvb):
+    xs = points(100, 3, 0)
+    xs[5, 1] = 1.5
+    with pytest.raises(hvb.HVBError) as e:
+        hvb.Raycast(xs, domain=hvb.cuboid(3, periodic=[]))
+    assert e.value.code == hvb._abi.HVB_EINVAL and "does not lie in the domain" in str(e.value)
+
+
+def test_degenerate_input_is_reported(hvb):
+    g = np.stack(np.meshgrid(*[np.arange(6.0)] * 3, indexing="ij"), -1).reshape(-1, 3) / 6 + 1 / 12
+    with pytest.raises(hvb.HVBError) as e:
+        run_gpu(hvb, g, True)
+    assert e.value.code == hvb._abi.HVB_EDEGENERATE
+
+
+# ---- BASELINE.json full sizes: properties that need no oracle run --------------------------------------------
+@pytest.mark.parametrize("d,n,vpp_lo,vpp_hi", [(3, 100000, 6.4, 7.1), (2, 1000000, 1.95, 2.05), (5, 50000, 60, 190)])
+def test_full_size_properties(hvb, d, n, vpp_lo, vpp_hi):
+    xs = points(n, d, 0)
+    mesh, s = run_gpu(hvb, xs, True)
+    V = mesh.sig.shape[0]
+    assert vpp_lo <= V / n <= vpp_hi, V / n
+    # rows sorted, unique, every row sorted and holding at least one real generator
+    assert (np.diff(mesh.sig, axis=1) > 0).all() and (mesh.sig[:, 0] <= n).all()
+    key = mesh.sig[1:] != mesh.sig[:-1]
+    first = key.argmax(axis=1)
+    assert key.any(axis=1).all()
+    assert (np.take_along_axis(mesh.sig[1:], first[:, None], 1) > np.take_along_axis(mesh.sig[:-1], first[:, None], 1)).all()
+    # verify_vertex (raycast.jl:477-502) on a sample: empty ball, equidistance; all vertices inside the domain
+    assert empty_ball_violations(mesh.sig, mesh.r, xs, sample=1500) == 0
+    assert mesh.r.min() >= -1e-12 and mesh.r.max() <= 1 + 1e-12
+    # every cell has vertices, and the neighbour lists equal the host recomputation
+    assert len(np.unique(mesh.sig[mesh.sig <= n])) == n
+    if d <= 3:
+        off, ids = mesh.neighbors()
+        off2, ids2 = neighbors_from_sig(mesh.sig, n)
+        assert np.array_equal(off, off2) and np.array_equal(ids, ids2)
+    st = s.stats()
+    assert st["degenerate"] == 0 and st["capacity_retries"] == 0

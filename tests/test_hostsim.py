@@ -1,0 +1,50 @@
+"""CPU check of the device algorithm's logic: hvb_core.cuh compiled as host C++ with a one-lane tile
+(tests/hostsim) against the oracle.  This is a debugging aid for a container without a GPU; the parity tests
+proper are tests/test_gpu_parity.py."""
+import numpy as np
+import pytest
+
+import hostsim
+import qhull_oracle
+from util import assert_same_mesh, points
+
+
+@pytest.mark.parametrize("d,n", [(2, 3000), (3, 1500), (4, 400), (5, 150), (6, 70)])
+@pytest.mark.parametrize("bounded", [True, False])
+def test_hostsim_matches_oracle(oracle, d, n, bounded):
+    xs = points(n, d, 300 + d)
+    if bounded:
+        base, normal = qhull_oracle.cuboid(d)
+        o, s = oracle.run(xs, base, normal), hostsim.run(xs, base, normal)
+    else:
+        o, s = oracle.run(xs), hostsim.run(xs)
+    assert_same_mesh(s["sig"], s["r"], o["sig"], o["r"], xs, tol=1e-9)
+    assert sorted(map(tuple, s["ray_edge"].tolist())) == sorted(map(tuple, o["ray_edge"].tolist()))
+    assert s["stats"]["degenerate"] == 0 and s["stats"]["seed_fail"] == 0
+
+
+@pytest.mark.parametrize("d,n", [(2, 2000), (3, 1000), (5, 120)])
+def test_fp32_filter_is_sound(d, n):
+    """the FP32 filter may only drop candidates that cannot win: results with and without it are identical"""
+    xs = points(n, d, 400 + d)
+    base, normal = qhull_oracle.cuboid(d)
+    a = hostsim.run(xs, base, normal, fp32=1)
+    b = hostsim.run(xs, base, normal, fp32=0)
+    assert np.array_equal(a["sig"], b["sig"]) and np.array_equal(a["r"], b["r"])
+    assert a["stats"]["cand64"] < b["stats"]["cand64"]
+
+
+@pytest.mark.parametrize("ppc,scale,stride", [(1, 1.05, 1), (8, 3.0, 64), (3, 1.3, 7)])
+def test_result_independent_of_tuning_knobs(oracle, ppc, scale, stride):
+    xs = points(800, 3, 5)
+    base, normal = qhull_oracle.cuboid(3)
+    o = oracle.run(xs, base, normal)
+    s = hostsim.run(xs, base, normal, ppc=ppc, probe_scale=scale, seed_stride=stride)
+    assert_same_mesh(s["sig"], s["r"], o["sig"], o["r"], xs, tol=1e-9)
+
+
+def test_offset_and_anisotropic_cloud(oracle):
+    """FP32 coordinates are stored relative to the bounding box: a far-away, stretched cloud must still be exact"""
+    xs = points(1200, 3, 6) * np.array([10.0, 1.0, 0.1]) + np.array([1000.0, -500.0, 3.0])
+    o, s = oracle.run(xs), hostsim.run(xs)
+    assert np.array_equal(s["sig"], o["sig"])

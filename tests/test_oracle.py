@@ -1,0 +1,68 @@
+"""CPU tests of the oracle: pins the restatement against the independent Qhull oracle and the golden vectors."""
+import glob
+import os
+
+import numpy as np
+import pytest
+
+import qhull_oracle
+from util import empty_ball_violations, neighbors_from_sig, points
+
+GOLDEN = sorted(glob.glob(os.path.join(os.path.dirname(__file__), "golden", "*.npz")))
+
+
+@pytest.mark.parametrize("path", GOLDEN, ids=[os.path.basename(p)[:-4] for p in GOLDEN])
+def test_oracle_reproduces_golden(oracle, path):
+    g = np.load(path)
+    P = g["base"].shape[0]
+    o = oracle.run(g["xs"], g["base"], g["normal"]) if P else oracle.run(g["xs"])
+    assert np.array_equal(o["sig"], g["sig"])
+    assert np.abs(o["r"] - g["r"]).max() <= 1e-12 * max(1.0, np.abs(g["r"]).max())
+    assert np.array_equal(o["ray_edge"], g["ray_edge"])
+    assert np.array_equal(o["nb_off"], g["nb_off"]) and np.array_equal(o["nb_ids"], g["nb_ids"])
+
+
+@pytest.mark.parametrize("d,n", [(2, 400), (3, 300), (4, 120), (5, 60)])
+def test_oracle_matches_qhull_bounded(oracle, d, n):
+    xs = points(n, d, 100 + d)
+    base, normal = qhull_oracle.cuboid(d)
+    o = oracle.run(xs, base, normal)
+    q = qhull_oracle.bounded(xs, base, normal)
+    so = [tuple(s) for s in o["sig"].tolist()]
+    assert set(so) == set(q)
+    assert max(np.abs(o["r"][k] - q[s]).max() for k, s in enumerate(so)) < 1e-11
+    assert o["stats"]["degenerate"] == 0
+    # the reference's invariant: one raycast per vertex (docs/src/index.md:93,96), no vertex found twice
+    assert o["stats"]["duplicates"] == 0
+
+
+@pytest.mark.parametrize("d,n", [(2, 400), (3, 300), (4, 120)])
+def test_oracle_matches_qhull_unbounded(oracle, d, n):
+    xs = points(n, d, 200 + d)
+    o = oracle.run(xs)
+    qv, qr = qhull_oracle.unbounded(xs)
+    assert {tuple(s) for s in o["sig"].tolist()} == set(qv)
+    assert {tuple(e) for e in o["ray_edge"].tolist()} == qr
+
+
+def test_oracle_verify_vertex_and_neighbors(oracle):
+    xs = points(2000, 3, 7)
+    base, normal = qhull_oracle.cuboid(3)
+    o = oracle.run(xs, base, normal)
+    assert empty_ball_violations(o["sig"], o["r"], xs, sample=500) == 0
+    off, ids = neighbors_from_sig(o["sig"], 2000)
+    assert np.array_equal(off, o["nb_off"]) and np.array_equal(ids, o["nb_ids"])
+
+
+def test_oracle_multithread_equals_singlethread(oracle):
+    xs = points(3000, 3, 9)
+    base, normal = qhull_oracle.cuboid(3)
+    a = oracle.run(xs, base, normal, nthreads=1)
+    b = oracle.run(xs, base, normal, nthreads=4)
+    assert np.array_equal(a["sig"], b["sig"])
+    assert np.abs(a["r"] - b["r"]).max() < 1e-11
+
+
+def test_oracle_rejects_too_few_points(oracle):
+    with pytest.raises(RuntimeError):
+        oracle.run(np.random.default_rng(0).random((3, 3)))
