@@ -4,14 +4,14 @@ import ctypes
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libhvb200.so")
+LIB_PATH = os.environ.get("HVB_LIB") or os.path.join(_HERE, "lib", "libhvb200.so")   # HVB_LIB: tuning builds
 
 HVB_OK, HVB_EINVAL, HVB_ECUDA, HVB_ENOGPU, HVB_ENOMEM, HVB_EDEGENERATE, HVB_ESTATE, HVB_EINCOMPLETE = 0, -1, -2, -3, -4, -5, -6, -7
 ERROR_NAMES = {-1: "HVB_EINVAL", -2: "HVB_ECUDA", -3: "HVB_ENOGPU", -4: "HVB_ENOMEM", -5: "HVB_EDEGENERATE",
                -6: "HVB_ESTATE", -7: "HVB_EINCOMPLETE"}
 
-EXPORTS = ("hvb_default_params", "hvb_create", "hvb_search", "hvb_counts", "hvb_fetch_vertices", "hvb_fetch_rays",
-           "hvb_neighbor_count", "hvb_fetch_neighbors", "hvb_view_vertices", "hvb_export_device", "hvb_merge_device",
+EXPORTS = ("hvb_default_params", "hvb_create", "hvb_set_points", "hvb_search", "hvb_counts", "hvb_fetch_vertices", "hvb_fetch_rays",
+           "hvb_neighbor_count", "hvb_fetch_neighbors", "hvb_view_vertices", "hvb_view_neighbors", "hvb_export_device", "hvb_merge_device",
            "hvb_stats", "hvb_last_error", "hvb_destroy", "hvb_version")
 
 
@@ -20,7 +20,7 @@ class hvb_params(ctypes.Structure):
                 ("plane_tolerance", ctypes.c_double), ("ray_tol", ctypes.c_double),
                 ("method", ctypes.c_int32), ("device", ctypes.c_int32), ("rank", ctypes.c_int32), ("world", ctypes.c_int32),
                 ("fp32_filter", ctypes.c_int32), ("on_degenerate", ctypes.c_int32), ("points_per_cell", ctypes.c_int32),
-                ("seed_stride", ctypes.c_int32), ("sort_output", ctypes.c_int32), ("tile_size", ctypes.c_int32),
+                ("seed_stride", ctypes.c_int32), ("sort_output", ctypes.c_int32), ("tile_size", ctypes.c_int32), ("neighbors", ctypes.c_int32), ("reserved1", ctypes.c_int32),
                 ("vertex_capacity", ctypes.c_int64), ("probe_scale", ctypes.c_double)]
 
 
@@ -55,6 +55,7 @@ def lib():
         L.hvb_default_params.argtypes = [ctypes.POINTER(hvb_params)]
         L.hvb_default_params.restype = None
         L.hvb_create.argtypes = [ctypes.POINTER(vp), i32, i64, vp, i32, vp, vp, ctypes.POINTER(hvb_params)]
+        L.hvb_set_points.argtypes = [vp, i64, vp]
         L.hvb_search.argtypes = [vp, vp, i64, vp, vp, i64, i32]
         L.hvb_counts.argtypes = [vp, ctypes.POINTER(i64), ctypes.POINTER(i64), ctypes.POINTER(i64)]
         L.hvb_fetch_vertices.argtypes = [vp, vp, vp]
@@ -62,6 +63,7 @@ def lib():
         L.hvb_neighbor_count.argtypes = [vp, ctypes.POINTER(i64)]
         L.hvb_fetch_neighbors.argtypes = [vp, vp, vp]
         L.hvb_view_vertices.argtypes = [vp, ctypes.POINTER(vp), ctypes.POINTER(vp), ctypes.POINTER(i64)]
+        L.hvb_view_neighbors.argtypes = [vp, ctypes.POINTER(vp), ctypes.POINTER(vp), ctypes.POINTER(i64)]
         L.hvb_export_device.argtypes = [vp, vp, vp, i64, ctypes.POINTER(i64)]
         L.hvb_merge_device.argtypes = [vp, vp, vp, i64]
         L.hvb_stats.argtypes = [vp, ctypes.POINTER(hvb_stats_t)]
@@ -70,8 +72,8 @@ def lib():
         L.hvb_destroy.argtypes = [vp]
         L.hvb_destroy.restype = None
         L.hvb_version.restype = ctypes.c_char_p
-        for name in ("hvb_create", "hvb_search", "hvb_counts", "hvb_fetch_vertices", "hvb_fetch_rays", "hvb_neighbor_count",
-                     "hvb_fetch_neighbors", "hvb_view_vertices", "hvb_export_device", "hvb_merge_device", "hvb_stats"):
+        for name in ("hvb_create", "hvb_set_points", "hvb_search", "hvb_counts", "hvb_fetch_vertices", "hvb_fetch_rays", "hvb_neighbor_count",
+                     "hvb_fetch_neighbors", "hvb_view_vertices", "hvb_view_neighbors", "hvb_export_device", "hvb_merge_device", "hvb_stats"):
             getattr(L, name).restype = i32
         _lib = L
     return _lib

@@ -112,6 +112,14 @@ class Raycast:
             self._ctx = None
             _abi.check(rc, None)
 
+    def set_points(self, xs):
+        """re-target this searcher to another generator set (same dimension and domain), re-using the device context"""
+        xs = VoronoiNodes(xs) if not (isinstance(xs, np.ndarray) and xs.flags.c_contiguous and xs.dtype == np.float64 and xs.ndim == 2 and xs.shape[0] > xs.shape[1]) else xs
+        if xs.shape[1] != self.dim:
+            raise ValueError("dimension mismatch")
+        _abi.check(_abi.lib().hvb_set_points(self._ctx, xs.shape[0], xs.ctypes.data_as(ctypes.c_void_p)), self._ctx)
+        self.xs, self.n = xs, xs.shape[0]
+
     def close(self):
         if getattr(self, "_ctx", None):
             _abi.lib().hvb_destroy(self._ctx)
@@ -129,19 +137,44 @@ class Raycast:
         return s.as_dict()
 
 
-class VoronoiMesh:
-    """Result of voronoi(): the vertex database in the reference's external numbering (1-based ids, plane p = n+p)."""
+class _Owned(np.ndarray):
+    """ndarray over page-locked memory of a device context; keeps the owning searcher alive"""
+    _owner = None
 
-    def __init__(self, searcher):
+
+def _wrap(ptr, shape, ctype, owner):
+    n = int(np.prod(shape))
+    if n == 0:
+        return np.empty(shape, dtype=np.dtype(ctype))
+    arr = np.ctypeslib.as_array(ctypes.cast(ptr, ctypes.POINTER(ctype)), shape=(n,)).reshape(shape).view(_Owned)
+    arr._owner = owner
+    return arr
+
+
+class VoronoiMesh:
+    """Result of voronoi(): the vertex database in the reference's external numbering (1-based ids, plane p = n+p).
+
+    With copy=False (default) `sig`, `r` and the neighbour arrays are zero-copy views of the context's page-locked
+    staging memory: they stay valid until the next search / set_points on the same searcher.  copy=True returns
+    private arrays (hvb_fetch_*)."""
+
+    def __init__(self, searcher, copy=False):
         self.searcher = searcher
+        self.copy = copy
         self.n, self.dim = searcher.n, searcher.dim
         L, ctx = _abi.lib(), searcher._ctx
         nv, nr, ml = ctypes.c_int64(), ctypes.c_int64(), ctypes.c_int64()
         _abi.check(L.hvb_counts(ctx, ctypes.byref(nv), ctypes.byref(nr), ctypes.byref(ml)), ctx)
         d = self.dim
-        self.sig = np.empty((nv.value, d + 1), dtype=np.int64)
-        self.r = np.empty((nv.value, d), dtype=np.float64)
-        _abi.check(L.hvb_fetch_vertices(ctx, self.sig.ctypes.data_as(ctypes.c_void_p), self.r.ctypes.data_as(ctypes.c_void_p)), ctx)
+        if copy:
+            self.sig = np.empty((nv.value, d + 1), dtype=np.int64)
+            self.r = np.empty((nv.value, d), dtype=np.float64)
+            _abi.check(L.hvb_fetch_vertices(ctx, self.sig.ctypes.data_as(ctypes.c_void_p), self.r.ctypes.data_as(ctypes.c_void_p)), ctx)
+        else:
+            ps, pr, cnt = ctypes.c_void_p(), ctypes.c_void_p(), ctypes.c_int64()
+            _abi.check(L.hvb_view_vertices(ctx, ctypes.byref(ps), ctypes.byref(pr), ctypes.byref(cnt)), ctx)
+            self.sig = _wrap(ps, (cnt.value, d + 1), ctypes.c_int64, searcher)
+            self.r = _wrap(pr, (cnt.value, d), ctypes.c_double, searcher)
         self.ray_edge = np.empty((nr.value, d), dtype=np.int64)
         self.ray_base = np.empty((nr.value, d))
         self.ray_dir = np.empty((nr.value, d))
@@ -156,11 +189,17 @@ class VoronoiMesh:
         """CSR (offsets[n+1], ids) of neighbors_of_cell for every cell (neighbors.jl:214-262)."""
         if self._nb is None:
             L, ctx = _abi.lib(), self.searcher._ctx
-            tot = ctypes.c_int64()
-            _abi.check(L.hvb_neighbor_count(ctx, ctypes.byref(tot)), ctx)
-            off = np.empty((self.n + 1,), dtype=np.int64)
-            ids = np.empty((tot.value,), dtype=np.int64)
-            _abi.check(L.hvb_fetch_neighbors(ctx, off.ctypes.data_as(ctypes.c_void_p), ids.ctypes.data_as(ctypes.c_void_p)), ctx)
+            if self.copy:
+                tot = ctypes.c_int64()
+                _abi.check(L.hvb_neighbor_count(ctx, ctypes.byref(tot)), ctx)
+                off = np.empty((self.n + 1,), dtype=np.int64)
+                ids = np.empty((tot.value,), dtype=np.int64)
+                _abi.check(L.hvb_fetch_neighbors(ctx, off.ctypes.data_as(ctypes.c_void_p), ids.ctypes.data_as(ctypes.c_void_p)), ctx)
+            else:
+                po, pi, tot = ctypes.c_void_p(), ctypes.c_void_p(), ctypes.c_int64()
+                _abi.check(L.hvb_view_neighbors(ctx, ctypes.byref(po), ctypes.byref(pi), ctypes.byref(tot)), ctx)
+                off = _wrap(po, (self.n + 1,), ctypes.c_int64, self.searcher)
+                ids = _wrap(pi, (tot.value,), ctypes.c_int64, self.searcher)
             self._nb = (off, ids)
         return self._nb
 
@@ -184,7 +223,7 @@ class VoronoiMesh:
         return self.sig.shape[0]
 
 
-def voronoi(xs, searcher=None, Iter=None, **_ignored):
+def voronoi(xs, searcher=None, Iter=None, copy=False, **_ignored):
     """voronoi(xs; searcher=Raycast(xs), Iter=1:length(xs)) (sysvoronoi.jl:7-39) -> (mesh, searcher)."""
     if searcher is None:
         searcher = Raycast(xs)
@@ -195,7 +234,7 @@ def voronoi(xs, searcher=None, Iter=None, **_ignored):
         cells = np.ascontiguousarray(np.asarray(list(Iter), dtype=np.int64))
         rc = L.hvb_search(ctx, cells.ctypes.data_as(ctypes.c_void_p), cells.shape[0], None, None, 0, 0)
     _abi.check(rc, ctx)
-    return VoronoiMesh(searcher), searcher
+    return VoronoiMesh(searcher, copy=copy), searcher
 
 
 class VoronoiGeometry:

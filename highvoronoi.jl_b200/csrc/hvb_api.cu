@@ -82,6 +82,7 @@ struct hvb_ctx {
     hvb_stats_t st;
     virtual ~hvb_ctx() {}
     virtual int init(const double* xs, const double* pbase, const double* pnormal) = 0;
+    virtual int set_points(int64_t n, const double* xs) = 0;
     virtual int search(const int64_t* cells, int64_t ncells, const int64_t* seed_sig, const double* seed_r, int64_t nseed, int stride) = 0;
     virtual int counts(int64_t* nv, int64_t* nr, int64_t* msl) = 0;
     virtual int fetch_vertices(int64_t* sig, double* r) = 0;
@@ -89,13 +90,14 @@ struct hvb_ctx {
     virtual int fetch_rays(int64_t* edge, double* base, double* dir, int64_t* node) = 0;
     virtual int neighbor_count(int64_t* total) = 0;
     virtual int fetch_neighbors(int64_t* off, int64_t* ids) = 0;
+    virtual int view_neighbors(const int64_t** off, const int64_t** ids, int64_t* total) = 0;
     virtual int export_device(void* sig, void* r, int64_t cap, int64_t* count) = 0;
     virtual int merge_device(const void* sig, const void* r, int64_t count) = 0;
 };
 
 template <int D>
 struct Ctx : hvb_ctx {
-    int G = (D == 2) ? 4 : (D == 3) ? 8 : (D == 4) ? 16 : 32;       // lanes per frontier entry (prm.tile_size overrides)
+    int G = (D == 2) ? 4 : (D == 3) ? 4 : (D == 4) ? 8 : 16;       // lanes per frontier entry (prm.tile_size overrides)
     bool debug = false;
     cudaStream_t stream = nullptr;
     int sms = 148;
@@ -139,6 +141,8 @@ struct Ctx : hvb_ctx {
     DBuf<u64> ptab;
     DBuf<u32> deg, ncur;
     DBuf<long long> nb_off, nb_ids;
+    HBuf<long long> h_nb_off, h_nb_ids;
+    bool nb_staged = false;
     int64_t nb_total = -1;
     std::vector<cudaEvent_t> ev_pool;
     cudaEvent_t ev_a = nullptr, ev_b = nullptr, ev_c = nullptr, ev_d = nullptr;
@@ -153,7 +157,7 @@ struct Ctx : hvb_ctx {
         ctr.release(); sc.release(); h_sc.release(); h_ctr.release(); cells_dev.release();
         out_sig[0].release(); out_sig[1].release(); out_r[0].release(); out_r[1].release(); key_hi.release(); key_lo.release(); key_tmp.release();
         idx[0].release(); idx[1].release(); ray_edge.release(); ray_node.release(); ray_base.release(); ray_dir.release();
-        h_sig.release(); h_r.release(); ptab.release(); deg.release(); ncur.release(); nb_off.release(); nb_ids.release();
+        h_sig.release(); h_r.release(); h_nb_off.release(); h_nb_ids.release(); ptab.release(); deg.release(); ncur.release(); nb_off.release(); nb_ids.release();
         for (cudaEvent_t e : ev_pool) cudaEventDestroy(e);
         if (ev_a) cudaEventDestroy(ev_a);
         if (ev_b) cudaEventDestroy(ev_b);
@@ -164,30 +168,49 @@ struct Ctx : hvb_ctx {
 
     static int blocks_for(int64_t items, int per_block) { return (int)std::max<int64_t>(1, (items + per_block - 1) / per_block); }
 
+    PlaneSet ps_host;
+    bool setup_done = false;
+
     int init(const double* xs, const double* pbase, const double* pnormal) override {
         memset(&dv, 0, sizeof(dv));
         memset(&st, 0, sizeof(st));
         CK(cudaSetDevice(prm.device));
-        cudaDeviceProp prop;
-        CK(cudaGetDeviceProperties(&prop, prm.device));
-        sms = prop.multiProcessorCount;
+        CK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, prm.device));
         CK(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
         CK(cudaEventCreate(&ev_a)); CK(cudaEventCreate(&ev_b)); CK(cudaEventCreate(&ev_c)); CK(cudaEventCreate(&ev_d));
-        CK(cudaEventRecord(ev_a, stream));
-        dv.n = (int)n;
         // planes: unit outward normals, offsets
-        PlaneSet ps;
-        memset(&ps, 0, sizeof(ps));
-        ps.P = P;
+        memset(&ps_host, 0, sizeof(ps_host));
+        ps_host.P = P;
         for (int p = 0; p < P; ++p) {
             double nr = 0;
             for (int k = 0; k < D; ++k) nr += pnormal[p * D + k] * pnormal[p * D + k];
             nr = sqrt(nr);
             if (!(nr > 0)) { err = "boundary plane with zero normal"; return HVB_EINVAL; }
             double off = 0;
-            for (int k = 0; k < D; ++k) { ps.normal[p * 6 + k] = pnormal[p * D + k] / nr; off += ps.normal[p * 6 + k] * pbase[p * D + k]; }
-            ps.off[p] = off;
+            for (int k = 0; k < D; ++k) { ps_host.normal[p * 6 + k] = pnormal[p * D + k] / nr; off += ps_host.normal[p * 6 + k] * pbase[p * D + k]; }
+            ps_host.off[p] = off;
         }
+        CK(planes.ensure(1)); CK(ctr.ensure(1)); CK(sc.ensure(1)); CK(h_sc.ensure(1)); CK(h_ctr.ensure(1));
+        CK(cudaMemcpyAsync(planes.p, &ps_host, sizeof(ps_host), cudaMemcpyHostToDevice, stream));
+        dv.plane_tol = prm.plane_tolerance;
+        dv.probe_scale = prm.probe_scale > 1.0 ? prm.probe_scale : 1.3;
+        dv.fp32_filter = prm.fp32_filter;
+        if (prm.tile_size == 1 || prm.tile_size == 2 || prm.tile_size == 4 || prm.tile_size == 8 || prm.tile_size == 16 || prm.tile_size == 32) G = prm.tile_size;
+        debug = getenv("HVB_DEBUG") != nullptr;
+        setup_done = true;
+        return set_points(n, xs);
+    }
+
+    // (re)loads the generators and rebuilds the spatial index; every buffer is reused when it is large enough
+    int set_points(int64_t n_new, const double* xs) override {
+        if (!setup_done) { err = "context not initialised"; return HVB_ESTATE; }
+        if (n_new <= D || !xs) { err = "There are not enough points to create a Voronoi tessellation"; return HVB_EINVAL; }
+        CK(cudaSetDevice(prm.device));
+        have_result = false; staged = false; nb_total = -1;
+        n = n_new;
+        CK(cudaEventRecord(ev_a, stream));
+        dv.n = (int)n;
+        const PlaneSet& ps = ps_host;
         // bounding box + domain check (check_boundary, boundary.jl:437)
         double blo[D], bhi[D];
         for (int k = 0; k < D; ++k) { blo[k] = 1e300; bhi[k] = -1e300; }
@@ -208,17 +231,10 @@ struct Ctx : hvb_ctx {
         }
         int ppc = prm.points_per_cell > 0 ? prm.points_per_cell : default_points_per_cell(D);
         ncells = setup_grid<D>(dv, blo, bhi, n, ppc);
-        dv.plane_tol = prm.plane_tolerance;
-        dv.probe_scale = prm.probe_scale > 1.0 ? prm.probe_scale : 1.3;
-        dv.fp32_filter = prm.fp32_filter;
-        if (prm.tile_size == 4 || prm.tile_size == 8 || prm.tile_size == 16 || prm.tile_size == 32) G = prm.tile_size;
-        debug = getenv("HVB_DEBUG") != nullptr;
         CK(xs_in.ensure((size_t)n * D)); CK(x64.ensure((size_t)n * D)); CK(x32.ensure((size_t)n * D));
         CK(perm.ensure(n)); CK(inv.ensure(n)); CK(cell_of.ensure(n)); CK(unseeded_list.ensure(n));
         CK(cell_start.ensure(ncells + 1)); CK(cell_cur.ensure(ncells + 1));
-        CK(planes.ensure(1)); CK(active.ensure(n)); CK(has_vertex.ensure(n));
-        CK(ctr.ensure(1)); CK(sc.ensure(1)); CK(h_sc.ensure(1)); CK(h_ctr.ensure(1));
-        CK(cudaMemcpyAsync(planes.p, &ps, sizeof(ps), cudaMemcpyHostToDevice, stream));
+        CK(active.ensure(n)); CK(has_vertex.ensure(n));
         CK(cudaMemcpyAsync(xs_in.p, xs, (size_t)n * D * sizeof(double), cudaMemcpyHostToDevice, stream));
         dv.cell_start = cell_start.p; dv.x32 = x32.p; dv.x64 = x64.p; dv.planes = planes.p; dv.active = active.p;
         dv.has_vertex = has_vertex.p; dv.ctr = ctr.p;
@@ -249,12 +265,7 @@ struct Ctx : hvb_ctx {
         ++launches;
     }
     void launch_seed(const int* seeds, int nseeds, int stride, int cur) {
-        switch (G) {
-            case 4: launch_seed_g<4>(seeds, nseeds, stride, cur); break;
-            case 8: launch_seed_g<8>(seeds, nseeds, stride, cur); break;
-            case 16: launch_seed_g<16>(seeds, nseeds, stride, cur); break;
-            default: launch_seed_g<32>(seeds, nseeds, stride, cur); break;
-        }
+        launch_seed_g<(D <= 3) ? 4 : 8>(seeds, nseeds, stride, cur);     // descents are few: one tile size per dimension
     }
     template <int GG>
     void launch_expand_g(u32 cnt, int cur, int nxt) {
@@ -263,6 +274,8 @@ struct Ctx : hvb_ctx {
     }
     void launch_expand(u32 cnt, int cur, int nxt) {
         switch (G) {
+            case 1: launch_expand_g<1>(cnt, cur, nxt); break;
+            case 2: launch_expand_g<2>(cnt, cur, nxt); break;
             case 4: launch_expand_g<4>(cnt, cur, nxt); break;
             case 8: launch_expand_g<8>(cnt, cur, nxt); break;
             case 16: launch_expand_g<16>(cnt, cur, nxt); break;
@@ -287,6 +300,10 @@ struct Ctx : hvb_ctx {
         dv.vsig = vsig.p; dv.vr = vr.p; dv.vcap = (u32)cap; dv.vtab = vtab.p; dv.etab = etab.p;
         dv.ray_item = ray_item.p; dv.ray_u = ray_u.p; dv.ray_cap = ray_cap;
         dv.vcount = &sc.p->vcount; dv.ray_count = &sc.p->ray_count;
+        // result buffers and page-locked staging are sized once with the tables (no allocation in steady state)
+        for (int i = 0; i < 2; ++i) { CK(out_sig[i].ensure((size_t)cap * (D + 1))); CK(out_r[i].ensure((size_t)cap * D)); }
+        CK(key_hi.ensure(cap)); CK(key_lo.ensure(cap)); CK(key_tmp.ensure(cap)); CK(idx[0].ensure(cap)); CK(idx[1].ensure(cap));
+        CK(h_sig.ensure((size_t)cap * (D + 1))); CK(h_r.ensure((size_t)cap * D));
         return HVB_OK;
     }
 
@@ -381,6 +398,8 @@ struct Ctx : hvb_ctx {
         int rc = finalize(); if (rc) return rc;
         CK(cudaEventRecord(ev_c, stream));
         rc = stage(); if (rc) return rc;
+        have_result = true;
+        if (prm.neighbors) { rc = build_neighbors(); if (rc) return rc; rc = stage_neighbors(); if (rc) return rc; }
         CK(cudaEventRecord(ev_d, stream));
         CK(cudaStreamSynchronize(stream));
         CK(cudaGetLastError());
@@ -396,10 +415,10 @@ struct Ctx : hvb_ctx {
         st.rows_scanned = (int64_t)c.rows; st.probe_stages = (int64_t)c.stages; st.rounds = rounds; st.seeds = (int64_t)c.seeds;
         st.degenerate = (int64_t)c.degenerate; st.kernel_launches = launches; st.capacity_retries = retries;
         have_result = true;
-        if (c.seed_fail > 0 && h_sc.p->unseeded > 0) { err = "descent failed for some cells"; return HVB_EINCOMPLETE; }
         if (c.degenerate > 0 && !prm.on_degenerate) {
             err = "non-general position: a vertex with more than dim+1 cospherical generators was met"; return HVB_EDEGENERATE;
         }
+        if (c.seed_fail > 0 && h_sc.p->unseeded > 0) { err = "descent failed for some cells"; return HVB_EINCOMPLETE; }
         return HVB_OK;
     }
 
@@ -499,6 +518,7 @@ struct Ctx : hvb_ctx {
     int build_neighbors() {
         if (nb_total >= 0) return HVB_OK;
         CK(cudaSetDevice(prm.device));
+        nb_staged = false;
         CK(deg.ensure(n)); CK(ncur.ensure(n)); CK(nb_off.ensure(n + 1));
         static const double nb_est[7] = {0, 0, 8, 20, 48, 120, 320};
         u64 want = next_pow2((u64)(std::min((double)nvert * D * (D + 1) / 2.0, (double)n * nb_est[D]) * 2.0) + 1024);
@@ -539,12 +559,27 @@ struct Ctx : hvb_ctx {
         *total = nb_total;
         return HVB_OK;
     }
-    int fetch_neighbors(int64_t* off, int64_t* ids) override {
+    int stage_neighbors() {
+        if (nb_staged) return HVB_OK;
+        CK(h_nb_off.ensure(n + 1)); CK(h_nb_ids.ensure(std::max<int64_t>(nb_total, 1)));
+        CK(cudaMemcpyAsync(h_nb_off.p, nb_off.p, (size_t)(n + 1) * 8, cudaMemcpyDeviceToHost, stream));
+        if (nb_total > 0) CK(cudaMemcpyAsync(h_nb_ids.p, nb_ids.p, (size_t)nb_total * 8, cudaMemcpyDeviceToHost, stream));
+        nb_staged = true;
+        return HVB_OK;
+    }
+    int view_neighbors(const int64_t** off, const int64_t** ids, int64_t* total) override {
         if (!have_result) { err = "no search result"; return HVB_ESTATE; }
         int rc = build_neighbors(); if (rc) return rc;
-        if (off) CK(cudaMemcpyAsync(off, nb_off.p, (size_t)(n + 1) * 8, cudaMemcpyDeviceToHost, stream));
-        if (ids && nb_total > 0) CK(cudaMemcpyAsync(ids, nb_ids.p, (size_t)nb_total * 8, cudaMemcpyDeviceToHost, stream));
+        rc = stage_neighbors(); if (rc) return rc;
         CK(cudaStreamSynchronize(stream));
+        *off = (const int64_t*)h_nb_off.p; *ids = (const int64_t*)h_nb_ids.p; *total = nb_total;
+        return HVB_OK;
+    }
+    int fetch_neighbors(int64_t* off, int64_t* ids) override {
+        const int64_t *o, *i; int64_t tot;
+        int rc = view_neighbors(&o, &i, &tot); if (rc) return rc;
+        if (off) memcpy(off, o, (size_t)(n + 1) * 8);
+        if (ids && tot > 0) memcpy(ids, i, (size_t)tot * 8);
         return HVB_OK;
     }
 
@@ -596,7 +631,7 @@ void hvb_default_params(hvb_params* p) {
     memset(p, 0, sizeof(*p));
     p->variance_tol = 1e-15; p->break_tol = 1e-5; p->b_nodes_tol = 1e-7; p->plane_tolerance = 1e-12; p->ray_tol = 1e-12;
     p->method = 0; p->device = 0; p->rank = 0; p->world = 1; p->fp32_filter = 1; p->on_degenerate = 0;
-    p->points_per_cell = 0; p->seed_stride = 0; p->sort_output = 1; p->vertex_capacity = 0; p->probe_scale = 0.0;
+    p->points_per_cell = 0; p->seed_stride = 0; p->sort_output = 1; p->neighbors = 0; p->reserved1 = 0; p->vertex_capacity = 0; p->probe_scale = 0.0;
 }
 
 int hvb_create(hvb_ctx** out, int dim, int64_t n, const double* xs, int nplanes, const double* plane_base,
@@ -631,6 +666,8 @@ int hvb_create(hvb_ctx** out, int dim, int64_t n, const double* xs, int nplanes,
     return HVB_OK;
 }
 
+int hvb_set_points(hvb_ctx* ctx, int64_t n, const double* xs) { return ctx ? ctx->set_points(n, xs) : HVB_EINVAL; }
+
 int hvb_search(hvb_ctx* ctx, const int64_t* cells, int64_t ncells, const int64_t* seed_sig, const double* seed_r, int64_t nseed, int sig_stride) {
     if (!ctx) return HVB_EINVAL;
     return ctx->search(cells, ncells, seed_sig, seed_r, nseed, sig_stride);
@@ -641,6 +678,7 @@ int hvb_view_vertices(hvb_ctx* ctx, const int64_t** sig, const double** r, int64
 int hvb_fetch_rays(hvb_ctx* ctx, int64_t* edge, double* base, double* dir, int64_t* node) { return ctx ? ctx->fetch_rays(edge, base, dir, node) : HVB_EINVAL; }
 int hvb_neighbor_count(hvb_ctx* ctx, int64_t* total) { return (ctx && total) ? ctx->neighbor_count(total) : HVB_EINVAL; }
 int hvb_fetch_neighbors(hvb_ctx* ctx, int64_t* offsets, int64_t* ids) { return ctx ? ctx->fetch_neighbors(offsets, ids) : HVB_EINVAL; }
+int hvb_view_neighbors(hvb_ctx* ctx, const int64_t** offsets, const int64_t** ids, int64_t* total) { return (ctx && offsets && ids && total) ? ctx->view_neighbors(offsets, ids, total) : HVB_EINVAL; }
 int hvb_export_device(hvb_ctx* ctx, void* sig_dev, void* r_dev, int64_t cap, int64_t* count) { return ctx ? ctx->export_device(sig_dev, r_dev, cap, count) : HVB_EINVAL; }
 int hvb_merge_device(hvb_ctx* ctx, const void* sig_dev, const void* r_dev, int64_t count) { return ctx ? ctx->merge_device(sig_dev, r_dev, count) : HVB_EINVAL; }
 int hvb_stats(hvb_ctx* ctx, hvb_stats_t* out) {

@@ -119,13 +119,13 @@ struct TileDev {
         mask = (G == 32) ? 0xffffffffu : (((1u << G) - 1u) << (wl & ~(G - 1)));
     }
     __device__ __forceinline__ int lane() const { return ln; }
-    __device__ __forceinline__ double shfl_xor(double v, int m) const { return __shfl_xor_sync(mask, v, m, G); }
-    __device__ __forceinline__ int shfl_xor(int v, int m) const { return __shfl_xor_sync(mask, v, m, G); }
-    __device__ __forceinline__ int shfl(int v, int src) const { return __shfl_sync(mask, v, src, G); }
-    __device__ __forceinline__ u32 shfl(u32 v, int src) const { return __shfl_sync(mask, v, src, G); }
-    __device__ __forceinline__ u64 shfl(u64 v, int src) const { return __shfl_sync(mask, v, src, G); }
+    __device__ __forceinline__ double shfl_xor(double v, int m) const { return G == 1 ? v : __shfl_xor_sync(mask, v, m, G); }
+    __device__ __forceinline__ int shfl_xor(int v, int m) const { return G == 1 ? v : __shfl_xor_sync(mask, v, m, G); }
+    __device__ __forceinline__ int shfl(int v, int src) const { return G == 1 ? v : __shfl_sync(mask, v, src, G); }
+    __device__ __forceinline__ u32 shfl(u32 v, int src) const { return G == 1 ? v : __shfl_sync(mask, v, src, G); }
+    __device__ __forceinline__ u64 shfl(u64 v, int src) const { return G == 1 ? v : __shfl_sync(mask, v, src, G); }
     // reconverges the lanes of this tile (they may still be split after lane-dependent work)
-    __device__ __forceinline__ void sync() const { __syncwarp(mask); }
+    __device__ __forceinline__ void sync() const { if (G > 1) __syncwarp(mask); }
     // ballot restricted to this tile, bit i = lane i of the tile
     __device__ __forceinline__ u32 ballot(bool p) const {
         u32 b = __ballot_sync(mask, p);

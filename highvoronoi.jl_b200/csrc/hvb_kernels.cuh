@@ -110,8 +110,11 @@ __global__ void __launch_bounds__(128) k_seed(Dev<D> dv, const int* __restrict__
     flush_stats(ls, dv.ctr);
 }
 
+#ifndef HVB_EXPAND_MINB
+#define HVB_EXPAND_MINB 1
+#endif
 template <int D, int G>
-__global__ void __launch_bounds__(128) k_expand(Dev<D> dv, const u32* __restrict__ q_in, const u32* __restrict__ n_in_ptr,
+__global__ void __launch_bounds__(128, HVB_EXPAND_MINB) k_expand(Dev<D> dv, const u32* __restrict__ q_in, const u32* __restrict__ n_in_ptr,
                                                 u32* q_out, u32* q_count, u32 q_cap) {
     TileDev<G> tile;
     LocalStats ls = {};

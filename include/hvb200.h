@@ -56,7 +56,9 @@ typedef struct hvb_params {
     int32_t points_per_cell;  /* target occupancy of a uniform-grid cell; 0 = auto */
     int32_t seed_stride;      /* one descent seed every `seed_stride` generators; 0 = auto */
     int32_t sort_output;      /* 1: vertices are returned in lexicographic order of their signature (default) */
-    int32_t tile_size;        /* lanes cooperating on one frontier entry: 4, 8, 16 or 32; 0 = auto by dimension */
+    int32_t tile_size;        /* lanes cooperating on one frontier entry: 1, 2, 4, 8, 16 or 32; 0 = auto by dimension */
+    int32_t neighbors;        /* 1: hvb_search also builds and stages the neighbour lists (default 0: on first request) */
+    int32_t reserved1;
     int64_t vertex_capacity;  /* 0 = estimate from lowerbound(d,d) (edgeiteratebase.jl:151); grows on demand */
     double probe_scale;       /* first probe ball radius / circumradius of the origin vertex; 0 = auto */
 } hvb_params;
@@ -95,6 +97,11 @@ int hvb_create(hvb_ctx** out, int dim, int64_t n, const double* xs,
                int nplanes, const double* plane_base, const double* plane_normal,
                const hvb_params* params);
 
+/* Re-targets an existing context to a new generator set of the same dimension and domain (a second
+ * Raycast(xs; domain, options) call in the reference): uploads the points and rebuilds the index, re-using every
+ * device and page-locked allocation of the context.  Invalidates the previous result. */
+int hvb_set_points(hvb_ctx* ctx, int64_t n, const double* xs);
+
 /* Replaces voronoi(mesh; Iter, searcher) (src/sysvoronoi.jl:21 -> _voronoi :41/:50 -> __voronoi :152):
  * cells = Iter (1-based, NULL = all cells); seed_sig/seed_r = vertices the mesh already holds
  * (nseed rows of sig_stride ids, unused entries 0; the refinement callers meshrefine.jl:199-215 pass a
@@ -119,6 +126,7 @@ int hvb_fetch_neighbors(hvb_ctx* ctx, int64_t* offsets, int64_t* ids);
 /* Zero-copy variants: pointers into page-locked host memory owned by the context, valid until the next
  * hvb_search / hvb_destroy.  Layout as in hvb_fetch_vertices. */
 int hvb_view_vertices(hvb_ctx* ctx, const int64_t** sig, const double** r, int64_t* nvert);
+int hvb_view_neighbors(hvb_ctx* ctx, const int64_t** offsets, const int64_t** ids, int64_t* total);
 
 /* Multi-GPU exchange step (parallelmesh.jl's shared store becomes: local search -> all-gather -> merge).
  * hvb_export_device copies this rank's vertices (int32 sig rows of dim+1 0-based caller ids, double r rows)

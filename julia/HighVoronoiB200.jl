@@ -1,0 +1,106 @@
+# HighVoronoiB200.jl -- the reference-side binding of libhvb200.so (NOT executed in the build container: Julia is not
+# installed there; the same C ABI is exercised by the Python ctypes mirror in highvoronoi.jl_b200/).
+#
+# What a HighVoronoi.jl maintainer adds to select the B200 backend through the existing `search_settings` seam:
+#
+#   1. one new threading singleton  `B200Thread(device, rank, world)`   (next to SingleThread/MultiThread/AutoThread,
+#      src/HighVoronoi.jl:60-81)
+#   2. one new method of `_voronoi(mesh, TODO, ..., threading::B200Thread)`   (next to src/sysvoronoi.jl:41 and :50)
+#
+# Everything else -- VoronoiGeometry / VoronoiData / refine! / ConvexHull -- is unchanged: they reach the search only
+# through `voronoi(mesh; Iter, searcher)` (sysvoronoi.jl:21), which dispatches on `searcher.parameters.threading`
+# (sysvoronoi.jl:38).
+#
+#   VG = VoronoiGeometry(xs, cuboid(3, periodic=[]); search_settings=(threading=B200Thread(0),), integrate=false)
+
+module HighVoronoiB200
+
+using HighVoronoi
+using StaticArrays
+import HighVoronoi: _voronoi, nodes, AbstractMesh, RaycastIncircleSkip
+
+const LIB = get(ENV, "HVB200_LIB", joinpath(@__DIR__, "..", "highvoronoi.jl_b200", "lib", "libhvb200.so"))
+
+# mirrors `struct hvb_params` (include/hvb200.h)
+mutable struct HvbParams
+    variance_tol::Cdouble; break_tol::Cdouble; b_nodes_tol::Cdouble; plane_tolerance::Cdouble; ray_tol::Cdouble
+    method::Int32; device::Int32; rank::Int32; world::Int32
+    fp32_filter::Int32; on_degenerate::Int32; points_per_cell::Int32; seed_stride::Int32; sort_output::Int32
+    tile_size::Int32; neighbors::Int32; reserved1::Int32
+    vertex_capacity::Int64; probe_scale::Cdouble
+    HvbParams() = new()
+end
+
+struct B200Thread            # <: the reference's threading singletons
+    device::Int32
+    rank::Int32
+    world::Int32
+end
+B200Thread(device::Integer=0) = B200Thread(Int32(device), Int32(0), Int32(1))
+
+last_error(ctx) = unsafe_string(ccall((:hvb_last_error, LIB), Cstring, (Ptr{Cvoid},), ctx))
+check(rc, ctx=C_NULL) = rc == 0 || error("libhvb200: code $rc: " * last_error(ctx))     # codes become Julia exceptions
+
+"""
+    _voronoi(mesh, TODO, ..., threading::B200Thread)
+
+Drop-in replacement of the cell loop (`__voronoi`, sysvoronoi.jl:152-215): flatten the generators and the boundary
+planes, run the search on the GPU, replay the result with the reference's own `push!(mesh, sig=>r)`
+(abstractmesh.jl:111) and `pushray!` (abstractmesh.jl:191).
+"""
+function _voronoi(mesh::AM, TODO, compact, v_offset, silence, iteration_reset, printsearcher,
+                  searcher::RaycastIncircleSkip, intro, threading::B200Thread) where {P, AM<:AbstractMesh{P}}
+    xs = nodes(mesh)                              # Vector{SVector{d,Float64}} == n x d row-major doubles (voronoinodes.jl:14)
+    d = size(P)[1]
+    n = length(xs)
+    planes = searcher.domain.planes               # boundary.jl:22-29
+    np = length(planes)
+    base = Matrix{Float64}(undef, d, np)
+    normal = Matrix{Float64}(undef, d, np)
+    for (k, pl) in enumerate(planes)
+        base[:, k] .= pl.base
+        normal[:, k] .= pl.normal
+    end
+    prm = HvbParams()
+    ccall((:hvb_default_params, LIB), Cvoid, (Ref{HvbParams},), prm)
+    par = searcher.parameters                     # raycast-types.jl:136-171
+    prm.variance_tol = par.variance_tol; prm.break_tol = par.break_tol; prm.b_nodes_tol = par.b_nodes_tol
+    prm.plane_tolerance = par.plane_tolerance; prm.ray_tol = par.ray_tol
+    prm.device = threading.device; prm.rank = threading.rank; prm.world = threading.world
+    ctx = Ref{Ptr{Cvoid}}(C_NULL)
+    GC.@preserve xs base normal begin
+        check(ccall((:hvb_create, LIB), Cint,
+                    (Ref{Ptr{Cvoid}}, Cint, Int64, Ptr{Float64}, Cint, Ptr{Float64}, Ptr{Float64}, Ref{HvbParams}),
+                    ctx, d, n, pointer(reinterpret(Float64, xs)), np, base, normal, prm))
+    end
+    c = ctx[]
+    try
+        cells = Int64.(TODO)                      # Iter (1-based)
+        all_cells = length(cells) == n
+        check(ccall((:hvb_search, LIB), Cint,
+                    (Ptr{Cvoid}, Ptr{Int64}, Int64, Ptr{Int64}, Ptr{Float64}, Int64, Cint),
+                    c, all_cells ? C_NULL : cells, all_cells ? 0 : length(cells), C_NULL, C_NULL, 0, 0), c)
+        nv = Ref{Int64}(0); nr = Ref{Int64}(0); ml = Ref{Int64}(0)
+        check(ccall((:hvb_counts, LIB), Cint, (Ptr{Cvoid}, Ref{Int64}, Ref{Int64}, Ref{Int64}), c, nv, nr, ml), c)
+        # zero-copy view of the page-locked result (valid until the context is destroyed)
+        psig = Ref{Ptr{Int64}}(C_NULL); pr = Ref{Ptr{Float64}}(C_NULL); cnt = Ref{Int64}(0)
+        check(ccall((:hvb_view_vertices, LIB), Cint, (Ptr{Cvoid}, Ref{Ptr{Int64}}, Ref{Ptr{Float64}}, Ref{Int64}), c, psig, pr, cnt), c)
+        sig = unsafe_wrap(Array, psig[], (d + 1, cnt[]))
+        r = unsafe_wrap(Array, pr[], (d, cnt[]))
+        for v in 1:cnt[]
+            push!(mesh, Vector{Int64}(view(sig, :, v)) => P(view(r, :, v)))          # abstractmesh.jl:111
+        end
+        if nr[] > 0
+            edge = Matrix{Int64}(undef, d, nr[]); rb = Matrix{Float64}(undef, d, nr[]); ru = similar(rb); node = Vector{Int64}(undef, nr[])
+            check(ccall((:hvb_fetch_rays, LIB), Cint, (Ptr{Cvoid}, Ptr{Int64}, Ptr{Float64}, Ptr{Float64}, Ptr{Int64}), c, edge, rb, ru, node), c)
+            for k in 1:nr[]
+                HighVoronoi.pushray!(mesh, Vector{Int64}(view(edge, :, k)), P(view(rb, :, k)), P(view(ru, :, k)), node[k])   # abstractmesh.jl:191
+            end
+        end
+    finally
+        ccall((:hvb_destroy, LIB), Cvoid, (Ptr{Cvoid},), c)
+    end
+    return mesh, searcher
+end
+
+end # module
