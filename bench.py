@@ -232,9 +232,11 @@ def main():
     sampler = ClockSampler(local_rank) if rank == 0 else None
     dev_ms_tot, e2e_tot, verts, launches, kern_ms, kern_launches, h2d, d2h = 0.0, 0.0, 0, 0, 0.0, 0, 0, 0
     stats_last = None
+    step_ms = []
     for it in range(args.steps):
         dm, es, V, st, nl, hb, db = step(it, True)
         dev_ms_tot += all_max(dm)
+        step_ms.append(round(dm, 3))
         e2e_tot += all_max(es)
         verts += V
         launches += nl
@@ -273,7 +275,8 @@ def main():
                      "kernel_ms_per_step": kern_ms / args.steps},
         "vertices_per_step": verts / args.steps,
         "stats_last_step": {k: stats_last[k] for k in ("raycasts", "duplicate_hits", "closed_skips", "candidates_fp32",
-                                                        "candidates_fp64", "rounds", "seeds", "ms_build", "ms_search", "ms_finalize")},
+                                                        "candidates_fp64", "rounds", "seeds", "ms_build", "ms_search", "ms_finalize", "ms_seed", "ms_neighbors", "ms_rows_sort", "capacity_retries")},
+        "step_ms_list": step_ms,
     }
     if not args.no_cpu_baseline and world == 1:
         sys.path.insert(0, os.path.join(ROOT, "oracle"))

@@ -29,7 +29,8 @@ class hvb_stats_t(ctypes.Structure):
                 ("vertices", "rays", "raycasts", "duplicate_hits", "closed_skips", "candidates_fp32", "candidates_fp64",
                  "rows_scanned", "probe_stages", "rounds", "seeds", "degenerate", "kernel_launches", "capacity_retries")] + \
                [(k, ctypes.c_double) for k in ("ms_build", "ms_search", "ms_finalize", "ms_expand_kernel")] + \
-               [("expand_launches", ctypes.c_int64), ("expand_items", ctypes.c_int64)]
+               [("expand_launches", ctypes.c_int64), ("expand_items", ctypes.c_int64)] + \
+               [(k, ctypes.c_double) for k in ("ms_seed", "ms_neighbors", "ms_rows_sort")]
 
     def as_dict(self):
         return {k: getattr(self, k) for k, _ in self._fields_}

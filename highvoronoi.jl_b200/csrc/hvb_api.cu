@@ -42,8 +42,11 @@ struct DBuf {
         if (n <= cap) return cudaSuccess;
         if (p) cudaFree(p);
         p = nullptr; cap = 0;
-        cudaError_t e = cudaMalloc((void**)&p, std::max<size_t>(n, 1) * sizeof(T));
-        if (e == cudaSuccess) cap = n;
+        // grow geometrically: sizes that creep up from step to step must not re-allocate (cudaFree synchronises)
+        size_t want = std::max<size_t>(n + n / 4, 1);
+        cudaError_t e = cudaMalloc((void**)&p, want * sizeof(T));
+        if (e != cudaSuccess) { want = std::max<size_t>(n, 1); e = cudaMalloc((void**)&p, want * sizeof(T)); }
+        if (e == cudaSuccess) cap = want;
         return e;
     }
     void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
@@ -64,8 +67,9 @@ struct HBuf {   // page-locked host memory
     void release() { if (p) cudaFreeHost(p); p = nullptr; cap = 0; }
 };
 
+struct Round { u32 qcount; u32 cursor; };   // frontier length and the work cursor of the round that consumes it
 struct Scalars {            // small device-side words, mirrored into pinned host memory after every round
-    u32 qcount[2];
+    Round rnd[2];
     u32 vcount;
     u32 ray_count;
     u32 unseeded;
@@ -115,7 +119,7 @@ struct Ctx : hvb_ctx {
     DBuf<int> vsig;
     DBuf<double> vr;
     DBuf<u64> vtab, etab;
-    DBuf<u32> q[2];
+    DBuf<u64> q[2];
     u32 qcap = 0;
     DBuf<u32> ray_item;
     DBuf<double> ray_u;
@@ -145,7 +149,7 @@ struct Ctx : hvb_ctx {
     bool nb_staged = false;
     int64_t nb_total = -1;
     std::vector<cudaEvent_t> ev_pool;
-    cudaEvent_t ev_a = nullptr, ev_b = nullptr, ev_c = nullptr, ev_d = nullptr;
+    cudaEvent_t ev_a = nullptr, ev_b = nullptr, ev_c = nullptr, ev_d = nullptr, ev_s0 = nullptr, ev_s1 = nullptr, ev_n0 = nullptr, ev_n1 = nullptr;
     int64_t launches = 0;
 
     ~Ctx() override {
@@ -163,6 +167,10 @@ struct Ctx : hvb_ctx {
         if (ev_b) cudaEventDestroy(ev_b);
         if (ev_c) cudaEventDestroy(ev_c);
         if (ev_d) cudaEventDestroy(ev_d);
+        if (ev_s0) cudaEventDestroy(ev_s0);
+        if (ev_s1) cudaEventDestroy(ev_s1);
+        if (ev_n0) cudaEventDestroy(ev_n0);
+        if (ev_n1) cudaEventDestroy(ev_n1);
         if (stream) cudaStreamDestroy(stream);
     }
 
@@ -178,6 +186,7 @@ struct Ctx : hvb_ctx {
         CK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, prm.device));
         CK(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
         CK(cudaEventCreate(&ev_a)); CK(cudaEventCreate(&ev_b)); CK(cudaEventCreate(&ev_c)); CK(cudaEventCreate(&ev_d));
+        CK(cudaEventCreate(&ev_s0)); CK(cudaEventCreate(&ev_s1)); CK(cudaEventCreate(&ev_n0)); CK(cudaEventCreate(&ev_n1));
         // planes: unit outward normals, offsets
         memset(&ps_host, 0, sizeof(ps_host));
         ps_host.P = P;
@@ -231,7 +240,7 @@ struct Ctx : hvb_ctx {
         }
         int ppc = prm.points_per_cell > 0 ? prm.points_per_cell : default_points_per_cell(D);
         ncells = setup_grid<D>(dv, blo, bhi, n, ppc);
-        CK(xs_in.ensure((size_t)n * D)); CK(x64.ensure((size_t)n * D)); CK(x32.ensure((size_t)n * D));
+        CK(xs_in.ensure((size_t)n * D)); CK(x64.ensure((size_t)n * D)); CK(x32.ensure((size_t)n * X32<D>::STRIDE));
         CK(perm.ensure(n)); CK(inv.ensure(n)); CK(cell_of.ensure(n)); CK(unseeded_list.ensure(n));
         CK(cell_start.ensure(ncells + 1)); CK(cell_cur.ensure(ncells + 1));
         CK(active.ensure(n)); CK(has_vertex.ensure(n));
@@ -261,7 +270,7 @@ struct Ctx : hvb_ctx {
     template <int GG>
     void launch_seed_g(const int* seeds, int nseeds, int stride, int cur) {
         k_seed<D, GG><<<std::min(blocks_for((int64_t)nseeds * GG, 128), sms * 16), 128, 0, stream>>>(
-            dv, seeds, nseeds, stride, q[cur].p, &sc.p->qcount[cur], qcap);
+            dv, seeds, nseeds, stride, q[cur].p, &sc.p->rnd[cur].qcount, qcap);
         ++launches;
     }
     void launch_seed(const int* seeds, int nseeds, int stride, int cur) {
@@ -270,7 +279,7 @@ struct Ctx : hvb_ctx {
     template <int GG>
     void launch_expand_g(u32 cnt, int cur, int nxt) {
         k_expand<D, GG><<<std::min(blocks_for((int64_t)cnt * GG, 128), sms * 16), 128, 0, stream>>>(
-            dv, q[cur].p, &sc.p->qcount[cur], q[nxt].p, &sc.p->qcount[nxt], qcap);
+            dv, q[cur].p, &sc.p->rnd[cur].qcount, &sc.p->rnd[cur].cursor, q[nxt].p, &sc.p->rnd[nxt].qcount, qcap);
     }
     void launch_expand(u32 cnt, int cur, int nxt) {
         switch (G) {
@@ -356,17 +365,25 @@ struct Ctx : hvb_ctx {
             }
             int nseeds = (int)((n + sstride - 1) / sstride);
             int cur = 0;
+            CK(cudaEventRecord(ev_s0, stream));
             launch_seed(nullptr, nseeds, sstride, cur);
+            CK(cudaEventRecord(ev_s1, stream));
             if (debug) fprintf(stderr, "[hvb] seeds=%d stride=%d G=%d vcap=%lld ncells=%lld\n", nseeds, sstride, G, (long long)vcap, (long long)ncells);
             bool overflow = false;
             u32 last_uns = 0xffffffffu, last_vcount = 0;
             for (;;) {
                 int rc = read_scalars(); if (rc) return rc;
                 if (h_sc.p->pflags || h_ctr.p->flags) { overflow = true; break; }
-                u32 cnt = h_sc.p->qcount[cur];
+                if (h_ctr.p->degenerate > 0 && !prm.on_degenerate) {
+                    // non-general position (edgeiterate.jl territory): stop at once instead of walking a corrupt frontier
+                    st.degenerate = (int64_t)h_ctr.p->degenerate;
+                    err = "non-general position: a vertex with more than dim+1 cospherical generators was met";
+                    return HVB_EDEGENERATE;
+                }
+                u32 cnt = h_sc.p->rnd[cur].qcount;
                 if (cnt > 0) {
                     int nxt = 1 - cur;
-                    CK(cudaMemsetAsync(&sc.p->qcount[nxt], 0, sizeof(u32), stream));
+                    CK(cudaMemsetAsync(&sc.p->rnd[nxt], 0, sizeof(Round), stream));
                     cudaEvent_t e0 = pool_event(n_ev++), e1 = pool_event(n_ev++);
                     CK(cudaEventRecord(e0, stream));
                     if (debug) fprintf(stderr, "[hvb] round %lld frontier=%u vertices=%u\n", (long long)rounds, cnt, h_sc.p->vcount);
@@ -384,7 +401,7 @@ struct Ctx : hvb_ctx {
                 if (uns == 0) break;
                 if (uns == last_uns && h_sc.p->vcount == last_vcount) break;   // descents keep failing: give up (HVB_EINCOMPLETE)
                 last_uns = uns; last_vcount = h_sc.p->vcount;
-                CK(cudaMemsetAsync(&sc.p->qcount[cur], 0, sizeof(u32), stream));
+                CK(cudaMemsetAsync(&sc.p->rnd[cur], 0, sizeof(Round), stream));
                 if (debug) fprintf(stderr, "[hvb] reseeding %u empty cells\n", uns);
                 launch_seed(unseeded_list.p, (int)uns, 1, cur);
                 ++rounds;
@@ -399,13 +416,18 @@ struct Ctx : hvb_ctx {
         CK(cudaEventRecord(ev_c, stream));
         rc = stage(); if (rc) return rc;
         have_result = true;
+        CK(cudaEventRecord(ev_n0, stream));
         if (prm.neighbors) { rc = build_neighbors(); if (rc) return rc; rc = stage_neighbors(); if (rc) return rc; }
+        CK(cudaEventRecord(ev_n1, stream));
         CK(cudaEventRecord(ev_d, stream));
         CK(cudaStreamSynchronize(stream));
         CK(cudaGetLastError());
         float ms = 0;
         cudaEventElapsedTime(&ms, ev_a, ev_b); st.ms_search = ms;
         cudaEventElapsedTime(&ms, ev_b, ev_d); st.ms_finalize = ms;
+        cudaEventElapsedTime(&ms, ev_s0, ev_s1); st.ms_seed = ms;
+        cudaEventElapsedTime(&ms, ev_n0, ev_n1); st.ms_neighbors = ms;
+        cudaEventElapsedTime(&ms, ev_b, ev_c); st.ms_rows_sort = ms;
         double kms = 0;
         for (size_t i = 0; i + 1 < n_ev; i += 2) { cudaEventElapsedTime(&ms, ev_pool[i], ev_pool[i + 1]); kms += ms; }
         st.ms_expand_kernel = kms; st.expand_launches = expand_launches; st.expand_items = items;

@@ -160,7 +160,7 @@ struct Dev {
     double hmin, diag;                 // smallest cell edge, diagonal of the bounding box
     double ext;                        // largest bounding-box extent: scale of the FP32 coordinate error
     const int* cell_start;             // [ncells + 1]
-    const float* x32;                  // [n][D]  coordinates minus lo, FP32 (filter)
+    const float* x32;                  // [n][X32<D>::STRIDE]  coordinates minus lo, FP32, padded (filter)
     const double* x64;                 // [n][D]  coordinates, FP64 (verification)
     const PlaneSet* planes;
     const unsigned char* active;       // [n] 1 = this context walks the edges of that cell (slab / Iter)
@@ -188,6 +188,32 @@ HVB_HD int cell_index(const Dev<D>& dv, const double* x) {
         idx = idx * dv.g[k] + (int)floor(v);
     }
     return idx;
+}
+
+// FP32 filter coordinates are padded to a vector-load friendly stride: 2, 4, 4, 8, 8 floats for d = 2..6
+template <int D>
+struct X32 { static const int STRIDE = (D == 2) ? 2 : (D <= 4) ? 4 : 8; };
+
+template <int D>
+HVB_HD void load_x32(const float* base, int idx, float (&x)[D]) {
+#if defined(__CUDA_ARCH__)
+    float t[8];
+    if (D == 2) {
+        float2 v = __ldg(reinterpret_cast<const float2*>(base) + idx);
+        t[0] = v.x; t[1] = v.y;
+    } else if (D <= 4) {
+        float4 v = __ldg(reinterpret_cast<const float4*>(base) + idx);
+        t[0] = v.x; t[1] = v.y; t[2] = v.z; t[3] = v.w;
+    } else {
+        float4 v = __ldg(reinterpret_cast<const float4*>(base) + 2 * (size_t)idx);
+        float4 w = __ldg(reinterpret_cast<const float4*>(base) + 2 * (size_t)idx + 1);
+        t[0] = v.x; t[1] = v.y; t[2] = v.z; t[3] = v.w; t[4] = w.x; t[5] = w.y; t[6] = w.z; t[7] = w.w;
+    }
+#pragma unroll
+    for (int k = 0; k < D; ++k) x[k] = t[k];
+#else
+    for (int k = 0; k < D; ++k) x[k] = base[(size_t)idx * X32<D>::STRIDE + k];
+#endif
 }
 
 struct LocalStats {
@@ -220,6 +246,13 @@ const u64 EDGE_FPMASK = (0x7ffffffULL << 36) | (1ULL << 63);
 // ------------------------------------------------------------------------------------------------------------
 // geometry
 // ------------------------------------------------------------------------------------------------------------
+HVB_HD double inv_sqrt(double x) {
+#if defined(__CUDA_ARCH__)
+    return rsqrt(x);
+#else
+    return 1.0 / sqrt(x);
+#endif
+}
 template <int D>
 HVB_HD double dotD(const double* a, const double* b) {
     double s = 0;
@@ -247,9 +280,9 @@ HVB_HD bool ortho_direction(double (&V)[D + 1][D], unsigned mask, double (&v)[D]
 #pragma unroll
                         for (int k = 0; k < D; ++k) V[i][k] -= s * V[j][k];
                     }
-                double nr = sqrt(dotD<D>(V[i], V[i]));
-                ok &= (nr > 0);
-                double inv = 1.0 / nr;
+                double nr2 = dotD<D>(V[i], V[i]);
+                ok &= (nr2 > 0);
+                double inv = inv_sqrt(nr2);
 #pragma unroll
                 for (int k = 0; k < D; ++k) V[i][k] *= inv;
             }
@@ -264,9 +297,9 @@ HVB_HD bool ortho_direction(double (&V)[D + 1][D], unsigned mask, double (&v)[D]
 #pragma unroll
                 for (int k = 0; k < D; ++k) v[k] -= s * V[j][k];
             }
-        double nr = sqrt(dotD<D>(v, v));
-        ok &= (nr > 0);
-        double inv = 1.0 / nr;
+        double nr2 = dotD<D>(v, v);
+        ok &= (nr2 > 0);
+        double inv = inv_sqrt(nr2);
 #pragma unroll
         for (int k = 0; k < D; ++k) v[k] *= inv;
     }
@@ -364,6 +397,161 @@ HVB_HD Filt make_filter(double t_best, double rho, double R0, double ext) {
 
 // Smallest t > 0 at which the ball centred at r + t u through x0 touches another generator or boundary plane.
 // All lanes of the tile call this with identical q; all return the same Best.
+// FP32 description of the current probe ball in grid-relative coordinates (used while the ball is of the order of
+// the cloud; far-away / huge balls of unbounded edges keep the FP64 path below).  Every quantity carries the margin
+// `m`, so the selected cells are a superset of the exact ones.
+template <int D>
+struct Ball32 {
+    float cen[D];      // centre minus grid origin
+    float rho2;        // squared radius, rounded up
+    float m;           // absolute safety margin on coordinates
+    float re[D];       // 1 / (cells of the box along axis k)
+};
+
+template <int D>
+HVB_HD bool row_range32(const Dev<D>& dv, const float (&uf)[D], const float (&x0f)[D], const int (&clo)[D], const int (&chi)[D],
+                        const Ball32<D>& b, int j, int& pa, int& pb) {
+    int base = 0;
+    float d2 = 0.f, umax = 0.f, uabs = 0.f;
+    int rem = j;
+    int cc[D];
+#pragma unroll
+    for (int k = D - 2; k >= 0; --k) {
+        int e = chi[k] - clo[k] + 1;
+        int qd = (int)(((float)rem + 0.5f) * b.re[k]);      // rem / e without an integer division (rem < 2^22)
+        cc[k] = clo[k] + (rem - qd * e);
+        rem = qd;
+    }
+#pragma unroll
+    for (int k = 0; k < D - 1; ++k) {
+        float hk = (float)dv.h[k];
+        float blo = (float)cc[k] * hk - b.m;
+        float bhi = blo + hk + 2.f * b.m;
+        float dd = fmaxf(0.f, fmaxf(blo - b.cen[k], b.cen[k] - bhi));
+        d2 = fmaf(dd, dd, d2);
+        umax += fmaxf(uf[k] * (blo - x0f[k]), uf[k] * (bhi - x0f[k]));
+        uabs += fabsf(uf[k]);
+        base = base * dv.g[k] + cc[k];
+    }
+    if (!(d2 <= b.rho2)) return false;
+    const int L = D - 1;
+    float s = sqrtf(b.rho2 - d2) * 1.000001f + b.m;
+    float zlo = b.cen[L] - s, zhi = b.cen[L] + s;
+    float ul = uf[L];
+    float slack = b.m * (uabs + fabsf(ul)) + 1e-5f * fabsf(umax) + 1e-6f * (float)dv.ext;
+    if (ul > 1e-3f) zlo = fmaxf(zlo, x0f[L] - (umax + slack) / ul * 1.00001f - b.m);
+    else if (ul < -1e-3f) zhi = fminf(zhi, x0f[L] - (umax + slack) / ul * 1.00001f + b.m);
+    else if (umax + slack + fabsf(ul) * (float)dv.ext * 2.f <= 0.f) return false;
+    float ihl = (float)dv.inv_h[L];
+    float gl = (float)dv.g[L];
+    float vlo = fminf(fmaxf(zlo * ihl - 2e-3f, 0.f), gl - 1.f);
+    float vhi = fminf(fmaxf(zhi * ihl + 2e-3f, -1.f), gl - 1.f);
+    int z0 = (int)floorf(vlo), z1 = (int)floorf(vhi);
+    if (z1 < z0) return false;
+    const int* cs = dv.cell_start + (size_t)base * dv.g[L];
+    pa = cs[z0]; pb = cs[z1 + 1];
+    return true;
+}
+
+// Point range [pa, pb) of grid row j of the current cell box: the cells of that row that can hold a generator
+// inside the search ball and on the positive side of the edge's hyperplane.  Issues the two cell_start loads.
+template <int D>
+HVB_HD bool row_range(const Dev<D>& dv, const RayQ<D>& q, const int (&clo)[D], const int (&chi)[D], const double (&cen)[D],
+                      double rho2, int j, int& pa, int& pb) {
+    int base = 0;
+    double d2 = 0, umax = 0;
+    int rem = j;
+    int cc[D];
+#pragma unroll
+    for (int k = D - 2; k >= 0; --k) {
+        int e = chi[k] - clo[k] + 1;
+        int qd = rem / e;
+        cc[k] = clo[k] + (rem - qd * e);
+        rem = qd;
+    }
+#pragma unroll
+    for (int k = 0; k < D - 1; ++k) {
+        double blo = dv.lo[k] + cc[k] * dv.h[k] - 1e-9 * dv.h[k];
+        double bhi = blo + dv.h[k] * (1.0 + 2e-9);
+        double dd = fmax(0.0, fmax(blo - cen[k], cen[k] - bhi));
+        d2 += dd * dd;
+        umax += fmax(q.u[k] * (blo - q.x0[k]), q.u[k] * (bhi - q.x0[k]));
+        base = base * dv.g[k] + cc[k];
+    }
+    if (!(d2 <= rho2)) return false;
+    const int L = D - 1;
+    double s = sqrt(rho2 - d2);
+    double zlo = cen[L] - s, zhi = cen[L] + s;
+    double ul = q.u[L];
+    double slack = 1e-9 * (dv.h[L] + fabs(umax));
+    if (ul > 1e-300) zlo = fmax(zlo, q.x0[L] - (umax + slack) / ul);
+    else if (ul < -1e-300) zhi = fmin(zhi, q.x0[L] - (umax + slack) / ul);
+    else if (umax + slack <= 0) return false;
+    double gl = (double)dv.g[L];
+    double vlo = fmin(fmax((zlo - dv.lo[L]) * dv.inv_h[L] - 1e-9, 0.0), gl - 1.0);
+    double vhi = fmin(fmax((zhi - dv.lo[L]) * dv.inv_h[L] + 1e-9, -1.0), gl - 1.0);
+    int z0 = (int)floor(vlo), z1 = (int)floor(vhi);
+    if (z1 < z0) return false;
+    const int* cs = dv.cell_start + (size_t)base * dv.g[L];
+    pa = cs[z0]; pb = cs[z1 + 1];
+    return true;
+}
+
+// FP32 pass over the points [pa, pb) in chunks of four: all loads of a chunk are issued before any arithmetic;
+// a candidate that survives the filter first tightens the bound from its own FP32 upper estimate, and only the
+// candidates that still survive are re-evaluated in FP64.
+template <int D>
+HVB_HD void scan_points(const Dev<D>& dv, const RayQ<D>& q, const float (&uf)[D], const float (&w2f)[D], const float (&x0f)[D],
+                        Filt& flt, int pa, int pb, Best& best, LocalStats& ls) {
+    ls.rows++;
+    ls.cand32 += (u32)(pb - pa);
+    if (!dv.fp32_filter) {
+        for (int p = pa; p < pb; ++p) verify64<D>(dv, q, p, best, ls);
+        return;
+    }
+    const int U = 4;
+    for (int p = pa; p < pb; p += U) {
+        float x[U][D];
+#pragma unroll
+        for (int i = 0; i < U; ++i) load_x32<D>(dv.x32, (p + i < pb) ? (p + i) : (pb - 1), x[i]);
+        float num[U], dh[U];
+        bool pass[U];
+#pragma unroll
+        for (int i = 0; i < U; ++i) {
+            float den = 0.f, nm = 0.f;
+#pragma unroll
+            for (int k = 0; k < D; ++k) {
+                float qk = x[i][k] - x0f[k];
+                den = fmaf(uf[k], qk, den);
+                nm = fmaf(qk, qk - w2f[k], nm);
+            }
+            num[i] = nm - flt.en;
+            dh[i] = den + flt.ed;
+            pass[i] = (p + i < pb) && dh[i] > 0.f && num[i] <= flt.tb2 * dh[i];
+            // FP32 self-tightening: the true 2t of this candidate is at most (num + en) / (den/2 - ed); only used
+            // when the denominator is safely positive (then the candidate is a valid one in FP64 as well)
+            float dl = den - flt.ed;
+            bool excluded = false;
+#pragma unroll
+            for (int e = 0; e < D + 1; ++e) excluded |= (e < q.nexcl && q.excl[e] == p + i);
+            if (pass[i] && !excluded && dl > flt.ed && num[i] > 0.f) {
+                float hi = (nm + flt.en) / dl * 1.000001f;
+                flt.tb2 = fminf(flt.tb2, hi);
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < U; ++i) {
+            if (pass[i] && num[i] <= flt.tb2 * dh[i]) {
+                double before = best.t;
+                verify64<D>(dv, q, p + i, best, ls);
+                if (best.t < before) flt.tb2 = fminf(flt.tb2, (float)(2.0 * best.t * (1.0 + 4.8e-7)) * 1.0000005f);
+            }
+        }
+    }
+}
+
+// Smallest t > 0 at which the ball centred at r + t u through x0 touches another generator or boundary plane.
+// All lanes of the tile call this with identical q; all return the same Best.
 template <int D, class T>
 HVB_HD Best min_t_query(const Dev<D>& dv, const T& tile, const RayQ<D>& q, LocalStats& ls) {
     Best best;
@@ -439,78 +627,33 @@ HVB_HD Best min_t_query(const Dev<D>& dv, const T& tile, const RayQ<D>& q, Local
         }
         if (empty) nrows = 0;
         Filt flt = make_filter<D>(halfspace_mode ? INFINITY : Ts, rho, R0, dv.ext);
-        double t_seen = best.t;
-
-        const int niter = (nrows + T::SIZE - 1) / T::SIZE;
-        for (int it = 0; it < niter; ++it) {
-            int j = it * T::SIZE + lane;
-            if (j < nrows) {
-                // decode the row
-                int base = 0;
-                double d2 = 0, umax = 0;
-                int rem = j;
-                int cc[D];
+        // FP32 row geometry while the ball is comparable to the cloud; FP64 for the huge balls of unbounded edges
+        double cmax = 0;
 #pragma unroll
-                for (int k = D - 2; k >= 0; --k) {
-                    int e = chi[k] - clo[k] + 1;
-                    cc[k] = clo[k] + rem % e;
-                    rem /= e;
-                }
+        for (int k = 0; k < D; ++k) cmax = fmax(cmax, fabs(cen[k] - dv.lo[k]));
+        const bool use32 = !halfspace_mode && rho < 32.0 * dv.diag && cmax < 32.0 * dv.diag && nrows < (1 << 22);
+        Ball32<D> b32;
+        if (use32) {
 #pragma unroll
-                for (int k = 0; k < D - 1; ++k) {
-                    double blo = dv.lo[k] + cc[k] * dv.h[k] - 1e-9 * dv.h[k];
-                    double bhi = blo + dv.h[k] * (1.0 + 2e-9);
-                    double dd = fmax(0.0, fmax(blo - cen[k], cen[k] - bhi));
-                    d2 += dd * dd;
-                    umax += fmax(q.u[k] * (blo - q.x0[k]), q.u[k] * (bhi - q.x0[k]));
-                    base = base * dv.g[k] + cc[k];
-                }
-                if (d2 <= rho2) {
-                    const int L = D - 1;
-                    double s = sqrt(rho2 - d2);
-                    double zlo = cen[L] - s, zhi = cen[L] + s;
-                    bool skip = false;
-                    double ul = q.u[L];
-                    double slack = 1e-9 * (dv.h[L] + fabs(umax));
-                    if (ul > 1e-300) zlo = fmax(zlo, q.x0[L] - (umax + slack) / ul);
-                    else if (ul < -1e-300) zhi = fmin(zhi, q.x0[L] - (umax + slack) / ul);
-                    else if (umax + slack <= 0) skip = true;
-                    if (!skip) {
-                        double gl = (double)dv.g[L];
-                        double vlo = fmin(fmax((zlo - dv.lo[L]) * dv.inv_h[L] - 1e-9, 0.0), gl - 1.0);
-                        double vhi = fmin(fmax((zhi - dv.lo[L]) * dv.inv_h[L] + 1e-9, -1.0), gl - 1.0);
-                        int z0 = (int)floor(vlo), z1 = (int)floor(vhi);
-                        if (z1 >= z0) {
-                            ls.rows++;
-                            const int* cs = dv.cell_start + (size_t)base * dv.g[L];
-                            int pa = cs[z0], pb = cs[z1 + 1];
-                            ls.cand32 += (u32)(pb - pa);
-                            if (dv.fp32_filter) {
-                                const float* xp = dv.x32 + (size_t)pa * D;
-                                for (int p = pa; p < pb; ++p, xp += D) {
-                                    float den = 0.f, num = 0.f;
-#pragma unroll
-                                    for (int k = 0; k < D; ++k) {
-                                        float qk = xp[k] - x0f[k];
-                                        den = fmaf(uf[k], qk, den);
-                                        num = fmaf(qk, qk - w2f[k], num);
-                                    }
-                                    float dh = den + flt.ed;
-                                    if (dh > 0.f && (num - flt.en) <= flt.tb2 * dh) {
-                                        verify64<D>(dv, q, p, best, ls);
-                                        if (best.t < t_seen) {
-                                            t_seen = best.t;
-                                            flt.tb2 = (float)(2.0 * best.t * (1.0 + 4.8e-7)) * 1.0000005f;
-                                        }
-                                    }
-                                }
-                            } else {
-                                for (int p = pa; p < pb; ++p) verify64<D>(dv, q, p, best, ls);
-                            }
-                        }
-                    }
-                }
+            for (int k = 0; k < D; ++k) {
+                b32.cen[k] = (float)(cen[k] - dv.lo[k]);
+                b32.re[k] = 1.0f / (float)(chi[k] - clo[k] + 1);
             }
+            b32.m = (float)(2e-6 * (dv.ext + cmax + rho));
+            b32.rho2 = (float)(rho2 * (1.0 + 1e-5)) * 1.000001f;
+        }
+
+        // rows lane, lane + G, ... ; the next row's range is requested before the current one is scanned
+        const int niter = (nrows + T::SIZE - 1) / T::SIZE;
+        int pa = 0, pb = 0, pa_n = 0, pb_n = 0;
+        bool have = (lane < nrows) && (use32 ? row_range32<D>(dv, uf, x0f, clo, chi, b32, lane, pa, pb)
+                                             : row_range<D>(dv, q, clo, chi, cen, rho2, lane, pa, pb));
+        for (int it = 0; it < niter; ++it) {
+            int jn = (it + 1) * T::SIZE + lane;
+            bool have_n = (jn < nrows) && (use32 ? row_range32<D>(dv, uf, x0f, clo, chi, b32, jn, pa_n, pb_n)
+                                                 : row_range<D>(dv, q, clo, chi, cen, rho2, jn, pa_n, pb_n));
+            if (have && pb > pa) scan_points<D>(dv, q, uf, w2f, x0f, flt, pa, pb, best, ls);
+            have = have_n; pa = pa_n; pb = pb_n;
             // share the best bound and shrink the ball
             if (T::SIZE > 1) best_reduce(tile, best);
             if (best.t < Ts) {
@@ -520,7 +663,11 @@ HVB_HD Best min_t_query(const Dev<D>& dv, const T& tile, const RayQ<D>& q, Local
                 rho2 = (q.R0sq - 2.0 * Ts * q.a + Ts * Ts) * (1.0 + 1e-12) + 1e-300;
                 rho = sqrt(rho2);
                 flt = make_filter<D>(Ts, rho, R0, dv.ext);
-                t_seen = best.t;
+                if (use32) {
+#pragma unroll
+                    for (int k = 0; k < D; ++k) b32.cen[k] = (float)(cen[k] - dv.lo[k]);
+                    b32.rho2 = (float)(rho2 * (1.0 + 1e-5)) * 1.000001f;
+                }
             }
         }
         if (best.t <= fmin(Tst, Ts) || !(Tst < INFINITY)) break;
@@ -595,15 +742,14 @@ HVB_HD bool edge_equal(const Dev<D>& dv, u64 s, const int* sig, int k) {
 }
 
 // Registers the sub-facet (sig minus position k) of vertex v.  First endpoint: the edge becomes an open frontier
-// entry (returns its slot); second endpoint: the edge is closed (returns ~0).  Replaces pushedge!
-// (edgehashing.jl:66-111) and queue_edges_OnFind (edgeiteratebase.jl:128-149).
+// entry (returns its slot); second endpoint: the edge is closed (returns ~0).  `h` is the edge hash and `s` the
+// already loaded content of its home slot.  Replaces pushedge! (edgehashing.jl:66-111) and queue_edges_OnFind
+// (edgeiteratebase.jl:128-149).
 template <int D>
-HVB_HD u64 edge_register(const Dev<D>& dv, const int* sig, u32 v, int k) {
-    u64 h = hash_ids<D>(sig, D + 1, k);
+HVB_HD u64 edge_register(const Dev<D>& dv, const int* sig, u32 v, int k, u64 h, u64 s) {
     u64 mine = edge_slot(h, v, k);
     u64 slot = h & dv.emask;
     for (;;) {
-        u64 s = ld_cg(dv.etab + slot);
         if (s == 0) {
             s = atom_cas(dv.etab + slot, 0ULL, mine);
             if (s == 0) return slot;
@@ -613,15 +759,36 @@ HVB_HD u64 edge_register(const Dev<D>& dv, const int* sig, u32 v, int k) {
             return ~0ULL;
         }
         slot = (slot + 1) & dv.emask;
+        s = ld_cg(dv.etab + slot);
     }
 }
 
+// frontier entry: [63:32] edge slot, [31:3] vertex index, [2:0] dropped position
+HVB_HD u64 frontier_entry(u64 slot, u32 v, int k) { return (slot << 32) | ((u64)v << 3) | (u64)k; }
+
 // Shared tail of a walk / a descent: store the vertex, register its d+1 sub-facets, append the open ones to the
-// next frontier.  sig sorted.  All lanes call; lane 0 inserts, lanes 0..D register one sub-facet each.
+// next frontier.  sig sorted.  All lanes call; lane 0 inserts, the sub-facets are dealt round-robin to the lanes.
+// The home slots of all sub-facets are loaded before any of them is processed (independent loads in flight).
 template <int D, class T>
 HVB_HD void commit_vertex(const Dev<D>& dv, const T& tile, const int* sig, const double* r,
-                          u32* q_out, u32* q_count, u32 q_cap, LocalStats& ls) {
+                          u64* q_out, u32* q_count, u32 q_cap, LocalStats& ls) {
     const int lane = tile.lane();
+    // which generators are real and belong to a cell this context explores
+    unsigned actmask = 0;
+#pragma unroll
+    for (int i = 0; i < D + 1; ++i)
+        if ((sig[i] < dv.n) && (dv.active[sig[i]] != 0)) actmask |= 1u << i;
+    // sub-facet k = pass * G + lane: every lane runs the SAME instructions on its own k (no serialisation by lane)
+    const int NPASS = (D + 1 + T::SIZE - 1) / T::SIZE;
+    u64 hs[NPASS], s0[NPASS];
+    bool mine[NPASS];
+#pragma unroll
+    for (int ps_ = 0; ps_ < NPASS; ++ps_) {
+        int k = ps_ * T::SIZE + lane;
+        mine[ps_] = (k < D + 1) && ((actmask & ~(1u << k)) != 0);     // the sub-facet keeps an explored real generator
+        hs[ps_] = 0; s0[ps_] = 0;
+        if (mine[ps_]) { hs[ps_] = hash_ids<D>(sig, D + 1, k); s0[ps_] = ld_cg(dv.etab + (hs[ps_] & dv.emask)); }
+    }
     u32 v = 0xffffffffu;
     if (lane == 0) v = vertex_insert<D>(dv, sig, r, ls);
     if (T::SIZE > 1) v = tile.shfl(v, 0);
@@ -631,17 +798,14 @@ HVB_HD void commit_vertex(const Dev<D>& dv, const T& tile, const int* sig, const
         for (int k = 0; k < D + 1; ++k)
             if (sig[k] < dv.n) dv.has_vertex[sig[k]] = 1;
     }
-    for (int k = lane; k < D + 1; k += T::SIZE) {
-        // the sub-facet must keep a real generator whose cell this context explores
-        bool act = false;
 #pragma unroll
-        for (int i = 0; i < D + 1; ++i)
-            if (i != k && sig[i] < dv.n) act |= (dv.active[sig[i]] != 0);
-        if (!act) continue;
-        u64 slot = edge_register<D>(dv, sig, v, k);
+    for (int ps_ = 0; ps_ < NPASS; ++ps_) {
+        if (!mine[ps_]) continue;
+        int k = ps_ * T::SIZE + lane;
+        u64 slot = edge_register<D>(dv, sig, v, k, hs[ps_], s0[ps_]);
         if (slot != ~0ULL) {
             u32 pos = atom_add(q_count, 1u);
-            if (pos < q_cap) q_out[pos] = (u32)slot;
+            if (pos < q_cap) q_out[pos] = frontier_entry(slot, v, k);
             else atom_or(&dv.ctr->flags, (u32)FLAG_QFULL);
         }
     }
@@ -660,17 +824,15 @@ HVB_HD void sorted_insert(int* sig, int cnt, int g) {
 // systematic_explore_vertex sysvoronoi.jl:490-525, one edge at a time)
 // ------------------------------------------------------------------------------------------------------------
 template <int D, class T>
-HVB_HD void expand_item(const Dev<D>& dv, const T& tile, u32 eslot, u32* q_out, u32* q_count, u32 q_cap, LocalStats& ls) {
+HVB_HD void expand_item(const Dev<D>& dv, const T& tile, u64 item, u64* q_out, u32* q_count, u32 q_cap, LocalStats& ls) {
     const int lane = tile.lane();
     // The closed bit is mutable: every lane must act on the SAME snapshot of the slot, otherwise part of the tile
     // leaves while the rest waits in a shuffle.  Lane 0 reads, the tile converges on the broadcast.
     tile.sync();
-    u64 s = 0;
-    if (lane == 0) s = ld_cg(dv.etab + eslot);
-    if (T::SIZE > 1) s = tile.shfl(s, 0);
-    if (s & EDGE_CLOSED) { ls.closed_skips += (lane == 0); return; }
-    const u32 v = (u32)((s >> 3) & 0xffffffffULL);
-    const int kd = (int)(s & 7);
+    const u32 eslot = (u32)(item >> 32);
+    const u32 v = (u32)((item >> 3) & 0x1fffffffULL);
+    const int kd = (int)(item & 7);
+    (void)eslot;                       // the closed bit was checked when the entry was acquired (k_expand)
     int sig[D + 1];
     RayQ<D> q;
 #pragma unroll
@@ -788,7 +950,7 @@ HVB_HD double unit_hash(u64& s) {          // deterministic stand-in for randn (
 }
 
 template <int D, class T>
-HVB_HD void seed_item(const Dev<D>& dv, const T& tile, int start, u32* q_out, u32* q_count, u32 q_cap, LocalStats& ls) {
+HVB_HD void seed_item(const Dev<D>& dv, const T& tile, int start, u64* q_out, u32* q_count, u32 q_cap, LocalStats& ls) {
     const int lane = tile.lane();
     tile.sync();
     ls.seeds += (lane == 0);
@@ -860,6 +1022,7 @@ HVB_HD void seed_item(const Dev<D>& dv, const T& tile, int start, u32* q_out, u3
                 best = min_t_query_call<D, T>(dv, tile, q, ls);
             }
             if (best.id < 0) { ok = false; break; }
+            if (best.t2 - best.t <= 1e-12 * fmax(best.t, sqrt(q.R0sq))) ls.degenerate += (lane == 0);
 #pragma unroll
             for (int k = 0; k < D; ++k) q.r[k] += best.t * q.u[k];
             sig[cnt++] = best.id;

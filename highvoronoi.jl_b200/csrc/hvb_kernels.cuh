@@ -45,13 +45,7 @@ __global__ void k_scatter(Dev<D> dv, const double* __restrict__ xs, const int* _
     if (i >= dv.n) return;
     int c = cell_of[i];
     int pos = cell_start[c] + atomicAdd(cursor + c, 1);
-    perm[pos] = i;
-#pragma unroll
-    for (int k = 0; k < D; ++k) {
-        double v = xs[(size_t)i * D + k];
-        x64[(size_t)pos * D + k] = v;
-        x32[(size_t)pos * D + k] = (float)(v - dv.lo[k]);
-    }
+    perm[pos] = i;                    // coordinates are written by k_cell_sort once the order inside the cell is fixed
 }
 
 // deterministic order inside a cell: sort each cell's entries by caller id (cells hold a handful of points)
@@ -70,10 +64,10 @@ __global__ void k_cell_sort(Dev<D> dv, const double* __restrict__ xs, const int*
     for (int i = a; i < b; ++i) {
         int o = perm[i];
 #pragma unroll
-        for (int k = 0; k < D; ++k) {
-            double v = xs[(size_t)o * D + k];
-            x64[(size_t)i * D + k] = v;
-            x32[(size_t)i * D + k] = (float)(v - dv.lo[k]);
+        for (int k = 0; k < X32<D>::STRIDE; ++k) {
+            double v = (k < D) ? xs[(size_t)o * D + (k < D ? k : 0)] : 0.0;
+            if (k < D) x64[(size_t)i * D + k] = v;
+            x32[(size_t)i * X32<D>::STRIDE + k] = (k < D) ? (float)(v - dv.lo[k < D ? k : 0]) : 0.f;
         }
     }
 }
@@ -98,7 +92,7 @@ __global__ void k_mark_cells(const long long* __restrict__ cells, long long ncel
 // ------------------------------------------------------------------------------------------------------------
 template <int D, int G>
 __global__ void __launch_bounds__(128) k_seed(Dev<D> dv, const int* __restrict__ seeds, int nseeds, int stride,
-                                              u32* q_out, u32* q_count, u32 q_cap) {
+                                              u64* q_out, u32* q_count, u32 q_cap) {
     TileDev<G> tile;
     LocalStats ls = {};
     const int tiles_per_block = blockDim.x / G;
@@ -113,16 +107,35 @@ __global__ void __launch_bounds__(128) k_seed(Dev<D> dv, const int* __restrict__
 #ifndef HVB_EXPAND_MINB
 #define HVB_EXPAND_MINB 1
 #endif
+// One frontier round.  Tiles pull entries from a shared cursor and skip closed edges while acquiring, so that all
+// tiles of a warp enter the expensive part (direction, min-t query, commit) with live work.
 template <int D, int G>
-__global__ void __launch_bounds__(128, HVB_EXPAND_MINB) k_expand(Dev<D> dv, const u32* __restrict__ q_in, const u32* __restrict__ n_in_ptr,
-                                                u32* q_out, u32* q_count, u32 q_cap) {
+__global__ void __launch_bounds__(128, HVB_EXPAND_MINB) k_expand(Dev<D> dv, const u64* __restrict__ q_in, const u32* __restrict__ n_in_ptr,
+                                                                 u32* cursor, u64* q_out, u32* q_count, u32 q_cap) {
     TileDev<G> tile;
     LocalStats ls = {};
     const u32 n_in = min(*n_in_ptr, q_cap);
-    const u32 tiles_per_block = blockDim.x / G;
-    const u32 ntiles = gridDim.x * tiles_per_block;
-    for (u32 it = blockIdx.x * tiles_per_block + threadIdx.x / G; it < n_in; it += ntiles)
-        expand_item<D, TileDev<G> >(dv, tile, q_in[it], q_out, q_count, q_cap, ls);
+    for (;;) {
+        u64 item = 0;
+        int live = 0;
+        if (tile.lane() == 0) {
+            for (;;) {
+                u32 idx = atomicAdd(cursor, 1u);
+                if (idx >= n_in) break;
+                u64 it = q_in[idx];
+                u64 s = __ldcg(dv.etab + (u32)(it >> 32));
+                if (s & EDGE_CLOSED) { ls.closed_skips++; continue; }
+                item = it; live = 1;
+                break;
+            }
+        }
+        if (G > 1) { item = tile.shfl(item, 0); live = tile.shfl(live, 0); }
+        // warp-uniform loop: every lane stays until no tile of the warp has work, and all tiles start their entries
+        // together (without this the lanes drift apart for good and the warp executes one lane at a time)
+        if (!__any_sync(0xffffffffu, live)) break;
+        if (live) expand_item<D, TileDev<G> >(dv, tile, item, q_out, q_count, q_cap, ls);
+        __syncwarp();
+    }
     flush_stats(ls, dv.ctr);
 }
 

@@ -84,6 +84,9 @@ typedef struct hvb_stats_t {
     double  ms_expand_kernel; /* device time of the dominant kernel (walk/expand), summed */
     int64_t expand_launches;
     int64_t expand_items;     /* frontier entries processed by it                         */
+    double  ms_seed;          /* device time of the first descent kernel                  */
+    double  ms_neighbors;     /* neighbour lists (when built inside hvb_search) + staging  */
+    double  ms_rows_sort;     /* part of ms_finalize: canonical rows + lexicographic sort  */
 } hvb_stats_t;
 
 /* fills *p with the reference's defaults (RaycastParameter(Float64), raycast-types.jl:312-324) */

@@ -34,9 +34,9 @@ static SimResult* run(int64_t n, const double* xs, int P, const double* base, co
     for (int64_t i = 0; i < n; ++i) { cell[i] = cell_index<D>(dv, xs + i * D); cstart[cell[i] + 1]++; }
     for (int64_t c = 0; c < ncell; ++c) cstart[c + 1] += cstart[c];
     { std::vector<int> cur(cstart.begin(), cstart.end() - 1); for (int64_t i = 0; i < n; ++i) perm[cur[cell[i]]++] = (int)i; }
-    std::vector<double> x64(n * D); std::vector<float> x32(n * D);
+    std::vector<double> x64(n * D); std::vector<float> x32(n * X32<D>::STRIDE, 0.f);
     for (int64_t i = 0; i < n; ++i)
-        for (int k = 0; k < D; ++k) { x64[i * D + k] = xs[(int64_t)perm[i] * D + k]; x32[i * D + k] = (float)(x64[i * D + k] - dv.lo[k]); }
+        for (int k = 0; k < D; ++k) { x64[i * D + k] = xs[(int64_t)perm[i] * D + k]; x32[i * X32<D>::STRIDE + k] = (float)(x64[i * D + k] - dv.lo[k]); }
     PlaneSet ps; memset(&ps, 0, sizeof(ps)); ps.P = P;
     for (int p = 0; p < P; ++p) {
         double nr = 0; for (int k = 0; k < D; ++k) nr += normal[p * D + k] * normal[p * D + k];
@@ -59,7 +59,7 @@ static SimResult* run(int64_t n, const double* xs, int P, const double* base, co
     dv.etab = etab.data(); dv.emask = ets - 1; dv.has_vertex = hasv.data();
     dv.ray_item = ritem.data(); dv.ray_u = ru.data(); dv.ray_count = &rcount; dv.ray_cap = rcap; dv.ctr = &ctr;
     u32 qcap = (u32)std::min<u64>(ets, 0xfffffff0u);
-    std::vector<u32> qa(qcap), qb(qcap);
+    std::vector<u64> qa(qcap), qb(qcap);
     u32 na = 0, nb = 0;
     TileHost tile; LocalStats ls; memset(&ls, 0, sizeof(ls));
     if (seed_stride <= 0) seed_stride = 16;
@@ -68,7 +68,10 @@ static SimResult* run(int64_t n, const double* xs, int P, const double* base, co
     for (;;) {
         while (na > 0) {
             nb = 0;
-            for (u32 i = 0; i < na; ++i) expand_item<D, TileHost>(dv, tile, qa[i], qb.data(), &nb, qcap, ls);
+            for (u32 i = 0; i < na; ++i) {
+                if (etab[(u32)(qa[i] >> 32)] & EDGE_CLOSED) { ls.closed_skips++; continue; }   // as in k_expand
+                expand_item<D, TileHost>(dv, tile, qa[i], qb.data(), &nb, qcap, ls);
+            }
             qa.swap(qb); na = nb; ++rounds;
         }
         // cells without any vertex get their own descent (sysvoronoi.jl:416-429)
