@@ -101,7 +101,7 @@ struct hvb_ctx {
 
 template <int D>
 struct Ctx : hvb_ctx {
-    int G = (D == 2) ? 4 : (D == 3) ? 4 : (D == 4) ? 8 : 16;       // lanes per frontier entry (prm.tile_size overrides)
+    int G = 1;                       // lanes per frontier entry; 1 measured best for d = 2..5 (prm.tile_size overrides)
     bool debug = false;
     cudaStream_t stream = nullptr;
     int sms = 148;

@@ -48,3 +48,13 @@ def test_offset_and_anisotropic_cloud(oracle):
     xs = points(1200, 3, 6) * np.array([10.0, 1.0, 0.1]) + np.array([1000.0, -500.0, 3.0])
     o, s = oracle.run(xs), hostsim.run(xs)
     assert np.array_equal(s["sig"], o["sig"])
+
+
+@pytest.mark.parametrize("d,n,seed", [(3, 1500, 7004), (2, 2500, 7001), (3, 1200, 7007), (4, 350, 7001)])
+def test_far_vertices_of_flat_hull_simplices(oracle, d, n, seed):
+    """stretched, offset, unbounded clouds have vertices 10^5 cloud diameters away: the walk towards and away from
+    them runs in half-space mode (regression: a NaN FP32 lower bound dropped every candidate there)"""
+    xs = np.random.default_rng(seed).random((n, d)) * np.array([7.0, 0.3, 1.0, 2.0][:d]) + 100.0
+    o, s = oracle.run(xs), hostsim.run(xs)
+    assert np.array_equal(s["sig"], o["sig"])
+    assert sorted(map(tuple, s["ray_edge"].tolist())) == sorted(map(tuple, o["ray_edge"].tolist()))
