@@ -163,28 +163,9 @@ def main():
         return float(t.item())
 
     def gather_merge(searcher):
-        """multi-GPU exchange: counts + padded payload by NCCL all-gather, dedup + sort on every rank"""
-        ctx = searcher._ctx
-        nv = ctypes.c_int64()
-        _abi.check(L.hvb_counts(ctx, ctypes.byref(nv), None, None), ctx)
-        cnt = torch.tensor([nv.value], dtype=torch.int64, device="cuda")
-        cnts = [torch.zeros_like(cnt) for _ in range(world)]
-        dist.all_gather(cnts, cnt)
-        cnts = [int(c.item()) for c in cnts]
-        cap = max(cnts)
-        sig = torch.zeros((cap, d + 1), dtype=torch.int64, device="cuda")
-        r = torch.zeros((cap, d), dtype=torch.float64, device="cuda")
-        got = ctypes.c_int64()
-        _abi.check(L.hvb_export_device(ctx, sig.data_ptr(), r.data_ptr(), cap, ctypes.byref(got)), ctx)
-        sig_all = torch.empty((world * cap, d + 1), dtype=torch.int64, device="cuda")
-        r_all = torch.empty((world * cap, d), dtype=torch.float64, device="cuda")
-        dist.all_gather_into_tensor(sig_all, sig)
-        dist.all_gather_into_tensor(r_all, r)
-        keep = torch.cat([torch.arange(k * cap, k * cap + c, device="cuda") for k, c in enumerate(cnts)])
-        sig_c, r_c = sig_all[keep].contiguous(), r_all[keep].contiguous()
-        torch.cuda.synchronize()
-        _abi.check(L.hvb_merge_device(ctx, sig_c.data_ptr(), r_c.data_ptr(), sig_c.shape[0]), ctx)
-        return (sig.numel() + r.numel()) * 8
+        """multi-GPU exchange: counts + padded rows by NCCL all-gather, dedup + sort on every rank"""
+        from hvb200 import multigpu
+        return multigpu.gather_and_merge(searcher)
 
     state = {"s": None}
     phases = np.zeros(4)
