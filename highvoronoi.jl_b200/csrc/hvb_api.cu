@@ -75,8 +75,11 @@ struct Scalars {            // small device-side words, mirrored into pinned hos
     u32 unseeded;
     u32 out_count;
     u32 pflags;
-    u32 pad;
+    u32 bbox_done;
+    u32 bbox_viol;
+    u32 pad2;
     double max_var;
+    double bbox[12];
 };
 
 struct hvb_ctx {
@@ -103,7 +106,8 @@ template <int D>
 struct Ctx : hvb_ctx {
     int G = 1;                       // lanes per frontier entry; 1 measured best for d = 2..5 (prm.tile_size overrides)
     bool debug = false;
-    cudaStream_t stream = nullptr;
+    cudaStream_t stream = nullptr, sstream = nullptr;    // compute stream, result-staging (D2H) stream
+    cudaEvent_t ev_stage = nullptr;
     int sms = 148;
     Dev<D> dv;
     int64_t ncells = 0;
@@ -114,6 +118,7 @@ struct Ctx : hvb_ctx {
     DBuf<PlaneSet> planes;
     DBuf<unsigned char> active, has_vertex;
     DBuf<char> cub_tmp;
+    DBuf<double> bbox_partial;
     // search state
     int64_t vcap = 0;
     DBuf<int> vsig;
@@ -156,7 +161,7 @@ struct Ctx : hvb_ctx {
         cudaSetDevice(prm.device);
         if (stream) cudaStreamSynchronize(stream);
         xs_in.release(); x64.release(); x32.release(); perm.release(); inv.release(); cell_of.release(); cell_start.release();
-        cell_cur.release(); unseeded_list.release(); planes.release(); active.release(); has_vertex.release(); cub_tmp.release();
+        cell_cur.release(); unseeded_list.release(); bbox_partial.release(); planes.release(); active.release(); has_vertex.release(); cub_tmp.release();
         vsig.release(); vr.release(); vtab.release(); etab.release(); q[0].release(); q[1].release(); ray_item.release(); ray_u.release();
         ctr.release(); sc.release(); h_sc.release(); h_ctr.release(); cells_dev.release();
         out_sig[0].release(); out_sig[1].release(); out_r[0].release(); out_r[1].release(); key_hi.release(); key_lo.release(); key_tmp.release();
@@ -167,10 +172,13 @@ struct Ctx : hvb_ctx {
         if (ev_b) cudaEventDestroy(ev_b);
         if (ev_c) cudaEventDestroy(ev_c);
         if (ev_d) cudaEventDestroy(ev_d);
+        if (ev_sd) cudaEventDestroy(ev_sd);
         if (ev_s0) cudaEventDestroy(ev_s0);
         if (ev_s1) cudaEventDestroy(ev_s1);
         if (ev_n0) cudaEventDestroy(ev_n0);
         if (ev_n1) cudaEventDestroy(ev_n1);
+        if (ev_stage) cudaEventDestroy(ev_stage);
+        if (sstream) { cudaStreamSynchronize(sstream); cudaStreamDestroy(sstream); }
         if (stream) cudaStreamDestroy(stream);
     }
 
@@ -185,6 +193,8 @@ struct Ctx : hvb_ctx {
         CK(cudaSetDevice(prm.device));
         CK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, prm.device));
         CK(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
+        CK(cudaStreamCreateWithFlags(&sstream, cudaStreamNonBlocking));
+        CK(cudaEventCreateWithFlags(&ev_stage, cudaEventDisableTiming));
         CK(cudaEventCreate(&ev_a)); CK(cudaEventCreate(&ev_b)); CK(cudaEventCreate(&ev_c)); CK(cudaEventCreate(&ev_d));
         CK(cudaEventCreate(&ev_s0)); CK(cudaEventCreate(&ev_s1)); CK(cudaEventCreate(&ev_n0)); CK(cudaEventCreate(&ev_n1));
         // planes: unit outward normals, offsets
@@ -219,32 +229,44 @@ struct Ctx : hvb_ctx {
         n = n_new;
         CK(cudaEventRecord(ev_a, stream));
         dv.n = (int)n;
-        const PlaneSet& ps = ps_host;
-        // bounding box + domain check (check_boundary, boundary.jl:437)
-        double blo[D], bhi[D];
-        for (int k = 0; k < D; ++k) { blo[k] = 1e300; bhi[k] = -1e300; }
-        for (int64_t i = 0; i < n; ++i) {
-            const double* x = xs + i * D;
-            for (int k = 0; k < D; ++k) {
-                if (!(x[k] == x[k]) || fabs(x[k]) > 1e150) { err = "non-finite generator coordinate"; return HVB_EINVAL; }
-                blo[k] = std::min(blo[k], x[k]); bhi[k] = std::max(bhi[k], x[k]);
-            }
-            for (int p = 0; p < P; ++p) {
-                double s = 0;
-                for (int k = 0; k < D; ++k) s += ps.normal[p * 6 + k] * x[k];
-                if (s > ps.off[p]) {
-                    char b[160]; snprintf(b, sizeof(b), "generator %lld does not lie in the domain (plane %d)", (long long)(i + 1), p + 1);
-                    err = b; return HVB_EINVAL;
+        // upload, then bounding box + domain check on the device (check_boundary, boundary.jl:437)
+        CK(xs_in.ensure((size_t)n * D));
+        CK(cudaMemcpyAsync(xs_in.p, xs, (size_t)n * D * sizeof(double), cudaMemcpyHostToDevice, stream));
+        const int bb_blocks = std::min(blocks_for(n, 256), sms * 4);
+        CK(bbox_partial.ensure((size_t)bb_blocks * 2 * D));
+        CK(cudaMemsetAsync(&sc.p->bbox_done, 0, sizeof(u32), stream));
+        CK(cudaMemsetAsync(&sc.p->bbox_viol, 0xff, sizeof(u32), stream));
+        k_bbox_check<D><<<bb_blocks, 256, 0, stream>>>(xs_in.p, (int)n, planes.p, bbox_partial.p, &sc.p->bbox_done, sc.p->bbox, &sc.p->bbox_viol);
+        ++launches;
+        CK(cudaMemcpyAsync(h_sc.p, sc.p, sizeof(Scalars), cudaMemcpyDeviceToHost, stream));
+        CK(cudaStreamSynchronize(stream));
+        CK(cudaGetLastError());
+        if (h_sc.p->bbox_viol != 0xffffffffu) {
+            const double* x = xs + (size_t)h_sc.p->bbox_viol * D;
+            bool finite = true;
+            for (int k = 0; k < D; ++k) finite &= (x[k] == x[k]) && fabs(x[k]) <= 1e150;
+            char b[200];
+            if (!finite) snprintf(b, sizeof(b), "non-finite coordinate in generator %u", h_sc.p->bbox_viol + 1);
+            else {
+                int pbad = 0;
+                for (int p = 0; p < P; ++p) {
+                    double sdot = 0;
+                    for (int k = 0; k < D; ++k) sdot += ps_host.normal[p * 6 + k] * x[k];
+                    if (sdot > ps_host.off[p]) { pbad = p + 1; break; }
                 }
+                snprintf(b, sizeof(b), "generator %u does not lie in the domain (plane %d)", h_sc.p->bbox_viol + 1, pbad);
             }
+            err = b;
+            return HVB_EINVAL;
         }
+        double blo[D], bhi[D];
+        for (int k = 0; k < D; ++k) { blo[k] = h_sc.p->bbox[k]; bhi[k] = h_sc.p->bbox[D + k]; }
         int ppc = prm.points_per_cell > 0 ? prm.points_per_cell : default_points_per_cell(D);
         ncells = setup_grid<D>(dv, blo, bhi, n, ppc);
-        CK(xs_in.ensure((size_t)n * D)); CK(x64.ensure((size_t)n * D)); CK(x32.ensure((size_t)n * X32<D>::STRIDE));
+        CK(x64.ensure((size_t)n * D)); CK(x32.ensure((size_t)n * X32<D>::STRIDE));
         CK(perm.ensure(n)); CK(inv.ensure(n)); CK(cell_of.ensure(n)); CK(unseeded_list.ensure(n));
         CK(cell_start.ensure(ncells + 1)); CK(cell_cur.ensure(ncells + 1));
         CK(active.ensure(n)); CK(has_vertex.ensure(n));
-        CK(cudaMemcpyAsync(xs_in.p, xs, (size_t)n * D * sizeof(double), cudaMemcpyHostToDevice, stream));
         dv.cell_start = cell_start.p; dv.x32 = x32.p; dv.x64 = x64.p; dv.planes = planes.p; dv.active = active.p;
         dv.has_vertex = has_vertex.p; dv.ctr = ctr.p;
         // counting sort into cells
@@ -414,11 +436,13 @@ struct Ctx : hvb_ctx {
         CK(cudaEventRecord(ev_b, stream));
         int rc = finalize(); if (rc) return rc;
         CK(cudaEventRecord(ev_c, stream));
-        rc = stage(); if (rc) return rc;
+        // a slab result is an intermediate: it is exported to the exchange step, not staged for the host
+        if (world == 1) { rc = stage(); if (rc) return rc; }
         have_result = true;
         CK(cudaEventRecord(ev_n0, stream));
         if (prm.neighbors) { rc = build_neighbors(); if (rc) return rc; rc = stage_neighbors(); if (rc) return rc; }
         CK(cudaEventRecord(ev_n1, stream));
+        CK(cudaStreamWaitEvent(stream, ev_stage_done(), 0));
         CK(cudaEventRecord(ev_d, stream));
         CK(cudaStreamSynchronize(stream));
         CK(cudaGetLastError());
@@ -489,6 +513,7 @@ struct Ctx : hvb_ctx {
         }
         int rc = read_scalars(); if (rc) return rc;
         nvert = h_sc.p->out_count;
+        if (std::max(1, prm.world) > 1) { res = 0; return HVB_OK; }     // slab rows are sorted after the merge
         return sort_rows((u32)nvert, bits);
     }
 
@@ -496,13 +521,22 @@ struct Ctx : hvb_ctx {
     int stage() {
         CK(h_sig.ensure((size_t)std::max<int64_t>(nvert, 1) * (D + 1))); CK(h_r.ensure((size_t)std::max<int64_t>(nvert, 1) * D));
         if (nvert > 0) {
-            CK(cudaMemcpyAsync(h_sig.p, out_sig[res].p, (size_t)nvert * (D + 1) * sizeof(long long), cudaMemcpyDeviceToHost, stream));
-            CK(cudaMemcpyAsync(h_r.p, out_r[res].p, (size_t)nvert * D * sizeof(double), cudaMemcpyDeviceToHost, stream));
+            // on the staging stream, so that the copy overlaps whatever the compute stream does next (neighbour lists)
+            CK(cudaEventRecord(ev_stage, stream));
+            CK(cudaStreamWaitEvent(sstream, ev_stage, 0));
+            CK(cudaMemcpyAsync(h_sig.p, out_sig[res].p, (size_t)nvert * (D + 1) * sizeof(long long), cudaMemcpyDeviceToHost, sstream));
+            CK(cudaMemcpyAsync(h_r.p, out_r[res].p, (size_t)nvert * D * sizeof(double), cudaMemcpyDeviceToHost, sstream));
         }
         staged = true;
         return HVB_OK;
     }
 
+    cudaEvent_t ev_sd = nullptr;
+    cudaEvent_t ev_stage_done() {          // an event on the staging stream that marks "everything staged so far is in host memory"
+        if (!ev_sd) cudaEventCreateWithFlags(&ev_sd, cudaEventDisableTiming);
+        cudaEventRecord(ev_sd, sstream);
+        return ev_sd;
+    }
     int counts(int64_t* nv, int64_t* nr, int64_t* msl) override {
         if (!have_result) { err = "no search result"; return HVB_ESTATE; }
         if (nv) *nv = nvert;
@@ -515,6 +549,7 @@ struct Ctx : hvb_ctx {
         CK(cudaSetDevice(prm.device));
         if (!staged) { int rc = stage(); if (rc) return rc; }
         CK(cudaStreamSynchronize(stream));
+        CK(cudaStreamSynchronize(sstream));
         *sig = (const int64_t*)h_sig.p; *r = h_r.p; *nv = nvert;
         return HVB_OK;
     }
@@ -635,7 +670,7 @@ struct Ctx : hvb_ctx {
         nvert = h_sc.p->out_count;
         rc = sort_rows((u32)nvert, bits); if (rc) return rc;
         nb_total = -1;
-        rc = stage(); if (rc) return rc;
+        staged = false;                      // staged on the first hvb_view_* / hvb_fetch_* (only ranks that read the result pay the D2H)
         CK(cudaStreamSynchronize(stream));
         CK(cudaGetLastError());
         st.vertices = nvert; st.kernel_launches = launches;

@@ -453,6 +453,62 @@ HVB_HD bool row_range32(const Dev<D>& dv, const float (&uf)[D], const float (&x0
     return true;
 }
 
+// Same as row_range32, but tells how far the row index may jump when the row is pruned: the rows of the cell box are
+// numbered with axis D-2 fastest, so if the partial distance over the leading axes 0..k already exceeds the radius,
+// every row that shares those leading cell coordinates is pruned at once.  Returns -1 if the row is usable (pa, pb
+// set), else the index of the first row that is not pruned by the same test (> j).  Pays off for d >= 4, where most
+// rows of the box miss the ball.
+template <int D>
+HVB_HD int row_try32(const Dev<D>& dv, const float (&uf)[D], const float (&x0f)[D], const int (&clo)[D], const int (&chi)[D],
+                     const Ball32<D>& b, int j, int& pa, int& pb) {
+    int rem = j;
+    int dg[D], pv[D];
+    int place = 1;
+#pragma unroll
+    for (int k = D - 2; k >= 0; --k) {
+        int e = chi[k] - clo[k] + 1;
+        int qd = (int)(((float)rem + 0.5f) * b.re[k]);
+        dg[k] = rem - qd * e;
+        rem = qd;
+        pv[k] = place;
+        place *= e;
+    }
+    int base = 0, prefix = 0;
+    float d2 = 0.f, umax = 0.f, uabs = 0.f;
+#pragma unroll
+    for (int k = 0; k < D - 1; ++k) {
+        int e = chi[k] - clo[k] + 1;
+        int c = clo[k] + dg[k];
+        prefix = prefix * e + dg[k];
+        float hk = (float)dv.h[k];
+        float blo = (float)c * hk - b.m;
+        float bhi = blo + hk + 2.f * b.m;
+        float dd = fmaxf(0.f, fmaxf(blo - b.cen[k], b.cen[k] - bhi));
+        d2 = fmaf(dd, dd, d2);
+        if (!(d2 <= b.rho2)) return (prefix + 1) * pv[k];
+        umax += fmaxf(uf[k] * (blo - x0f[k]), uf[k] * (bhi - x0f[k]));
+        uabs += fabsf(uf[k]);
+        base = base * dv.g[k] + c;
+    }
+    const int L = D - 1;
+    float s = sqrtf(b.rho2 - d2) * 1.000001f + b.m;
+    float zlo = b.cen[L] - s, zhi = b.cen[L] + s;
+    float ul = uf[L];
+    float slack = b.m * (uabs + fabsf(ul)) + 1e-5f * fabsf(umax) + 1e-6f * (float)dv.ext;
+    if (ul > 1e-3f) zlo = fmaxf(zlo, x0f[L] - (umax + slack) / ul * 1.00001f - b.m);
+    else if (ul < -1e-3f) zhi = fminf(zhi, x0f[L] - (umax + slack) / ul * 1.00001f + b.m);
+    else if (umax + slack + fabsf(ul) * (float)dv.ext * 2.f <= 0.f) return j + 1;
+    float ihl = (float)dv.inv_h[L];
+    float gl = (float)dv.g[L];
+    float vlo = fminf(fmaxf(zlo * ihl - 2e-3f, 0.f), gl - 1.f);
+    float vhi = fminf(fmaxf(zhi * ihl + 2e-3f, -1.f), gl - 1.f);
+    int z0 = (int)floorf(vlo), z1 = (int)floorf(vhi);
+    if (z1 < z0) return j + 1;
+    const int* cs = dv.cell_start + (size_t)base * dv.g[L];
+    pa = cs[z0]; pb = cs[z1 + 1];
+    return -1;
+}
+
 // Point range [pa, pb) of grid row j of the current cell box: the cells of that row that can hold a generator
 // inside the search ball and on the positive side of the edge's hyperplane.  Issues the two cell_start loads.
 template <int D>
@@ -643,6 +699,37 @@ HVB_HD Best min_t_query(const Dev<D>& dv, const T& tile, const RayQ<D>& q, Local
             b32.rho2 = (float)(rho2 * (1.0 + 1e-5)) * 1.000001f;
         }
 
+        if (D >= 4) {
+            // d >= 4: walk the rows with block pruning (row_try32); a lane keeps its residue class lane mod G
+            int j = lane;
+            int pa = 0, pb = 0;
+            for (;;) {
+                bool have = false;
+                while (j < nrows) {
+                    int jn = use32 ? row_try32<D>(dv, uf, x0f, clo, chi, b32, j, pa, pb)
+                                   : (row_range<D>(dv, q, clo, chi, cen, rho2, j, pa, pb) ? -1 : j + 1);
+                    if (jn < 0) { have = true; j += T::SIZE; break; }
+                    j = (T::SIZE == 1) ? jn : jn + ((T::SIZE - ((jn - lane) % T::SIZE)) % T::SIZE);
+                }
+                if (T::SIZE > 1) { if (tile.ballot(have) == 0u) break; }
+                else if (!have) break;
+                if (have && pb > pa) scan_points<D>(dv, q, uf, w2f, x0f, flt, pa, pb, best, ls);
+                if (T::SIZE > 1) best_reduce(tile, best);
+                if (best.t < Ts) {
+                    Ts = best.t;
+#pragma unroll
+                    for (int k = 0; k < D; ++k) cen[k] = q.r[k] + Ts * q.u[k];
+                    rho2 = (q.R0sq - 2.0 * Ts * q.a + Ts * Ts) * (1.0 + 1e-12) + 1e-300;
+                    rho = sqrt(rho2);
+                    flt = make_filter<D>(Ts, rho, R0, dv.ext);
+                    if (use32) {
+#pragma unroll
+                        for (int k = 0; k < D; ++k) b32.cen[k] = (float)(cen[k] - dv.lo[k]);
+                        b32.rho2 = (float)(rho2 * (1.0 + 1e-5)) * 1.000001f;
+                    }
+                }
+            }
+        } else {
         // rows lane, lane + G, ... ; the next row's range is requested before the current one is scanned
         const int niter = (nrows + T::SIZE - 1) / T::SIZE;
         int pa = 0, pb = 0, pa_n = 0, pb_n = 0;
@@ -669,6 +756,7 @@ HVB_HD Best min_t_query(const Dev<D>& dv, const T& tile, const RayQ<D>& q, Local
                     b32.rho2 = (float)(rho2 * (1.0 + 1e-5)) * 1.000001f;
                 }
             }
+        }
         }
         if (best.t <= fmin(Tst, Ts) || !(Tst < INFINITY)) break;
         scale *= 2.0;

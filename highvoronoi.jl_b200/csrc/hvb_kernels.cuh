@@ -25,6 +25,83 @@ __device__ __forceinline__ void flush_stats(const LocalStats& ls, Counters* c) {
 // ------------------------------------------------------------------------------------------------------------
 // spatial index: counting sort of the generators into grid cells (replaces the KD-tree build, kd_tree.jl:27-158)
 // ------------------------------------------------------------------------------------------------------------
+// bounding box of the generators + domain check (check_boundary, boundary.jl:437): per-block partials, reduced by
+// the last block to finish.  out: [2*D] doubles (min, max), viol: smallest index of a generator outside a plane
+// (or non-finite), 0xffffffff if none
+template <int D>
+__global__ void k_bbox_check(const double* __restrict__ xs, int n, const PlaneSet* __restrict__ ps, double* __restrict__ partial,
+                             unsigned int* __restrict__ done, double* __restrict__ out, unsigned int* __restrict__ viol) {
+    double mn[D], mx[D];
+#pragma unroll
+    for (int k = 0; k < D; ++k) { mn[k] = 1e300; mx[k] = -1e300; }
+    unsigned int bad = 0xffffffffu;
+    const int P = ps->P;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        double x[D];
+        bool ok = true;
+#pragma unroll
+        for (int k = 0; k < D; ++k) {
+            x[k] = xs[(size_t)i * D + k];
+            ok &= (x[k] == x[k]) && (fabs(x[k]) <= 1e150);
+            mn[k] = fmin(mn[k], x[k]); mx[k] = fmax(mx[k], x[k]);
+        }
+        for (int p = 0; p < P; ++p) {
+            double sdot = 0;
+#pragma unroll
+            for (int k = 0; k < D; ++k) sdot += ps->normal[p * 6 + k] * x[k];
+            ok &= !(sdot > ps->off[p]);
+        }
+        if (!ok) bad = min(bad, (unsigned int)i);
+    }
+#pragma unroll
+    for (int m = 16; m >= 1; m >>= 1) {
+#pragma unroll
+        for (int k = 0; k < D; ++k) {
+            mn[k] = fmin(mn[k], __shfl_xor_sync(0xffffffffu, mn[k], m));
+            mx[k] = fmax(mx[k], __shfl_xor_sync(0xffffffffu, mx[k], m));
+        }
+        bad = min(bad, __shfl_xor_sync(0xffffffffu, bad, m));
+    }
+    __shared__ double sm[8][2 * D];
+    __shared__ unsigned int sbad[8];
+    __shared__ bool last;
+    const int w = threadIdx.x >> 5;
+    if ((threadIdx.x & 31) == 0) {
+#pragma unroll
+        for (int k = 0; k < D; ++k) { sm[w][k] = mn[k]; sm[w][D + k] = mx[k]; }
+        sbad[w] = bad;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const int nw = blockDim.x >> 5;
+        for (int j = 1; j < nw; ++j) {
+#pragma unroll
+            for (int k = 0; k < D; ++k) { sm[0][k] = fmin(sm[0][k], sm[j][k]); sm[0][D + k] = fmax(sm[0][D + k], sm[j][D + k]); }
+            sbad[0] = min(sbad[0], sbad[j]);
+        }
+#pragma unroll
+        for (int k = 0; k < 2 * D; ++k) partial[(size_t)blockIdx.x * 2 * D + k] = sm[0][k];
+        if (sbad[0] != 0xffffffffu) atomicMin(viol, sbad[0]);
+        __threadfence();
+        last = (atomicAdd(done, 1u) == gridDim.x - 1);
+    }
+    __syncthreads();
+    if (last && threadIdx.x == 0) {
+        double r[2 * D];
+#pragma unroll
+        for (int k = 0; k < D; ++k) { r[k] = 1e300; r[D + k] = -1e300; }
+        for (unsigned int b = 0; b < gridDim.x; ++b) {
+#pragma unroll
+            for (int k = 0; k < D; ++k) {
+                r[k] = fmin(r[k], __ldcg(partial + (size_t)b * 2 * D + k));
+                r[D + k] = fmax(r[D + k], __ldcg(partial + (size_t)b * 2 * D + D + k));
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < 2 * D; ++k) out[k] = r[k];
+    }
+}
+
 template <int D>
 __global__ void k_cell_count(Dev<D> dv, const double* __restrict__ xs, int* __restrict__ cell_of, int* __restrict__ cell_cnt) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
