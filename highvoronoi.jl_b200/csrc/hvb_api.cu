@@ -212,7 +212,7 @@ struct Ctx : hvb_ctx {
         CK(planes.ensure(1)); CK(ctr.ensure(1)); CK(sc.ensure(1)); CK(h_sc.ensure(1)); CK(h_ctr.ensure(1));
         CK(cudaMemcpyAsync(planes.p, &ps_host, sizeof(ps_host), cudaMemcpyHostToDevice, stream));
         dv.plane_tol = prm.plane_tolerance;
-        dv.probe_scale = prm.probe_scale > 1.0 ? prm.probe_scale : 1.3;
+        dv.probe_scale = prm.probe_scale > 1.0 ? prm.probe_scale : default_probe_scale(D);
         dv.fp32_filter = prm.fp32_filter;
         if (prm.tile_size == 1 || prm.tile_size == 2 || prm.tile_size == 4 || prm.tile_size == 8 || prm.tile_size == 16 || prm.tile_size == 32) G = prm.tile_size;
         debug = getenv("HVB_DEBUG") != nullptr;

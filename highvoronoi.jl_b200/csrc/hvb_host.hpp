@@ -13,10 +13,12 @@ inline double simplices_per_point(int d) {
     static const double s[7] = {0, 0, 2.0, 6.77, 31.8, 186.7, 1296.4};
     return s[d];
 }
+// measured on B200 (profiles/r1_tile_occupancy_sweep.md, knob sweeps): longer rows amortise the per-row geometry
 inline int default_points_per_cell(int d) {
-    static const int p[7] = {0, 0, 2, 2, 3, 3, 4};
+    static const int p[7] = {0, 0, 4, 5, 4, 3, 4};
     return p[d];
 }
+inline double default_probe_scale(int d) { return d <= 3 ? 1.5 : 1.3; }
 inline int tile_size_for_dim(int d) {
     static const int g[7] = {0, 0, 4, 8, 16, 32, 32};
     return g[d];

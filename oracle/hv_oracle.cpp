@@ -41,6 +41,7 @@
 #include <unordered_set>
 #include <vector>
 #include <thread>
+#include <chrono>
 
 namespace {
 
@@ -185,7 +186,7 @@ struct Ray { std::vector<i64> edge; double r[MAXD], u[MAXD]; i64 cell; };
 
 struct Stats {
     i64 raycasts = 0, nn_calls = 0, inrange_calls = 0, points_visited = 0, descents = 0,
-        corrections = 0, degenerate = 0, duplicates = 0, rejected = 0;
+        corrections = 0, degenerate = 0, duplicates = 0, rejected = 0, search_us = 0, build_us = 0;
 };
 
 // Shared problem description (read-only during the search).
@@ -201,13 +202,22 @@ struct Problem {
 // index lists), abstractmesh.jl:111-125 (push! + push_ref!).  One mutex stands in for the
 // reference's read/write lock (hvdatabase.jl:42,97,112).
 struct Store {
-    std::vector<Vertex> verts;
-    std::vector<std::vector<i64> > cell_lists;  // per real cell: indices into verts (owned + refs)
-    std::unordered_set<std::vector<i64>, SigHash> keys;
+    // vertex records live in fixed blocks so that readers never see a reallocation (the reference's blocked heap,
+    // hvdatabase.jl:94-110); the key set and the per-cell lists are sharded so that slab threads rarely collide
+    // (the reference uses one read/write lock, hvdatabase.jl:42: this restatement is at least as scalable)
+    static const int BLK = 4096, NSH = 64, NCL = 4096;
+    std::vector<Vertex*> blocks;
+    i64 nverts = 0;
+    std::mutex vmtx;
+    std::vector<std::vector<i64> > cell_lists;  // per real cell: indices of vertex records (owned + refs)
+    std::unordered_set<std::vector<i64>, SigHash> keys[NSH];
+    std::mutex kmtx[NSH], cmtx[NCL], rmtx;
     std::vector<Ray> rays;
     std::vector<char> dirty;                    // stands in for searcher.positions (sysvoronoi.jl:190-204)
-    std::mutex mtx;
     bool threaded = false;
+    Store() : blocks(1 << 18, (Vertex*)0) {}
+    ~Store() { for (Vertex* b : blocks) delete[] b; }
+    Vertex& at(i64 i) { return blocks[i / BLK][i % BLK]; }
 };
 
 // Per-thread searcher state: raycast-types.jl:373-431 (RaycastIncircleSkip) + extended.jl:9-63,78-142.
@@ -559,29 +569,43 @@ struct Searcher {
     // ---- store access (abstractmesh.jl:111-153) -------------------------------------------
     // returns false if the vertex was already present (never in single-thread mode).
     bool push_vertex(const std::vector<i64>& sig, const double* r, i64 cell) {
-        std::unique_lock<std::mutex> lk(st.mtx, std::defer_lock);
-        if (st.threaded) lk.lock();
-        if (!st.keys.insert(sig).second) { ++stats.duplicates; return false; }
-        for (i64 g : sig) if (g < N && g != cell) st.dirty[g] = 1;
-        Vertex v; v.sig = sig; std::memcpy(v.r, r, sizeof(double) * d);
-        i64 id = (i64)st.verts.size();
-        st.verts.push_back(v);
-        for (i64 g : sig) if (g < N) st.cell_lists[g].push_back(id);     // owner + refs, planes skipped (voronoi_mesh.jl:222)
+        int sh = (int)(SigHash()(sig) % Store::NSH);
+        {
+            std::unique_lock<std::mutex> lk(st.kmtx[sh], std::defer_lock);
+            if (st.threaded) lk.lock();
+            if (!st.keys[sh].insert(sig).second) { ++stats.duplicates; return false; }
+        }
+        i64 id;
+        {
+            std::unique_lock<std::mutex> lk(st.vmtx, std::defer_lock);
+            if (st.threaded) lk.lock();
+            id = st.nverts++;
+            if (!st.blocks[id / Store::BLK]) st.blocks[id / Store::BLK] = new Vertex[Store::BLK];
+        }
+        Vertex& v = st.at(id);
+        v.sig = sig; std::memcpy(v.r, r, sizeof(double) * d);
+        for (i64 g : sig) {
+            if (g >= N) continue;                                        // planes hold no list (voronoi_mesh.jl:222)
+            std::unique_lock<std::mutex> lk(st.cmtx[g % Store::NCL], std::defer_lock);
+            if (st.threaded) lk.lock();
+            st.cell_lists[g].push_back(id);
+            if (g != cell) st.dirty[g] = 1;
+        }
         return true;
     }
     void cell_vertices(i64 cell, std::vector<i64>& out) {
-        std::unique_lock<std::mutex> lk(st.mtx, std::defer_lock);
+        std::unique_lock<std::mutex> lk(st.cmtx[cell % Store::NCL], std::defer_lock);
         if (st.threaded) lk.lock();
         st.dirty[cell] = 0;
         out = st.cell_lists[cell];
     }
     void get_vertex(i64 id, std::vector<i64>& sig, double* r) {
-        std::unique_lock<std::mutex> lk(st.mtx, std::defer_lock);
-        if (st.threaded) lk.lock();
-        sig = st.verts[id].sig; std::memcpy(r, st.verts[id].r, sizeof(double) * d);
+        // the record was completed before its index was published under the cell's lock
+        const Vertex& v = st.at(id);
+        sig = v.sig; std::memcpy(r, v.r, sizeof(double) * d);
     }
     void push_ray(const std::vector<i64>& edge, const double* r, const double* u, i64 cell) {
-        std::unique_lock<std::mutex> lk(st.mtx, std::defer_lock);
+        std::unique_lock<std::mutex> lk(st.rmtx, std::defer_lock);
         if (st.threaded) lk.lock();
         Ray ry; ry.edge = edge; std::memcpy(ry.r, r, sizeof(double) * d); std::memcpy(ry.u, u, sizeof(double) * d); ry.cell = cell;
         st.rays.push_back(ry);
@@ -709,7 +733,9 @@ void* hvo_run(int dim, int64_t n, const double* xs, int nplanes, const double* p
         double nr = std::sqrt(dot(&pb.pnormal[p * dim], &pb.pnormal[p * dim], dim));
         for (int k = 0; k < dim; ++k) pb.pnormal[p * dim + k] /= nr;
     }
+    auto t0 = std::chrono::steady_clock::now();
     pb.tree.build(pb.xs.data(), n, dim);
+    auto t1 = std::chrono::steady_clock::now();
     Store st;
     st.cell_lists.resize(n);
     st.dirty.assign(n, 1);
@@ -740,8 +766,12 @@ void* hvo_run(int dim, int64_t n, const double* xs, int nplanes, const double* p
             for (i64 i = 0; i < n; ++i) if (st.dirty[i]) todo.push_back(i);
         }
     }
+    auto t2 = std::chrono::steady_clock::now();
     for (int t = 0; t < nthreads; ++t) add_stats(res->stats, tstats[t]);
-    res->verts.swap(st.verts);
+    res->stats.build_us = std::chrono::duration_cast<std::chrono::microseconds>(t1 - t0).count();
+    res->stats.search_us = std::chrono::duration_cast<std::chrono::microseconds>(t2 - t1).count();
+    res->verts.reserve(st.nverts);
+    for (i64 i = 0; i < st.nverts; ++i) res->verts.push_back(st.at(i));
     std::sort(res->verts.begin(), res->verts.end(), [](const Vertex& a, const Vertex& b) { return a.sig < b.sig; });
     res->rays.swap(st.rays);
     std::sort(res->rays.begin(), res->rays.end(), [](const Ray& a, const Ray& b) { return a.edge < b.edge; });
@@ -786,11 +816,13 @@ void hvo_fetch_neighbors(void* h, int64_t* offsets, int64_t* ids) {
     for (size_t i = 0; i < R->nb_off.size(); ++i) offsets[i] = R->nb_off[i];
     for (size_t i = 0; i < R->nb_ids.size(); ++i) ids[i] = R->nb_ids[i] + 1;
 }
-// stats[0..8] = raycasts, nn_calls, inrange_calls, points_visited, descents, corrections, degenerate, duplicates, rejected
+// stats[0..10] = raycasts, nn_calls, inrange_calls, points_visited, descents, corrections, degenerate, duplicates, rejected,
+//                 search_us (voronoi() proper: the cell loop), build_us (KD-tree build = Raycast(xs))
 void hvo_stats(void* h, int64_t* s) {
     Result* R = (Result*)h;
     s[0] = R->stats.raycasts; s[1] = R->stats.nn_calls; s[2] = R->stats.inrange_calls; s[3] = R->stats.points_visited;
     s[4] = R->stats.descents; s[5] = R->stats.corrections; s[6] = R->stats.degenerate; s[7] = R->stats.duplicates; s[8] = R->stats.rejected;
+    s[9] = R->stats.search_us; s[10] = R->stats.build_us;
 }
 void hvo_free(void* h) { delete (Result*)h; }
 

@@ -14,7 +14,7 @@ _LIB = os.path.join(_HERE, "_build", "libhvoracle.so")
 _lib = None
 
 STAT_NAMES = ("raycasts", "nn_calls", "inrange_calls", "points_visited", "descents",
-              "corrections", "degenerate", "duplicates", "rejected")
+              "corrections", "degenerate", "duplicates", "rejected", "search_us", "build_us")
 
 
 def build(force=False):
