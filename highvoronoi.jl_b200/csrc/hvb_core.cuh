@@ -101,6 +101,7 @@ struct TileHost {
     HVB_HD int lane() const { return 0; }
     HVB_HD double shfl_xor(double v, int) const { return v; }
     HVB_HD int shfl_xor(int v, int) const { return v; }
+    HVB_HD float shfl_xor(float v, int) const { return v; }
     HVB_HD int shfl(int v, int) const { return v; }
     HVB_HD u32 shfl(u32 v, int) const { return v; }
     HVB_HD u64 shfl(u64 v, int) const { return v; }
@@ -121,6 +122,7 @@ struct TileDev {
     __device__ __forceinline__ int lane() const { return ln; }
     __device__ __forceinline__ double shfl_xor(double v, int m) const { return G == 1 ? v : __shfl_xor_sync(mask, v, m, G); }
     __device__ __forceinline__ int shfl_xor(int v, int m) const { return G == 1 ? v : __shfl_xor_sync(mask, v, m, G); }
+    __device__ __forceinline__ float shfl_xor(float v, int m) const { return G == 1 ? v : __shfl_xor_sync(mask, v, m, G); }
     __device__ __forceinline__ int shfl(int v, int src) const { return G == 1 ? v : __shfl_sync(mask, v, src, G); }
     __device__ __forceinline__ u32 shfl(u32 v, int src) const { return G == 1 ? v : __shfl_sync(mask, v, src, G); }
     __device__ __forceinline__ u64 shfl(u64 v, int src) const { return G == 1 ? v : __shfl_sync(mask, v, src, G); }
@@ -351,10 +353,10 @@ HVB_HD void best_reduce(const T& tile, Best& b) {
 
 // FP64 evaluation of one generator: get_t_hp (raycast.jl:427-432) under the predicate of myskips (:385)
 template <int D>
-HVB_HD void verify64(const Dev<D>& dv, const RayQ<D>& q, int j, Best& best, LocalStats& ls) {
+HVB_HD bool verify64(const Dev<D>& dv, const RayQ<D>& q, int j, Best& best, LocalStats& ls) {
 #pragma unroll
     for (int e = 0; e < D + 1; ++e)
-        if (e < q.nexcl && q.excl[e] == j) return;
+        if (e < q.nexcl && q.excl[e] == j) return false;
     const double* x = dv.x64 + (size_t)j * D;
     double ux = 0, num = 0, den = 0;
 #pragma unroll
@@ -366,10 +368,11 @@ HVB_HD void verify64(const Dev<D>& dv, const RayQ<D>& q, int j, Best& best, Loca
         den += q.u[k] * dx;
     }
     ls.cand64++;
-    if (!(ux > q.c) || !(den > 0)) return;
+    if (!(ux > q.c) || !(den > 0)) return false;
     double t = num / (2.0 * den);
-    if (!(t >= dv.plane_tol)) return;                 // raycast.jl:887-889
+    if (!(t >= dv.plane_tol)) return false;           // raycast.jl:887-889
     best_offer(best, t, j);
+    return true;
 }
 
 // per-stage FP32 filter constants
@@ -553,12 +556,23 @@ HVB_HD bool row_range(const Dev<D>& dv, const RayQ<D>& q, const int (&clo)[D], c
     return true;
 }
 
-// FP32 pass over the points [pa, pb) in chunks of four: all loads of a chunk are issued before any arithmetic;
-// a candidate that survives the filter first tightens the bound from its own FP32 upper estimate, and only the
-// candidates that still survive are re-evaluated in FP64.
+// FP32 bookkeeping of a probe stage: the candidate with the smallest FP32 UPPER bound of 2t (`cb`) and at most one
+// rival whose FP32 interval overlaps it (`cr`).  Everything else is decided in FP32; the FP64 evaluation
+// (get_t_hp, raycast.jl:427) runs once per stage for cb -- all lanes of a warp reach it together -- and only in
+// rare cases for a rival.  id < 0: empty.
+struct Cand32 { int id; float lo, hi; };
+struct ScanState {
+    Cand32 cb, cr;
+    bool tighten;          // FP32 upper bounds may be trusted for this ray (see min_t_query)
+    bool rejected;         // FP64 refused a candidate that had tightened the bound: the stage is redone without tightening
+};
+
+HVB_HD float upper_2t(double t) { return (float)(2.0 * t * (1.0 + 4.8e-7)) * 1.0000005f; }
+
+// FP32 pass over the points [pa, pb) in chunks of four: all loads of a chunk are issued before any arithmetic.
 template <int D>
 HVB_HD void scan_points(const Dev<D>& dv, const RayQ<D>& q, const float (&uf)[D], const float (&w2f)[D], const float (&x0f)[D],
-                        Filt& flt, int pa, int pb, Best& best, LocalStats& ls) {
+                        Filt& flt, int pa, int pb, ScanState& st, Best& best, LocalStats& ls) {
     ls.rows++;
     ls.cand32 += (u32)(pb - pa);
     if (!dv.fp32_filter) {
@@ -570,7 +584,7 @@ HVB_HD void scan_points(const Dev<D>& dv, const RayQ<D>& q, const float (&uf)[D]
         float x[U][D];
 #pragma unroll
         for (int i = 0; i < U; ++i) load_x32<D>(dv.x32, (p + i < pb) ? (p + i) : (pb - 1), x[i]);
-        float num[U], dh[U];
+        float nlo[U], nhi[U], dh[U], dl[U];
         bool pass[U];
 #pragma unroll
         for (int i = 0; i < U; ++i) {
@@ -581,29 +595,55 @@ HVB_HD void scan_points(const Dev<D>& dv, const RayQ<D>& q, const float (&uf)[D]
                 den = fmaf(uf[k], qk, den);
                 nm = fmaf(qk, qk - w2f[k], nm);
             }
-            num[i] = nm - flt.en;
-            dh[i] = den + flt.ed;
-            pass[i] = (p + i < pb) && dh[i] > 0.f && num[i] <= flt.tb2 * dh[i];
-            // FP32 self-tightening: the true 2t of this candidate is at most (num + en) / (den/2 - ed); only used
-            // when the denominator is safely positive (then the candidate is a valid one in FP64 as well)
-            float dl = den - flt.ed;
-            bool excluded = false;
-#pragma unroll
-            for (int e = 0; e < D + 1; ++e) excluded |= (e < q.nexcl && q.excl[e] == p + i);
-            if (pass[i] && !excluded && dl > flt.ed && num[i] > 0.f) {
-                float hi = (nm + flt.en) / dl * 1.000001f;
-                flt.tb2 = fminf(flt.tb2, hi);
-            }
+            nlo[i] = nm - flt.en; nhi[i] = nm + flt.en;
+            dh[i] = den + flt.ed; dl[i] = den - flt.ed;
+            pass[i] = (p + i < pb) && dh[i] > 0.f && nlo[i] <= flt.tb2 * dh[i];
         }
 #pragma unroll
         for (int i = 0; i < U; ++i) {
-            if (pass[i] && num[i] <= flt.tb2 * dh[i]) {
+            if (!(pass[i] && nlo[i] <= flt.tb2 * dh[i])) continue;       // re-checked: the bound may have tightened within the chunk
+            const int id = p + i;
+            bool excluded = false;
+#pragma unroll
+            for (int e = 0; e < D + 1; ++e) excluded |= (e < q.nexcl && q.excl[e] == id);
+            if (excluded) continue;
+            // an FP32 upper bound exists when the denominator is safely positive and t is safely > 0: such a
+            // candidate is valid in FP64 as well (u.x > c, den > 0, t >= plane_tol)
+            const bool bounded = st.tighten && dl[i] > flt.ed && nlo[i] > 0.f;
+            int to_verify = -1;
+            if (!bounded) to_verify = id;
+            else {
+                float lo = nlo[i] / dh[i]; lo -= fabsf(lo) * 4e-7f;
+                float hi = nhi[i] / dl[i] * 1.000001f;
+                if (hi < st.cb.hi) {
+                    // new FP32 best; the old one stays as the rival if its interval still overlaps
+                    if (st.cb.id >= 0 && st.cb.lo <= hi) {
+                        if (st.cr.id >= 0 && st.cr.lo <= hi) to_verify = st.cr.id;    // no room: settle the displaced rival now
+                        st.cr = st.cb;
+                    } else if (st.cr.id >= 0 && st.cr.lo > hi) st.cr.id = -1;
+                    st.cb.id = id; st.cb.lo = lo; st.cb.hi = hi;
+                    flt.tb2 = fminf(flt.tb2, hi);
+                } else if (st.cr.id < 0) { st.cr.id = id; st.cr.lo = lo; st.cr.hi = hi; }
+                else to_verify = id;
+            }
+            if (to_verify >= 0) {
                 double before = best.t;
-                verify64<D>(dv, q, p + i, best, ls);
-                if (best.t < before) flt.tb2 = fminf(flt.tb2, (float)(2.0 * best.t * (1.0 + 4.8e-7)) * 1.0000005f);
+                verify64<D>(dv, q, to_verify, best, ls);
+                if (best.t < before) flt.tb2 = fminf(flt.tb2, upper_2t(best.t));
             }
         }
     }
+}
+
+// end of a probe stage: the FP64 evaluation of the FP32 winner (and of a surviving rival)
+template <int D>
+HVB_HD void settle_stage(const Dev<D>& dv, const RayQ<D>& q, ScanState& st, float tb2, Best& best, LocalStats& ls) {
+    if (st.cb.id >= 0 && st.cb.lo <= tb2) {
+        if (!verify64<D>(dv, q, st.cb.id, best, ls)) st.rejected = true;
+    }
+    if (st.cr.id >= 0 && st.cr.lo <= tb2) verify64<D>(dv, q, st.cr.id, best, ls);
+    st.cb.id = -1; st.cb.hi = INFINITY; st.cb.lo = 0.f;
+    st.cr.id = -1;
 }
 
 // Smallest t > 0 at which the ball centred at r + t u through x0 touches another generator or boundary plane.
@@ -649,8 +689,12 @@ HVB_HD Best min_t_query(const Dev<D>& dv, const T& tile, const RayQ<D>& q, Local
     const double R0p = fmax(R0, 0.5 * dv.hmin);
     const double perp2 = fmax(q.R0sq - q.a * q.a, 0.0);       // squared distance of x0 to the ray's line
     double scale = dv.probe_scale;
+    ScanState st;
+    st.cb.id = -1; st.cb.lo = 0.f; st.cb.hi = INFINITY; st.cr.id = -1; st.cr.lo = 0.f; st.cr.hi = INFINITY;
+    st.rejected = false;
+    st.tighten = true;
 
-    for (int stage = 0; stage < 64; ++stage) {
+    for (int stage = 0; stage < 96; ++stage) {
         ls.stages += (lane == 0);
         double rho_t = scale * R0p;
         double Tst = (rho_t > 1e4 * dv.diag) ? INFINITY : q.a + sqrt(fmax(rho_t * rho_t - perp2, 0.0));
@@ -683,6 +727,9 @@ HVB_HD Best min_t_query(const Dev<D>& dv, const T& tile, const RayQ<D>& q, Local
         }
         if (empty) nrows = 0;
         Filt flt = make_filter<D>(halfspace_mode ? INFINITY : Ts, rho, R0, dv.ext);
+        // FP32 upper bounds certify validity only while the filter's denominator margin dominates the half-space slack
+        if (!((float)(fabs(q.c) * 8e-12) < flt.ed)) st.tighten = false;
+        const double Ts0 = Ts;
         // FP32 row geometry while the ball is comparable to the cloud; FP64 for the huge balls of unbounded edges
         double cmax = 0;
 #pragma unroll
@@ -713,15 +760,20 @@ HVB_HD Best min_t_query(const Dev<D>& dv, const T& tile, const RayQ<D>& q, Local
                 }
                 if (T::SIZE > 1) { if (tile.ballot(have) == 0u) break; }
                 else if (!have) break;
-                if (have && pb > pa) scan_points<D>(dv, q, uf, w2f, x0f, flt, pa, pb, best, ls);
-                if (T::SIZE > 1) best_reduce(tile, best);
-                if (best.t < Ts) {
-                    Ts = best.t;
+                if (have && pb > pa) scan_points<D>(dv, q, uf, w2f, x0f, flt, pa, pb, st, best, ls);
+                if (T::SIZE > 1) {
+                    best_reduce(tile, best);
+#pragma unroll
+                    for (int m = T::SIZE / 2; m >= 1; m >>= 1) flt.tb2 = fminf(flt.tb2, tile.shfl_xor(flt.tb2, m));
+                }
+                const double Tshr = fmin(best.t, 0.5 * (double)flt.tb2);
+                if (Tshr < 0.92 * Ts) {
+                    Ts = Tshr;
 #pragma unroll
                     for (int k = 0; k < D; ++k) cen[k] = q.r[k] + Ts * q.u[k];
                     rho2 = (q.R0sq - 2.0 * Ts * q.a + Ts * Ts) * (1.0 + 1e-12) + 1e-300;
                     rho = sqrt(rho2);
-                    flt = make_filter<D>(Ts, rho, R0, dv.ext);
+                    { float keep = flt.tb2; flt = make_filter<D>(Ts, rho, R0, dv.ext); flt.tb2 = fminf(flt.tb2, keep); }
                     if (use32) {
 #pragma unroll
                         for (int k = 0; k < D; ++k) b32.cen[k] = (float)(cen[k] - dv.lo[k]);
@@ -739,17 +791,22 @@ HVB_HD Best min_t_query(const Dev<D>& dv, const T& tile, const RayQ<D>& q, Local
             int jn = (it + 1) * T::SIZE + lane;
             bool have_n = (jn < nrows) && (use32 ? row_range32<D>(dv, uf, x0f, clo, chi, b32, jn, pa_n, pb_n)
                                                  : row_range<D>(dv, q, clo, chi, cen, rho2, jn, pa_n, pb_n));
-            if (have && pb > pa) scan_points<D>(dv, q, uf, w2f, x0f, flt, pa, pb, best, ls);
+            if (have && pb > pa) scan_points<D>(dv, q, uf, w2f, x0f, flt, pa, pb, st, best, ls);
             have = have_n; pa = pa_n; pb = pb_n;
             // share the best bound and shrink the ball
-            if (T::SIZE > 1) best_reduce(tile, best);
-            if (best.t < Ts) {
-                Ts = best.t;
+            if (T::SIZE > 1) {
+                best_reduce(tile, best);
+#pragma unroll
+                for (int m = T::SIZE / 2; m >= 1; m >>= 1) flt.tb2 = fminf(flt.tb2, tile.shfl_xor(flt.tb2, m));
+            }
+            const double Tshr = fmin(best.t, 0.5 * (double)flt.tb2);     // tb2 / 2 bounds the winner once a candidate tightened it
+            if (Tshr < 0.92 * Ts) {
+                Ts = Tshr;
 #pragma unroll
                 for (int k = 0; k < D; ++k) cen[k] = q.r[k] + Ts * q.u[k];
                 rho2 = (q.R0sq - 2.0 * Ts * q.a + Ts * Ts) * (1.0 + 1e-12) + 1e-300;
                 rho = sqrt(rho2);
-                flt = make_filter<D>(Ts, rho, R0, dv.ext);
+                { float keep = flt.tb2; flt = make_filter<D>(Ts, rho, R0, dv.ext); flt.tb2 = fminf(flt.tb2, keep); }
                 if (use32) {
 #pragma unroll
                     for (int k = 0; k < D; ++k) b32.cen[k] = (float)(cen[k] - dv.lo[k]);
@@ -758,7 +815,17 @@ HVB_HD Best min_t_query(const Dev<D>& dv, const T& tile, const RayQ<D>& q, Local
             }
         }
         }
-        if (best.t <= fmin(Tst, Ts) || !(Tst < INFINITY)) break;
+        if (T::SIZE > 1) {
+#pragma unroll
+            for (int m = T::SIZE / 2; m >= 1; m >>= 1) flt.tb2 = fminf(flt.tb2, tile.shfl_xor(flt.tb2, m));
+        }
+        settle_stage<D>(dv, q, st, flt.tb2, best, ls);
+        if (T::SIZE > 1) {
+            best_reduce(tile, best);
+            st.rejected = tile.ballot(st.rejected) != 0u;
+        }
+        if (st.rejected) { st.rejected = false; st.tighten = false; continue; }     // redo this stage, FP64 decides everything
+        if (best.t <= Ts0 || !(Tst < INFINITY)) break;
         scale *= 2.0;
     }
     return best;

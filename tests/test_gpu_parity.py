@@ -132,6 +132,18 @@ def test_degenerate_input_is_reported(hvb):
     assert e.value.code == hvb._abi.HVB_EDEGENERATE
 
 
+# ---- BASELINE.json full sizes against the oracle itself (multi-threaded restatement, ~10 s each) -------------------
+@pytest.mark.parametrize("d,n", [(3, 100000), (2, 300000), (5, 5000), (4, 20000)])
+def test_full_size_matches_oracle(hvb, oracle, d, n):
+    xs = points(n, d, 0)
+    base, normal = qhull_oracle.cuboid(d)
+    o = oracle.run(xs, base, normal, nthreads=min(8, os.cpu_count() or 1))
+    mesh, s = run_gpu(hvb, xs, True)
+    assert_same_mesh(mesh.sig, mesh.r, o["sig"], o["r"], xs, COORD_TOL)
+    off, ids = mesh.neighbors()
+    assert np.array_equal(off, o["nb_off"]) and np.array_equal(ids, o["nb_ids"])
+
+
 # ---- BASELINE.json full sizes: properties that need no oracle run --------------------------------------------
 @pytest.mark.parametrize("d,n,vpp_lo,vpp_hi", [(3, 100000, 6.4, 7.1), (2, 1000000, 1.95, 2.05), (5, 50000, 60, 190)])
 def test_full_size_properties(hvb, d, n, vpp_lo, vpp_hi):
