@@ -599,9 +599,19 @@ HVB_HD void scan_points(const Dev<D>& dv, const RayQ<D>& q, const float (&uf)[D]
             dh[i] = den + flt.ed; dl[i] = den - flt.ed;
             pass[i] = (p + i < pb) && dh[i] > 0.f && nlo[i] <= flt.tb2 * dh[i];
         }
+        // survivors are handled one per loop trip, whatever their position in the chunk: the lanes of a warp that have
+        // a survivor run this (branchy) bookkeeping together instead of position by position
+        unsigned pmask = 0;
 #pragma unroll
-        for (int i = 0; i < U; ++i) {
-            if (!(pass[i] && nlo[i] <= flt.tb2 * dh[i])) continue;       // re-checked: the bound may have tightened within the chunk
+        for (int i = 0; i < U; ++i) pmask |= pass[i] ? (1u << i) : 0u;
+        while (pmask) {
+            const int i = (pmask & 1u) ? 0 : (pmask & 2u) ? 1 : (pmask & 4u) ? 2 : 3;
+            pmask &= pmask - 1u;
+            const float nlo_i = (i == 0) ? nlo[0] : (i == 1) ? nlo[1] : (i == 2) ? nlo[2] : nlo[3];
+            const float nhi_i = (i == 0) ? nhi[0] : (i == 1) ? nhi[1] : (i == 2) ? nhi[2] : nhi[3];
+            const float dh_i = (i == 0) ? dh[0] : (i == 1) ? dh[1] : (i == 2) ? dh[2] : dh[3];
+            const float dl_i = (i == 0) ? dl[0] : (i == 1) ? dl[1] : (i == 2) ? dl[2] : dl[3];
+            if (!(nlo_i <= flt.tb2 * dh_i)) continue;                    // re-checked: the bound may have tightened within the chunk
             const int id = p + i;
             bool excluded = false;
 #pragma unroll
@@ -609,12 +619,12 @@ HVB_HD void scan_points(const Dev<D>& dv, const RayQ<D>& q, const float (&uf)[D]
             if (excluded) continue;
             // an FP32 upper bound exists when the denominator is safely positive and t is safely > 0: such a
             // candidate is valid in FP64 as well (u.x > c, den > 0, t >= plane_tol)
-            const bool bounded = st.tighten && dl[i] > flt.ed && nlo[i] > 0.f;
+            const bool bounded = st.tighten && dl_i > flt.ed && nlo_i > 0.f;
             int to_verify = -1;
             if (!bounded) to_verify = id;
             else {
-                float lo = nlo[i] / dh[i]; lo -= fabsf(lo) * 4e-7f;
-                float hi = nhi[i] / dl[i] * 1.000001f;
+                float lo = nlo_i / dh_i; lo -= fabsf(lo) * 4e-7f;
+                float hi = nhi_i / dl_i * 1.000001f;
                 if (hi < st.cb.hi) {
                     // new FP32 best; the old one stays as the rival if its interval still overlaps
                     if (st.cb.id >= 0 && st.cb.lo <= hi) {
@@ -846,14 +856,13 @@ HVB_HD bool sig_equal(const Dev<D>& dv, u32 v, const int* sig) {
 // Inserts (sig, r) unless present.  Returns the new index, or 0xffffffff if it was known / the store is full.
 // Replaces haskey + push! (abstractmesh.jl:111-153 -> hvdatabase.jl:94-116).
 template <int D>
-HVB_HD u32 vertex_insert(const Dev<D>& dv, const int* sig, const double* r, LocalStats& ls) {
-    u64 h = hash_ids<D>(sig, D + 1, -1);
+HVB_HD u32 vertex_insert(const Dev<D>& dv, const int* sig, const double* r, LocalStats& ls, u64 h, u64 s) {
+    // h = hash of sig, s = already loaded content of its home slot
     u64 fp = (h >> 32) << 32;
     if (fp == 0) fp = 1ULL << 32;
     u64 slot = h & dv.vmask;
     u32 mine = 0xffffffffu;
     for (;;) {
-        u64 s = ld_cg(dv.vtab + slot);
         if (s == 0) {
             if (mine == 0xffffffffu) {
                 mine = atom_add(dv.vcount, 1u);
@@ -875,6 +884,7 @@ HVB_HD u32 vertex_insert(const Dev<D>& dv, const int* sig, const double* r, Loca
             return 0xffffffffu;
         }
         slot = (slot + 1) & dv.vmask;
+        s = ld_cg(dv.vtab + slot);
     }
 }
 
@@ -900,8 +910,27 @@ HVB_HD bool edge_equal(const Dev<D>& dv, u64 s, const int* sig, int k) {
 // entry (returns its slot); second endpoint: the edge is closed (returns ~0).  `h` is the edge hash and `s` the
 // already loaded content of its home slot.  Replaces pushedge! (edgehashing.jl:66-111) and queue_edges_OnFind
 // (edgeiteratebase.jl:128-149).
+// the same comparison against a row that is already in registers (row = signature of the vertex named by slot s)
 template <int D>
-HVB_HD u64 edge_register(const Dev<D>& dv, const int* sig, u32 v, int k, u64 h, u64 s) {
+HVB_HD bool edge_equal_row(const int (&row)[D + 1], u64 s, const int* sig, int k) {
+    const int k2 = (int)(s & 7);
+    bool eq = true;
+    int i2 = 0;
+#pragma unroll
+    for (int i = 0; i < D + 1; ++i) {
+        if (i == k) continue;
+        if (i2 == k2) ++i2;
+        int val = 0;
+#pragma unroll
+        for (int j = 0; j < D + 1; ++j) val = (j == i2) ? row[j] : val;
+        eq &= (val == sig[i]);
+        ++i2;
+    }
+    return eq;
+}
+
+template <int D>
+HVB_HD u64 edge_register(const Dev<D>& dv, const int* sig, u32 v, int k, u64 h, u64 s, bool have_row, const int (&row)[D + 1]) {
     u64 mine = edge_slot(h, v, k);
     u64 slot = h & dv.emask;
     for (;;) {
@@ -909,12 +938,13 @@ HVB_HD u64 edge_register(const Dev<D>& dv, const int* sig, u32 v, int k, u64 h, 
             s = atom_cas(dv.etab + slot, 0ULL, mine);
             if (s == 0) return slot;
         }
-        if (((s ^ mine) & EDGE_FPMASK) == 0 && edge_equal<D>(dv, s, sig, k)) {
+        if (((s ^ mine) & EDGE_FPMASK) == 0 && (have_row ? edge_equal_row<D>(row, s, sig, k) : edge_equal<D>(dv, s, sig, k))) {
             if (!(s & EDGE_CLOSED)) atom_or(dv.etab + slot, EDGE_CLOSED);
             return ~0ULL;
         }
         slot = (slot + 1) & dv.emask;
         s = ld_cg(dv.etab + slot);
+        have_row = false;
     }
 }
 
@@ -935,6 +965,11 @@ HVB_HD void commit_vertex(const Dev<D>& dv, const T& tile, const int* sig, const
         if ((sig[i] < dv.n) && (dv.active[sig[i]] != 0)) actmask |= 1u << i;
     // sub-facet k = pass * G + lane: every lane runs the SAME instructions on its own k (no serialisation by lane)
     const int NPASS = (D + 1 + T::SIZE - 1) / T::SIZE;
+    // every independent load of the commit is issued up front: the vertex set's home slot, the home slots of the
+    // sub-facets and (d <= 4) the signatures behind matching edge slots
+    const u64 hv = hash_ids<D>(sig, D + 1, -1);
+    u64 sv = 0;
+    if (lane == 0) sv = ld_cg(dv.vtab + (hv & dv.vmask));
     u64 hs[NPASS], s0[NPASS];
     bool mine[NPASS];
 #pragma unroll
@@ -944,8 +979,25 @@ HVB_HD void commit_vertex(const Dev<D>& dv, const T& tile, const int* sig, const
         hs[ps_] = 0; s0[ps_] = 0;
         if (mine[ps_]) { hs[ps_] = hash_ids<D>(sig, D + 1, k); s0[ps_] = ld_cg(dv.etab + (hs[ps_] & dv.emask)); }
     }
+    const bool PREROW = (D <= 4);
+    int crow[PREROW ? NPASS : 1][D + 1];
+    bool cvalid[NPASS];
+#pragma unroll
+    for (int ps_ = 0; ps_ < NPASS; ++ps_) {
+        cvalid[ps_] = false;
+        if (PREROW) {
+            cvalid[ps_] = mine[ps_] && s0[ps_] != 0 && (((s0[ps_] ^ edge_slot(hs[ps_], 0u, 0)) & EDGE_FPMASK) == 0);
+#pragma unroll
+            for (int i = 0; i < D + 1; ++i) crow[PREROW ? ps_ : 0][i] = 0;
+            if (cvalid[ps_]) {
+                const int* prow = dv.vsig + (size_t)((u32)((s0[ps_] >> 3) & 0xffffffffULL)) * (D + 1);
+#pragma unroll
+                for (int i = 0; i < D + 1; ++i) crow[PREROW ? ps_ : 0][i] = ld_cg(prow + i);
+            }
+        }
+    }
     u32 v = 0xffffffffu;
-    if (lane == 0) v = vertex_insert<D>(dv, sig, r, ls);
+    if (lane == 0) v = vertex_insert<D>(dv, sig, r, ls, hv, sv);
     if (T::SIZE > 1) v = tile.shfl(v, 0);
     if (v == 0xffffffffu) return;
     if (lane == 0) {
@@ -957,7 +1009,7 @@ HVB_HD void commit_vertex(const Dev<D>& dv, const T& tile, const int* sig, const
     for (int ps_ = 0; ps_ < NPASS; ++ps_) {
         if (!mine[ps_]) continue;
         int k = ps_ * T::SIZE + lane;
-        u64 slot = edge_register<D>(dv, sig, v, k, hs[ps_], s0[ps_]);
+        u64 slot = edge_register<D>(dv, sig, v, k, hs[ps_], s0[ps_], cvalid[ps_], crow[PREROW ? ps_ : 0]);
         if (slot != ~0ULL) {
             u32 pos = atom_add(q_count, 1u);
             if (pos < q_cap) q_out[pos] = frontier_entry(slot, v, k);
