@@ -178,7 +178,7 @@ def main():
         barrier()
         t0 = time.perf_counter()
         if state["s"] is None:                           # the context (device + page-locked buffers) is re-used
-            opts = hvb200.RaycastParameter(threading=hvb200.B200Thread(local_rank, rank, world), neighbors=1 if world == 1 else 0, **settings)
+            opts = hvb200.RaycastParameter(threading=hvb200.B200Thread(local_rank, rank, world), neighbors=1, **settings)
             state["s"] = hvb200.Raycast(xs, domain=dom, options=opts)
         else:
             state["s"].set_points(xs)                    # H2D + index build
@@ -196,16 +196,36 @@ def main():
             torch.cuda.synchronize()
             dev_ms += te0.elapsed_time(te1)
         t1b = time.perf_counter()
-        mesh = hvb200.VoronoiMesh(s)                               # D2H of vertices (and rays)
-        t1c = time.perf_counter()
-        off, ids = mesh.neighbors()                                # neighbour lists + D2H
+        if dist is None:
+            mesh = hvb200.VoronoiMesh(s)                           # D2H of vertices (and rays)
+            sig_h, r_h = mesh.sig, mesh.r
+            V = sig_h.shape[0]
+            t1c = time.perf_counter()
+            off, ids = mesh.neighbors()                            # neighbour lists + D2H
+        else:
+            # every rank keeps its shard of the merged, sorted list and the neighbour lists of its own cells
+            nv = ctypes.c_int64()
+            _abi.check(L.hvb_counts(s._ctx, ctypes.byref(nv), None, None), s._ctx)
+            V = nv.value
+            lo, hi = V * rank // world, V * (rank + 1) // world
+            if "sig_h" not in state:                         # page-locked host buffers of the caller, allocated once
+                cap_h = int(1.3 * V / world) + 1024
+                state["sig_h"] = torch.empty((cap_h, d + 1), dtype=torch.int64, pin_memory=True).numpy()
+                state["r_h"] = torch.empty((cap_h, d), dtype=torch.float64, pin_memory=True).numpy()
+            sig_h, r_h = state["sig_h"], state["r_h"]
+            _abi.check(L.hvb_fetch_vertices_range(s._ctx, lo, hi - lo, sig_h.ctypes.data_as(ctypes.c_void_p),
+                                                  r_h.ctypes.data_as(ctypes.c_void_p)), s._ctx)
+            sig_h, r_h = sig_h[:hi - lo], r_h[:hi - lo]
+            t1c = time.perf_counter()
+            po, pi, tot = ctypes.c_void_p(), ctypes.c_void_p(), ctypes.c_int64()
+            _abi.check(L.hvb_view_neighbors(s._ctx, ctypes.byref(po), ctypes.byref(pi), ctypes.byref(tot)), s._ctx)
+            off = np.empty(n_total + 1, dtype=np.int64); ids = np.empty(int(tot.value), dtype=np.int64)   # byte accounting of the staged CSR
         torch.cuda.synchronize()
         t2 = time.perf_counter()
         if timed:
             phases[:] += (t1 - t0, t1b - t1, t1c - t1b, t2 - t1c)
-        V = mesh.sig.shape[0]
         h2d = xs.nbytes
-        d2h = mesh.sig.nbytes + mesh.r.nbytes + off.nbytes + ids.nbytes
+        d2h = sig_h.nbytes + r_h.nbytes + off.nbytes + ids.nbytes
         st2 = s.stats()
         return dev_ms, t2 - t0, V, st, st2["kernel_launches"], h2d, d2h
 

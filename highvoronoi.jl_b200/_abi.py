@@ -10,7 +10,7 @@ HVB_OK, HVB_EINVAL, HVB_ECUDA, HVB_ENOGPU, HVB_ENOMEM, HVB_EDEGENERATE, HVB_ESTA
 ERROR_NAMES = {-1: "HVB_EINVAL", -2: "HVB_ECUDA", -3: "HVB_ENOGPU", -4: "HVB_ENOMEM", -5: "HVB_EDEGENERATE",
                -6: "HVB_ESTATE", -7: "HVB_EINCOMPLETE"}
 
-EXPORTS = ("hvb_default_params", "hvb_create", "hvb_set_points", "hvb_search", "hvb_counts", "hvb_fetch_vertices", "hvb_fetch_rays",
+EXPORTS = ("hvb_default_params", "hvb_create", "hvb_set_points", "hvb_search", "hvb_counts", "hvb_fetch_vertices", "hvb_fetch_vertices_range", "hvb_fetch_rays",
            "hvb_neighbor_count", "hvb_fetch_neighbors", "hvb_view_vertices", "hvb_view_neighbors", "hvb_export_device", "hvb_merge_device",
            "hvb_stats", "hvb_last_error", "hvb_destroy", "hvb_version")
 
@@ -60,6 +60,7 @@ def lib():
         L.hvb_search.argtypes = [vp, vp, i64, vp, vp, i64, i32]
         L.hvb_counts.argtypes = [vp, ctypes.POINTER(i64), ctypes.POINTER(i64), ctypes.POINTER(i64)]
         L.hvb_fetch_vertices.argtypes = [vp, vp, vp]
+        L.hvb_fetch_vertices_range.argtypes = [vp, i64, i64, vp, vp]
         L.hvb_fetch_rays.argtypes = [vp, vp, vp, vp, vp]
         L.hvb_neighbor_count.argtypes = [vp, ctypes.POINTER(i64)]
         L.hvb_fetch_neighbors.argtypes = [vp, vp, vp]
@@ -73,7 +74,7 @@ def lib():
         L.hvb_destroy.argtypes = [vp]
         L.hvb_destroy.restype = None
         L.hvb_version.restype = ctypes.c_char_p
-        for name in ("hvb_create", "hvb_set_points", "hvb_search", "hvb_counts", "hvb_fetch_vertices", "hvb_fetch_rays", "hvb_neighbor_count",
+        for name in ("hvb_create", "hvb_set_points", "hvb_search", "hvb_counts", "hvb_fetch_vertices", "hvb_fetch_vertices_range", "hvb_fetch_rays", "hvb_neighbor_count",
                      "hvb_fetch_neighbors", "hvb_view_vertices", "hvb_view_neighbors", "hvb_export_device", "hvb_merge_device", "hvb_stats"):
             getattr(L, name).restype = i32
         _lib = L

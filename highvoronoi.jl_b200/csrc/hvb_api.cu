@@ -94,6 +94,7 @@ struct hvb_ctx {
     virtual int counts(int64_t* nv, int64_t* nr, int64_t* msl) = 0;
     virtual int fetch_vertices(int64_t* sig, double* r) = 0;
     virtual int view_vertices(const int64_t** sig, const double** r, int64_t* nv) = 0;
+    virtual int fetch_vertices_range(int64_t first, int64_t count, int64_t* sig, double* r) = 0;
     virtual int fetch_rays(int64_t* edge, double* base, double* dir, int64_t* node) = 0;
     virtual int neighbor_count(int64_t* total) = 0;
     virtual int fetch_neighbors(int64_t* off, int64_t* ids) = 0;
@@ -560,6 +561,18 @@ struct Ctx : hvb_ctx {
         if (r) memcpy(r, rr, (size_t)nv * D * sizeof(double));
         return HVB_OK;
     }
+    // rows [first, first + count) straight from the device (no staging of the whole result): the shard of a rank
+    int fetch_vertices_range(int64_t first, int64_t count, int64_t* sig, double* r) override {
+        if (!have_result) { err = "no search result"; return HVB_ESTATE; }
+        if (first < 0 || count < 0 || first + count > nvert) { err = "row range out of bounds"; return HVB_EINVAL; }
+        CK(cudaSetDevice(prm.device));
+        if (count > 0) {
+            if (sig) CK(cudaMemcpyAsync(sig, out_sig[res].p + (size_t)first * (D + 1), (size_t)count * (D + 1) * 8, cudaMemcpyDeviceToHost, stream));
+            if (r) CK(cudaMemcpyAsync(r, out_r[res].p + (size_t)first * D, (size_t)count * D * 8, cudaMemcpyDeviceToHost, stream));
+        }
+        CK(cudaStreamSynchronize(stream));
+        return HVB_OK;
+    }
     int fetch_rays(int64_t* edge, double* base, double* dir, int64_t* node) override {
         if (!have_result) { err = "no search result"; return HVB_ESTATE; }
         CK(cudaSetDevice(prm.device));
@@ -669,7 +682,7 @@ struct Ctx : hvb_ctx {
         int rc = read_scalars(); if (rc) return rc;
         nvert = h_sc.p->out_count;
         rc = sort_rows((u32)nvert, bits); if (rc) return rc;
-        nb_total = -1;
+        if (!(prm.neighbors && std::max(1, prm.world) > 1)) nb_total = -1;   // slab-built lists stay: they are complete for the rank's own cells
         staged = false;                      // staged on the first hvb_view_* / hvb_fetch_* (only ranks that read the result pay the D2H)
         CK(cudaStreamSynchronize(stream));
         CK(cudaGetLastError());
@@ -731,6 +744,7 @@ int hvb_search(hvb_ctx* ctx, const int64_t* cells, int64_t ncells, const int64_t
 }
 int hvb_counts(hvb_ctx* ctx, int64_t* nvert, int64_t* nrays, int64_t* max_siglen) { return ctx ? ctx->counts(nvert, nrays, max_siglen) : HVB_EINVAL; }
 int hvb_fetch_vertices(hvb_ctx* ctx, int64_t* sig, double* r) { return ctx ? ctx->fetch_vertices(sig, r) : HVB_EINVAL; }
+int hvb_fetch_vertices_range(hvb_ctx* ctx, int64_t first, int64_t count, int64_t* sig, double* r) { return ctx ? ctx->fetch_vertices_range(first, count, sig, r) : HVB_EINVAL; }
 int hvb_view_vertices(hvb_ctx* ctx, const int64_t** sig, const double** r, int64_t* nvert) { return (ctx && sig && r && nvert) ? ctx->view_vertices(sig, r, nvert) : HVB_EINVAL; }
 int hvb_fetch_rays(hvb_ctx* ctx, int64_t* edge, double* base, double* dir, int64_t* node) { return ctx ? ctx->fetch_rays(edge, base, dir, node) : HVB_EINVAL; }
 int hvb_neighbor_count(hvb_ctx* ctx, int64_t* total) { return (ctx && total) ? ctx->neighbor_count(total) : HVB_EINVAL; }

@@ -57,7 +57,8 @@ typedef struct hvb_params {
     int32_t seed_stride;      /* one descent seed every `seed_stride` generators; 0 = auto */
     int32_t sort_output;      /* 1: vertices are returned in lexicographic order of their signature (default) */
     int32_t tile_size;        /* lanes cooperating on one frontier entry: 1, 2, 4, 8, 16 or 32; 0 = auto by dimension */
-    int32_t neighbors;        /* 1: hvb_search also builds and stages the neighbour lists (default 0: on first request) */
+    int32_t neighbors;        /* 1: hvb_search also builds and stages the neighbour lists (default 0: on first request);
+                                 with world > 1 they are built from the slab result: complete for the rank's own cells */
     int32_t reserved1;
     int64_t vertex_capacity;  /* 0 = estimate from lowerbound(d,d) (edgeiteratebase.jl:151); grows on demand */
     double probe_scale;       /* first probe ball radius / circumradius of the origin vertex; 0 = auto */
@@ -118,6 +119,10 @@ int hvb_counts(hvb_ctx* ctx, int64_t* nvert, int64_t* nrays, int64_t* max_siglen
 /* Replaces the replay target push!(mesh, sig=>r) (src/abstractmesh.jl:111): sig = nvert x (dim+1) sorted
  * 1-based ids, r = nvert x dim. */
 int hvb_fetch_vertices(hvb_ctx* ctx, int64_t* sig, double* r);
+
+/* rows [first, first+count) of the same arrays, copied straight from the device: the shard a rank keeps after
+ * hvb_merge_device (the whole merged list need not be staged on every rank). */
+int hvb_fetch_vertices_range(hvb_ctx* ctx, int64_t first, int64_t count, int64_t* sig, double* r);
 
 /* Replaces pushray!(mesh, full_edge, r, u, _Cell) (src/abstractmesh.jl:191, sysvoronoi.jl:504-511). */
 int hvb_fetch_rays(hvb_ctx* ctx, int64_t* edge, double* base, double* dir, int64_t* node);
