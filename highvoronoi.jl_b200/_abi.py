@@ -20,7 +20,7 @@ class hvb_params(ctypes.Structure):
                 ("plane_tolerance", ctypes.c_double), ("ray_tol", ctypes.c_double),
                 ("method", ctypes.c_int32), ("device", ctypes.c_int32), ("rank", ctypes.c_int32), ("world", ctypes.c_int32),
                 ("fp32_filter", ctypes.c_int32), ("on_degenerate", ctypes.c_int32), ("points_per_cell", ctypes.c_int32),
-                ("seed_stride", ctypes.c_int32), ("sort_output", ctypes.c_int32), ("tile_size", ctypes.c_int32), ("neighbors", ctypes.c_int32), ("reserved1", ctypes.c_int32),
+                ("seed_stride", ctypes.c_int32), ("sort_output", ctypes.c_int32), ("tile_size", ctypes.c_int32), ("neighbors", ctypes.c_int32), ("persistent", ctypes.c_int32),
                 ("vertex_capacity", ctypes.c_int64), ("probe_scale", ctypes.c_double)]
 
 

@@ -75,6 +75,7 @@ struct Scalars {            // small device-side words, mirrored into pinned hos
     u32 unseeded;
     u32 out_count;
     u32 pflags;
+    u32 q_head, q_done, q_abort;      // single-launch walk (k_walk): tickets, processed entries, safety abort
     u32 bbox_done;
     u32 bbox_viol;
     u32 pad2;
@@ -107,6 +108,7 @@ template <int D>
 struct Ctx : hvb_ctx {
     int G = 1;                       // lanes per frontier entry; 1 measured best for d = 2..5 (prm.tile_size overrides)
     bool debug = false;
+    bool persistent = true;          // single-launch walk (k_walk) instead of one launch per frontier round (prm.persistent)
     cudaStream_t stream = nullptr, sstream = nullptr;    // compute stream, result-staging (D2H) stream
     cudaEvent_t ev_stage = nullptr;
     int sms = 148;
@@ -217,6 +219,7 @@ struct Ctx : hvb_ctx {
         dv.fp32_filter = prm.fp32_filter;
         if (prm.tile_size == 1 || prm.tile_size == 2 || prm.tile_size == 4 || prm.tile_size == 8 || prm.tile_size == 16 || prm.tile_size == 32) G = prm.tile_size;
         debug = getenv("HVB_DEBUG") != nullptr;
+        persistent = prm.persistent != 0;
         setup_done = true;
         return set_points(n, xs);
     }
@@ -304,6 +307,23 @@ struct Ctx : hvb_ctx {
         k_expand<D, GG><<<std::min(blocks_for((int64_t)cnt * GG, 128), sms * 16), 128, 0, stream>>>(
             dv, q[cur].p, &sc.p->rnd[cur].qcount, &sc.p->rnd[cur].cursor, q[nxt].p, &sc.p->rnd[nxt].qcount, qcap);
     }
+    template <int GG>
+    int launch_walk_g(const WalkQueue& wq) {
+        int per_sm = 0;
+        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_walk<D, GG>, 128, 0));
+        k_walk<D, GG><<<std::max(1, per_sm) * sms, 128, 0, stream>>>(dv, wq);
+        return HVB_OK;
+    }
+    int launch_walk(const WalkQueue& wq) {
+        switch (G) {
+            case 1: return launch_walk_g<1>(wq);
+            case 2: return launch_walk_g<2>(wq);
+            case 4: return launch_walk_g<4>(wq);
+            case 8: return launch_walk_g<8>(wq);
+            case 16: return launch_walk_g<16>(wq);
+            default: return launch_walk_g<32>(wq);
+        }
+    }
     void launch_expand(u32 cnt, int cur, int nxt) {
         switch (G) {
             case 1: launch_expand_g<1>(cnt, cur, nxt); break;
@@ -388,15 +408,51 @@ struct Ctx : hvb_ctx {
             }
             int nseeds = (int)((n + sstride - 1) / sstride);
             int cur = 0;
+            if (persistent) CK(cudaMemsetAsync(q[0].p, 0xff, (size_t)qcap * sizeof(u64), stream));   // nothing published yet
             CK(cudaEventRecord(ev_s0, stream));
             launch_seed(nullptr, nseeds, sstride, cur);
             CK(cudaEventRecord(ev_s1, stream));
             if (debug) fprintf(stderr, "[hvb] seeds=%d stride=%d G=%d vcap=%lld ncells=%lld\n", nseeds, sstride, G, (long long)vcap, (long long)ncells);
             bool overflow = false;
             u32 last_uns = 0xffffffffu, last_vcount = 0;
+            if (persistent) {
+                // ---- single-launch walk: seeds were appended to q[0]; k_walk drains and extends it ----------------
+                WalkQueue wq;
+                wq.q = q[0].p; wq.tail = &sc.p->rnd[0].qcount; wq.head = &sc.p->q_head; wq.done = &sc.p->q_done;
+                wq.abort = &sc.p->q_abort; wq.cap = qcap; wq.stop_on_degenerate = prm.on_degenerate ? 0u : 1u;
+                for (;;) {
+                    cudaEvent_t e0 = pool_event(n_ev++), e1 = pool_event(n_ev++);
+                    CK(cudaEventRecord(e0, stream));
+                    int rcw = launch_walk(wq); if (rcw) return rcw;
+                    CK(cudaEventRecord(e1, stream));
+                    ++launches; ++expand_launches; ++rounds;
+                    // cells of this context without a vertex get their own descent (rarely any)
+                    CK(cudaMemsetAsync(&sc.p->unseeded, 0, sizeof(u32), stream));
+                    k_unseeded<D><<<blocks_for(n, 256), 256, 0, stream>>>(dv, unseeded_list.p, &sc.p->unseeded); ++launches;
+                    int rc = read_scalars(); if (rc) return rc;
+                    items = h_sc.p->q_done;
+                    if (h_sc.p->q_abort) { err = "walk kernel timed out (internal error)"; return HVB_ECUDA; }
+                    if ((h_ctr.p->degenerate > 0 || (h_ctr.p->flags & FLAG_DEGEN)) && !prm.on_degenerate) {
+                        st.degenerate = (int64_t)std::max<u64>(h_ctr.p->degenerate, 1);
+                        err = "non-general position: a vertex with more than dim+1 cospherical generators was met";
+                        return HVB_EDEGENERATE;
+                    }
+                    if (h_sc.p->pflags || (h_ctr.p->flags & FLAG_OVERFLOW_MASK)) { overflow = true; break; }
+                    u32 uns = h_sc.p->unseeded;
+                    if (uns == 0) break;
+                    if (uns == last_uns && h_sc.p->vcount == last_vcount) break;
+                    last_uns = uns; last_vcount = h_sc.p->vcount;
+                    if (debug) fprintf(stderr, "[hvb] reseeding %u empty cells\n", uns);
+                    // every entry below the old tail is processed: tickets restart there
+                    u32 tl = h_sc.p->rnd[0].qcount;
+                    CK(cudaMemcpyAsync(&sc.p->q_head, &tl, sizeof(u32), cudaMemcpyHostToDevice, stream));
+                    launch_seed(unseeded_list.p, (int)uns, 1, 0);
+                    if (rounds > 1000) { err = "search does not terminate"; return HVB_EINCOMPLETE; }
+                }
+            } else
             for (;;) {
                 int rc = read_scalars(); if (rc) return rc;
-                if (h_sc.p->pflags || h_ctr.p->flags) { overflow = true; break; }
+                if (h_sc.p->pflags || (h_ctr.p->flags & FLAG_OVERFLOW_MASK)) { overflow = true; break; }
                 if (h_ctr.p->degenerate > 0 && !prm.on_degenerate) {
                     // non-general position (edgeiterate.jl territory): stop at once instead of walking a corrupt frontier
                     st.degenerate = (int64_t)h_ctr.p->degenerate;
@@ -701,7 +757,7 @@ void hvb_default_params(hvb_params* p) {
     memset(p, 0, sizeof(*p));
     p->variance_tol = 1e-15; p->break_tol = 1e-5; p->b_nodes_tol = 1e-7; p->plane_tolerance = 1e-12; p->ray_tol = 1e-12;
     p->method = 0; p->device = 0; p->rank = 0; p->world = 1; p->fp32_filter = 1; p->on_degenerate = 0;
-    p->points_per_cell = 0; p->seed_stride = 0; p->sort_output = 1; p->neighbors = 0; p->reserved1 = 0; p->vertex_capacity = 0; p->probe_scale = 0.0;
+    p->points_per_cell = 0; p->seed_stride = 0; p->sort_output = 1; p->neighbors = 0; p->persistent = 1; p->vertex_capacity = 0; p->probe_scale = 0.0;
 }
 
 int hvb_create(hvb_ctx** out, int dim, int64_t n, const double* xs, int nplanes, const double* plane_base,

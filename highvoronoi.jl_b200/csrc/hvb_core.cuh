@@ -151,7 +151,8 @@ struct Counters {
     u32 flags;                         // bit0 vertex store full, bit1 frontier full, bit2 ray list full
     u32 pad;
 };
-enum { FLAG_VFULL = 1, FLAG_QFULL = 2, FLAG_RFULL = 4 };
+enum { FLAG_VFULL = 1, FLAG_QFULL = 2, FLAG_RFULL = 4, FLAG_PAIRFULL = 8, FLAG_DEGEN = 16 };
+const u32 FLAG_OVERFLOW_MASK = FLAG_VFULL | FLAG_QFULL | FLAG_RFULL;
 
 template <int D>
 struct Dev {
@@ -1115,7 +1116,7 @@ HVB_HD void expand_item(const Dev<D>& dv, const T& tile, u64 item, u64* q_out, u
         }
         return;
     }
-    if (best.t2 - best.t <= 1e-12 * fmax(best.t, sqrt(q.R0sq))) ls.degenerate += (lane == 0);
+    if (best.t2 - best.t <= 1e-12 * fmax(best.t, sqrt(q.R0sq))) { ls.degenerate += (lane == 0); if (lane == 0) atom_or(&dv.ctr->flags, (u32)FLAG_DEGEN); }
     // new vertex: (sig minus position kd) plus the winner, kept sorted with static indexing
     int sig2[D + 1];
     {
@@ -1229,7 +1230,7 @@ HVB_HD void seed_item(const Dev<D>& dv, const T& tile, int start, u64* q_out, u3
                 best = min_t_query_call<D, T>(dv, tile, q, ls);
             }
             if (best.id < 0) { ok = false; break; }
-            if (best.t2 - best.t <= 1e-12 * fmax(best.t, sqrt(q.R0sq))) ls.degenerate += (lane == 0);
+            if (best.t2 - best.t <= 1e-12 * fmax(best.t, sqrt(q.R0sq))) { ls.degenerate += (lane == 0); if (lane == 0) atom_or(&dv.ctr->flags, (u32)FLAG_DEGEN); }
 #pragma unroll
             for (int k = 0; k < D; ++k) q.r[k] += best.t * q.u[k];
             sig[cnt++] = best.id;

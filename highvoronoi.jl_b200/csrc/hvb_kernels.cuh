@@ -218,6 +218,75 @@ __global__ void __launch_bounds__(128, HVB_EXPAND_MINB) k_expand(Dev<D> dv, cons
     flush_stats(ls, dv.ctr);
 }
 
+// The whole frontier walk as ONE launch: a single append-only queue (every edge enters it exactly once), consumers
+// take tickets (atomicAdd on `head`) and wait for the entry behind their ticket to be published, producers append at
+// `tail`.  No round barrier: an edge opened by a new vertex is walked as soon as a lane is free, so there are no
+// per-round tails and no host round trips.  Termination: `done` counts fully processed entries (including their
+// pushes); when done == tail and a lane's ticket is >= tail nothing can ever be published again.
+// A lane never blocks: if its entry is not there yet it idles for one trip of the warp-uniform loop.
+struct WalkQueue {
+    u64* q;            // [cap], 0xff..ff = not yet published
+    u32* tail;         // entries appended so far (also q_count of commit_vertex)
+    u32* head;         // tickets handed out
+    u32* done;         // entries fully processed
+    u32* abort;        // set when the safety timeout fires
+    u32 cap;
+    u32 stop_on_degenerate;
+};
+#define HVB_Q_EMPTY 0xffffffffffffffffULL
+
+template <int D, int G>
+__global__ void __launch_bounds__(128, HVB_EXPAND_MINB) k_walk(Dev<D> dv, WalkQueue wq) {
+    TileDev<G> tile;
+    LocalStats ls = {};
+    u32 ticket = 0xffffffffu;          // held by lane 0 of the tile
+    u32 my_done = 0;                   // processed entries not yet added to *done
+    long long t_idle = clock64();
+    for (u32 trip = 0;; ++trip) {
+        u64 item = 0;
+        int live = 0, finished = 0;
+        if (tile.lane() == 0) {
+            // non-general position stops the walk at once (the host reports HVB_EDEGENERATE); so does the safety abort
+            if ((wq.stop_on_degenerate && (__ldcg(&dv.ctr->flags) & FLAG_DEGEN)) || __ldcg(wq.abort)) finished = 1;
+            for (int tries = 0; tries < 4 && !live && !finished; ++tries) {
+                if (ticket == 0xffffffffu) ticket = atomicAdd(wq.head, 1u);
+                // a ticket beyond the queue's capacity can never be served (pushes beyond it are refused and flagged
+                // by commit_vertex): such a lane only waits for the end like one whose entry is not published yet
+                u64 it = (ticket < wq.cap) ? __ldcg(wq.q + ticket) : HVB_Q_EMPTY;
+                if (it == HVB_Q_EMPTY) {
+                    // nothing behind this ticket yet: publish my progress, then test for global completion
+                    if (my_done) { __threadfence(); atomicAdd(wq.done, my_done); my_done = 0; }
+                    u32 dn = __ldcg(wq.done);
+                    u32 tl = __ldcg(wq.tail);
+                    if ((dn == tl && ticket >= tl) || __ldcg(wq.abort)) finished = 1;
+                    break;
+                }
+                u64 s = __ldcg(dv.etab + (u32)(it >> 32));
+                if (!(s >> 63)) break;                          // the edge slot is not visible yet: retry next trip
+                ticket = 0xffffffffu;
+                if (s & EDGE_CLOSED) { ls.closed_skips++; ++my_done; continue; }
+                item = it; live = 1;
+            }
+        }
+        if (G > 1) { item = tile.shfl(item, 0); live = tile.shfl(live, 0); finished = tile.shfl(finished, 0); }
+        if (__all_sync(0xffffffffu, finished)) break;
+        const bool any_live = __any_sync(0xffffffffu, live) != 0;      // voted by all lanes BEFORE they part ways
+        if (live) {
+            expand_item<D, TileDev<G> >(dv, tile, item, wq.q, wq.tail, wq.cap, ls);
+            if (tile.lane() == 0) ++my_done;
+        }
+        if (any_live) t_idle = clock64();
+        else {
+            // the whole warp is idle: back off, and make sure a bug can never hang the device (20 s without work)
+            __nanosleep(256);
+            if ((trip & 1023u) == 1023u && clock64() - t_idle > 40000000000LL) atomicExch(wq.abort, 1u);
+        }
+        __syncwarp();
+    }
+    if (tile.lane() == 0 && my_done) { __threadfence(); atomicAdd(wq.done, my_done); }
+    flush_stats(ls, dv.ctr);
+}
+
 // cells of this context that still have no vertex (sysvoronoi.jl:416-429: they get their own descent)
 template <int D>
 __global__ void k_unseeded(Dev<D> dv, int* list, u32* count) {

@@ -59,7 +59,8 @@ typedef struct hvb_params {
     int32_t tile_size;        /* lanes cooperating on one frontier entry: 1, 2, 4, 8, 16 or 32; 0 = auto by dimension */
     int32_t neighbors;        /* 1: hvb_search also builds and stages the neighbour lists (default 0: on first request);
                                  with world > 1 they are built from the slab result: complete for the rank's own cells */
-    int32_t reserved1;
+    int32_t persistent;       /* 1 (default): the frontier walk is one persistent launch with a device-side queue;
+                                 0: one launch per frontier round */
     int64_t vertex_capacity;  /* 0 = estimate from lowerbound(d,d) (edgeiteratebase.jl:151); grows on demand */
     double probe_scale;       /* first probe ball radius / circumradius of the origin vertex; 0 = auto */
 } hvb_params;

@@ -26,7 +26,7 @@ mutable struct HvbParams
     variance_tol::Cdouble; break_tol::Cdouble; b_nodes_tol::Cdouble; plane_tolerance::Cdouble; ray_tol::Cdouble
     method::Int32; device::Int32; rank::Int32; world::Int32
     fp32_filter::Int32; on_degenerate::Int32; points_per_cell::Int32; seed_stride::Int32; sort_output::Int32
-    tile_size::Int32; neighbors::Int32; reserved1::Int32
+    tile_size::Int32; neighbors::Int32; persistent::Int32
     vertex_capacity::Int64; probe_scale::Cdouble
     HvbParams() = new()
 end

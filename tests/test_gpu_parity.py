@@ -117,6 +117,41 @@ def test_slab_union_equals_full(hvb, oracle):
     assert rows == {tuple(r) for r in o["sig"].tolist()}
 
 
+def test_capacity_retry_path(hvb, oracle):
+    """a far too small vertex capacity must be grown transparently (tables re-allocated, search restarted)"""
+    xs = points(3000, 3, 12)
+    base, normal = qhull_oracle.cuboid(3)
+    o = oracle.run(xs, base, normal)
+    for persistent in (1, 0):
+        mesh, s = run_gpu(hvb, xs, True, vertex_capacity=700, persistent=persistent)
+        assert np.array_equal(mesh.sig, o["sig"])
+        assert s.stats()["capacity_retries"] >= 3
+
+
+@pytest.mark.parametrize("persistent", [0, 1])
+@pytest.mark.parametrize("tile", [1, 2, 4, 8, 16, 32])
+def test_every_tile_size_and_both_walk_modes(hvb, oracle, tile, persistent):
+    xs = points(4000, 3, 13)
+    base, normal = qhull_oracle.cuboid(3)
+    o = oracle.run(xs, base, normal)
+    mesh, _ = run_gpu(hvb, xs, True, tile_size=tile, persistent=persistent)
+    assert_same_mesh(mesh.sig, mesh.r, o["sig"], o["r"], xs, COORD_TOL)
+
+
+def test_context_reuse_set_points(hvb, oracle):
+    """hvb_set_points: one context, several clouds of different sizes, results independent of the history"""
+    base, normal = qhull_oracle.cuboid(3)
+    s = hvb.Raycast(points(2000, 3, 14), domain=hvb.cuboid(3, periodic=[]))
+    for n, seed in [(2000, 14), (9000, 15), (500, 16), (9000, 15)]:
+        xs = points(n, 3, seed)
+        s.set_points(xs)
+        mesh, _ = hvb.voronoi(xs, searcher=s)
+        o = oracle.run(xs, base, normal)
+        assert_same_mesh(mesh.sig, mesh.r, o["sig"], o["r"], xs, COORD_TOL)
+        off, ids = mesh.neighbors()
+        assert np.array_equal(off, o["nb_off"]) and np.array_equal(ids, o["nb_ids"])
+
+
 def test_points_outside_domain_are_rejected(hvb):
     xs = points(100, 3, 0)
     xs[5, 1] = 1.5
