@@ -43,6 +43,16 @@ def measured_peak():
         return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
+def measured_traffic(workload):
+    """dram__bytes_read.sum + dram__bytes_write.sum of the dominant kernel per launch, from the committed ncu capture
+    (profiles/r1_traffic.json; null when no capture exists for this workload)"""
+    try:
+        with open(os.path.join(ROOT, "profiles", "r1_traffic.json")) as f:
+            return json.load(f).get(workload, {}).get("dram_bytes_per_launch")
+    except Exception:
+        return None
+
+
 class ClockSampler:
     """samples nvidia-smi clocks / throttle reasons during the timed region"""
     Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
@@ -271,8 +281,8 @@ def main():
                 "phase_ms": dict(zip(("set_points", "search", "fetch_vertices", "neighbors"), (1e3 * phases / args.steps).round(3).tolist()))},
         "gpu_launches": launches,
         "clocks": clocks,
-        "roofline": {"bound": "hbm", "kernel": "k_expand<%d>" % d, "achieved": achieved, "peak": peak, "unit": "GB/s",
-                     "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+        "roofline": {"bound": "hbm", "kernel": ("k_walk<%d>" if settings.get("persistent", 1) else "k_expand<%d>") % d, "achieved": achieved, "peak": peak, "unit": "GB/s",
+                     "frac": achieved / peak, "traffic": measured_traffic(args.workload), "peak_source": peak_src,
                      "bytes_per_vertex": B_ALG[d], "launches_per_step": kern_launches / args.steps,
                      "kernel_ms_per_step": kern_ms / args.steps},
         "vertices_per_step": verts / args.steps,

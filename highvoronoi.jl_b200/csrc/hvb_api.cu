@@ -236,7 +236,7 @@ struct Ctx : hvb_ctx {
         // upload, then bounding box + domain check on the device (check_boundary, boundary.jl:437)
         CK(xs_in.ensure((size_t)n * D));
         CK(cudaMemcpyAsync(xs_in.p, xs, (size_t)n * D * sizeof(double), cudaMemcpyHostToDevice, stream));
-        const int bb_blocks = std::min(blocks_for(n, 256), sms * 4);
+        const int bb_blocks = std::min(blocks_for(n, 256), sms);
         CK(bbox_partial.ensure((size_t)bb_blocks * 2 * D));
         CK(cudaMemsetAsync(&sc.p->bbox_done, 0, sizeof(u32), stream));
         CK(cudaMemsetAsync(&sc.p->bbox_viol, 0xff, sizeof(u32), stream));

@@ -247,7 +247,11 @@ __global__ void __launch_bounds__(128, HVB_EXPAND_MINB) k_walk(Dev<D> dv, WalkQu
         int live = 0, finished = 0;
         if (tile.lane() == 0) {
             // non-general position stops the walk at once (the host reports HVB_EDEGENERATE); so does the safety abort
-            if ((wq.stop_on_degenerate && (__ldcg(&dv.ctr->flags) & FLAG_DEGEN)) || __ldcg(wq.abort)) finished = 1;
+            // (so does a full vertex store / queue: the host grows the tables and restarts)
+            {
+                const u32 fl = __ldcg(&dv.ctr->flags);
+                if ((fl & FLAG_OVERFLOW_MASK) || (wq.stop_on_degenerate && (fl & FLAG_DEGEN)) || __ldcg(wq.abort)) finished = 1;
+            }
             for (int tries = 0; tries < 4 && !live && !finished; ++tries) {
                 if (ticket == 0xffffffffu) ticket = atomicAdd(wq.head, 1u);
                 // a ticket beyond the queue's capacity can never be served (pushes beyond it are refused and flagged
