@@ -181,10 +181,11 @@ __global__ void __launch_bounds__(128) k_seed(Dev<D> dv, const int* __restrict__
     flush_stats(ls, dv.ctr);
 }
 
-// resident blocks per SM the walk kernel is compiled for: 4 (<= 128 registers) measured best for d <= 3, the
-// register-hungry higher dimensions run faster unconstrained (profiles/r1_tile_occupancy_sweep.md)
+// resident blocks per SM the walk kernel is compiled for: 4 (<= 128 registers per thread) measured best for d = 2..5
+// although the higher dimensions spill: occupancy matters more to this latency-bound kernel
+// (profiles/r1_tile_occupancy_sweep.md)
 #ifndef HVB_EXPAND_MINB
-#define HVB_EXPAND_MINB ((D <= 3) ? 4 : 1)
+#define HVB_EXPAND_MINB 4
 #endif
 // One frontier round.  Tiles pull entries from a shared cursor and skip closed edges while acquiring, so that all
 // tiles of a warp enter the expensive part (direction, min-t query, commit) with live work.
