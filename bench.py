@@ -31,7 +31,7 @@ sys.path.insert(0, ROOT)
 # algorithmic bytes per vertex, SURVEY.md section 8(d) / BASELINE.md section 3
 B_ALG = {2: 240.0, 3: 429.0, 4: 740.0, 5: 1344.0, 6: 2755.0}
 WORKLOADS = {  # name -> (points per GPU, dim)
-    "C2": (100000, 3), "C1": (1000, 3), "C3": (1000000, 2), "C4": (50000, 5), "C4s": (20000, 5), "D4": (30000, 4),
+    "C2": (100000, 3), "C1": (1000, 3), "C3": (1000000, 2), "C4": (50000, 5), "C4s": (20000, 5), "D4": (30000, 4), "D6": (4000, 6),
 }
 
 
