@@ -102,6 +102,7 @@ struct hvb_ctx {
     virtual int view_neighbors(const int64_t** off, const int64_t** ids, int64_t* total) = 0;
     virtual int export_device(void* sig, void* r, int64_t cap, int64_t* count) = 0;
     virtual int merge_device(const void* sig, const void* r, int64_t count) = 0;
+    virtual int adopt_device(const void* sig, const void* r, int64_t count) = 0;
 };
 
 template <int D>
@@ -498,6 +499,7 @@ struct Ctx : hvb_ctx {
         have_result = true;
         CK(cudaEventRecord(ev_n0, stream));
         if (prm.neighbors) { rc = build_neighbors(); if (rc) return rc; rc = stage_neighbors(); if (rc) return rc; }
+        if (world > 1 && cells == nullptr) { rc = finalize_owned(); if (rc) return rc; }
         CK(cudaEventRecord(ev_n1, stream));
         CK(cudaStreamWaitEvent(stream, ev_stage_done(), 0));
         CK(cudaEventRecord(ev_d, stream));
@@ -560,7 +562,7 @@ struct Ctx : hvb_ctx {
         int bits = id_bits();
         if (nrec > 0) {
             k_final_rows<D><<<blocks_for(nrec, 128), 128, 0, stream>>>(dv, perm.p, nrec, bits, out_sig[0].p, out_r[0].p, key_hi.p, key_lo.p,
-                                                                     &sc.p->out_count, &sc.p->max_var);
+                                                                     &sc.p->out_count, &sc.p->max_var, 0, 0);
             ++launches;
         }
         if (nrays > 0) {
@@ -571,6 +573,23 @@ struct Ctx : hvb_ctx {
         int rc = read_scalars(); if (rc) return rc;
         nvert = h_sc.p->out_count;
         if (std::max(1, prm.world) > 1) { res = 0; return HVB_OK; }     // slab rows are sorted after the merge
+        return sort_rows((u32)nvert, bits);
+    }
+
+    // multi-GPU: keep only the vertices this rank owns (after the neighbour lists were built from ALL local rows)
+    int finalize_owned() {
+        const int world = std::max(1, prm.world), rank = std::min(std::max(0, prm.rank), world - 1);
+        u32 nrec = std::min<u32>(h_sc.p->vcount, (u32)vcap);
+        int lo = (int)(n * rank / world), hi = (int)(n * (rank + 1) / world);
+        int bits = id_bits();
+        CK(cudaMemsetAsync(&sc.p->out_count, 0, sizeof(u32), stream));
+        if (nrec > 0) {
+            k_final_rows<D><<<blocks_for(nrec, 128), 128, 0, stream>>>(dv, perm.p, nrec, bits, out_sig[0].p, out_r[0].p, key_hi.p, key_lo.p,
+                                                                     &sc.p->out_count, &sc.p->max_var, lo, hi);
+            ++launches;
+        }
+        int rc = read_scalars(); if (rc) return rc;
+        nvert = h_sc.p->out_count;
         return sort_rows((u32)nvert, bits);
     }
 
@@ -721,6 +740,20 @@ struct Ctx : hvb_ctx {
         CK(cudaStreamSynchronize(stream));
         return HVB_OK;
     }
+    // the gathered rows of all ranks are disjoint (ownership rule) and sorted per rank: they become the result as-is
+    int adopt_device(const void* sig, const void* r, int64_t count) override {
+        CK(cudaSetDevice(prm.device));
+        CK(out_sig[0].ensure((size_t)std::max<int64_t>(count, 1) * (D + 1))); CK(out_r[0].ensure((size_t)std::max<int64_t>(count, 1) * D));
+        if (count > 0) {
+            CK(cudaMemcpyAsync(out_sig[0].p, sig, (size_t)count * (D + 1) * 8, cudaMemcpyDeviceToDevice, stream));
+            CK(cudaMemcpyAsync(out_r[0].p, r, (size_t)count * D * 8, cudaMemcpyDeviceToDevice, stream));
+        }
+        CK(cudaStreamSynchronize(stream));
+        nvert = count; res = 0; staged = false; have_result = true;
+        if (!(prm.neighbors && std::max(1, prm.world) > 1)) nb_total = -1;
+        st.vertices = nvert;
+        return HVB_OK;
+    }
     int merge_device(const void* sig, const void* r, int64_t count) override {
         CK(cudaSetDevice(prm.device));
         for (int i = 0; i < 2; ++i) { CK(out_sig[i].ensure((size_t)std::max<int64_t>(count, 1) * (D + 1))); CK(out_r[i].ensure((size_t)std::max<int64_t>(count, 1) * D)); }
@@ -808,6 +841,7 @@ int hvb_fetch_neighbors(hvb_ctx* ctx, int64_t* offsets, int64_t* ids) { return c
 int hvb_view_neighbors(hvb_ctx* ctx, const int64_t** offsets, const int64_t** ids, int64_t* total) { return (ctx && offsets && ids && total) ? ctx->view_neighbors(offsets, ids, total) : HVB_EINVAL; }
 int hvb_export_device(hvb_ctx* ctx, void* sig_dev, void* r_dev, int64_t cap, int64_t* count) { return ctx ? ctx->export_device(sig_dev, r_dev, cap, count) : HVB_EINVAL; }
 int hvb_merge_device(hvb_ctx* ctx, const void* sig_dev, const void* r_dev, int64_t count) { return ctx ? ctx->merge_device(sig_dev, r_dev, count) : HVB_EINVAL; }
+int hvb_adopt_device(hvb_ctx* ctx, const void* sig_dev, const void* r_dev, int64_t count) { return ctx ? ctx->adopt_device(sig_dev, r_dev, count) : HVB_EINVAL; }
 int hvb_stats(hvb_ctx* ctx, hvb_stats_t* out) {
     if (!ctx || !out) return HVB_EINVAL;
     *out = ctx->st;

@@ -308,11 +308,15 @@ template <int D>
 __global__ void k_final_rows(Dev<D> dv, const int* __restrict__ perm, u32 nrec, int bits,
                              long long* __restrict__ out_sig, double* __restrict__ out_r,
                              u64* __restrict__ key_hi, u64* __restrict__ key_lo, u32* __restrict__ out_count,
-                             double* __restrict__ max_var) {
+                             double* __restrict__ max_var, int own_lo, int own_hi) {
     u32 v = blockIdx.x * blockDim.x + threadIdx.x;
     if (v >= nrec) return;
     const int* s = dv.vsig + (size_t)v * (D + 1);
     if (s[0] < 0) return;
+    // multi-GPU ownership rule: a vertex belongs to the slab that holds its first generator in grid order (s is
+    // sorted by internal = grid-order id); every rank finds all vertices it owns, so the owned sets are disjoint
+    // and their union is the full set -- a deterministic dedup that needs no communication
+    if (own_hi > own_lo && (s[0] < own_lo || s[0] >= own_hi)) return;
     int in[D + 1];
     long long og[D + 1];
 #pragma unroll

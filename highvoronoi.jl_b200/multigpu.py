@@ -40,8 +40,10 @@ def all_gather_rows(sig, r, count, group=None):
     return sig_all, r_all, (sig_p.numel() + r_p.numel()) * 8
 
 
-def gather_and_merge(searcher, group=None):
-    """exchange + merge for a searcher that finished its slab search; afterwards the context holds the global result"""
+def gather_and_merge(searcher, group=None, dedup=False):
+    """exchange step for a searcher that finished its slab search; afterwards the context holds the global result.
+    The ranks return disjoint, sorted, owned rows, so the gathered concatenation is installed as-is
+    (hvb_adopt_device); dedup=True runs the generic hash dedup + global sort instead (hvb_merge_device)."""
     L, ctx = _abi.lib(), searcher._ctx
     d = searcher.dim
     nv = ctypes.c_int64()
@@ -53,5 +55,6 @@ def gather_and_merge(searcher, group=None):
     _abi.check(L.hvb_export_device(ctx, sig.data_ptr(), r.data_ptr(), cap, ctypes.byref(got)), ctx)
     sig_all, r_all, sent = all_gather_rows(sig, r, got.value, group)
     torch.cuda.synchronize()
-    _abi.check(L.hvb_merge_device(ctx, sig_all.data_ptr(), r_all.data_ptr(), sig_all.shape[0]), ctx)
+    fn = L.hvb_merge_device if dedup else L.hvb_adopt_device
+    _abi.check(fn(ctx, sig_all.data_ptr(), r_all.data_ptr(), sig_all.shape[0]), ctx)
     return sent

@@ -138,12 +138,17 @@ int hvb_view_vertices(hvb_ctx* ctx, const int64_t** sig, const double** r, int64
 int hvb_view_neighbors(hvb_ctx* ctx, const int64_t** offsets, const int64_t** ids, int64_t* total);
 
 /* Multi-GPU exchange step (parallelmesh.jl's shared store becomes: local search -> all-gather -> merge).
- * hvb_export_device copies this rank's vertices (int32 sig rows of dim+1 0-based caller ids, double r rows)
+ * hvb_export_device copies this rank's vertices (int64 sig rows of dim+1 sorted 1-based caller ids, double r rows)
  * into caller-provided DEVICE buffers of capacity `cap` rows; hvb_merge_device replaces the context's result
  * by the deduplicated, sorted union of `count` gathered rows (device pointers).  The collective itself
  * (NCCL all-gather) is issued by the host language between the two calls. */
 int hvb_export_device(hvb_ctx* ctx, void* sig_dev, void* r_dev, int64_t cap, int64_t* count);
 int hvb_merge_device(hvb_ctx* ctx, const void* sig_dev, const void* r_dev, int64_t count);
+/* With world > 1 a context returns only the vertices it OWNS (first generator in grid order inside its slab): the
+ * owned sets of the ranks are disjoint, sorted, and their union is the full vertex set.  After the all-gather the
+ * concatenation (rank order) is therefore already deduplicated: hvb_adopt_device installs it as the result without
+ * the hash dedup and re-sort of hvb_merge_device. */
+int hvb_adopt_device(hvb_ctx* ctx, const void* sig_dev, const void* r_dev, int64_t count);
 
 /* rare_events / statistics.jl:132-143 analogue */
 int hvb_stats(hvb_ctx* ctx, hvb_stats_t* out);

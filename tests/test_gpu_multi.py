@@ -36,7 +36,7 @@ def _worker(rank, world, port, n, d, out):
     s = hvb200.Raycast(xs, domain=dom, options=hvb200.RaycastParameter(threading=hvb200.B200Thread(rank, rank, world)))
     mesh, _ = hvb200.voronoi(xs, searcher=s)
     local = mesh.sig.shape[0]
-    multigpu.gather_and_merge(s)
+    multigpu.gather_and_merge(s, dedup=(rank == 0))          # rank 0 exercises the generic dedup + sort, rank 1 the adopt path
     merged = hvb200.VoronoiMesh(s, copy=True)
     off, ids = merged.neighbors()
     out[rank] = (merged.sig.copy(), merged.r.copy(), np.array(off), np.array(ids), local)
@@ -57,8 +57,12 @@ def test_two_gpu_merge_equals_single(hvb):
     single = hvb.Raycast(xs, domain=hvb.cuboid(d, periodic=[]))
     mesh, _ = hvb.voronoi(xs, searcher=single, copy=True)
     off, ids = mesh.neighbors()
+    assert res[0][4] + res[1][4] == mesh.sig.shape[0]                            # disjoint owned shards
     for rank in range(world):
         sig, r, o2, i2, local = res[rank]
+        if rank == 1:                                                            # adopt path: sorted runs in rank order
+            order = np.lexsort(sig.T[::-1])
+            sig, r = sig[order], r[order]
         assert np.array_equal(sig, mesh.sig) and np.array_equal(r, mesh.r)      # bitwise: canonical coordinates
         assert np.array_equal(o2, off) and np.array_equal(i2, ids)
         assert local < mesh.sig.shape[0]

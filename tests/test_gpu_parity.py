@@ -109,12 +109,16 @@ def test_slab_union_equals_full(hvb, oracle):
     xs = points(6000, 3, 10)
     base, normal = qhull_oracle.cuboid(3)
     o = oracle.run(xs, base, normal)
-    rows = set()
+    rows, total = set(), 0
     for rank in range(4):
-        s = hvb.Raycast(xs, domain=hvb.cuboid(3, periodic=[]), options=hvb.RaycastParameter(threading=hvb.B200Thread(0, rank, 4)))
+        s = hvb.Raycast(xs, domain=hvb.cuboid(3, periodic=[]), options=hvb.RaycastParameter(threading=hvb.B200Thread(0, rank, 4), neighbors=1))
         mesh, _ = hvb.voronoi(xs, searcher=s)
+        assert (np.diff(mesh.sig[:, 0]) >= 0).all()                      # each shard is sorted
         rows |= {tuple(r) for r in mesh.sig.tolist()}
+        total += mesh.sig.shape[0]
+        assert s.stats()["raycasts"] < 0.6 * len(o["sig"])               # a rank walks its slab only
     assert rows == {tuple(r) for r in o["sig"].tolist()}
+    assert total == len(o["sig"])                                        # ownership rule: the shards are disjoint
 
 
 def test_capacity_retry_path(hvb, oracle):
