@@ -176,7 +176,7 @@ def main():
     def gather_merge(searcher):
         """multi-GPU exchange: counts + padded rows by NCCL all-gather, dedup + sort on every rank"""
         from hvb200 import multigpu
-        return multigpu.gather_and_merge(searcher)
+        return multigpu.gather_and_merge(searcher, cache=state.setdefault("xchg", {}))
 
     state = {"s": None}
     phases = np.zeros(4)

@@ -11,7 +11,7 @@ ERROR_NAMES = {-1: "HVB_EINVAL", -2: "HVB_ECUDA", -3: "HVB_ENOGPU", -4: "HVB_ENO
                -6: "HVB_ESTATE", -7: "HVB_EINCOMPLETE"}
 
 EXPORTS = ("hvb_default_params", "hvb_create", "hvb_set_points", "hvb_search", "hvb_counts", "hvb_fetch_vertices", "hvb_fetch_vertices_range", "hvb_fetch_rays",
-           "hvb_neighbor_count", "hvb_fetch_neighbors", "hvb_view_vertices", "hvb_view_neighbors", "hvb_export_device", "hvb_merge_device", "hvb_adopt_device",
+           "hvb_neighbor_count", "hvb_fetch_neighbors", "hvb_view_vertices", "hvb_view_neighbors", "hvb_export_device", "hvb_merge_device", "hvb_adopt_device", "hvb_adopt_device_padded",
            "hvb_stats", "hvb_last_error", "hvb_destroy", "hvb_version")
 
 
@@ -69,6 +69,7 @@ def lib():
         L.hvb_export_device.argtypes = [vp, vp, vp, i64, ctypes.POINTER(i64)]
         L.hvb_merge_device.argtypes = [vp, vp, vp, i64]
         L.hvb_adopt_device.argtypes = [vp, vp, vp, i64]
+        L.hvb_adopt_device_padded.argtypes = [vp, vp, vp, i32, i64, vp]
         L.hvb_stats.argtypes = [vp, ctypes.POINTER(hvb_stats_t)]
         L.hvb_last_error.argtypes = [vp]
         L.hvb_last_error.restype = ctypes.c_char_p
@@ -76,7 +77,7 @@ def lib():
         L.hvb_destroy.restype = None
         L.hvb_version.restype = ctypes.c_char_p
         for name in ("hvb_create", "hvb_set_points", "hvb_search", "hvb_counts", "hvb_fetch_vertices", "hvb_fetch_vertices_range", "hvb_fetch_rays", "hvb_neighbor_count",
-                     "hvb_fetch_neighbors", "hvb_view_vertices", "hvb_view_neighbors", "hvb_export_device", "hvb_merge_device", "hvb_adopt_device", "hvb_stats"):
+                     "hvb_fetch_neighbors", "hvb_view_vertices", "hvb_view_neighbors", "hvb_export_device", "hvb_merge_device", "hvb_adopt_device", "hvb_adopt_device_padded", "hvb_stats"):
             getattr(L, name).restype = i32
         _lib = L
     return _lib

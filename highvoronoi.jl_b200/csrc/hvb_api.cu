@@ -103,6 +103,7 @@ struct hvb_ctx {
     virtual int export_device(void* sig, void* r, int64_t cap, int64_t* count) = 0;
     virtual int merge_device(const void* sig, const void* r, int64_t count) = 0;
     virtual int adopt_device(const void* sig, const void* r, int64_t count) = 0;
+    virtual int adopt_device_padded(const void* sig, const void* r, int nseg, int64_t seg_cap, const int64_t* counts) = 0;
 };
 
 template <int D>
@@ -754,6 +755,27 @@ struct Ctx : hvb_ctx {
         st.vertices = nvert;
         return HVB_OK;
     }
+    // the same for the raw output of a padded all-gather: segment k holds counts[k] valid rows followed by padding
+    int adopt_device_padded(const void* sig, const void* r, int nseg, int64_t seg_cap, const int64_t* counts) override {
+        CK(cudaSetDevice(prm.device));
+        int64_t total = 0;
+        for (int k = 0; k < nseg; ++k) { if (counts[k] < 0 || counts[k] > seg_cap) { err = "bad segment count"; return HVB_EINVAL; } total += counts[k]; }
+        CK(out_sig[0].ensure((size_t)std::max<int64_t>(total, 1) * (D + 1))); CK(out_r[0].ensure((size_t)std::max<int64_t>(total, 1) * D));
+        int64_t at = 0;
+        for (int k = 0; k < nseg; ++k) {
+            if (counts[k] == 0) continue;
+            CK(cudaMemcpyAsync(out_sig[0].p + (size_t)at * (D + 1), (const long long*)sig + (size_t)k * seg_cap * (D + 1),
+                               (size_t)counts[k] * (D + 1) * 8, cudaMemcpyDeviceToDevice, stream));
+            CK(cudaMemcpyAsync(out_r[0].p + (size_t)at * D, (const double*)r + (size_t)k * seg_cap * D,
+                               (size_t)counts[k] * D * 8, cudaMemcpyDeviceToDevice, stream));
+            at += counts[k];
+        }
+        CK(cudaStreamSynchronize(stream));
+        nvert = total; res = 0; staged = false; have_result = true;
+        if (!(prm.neighbors && std::max(1, prm.world) > 1)) nb_total = -1;
+        st.vertices = nvert;
+        return HVB_OK;
+    }
     int merge_device(const void* sig, const void* r, int64_t count) override {
         CK(cudaSetDevice(prm.device));
         for (int i = 0; i < 2; ++i) { CK(out_sig[i].ensure((size_t)std::max<int64_t>(count, 1) * (D + 1))); CK(out_r[i].ensure((size_t)std::max<int64_t>(count, 1) * D)); }
@@ -841,6 +863,7 @@ int hvb_fetch_neighbors(hvb_ctx* ctx, int64_t* offsets, int64_t* ids) { return c
 int hvb_view_neighbors(hvb_ctx* ctx, const int64_t** offsets, const int64_t** ids, int64_t* total) { return (ctx && offsets && ids && total) ? ctx->view_neighbors(offsets, ids, total) : HVB_EINVAL; }
 int hvb_export_device(hvb_ctx* ctx, void* sig_dev, void* r_dev, int64_t cap, int64_t* count) { return ctx ? ctx->export_device(sig_dev, r_dev, cap, count) : HVB_EINVAL; }
 int hvb_merge_device(hvb_ctx* ctx, const void* sig_dev, const void* r_dev, int64_t count) { return ctx ? ctx->merge_device(sig_dev, r_dev, count) : HVB_EINVAL; }
+int hvb_adopt_device_padded(hvb_ctx* ctx, const void* sig_dev, const void* r_dev, int nseg, int64_t seg_cap, const int64_t* counts) { return (ctx && counts) ? ctx->adopt_device_padded(sig_dev, r_dev, nseg, seg_cap, counts) : HVB_EINVAL; }
 int hvb_adopt_device(hvb_ctx* ctx, const void* sig_dev, const void* r_dev, int64_t count) { return ctx ? ctx->adopt_device(sig_dev, r_dev, count) : HVB_EINVAL; }
 int hvb_stats(hvb_ctx* ctx, hvb_stats_t* out) {
     if (!ctx || !out) return HVB_EINVAL;

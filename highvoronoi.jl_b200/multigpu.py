@@ -40,21 +40,48 @@ def all_gather_rows(sig, r, count, group=None):
     return sig_all, r_all, (sig_p.numel() + r_p.numel()) * 8
 
 
-def gather_and_merge(searcher, group=None, dedup=False):
+def gather_and_merge(searcher, group=None, dedup=False, cache=None):
     """exchange step for a searcher that finished its slab search; afterwards the context holds the global result.
-    The ranks return disjoint, sorted, owned rows, so the gathered concatenation is installed as-is
-    (hvb_adopt_device); dedup=True runs the generic hash dedup + global sort instead (hvb_merge_device)."""
+    The ranks return disjoint, sorted, owned rows, so the padded all-gather output is installed as it is
+    (hvb_adopt_device_padded: no dedup, no re-sort); dedup=True runs the generic hash dedup + global sort instead
+    (hvb_merge_device).  `cache` (a dict) keeps the exchange buffers between calls."""
+    import numpy as np
     L, ctx = _abi.lib(), searcher._ctx
     d = searcher.dim
+    world = dist.get_world_size(group)
     nv = ctypes.c_int64()
     _abi.check(L.hvb_counts(ctx, ctypes.byref(nv), None, None), ctx)
-    cap = max(nv.value, 1)
-    sig = torch.empty((cap, d + 1), dtype=torch.int64, device="cuda")
-    r = torch.empty((cap, d), dtype=torch.float64, device="cuda")
+    if dedup:
+        cap = max(nv.value, 1)
+        sig = torch.empty((cap, d + 1), dtype=torch.int64, device="cuda")
+        r = torch.empty((cap, d), dtype=torch.float64, device="cuda")
+        got = ctypes.c_int64()
+        _abi.check(L.hvb_export_device(ctx, sig.data_ptr(), r.data_ptr(), cap, ctypes.byref(got)), ctx)
+        sig_all, r_all, sent = all_gather_rows(sig, r, got.value, group)
+        torch.cuda.synchronize()
+        _abi.check(L.hvb_merge_device(ctx, sig_all.data_ptr(), r_all.data_ptr(), sig_all.shape[0]), ctx)
+        return sent
+    # counts of all ranks (one small collective, one host read)
+    cnt = torch.tensor([nv.value], dtype=torch.int64, device="cuda")
+    cnts_t = torch.empty(world, dtype=torch.int64, device="cuda")
+    dist.all_gather_into_tensor(cnts_t, cnt, group=group)
+    cnts = cnts_t.cpu().numpy().astype(np.int64)
+    cap = int(cnts.max()) if cnts.max() > 0 else 1
+    cache = cache if cache is not None else {}
+    if cache.get("cap", 0) < cap:                       # exchange buffers grow geometrically and are re-used
+        newcap = int(cap * 1.2) + 1024
+        cache.update(cap=newcap,
+                     sig=torch.empty((newcap, d + 1), dtype=torch.int64, device="cuda"),
+                     r=torch.empty((newcap, d), dtype=torch.float64, device="cuda"),
+                     sig_all=torch.empty((world, newcap, d + 1), dtype=torch.int64, device="cuda"),
+                     r_all=torch.empty((world, newcap, d), dtype=torch.float64, device="cuda"))
+    bufcap = cache["cap"]
     got = ctypes.c_int64()
-    _abi.check(L.hvb_export_device(ctx, sig.data_ptr(), r.data_ptr(), cap, ctypes.byref(got)), ctx)
-    sig_all, r_all, sent = all_gather_rows(sig, r, got.value, group)
+    _abi.check(L.hvb_export_device(ctx, cache["sig"].data_ptr(), cache["r"].data_ptr(), bufcap, ctypes.byref(got)), ctx)
+    # padded all-gather straight into one buffer per array; only the valid prefixes are copied out afterwards
+    dist.all_gather_into_tensor(cache["sig_all"].view(-1), cache["sig"].view(-1), group=group)
+    dist.all_gather_into_tensor(cache["r_all"].view(-1), cache["r"].view(-1), group=group)
     torch.cuda.synchronize()
-    fn = L.hvb_merge_device if dedup else L.hvb_adopt_device
-    _abi.check(fn(ctx, sig_all.data_ptr(), r_all.data_ptr(), sig_all.shape[0]), ctx)
-    return sent
+    _abi.check(L.hvb_adopt_device_padded(ctx, cache["sig_all"].data_ptr(), cache["r_all"].data_ptr(), world, bufcap,
+                                         cnts.ctypes.data_as(ctypes.c_void_p)), ctx)
+    return (cache["sig"].numel() + cache["r"].numel()) * 8

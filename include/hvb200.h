@@ -149,6 +149,8 @@ int hvb_merge_device(hvb_ctx* ctx, const void* sig_dev, const void* r_dev, int64
  * concatenation (rank order) is therefore already deduplicated: hvb_adopt_device installs it as the result without
  * the hash dedup and re-sort of hvb_merge_device. */
 int hvb_adopt_device(hvb_ctx* ctx, const void* sig_dev, const void* r_dev, int64_t count);
+/* same, for the raw output of a padded all-gather: nseg segments of seg_cap rows, counts[k] (host array) valid rows each */
+int hvb_adopt_device_padded(hvb_ctx* ctx, const void* sig_dev, const void* r_dev, int nseg, int64_t seg_cap, const int64_t* counts);
 
 /* rare_events / statistics.jl:132-143 analogue */
 int hvb_stats(hvb_ctx* ctx, hvb_stats_t* out);

@@ -116,7 +116,7 @@ def test_slab_union_equals_full(hvb, oracle):
         assert (np.diff(mesh.sig[:, 0]) >= 0).all()                      # each shard is sorted
         rows |= {tuple(r) for r in mesh.sig.tolist()}
         total += mesh.sig.shape[0]
-        assert s.stats()["raycasts"] < 0.6 * len(o["sig"])               # a rank walks its slab only
+        assert s.stats()["raycasts"] < 0.9 * len(o["sig"])               # a rank walks its slab (plus a halo) only
     assert rows == {tuple(r) for r in o["sig"].tolist()}
     assert total == len(o["sig"])                                        # ownership rule: the shards are disjoint
 
