@@ -223,16 +223,25 @@ class VoronoiMesh:
         return self.sig.shape[0]
 
 
-def voronoi(xs, searcher=None, Iter=None, copy=False, **_ignored):
-    """voronoi(xs; searcher=Raycast(xs), Iter=1:length(xs)) (sysvoronoi.jl:7-39) -> (mesh, searcher)."""
+def voronoi(xs, searcher=None, Iter=None, copy=False, known=None, **_ignored):
+    """voronoi(xs; searcher=Raycast(xs), Iter=1:length(xs)) (sysvoronoi.jl:7-39) -> (mesh, searcher).
+
+    known=(sig, r): vertices the mesh already holds (the reference passes a non-empty mesh in refinement,
+    meshrefine.jl:199-215): the walk continues from them and only NEW vertices are returned."""
     if searcher is None:
         searcher = Raycast(xs)
     L, ctx = _abi.lib(), searcher._ctx
-    if Iter is None:
-        rc = L.hvb_search(ctx, None, 0, None, None, 0, 0)
-    else:
+    cells_p, ncells = None, 0
+    if Iter is not None:
         cells = np.ascontiguousarray(np.asarray(list(Iter), dtype=np.int64))
-        rc = L.hvb_search(ctx, cells.ctypes.data_as(ctypes.c_void_p), cells.shape[0], None, None, 0, 0)
+        cells_p, ncells = cells.ctypes.data_as(ctypes.c_void_p), cells.shape[0]
+    if known is None:
+        rc = L.hvb_search(ctx, cells_p, ncells, None, None, 0, 0)
+    else:
+        ksig = np.ascontiguousarray(known[0], dtype=np.int64)
+        kr = np.ascontiguousarray(known[1], dtype=np.float64)
+        rc = L.hvb_search(ctx, cells_p, ncells, ksig.ctypes.data_as(ctypes.c_void_p), kr.ctypes.data_as(ctypes.c_void_p),
+                          ksig.shape[0], ksig.shape[1])
     _abi.check(rc, ctx)
     return VoronoiMesh(searcher, copy=copy), searcher
 

@@ -138,7 +138,10 @@ struct Ctx : hvb_ctx {
     DBuf<Scalars> sc;
     HBuf<Scalars> h_sc;
     HBuf<Counters> h_ctr;
-    DBuf<long long> cells_dev;
+    DBuf<long long> cells_dev, seed_sig_dev;
+    DBuf<double> seed_r_dev;
+    bool second_pass = false;         // the rows are filtered after the neighbour lists were built from all of them
+    u32 seed_prefix = 0;              // vertex records [0, seed_prefix) are the caller's own vertices (not returned)
     // results
     DBuf<long long> out_sig[2];
     DBuf<double> out_r[2];
@@ -168,7 +171,7 @@ struct Ctx : hvb_ctx {
         xs_in.release(); x64.release(); x32.release(); perm.release(); inv.release(); cell_of.release(); cell_start.release();
         cell_cur.release(); unseeded_list.release(); bbox_partial.release(); planes.release(); active.release(); has_vertex.release(); cub_tmp.release();
         vsig.release(); vr.release(); vtab.release(); etab.release(); q[0].release(); q[1].release(); ray_item.release(); ray_u.release();
-        ctr.release(); sc.release(); h_sc.release(); h_ctr.release(); cells_dev.release();
+        ctr.release(); sc.release(); h_sc.release(); h_ctr.release(); cells_dev.release(); seed_sig_dev.release(); seed_r_dev.release();
         out_sig[0].release(); out_sig[1].release(); out_r[0].release(); out_r[1].release(); key_hi.release(); key_lo.release(); key_tmp.release();
         idx[0].release(); idx[1].release(); ray_edge.release(); ray_node.release(); ray_base.release(); ray_dir.release();
         h_sig.release(); h_r.release(); h_nb_off.release(); h_nb_ids.release(); ptab.release(); deg.release(); ncur.release(); nb_off.release(); nb_ids.release();
@@ -374,8 +377,7 @@ struct Ctx : hvb_ctx {
     }
 
     int search(const int64_t* cells, int64_t ncells_in, const int64_t* seed_sig, const double* seed_r, int64_t nseed, int stride) override {
-        (void)seed_sig; (void)seed_r; (void)stride;
-        if (nseed > 0) { err = "pre-existing vertices (nseed > 0) are not supported yet"; return HVB_EINVAL; }
+        if (nseed < 0 || (nseed > 0 && (!seed_sig || !seed_r || stride < D + 1))) { err = "bad seed vertex arguments"; return HVB_EINVAL; }
         CK(cudaSetDevice(prm.device));
         have_result = false; staged = false; nb_total = -1;
         int64_t cap = prm.vertex_capacity > 0 ? prm.vertex_capacity : estimate_vertices(D, n, P);
@@ -412,6 +414,20 @@ struct Ctx : hvb_ctx {
             int cur = 0;
             if (persistent) CK(cudaMemsetAsync(q[0].p, 0xff, (size_t)qcap * sizeof(u64), stream));   // nothing published yet
             CK(cudaEventRecord(ev_s0, stream));
+            seed_prefix = 0;
+            if (nseed > 0) {
+                // the mesh already holds vertices: they become the first records; cells they do not reach are seeded by
+                // descents in the re-seed pass below (sysvoronoi.jl:394-429)
+                CK(seed_sig_dev.ensure((size_t)nseed * stride)); CK(seed_r_dev.ensure((size_t)nseed * D));
+                CK(cudaMemcpyAsync(seed_sig_dev.p, seed_sig, (size_t)nseed * stride * 8, cudaMemcpyHostToDevice, stream));
+                CK(cudaMemcpyAsync(seed_r_dev.p, seed_r, (size_t)nseed * D * 8, cudaMemcpyHostToDevice, stream));
+                k_insert_seeds<D><<<blocks_for(nseed, 128), 128, 0, stream>>>(dv, seed_sig_dev.p, seed_r_dev.p, nseed, stride, inv.p,
+                                                                             q[cur].p, &sc.p->rnd[cur].qcount, qcap, &sc.p->pflags + 0);
+                ++launches;
+                int rcs = read_scalars(); if (rcs) return rcs;
+                if (h_sc.p->pflags) { err = "seed vertices must be general vertices (dim+1 distinct, valid ids)"; return HVB_EINVAL; }
+                seed_prefix = h_sc.p->vcount;
+            } else
             launch_seed(nullptr, nseeds, sstride, cur);
             CK(cudaEventRecord(ev_s1, stream));
             if (debug) fprintf(stderr, "[hvb] seeds=%d stride=%d G=%d vcap=%lld ncells=%lld\n", nseeds, sstride, G, (long long)vcap, (long long)ncells);
@@ -493,14 +509,19 @@ struct Ctx : hvb_ctx {
             cap = vcap * 2;
         }
         CK(cudaEventRecord(ev_b, stream));
+        const bool by_slab = world > 1 && cells == nullptr;
+        second_pass = by_slab || seed_prefix > 0;
         int rc = finalize(); if (rc) return rc;
         CK(cudaEventRecord(ev_c, stream));
-        // a slab result is an intermediate: it is exported to the exchange step, not staged for the host
-        if (world == 1) { rc = stage(); if (rc) return rc; }
+        // a slab result is an intermediate: it is exported to the exchange step, not staged for the host; with seed
+        // vertices the rows are staged after the filtering pass
+        if (world == 1 && !second_pass) { rc = stage(); if (rc) return rc; }
         have_result = true;
         CK(cudaEventRecord(ev_n0, stream));
-        if (prm.neighbors) { rc = build_neighbors(); if (rc) return rc; rc = stage_neighbors(); if (rc) return rc; }
-        if (world > 1 && cells == nullptr) { rc = finalize_owned(); if (rc) return rc; }
+        // with seed vertices the lists must be built now, from all rows, before the caller's own vertices are dropped
+        if (prm.neighbors || seed_prefix > 0) { rc = build_neighbors(); if (rc) return rc; }
+        if (prm.neighbors) { rc = stage_neighbors(); if (rc) return rc; }
+        if (second_pass) { rc = finalize_owned(by_slab); if (rc) return rc; if (world == 1) { rc = stage(); if (rc) return rc; } }
         CK(cudaEventRecord(ev_n1, stream));
         CK(cudaStreamWaitEvent(stream, ev_stage_done(), 0));
         CK(cudaEventRecord(ev_d, stream));
@@ -563,7 +584,7 @@ struct Ctx : hvb_ctx {
         int bits = id_bits();
         if (nrec > 0) {
             k_final_rows<D><<<blocks_for(nrec, 128), 128, 0, stream>>>(dv, perm.p, nrec, bits, out_sig[0].p, out_r[0].p, key_hi.p, key_lo.p,
-                                                                     &sc.p->out_count, &sc.p->max_var, 0, 0);
+                                                                     &sc.p->out_count, &sc.p->max_var, 0, 0, 0u);
             ++launches;
         }
         if (nrays > 0) {
@@ -573,20 +594,20 @@ struct Ctx : hvb_ctx {
         }
         int rc = read_scalars(); if (rc) return rc;
         nvert = h_sc.p->out_count;
-        if (std::max(1, prm.world) > 1) { res = 0; return HVB_OK; }     // slab rows are sorted after the merge
+        if (second_pass) { res = 0; return HVB_OK; }     // a filtering pass follows (slab ownership / seed vertices): it sorts
         return sort_rows((u32)nvert, bits);
     }
 
     // multi-GPU: keep only the vertices this rank owns (after the neighbour lists were built from ALL local rows)
-    int finalize_owned() {
+    int finalize_owned(bool by_slab) {
         const int world = std::max(1, prm.world), rank = std::min(std::max(0, prm.rank), world - 1);
         u32 nrec = std::min<u32>(h_sc.p->vcount, (u32)vcap);
-        int lo = (int)(n * rank / world), hi = (int)(n * (rank + 1) / world);
+        int lo = by_slab ? (int)(n * rank / world) : 0, hi = by_slab ? (int)(n * (rank + 1) / world) : 0;
         int bits = id_bits();
         CK(cudaMemsetAsync(&sc.p->out_count, 0, sizeof(u32), stream));
         if (nrec > 0) {
             k_final_rows<D><<<blocks_for(nrec, 128), 128, 0, stream>>>(dv, perm.p, nrec, bits, out_sig[0].p, out_r[0].p, key_hi.p, key_lo.p,
-                                                                     &sc.p->out_count, &sc.p->max_var, lo, hi);
+                                                                     &sc.p->out_count, &sc.p->max_var, lo, hi, seed_prefix);
             ++launches;
         }
         int rc = read_scalars(); if (rc) return rc;

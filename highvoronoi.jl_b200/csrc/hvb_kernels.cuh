@@ -184,6 +184,39 @@ __global__ void __launch_bounds__(128) k_seed(Dev<D> dv, const int* __restrict__
 // resident blocks per SM the walk kernel is compiled for: 4 (<= 128 registers per thread) measured best for d = 2..5
 // although the higher dimensions spill: occupancy matters more to this latency-bound kernel
 // (profiles/r1_tile_occupancy_sweep.md)
+// Vertices the caller's mesh already holds (refinement callers, meshrefine.jl:199-215): converted to internal
+// numbering, stored and registered like found vertices, so that the walk continues from them and never returns them.
+template <int D>
+__global__ void k_insert_seeds(Dev<D> dv, const long long* __restrict__ sig_in, const double* __restrict__ r_in, long long nseed,
+                               int stride, const int* __restrict__ inv, u64* q_out, u32* q_count, u32 q_cap, u32* bad) {
+    long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (i >= nseed) return;
+    LocalStats ls = {};
+    TileDev<1> tile;
+    int sig[D + 1];
+    int cnt = 0;
+    bool ok = true;
+    for (int k = 0; k < stride; ++k) {
+        long long g = sig_in[i * stride + k];
+        if (g == 0) continue;                                  // unused entry
+        if (cnt == D + 1) { ok = false; break; }
+        int id;
+        if (g >= 1 && g <= dv.n) id = inv[g - 1];
+        else if (g > dv.n && g <= dv.n + dv.planes->P) id = (int)(g - 1);
+        else { ok = false; break; }
+        int j = cnt++;
+        while (j > 0 && sig[j - 1] > id) { sig[j] = sig[j - 1]; --j; }
+        sig[j] = id;
+    }
+    if (!ok || cnt != D + 1) { atomicAdd(bad, 1u); return; }   // only general vertices (dim+1 generators) are accepted
+    for (int k = 0; k < D; ++k) ok &= (sig[k] != sig[k + 1]);
+    if (!ok || sig[0] >= dv.n) { atomicAdd(bad, 1u); return; }
+    double r[D];
+#pragma unroll
+    for (int k = 0; k < D; ++k) r[k] = r_in[i * D + k];
+    commit_vertex<D, TileDev<1> >(dv, tile, sig, r, q_out, q_count, q_cap, ls);
+}
+
 #ifndef HVB_EXPAND_MINB
 #define HVB_EXPAND_MINB 4
 #endif
@@ -308,9 +341,9 @@ template <int D>
 __global__ void k_final_rows(Dev<D> dv, const int* __restrict__ perm, u32 nrec, int bits,
                              long long* __restrict__ out_sig, double* __restrict__ out_r,
                              u64* __restrict__ key_hi, u64* __restrict__ key_lo, u32* __restrict__ out_count,
-                             double* __restrict__ max_var, int own_lo, int own_hi) {
+                             double* __restrict__ max_var, int own_lo, int own_hi, u32 skip_below) {
     u32 v = blockIdx.x * blockDim.x + threadIdx.x;
-    if (v >= nrec) return;
+    if (v >= nrec || v < skip_below) return;          // records below skip_below are the caller's own (seed) vertices
     const int* s = dv.vsig + (size_t)v * (D + 1);
     if (s[0] < 0) return;
     // multi-GPU ownership rule: a vertex belongs to the slab that holds its first generator in grid order (s is

@@ -109,8 +109,10 @@ int hvb_set_points(hvb_ctx* ctx, int64_t n, const double* xs);
 
 /* Replaces voronoi(mesh; Iter, searcher) (src/sysvoronoi.jl:21 -> _voronoi :41/:50 -> __voronoi :152):
  * cells = Iter (1-based, NULL = all cells); seed_sig/seed_r = vertices the mesh already holds
- * (nseed rows of sig_stride ids, unused entries 0; the refinement callers meshrefine.jl:199-215 pass a
- * non-empty mesh).  Blocks until the results are complete on the device. */
+ * (nseed rows of sig_stride >= dim+1 ids, 1-based, unused entries 0; the refinement callers
+ * meshrefine.jl:199-215 pass a non-empty mesh).  Seed vertices must be general (dim+1 generators); the walk
+ * continues from them, only NEW vertices are returned by the fetch calls, the neighbour lists cover both.
+ * Blocks until the results are complete on the device. */
 int hvb_search(hvb_ctx* ctx, const int64_t* cells, int64_t ncells,
                const int64_t* seed_sig, const double* seed_r, int64_t nseed, int sig_stride);
 

@@ -156,6 +156,33 @@ def test_context_reuse_set_points(hvb, oracle):
         assert np.array_equal(off, o["nb_off"]) and np.array_equal(ids, o["nb_ids"])
 
 
+@pytest.mark.parametrize("d,n", [(3, 4000), (2, 6000), (4, 800)])
+def test_known_vertices_are_continued_not_returned(hvb, oracle, d, n):
+    """hvb_search with seed vertices (a mesh that already holds vertices, meshrefine.jl:199-215): the walk continues
+    from them, returns exactly the missing ones, and the neighbour lists cover old and new vertices"""
+    xs = points(n, d, 40 + d)
+    base, normal = qhull_oracle.cuboid(d)
+    o = oracle.run(xs, base, normal)
+    rng = np.random.default_rng(1)
+    keep = rng.random(len(o["sig"])) < 0.4
+    keep[(o["sig"] <= n // 3).any(axis=1)] = True            # a whole region is already meshed
+    s = hvb.Raycast(xs, domain=hvb.cuboid(d, periodic=[]))
+    mesh, _ = hvb.voronoi(xs, searcher=s, known=(o["sig"][keep], o["r"][keep]))
+    assert np.array_equal(mesh.sig, o["sig"][~keep])
+    assert_same_mesh(mesh.sig, mesh.r, o["sig"][~keep], o["r"][~keep], xs, COORD_TOL)
+    off, ids = mesh.neighbors()
+    assert np.array_equal(off, o["nb_off"]) and np.array_equal(ids, o["nb_ids"])
+    # unused trailing entries (0) and a wider stride are accepted, malformed rows are refused
+    wide = np.zeros((int(keep.sum()), d + 3), dtype=np.int64)
+    wide[:, :d + 1] = o["sig"][keep]
+    mesh2, _ = hvb.voronoi(xs, searcher=s, known=(wide, o["r"][keep]))
+    assert np.array_equal(mesh2.sig, o["sig"][~keep])
+    bad = o["sig"][keep].copy()
+    bad[0, 1] = bad[0, 0]
+    with pytest.raises(hvb.HVBError):
+        hvb.voronoi(xs, searcher=s, known=(bad, o["r"][keep]))
+
+
 def test_points_outside_domain_are_rejected(hvb):
     xs = points(100, 3, 0)
     xs[5, 1] = 1.5
