@@ -580,7 +580,10 @@ HVB_HD void scan_points(const Dev<D>& dv, const RayQ<D>& q, const float (&uf)[D]
         for (int p = pa; p < pb; ++p) verify64<D>(dv, q, p, best, ls);
         return;
     }
-    const int U = 4;
+#ifndef HVB_SCAN_U
+#define HVB_SCAN_U 4
+#endif
+    const int U = HVB_SCAN_U;
     for (int p = pa; p < pb; p += U) {
         float x[U][D];
 #pragma unroll
@@ -606,12 +609,16 @@ HVB_HD void scan_points(const Dev<D>& dv, const RayQ<D>& q, const float (&uf)[D]
 #pragma unroll
         for (int i = 0; i < U; ++i) pmask |= pass[i] ? (1u << i) : 0u;
         while (pmask) {
-            const int i = (pmask & 1u) ? 0 : (pmask & 2u) ? 1 : (pmask & 4u) ? 2 : 3;
+            int i = 0;
+#pragma unroll
+            for (int b = U - 1; b >= 0; --b) i = ((pmask >> b) & 1u) ? b : i;       // lowest set bit
             pmask &= pmask - 1u;
-            const float nlo_i = (i == 0) ? nlo[0] : (i == 1) ? nlo[1] : (i == 2) ? nlo[2] : nlo[3];
-            const float nhi_i = (i == 0) ? nhi[0] : (i == 1) ? nhi[1] : (i == 2) ? nhi[2] : nhi[3];
-            const float dh_i = (i == 0) ? dh[0] : (i == 1) ? dh[1] : (i == 2) ? dh[2] : dh[3];
-            const float dl_i = (i == 0) ? dl[0] : (i == 1) ? dl[1] : (i == 2) ? dl[2] : dl[3];
+            float nlo_i = nlo[0], nhi_i = nhi[0], dh_i = dh[0], dl_i = dl[0];
+#pragma unroll
+            for (int b = 1; b < U; ++b) {
+                nlo_i = (i == b) ? nlo[b] : nlo_i; nhi_i = (i == b) ? nhi[b] : nhi_i;
+                dh_i = (i == b) ? dh[b] : dh_i; dl_i = (i == b) ? dl[b] : dl_i;
+            }
             if (!(nlo_i <= flt.tb2 * dh_i)) continue;                    // re-checked: the bound may have tightened within the chunk
             const int id = p + i;
             bool excluded = false;
