@@ -12,7 +12,7 @@ ERROR_NAMES = {-1: "HVB_EINVAL", -2: "HVB_ECUDA", -3: "HVB_ENOGPU", -4: "HVB_ENO
 
 EXPORTS = ("hvb_default_params", "hvb_create", "hvb_set_points", "hvb_search", "hvb_counts", "hvb_fetch_vertices", "hvb_fetch_vertices_range", "hvb_fetch_rays",
            "hvb_neighbor_count", "hvb_fetch_neighbors", "hvb_view_vertices", "hvb_view_neighbors", "hvb_export_device", "hvb_merge_device", "hvb_adopt_device", "hvb_adopt_device_padded",
-           "hvb_stats", "hvb_last_error", "hvb_destroy", "hvb_version")
+           "hvb_stats", "hvb_last_error", "hvb_destroy", "hvb_version", "hvb_create_periodic", "hvb_halo_count", "hvb_fetch_halo", "hvb_fetch_vertex_flags")
 
 
 class hvb_params(ctypes.Structure):
@@ -21,7 +21,7 @@ class hvb_params(ctypes.Structure):
                 ("method", ctypes.c_int32), ("device", ctypes.c_int32), ("rank", ctypes.c_int32), ("world", ctypes.c_int32),
                 ("fp32_filter", ctypes.c_int32), ("on_degenerate", ctypes.c_int32), ("points_per_cell", ctypes.c_int32),
                 ("seed_stride", ctypes.c_int32), ("sort_output", ctypes.c_int32), ("tile_size", ctypes.c_int32), ("neighbors", ctypes.c_int32), ("persistent", ctypes.c_int32),
-                ("vertex_capacity", ctypes.c_int64), ("probe_scale", ctypes.c_double)]
+                ("vertex_capacity", ctypes.c_int64), ("probe_scale", ctypes.c_double), ("periodic_margin", ctypes.c_double)]
 
 
 class hvb_stats_t(ctypes.Structure):
@@ -30,7 +30,8 @@ class hvb_stats_t(ctypes.Structure):
                  "rows_scanned", "probe_stages", "rounds", "seeds", "degenerate", "kernel_launches", "capacity_retries")] + \
                [(k, ctypes.c_double) for k in ("ms_build", "ms_search", "ms_finalize", "ms_expand_kernel")] + \
                [("expand_launches", ctypes.c_int64), ("expand_items", ctypes.c_int64)] + \
-               [(k, ctypes.c_double) for k in ("ms_seed", "ms_neighbors", "ms_rows_sort")]
+               [(k, ctypes.c_double) for k in ("ms_seed", "ms_neighbors", "ms_rows_sort")] + \
+               [(k, ctypes.c_int64) for k in ("halo_nodes", "unique_vertices", "periodic_retries")]
 
     def as_dict(self):
         return {k: getattr(self, k) for k, _ in self._fields_}
@@ -56,6 +57,10 @@ def lib():
         L.hvb_default_params.argtypes = [ctypes.POINTER(hvb_params)]
         L.hvb_default_params.restype = None
         L.hvb_create.argtypes = [ctypes.POINTER(vp), i32, i64, vp, i32, vp, vp, ctypes.POINTER(hvb_params)]
+        L.hvb_create_periodic.argtypes = [ctypes.POINTER(vp), i32, i64, vp, i32, vp, vp, vp, ctypes.POINTER(hvb_params)]
+        L.hvb_halo_count.argtypes = [vp, ctypes.POINTER(i64), ctypes.POINTER(ctypes.c_int32), ctypes.POINTER(ctypes.c_double)]
+        L.hvb_fetch_halo.argtypes = [vp, vp, vp, vp]
+        L.hvb_fetch_vertex_flags.argtypes = [vp, vp]
         L.hvb_set_points.argtypes = [vp, i64, vp]
         L.hvb_search.argtypes = [vp, vp, i64, vp, vp, i64, i32]
         L.hvb_counts.argtypes = [vp, ctypes.POINTER(i64), ctypes.POINTER(i64), ctypes.POINTER(i64)]
@@ -76,7 +81,7 @@ def lib():
         L.hvb_destroy.argtypes = [vp]
         L.hvb_destroy.restype = None
         L.hvb_version.restype = ctypes.c_char_p
-        for name in ("hvb_create", "hvb_set_points", "hvb_search", "hvb_counts", "hvb_fetch_vertices", "hvb_fetch_vertices_range", "hvb_fetch_rays", "hvb_neighbor_count",
+        for name in ("hvb_create", "hvb_create_periodic", "hvb_halo_count", "hvb_fetch_halo", "hvb_fetch_vertex_flags", "hvb_set_points", "hvb_search", "hvb_counts", "hvb_fetch_vertices", "hvb_fetch_vertices_range", "hvb_fetch_rays", "hvb_neighbor_count",
                      "hvb_fetch_neighbors", "hvb_view_vertices", "hvb_view_neighbors", "hvb_export_device", "hvb_merge_device", "hvb_adopt_device", "hvb_adopt_device_padded", "hvb_stats"):
             getattr(L, name).restype = i32
         _lib = L

@@ -36,6 +36,15 @@ class Boundary:
     def __len__(self):
         return self.base.shape[0]
 
+    def plane_bc(self):
+        """Plane.BC per plane (boundary.jl:15-29): 1-based partner index for periodic planes, 0 otherwise.  `periodic`
+        lists 1-based axes of a cuboid: plane 2i-1 and plane 2i are partners (boundary.jl:517-519)."""
+        bc = np.zeros(len(self), dtype=np.int32)
+        for i in self.periodic:
+            bc[2 * i - 2] = 2 * i
+            bc[2 * i - 1] = 2 * i - 1
+        return bc
+
 
 def cuboid(dim, dimensions=None, periodic=None, neumann=(), offset=None):
     """cuboid(dim; dimensions, periodic, neumann, offset) (boundary.jl:510-534).  Plane 2i-1 is the upper face of
@@ -95,7 +104,10 @@ class Raycast:
     """Raycast(xs; domain=Boundary(), options=RaycastParameter()) (raycast.jl:26): owns the device context
     (generators + spatial index)."""
 
-    def __init__(self, xs, domain=None, options=None):
+    def __init__(self, xs, domain=None, options=None, periodic=False):
+        """periodic=True: the periodic planes of `domain` are honoured by the backend (halo generators + certificate,
+        hvb_create_periodic) -- what VoronoiGeometry does for such a domain.  The default treats every plane as a
+        mirror, like the reference's own voronoi() call (geometry.jl:156)."""
         self.xs = VoronoiNodes(xs) if not (isinstance(xs, np.ndarray) and xs.flags.c_contiguous and xs.dtype == np.float64 and xs.ndim == 2 and xs.shape[0] > xs.shape[1]) else xs
         self.domain = domain if domain is not None else Boundary()
         self.parameters = options if options is not None else RaycastParameter()
@@ -106,11 +118,31 @@ class Raycast:
         P = len(self.domain)
         base = self.domain.base.ctypes.data_as(ctypes.c_void_p) if P else None
         normal = self.domain.normal.ctypes.data_as(ctypes.c_void_p) if P else None
-        rc = L.hvb_create(ctypes.byref(self._ctx), d, n, self.xs.ctypes.data_as(ctypes.c_void_p), P, base, normal,
-                          ctypes.byref(self.parameters))
+        self.periodic = bool(periodic) and len(self.domain.periodic) > 0
+        if self.periodic:
+            self._bc = self.domain.plane_bc()
+            rc = L.hvb_create_periodic(ctypes.byref(self._ctx), d, n, self.xs.ctypes.data_as(ctypes.c_void_p), P, base, normal,
+                                       self._bc.ctypes.data_as(ctypes.c_void_p), ctypes.byref(self.parameters))
+        else:
+            rc = L.hvb_create(ctypes.byref(self._ctx), d, n, self.xs.ctypes.data_as(ctypes.c_void_p), P, base, normal,
+                              ctypes.byref(self.parameters))
         if rc != _abi.HVB_OK:
             self._ctx = None
             _abi.check(rc, None)
+
+    def halo(self):
+        """(origin, mult, xs, margin) of a periodic searcher: halo generator n+1+i copies caller generator origin[i]
+        shifted by sum_k mult[i,k] periods of periodic pair k (references / reference_shifts, domain.jl:338-390)."""
+        L, ctx = _abi.lib(), self._ctx
+        nh, npairs, margin = ctypes.c_int64(), ctypes.c_int32(), ctypes.c_double()
+        _abi.check(L.hvb_halo_count(ctx, ctypes.byref(nh), ctypes.byref(npairs), ctypes.byref(margin)), ctx)
+        origin = np.empty((nh.value,), dtype=np.int64)
+        mult = np.empty((nh.value, max(npairs.value, 0)), dtype=np.int32)
+        xs = np.empty((nh.value, self.dim), dtype=np.float64)
+        if nh.value:
+            P = lambda a: a.ctypes.data_as(ctypes.c_void_p)
+            _abi.check(L.hvb_fetch_halo(ctx, P(origin), P(mult), P(xs)), ctx)
+        return origin, mult, xs, margin.value
 
     def set_points(self, xs):
         """re-target this searcher to another generator set (same dimension and domain), re-using the device context"""
@@ -184,6 +216,29 @@ class VoronoiMesh:
             _abi.check(L.hvb_fetch_rays(ctx, P(self.ray_edge), P(self.ray_base), P(self.ray_dir), P(self.ray_node)), ctx)
         self._nb = None
         self._cell_index = None
+        self.n_halo = 0
+        if getattr(searcher, "periodic", False):
+            # extended numbering: caller generators 1..n, halo n+1..n+n_halo, planes behind
+            self.halo_origin, self.halo_mult, self.halo_xs, self.margin = searcher.halo()
+            self.n_halo = self.halo_origin.shape[0]
+            self.n_user = self.n
+            self.n = self.n + self.n_halo
+            self.canonical = np.empty((nv.value,), dtype=np.uint8)
+            if nv.value:
+                _abi.check(L.hvb_fetch_vertex_flags(ctx, self.canonical.ctypes.data_as(ctypes.c_void_p)), ctx)
+            self.canonical = self.canonical.astype(bool)
+
+    def origin_of(self, ids):
+        """folds extended ids back to caller ids (halo -> the generator it copies; planes -> n_user + p)"""
+        ids = np.asarray(ids)
+        if not self.n_halo:
+            return ids
+        out = ids.copy()
+        h = (ids > self.n_user) & (ids <= self.n)
+        out[h] = self.halo_origin[ids[h] - self.n_user - 1]
+        pl = ids > self.n
+        out[pl] = ids[pl] - self.n_halo
+        return out
 
     def neighbors(self):
         """CSR (offsets[n+1], ids) of neighbors_of_cell for every cell (neighbors.jl:214-262)."""
@@ -254,7 +309,8 @@ class VoronoiGeometry:
         xs = VoronoiNodes(xs)
         b = b if b is not None else Boundary()
         opts = RaycastParameter(**(search_settings or {}))
-        self.searcher = Raycast(xs, domain=b, options=opts)
+        # a domain with periodic planes is periodised by the backend (the reference: Create_Discrete_Domain, domain.jl:175)
+        self.searcher = Raycast(xs, domain=b, options=opts, periodic=len(b.periodic) > 0)
         self.mesh, _ = voronoi(xs, searcher=self.searcher)
         self.nodes = xs
         self.domain = b
@@ -267,7 +323,9 @@ class VoronoiData:
         self.nodes = VG.nodes
         m = VG.mesh
         if getvertices:
-            self.vertices = [list(m.vertices_iterator(i)) for i in range(1, m.n + 1)]
+            self.vertices = [list(m.vertices_iterator(i)) for i in range(1, getattr(m, "n_user", m.n) + 1)]
+        nu = getattr(m, "n_user", m.n)
         if getneighbors:
             off, ids = m.neighbors()
-            self.neighbors = [ids[off[i]:off[i + 1]] for i in range(m.n)]
+            # periodic domains: neighbours folded back to the caller's ids (reduce_to_periodic, voronoidata.jl:623)
+            self.neighbors = [np.unique(m.origin_of(ids[off[i]:off[i + 1]])) for i in range(nu)]

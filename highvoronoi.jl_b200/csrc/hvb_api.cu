@@ -49,6 +49,20 @@ struct DBuf {
         if (e == cudaSuccess) cap = want;
         return e;
     }
+    // grows to n elements and keeps the first `keep` elements (device-to-device copy on `st`)
+    cudaError_t grow_keep(size_t n, size_t keep, cudaStream_t st) {
+        if (n <= cap) return cudaSuccess;
+        T* np_ = nullptr;
+        size_t want = std::max<size_t>(n + n / 4, 1);
+        cudaError_t e = cudaMalloc((void**)&np_, want * sizeof(T));
+        if (e != cudaSuccess) { want = std::max<size_t>(n, 1); e = cudaMalloc((void**)&np_, want * sizeof(T)); }
+        if (e != cudaSuccess) return e;
+        if (p && keep) e = cudaMemcpyAsync(np_, p, keep * sizeof(T), cudaMemcpyDeviceToDevice, st);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+        if (p) cudaFree(p);
+        p = np_; cap = want;
+        return e;
+    }
     void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
 };
 template <class T>
@@ -89,7 +103,10 @@ struct hvb_ctx {
     std::string err;
     hvb_stats_t st;
     virtual ~hvb_ctx() {}
-    virtual int init(const double* xs, const double* pbase, const double* pnormal) = 0;
+    virtual int init(const double* xs, const double* pbase, const double* pnormal, const int32_t* plane_bc) = 0;
+    virtual int halo_count(int64_t* nhalo, int32_t* npairs, double* margin) = 0;
+    virtual int fetch_halo(int64_t* origin, int32_t* mult, double* xs) = 0;
+    virtual int fetch_vertex_flags(uint8_t* flags) = 0;
     virtual int set_points(int64_t n, const double* xs) = 0;
     virtual int search(const int64_t* cells, int64_t ncells, const int64_t* seed_sig, const double* seed_r, int64_t nseed, int stride) = 0;
     virtual int counts(int64_t* nv, int64_t* nr, int64_t* msl) = 0;
@@ -186,16 +203,34 @@ struct Ctx : hvb_ctx {
         if (ev_n0) cudaEventDestroy(ev_n0);
         if (ev_n1) cudaEventDestroy(ev_n1);
         if (ev_stage) cudaEventDestroy(ev_stage);
+        if (ev_p0) cudaEventDestroy(ev_p0);
+        if (ev_p1) cudaEventDestroy(ev_p1);
+        halo_cnt.release(); halo_off.release(); halo_origin.release(); halo_mult.release(); vflags.release(); cert.release(); h_cert.release();
         if (sstream) { cudaStreamSynchronize(sstream); cudaStreamDestroy(sstream); }
         if (stream) cudaStreamDestroy(stream);
     }
 
     static int blocks_for(int64_t items, int per_block) { return (int)std::max<int64_t>(1, (items + per_block - 1) / per_block); }
 
-    PlaneSet ps_host;
+    PlaneSet ps_host;                 // the planes on the device (periodic planes pushed outwards by `margin`)
+    PlaneSet ps_orig;                 // the caller's planes
     bool setup_done = false;
+    // periodic domains: caller generators [0, n_user) + halo copies [n_user, n)
+    bool periodic = false;
+    int64_t n_user = 0, n_halo = 0;
+    double margin = 0;
+    HaloSpec halo;
+    PeriodicCert pcert;
+    double pair_width[HVB_MAX_PAIRS];
+    DBuf<int> halo_cnt, halo_off, halo_origin;
+    DBuf<signed char> halo_mult;
+    DBuf<unsigned char> vflags;
+    DBuf<CertOut> cert;
+    HBuf<CertOut> h_cert;
+    bool have_flags = false;
+    cudaEvent_t ev_p0 = nullptr, ev_p1 = nullptr;
 
-    int init(const double* xs, const double* pbase, const double* pnormal) override {
+    int init(const double* xs, const double* pbase, const double* pnormal, const int32_t* plane_bc) override {
         memset(&dv, 0, sizeof(dv));
         memset(&st, 0, sizeof(st));
         CK(cudaSetDevice(prm.device));
@@ -205,6 +240,7 @@ struct Ctx : hvb_ctx {
         CK(cudaEventCreateWithFlags(&ev_stage, cudaEventDisableTiming));
         CK(cudaEventCreate(&ev_a)); CK(cudaEventCreate(&ev_b)); CK(cudaEventCreate(&ev_c)); CK(cudaEventCreate(&ev_d));
         CK(cudaEventCreate(&ev_s0)); CK(cudaEventCreate(&ev_s1)); CK(cudaEventCreate(&ev_n0)); CK(cudaEventCreate(&ev_n1));
+        CK(cudaEventCreate(&ev_p0)); CK(cudaEventCreate(&ev_p1));
         // planes: unit outward normals, offsets
         memset(&ps_host, 0, sizeof(ps_host));
         ps_host.P = P;
@@ -217,8 +253,37 @@ struct Ctx : hvb_ctx {
             for (int k = 0; k < D; ++k) { ps_host.normal[p * 6 + k] = pnormal[p * D + k] / nr; off += ps_host.normal[p * 6 + k] * pbase[p * D + k]; }
             ps_host.off[p] = off;
         }
+        ps_orig = ps_host;
+        // periodic plane pairs (Plane.BC > 0 names the partner plane, boundary.jl:15-29; cuboid boundary.jl:510-534)
+        memset(&halo, 0, sizeof(halo));
+        memset(&pcert, 0, sizeof(pcert));
+        pcert.nplanes = P;
+        for (int p = 0; p < P; ++p) pcert.off_orig[p] = ps_orig.off[p];
+        periodic = false;
+        if (plane_bc) {
+            for (int p = 0; p < P; ++p) {
+                int q = plane_bc[p] - 1;
+                if (plane_bc[p] <= 0) continue;
+                if (q >= P || q == p || plane_bc[q] - 1 != p) { err = "periodic planes must name each other as partners"; return HVB_EINVAL; }
+                double dotn = 0;
+                for (int k = 0; k < D; ++k) dotn += ps_orig.normal[p * 6 + k] * ps_orig.normal[q * 6 + k];
+                if (!(dotn < -1.0 + 1e-9)) { err = "periodic partner planes must be parallel with opposite normals"; return HVB_EINVAL; }
+                pcert.is_periodic[p] = 1;
+                if (q < p) continue;                      // the pair is recorded once, at its lower plane index
+                if (halo.npairs == HVB_MAX_PAIRS) { err = "too many periodic plane pairs"; return HVB_EINVAL; }
+                const int i = halo.npairs++;
+                halo.plane_a[i] = p; halo.plane_b[i] = q;
+                const double width = ps_orig.off[p] + ps_orig.off[q];
+                if (!(width > 0)) { err = "periodic planes enclose an empty slab"; return HVB_EINVAL; }
+                pair_width[i] = width;
+                for (int k = 0; k < D; ++k) halo.T[i][k] = ps_orig.normal[p * 6 + k] * width;
+            }
+            periodic = halo.npairs > 0;
+        }
+        if (periodic && std::max(1, prm.world) > 1) { err = "periodic domains are not sharded across GPUs yet (world must be 1)"; return HVB_EINVAL; }
         CK(planes.ensure(1)); CK(ctr.ensure(1)); CK(sc.ensure(1)); CK(h_sc.ensure(1)); CK(h_ctr.ensure(1));
-        CK(cudaMemcpyAsync(planes.p, &ps_host, sizeof(ps_host), cudaMemcpyHostToDevice, stream));
+        CK(cert.ensure(1)); CK(h_cert.ensure(1));
+        CK(cudaMemcpyAsync(planes.p, &ps_orig, sizeof(ps_orig), cudaMemcpyHostToDevice, stream));
         dv.plane_tol = prm.plane_tolerance;
         dv.probe_scale = prm.probe_scale > 1.0 ? prm.probe_scale : default_probe_scale(D);
         dv.fp32_filter = prm.fp32_filter;
@@ -229,45 +294,109 @@ struct Ctx : hvb_ctx {
         return set_points(n, xs);
     }
 
-    // (re)loads the generators and rebuilds the spatial index; every buffer is reused when it is large enough
-    int set_points(int64_t n_new, const double* xs) override {
-        if (!setup_done) { err = "context not initialised"; return HVB_ESTATE; }
-        if (n_new <= D || !xs) { err = "There are not enough points to create a Voronoi tessellation"; return HVB_EINVAL; }
-        CK(cudaSetDevice(prm.device));
-        have_result = false; staged = false; nb_total = -1;
-        n = n_new;
-        CK(cudaEventRecord(ev_a, stream));
-        dv.n = (int)n;
-        // upload, then bounding box + domain check on the device (check_boundary, boundary.jl:437)
-        CK(xs_in.ensure((size_t)n * D));
-        CK(cudaMemcpyAsync(xs_in.p, xs, (size_t)n * D * sizeof(double), cudaMemcpyHostToDevice, stream));
-        const int bb_blocks = std::min(blocks_for(n, 256), sms);
+    // bounding box + domain check (check_boundary, boundary.jl:437) of `cnt` points against the planes on the device;
+    // the box lands in h_sc.p->bbox.  `host_xs` (may be null) is only used to word the error message.
+    int check_points(const double* dev_xs, int64_t cnt, const double* host_xs) {
+        const int bb_blocks = std::min(blocks_for(cnt, 256), sms);
         CK(bbox_partial.ensure((size_t)bb_blocks * 2 * D));
         CK(cudaMemsetAsync(&sc.p->bbox_done, 0, sizeof(u32), stream));
         CK(cudaMemsetAsync(&sc.p->bbox_viol, 0xff, sizeof(u32), stream));
-        k_bbox_check<D><<<bb_blocks, 256, 0, stream>>>(xs_in.p, (int)n, planes.p, bbox_partial.p, &sc.p->bbox_done, sc.p->bbox, &sc.p->bbox_viol);
+        k_bbox_check<D><<<bb_blocks, 256, 0, stream>>>(dev_xs, (int)cnt, planes.p, bbox_partial.p, &sc.p->bbox_done, sc.p->bbox, &sc.p->bbox_viol);
         ++launches;
         CK(cudaMemcpyAsync(h_sc.p, sc.p, sizeof(Scalars), cudaMemcpyDeviceToHost, stream));
         CK(cudaStreamSynchronize(stream));
         CK(cudaGetLastError());
         if (h_sc.p->bbox_viol != 0xffffffffu) {
-            const double* x = xs + (size_t)h_sc.p->bbox_viol * D;
+            char b[200];
+            if (!host_xs) { snprintf(b, sizeof(b), "internal error: halo generator %u outside the pushed planes", h_sc.p->bbox_viol + 1); err = b; return HVB_ECUDA; }
+            const double* x = host_xs + (size_t)h_sc.p->bbox_viol * D;
             bool finite = true;
             for (int k = 0; k < D; ++k) finite &= (x[k] == x[k]) && fabs(x[k]) <= 1e150;
-            char b[200];
             if (!finite) snprintf(b, sizeof(b), "non-finite coordinate in generator %u", h_sc.p->bbox_viol + 1);
             else {
                 int pbad = 0;
                 for (int p = 0; p < P; ++p) {
                     double sdot = 0;
-                    for (int k = 0; k < D; ++k) sdot += ps_host.normal[p * 6 + k] * x[k];
-                    if (sdot > ps_host.off[p]) { pbad = p + 1; break; }
+                    for (int k = 0; k < D; ++k) sdot += ps_orig.normal[p * 6 + k] * x[k];
+                    if (sdot > ps_orig.off[p]) { pbad = p + 1; break; }
                 }
                 snprintf(b, sizeof(b), "generator %u does not lie in the domain (plane %d)", h_sc.p->bbox_viol + 1, pbad);
             }
             err = b;
             return HVB_EINVAL;
         }
+        return HVB_OK;
+    }
+
+    // (re)loads the generators and rebuilds the spatial index; every buffer is reused when it is large enough
+    int set_points(int64_t n_new, const double* xs) override {
+        if (!setup_done) { err = "context not initialised"; return HVB_ESTATE; }
+        if (n_new <= D || !xs) { err = "There are not enough points to create a Voronoi tessellation"; return HVB_EINVAL; }
+        CK(cudaSetDevice(prm.device));
+        have_result = false; staged = false; nb_total = -1; have_flags = false;
+        n_user = n_new; n = n_new; n_halo = 0;
+        CK(cudaEventRecord(ev_a, stream));
+        // upload, then bounding box + domain check on the device against the caller's planes
+        CK(xs_in.ensure((size_t)n * D));
+        CK(cudaMemcpyAsync(xs_in.p, xs, (size_t)n * D * sizeof(double), cudaMemcpyHostToDevice, stream));
+        if (periodic) CK(cudaMemcpyAsync(planes.p, &ps_orig, sizeof(ps_orig), cudaMemcpyHostToDevice, stream));
+        int rc = check_points(xs_in.p, n, xs); if (rc) return rc;
+        if (periodic) {
+            // first margin: twice the typical circumradius of a Poisson-Delaunay simplex at this density, times a
+            // dimension-dependent allowance for the largest ball; the certificate (certify()) corrects it if needed
+            static const double cd[7] = {0, 0, 3.14159265358979, 4.18879020478639, 4.93480220054468, 5.26378901391432, 5.16771278004997};
+            static const double allow[7] = {0, 0, 3.2, 2.4, 1.9, 1.7, 1.55};
+            double vol = 1.0;
+            for (int k = 0; k < D; ++k) vol *= std::max(h_sc.p->bbox[D + k] - h_sc.p->bbox[k], 1e-300);
+            const double spacing = pow(vol / (double)n_user, 1.0 / D);
+            margin = prm.periodic_margin > 0 ? prm.periodic_margin : 2.0 * spacing * pow((double)D / cd[D], 1.0 / D) * allow[D];
+            rc = build_halo(); if (rc) return rc;
+        }
+        return build_index();
+    }
+
+    // periodic domains: pushes the periodic planes outwards by `margin`, appends the halo copies of the caller's
+    // generators that fall inside the pushed planes (reflect_nodes, domain.jl:338) and recomputes the bounding box
+    int build_halo() {
+        double wmin = 1e300;
+        for (int i = 0; i < halo.npairs; ++i) wmin = std::min(wmin, pair_width[i]);
+        if (!(margin > 0)) margin = 0.25 * wmin;
+        if (margin > 2.0 * wmin) { err = "periodic cells extend over more than two periods: too few generators for this domain"; return HVB_EINCOMPLETE; }
+        ps_host = ps_orig;
+        halo.ncodes = 1;
+        for (int i = 0; i < halo.npairs; ++i) {
+            ps_host.off[halo.plane_a[i]] += margin; ps_host.off[halo.plane_b[i]] += margin;
+            halo.K[i] = std::max(1, (int)ceil(margin / pair_width[i]));
+            halo.ncodes *= 2 * halo.K[i] + 1;
+        }
+        CK(cudaMemcpyAsync(planes.p, &ps_host, sizeof(ps_host), cudaMemcpyHostToDevice, stream));
+        CK(halo_cnt.ensure(n_user + 1)); CK(halo_off.ensure(n_user + 1));
+        CK(cudaMemsetAsync(halo_cnt.p + n_user, 0, sizeof(int), stream));
+        k_halo<D><<<blocks_for(n_user, 128), 128, 0, stream>>>(xs_in.p, (int)n_user, halo, planes.p, halo_cnt.p, nullptr, nullptr, nullptr, nullptr);
+        ++launches;
+        size_t tmp_bytes = 0;
+        CK(cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, halo_cnt.p, halo_off.p, (int)(n_user + 1), stream));
+        CK(cub_tmp.ensure(tmp_bytes));
+        CK(cub::DeviceScan::ExclusiveSum(cub_tmp.p, tmp_bytes, halo_cnt.p, halo_off.p, (int)(n_user + 1), stream));
+        int total = 0;
+        CK(cudaMemcpyAsync(&total, halo_off.p + n_user, sizeof(int), cudaMemcpyDeviceToHost, stream));
+        CK(cudaStreamSynchronize(stream));
+        n_halo = total;
+        n = n_user + n_halo;
+        if (n > 0x7ff00000LL) { err = "too many generators after adding the periodic halo"; return HVB_EINVAL; }
+        CK(xs_in.grow_keep((size_t)n * D, (size_t)n_user * D, stream));
+        CK(halo_origin.ensure(std::max<int64_t>(n_halo, 1))); CK(halo_mult.ensure(std::max<int64_t>(n_halo, 1) * halo.npairs));
+        if (n_halo > 0) {
+            k_halo<D><<<blocks_for(n_user, 128), 128, 0, stream>>>(xs_in.p, (int)n_user, halo, planes.p, nullptr, halo_off.p, xs_in.p, halo_origin.p, halo_mult.p);
+            ++launches;
+        }
+        if (debug) fprintf(stderr, "[hvb] periodic: margin %.4g, %lld halo generators for %lld caller generators\n", margin, (long long)n_halo, (long long)n_user);
+        return check_points(xs_in.p, n, nullptr);
+    }
+
+    // grid index over the n generators in xs_in (bounding box in h_sc.p->bbox)
+    int build_index() {
+        dv.n = (int)n;
         double blo[D], bhi[D];
         for (int k = 0; k < D; ++k) { blo[k] = h_sc.p->bbox[k]; bhi[k] = h_sc.p->bbox[D + k]; }
         int ppc = prm.points_per_cell > 0 ? prm.points_per_cell : default_points_per_cell(D);
@@ -295,6 +424,7 @@ struct Ctx : hvb_ctx {
         float ms = 0;
         cudaEventElapsedTime(&ms, ev_a, ev_b);
         st.ms_build = ms;
+        st.halo_nodes = n_halo;
         return HVB_OK;
     }
 
@@ -360,7 +490,8 @@ struct Ctx : hvb_ctx {
         // result buffers and page-locked staging are sized once with the tables (no allocation in steady state)
         for (int i = 0; i < 2; ++i) { CK(out_sig[i].ensure((size_t)cap * (D + 1))); CK(out_r[i].ensure((size_t)cap * D)); }
         CK(key_hi.ensure(cap)); CK(key_lo.ensure(cap)); CK(key_tmp.ensure(cap)); CK(idx[0].ensure(cap)); CK(idx[1].ensure(cap));
-        CK(h_sig.ensure((size_t)cap * (D + 1))); CK(h_r.ensure((size_t)cap * D));
+        // page-locked staging is pre-sized with the tables only while that stays small (stage() sizes it by the result otherwise)
+        if ((size_t)cap * (2 * D + 1) * 8 <= ((size_t)2 << 30)) { CK(h_sig.ensure((size_t)cap * (D + 1))); CK(h_r.ensure((size_t)cap * D)); }
         return HVB_OK;
     }
 
@@ -376,11 +507,110 @@ struct Ctx : hvb_ctx {
         return ev_pool[i];
     }
 
+    // Periodic domains: the search runs on caller generators + halo and is followed by the certificate; if a ball
+    // leaves the pushed planes the margin grows to what the certificate asks for and the search is repeated
+    // (the reference repeats its halo step a fixed number of times instead: Create_Discrete_Domain domain.jl:175-213,
+    // periodize! :139-166).
     int search(const int64_t* cells, int64_t ncells_in, const int64_t* seed_sig, const double* seed_r, int64_t nseed, int stride) override {
+        if (!periodic) return search_once(cells, ncells_in, seed_sig, seed_r, nseed, stride);
+        if (nseed > 0) { err = "seed vertices are not supported on a periodic context"; return HVB_EINVAL; }
+        if (cells) for (int64_t i = 0; i < ncells_in; ++i) if (cells[i] < 1 || cells[i] > n_user) { err = "Iter names a cell that is not a caller generator"; return HVB_EINVAL; }
+        int64_t retries = 0;
+        double ms_cert = 0;
+        for (;;) {
+            int rc = search_once(cells, ncells_in, nullptr, nullptr, 0, 0); if (rc) return rc;
+            bool ok = false; double need = 0;
+            rc = certify(&ok, &need, &ms_cert); if (rc) return rc;
+            if (ok) break;
+            if (++retries > 6) { err = "periodic certificate still fails after 6 margin increases"; return HVB_EINCOMPLETE; }
+            margin = std::max(1.5 * margin, 1.1 * need);
+            if (debug) fprintf(stderr, "[hvb] periodic certificate failed (needs margin %.4g): retry with margin %.4g\n", need, margin);
+            CK(cudaEventRecord(ev_a, stream));
+            rc = build_halo(); if (rc) return rc;
+            rc = build_index(); if (rc) return rc;
+        }
+        st.periodic_retries = retries;
+        st.ms_finalize += ms_cert;
+        return HVB_OK;
+    }
+
+    int certify(bool* ok, double* need, double* ms_total) {
+        CK(cudaEventRecord(ev_p0, stream));
+        CK(vflags.ensure(std::max<int64_t>(nvert, 1)));
+        CK(cudaMemsetAsync(cert.p, 0, sizeof(CertOut), stream));
+        if (nvert > 0) {
+            k_certify<D><<<blocks_for(nvert, 128), 128, 0, stream>>>(out_sig[res].p, out_r[res].p, (u32)nvert, (long long)n_user, (long long)n,
+                                                                    xs_in.p, halo_origin.p, planes.p, pcert, vflags.p, cert.p);
+            ++launches;
+        }
+        CK(cudaMemcpyAsync(h_cert.p, cert.p, sizeof(CertOut), cudaMemcpyDeviceToHost, stream));
+        CK(cudaEventRecord(ev_p1, stream));
+        CK(cudaStreamSynchronize(stream));
+        CK(cudaGetLastError());
+        float ms = 0;
+        cudaEventElapsedTime(&ms, ev_p0, ev_p1);
+        *ms_total += ms;
+        double excess;
+        memcpy(&excess, &h_cert.p->max_excess_bits, sizeof(double));
+        *need = excess;
+        if (h_cert.p->self_neighbor > 0) {
+            err = "a periodic cell neighbours its own image: too few generators for this periodic domain";
+            return HVB_EINCOMPLETE;
+        }
+        *ok = (h_cert.p->on_pushed_plane == 0) && (excess <= margin);
+        if (h_cert.p->on_pushed_plane > 0) *need = std::max(*need, 1.5 * margin);
+        st.unique_vertices = h_cert.p->canonical;
+        st.kernel_launches = launches;
+        have_flags = *ok;
+        return HVB_OK;
+    }
+
+    int halo_count(int64_t* nhalo, int32_t* npairs, double* mg) override {
+        if (nhalo) *nhalo = n_halo;
+        if (npairs) *npairs = halo.npairs;
+        if (mg) *mg = periodic ? margin : 0.0;
+        return HVB_OK;
+    }
+    int fetch_halo(int64_t* origin, int32_t* mult, double* xs) override {
+        if (!periodic || n_halo == 0) return HVB_OK;
+        CK(cudaSetDevice(prm.device));
+        std::vector<int> o(n_halo);
+        std::vector<signed char> m((size_t)n_halo * halo.npairs);
+        CK(cudaMemcpyAsync(o.data(), halo_origin.p, (size_t)n_halo * sizeof(int), cudaMemcpyDeviceToHost, stream));
+        CK(cudaMemcpyAsync(m.data(), halo_mult.p, (size_t)n_halo * halo.npairs, cudaMemcpyDeviceToHost, stream));
+        if (xs) CK(cudaMemcpyAsync(xs, xs_in.p + (size_t)n_user * D, (size_t)n_halo * D * sizeof(double), cudaMemcpyDeviceToHost, stream));
+        CK(cudaStreamSynchronize(stream));
+        if (origin) for (int64_t i = 0; i < n_halo; ++i) origin[i] = (int64_t)o[i] + 1;
+        if (mult) for (size_t i = 0; i < m.size(); ++i) mult[i] = (int32_t)m[i];
+        return HVB_OK;
+    }
+    int fetch_vertex_flags(uint8_t* flags) override {
+        if (!have_result) { err = "no search result"; return HVB_ESTATE; }
+        if (!flags) { err = "null output"; return HVB_EINVAL; }
+        CK(cudaSetDevice(prm.device));
+        if (!periodic || !have_flags) { memset(flags, 1, (size_t)nvert); return HVB_OK; }   // without a halo every row is its own representative
+        if (nvert > 0) CK(cudaMemcpyAsync(flags, vflags.p, (size_t)nvert, cudaMemcpyDeviceToHost, stream));
+        CK(cudaStreamSynchronize(stream));
+        return HVB_OK;
+    }
+
+    // expected number of periodic images of a vertex that touch caller generators (capacity estimate only)
+    double periodic_versions() const {
+        static const double cd[7] = {0, 0, 3.14159265358979, 4.18879020478639, 4.93480220054468, 5.26378901391432, 5.16771278004997};
+        double vol = 1.0;
+        for (int k = 0; k < D; ++k) vol *= std::max(dv.g[k] * dv.h[k], 1e-300);
+        const double rtyp = pow(vol / (double)std::max<int64_t>(n, 1), 1.0 / D) * pow((double)D / cd[D], 1.0 / D);
+        double stay = 1.0;
+        for (int i = 0; i < halo.npairs; ++i) stay *= 1.0 - std::min(1.0, 2.0 * rtyp / pair_width[i]);
+        return std::min((double)(D + 1), 1.0 + D * (1.0 - stay));
+    }
+
+    int search_once(const int64_t* cells, int64_t ncells_in, const int64_t* seed_sig, const double* seed_r, int64_t nseed, int stride) {
         if (nseed < 0 || (nseed > 0 && (!seed_sig || !seed_r || stride < D + 1))) { err = "bad seed vertex arguments"; return HVB_EINVAL; }
         CK(cudaSetDevice(prm.device));
-        have_result = false; staged = false; nb_total = -1;
-        int64_t cap = prm.vertex_capacity > 0 ? prm.vertex_capacity : estimate_vertices(D, n, P);
+        have_result = false; staged = false; nb_total = -1; have_flags = false;
+        int64_t cap = prm.vertex_capacity > 0 ? prm.vertex_capacity
+                      : (periodic ? (int64_t)(estimate_vertices(D, n_user, P) * periodic_versions()) : estimate_vertices(D, n, P));
         if (vcap >= cap) cap = vcap;
         int retries = 0;
         const int world = std::max(1, prm.world), rank = std::min(std::max(0, prm.rank), world - 1);
@@ -397,7 +627,9 @@ struct Ctx : hvb_ctx {
             CK(cudaMemsetAsync(sc.p, 0, sizeof(Scalars), stream));
             if (cells == nullptr) {
                 int lo = (int)(n * rank / world), hi = (int)(n * (rank + 1) / world);
-                k_fill_active_range<<<blocks_for(n, 256), 256, 0, stream>>>(active.p, (int)n, lo, hi); ++launches;
+                if (periodic) k_fill_active_orig<<<blocks_for(n, 256), 256, 0, stream>>>(active.p, perm.p, (int)n, (int)n_user, lo, hi);
+                else k_fill_active_range<<<blocks_for(n, 256), 256, 0, stream>>>(active.p, (int)n, lo, hi);
+                ++launches;
             } else {
                 CK(cells_dev.ensure(ncells_in));
                 CK(cudaMemcpyAsync(cells_dev.p, cells, ncells_in * sizeof(long long), cudaMemcpyHostToDevice, stream));
@@ -407,8 +639,10 @@ struct Ctx : hvb_ctx {
             // seeds: one descent every `stride` generators of the sorted order
             int sstride = prm.seed_stride;
             if (sstride <= 0) {
-                int64_t want = std::min<int64_t>(std::max<int64_t>(n / 16, 2048), 65536);
-                sstride = (int)std::max<int64_t>(1, n / want);
+                // one descent per 8 explored cells (measured on C2: 8 beats 4, 16 and 32; profiles/r1_sweeps_session2.md)
+                const int64_t n_act = periodic ? n_user : n;
+                int64_t want = std::min<int64_t>(std::max<int64_t>(n_act / 8, 2048), 65536);
+                sstride = (int)std::max<int64_t>(1, n_act / want);
             }
             int nseeds = (int)((n + sstride - 1) / sstride);
             int cur = 0;
@@ -537,7 +771,7 @@ struct Ctx : hvb_ctx {
         for (size_t i = 0; i + 1 < n_ev; i += 2) { cudaEventElapsedTime(&ms, ev_pool[i], ev_pool[i + 1]); kms += ms; }
         st.ms_expand_kernel = kms; st.expand_launches = expand_launches; st.expand_items = items;
         const Counters& c = *h_ctr.p;
-        st.vertices = nvert; st.rays = nrays; st.raycasts = (int64_t)c.raycasts; st.duplicate_hits = (int64_t)c.dup_hits;
+        st.vertices = nvert; st.unique_vertices = nvert; st.periodic_retries = 0; st.rays = nrays; st.raycasts = (int64_t)c.raycasts; st.duplicate_hits = (int64_t)c.dup_hits;
         st.closed_skips = (int64_t)c.closed_skips; st.candidates_fp32 = (int64_t)c.cand32; st.candidates_fp64 = (int64_t)c.cand64;
         st.rows_scanned = (int64_t)c.rows; st.probe_stages = (int64_t)c.stages; st.rounds = rounds; st.seeds = (int64_t)c.seeds;
         st.degenerate = (int64_t)c.degenerate; st.kernel_launches = launches; st.capacity_retries = retries;
@@ -833,11 +1067,16 @@ void hvb_default_params(hvb_params* p) {
     memset(p, 0, sizeof(*p));
     p->variance_tol = 1e-15; p->break_tol = 1e-5; p->b_nodes_tol = 1e-7; p->plane_tolerance = 1e-12; p->ray_tol = 1e-12;
     p->method = 0; p->device = 0; p->rank = 0; p->world = 1; p->fp32_filter = 1; p->on_degenerate = 0;
-    p->points_per_cell = 0; p->seed_stride = 0; p->sort_output = 1; p->neighbors = 0; p->persistent = 1; p->vertex_capacity = 0; p->probe_scale = 0.0;
+    p->points_per_cell = 0; p->seed_stride = 0; p->sort_output = 1; p->neighbors = 0; p->persistent = 1; p->vertex_capacity = 0; p->probe_scale = 0.0; p->periodic_margin = 0.0;
 }
 
 int hvb_create(hvb_ctx** out, int dim, int64_t n, const double* xs, int nplanes, const double* plane_base,
                const double* plane_normal, const hvb_params* params) {
+    return hvb_create_periodic(out, dim, n, xs, nplanes, plane_base, plane_normal, nullptr, params);
+}
+
+int hvb_create_periodic(hvb_ctx** out, int dim, int64_t n, const double* xs, int nplanes, const double* plane_base,
+                        const double* plane_normal, const int32_t* plane_bc, const hvb_params* params) {
     if (!out) return HVB_EINVAL;
     *out = nullptr;
     hvb_params prm;
@@ -862,7 +1101,7 @@ int hvb_create(hvb_ctx** out, int dim, int64_t n, const double* xs, int nplanes,
         case 6: c = new Ctx<6>(); break;
     }
     c->dim = dim; c->n = n; c->P = nplanes; c->prm = prm;
-    int rc = c->init(xs, plane_base, plane_normal);
+    int rc = c->init(xs, plane_base, plane_normal, plane_bc);
     if (rc != HVB_OK) { g_create_error = c->err; delete c; return rc; }
     *out = c;
     return HVB_OK;
@@ -886,6 +1125,9 @@ int hvb_export_device(hvb_ctx* ctx, void* sig_dev, void* r_dev, int64_t cap, int
 int hvb_merge_device(hvb_ctx* ctx, const void* sig_dev, const void* r_dev, int64_t count) { return ctx ? ctx->merge_device(sig_dev, r_dev, count) : HVB_EINVAL; }
 int hvb_adopt_device_padded(hvb_ctx* ctx, const void* sig_dev, const void* r_dev, int nseg, int64_t seg_cap, const int64_t* counts) { return (ctx && counts) ? ctx->adopt_device_padded(sig_dev, r_dev, nseg, seg_cap, counts) : HVB_EINVAL; }
 int hvb_adopt_device(hvb_ctx* ctx, const void* sig_dev, const void* r_dev, int64_t count) { return ctx ? ctx->adopt_device(sig_dev, r_dev, count) : HVB_EINVAL; }
+int hvb_halo_count(hvb_ctx* ctx, int64_t* nhalo, int32_t* npairs, double* margin) { return ctx ? ctx->halo_count(nhalo, npairs, margin) : HVB_EINVAL; }
+int hvb_fetch_halo(hvb_ctx* ctx, int64_t* origin, int32_t* mult, double* xs) { return ctx ? ctx->fetch_halo(origin, mult, xs) : HVB_EINVAL; }
+int hvb_fetch_vertex_flags(hvb_ctx* ctx, uint8_t* flags) { return ctx ? ctx->fetch_vertex_flags(flags) : HVB_EINVAL; }
 int hvb_stats(hvb_ctx* ctx, hvb_stats_t* out) {
     if (!ctx || !out) return HVB_EINVAL;
     *out = ctx->st;

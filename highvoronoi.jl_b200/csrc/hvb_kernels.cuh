@@ -165,6 +165,152 @@ __global__ void k_mark_cells(const long long* __restrict__ cells, long long ncel
 }
 
 // ------------------------------------------------------------------------------------------------------------
+// periodic domains: halo generators (reflect_nodes domain.jl:338-390, iteratively_reflected_points! :310-336) and the
+// certificate that replaces the reference's repeat-until-stable periodize! passes (domain.jl:139-166)
+// ------------------------------------------------------------------------------------------------------------
+// Periodic plane pairs: plane a and its partner b have opposite normals; T = n_a * width moves a point one period
+// in direction n_a.  A halo copy is x + sum_p k_p T_p with integer multiplicities |k_p| <= K_p, not all zero, kept
+// if it lies inside the periodic planes pushed outwards by the margin (the PlaneSet on the device holds the pushed
+// planes: expand_internal_boundary, domain.jl:145).
+#define HVB_MAX_PAIRS 8
+struct HaloSpec {
+    int npairs;
+    int K[HVB_MAX_PAIRS];
+    int plane_a[HVB_MAX_PAIRS], plane_b[HVB_MAX_PAIRS];
+    double T[HVB_MAX_PAIRS][6];
+    int ncodes;
+};
+
+// one thread per caller generator, all shift codes in ascending order: deterministic halo numbering without atomics.
+// Pass 1 (xs_out == nullptr) counts the accepted copies of every generator, pass 2 writes them behind offs[i].
+template <int D>
+__global__ void k_halo(const double* xs, int n_user, HaloSpec hs, const PlaneSet* __restrict__ ps,
+                       int* __restrict__ counts, const int* __restrict__ offs, double* xs_out,
+                       int* __restrict__ origin, signed char* __restrict__ mult) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_user) return;
+    double x[D];
+#pragma unroll
+    for (int k = 0; k < D; ++k) x[k] = xs[(size_t)i * D + k];
+    int cnt = 0;
+    const int base = xs_out ? offs[i] : 0;
+    for (int code = 0; code < hs.ncodes; ++code) {
+        int km[HVB_MAX_PAIRS];
+        int rem = code;
+        bool zero = true;
+        for (int p = 0; p < hs.npairs; ++p) {
+            int w = 2 * hs.K[p] + 1;
+            km[p] = rem % w - hs.K[p];
+            rem /= w;
+            zero &= (km[p] == 0);
+        }
+        if (zero) continue;
+        double y[D];
+#pragma unroll
+        for (int k = 0; k < D; ++k) y[k] = x[k];
+        for (int p = 0; p < hs.npairs; ++p) {
+#pragma unroll
+            for (int k = 0; k < D; ++k) y[k] += (double)km[p] * hs.T[p][k];
+        }
+        bool ok = true;
+        for (int p = 0; p < hs.npairs && ok; ++p) {
+            // the same expression as the domain check (k_bbox_check): a kept copy passes it bit for bit
+            double sa = 0, sb = 0;
+#pragma unroll
+            for (int k = 0; k < D; ++k) { sa += ps->normal[hs.plane_a[p] * 6 + k] * y[k]; sb += ps->normal[hs.plane_b[p] * 6 + k] * y[k]; }
+            ok = !(sa > ps->off[hs.plane_a[p]]) && !(sb > ps->off[hs.plane_b[p]]);
+        }
+        if (!ok) continue;
+        if (xs_out) {
+            int pos = base + cnt;
+#pragma unroll
+            for (int k = 0; k < D; ++k) xs_out[(size_t)(n_user + pos) * D + k] = y[k];
+            origin[pos] = i;
+            for (int p = 0; p < hs.npairs; ++p) mult[(size_t)pos * hs.npairs + p] = (signed char)km[p];
+        }
+        ++cnt;
+    }
+    if (!xs_out) counts[i] = cnt;
+}
+
+// active[g] = 1 for the caller's own generators (not the halo) inside the slab of sorted positions [lo, hi)
+__global__ void k_fill_active_orig(unsigned char* active, const int* __restrict__ perm, int n, int n_user, int lo, int hi) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) active[i] = (i >= lo && i < hi && perm[i] < n_user) ? 1 : 0;
+}
+
+// Certificate of a periodic result.  A vertex that touches one of the caller's generators is a vertex of the
+// periodic tessellation if its (empty) ball stays inside the pushed periodic planes: then no periodic image that was
+// NOT copied can lie in the ball.  If this holds for all vertices and none of them sits on a pushed plane, every
+// cell of a caller generator is exactly its periodic cell.  Per row: the excess of the ball
+// over every ORIGINAL periodic plane (-> smallest sufficient margin), whether it touches a pushed periodic plane,
+// and the flag "canonical representative": among the periodic images of a vertex that touch caller generators
+// exactly one has its smallest-origin generator unshifted.
+struct PeriodicCert {
+    int nplanes;
+    int is_periodic[HVB_MAX_PLANES];
+    double off_orig[HVB_MAX_PLANES];
+};
+struct CertOut {
+    unsigned long long max_excess_bits;   // max over rows of (n_p . r + R - off_orig_p), >= 0, as double bits
+    unsigned int on_pushed_plane;         // rows with a pushed periodic plane in their signature
+    unsigned int canonical;               // rows flagged canonical
+    unsigned int self_neighbor;           // rows holding two images of the same generator (domain too small)
+    unsigned int pad;
+};
+template <int D>
+__global__ void k_certify(const long long* __restrict__ sig, const double* __restrict__ r, u32 nv, long long n_user, long long n_ext,
+                          const double* __restrict__ xs_ext, const int* __restrict__ halo_origin, const PlaneSet* __restrict__ ps,
+                          PeriodicCert pc, unsigned char* __restrict__ vflags, CertOut* __restrict__ out) {
+    u32 v = blockIdx.x * blockDim.x + threadIdx.x;
+    if (v >= nv) return;
+    long long s[D + 1];
+#pragma unroll
+    for (int k = 0; k < D + 1; ++k) s[k] = sig[(size_t)v * (D + 1) + k];
+    double c[D];
+#pragma unroll
+    for (int k = 0; k < D; ++k) c[k] = r[(size_t)v * D + k];
+    // radius: distance to the first generator (rows are sorted, planes last; s[0] is always a generator)
+    double R2 = 0;
+#pragma unroll
+    for (int k = 0; k < D; ++k) { double t = xs_ext[(size_t)(s[0] - 1) * D + k] - c[k]; R2 += t * t; }
+    const double R = sqrt(R2);
+    bool pushed = false, self_nb = false;
+    long long min_origin = 0x7fffffffffffffffLL;
+    bool min_unshifted = false;
+#pragma unroll
+    for (int k = 0; k < D + 1; ++k) {
+        if (s[k] > n_ext) { pushed |= (pc.is_periodic[(int)(s[k] - n_ext - 1)] != 0); continue; }
+        long long o = (s[k] <= n_user) ? s[k] - 1 : (long long)halo_origin[s[k] - n_user - 1];
+        if (o < min_origin) { min_origin = o; min_unshifted = (s[k] <= n_user); }
+        else if (o == min_origin && s[k] <= n_user) min_unshifted = true;
+    }
+    // images of the same generator further down the row (not only of the smallest origin)
+#pragma unroll
+    for (int a = 0; a < D + 1; ++a)
+#pragma unroll
+        for (int b = a + 1; b < D + 1; ++b)
+            if (s[a] <= n_ext && s[b] <= n_ext) {
+                long long oa = (s[a] <= n_user) ? s[a] - 1 : (long long)halo_origin[s[a] - n_user - 1];
+                long long ob = (s[b] <= n_user) ? s[b] - 1 : (long long)halo_origin[s[b] - n_user - 1];
+                self_nb |= (oa == ob);
+            }
+    double excess = 0;
+    for (int p = 0; p < pc.nplanes; ++p) {
+        if (!pc.is_periodic[p]) continue;
+        double sdot = 0;
+#pragma unroll
+        for (int k = 0; k < D; ++k) sdot += ps->normal[p * 6 + k] * c[k];
+        excess = fmax(excess, sdot + R - pc.off_orig[p]);
+    }
+    vflags[v] = min_unshifted ? 1 : 0;
+    if (excess > 0) atomicMax(&out->max_excess_bits, (unsigned long long)__double_as_longlong(excess));
+    if (pushed) atomicAdd(&out->on_pushed_plane, 1u);
+    if (min_unshifted) atomicAdd(&out->canonical, 1u);
+    if (self_nb) atomicAdd(&out->self_neighbor, 1u);
+}
+
+// ------------------------------------------------------------------------------------------------------------
 // seeding and frontier rounds
 // ------------------------------------------------------------------------------------------------------------
 template <int D, int G>

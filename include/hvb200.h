@@ -63,6 +63,8 @@ typedef struct hvb_params {
                                  0: one launch per frontier round */
     int64_t vertex_capacity;  /* 0 = estimate from lowerbound(d,d) (edgeiteratebase.jl:151); grows on demand */
     double probe_scale;       /* first probe ball radius / circumradius of the origin vertex; 0 = auto */
+    double periodic_margin;   /* hvb_create_periodic: first halo margin (distance outside the periodic planes); 0 = auto
+                                 from the generator density.  The certificate enlarges it when it proves too small. */
 } hvb_params;
 
 typedef struct hvb_stats_t {
@@ -89,6 +91,9 @@ typedef struct hvb_stats_t {
     double  ms_seed;          /* device time of the first descent kernel                  */
     double  ms_neighbors;     /* neighbour lists (when built inside hvb_search) + staging  */
     double  ms_rows_sort;     /* part of ms_finalize: canonical rows + lexicographic sort  */
+    int64_t halo_nodes;       /* periodic contexts: halo generators appended behind the caller's      */
+    int64_t unique_vertices;  /* vertices counted once per periodic image class (= vertices otherwise) */
+    int64_t periodic_retries; /* searches repeated because the periodic certificate asked for a larger margin */
 } hvb_stats_t;
 
 /* fills *p with the reference's defaults (RaycastParameter(Float64), raycast-types.jl:312-324) */
@@ -101,6 +106,33 @@ void hvb_default_params(hvb_params* p);
 int hvb_create(hvb_ctx** out, int dim, int64_t n, const double* xs,
                int nplanes, const double* plane_base, const double* plane_normal,
                const hvb_params* params);
+
+/* Periodic domains.  Replaces the halo orchestration of VoronoiGeometry for boundaries with periodic planes
+ * (Create_Discrete_Domain src/domain.jl:175-213, reflect_nodes :338-390, periodize! :139-166, expand_internal_boundary).
+ * plane_bc[p] is Plane.BC of plane p (boundary.jl:15-29): > 0 = 1-based index of the periodic partner plane (parallel,
+ * opposite normal; cuboid(d) pairs plane 2i-1 with 2i, boundary.jl:510-534), <= 0 = Dirichlet/Neumann (a mirror on this path).
+ * The context appends HALO generators -- copies x + sum_k m_k T_k of caller generators, T_k = one period along
+ * the normal of the lower-indexed plane of pair k, m_k integer -- that lie within `margin` outside the periodic
+ * planes, pushes those planes outwards by `margin`, and hvb_search explores the cells of the CALLER generators only.
+ * After the search a certificate is evaluated on the device: every returned vertex has its empty ball inside the
+ * pushed planes, hence no periodic image that was not copied can lie in it and every caller cell is exactly its
+ * periodic cell; otherwise the margin grows to what the certificate demands and the search is repeated.
+ * Numbering of the results: caller generators 1..n, halo generators n+1..n+nhalo (hvb_fetch_halo), plane p =
+ * n+nhalo+p.  Returned are all vertices that touch a caller generator; a vertex whose generators wrap around the
+ * domain appears once per image that touches caller generators (each caller cell needs its own image, as in the
+ * reference's mesh); hvb_fetch_vertex_flags marks one canonical image per class (hvb_stats_t.unique_vertices).
+ * Neighbour lists have n+nhalo+1 offsets; only the lists of the caller generators are complete.
+ * plane_bc == NULL is hvb_create.  world > 1 and seed vertices are not supported on periodic contexts yet. */
+int hvb_create_periodic(hvb_ctx** out, int dim, int64_t n, const double* xs,
+                        int nplanes, const double* plane_base, const double* plane_normal, const int32_t* plane_bc,
+                        const hvb_params* params);
+/* halo of a periodic context (references / reference_shifts of the reference's domain, domain.jl:338-390):
+ * origin[i] = 1-based caller generator that halo generator n+1+i copies, mult[i*npairs + k] = m_k, xs = coordinates
+ * (nhalo x dim; any output pointer may be NULL).  npairs pairs are numbered by ascending lower plane index. */
+int hvb_halo_count(hvb_ctx* ctx, int64_t* nhalo, int32_t* npairs, double* margin);
+int hvb_fetch_halo(hvb_ctx* ctx, int64_t* origin, int32_t* mult, double* xs);
+/* flags[v] bit 0: vertex v is the canonical image of its periodic class (always 1 on non-periodic contexts) */
+int hvb_fetch_vertex_flags(hvb_ctx* ctx, uint8_t* flags);
 
 /* Re-targets an existing context to a new generator set of the same dimension and domain (a second
  * Raycast(xs; domain, options) call in the reference): uploads the points and rebuilds the index, re-using every

@@ -27,7 +27,7 @@ mutable struct HvbParams
     method::Int32; device::Int32; rank::Int32; world::Int32
     fp32_filter::Int32; on_degenerate::Int32; points_per_cell::Int32; seed_stride::Int32; sort_output::Int32
     tile_size::Int32; neighbors::Int32; persistent::Int32
-    vertex_capacity::Int64; probe_scale::Cdouble
+    vertex_capacity::Int64; probe_scale::Cdouble; periodic_margin::Cdouble
     HvbParams() = new()
 end
 
