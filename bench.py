@@ -7,8 +7,10 @@ boundary, vertex search + neighbours).  N > 1: the same density per GPU -- N x 1
 replicated, GPU k walks slab k of the spatially sorted order (parallelmesh.jl:52-87), vertex lists merged by one
 NCCL all-gather + deterministic dedup -- i.e. weak scaling along the reference's own decomposition.
 
-  value : whole-job vertices/s with the generators resident in HBM and the index built (hvb_search only, device
-          time from CUDA events on the library's stream; for N > 1 plus the all-gather + merge, max over ranks)
+  value : whole-job vertices/s with the generators resident in HBM and the index built, result (sorted vertex rows +
+          neighbour lists) complete in HBM: hvb_search only, device time from CUDA events on the library's stream
+          (ms_search + ms_finalize; the page-locked D2H staging that overlaps the neighbour build is reported as
+          ms_stage_wait and counted in e2e, not here); for N > 1 plus the all-gather + merge, max over ranks
   e2e   : the same through the public API from HOST buffers: hvb_create (H2D + index build) + hvb_search +
           hvb_fetch_vertices + hvb_fetch_neighbors (D2H), wall clock with the device idle on both sides
   --impl reference : the CPU restatement of the reference algorithm (oracle/, the reference is Julia and cannot
@@ -32,7 +34,10 @@ sys.path.insert(0, ROOT)
 B_ALG = {2: 240.0, 3: 429.0, 4: 740.0, 5: 1344.0, 6: 2755.0}
 WORKLOADS = {  # name -> (points per GPU, dim)
     "C2": (100000, 3), "C1": (1000, 3), "C3": (1000000, 2), "C4": (50000, 5), "C4s": (20000, 5), "D4": (30000, 4), "D6": (4000, 6),
+    # periodic unit cube, cuboid(d) with every axis periodic (hvb_create_periodic): C5 = configs[4] of BASELINE.json
+    "C5": (20000, 6), "C5s": (4000, 6), "P3": (100000, 3), "P2": (1000000, 2),
 }
+PERIODIC = {"C5", "C5s", "P3", "P2"}
 
 
 def measured_peak():
@@ -157,7 +162,10 @@ def main():
         k, v = kv.split("=")
         settings[k] = float(v) if "." in v else int(v)
     n_total = n_per_gpu * world
-    dom = hvb200.cuboid(d, periodic=[])
+    periodic = args.workload in PERIODIC
+    if periodic and world > 1:
+        raise SystemExit("periodic workloads run on one GPU (periodic contexts are not sharded yet)")
+    dom = hvb200.cuboid(d) if periodic else hvb200.cuboid(d, periodic=[])
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device="cuda")      # > 126 MB L2
 
     def barrier():
@@ -189,7 +197,7 @@ def main():
         t0 = time.perf_counter()
         if state["s"] is None:                           # the context (device + page-locked buffers) is re-used
             opts = hvb200.RaycastParameter(threading=hvb200.B200Thread(local_rank, rank, world), neighbors=1, **settings)
-            state["s"] = hvb200.Raycast(xs, domain=dom, options=opts)
+            state["s"] = hvb200.Raycast(xs, domain=dom, options=opts, periodic=periodic)
         else:
             state["s"].set_points(xs)                    # H2D + index build
         s = state["s"]
@@ -209,7 +217,8 @@ def main():
         if dist is None:
             mesh = hvb200.VoronoiMesh(s)                           # D2H of vertices (and rays)
             sig_h, r_h = mesh.sig, mesh.r
-            V = sig_h.shape[0]
+            # periodic: vertices are counted once per image class ("excl. halo duplicates")
+            V = st["unique_vertices"] if periodic else sig_h.shape[0]
             t1c = time.perf_counter()
             off, ids = mesh.neighbors()                            # neighbour lists + D2H
         else:
@@ -272,8 +281,9 @@ def main():
         "metric": "voronoi_vertices_per_sec", "value": value, "unit": "vertices/s", "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": dev_ms_tot / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": "%s: %d uniform points per GPU (%d total), d=%d, cuboid(d,periodic=[]), vertices + neighbours"
-                               % (args.workload, n_per_gpu, n_total, d),
+        "config": {"workload": "%s: %d uniform points per GPU (%d total), d=%d, %s, vertices + neighbours"
+                               % (args.workload, n_per_gpu, n_total, d,
+                                  "cuboid(d) all axes periodic: halo generators + certificate on the device" if periodic else "cuboid(d,periodic=[])"),
                    "parallelism": "slab%d" % world, "l2": "256 MiB L2 flush before every step; steps timed one by one and summed",
                    "settings": settings},
         "e2e": {"value": e2e, "unit": "vertices/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
@@ -287,7 +297,8 @@ def main():
                      "kernel_ms_per_step": kern_ms / args.steps},
         "vertices_per_step": verts / args.steps,
         "stats_last_step": {k: stats_last[k] for k in ("raycasts", "duplicate_hits", "closed_skips", "candidates_fp32",
-                                                        "candidates_fp64", "rounds", "seeds", "ms_build", "ms_search", "ms_finalize", "ms_seed", "ms_neighbors", "ms_rows_sort", "capacity_retries")},
+                                                        "candidates_fp64", "rounds", "seeds", "ms_build", "ms_search", "ms_finalize", "ms_seed", "ms_neighbors", "ms_rows_sort", "ms_stage_wait", "capacity_retries",
+                                                        "vertices", "unique_vertices", "halo_nodes", "periodic_retries")},
         "step_ms_list": step_ms,
     }
     if not args.no_cpu_baseline and world == 1:

@@ -162,7 +162,7 @@ struct Ctx : hvb_ctx {
     // results
     DBuf<long long> out_sig[2];
     DBuf<double> out_r[2];
-    DBuf<u64> key_hi, key_lo, key_tmp;
+    DBuf<u64> key_top, key_hi, key_lo, key_tmp;
     DBuf<u32> idx[2];
     int res = 0;                     // which of out_sig/out_r holds the final rows
     int64_t nvert = 0, nrays = 0;
@@ -189,7 +189,7 @@ struct Ctx : hvb_ctx {
         cell_cur.release(); unseeded_list.release(); bbox_partial.release(); planes.release(); active.release(); has_vertex.release(); cub_tmp.release();
         vsig.release(); vr.release(); vtab.release(); etab.release(); q[0].release(); q[1].release(); ray_item.release(); ray_u.release();
         ctr.release(); sc.release(); h_sc.release(); h_ctr.release(); cells_dev.release(); seed_sig_dev.release(); seed_r_dev.release();
-        out_sig[0].release(); out_sig[1].release(); out_r[0].release(); out_r[1].release(); key_hi.release(); key_lo.release(); key_tmp.release();
+        out_sig[0].release(); out_sig[1].release(); out_r[0].release(); out_r[1].release(); key_top.release(); key_hi.release(); key_lo.release(); key_tmp.release();
         idx[0].release(); idx[1].release(); ray_edge.release(); ray_node.release(); ray_base.release(); ray_dir.release();
         h_sig.release(); h_r.release(); h_nb_off.release(); h_nb_ids.release(); ptab.release(); deg.release(); ncur.release(); nb_off.release(); nb_ids.release();
         for (cudaEvent_t e : ev_pool) cudaEventDestroy(e);
@@ -489,7 +489,7 @@ struct Ctx : hvb_ctx {
         dv.vcount = &sc.p->vcount; dv.ray_count = &sc.p->ray_count;
         // result buffers and page-locked staging are sized once with the tables (no allocation in steady state)
         for (int i = 0; i < 2; ++i) { CK(out_sig[i].ensure((size_t)cap * (D + 1))); CK(out_r[i].ensure((size_t)cap * D)); }
-        CK(key_hi.ensure(cap)); CK(key_lo.ensure(cap)); CK(key_tmp.ensure(cap)); CK(idx[0].ensure(cap)); CK(idx[1].ensure(cap));
+        CK(key_top.ensure(cap)); CK(key_hi.ensure(cap)); CK(key_lo.ensure(cap)); CK(key_tmp.ensure(cap)); CK(idx[0].ensure(cap)); CK(idx[1].ensure(cap));
         // page-locked staging is pre-sized with the tables only while that stays small (stage() sizes it by the result otherwise)
         if ((size_t)cap * (2 * D + 1) * 8 <= ((size_t)2 << 30)) { CK(h_sig.ensure((size_t)cap * (D + 1))); CK(h_r.ensure((size_t)cap * D)); }
         return HVB_OK;
@@ -757,11 +757,15 @@ struct Ctx : hvb_ctx {
         if (prm.neighbors) { rc = stage_neighbors(); if (rc) return rc; }
         if (second_pass) { rc = finalize_owned(by_slab); if (rc) return rc; if (world == 1) { rc = stage(); if (rc) return rc; } }
         CK(cudaEventRecord(ev_n1, stream));
-        CK(cudaStreamWaitEvent(stream, ev_stage_done(), 0));
+        // ev_d: the result (rows, neighbour lists) is complete in HBM.  The page-locked staging copies run on their own
+        // stream and are waited for here, outside ms_finalize: they belong to the end-to-end time, not to the search
         CK(cudaEventRecord(ev_d, stream));
+        CK(cudaStreamWaitEvent(stream, ev_stage_done(), 0));
+        CK(cudaEventRecord(ev_p1, stream));
         CK(cudaStreamSynchronize(stream));
         CK(cudaGetLastError());
         float ms = 0;
+        cudaEventElapsedTime(&ms, ev_d, ev_p1); st.ms_stage_wait = ms;
         cudaEventElapsedTime(&ms, ev_a, ev_b); st.ms_search = ms;
         cudaEventElapsedTime(&ms, ev_b, ev_d); st.ms_finalize = ms;
         cudaEventElapsedTime(&ms, ev_s0, ev_s1); st.ms_seed = ms;
@@ -785,27 +789,32 @@ struct Ctx : hvb_ctx {
 
     int id_bits() const { int b = 1; while ((1LL << b) < n + P + 1) ++b; return b; }
 
-    // sorts `count` rows held in out_sig[0]/out_r[0] (keys in key_hi/key_lo) into out_sig[1]/out_r[1]
+    // sorts `count` rows held in out_sig[0]/out_r[0] (192-bit keys in key_top/key_hi/key_lo) into out_sig[1]/out_r[1]:
+    // LSD radix sort, one stable pass per 64-bit key word that carries bits
     int sort_rows(u32 count, int bits) {
         res = 0;
         if (!prm.sort_output || count == 0) return HVB_OK;
-        if ((D + 1) * bits > 128) return HVB_OK;            // keys do not fit 128 bits: leave unsorted
+        const int total_bits = (D + 1) * bits;
+        if (total_bits > 192) return HVB_OK;               // cannot happen for n < 2^27 (d = 6) / 2^31 (d <= 5)
         CK(idx[0].ensure(count)); CK(idx[1].ensure(count)); CK(key_tmp.ensure(count));
         k_iota<<<blocks_for(count, 256), 256, 0, stream>>>(idx[0].p, count); ++launches;
-        size_t tmp_bytes = 0;
-        int lo_bits = std::min(64, (D + 1) * bits), hi_bits = (D + 1) * bits - lo_bits;
-        CK(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, key_lo.p, key_tmp.p, idx[0].p, idx[1].p, (int)count, 0, lo_bits, stream));
-        CK(cub_tmp.ensure(tmp_bytes));
-        CK(cub::DeviceRadixSort::SortPairs(cub_tmp.p, tmp_bytes, key_lo.p, key_tmp.p, idx[0].p, idx[1].p, (int)count, 0, lo_bits, stream));
-        int fin = 1;
-        if (hi_bits > 0) {
-            k_gather_u64<<<blocks_for(count, 256), 256, 0, stream>>>(key_hi.p, idx[1].p, key_lo.p, count); ++launches;
-            CK(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, key_lo.p, key_tmp.p, idx[1].p, idx[0].p, (int)count, 0, hi_bits, stream));
+        const u64* words[3] = {key_lo.p, key_hi.p, key_top.p};
+        int cur = 0;
+        for (int w = 0; w < 3; ++w) {
+            const int wbits = std::min(64, total_bits - 64 * w);
+            if (wbits <= 0) break;
+            const u64* keys = words[w];
+            if (w > 0) {        // bring the word into the current order (key_lo is free after the first pass)
+                k_gather_u64<<<blocks_for(count, 256), 256, 0, stream>>>(words[w], idx[cur].p, key_lo.p, count); ++launches;
+                keys = key_lo.p;
+            }
+            size_t tmp_bytes = 0;
+            CK(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, keys, key_tmp.p, idx[cur].p, idx[1 - cur].p, (int)count, 0, wbits, stream));
             CK(cub_tmp.ensure(tmp_bytes));
-            CK(cub::DeviceRadixSort::SortPairs(cub_tmp.p, tmp_bytes, key_lo.p, key_tmp.p, idx[1].p, idx[0].p, (int)count, 0, hi_bits, stream));
-            fin = 0;
+            CK(cub::DeviceRadixSort::SortPairs(cub_tmp.p, tmp_bytes, keys, key_tmp.p, idx[cur].p, idx[1 - cur].p, (int)count, 0, wbits, stream));
+            cur = 1 - cur;
         }
-        k_gather_rows<D><<<blocks_for(count, 256), 256, 0, stream>>>(out_sig[0].p, out_r[0].p, idx[fin].p, out_sig[1].p, out_r[1].p, count); ++launches;
+        k_gather_rows<D><<<blocks_for(count, 256), 256, 0, stream>>>(out_sig[0].p, out_r[0].p, idx[cur].p, out_sig[1].p, out_r[1].p, count); ++launches;
         res = 1;
         return HVB_OK;
     }
@@ -814,10 +823,10 @@ struct Ctx : hvb_ctx {
         u32 nrec = std::min<u32>(h_sc.p->vcount, (u32)vcap);
         nrays = std::min<u32>(h_sc.p->ray_count, ray_cap);
         for (int i = 0; i < 2; ++i) { CK(out_sig[i].ensure((size_t)std::max<u32>(nrec, 1) * (D + 1))); CK(out_r[i].ensure((size_t)std::max<u32>(nrec, 1) * D)); }
-        CK(key_hi.ensure(std::max<u32>(nrec, 1))); CK(key_lo.ensure(std::max<u32>(nrec, 1)));
+        CK(key_top.ensure(std::max<u32>(nrec, 1))); CK(key_hi.ensure(std::max<u32>(nrec, 1))); CK(key_lo.ensure(std::max<u32>(nrec, 1)));
         int bits = id_bits();
         if (nrec > 0) {
-            k_final_rows<D><<<blocks_for(nrec, 128), 128, 0, stream>>>(dv, perm.p, nrec, bits, out_sig[0].p, out_r[0].p, key_hi.p, key_lo.p,
+            k_final_rows<D><<<blocks_for(nrec, 128), 128, 0, stream>>>(dv, perm.p, nrec, bits, out_sig[0].p, out_r[0].p, key_top.p, key_hi.p, key_lo.p,
                                                                      &sc.p->out_count, &sc.p->max_var, 0, 0, 0u);
             ++launches;
         }
@@ -840,7 +849,7 @@ struct Ctx : hvb_ctx {
         int bits = id_bits();
         CK(cudaMemsetAsync(&sc.p->out_count, 0, sizeof(u32), stream));
         if (nrec > 0) {
-            k_final_rows<D><<<blocks_for(nrec, 128), 128, 0, stream>>>(dv, perm.p, nrec, bits, out_sig[0].p, out_r[0].p, key_hi.p, key_lo.p,
+            k_final_rows<D><<<blocks_for(nrec, 128), 128, 0, stream>>>(dv, perm.p, nrec, bits, out_sig[0].p, out_r[0].p, key_top.p, key_hi.p, key_lo.p,
                                                                      &sc.p->out_count, &sc.p->max_var, lo, hi, seed_prefix);
             ++launches;
         }
@@ -922,13 +931,15 @@ struct Ctx : hvb_ctx {
         nb_staged = false;
         CK(deg.ensure(n)); CK(ncur.ensure(n)); CK(nb_off.ensure(n + 1));
         static const double nb_est[7] = {0, 0, 8, 20, 48, 120, 320};
-        u64 want = next_pow2((u64)(std::min((double)nvert * D * (D + 1) / 2.0, (double)n * nb_est[D]) * 2.0) + 1024);
+        // periodic contexts build the lists of the caller's cells only (n_user == n otherwise)
+        const long long n_list = periodic ? n_user : n;
+        u64 want = next_pow2((u64)(std::min((double)nvert * D * (D + 1) / 2.0, (double)n_list * nb_est[D]) * 2.0) + 1024);
         for (int attempt = 0; attempt < 8; ++attempt) {
             CK(ptab.ensure(want));
             CK(cudaMemsetAsync(ptab.p, 0, want * sizeof(u64), stream));
             CK(cudaMemsetAsync(deg.p, 0, n * sizeof(u32), stream));
             CK(cudaMemsetAsync(&sc.p->pflags, 0, sizeof(u32), stream));
-            if (nvert > 0) { k_pairs<D><<<blocks_for(nvert, 128), 128, 0, stream>>>(out_sig[res].p, (u32)nvert, n, ptab.p, want - 1, deg.p, &sc.p->pflags); ++launches; }
+            if (nvert > 0) { k_pairs<D><<<blocks_for(nvert, 128), 128, 0, stream>>>(out_sig[res].p, (u32)nvert, n_list, ptab.p, want - 1, deg.p, &sc.p->pflags); ++launches; }
             int rc = read_scalars(); if (rc) return rc;
             if (!(h_sc.p->pflags & 8u)) break;
             want *= 4;
@@ -946,7 +957,7 @@ struct Ctx : hvb_ctx {
         CK(cudaStreamSynchronize(stream));
         CK(nb_ids.ensure(std::max<long long>(total, 1)));
         CK(cudaMemsetAsync(ncur.p, 0, n * sizeof(u32), stream));
-        k_pair_fill<<<blocks_for((int64_t)want, 256), 256, 0, stream>>>(ptab.p, want, n, nb_off.p, ncur.p, nb_ids.p); ++launches;
+        k_pair_fill<<<blocks_for((int64_t)want, 256), 256, 0, stream>>>(ptab.p, want, n_list, nb_off.p, ncur.p, nb_ids.p); ++launches;
         k_sort_lists<<<blocks_for(n, 128), 128, 0, stream>>>(nb_off.p, nb_ids.p, n); ++launches;
         CK(cudaStreamSynchronize(stream));
         CK(cudaGetLastError());
@@ -963,8 +974,10 @@ struct Ctx : hvb_ctx {
     int stage_neighbors() {
         if (nb_staged) return HVB_OK;
         CK(h_nb_off.ensure(n + 1)); CK(h_nb_ids.ensure(std::max<int64_t>(nb_total, 1)));
-        CK(cudaMemcpyAsync(h_nb_off.p, nb_off.p, (size_t)(n + 1) * 8, cudaMemcpyDeviceToHost, stream));
-        if (nb_total > 0) CK(cudaMemcpyAsync(h_nb_ids.p, nb_ids.p, (size_t)nb_total * 8, cudaMemcpyDeviceToHost, stream));
+        CK(cudaEventRecord(ev_stage, stream));
+        CK(cudaStreamWaitEvent(sstream, ev_stage, 0));
+        CK(cudaMemcpyAsync(h_nb_off.p, nb_off.p, (size_t)(n + 1) * 8, cudaMemcpyDeviceToHost, sstream));
+        if (nb_total > 0) CK(cudaMemcpyAsync(h_nb_ids.p, nb_ids.p, (size_t)nb_total * 8, cudaMemcpyDeviceToHost, sstream));
         nb_staged = true;
         return HVB_OK;
     }
@@ -973,6 +986,7 @@ struct Ctx : hvb_ctx {
         int rc = build_neighbors(); if (rc) return rc;
         rc = stage_neighbors(); if (rc) return rc;
         CK(cudaStreamSynchronize(stream));
+        CK(cudaStreamSynchronize(sstream));
         *off = (const int64_t*)h_nb_off.p; *ids = (const int64_t*)h_nb_ids.p; *total = nb_total;
         return HVB_OK;
     }
@@ -1034,7 +1048,7 @@ struct Ctx : hvb_ctx {
     int merge_device(const void* sig, const void* r, int64_t count) override {
         CK(cudaSetDevice(prm.device));
         for (int i = 0; i < 2; ++i) { CK(out_sig[i].ensure((size_t)std::max<int64_t>(count, 1) * (D + 1))); CK(out_r[i].ensure((size_t)std::max<int64_t>(count, 1) * D)); }
-        CK(key_hi.ensure(std::max<int64_t>(count, 1))); CK(key_lo.ensure(std::max<int64_t>(count, 1)));
+        CK(key_top.ensure(std::max<int64_t>(count, 1))); CK(key_hi.ensure(std::max<int64_t>(count, 1))); CK(key_lo.ensure(std::max<int64_t>(count, 1)));
         u64 ts = next_pow2((u64)count * 2 + 16);
         CK(ptab.ensure(ts));
         CK(cudaMemsetAsync(ptab.p, 0, ts * sizeof(u64), stream));
@@ -1042,7 +1056,7 @@ struct Ctx : hvb_ctx {
         int bits = id_bits();
         if (count > 0) {
             k_merge_rows<D><<<blocks_for(count, 128), 128, 0, stream>>>((const long long*)sig, (const double*)r, (u64)count, bits, ptab.p, ts - 1,
-                                                                      out_sig[0].p, out_r[0].p, key_hi.p, key_lo.p, &sc.p->out_count);
+                                                                      out_sig[0].p, out_r[0].p, key_top.p, key_hi.p, key_lo.p, &sc.p->out_count);
             ++launches;
         }
         int rc = read_scalars(); if (rc) return rc;

@@ -486,7 +486,7 @@ __global__ void k_unseeded(Dev<D> dv, int* list, u32* count) {
 template <int D>
 __global__ void k_final_rows(Dev<D> dv, const int* __restrict__ perm, u32 nrec, int bits,
                              long long* __restrict__ out_sig, double* __restrict__ out_r,
-                             u64* __restrict__ key_hi, u64* __restrict__ key_lo, u32* __restrict__ out_count,
+                             u64* __restrict__ key_top, u64* __restrict__ key_hi, u64* __restrict__ key_lo, u32* __restrict__ out_count,
                              double* __restrict__ max_var, int own_lo, int own_hi, u32 skip_below) {
     u32 v = blockIdx.x * blockDim.x + threadIdx.x;
     if (v >= nrec || v < skip_below) return;          // records below skip_below are the caller's own (seed) vertices
@@ -514,17 +514,18 @@ __global__ void k_final_rows(Dev<D> dv, const int* __restrict__ perm, u32 nrec, 
     double r[D];
     double var = canonical_vertex<D>(dv, in, r);
     u32 pos = atomicAdd(out_count, 1u);
-    u64 hi = 0, lo = 0;
+    u64 top = 0, hi = 0, lo = 0;
 #pragma unroll
     for (int k = 0; k < D + 1; ++k) {
         out_sig[(size_t)pos * (D + 1) + k] = og[k] + 1;
-        // 128-bit key = concatenation of the ids, first id most significant
+        // 192-bit key = concatenation of the ids, first id most significant
+        top = (top << bits) | (hi >> (64 - bits));
         hi = (hi << bits) | (lo >> (64 - bits));
         lo = (lo << bits) | (u64)og[k];
     }
 #pragma unroll
     for (int k = 0; k < D; ++k) out_r[(size_t)pos * D + k] = r[k];
-    key_hi[pos] = hi; key_lo[pos] = lo;
+    key_top[pos] = top; key_hi[pos] = hi; key_lo[pos] = lo;
     if (var > 1e-18) atomicMax(reinterpret_cast<unsigned long long*>(max_var), (unsigned long long)__double_as_longlong(var));
 }
 
@@ -587,7 +588,7 @@ __global__ void k_pairs(const long long* __restrict__ sig, u32 nv, long long n, 
     for (int i = 0; i < D + 1; ++i) {
 #pragma unroll
         for (int j = i + 1; j < D + 1; ++j) {
-            if (s[i] > n) continue;                       // both are planes
+            if (s[i] > n) continue;                       // neither is a cell whose list is built (ids ascend: both are planes, or halo / planes)
             u64 key = ((u64)s[i] << 32) | (u64)s[j];      // 1-based ids: key != 0
             u64 slot = mix64(key) & pmask;
             for (u32 probe = 0;; ++probe) {
@@ -643,7 +644,7 @@ __global__ void k_u32_to_i64(const u32* __restrict__ a, long long* __restrict__ 
 template <int D>
 __global__ void k_merge_rows(const long long* __restrict__ sig_in, const double* __restrict__ r_in, u64 count, int bits,
                              u64* __restrict__ tab, u64 mask, long long* __restrict__ sig_out, double* __restrict__ r_out,
-                             u64* __restrict__ key_hi, u64* __restrict__ key_lo, u32* __restrict__ out_count) {
+                             u64* __restrict__ key_top, u64* __restrict__ key_hi, u64* __restrict__ key_lo, u32* __restrict__ out_count) {
     u64 i = blockIdx.x * (u64)blockDim.x + threadIdx.x;
     if (i >= count) return;
     long long s[D + 1];
@@ -666,16 +667,17 @@ __global__ void k_merge_rows(const long long* __restrict__ sig_in, const double*
         slot = (slot + 1) & mask;
     }
     u32 pos = atomicAdd(out_count, 1u);
-    u64 hi = 0, lo = 0;
+    u64 top = 0, hi = 0, lo = 0;
 #pragma unroll
     for (int k = 0; k < D + 1; ++k) {
         sig_out[(size_t)pos * (D + 1) + k] = s[k];
+        top = (top << bits) | (hi >> (64 - bits));
         hi = (hi << bits) | (lo >> (64 - bits));
         lo = (lo << bits) | (u64)(s[k] - 1);
     }
 #pragma unroll
     for (int k = 0; k < D; ++k) r_out[(size_t)pos * D + k] = r_in[i * D + k];
-    key_hi[pos] = hi; key_lo[pos] = lo;
+    key_top[pos] = top; key_hi[pos] = hi; key_lo[pos] = lo;
 }
 
 }  // namespace hvb

@@ -84,7 +84,7 @@ typedef struct hvb_stats_t {
     int64_t capacity_retries;
     double  ms_build;         /* H2D + grid build                                         */
     double  ms_search;        /* seeding + frontier rounds                                */
-    double  ms_finalize;      /* canonical coordinates, sort, neighbour lists             */
+    double  ms_finalize;      /* canonical coordinates, sort, neighbour lists: result complete in HBM */
     double  ms_expand_kernel; /* device time of the dominant kernel (walk/expand), summed */
     int64_t expand_launches;
     int64_t expand_items;     /* frontier entries processed by it                         */
@@ -94,6 +94,8 @@ typedef struct hvb_stats_t {
     int64_t halo_nodes;       /* periodic contexts: halo generators appended behind the caller's      */
     int64_t unique_vertices;  /* vertices counted once per periodic image class (= vertices otherwise) */
     int64_t periodic_retries; /* searches repeated because the periodic certificate asked for a larger margin */
+    double  ms_stage_wait;    /* time hvb_search waited, after the result was complete in HBM (end of ms_finalize), for the
+                                 page-locked staging copies (D2H) that overlap the neighbour build */
 } hvb_stats_t;
 
 /* fills *p with the reference's defaults (RaycastParameter(Float64), raycast-types.jl:312-324) */
@@ -121,7 +123,7 @@ int hvb_create(hvb_ctx** out, int dim, int64_t n, const double* xs,
  * n+nhalo+p.  Returned are all vertices that touch a caller generator; a vertex whose generators wrap around the
  * domain appears once per image that touches caller generators (each caller cell needs its own image, as in the
  * reference's mesh); hvb_fetch_vertex_flags marks one canonical image per class (hvb_stats_t.unique_vertices).
- * Neighbour lists have n+nhalo+1 offsets; only the lists of the caller generators are complete.
+ * Neighbour lists have n+nhalo+1 offsets; they are built for the caller generators (halo cells get empty lists).
  * plane_bc == NULL is hvb_create.  world > 1 and seed vertices are not supported on periodic contexts yet. */
 int hvb_create_periodic(hvb_ctx** out, int dim, int64_t n, const double* xs,
                         int nplanes, const double* plane_base, const double* plane_normal, const int32_t* plane_bc,
