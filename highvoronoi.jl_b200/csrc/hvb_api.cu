@@ -97,6 +97,17 @@ struct Scalars {            // small device-side words, mirrored into pinned hos
     double bbox[12];
 };
 
+// Small device words -> page-locked host memory, written by the SMs (the host pointers are device-accessible under
+// unified addressing).  A cudaMemcpy would queue on the D2H copy engine BEHIND the result staging copy that runs on
+// the staging stream: the neighbour build then waited a whole staging copy for every 100-byte read.
+__global__ void k_publish(const u32* __restrict__ a, u32* ha, int na, const u32* __restrict__ b, u32* hb, int nb,
+                          const long long* __restrict__ extra, long long* hextra) {
+    for (int i = threadIdx.x; i < na; i += blockDim.x) ha[i] = __ldcg(a + i);
+    for (int i = threadIdx.x; i < nb; i += blockDim.x) hb[i] = __ldcg(b + i);
+    if (extra && threadIdx.x == 0) *hextra = __ldcg(extra);
+    __threadfence_system();
+}
+
 struct hvb_ctx {
     int dim = 0; int64_t n = 0; int P = 0;
     hvb_params prm;
@@ -155,6 +166,7 @@ struct Ctx : hvb_ctx {
     DBuf<Scalars> sc;
     HBuf<Scalars> h_sc;
     HBuf<Counters> h_ctr;
+    HBuf<long long> h_extra;
     DBuf<long long> cells_dev, seed_sig_dev;
     DBuf<double> seed_r_dev;
     bool second_pass = false;         // the rows are filtered after the neighbour lists were built from all of them
@@ -188,7 +200,7 @@ struct Ctx : hvb_ctx {
         xs_in.release(); x64.release(); x32.release(); perm.release(); inv.release(); cell_of.release(); cell_start.release();
         cell_cur.release(); unseeded_list.release(); bbox_partial.release(); planes.release(); active.release(); has_vertex.release(); cub_tmp.release();
         vsig.release(); vr.release(); vtab.release(); etab.release(); q[0].release(); q[1].release(); ray_item.release(); ray_u.release();
-        ctr.release(); sc.release(); h_sc.release(); h_ctr.release(); cells_dev.release(); seed_sig_dev.release(); seed_r_dev.release();
+        ctr.release(); sc.release(); h_sc.release(); h_ctr.release(); h_extra.release(); cells_dev.release(); seed_sig_dev.release(); seed_r_dev.release();
         out_sig[0].release(); out_sig[1].release(); out_r[0].release(); out_r[1].release(); key_top.release(); key_hi.release(); key_lo.release(); key_tmp.release();
         idx[0].release(); idx[1].release(); ray_edge.release(); ray_node.release(); ray_base.release(); ray_dir.release();
         h_sig.release(); h_r.release(); h_nb_off.release(); h_nb_ids.release(); ptab.release(); deg.release(); ncur.release(); nb_off.release(); nb_ids.release();
@@ -281,7 +293,7 @@ struct Ctx : hvb_ctx {
             periodic = halo.npairs > 0;
         }
         if (periodic && std::max(1, prm.world) > 1) { err = "periodic domains are not sharded across GPUs yet (world must be 1)"; return HVB_EINVAL; }
-        CK(planes.ensure(1)); CK(ctr.ensure(1)); CK(sc.ensure(1)); CK(h_sc.ensure(1)); CK(h_ctr.ensure(1));
+        CK(planes.ensure(1)); CK(ctr.ensure(1)); CK(sc.ensure(1)); CK(h_sc.ensure(1)); CK(h_ctr.ensure(1)); CK(h_extra.ensure(1));
         CK(cert.ensure(1)); CK(h_cert.ensure(1));
         CK(cudaMemcpyAsync(planes.p, &ps_orig, sizeof(ps_orig), cudaMemcpyHostToDevice, stream));
         dv.plane_tol = prm.plane_tolerance;
@@ -495,10 +507,14 @@ struct Ctx : hvb_ctx {
         return HVB_OK;
     }
 
-    int read_scalars() {
-        CK(cudaMemcpyAsync(h_sc.p, sc.p, sizeof(Scalars), cudaMemcpyDeviceToHost, stream));
-        CK(cudaMemcpyAsync(h_ctr.p, ctr.p, sizeof(Counters), cudaMemcpyDeviceToHost, stream));
+    // mirrors Scalars + Counters (and optionally one more device word) into page-locked host memory and waits
+    int read_scalars(const long long* extra = nullptr, long long* extra_out = nullptr) {
+        static_assert(sizeof(Scalars) % 4 == 0 && sizeof(Counters) % 4 == 0, "word copy");
+        k_publish<<<1, 64, 0, stream>>>((const u32*)sc.p, (u32*)h_sc.p, (int)(sizeof(Scalars) / 4), (const u32*)ctr.p, (u32*)h_ctr.p,
+                                        (int)(sizeof(Counters) / 4), extra, h_extra.p);
+        ++launches;
         CK(cudaStreamSynchronize(stream));
+        if (extra_out) *extra_out = *h_extra.p;
         return HVB_OK;
     }
 
@@ -543,7 +559,9 @@ struct Ctx : hvb_ctx {
                                                                     xs_in.p, halo_origin.p, planes.p, pcert, vflags.p, cert.p);
             ++launches;
         }
-        CK(cudaMemcpyAsync(h_cert.p, cert.p, sizeof(CertOut), cudaMemcpyDeviceToHost, stream));
+        static_assert(sizeof(CertOut) % 4 == 0, "word copy");
+        k_publish<<<1, 64, 0, stream>>>((const u32*)cert.p, (u32*)h_cert.p, (int)(sizeof(CertOut) / 4), nullptr, nullptr, 0, nullptr, nullptr);
+        ++launches;
         CK(cudaEventRecord(ev_p1, stream));
         CK(cudaStreamSynchronize(stream));
         CK(cudaGetLastError());
@@ -953,8 +971,7 @@ struct Ctx : hvb_ctx {
         CK(cub_tmp.ensure(tmp_bytes));
         CK(cub::DeviceScan::ExclusiveSum(cub_tmp.p, tmp_bytes, nb_off.p, nb_off.p, (int)(n + 1), stream));
         long long total = 0;
-        CK(cudaMemcpyAsync(&total, nb_off.p + n, sizeof(long long), cudaMemcpyDeviceToHost, stream));
-        CK(cudaStreamSynchronize(stream));
+        { int rc = read_scalars(nb_off.p + n, &total); if (rc) return rc; }
         CK(nb_ids.ensure(std::max<long long>(total, 1)));
         CK(cudaMemsetAsync(ncur.p, 0, n * sizeof(u32), stream));
         k_pair_fill<<<blocks_for((int64_t)want, 256), 256, 0, stream>>>(ptab.p, want, n_list, nb_off.p, ncur.p, nb_ids.p); ++launches;

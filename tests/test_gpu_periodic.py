@@ -111,9 +111,10 @@ def test_periodic_argument_errors(hvb):
     assert L.hvb_create_periodic(ctypes.byref(ctx), 2, 50, P(xs), 4, P(b.base), P(b.normal), P(bad), None) == hvb._abi.HVB_EINVAL
     bad = np.array([3, 0, 1, 0], dtype=np.int32)                    # partners that are not parallel
     assert L.hvb_create_periodic(ctypes.byref(ctx), 2, 50, P(xs), 4, P(b.base), P(b.normal), P(bad), None) == hvb._abi.HVB_EINVAL
-    # too few generators for the period: a cell would neighbour its own image
+    # too few generators for the period: a cell would neighbour its own image (three clustered points: their cells
+    # are strips that wrap around the torus; three well spread points would NOT do, their torus triangulation is proper)
     with pytest.raises(hvb.HVBError) as e:
-        run_periodic(hvb, points(3, 2, 2), (1, 2))
+        run_periodic(hvb, 0.4 + 0.05 * points(3, 2, 2), (1, 2))
     assert e.value.code in (hvb._abi.HVB_EINCOMPLETE, hvb._abi.HVB_EINVAL)
     # periodic contexts do not take seed vertices
     s = hvb.Raycast(points(500, 2, 3), domain=hvb.cuboid(2), periodic=True)
