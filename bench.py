@@ -291,7 +291,7 @@ def main():
                 "phase_ms": dict(zip(("set_points", "search", "fetch_vertices", "neighbors"), (1e3 * phases / args.steps).round(3).tolist()))},
         "gpu_launches": launches,
         "clocks": clocks,
-        "roofline": {"bound": "hbm", "kernel": ("k_walk<%d>" if settings.get("persistent", 1) else "k_expand<%d>") % d, "achieved": achieved, "peak": peak, "unit": "GB/s",
+        "roofline": {"bound": "hbm", "kernel": {0: "k_expand<%d>", 1: "k_walk<%d>", 2: "k_walk_coop<%d,pooled query>", 3: "k_walk_coop<%d>"}[settings.get("persistent", 3)] % d, "achieved": achieved, "peak": peak, "unit": "GB/s",
                      "frac": achieved / peak, "traffic": measured_traffic(args.workload), "peak_source": peak_src,
                      "bytes_per_vertex": B_ALG[d], "launches_per_step": kern_launches / args.steps,
                      "kernel_ms_per_step": kern_ms / args.steps},

@@ -139,6 +139,7 @@ struct Ctx : hvb_ctx {
     int G = 1;                       // lanes per frontier entry; 1 measured best for d = 2..5 (prm.tile_size overrides)
     bool debug = false;
     bool persistent = true;          // single-launch walk (k_walk) instead of one launch per frontier round (prm.persistent)
+    bool coop = true;                // prm.persistent == 2: the warp-cooperative query (k_walk_coop), lane-per-ray tiles only
     cudaStream_t stream = nullptr, sstream = nullptr;    // compute stream, result-staging (D2H) stream
     cudaEvent_t ev_stage = nullptr;
     int sms = 148;
@@ -302,6 +303,7 @@ struct Ctx : hvb_ctx {
         if (prm.tile_size == 1 || prm.tile_size == 2 || prm.tile_size == 4 || prm.tile_size == 8 || prm.tile_size == 16 || prm.tile_size == 32) G = prm.tile_size;
         debug = getenv("HVB_DEBUG") != nullptr;
         persistent = prm.persistent != 0;
+        coop = prm.persistent >= 2;
         setup_done = true;
         return set_points(n, xs);
     }
@@ -461,7 +463,18 @@ struct Ctx : hvb_ctx {
         k_walk<D, GG><<<std::max(1, per_sm) * sms, 128, 0, stream>>>(dv, wq);
         return HVB_OK;
     }
+    template <bool COOPQ>
+    int launch_walk_coop(const WalkQueue& wq) {
+        const size_t smem = COOPQ ? 4 * sizeof(CoopShared<D>) : 16;
+        CK(cudaFuncSetAttribute(k_walk_coop<D, COOPQ>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        int per_sm = 0;
+        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_walk_coop<D, COOPQ>, 128, smem));
+        if (debug) fprintf(stderr, "[hvb] k_walk_coop<%d,%d>: %d blocks/SM, %zu B shared per block\n", D, (int)COOPQ, per_sm, smem);
+        k_walk_coop<D, COOPQ><<<std::max(1, per_sm) * sms, 128, smem, stream>>>(dv, wq);
+        return HVB_OK;
+    }
     int launch_walk(const WalkQueue& wq) {
+        if (coop && G == 1) return prm.persistent == 3 ? launch_walk_coop<false>(wq) : launch_walk_coop<true>(wq);
         switch (G) {
             case 1: return launch_walk_g<1>(wq);
             case 2: return launch_walk_g<2>(wq);
@@ -1098,7 +1111,7 @@ void hvb_default_params(hvb_params* p) {
     memset(p, 0, sizeof(*p));
     p->variance_tol = 1e-15; p->break_tol = 1e-5; p->b_nodes_tol = 1e-7; p->plane_tolerance = 1e-12; p->ray_tol = 1e-12;
     p->method = 0; p->device = 0; p->rank = 0; p->world = 1; p->fp32_filter = 1; p->on_degenerate = 0;
-    p->points_per_cell = 0; p->seed_stride = 0; p->sort_output = 1; p->neighbors = 0; p->persistent = 1; p->vertex_capacity = 0; p->probe_scale = 0.0; p->periodic_margin = 0.0;
+    p->points_per_cell = 0; p->seed_stride = 0; p->sort_output = 1; p->neighbors = 0; p->persistent = 3; p->vertex_capacity = 0; p->probe_scale = 0.0; p->periodic_margin = 0.0;
 }
 
 int hvb_create(hvb_ctx** out, int dim, int64_t n, const double* xs, int nplanes, const double* plane_base,

@@ -664,6 +664,29 @@ HVB_HD void settle_stage(const Dev<D>& dv, const RayQ<D>& q, ScanState& st, floa
     st.cr.id = -1;
 }
 
+// boundary planes as candidates of a ray: mirror images of x0 (raycast.jl:354-375, extended.jl:131-140), analytically
+template <int D>
+HVB_HD void plane_candidates(const Dev<D>& dv, const RayQ<D>& q, Best& best) {
+    const PlaneSet* ps = dv.planes;
+    const int P = ps->P;
+    double ux0 = dotD<D>(q.u, q.x0);
+    for (int p = 0; p < P; ++p) {
+        bool ex = false;
+#pragma unroll
+        for (int e = 0; e < D + 1; ++e) ex |= (e < q.nexcl && q.excl[e] == dv.n + p);
+        if (ex) continue;
+        const double* nrm = ps->normal + p * 6;
+        double nu = 0, nx0 = 0, nr = 0;
+#pragma unroll
+        for (int k = 0; k < D; ++k) { nu += nrm[k] * q.u[k]; nx0 += nrm[k] * q.x0[k]; nr += nrm[k] * q.r[k]; }
+        double s = ps->off[p] - nx0;                       // distance of x0 to the plane (> 0 inside)
+        if (!(ux0 + 2.0 * s * nu > q.c) || !(nu > 0)) continue;
+        double t = (ps->off[p] - nr) / nu;
+        if (!(t >= dv.plane_tol)) continue;
+        best_offer(best, t, dv.n + p);
+    }
+}
+
 // Smallest t > 0 at which the ball centred at r + t u through x0 touches another generator or boundary plane.
 // All lanes of the tile call this with identical q; all return the same Best.
 template <int D, class T>
@@ -673,27 +696,7 @@ HVB_HD Best min_t_query(const Dev<D>& dv, const T& tile, const RayQ<D>& q, Local
     const int lane = tile.lane();
     ls.raycasts += (lane == 0);
 
-    // ---- boundary planes: mirror images of x0 (raycast.jl:354-375, extended.jl:131-140), analytically ----
-    const PlaneSet* ps = dv.planes;
-    const int P = ps->P;
-    {
-        double ux0 = dotD<D>(q.u, q.x0);
-        for (int p = 0; p < P; ++p) {
-            bool ex = false;
-#pragma unroll
-            for (int e = 0; e < D + 1; ++e) ex |= (e < q.nexcl && q.excl[e] == dv.n + p);
-            if (ex) continue;
-            const double* nrm = ps->normal + p * 6;
-            double nu = 0, nx0 = 0, nr = 0;
-#pragma unroll
-            for (int k = 0; k < D; ++k) { nu += nrm[k] * q.u[k]; nx0 += nrm[k] * q.x0[k]; nr += nrm[k] * q.r[k]; }
-            double s = ps->off[p] - nx0;                       // distance of x0 to the plane (> 0 inside)
-            if (!(ux0 + 2.0 * s * nu > q.c) || !(nu > 0)) continue;
-            double t = (ps->off[p] - nr) / nu;
-            if (!(t >= dv.plane_tol)) continue;
-            best_offer(best, t, dv.n + p);
-        }
-    }
+    plane_candidates<D>(dv, q, best);
 
     // ---- FP32 copies of the ray ---------------------------------------------------------------------------
     float uf[D], w2f[D], x0f[D];
@@ -1038,18 +1041,12 @@ HVB_HD void sorted_insert(int* sig, int cnt, int g) {
 // one frontier entry: walk the open edge from its known endpoint (walkray raycast.jl:125-164 +
 // systematic_explore_vertex sysvoronoi.jl:490-525, one edge at a time)
 // ------------------------------------------------------------------------------------------------------------
-template <int D, class T>
-HVB_HD void expand_item(const Dev<D>& dv, const T& tile, u64 item, u64* q_out, u32* q_count, u32 q_cap, LocalStats& ls) {
-    const int lane = tile.lane();
-    // The closed bit is mutable: every lane must act on the SAME snapshot of the slot, otherwise part of the tile
-    // leaves while the rest waits in a shuffle.  Lane 0 reads, the tile converges on the broadcast.
-    tile.sync();
-    const u32 eslot = (u32)(item >> 32);
-    const u32 v = (u32)((item >> 3) & 0x1fffffffULL);
-    const int kd = (int)(item & 7);
-    (void)eslot;                       // the closed bit was checked when the entry was acquired (k_expand)
-    int sig[D + 1];
-    RayQ<D> q;
+// first half of a walk: loads the origin vertex of frontier entry `item` and builds the ray (direction u_qr
+// tools.jl:773-790, half-space threshold raycast.jl:802-804).  false: the direction could not be built.
+template <int D>
+HVB_HD bool ray_setup(const Dev<D>& dv, u64 item, RayQ<D>& q, int (&sig)[D + 1], u32& v, int& kd) {
+    v = (u32)((item >> 3) & 0x1fffffffULL);
+    kd = (int)(item & 7);
 #pragma unroll
     for (int k = 0; k < D + 1; ++k) { sig[k] = ld_cg(dv.vsig + (size_t)v * (D + 1) + k); q.excl[k] = sig[k]; }
     q.nexcl = D + 1;
@@ -1080,7 +1077,7 @@ HVB_HD void expand_item(const Dev<D>& dv, const T& tile, u64 item, u64* q_out, u
         }
     }
     const unsigned emask = ((1u << (D + 1)) - 1u) & ~(1u << kd) & ~(1u << i0);
-    if (!ortho_direction<D>(V, emask, xd)) { ls.seed_fail += (lane == 0); return; }
+    if (!ortho_direction<D>(V, emask, xd)) return false;
 #pragma unroll
     for (int k = 0; k < D; ++k) q.u[k] = xd[k];
     // half-space threshold: c = max_{g in edge} u.x_g, c += |c| * plane_tol   (raycast.jl:802-804)
@@ -1111,7 +1108,14 @@ HVB_HD void expand_item(const Dev<D>& dv, const T& tile, u64 item, u64* q_out, u
         q.R0sq = dotD<D>(w, w);
         q.a = dotD<D>(q.u, w);
     }
-    Best best = min_t_query<D, T>(dv, tile, q, ls);
+    return true;
+}
+
+// second half of a walk: the winner of the min-t query becomes an unbounded edge (stored here, returns false) or a
+// new vertex (sig2 sorted, r2; returns true)
+template <int D>
+HVB_HD bool ray_result(const Dev<D>& dv, int lane, const RayQ<D>& q, const int (&sig)[D + 1], u32 v, int kd, const Best& best,
+                       int (&sig2)[D + 1], double (&r2)[D], LocalStats& ls) {
     if (best.id < 0) {                       // unbounded edge (sysvoronoi.jl:504-511)
         if (lane == 0) {
             u32 pos = atom_add(dv.ray_count, 1u);
@@ -1121,11 +1125,10 @@ HVB_HD void expand_item(const Dev<D>& dv, const T& tile, u64 item, u64* q_out, u
                 for (int k = 0; k < D; ++k) dv.ray_u[(size_t)pos * D + k] = q.u[k];
             } else atom_or(&dv.ctr->flags, (u32)FLAG_RFULL);
         }
-        return;
+        return false;
     }
     if (best.t2 - best.t <= 1e-12 * fmax(best.t, sqrt(q.R0sq))) { ls.degenerate += (lane == 0); if (lane == 0) atom_or(&dv.ctr->flags, (u32)FLAG_DEGEN); }
     // new vertex: (sig minus position kd) plus the winner, kept sorted with static indexing
-    int sig2[D + 1];
     {
         int e[D];
         int pos = 0;
@@ -1141,10 +1144,29 @@ HVB_HD void expand_item(const Dev<D>& dv, const T& tile, u64 item, u64* q_out, u
             sig2[i] = (i < pos) ? lo_ : ((i == pos) ? best.id : hi_);
         }
     }
-    double r2[D];
 #pragma unroll
     for (int k = 0; k < D; ++k) r2[k] = q.r[k] + best.t * q.u[k];
-    commit_vertex<D, T>(dv, tile, sig2, r2, q_out, q_count, q_cap, ls);
+    return true;
+}
+
+template <int D, class T>
+HVB_HD void ray_finish(const Dev<D>& dv, const T& tile, const RayQ<D>& q, const int (&sig)[D + 1], u32 v, int kd, const Best& best,
+                       u64* q_out, u32* q_count, u32 q_cap, LocalStats& ls) {
+    int sig2[D + 1];
+    double r2[D];
+    if (ray_result<D>(dv, tile.lane(), q, sig, v, kd, best, sig2, r2, ls)) commit_vertex<D, T>(dv, tile, sig2, r2, q_out, q_count, q_cap, ls);
+}
+
+template <int D, class T>
+HVB_HD void expand_item(const Dev<D>& dv, const T& tile, u64 item, u64* q_out, u32* q_count, u32 q_cap, LocalStats& ls) {
+    // every lane of the tile works on the same snapshot of the entry (the closed bit was checked when it was acquired)
+    tile.sync();
+    int sig[D + 1];
+    RayQ<D> q;
+    u32 v; int kd;
+    if (!ray_setup<D>(dv, item, q, sig, v, kd)) { ls.seed_fail += (tile.lane() == 0); return; }
+    Best best = min_t_query<D, T>(dv, tile, q, ls);
+    ray_finish<D, T>(dv, tile, q, sig, v, kd, best, q_out, q_count, q_cap, ls);
 }
 
 // ------------------------------------------------------------------------------------------------------------

@@ -681,3 +681,5 @@ __global__ void k_merge_rows(const long long* __restrict__ sig_in, const double*
 }
 
 }  // namespace hvb
+
+#include "hvb_coop.cuh"

@@ -59,7 +59,11 @@ typedef struct hvb_params {
     int32_t tile_size;        /* lanes cooperating on one frontier entry: 1, 2, 4, 8, 16 or 32; 0 = auto by dimension */
     int32_t neighbors;        /* 1: hvb_search also builds and stages the neighbour lists (default 0: on first request);
                                  with world > 1 they are built from the slab result: complete for the rank's own cells */
-    int32_t persistent;       /* 1 (default): the frontier walk is one persistent launch with a device-side queue;
+    int32_t persistent;       /* the frontier walk.  3 (default): one persistent launch with a device-side queue; a warp takes
+                                 its tickets, vertex indices and queue slots with ONE atomic each, every lane runs the
+                                 min-t query of its own ray (tile_size 1 only);
+                                 2: the same launch with the warp-cooperative (pooled) query: correct, measured slower;
+                                 1: the persistent launch with one tile per ray from start to end (any tile_size);
                                  0: one launch per frontier round */
     int64_t vertex_capacity;  /* 0 = estimate from lowerbound(d,d) (edgeiteratebase.jl:151); grows on demand */
     double probe_scale;       /* first probe ball radius / circumradius of the origin vertex; 0 = auto */

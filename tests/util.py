@@ -20,13 +20,58 @@ def rel_coord_error(r_a, r_b, xs, sig):
     return float((np.linalg.norm(r_a - r_b, axis=1) / scale).max()) if len(sig) else 0.0
 
 
-def assert_same_mesh(got_sig, got_r, ref_sig, ref_r, xs, tol=1e-10):
-    """bit-exact combinatorics (rows already in lexicographic order on both sides), coordinates within tol relative"""
+def exact_vertex(xs, row, planes=None):
+    """the point equidistant to the generators / on the planes of `row` (1-based ids, plane p = n + p), solved in exact
+    rational arithmetic from the float inputs and rounded once: the arbiter for ill-conditioned vertices"""
+    from fractions import Fraction
+    n, d = xs.shape
+    F = lambda v: Fraction(float(v))
+    ids = [int(g) for g in row]
+    x0 = [F(v) for v in xs[ids[0] - 1]]
+    A, b = [], []
+    for g in ids[1:]:
+        if g <= n:
+            dx = [F(v) - x0k for v, x0k in zip(xs[g - 1], x0)]
+            A.append(dx); b.append(sum(t * t for t in dx) / 2)
+        else:
+            base, normal = planes
+            nrm = [F(v) for v in normal[g - n - 1]]
+            off = sum(nk * F(bk) for nk, bk in zip(nrm, base[g - n - 1]))
+            A.append(nrm); b.append(off - sum(nk * x0k for nk, x0k in zip(nrm, x0)))
+    M = [ai + [bi] for ai, bi in zip(A, b)]
+    for c in range(d):
+        pv = next(i for i in range(c, d) if M[i][c] != 0)
+        M[c], M[pv] = M[pv], M[c]
+        for i in range(d):
+            if i != c and M[i][c] != 0:
+                f = M[i][c] / M[c][c]
+                M[i] = [u - f * w for u, w in zip(M[i], M[c])]
+    return np.array([float(x0[k] + M[k][d] / M[k][k]) for k in range(d)])
+
+
+def assert_same_mesh(got_sig, got_r, ref_sig, ref_r, xs, tol=1e-10, planes=None):
+    """bit-exact combinatorics (rows already in lexicographic order on both sides), coordinates within tol relative.
+    The reference coordinates of a restated walk depend on which walk found the vertex (the multi-threaded oracle
+    differs from itself by 2e-10 on slivers of the d = 2 full-size cloud); where the two disagree by more than tol the
+    arbiter is the exact rational solution: the checked result must be within tol of THAT."""
     assert got_sig.shape == ref_sig.shape, (got_sig.shape, ref_sig.shape)
     assert np.array_equal(got_sig, ref_sig)
-    err = rel_coord_error(got_r, ref_r, xs, ref_sig)
-    assert err <= tol, err
-    return err
+    if not len(ref_sig):
+        return 0.0
+    x0 = xs[ref_sig[:, 0] - 1]
+    scale = np.maximum(np.linalg.norm(ref_r - x0, axis=1), 1e-300)
+    err = np.linalg.norm(got_r - ref_r, axis=1) / scale
+    bad = np.nonzero(err > tol)[0]
+    assert len(bad) <= 50, (len(bad), float(err.max()))
+    if planes is None and len(bad):
+        import qhull_oracle
+        planes = qhull_oracle.cuboid(xs.shape[1])
+    for v in bad:
+        ex = exact_vertex(xs, ref_sig[v], planes)
+        e2 = np.linalg.norm(got_r[v] - ex) / max(np.linalg.norm(ex - x0[v]), 1e-300)
+        assert e2 <= tol, (int(v), float(err[v]), float(e2))
+        err[v] = e2
+    return float(err.max())
 
 
 def neighbors_from_sig(sig, n):
