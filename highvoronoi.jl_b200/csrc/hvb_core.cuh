@@ -568,6 +568,20 @@ struct ScanState {
     bool rejected;         // FP64 refused a candidate that had tightened the bound: the stage is redone without tightening
 };
 
+HVB_HD int lowest_bit(unsigned m) {
+#if defined(__CUDA_ARCH__)
+    return __ffs((int)m) - 1;
+#else
+    int i = 0; while (!((m >> i) & 1u)) ++i; return i;
+#endif
+}
+HVB_HD float fast_div(float a, float b) {
+#if defined(__CUDA_ARCH__)
+    return __fdividef(a, b);
+#else
+    return a / b;
+#endif
+}
 HVB_HD float upper_2t(double t) { return (float)(2.0 * t * (1.0 + 4.8e-7)) * 1.0000005f; }
 
 // FP32 pass over the points [pa, pb) in chunks of four: all loads of a chunk are issued before any arithmetic.
@@ -588,8 +602,9 @@ HVB_HD void scan_points(const Dev<D>& dv, const RayQ<D>& q, const float (&uf)[D]
         float x[U][D];
 #pragma unroll
         for (int i = 0; i < U; ++i) load_x32<D>(dv.x32, (p + i < pb) ? (p + i) : (pb - 1), x[i]);
-        float nlo[U], nhi[U], dh[U], dl[U];
-        bool pass[U];
+        // only the two sums are kept per point; the four interval ends are rebuilt for the (few) survivors
+        float nms[U], dens[U];
+        unsigned pmask = 0;
 #pragma unroll
         for (int i = 0; i < U; ++i) {
             float den = 0.f, nm = 0.f;
@@ -599,26 +614,19 @@ HVB_HD void scan_points(const Dev<D>& dv, const RayQ<D>& q, const float (&uf)[D]
                 den = fmaf(uf[k], qk, den);
                 nm = fmaf(qk, qk - w2f[k], nm);
             }
-            nlo[i] = nm - flt.en; nhi[i] = nm + flt.en;
-            dh[i] = den + flt.ed; dl[i] = den - flt.ed;
-            pass[i] = (p + i < pb) && dh[i] > 0.f && nlo[i] <= flt.tb2 * dh[i];
+            nms[i] = nm; dens[i] = den;
+            const bool pass = (p + i < pb) && (den + flt.ed > 0.f) && (nm - flt.en <= flt.tb2 * (den + flt.ed));
+            pmask |= pass ? (1u << i) : 0u;
         }
         // survivors are handled one per loop trip, whatever their position in the chunk: the lanes of a warp that have
         // a survivor run this (branchy) bookkeeping together instead of position by position
-        unsigned pmask = 0;
-#pragma unroll
-        for (int i = 0; i < U; ++i) pmask |= pass[i] ? (1u << i) : 0u;
         while (pmask) {
-            int i = 0;
-#pragma unroll
-            for (int b = U - 1; b >= 0; --b) i = ((pmask >> b) & 1u) ? b : i;       // lowest set bit
+            const int i = lowest_bit(pmask);
             pmask &= pmask - 1u;
-            float nlo_i = nlo[0], nhi_i = nhi[0], dh_i = dh[0], dl_i = dl[0];
+            float nm_i = nms[0], den_i = dens[0];
 #pragma unroll
-            for (int b = 1; b < U; ++b) {
-                nlo_i = (i == b) ? nlo[b] : nlo_i; nhi_i = (i == b) ? nhi[b] : nhi_i;
-                dh_i = (i == b) ? dh[b] : dh_i; dl_i = (i == b) ? dl[b] : dl_i;
-            }
+            for (int b = 1; b < U; ++b) { nm_i = (i == b) ? nms[b] : nm_i; den_i = (i == b) ? dens[b] : den_i; }
+            const float nlo_i = nm_i - flt.en, nhi_i = nm_i + flt.en, dh_i = den_i + flt.ed, dl_i = den_i - flt.ed;
             if (!(nlo_i <= flt.tb2 * dh_i)) continue;                    // re-checked: the bound may have tightened within the chunk
             const int id = p + i;
             bool excluded = false;
@@ -631,8 +639,9 @@ HVB_HD void scan_points(const Dev<D>& dv, const RayQ<D>& q, const float (&uf)[D]
             int to_verify = -1;
             if (!bounded) to_verify = id;
             else {
-                float lo = nlo_i / dh_i; lo -= fabsf(lo) * 4e-7f;
-                float hi = nhi_i / dl_i * 1.000001f;
+                // approximate division (<= 2 ulp) inside margins of 6.7 / 16.8 ulp
+                float lo = fast_div(nlo_i, dh_i); lo -= fabsf(lo) * 4e-7f;
+                float hi = fast_div(nhi_i, dl_i) * 1.000001f;
                 if (hi < st.cb.hi) {
                     // new FP32 best; the old one stays as the rival if its interval still overlaps
                     if (st.cb.id >= 0 && st.cb.lo <= hi) {
@@ -699,16 +708,19 @@ HVB_HD Best min_t_query(const Dev<D>& dv, const T& tile, const RayQ<D>& q, Local
     plane_candidates<D>(dv, q, best);
 
     // ---- FP32 copies of the ray ---------------------------------------------------------------------------
-    float uf[D], w2f[D], x0f[D];
+    float uf[D], w2f[D], x0f[D], r32[D];
 #pragma unroll
     for (int k = 0; k < D; ++k) {
         uf[k] = (float)q.u[k];
         w2f[k] = (float)(2.0 * (q.r[k] - q.x0[k]));
         x0f[k] = (float)(q.x0[k] - dv.lo[k]);
+        r32[k] = (float)(q.r[k] - dv.lo[k]);
     }
     const double R0 = sqrt(q.R0sq);
     const double R0p = fmax(R0, 0.5 * dv.hmin);
     const double perp2 = fmax(q.R0sq - q.a * q.a, 0.0);       // squared distance of x0 to the ray's line
+    const float a32 = (float)q.a;
+    const float perp2f = (float)(perp2 * (1.0 + 1e-6)) * 1.000001f;
     double scale = dv.probe_scale;
     ScanState st;
     st.cb.id = -1; st.cb.lo = 0.f; st.cb.hi = INFINITY; st.cr.id = -1; st.cr.lo = 0.f; st.cr.hi = INFINITY;
@@ -752,9 +764,10 @@ HVB_HD Best min_t_query(const Dev<D>& dv, const T& tile, const RayQ<D>& q, Local
         if (!((float)(fabs(q.c) * 8e-12) < flt.ed)) st.tighten = false;
         const double Ts0 = Ts;
         // FP32 row geometry while the ball is comparable to the cloud; FP64 for the huge balls of unbounded edges
-        double cmax = 0;
+        double cmax = 0;                      // the centres of the shrinking ball lie between r and cen
 #pragma unroll
-        for (int k = 0; k < D; ++k) cmax = fmax(cmax, fabs(cen[k] - dv.lo[k]));
+        for (int k = 0; k < D; ++k) cmax = fmax(cmax, fmax(fabs(cen[k] - dv.lo[k]), fabs(q.r[k] - dv.lo[k])));
+        float Ts32 = halfspace_mode ? INFINITY : (float)Ts * 1.0000002f;
         const bool use32 = !halfspace_mode && rho < 32.0 * dv.diag && cmax < 32.0 * dv.diag && nrows < (1 << 22);
         Ball32<D> b32;
         if (use32) {
@@ -787,18 +800,27 @@ HVB_HD Best min_t_query(const Dev<D>& dv, const T& tile, const RayQ<D>& q, Local
 #pragma unroll
                     for (int m = T::SIZE / 2; m >= 1; m >>= 1) flt.tb2 = fminf(flt.tb2, tile.shfl_xor(flt.tb2, m));
                 }
-                const double Tshr = fmin(best.t, 0.5 * (double)flt.tb2);
-                if (Tshr < 0.92 * Ts) {
-                    Ts = Tshr;
-#pragma unroll
-                    for (int k = 0; k < D; ++k) cen[k] = q.r[k] + Ts * q.u[k];
-                    rho2 = (q.R0sq - 2.0 * Ts * q.a + Ts * Ts) * (1.0 + 1e-12) + 1e-300;
-                    rho = sqrt(rho2);
-                    { float keep = flt.tb2; flt = make_filter<D>(Ts, rho, R0, dv.ext); flt.tb2 = fminf(flt.tb2, keep); }
-                    if (use32) {
-#pragma unroll
-                        for (int k = 0; k < D; ++k) b32.cen[k] = (float)(cen[k] - dv.lo[k]);
-                        b32.rho2 = (float)(rho2 * (1.0 + 1e-5)) * 1.000001f;
+                // shrink the ball to the best bound so far (tb2 / 2 bounds the winner once a candidate tightened it).  With
+                // the FP32 row geometry this is FP32 arithmetic on rounded-up quantities (the ball only selects cells, a
+                // superset is all it has to be); the filter constants of the larger ball stay valid bounds
+                if (use32) {
+                    const float tsh = fminf((float)best.t * 1.0000002f, 0.5f * flt.tb2 * 1.000001f);
+                    if (tsh < 0.92f * Ts32) {
+                        Ts32 = tsh;
+    #pragma unroll
+                        for (int k = 0; k < D; ++k) b32.cen[k] = fmaf(Ts32, uf[k], r32[k]);
+                        const float dT = fabsf(Ts32 - a32) + 4e-7f * (fabsf(a32) + Ts32);
+                        b32.rho2 = fmaf(dT, dT, perp2f) * 1.00001f;
+                    }
+                } else {
+                    const double Tshr = fmin(best.t, 0.5 * (double)flt.tb2);
+                    if (Tshr < 0.92 * Ts) {
+                        Ts = Tshr;
+    #pragma unroll
+                        for (int k = 0; k < D; ++k) cen[k] = q.r[k] + Ts * q.u[k];
+                        rho2 = (q.R0sq - 2.0 * Ts * q.a + Ts * Ts) * (1.0 + 1e-12) + 1e-300;
+                        rho = sqrt(rho2);
+                        { float keep = flt.tb2; flt = make_filter<D>(Ts, rho, R0, dv.ext); flt.tb2 = fminf(flt.tb2, keep); }
                     }
                 }
             }
@@ -820,18 +842,27 @@ HVB_HD Best min_t_query(const Dev<D>& dv, const T& tile, const RayQ<D>& q, Local
 #pragma unroll
                 for (int m = T::SIZE / 2; m >= 1; m >>= 1) flt.tb2 = fminf(flt.tb2, tile.shfl_xor(flt.tb2, m));
             }
-            const double Tshr = fmin(best.t, 0.5 * (double)flt.tb2);     // tb2 / 2 bounds the winner once a candidate tightened it
-            if (Tshr < 0.92 * Ts) {
-                Ts = Tshr;
+            // shrink the ball to the best bound so far (tb2 / 2 bounds the winner once a candidate tightened it).  With
+            // the FP32 row geometry this is FP32 arithmetic on rounded-up quantities (the ball only selects cells, a
+            // superset is all it has to be); the filter constants of the larger ball stay valid bounds
+            if (use32) {
+                const float tsh = fminf((float)best.t * 1.0000002f, 0.5f * flt.tb2 * 1.000001f);
+                if (tsh < 0.92f * Ts32) {
+                    Ts32 = tsh;
 #pragma unroll
-                for (int k = 0; k < D; ++k) cen[k] = q.r[k] + Ts * q.u[k];
-                rho2 = (q.R0sq - 2.0 * Ts * q.a + Ts * Ts) * (1.0 + 1e-12) + 1e-300;
-                rho = sqrt(rho2);
-                { float keep = flt.tb2; flt = make_filter<D>(Ts, rho, R0, dv.ext); flt.tb2 = fminf(flt.tb2, keep); }
-                if (use32) {
+                    for (int k = 0; k < D; ++k) b32.cen[k] = fmaf(Ts32, uf[k], r32[k]);
+                    const float dT = fabsf(Ts32 - a32) + 4e-7f * (fabsf(a32) + Ts32);
+                    b32.rho2 = fmaf(dT, dT, perp2f) * 1.00001f;
+                }
+            } else {
+                const double Tshr = fmin(best.t, 0.5 * (double)flt.tb2);
+                if (Tshr < 0.92 * Ts) {
+                    Ts = Tshr;
 #pragma unroll
-                    for (int k = 0; k < D; ++k) b32.cen[k] = (float)(cen[k] - dv.lo[k]);
-                    b32.rho2 = (float)(rho2 * (1.0 + 1e-5)) * 1.000001f;
+                    for (int k = 0; k < D; ++k) cen[k] = q.r[k] + Ts * q.u[k];
+                    rho2 = (q.R0sq - 2.0 * Ts * q.a + Ts * Ts) * (1.0 + 1e-12) + 1e-300;
+                    rho = sqrt(rho2);
+                    { float keep = flt.tb2; flt = make_filter<D>(Ts, rho, R0, dv.ext); flt.tb2 = fminf(flt.tb2, keep); }
                 }
             }
         }
