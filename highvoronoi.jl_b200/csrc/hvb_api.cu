@@ -141,7 +141,13 @@ struct Ctx : hvb_ctx {
     bool persistent = true;          // single-launch walk (k_walk) instead of one launch per frontier round (prm.persistent)
     bool coop = true;                // prm.persistent == 2: the warp-cooperative query (k_walk_coop), lane-per-ray tiles only
     cudaStream_t stream = nullptr, sstream = nullptr;    // compute stream, result-staging (D2H) stream
-    cudaEvent_t ev_stage = nullptr;
+    cudaStream_t nstream = nullptr;                      // neighbour lists, built next to the row sort (both read the unsorted rows)
+    cudaStream_t sstream2 = nullptr;                     // staging of the neighbour lists (whichever of rows / lists is ready first goes first)
+    cudaEvent_t ev_stage = nullptr, ev_rows = nullptr, ev_nb = nullptr;
+    struct NbScalars { u32 pflags; u32 pad; };
+    DBuf<NbScalars> nbsc;
+    HBuf<NbScalars> h_nbsc;
+    HBuf<long long> h_nbtotal;
     int sms = 148;
     Dev<D> dv;
     int64_t ncells = 0;
@@ -151,7 +157,8 @@ struct Ctx : hvb_ctx {
     DBuf<int> perm, inv, cell_of, cell_start, cell_cur, unseeded_list;
     DBuf<PlaneSet> planes;
     DBuf<unsigned char> active, has_vertex;
-    DBuf<char> cub_tmp;
+    DBuf<char> cub_tmp, nb_cub_tmp;
+    cudaStream_t nb_ns = nullptr;     // the stream the current neighbour lists were built on
     DBuf<double> bbox_partial;
     // search state
     int64_t vcap = 0;
@@ -199,7 +206,7 @@ struct Ctx : hvb_ctx {
         cudaSetDevice(prm.device);
         if (stream) cudaStreamSynchronize(stream);
         xs_in.release(); x64.release(); x32.release(); perm.release(); inv.release(); cell_of.release(); cell_start.release();
-        cell_cur.release(); unseeded_list.release(); bbox_partial.release(); planes.release(); active.release(); has_vertex.release(); cub_tmp.release();
+        nb_cub_tmp.release(); cell_cur.release(); unseeded_list.release(); bbox_partial.release(); planes.release(); active.release(); has_vertex.release(); cub_tmp.release();
         vsig.release(); vr.release(); vtab.release(); etab.release(); q[0].release(); q[1].release(); ray_item.release(); ray_u.release();
         ctr.release(); sc.release(); h_sc.release(); h_ctr.release(); h_extra.release(); cells_dev.release(); seed_sig_dev.release(); seed_r_dev.release();
         out_sig[0].release(); out_sig[1].release(); out_r[0].release(); out_r[1].release(); key_top.release(); key_hi.release(); key_lo.release(); key_tmp.release();
@@ -211,11 +218,17 @@ struct Ctx : hvb_ctx {
         if (ev_c) cudaEventDestroy(ev_c);
         if (ev_d) cudaEventDestroy(ev_d);
         if (ev_sd) cudaEventDestroy(ev_sd);
+        if (ev_sd2) cudaEventDestroy(ev_sd2);
         if (ev_s0) cudaEventDestroy(ev_s0);
         if (ev_s1) cudaEventDestroy(ev_s1);
         if (ev_n0) cudaEventDestroy(ev_n0);
         if (ev_n1) cudaEventDestroy(ev_n1);
         if (ev_stage) cudaEventDestroy(ev_stage);
+        if (ev_rows) cudaEventDestroy(ev_rows);
+        if (ev_nb) cudaEventDestroy(ev_nb);
+        nbsc.release(); h_nbsc.release(); h_nbtotal.release();
+        if (nstream) { cudaStreamSynchronize(nstream); cudaStreamDestroy(nstream); }
+        if (sstream2) { cudaStreamSynchronize(sstream2); cudaStreamDestroy(sstream2); }
         if (ev_p0) cudaEventDestroy(ev_p0);
         if (ev_p1) cudaEventDestroy(ev_p1);
         halo_cnt.release(); halo_off.release(); halo_origin.release(); halo_mult.release(); vflags.release(); cert.release(); h_cert.release();
@@ -250,7 +263,16 @@ struct Ctx : hvb_ctx {
         CK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, prm.device));
         CK(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
         CK(cudaStreamCreateWithFlags(&sstream, cudaStreamNonBlocking));
+        CK(cudaStreamCreateWithFlags(&sstream2, cudaStreamNonBlocking));
+        {   // the neighbour build yields to the compute stream (the row sort gates the large staging copy)
+            int prio_lo = 0, prio_hi = 0;
+            CK(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
+            CK(cudaStreamCreateWithPriority(&nstream, cudaStreamNonBlocking, prio_lo));
+        }
         CK(cudaEventCreateWithFlags(&ev_stage, cudaEventDisableTiming));
+        CK(cudaEventCreateWithFlags(&ev_rows, cudaEventDisableTiming));
+        CK(cudaEventCreateWithFlags(&ev_nb, cudaEventDisableTiming));
+        CK(nbsc.ensure(1)); CK(h_nbsc.ensure(1)); CK(h_nbtotal.ensure(1));
         CK(cudaEventCreate(&ev_a)); CK(cudaEventCreate(&ev_b)); CK(cudaEventCreate(&ev_c)); CK(cudaEventCreate(&ev_d));
         CK(cudaEventCreate(&ev_s0)); CK(cudaEventCreate(&ev_s1)); CK(cudaEventCreate(&ev_n0)); CK(cudaEventCreate(&ev_n1));
         CK(cudaEventCreate(&ev_p0)); CK(cudaEventCreate(&ev_p1));
@@ -782,16 +804,23 @@ struct Ctx : hvb_ctx {
         // vertices the rows are staged after the filtering pass
         if (world == 1 && !second_pass) { rc = stage(); if (rc) return rc; }
         have_result = true;
-        CK(cudaEventRecord(ev_n0, stream));
-        // with seed vertices the lists must be built now, from all rows, before the caller's own vertices are dropped
-        if (prm.neighbors || seed_prefix > 0) { rc = build_neighbors(); if (rc) return rc; }
+        // The lists are built from the UNSORTED rows (a set of pairs does not care about the row order) on their own stream,
+        // next to the radix sort of the rows that finalize() has just queued on the compute stream.
+        // With seed vertices the lists must be built now, from all rows, before the caller's own vertices are dropped
+        CK(cudaStreamWaitEvent(nstream, ev_rows, 0));
+        CK(cudaEventRecord(ev_n0, nstream));
+        if (prm.neighbors || seed_prefix > 0) { rc = build_neighbors(nstream, out_sig[0].p); if (rc) return rc; }
         if (prm.neighbors) { rc = stage_neighbors(); if (rc) return rc; }
+        CK(cudaEventRecord(ev_n1, nstream));
+        CK(cudaStreamWaitEvent(stream, ev_n1, 0));
         if (second_pass) { rc = finalize_owned(by_slab); if (rc) return rc; if (world == 1) { rc = stage(); if (rc) return rc; } }
-        CK(cudaEventRecord(ev_n1, stream));
         // ev_d: the result (rows, neighbour lists) is complete in HBM.  The page-locked staging copies run on their own
         // stream and are waited for here, outside ms_finalize: they belong to the end-to-end time, not to the search
         CK(cudaEventRecord(ev_d, stream));
         CK(cudaStreamWaitEvent(stream, ev_stage_done(), 0));
+        if (!ev_sd2) CK(cudaEventCreateWithFlags(&ev_sd2, cudaEventDisableTiming));
+        CK(cudaEventRecord(ev_sd2, sstream2));
+        CK(cudaStreamWaitEvent(stream, ev_sd2, 0));
         CK(cudaEventRecord(ev_p1, stream));
         CK(cudaStreamSynchronize(stream));
         CK(cudaGetLastError());
@@ -868,6 +897,7 @@ struct Ctx : hvb_ctx {
         }
         int rc = read_scalars(); if (rc) return rc;
         nvert = h_sc.p->out_count;
+        CK(cudaEventRecord(ev_rows, stream));            // the unsorted rows are complete: the neighbour build may start
         if (second_pass) { res = 0; return HVB_OK; }     // a filtering pass follows (slab ownership / seed vertices): it sorts
         return sort_rows((u32)nvert, bits);
     }
@@ -903,7 +933,7 @@ struct Ctx : hvb_ctx {
         return HVB_OK;
     }
 
-    cudaEvent_t ev_sd = nullptr;
+    cudaEvent_t ev_sd = nullptr, ev_sd2 = nullptr;
     cudaEvent_t ev_stage_done() {          // an event on the staging stream that marks "everything staged so far is in host memory"
         if (!ev_sd) cudaEventCreateWithFlags(&ev_sd, cudaEventDisableTiming);
         cudaEventRecord(ev_sd, sstream);
@@ -956,9 +986,12 @@ struct Ctx : hvb_ctx {
         return HVB_OK;
     }
 
-    int build_neighbors() {
+    // neighbour lists from `rows` (nvert rows of sorted caller ids, in any order) on stream `ns`
+    int build_neighbors(cudaStream_t ns = nullptr, const long long* rows = nullptr) {
         if (nb_total >= 0) return HVB_OK;
         CK(cudaSetDevice(prm.device));
+        if (!ns) ns = stream;
+        if (!rows) rows = out_sig[res].p;
         nb_staged = false;
         CK(deg.ensure(n)); CK(ncur.ensure(n)); CK(nb_off.ensure(n + 1));
         static const double nb_est[7] = {0, 0, 8, 20, 48, 120, 320};
@@ -969,29 +1002,35 @@ struct Ctx : hvb_ctx {
         // memset + the fill pass touch a quarter of what an entry-per-list-element table would need
         u64 want = next_pow2((u64)std::min((double)nvert * D * (D + 1) / 2.0 * 2.0, (double)n_list * nb_est[D]) + 1024);
         long long total = 0;
+        size_t tmp_bytes = 0;
+        CK(cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, nb_off.p, nb_off.p, (int)(n + 1), ns));
+        CK(nb_cub_tmp.ensure(tmp_bytes));
         for (int attempt = 0; attempt < 8; ++attempt) {
             CK(ptab.ensure(want));
-            CK(cudaMemsetAsync(ptab.p, 0, want * sizeof(u64), stream));
-            CK(cudaMemsetAsync(deg.p, 0, n * sizeof(u32), stream));
-            CK(cudaMemsetAsync(&sc.p->pflags, 0, sizeof(u32), stream));
-            if (nvert > 0) { k_pairs<D><<<blocks_for(nvert, 128), 128, 0, stream>>>(out_sig[res].p, (u32)nvert, n_list, ptab.p, want - 1, deg.p, &sc.p->pflags); ++launches; }
+            CK(cudaMemsetAsync(ptab.p, 0, want * sizeof(u64), ns));
+            CK(cudaMemsetAsync(deg.p, 0, n * sizeof(u32), ns));
+            CK(cudaMemsetAsync(nbsc.p, 0, sizeof(NbScalars), ns));
+            if (nvert > 0) { k_pairs<D><<<blocks_for(nvert, 128), 128, 0, ns>>>(rows, (u32)nvert, n_list, ptab.p, want - 1, deg.p, &nbsc.p->pflags); ++launches; }
             // offsets = exclusive scan of the degrees (as int64); one host round trip brings the overflow flag and the total
-            k_u32_to_i64<<<blocks_for(n, 256), 256, 0, stream>>>(deg.p, nb_off.p, n); ++launches;
-            CK(cudaMemsetAsync(nb_off.p + n, 0, sizeof(long long), stream));
-            size_t tmp_bytes = 0;
-            CK(cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, nb_off.p, nb_off.p, (int)(n + 1), stream));
-            CK(cub_tmp.ensure(tmp_bytes));
-            CK(cub::DeviceScan::ExclusiveSum(cub_tmp.p, tmp_bytes, nb_off.p, nb_off.p, (int)(n + 1), stream));
-            int rc = read_scalars(nb_off.p + n, &total); if (rc) return rc;
-            if (!(h_sc.p->pflags & 8u)) break;
+            k_u32_to_i64<<<blocks_for(n, 256), 256, 0, ns>>>(deg.p, nb_off.p, n); ++launches;
+            CK(cudaMemsetAsync(nb_off.p + n, 0, sizeof(long long), ns));
+            CK(cub::DeviceScan::ExclusiveSum(nb_cub_tmp.p, tmp_bytes, nb_off.p, nb_off.p, (int)(n + 1), ns));
+            k_publish<<<1, 32, 0, ns>>>((const u32*)nbsc.p, (u32*)h_nbsc.p, (int)(sizeof(NbScalars) / 4), nullptr, nullptr, 0, nb_off.p + n, h_nbtotal.p);
+            ++launches;
+            CK(cudaStreamSynchronize(ns));
+            total = *h_nbtotal.p;
+            if (!(h_nbsc.p->pflags & 8u)) break;
             want *= 4;
             if (attempt == 7) { err = "neighbour pair table overflow"; return HVB_ENOMEM; }
         }
         CK(nb_ids.ensure(std::max<long long>(total, 1)));
-        CK(cudaMemsetAsync(ncur.p, 0, n * sizeof(u32), stream));
-        k_pair_fill<<<blocks_for((int64_t)want, 256), 256, 0, stream>>>(ptab.p, want, n_list, nb_off.p, ncur.p, nb_ids.p); ++launches;
-        k_sort_lists<<<blocks_for(n, 128), 128, 0, stream>>>(nb_off.p, nb_ids.p, n); ++launches;
+        CK(cudaMemsetAsync(ncur.p, 0, n * sizeof(u32), ns));
+        k_pair_fill<<<blocks_for((int64_t)want, 256), 256, 0, ns>>>(ptab.p, want, n_list, nb_off.p, ncur.p, nb_ids.p); ++launches;
+        k_sort_lists<<<blocks_for(n, 128), 128, 0, ns>>>(nb_off.p, nb_ids.p, n); ++launches;
         CK(cudaGetLastError());          // no host wait here: the staging copy / the fetch calls order themselves behind the stream
+        CK(cudaEventRecord(ev_nb, ns));
+        CK(cudaStreamWaitEvent(stream, ev_nb, 0));       // whatever the compute stream does next sees the lists
+        nb_ns = ns;
         nb_total = total;
         st.kernel_launches = launches;
         return HVB_OK;
@@ -1005,10 +1044,9 @@ struct Ctx : hvb_ctx {
     int stage_neighbors() {
         if (nb_staged) return HVB_OK;
         CK(h_nb_off.ensure(n + 1)); CK(h_nb_ids.ensure(std::max<int64_t>(nb_total, 1)));
-        CK(cudaEventRecord(ev_stage, stream));
-        CK(cudaStreamWaitEvent(sstream, ev_stage, 0));
-        CK(cudaMemcpyAsync(h_nb_off.p, nb_off.p, (size_t)(n + 1) * 8, cudaMemcpyDeviceToHost, sstream));
-        if (nb_total > 0) CK(cudaMemcpyAsync(h_nb_ids.p, nb_ids.p, (size_t)nb_total * 8, cudaMemcpyDeviceToHost, sstream));
+        CK(cudaStreamWaitEvent(sstream2, ev_nb, 0));
+        CK(cudaMemcpyAsync(h_nb_off.p, nb_off.p, (size_t)(n + 1) * 8, cudaMemcpyDeviceToHost, sstream2));
+        if (nb_total > 0) CK(cudaMemcpyAsync(h_nb_ids.p, nb_ids.p, (size_t)nb_total * 8, cudaMemcpyDeviceToHost, sstream2));
         nb_staged = true;
         return HVB_OK;
     }
@@ -1017,7 +1055,7 @@ struct Ctx : hvb_ctx {
         int rc = build_neighbors(); if (rc) return rc;
         rc = stage_neighbors(); if (rc) return rc;
         CK(cudaStreamSynchronize(stream));
-        CK(cudaStreamSynchronize(sstream));
+        CK(cudaStreamSynchronize(sstream2));
         *off = (const int64_t*)h_nb_off.p; *ids = (const int64_t*)h_nb_ids.p; *total = nb_total;
         return HVB_OK;
     }

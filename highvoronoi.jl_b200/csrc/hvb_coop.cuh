@@ -47,11 +47,11 @@ __device__ __forceinline__ bool coop_zrange(const Dev<D>& dv, const CoopShared<D
     const float ul = sh.uf[L][o], x0L = sh.x0f[L][o];
     const float cenL = fmaf(Ts, ul, sh.r32[L][o]);
     float zlo = cenL - s, zhi = cenL + s;
-    const float slack = m * (uabs + fabsf(ul)) + 1e-5f * fabsf(umax) + 1e-6f * (float)dv.ext;
+    const float slack = m * (uabs + fabsf(ul)) + 1e-5f * fabsf(umax) + 1e-6f * dv.ext32;
     if (ul > 1e-3f) zlo = fmaxf(zlo, x0L - (umax + slack) / ul * 1.00001f - m);
     else if (ul < -1e-3f) zhi = fminf(zhi, x0L - (umax + slack) / ul * 1.00001f + m);
-    else if (umax + slack + fabsf(ul) * (float)dv.ext * 2.f <= 0.f) return false;
-    const float ihl = (float)dv.inv_h[L];
+    else if (umax + slack + fabsf(ul) * dv.ext32 * 2.f <= 0.f) return false;
+    const float ihl = dv.inv_h32[L];
     const float gl = (float)dv.g[L];
     const float vlo = fminf(fmaxf(zlo * ihl - 2e-3f, 0.f), gl - 1.f);
     const float vhi = fminf(fmaxf(zhi * ihl + 2e-3f, -1.f), gl - 1.f);
@@ -66,7 +66,7 @@ __device__ __forceinline__ bool coop_zrange(const Dev<D>& dv, const CoopShared<D
 template <int D>
 __device__ __forceinline__ void coop_axis(const Dev<D>& dv, const CoopShared<D>& sh, int o, int k, int c, float Ts, float m,
                                           float& d2, float& umax, float& uabs, int& base) {
-    const float hk = (float)dv.h[k];
+    const float hk = dv.h32[k];
     const float blo = (float)c * hk - m;
     const float bhi = blo + hk + 2.f * m;
     const float ufk = sh.uf[k][o], x0k = sh.x0f[k][o];
@@ -127,7 +127,7 @@ __device__ __forceinline__ void coop_scan(const Dev<D>& dv, CoopShared<D>& sh, L
                 const int A = D - 2;
                 const float s = sqrtf(rho2 - d2) * 1.000001f + m;
                 const float cenA = fmaf(Ts, sh.uf[A][o], sh.r32[A][o]);
-                const float iha = (float)dv.inv_h[A];
+                const float iha = dv.inv_h32[A];
                 const int blo = sh.clo[A][o], bhi = blo + sh.ext[A][o] - 1;
                 const float vlo = fminf(fmaxf((cenA - s) * iha - 2e-3f, (float)blo), (float)bhi);
                 const float vhi = fminf(fmaxf((cenA + s) * iha + 2e-3f, (float)blo - 1.f), (float)bhi);

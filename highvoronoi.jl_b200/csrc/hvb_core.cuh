@@ -162,6 +162,8 @@ struct Dev {
     int g[D];                          // cells per axis (linear index: axis D-1 fastest)
     double hmin, diag;                 // smallest cell edge, diagonal of the bounding box
     double ext;                        // largest bounding-box extent: scale of the FP32 coordinate error
+    float h32[D], inv_h32[D], ext32;   // (float) of h, inv_h, ext: the FP32 row geometry must not convert them per row
+    int pad32;
     const int* cell_start;             // [ncells + 1]
     const float* x32;                  // [n][X32<D>::STRIDE]  coordinates minus lo, FP32, padded (filter)
     const double* x64;                 // [n][D]  coordinates, FP64 (verification)
@@ -428,7 +430,7 @@ HVB_HD bool row_range32(const Dev<D>& dv, const float (&uf)[D], const float (&x0
     }
 #pragma unroll
     for (int k = 0; k < D - 1; ++k) {
-        float hk = (float)dv.h[k];
+        float hk = dv.h32[k];
         float blo = (float)cc[k] * hk - b.m;
         float bhi = blo + hk + 2.f * b.m;
         float dd = fmaxf(0.f, fmaxf(blo - b.cen[k], b.cen[k] - bhi));
@@ -442,11 +444,11 @@ HVB_HD bool row_range32(const Dev<D>& dv, const float (&uf)[D], const float (&x0
     float s = sqrtf(b.rho2 - d2) * 1.000001f + b.m;
     float zlo = b.cen[L] - s, zhi = b.cen[L] + s;
     float ul = uf[L];
-    float slack = b.m * (uabs + fabsf(ul)) + 1e-5f * fabsf(umax) + 1e-6f * (float)dv.ext;
+    float slack = b.m * (uabs + fabsf(ul)) + 1e-5f * fabsf(umax) + 1e-6f * dv.ext32;
     if (ul > 1e-3f) zlo = fmaxf(zlo, x0f[L] - (umax + slack) / ul * 1.00001f - b.m);
     else if (ul < -1e-3f) zhi = fminf(zhi, x0f[L] - (umax + slack) / ul * 1.00001f + b.m);
-    else if (umax + slack + fabsf(ul) * (float)dv.ext * 2.f <= 0.f) return false;
-    float ihl = (float)dv.inv_h[L];
+    else if (umax + slack + fabsf(ul) * dv.ext32 * 2.f <= 0.f) return false;
+    float ihl = dv.inv_h32[L];
     float gl = (float)dv.g[L];
     float vlo = fminf(fmaxf(zlo * ihl - 2e-3f, 0.f), gl - 1.f);
     float vhi = fminf(fmaxf(zhi * ihl + 2e-3f, -1.f), gl - 1.f);
@@ -484,7 +486,7 @@ HVB_HD int row_try32(const Dev<D>& dv, const float (&uf)[D], const float (&x0f)[
         int e = chi[k] - clo[k] + 1;
         int c = clo[k] + dg[k];
         prefix = prefix * e + dg[k];
-        float hk = (float)dv.h[k];
+        float hk = dv.h32[k];
         float blo = (float)c * hk - b.m;
         float bhi = blo + hk + 2.f * b.m;
         float dd = fmaxf(0.f, fmaxf(blo - b.cen[k], b.cen[k] - bhi));
@@ -498,11 +500,11 @@ HVB_HD int row_try32(const Dev<D>& dv, const float (&uf)[D], const float (&x0f)[
     float s = sqrtf(b.rho2 - d2) * 1.000001f + b.m;
     float zlo = b.cen[L] - s, zhi = b.cen[L] + s;
     float ul = uf[L];
-    float slack = b.m * (uabs + fabsf(ul)) + 1e-5f * fabsf(umax) + 1e-6f * (float)dv.ext;
+    float slack = b.m * (uabs + fabsf(ul)) + 1e-5f * fabsf(umax) + 1e-6f * dv.ext32;
     if (ul > 1e-3f) zlo = fmaxf(zlo, x0f[L] - (umax + slack) / ul * 1.00001f - b.m);
     else if (ul < -1e-3f) zhi = fminf(zhi, x0f[L] - (umax + slack) / ul * 1.00001f + b.m);
-    else if (umax + slack + fabsf(ul) * (float)dv.ext * 2.f <= 0.f) return j + 1;
-    float ihl = (float)dv.inv_h[L];
+    else if (umax + slack + fabsf(ul) * dv.ext32 * 2.f <= 0.f) return j + 1;
+    float ihl = dv.inv_h32[L];
     float gl = (float)dv.g[L];
     float vlo = fminf(fmaxf(zlo * ihl - 2e-3f, 0.f), gl - 1.f);
     float vhi = fminf(fmaxf(zhi * ihl + 2e-3f, -1.f), gl - 1.f);
@@ -719,8 +721,16 @@ HVB_HD Best min_t_query(const Dev<D>& dv, const T& tile, const RayQ<D>& q, Local
     const double R0 = sqrt(q.R0sq);
     const double R0p = fmax(R0, 0.5 * dv.hmin);
     const double perp2 = fmax(q.R0sq - q.a * q.a, 0.0);       // squared distance of x0 to the ray's line
-    const float a32 = (float)q.a;
-    const float perp2f = (float)(perp2 * (1.0 + 1e-6)) * 1.000001f;
+    float a32 = (float)q.a;
+    float perp2f = (float)(perp2 * (1.0 + 1e-6)) * 1.000001f;
+#if defined(__CUDA_ARCH__)
+    // Without this the compiler re-derives the FP32 copies from the doubles at their uses inside the scan loops
+    // (FP64 subtract + FP64->FP32 conversion per use: 12 % of the warp instructions at d = 5,
+    // profiles/r1_srcprofile_k_walk.md): values that come out of an asm statement cannot be rematerialised.
+#pragma unroll
+    for (int k = 0; k < D; ++k) asm volatile("" : "+f"(uf[k]), "+f"(w2f[k]), "+f"(x0f[k]), "+f"(r32[k]));
+    asm volatile("" : "+f"(a32), "+f"(perp2f));
+#endif
     double scale = dv.probe_scale;
     ScanState st;
     st.cb.id = -1; st.cb.lo = 0.f; st.cb.hi = INFINITY; st.cr.id = -1; st.cr.lo = 0.f; st.cr.hi = INFINITY;

@@ -58,8 +58,11 @@ inline int64_t setup_grid(Dev<D>& dv, const double* blo, const double* bhi, int6
         dv.h[k] = ext[k] / dv.g[k];
         dv.inv_h[k] = 1.0 / dv.h[k];
         dv.hmin = std::min(dv.hmin, dv.h[k]);
+        dv.h32[k] = (float)dv.h[k];
+        dv.inv_h32[k] = (float)dv.inv_h[k];
     }
     dv.ext = emax;
+    dv.ext32 = (float)emax;
     dv.diag = sqrt(diag2) > 0 ? sqrt(diag2) : 1.0;
     return cells;
 }
