@@ -143,7 +143,7 @@ struct Ctx : hvb_ctx {
     cudaStream_t stream = nullptr, sstream = nullptr;    // compute stream, result-staging (D2H) stream
     cudaStream_t nstream = nullptr;                      // neighbour lists, built next to the row sort (both read the unsorted rows)
     cudaStream_t sstream2 = nullptr;                     // staging of the neighbour lists (whichever of rows / lists is ready first goes first)
-    cudaEvent_t ev_stage = nullptr, ev_rows = nullptr, ev_nb = nullptr;
+    cudaEvent_t ev_stage = nullptr, ev_nb = nullptr;
     struct NbScalars { u32 pflags; u32 pad; };
     DBuf<NbScalars> nbsc;
     HBuf<NbScalars> h_nbsc;
@@ -158,7 +158,6 @@ struct Ctx : hvb_ctx {
     DBuf<PlaneSet> planes;
     DBuf<unsigned char> active, has_vertex;
     DBuf<char> cub_tmp, nb_cub_tmp;
-    cudaStream_t nb_ns = nullptr;     // the stream the current neighbour lists were built on
     DBuf<double> bbox_partial;
     // search state
     int64_t vcap = 0;
@@ -177,7 +176,6 @@ struct Ctx : hvb_ctx {
     HBuf<long long> h_extra;
     DBuf<long long> cells_dev, seed_sig_dev;
     DBuf<double> seed_r_dev;
-    bool second_pass = false;         // the rows are filtered after the neighbour lists were built from all of them
     u32 seed_prefix = 0;              // vertex records [0, seed_prefix) are the caller's own vertices (not returned)
     // results
     DBuf<long long> out_sig[2];
@@ -224,7 +222,6 @@ struct Ctx : hvb_ctx {
         if (ev_n0) cudaEventDestroy(ev_n0);
         if (ev_n1) cudaEventDestroy(ev_n1);
         if (ev_stage) cudaEventDestroy(ev_stage);
-        if (ev_rows) cudaEventDestroy(ev_rows);
         if (ev_nb) cudaEventDestroy(ev_nb);
         nbsc.release(); h_nbsc.release(); h_nbtotal.release();
         if (nstream) { cudaStreamSynchronize(nstream); cudaStreamDestroy(nstream); }
@@ -270,7 +267,6 @@ struct Ctx : hvb_ctx {
             CK(cudaStreamCreateWithPriority(&nstream, cudaStreamNonBlocking, prio_lo));
         }
         CK(cudaEventCreateWithFlags(&ev_stage, cudaEventDisableTiming));
-        CK(cudaEventCreateWithFlags(&ev_rows, cudaEventDisableTiming));
         CK(cudaEventCreateWithFlags(&ev_nb, cudaEventDisableTiming));
         CK(nbsc.ensure(1)); CK(h_nbsc.ensure(1)); CK(h_nbtotal.ensure(1));
         CK(cudaEventCreate(&ev_a)); CK(cudaEventCreate(&ev_b)); CK(cudaEventCreate(&ev_c)); CK(cudaEventCreate(&ev_d));
@@ -797,23 +793,23 @@ struct Ctx : hvb_ctx {
         }
         CK(cudaEventRecord(ev_b, stream));
         const bool by_slab = world > 1 && cells == nullptr;
-        second_pass = by_slab || seed_prefix > 0;
-        int rc = finalize(); if (rc) return rc;
-        CK(cudaEventRecord(ev_c, stream));
-        // a slab result is an intermediate: it is exported to the exchange step, not staged for the host; with seed
-        // vertices the rows are staged after the filtering pass
-        if (world == 1 && !second_pass) { rc = stage(); if (rc) return rc; }
-        have_result = true;
-        // The lists are built from the UNSORTED rows (a set of pairs does not care about the row order) on their own stream,
-        // next to the radix sort of the rows that finalize() has just queued on the compute stream.
-        // With seed vertices the lists must be built now, from all rows, before the caller's own vertices are dropped
-        CK(cudaStreamWaitEvent(nstream, ev_rows, 0));
+        // The neighbour lists are built from the vertex records of the walk (a set of pairs needs neither the result rows
+        // nor their order) on their own stream, next to k_final_rows and the radix sort of the rows.  With seed vertices
+        // they must be built now: the caller's own vertices are part of the lists but not of the returned rows
+        const bool want_nb = prm.neighbors || seed_prefix > 0;
+        int rc = HVB_OK;
+        CK(cudaStreamWaitEvent(nstream, ev_b, 0));
         CK(cudaEventRecord(ev_n0, nstream));
-        if (prm.neighbors || seed_prefix > 0) { rc = build_neighbors(nstream, out_sig[0].p); if (rc) return rc; }
+        if (want_nb) { rc = nb_prepare(true, nullptr); if (rc) return rc; rc = nb_enqueue(nstream); if (rc) return rc; }
+        rc = finalize(by_slab); if (rc) return rc;
+        CK(cudaEventRecord(ev_c, stream));
+        // a slab result is an intermediate: it is exported to the exchange step, not staged for the host
+        if (world == 1) { rc = stage(); if (rc) return rc; }
+        have_result = true;
+        if (want_nb) { rc = nb_finish(nstream); if (rc) return rc; }
         if (prm.neighbors) { rc = stage_neighbors(); if (rc) return rc; }
         CK(cudaEventRecord(ev_n1, nstream));
         CK(cudaStreamWaitEvent(stream, ev_n1, 0));
-        if (second_pass) { rc = finalize_owned(by_slab); if (rc) return rc; if (world == 1) { rc = stage(); if (rc) return rc; } }
         // ev_d: the result (rows, neighbour lists) is complete in HBM.  The page-locked staging copies run on their own
         // stream and are waited for here, outside ms_finalize: they belong to the end-to-end time, not to the search
         CK(cudaEventRecord(ev_d, stream));
@@ -879,39 +875,23 @@ struct Ctx : hvb_ctx {
         return HVB_OK;
     }
 
-    int finalize() {
+    int finalize(bool by_slab) {
         u32 nrec = std::min<u32>(h_sc.p->vcount, (u32)vcap);
         nrays = std::min<u32>(h_sc.p->ray_count, ray_cap);
         for (int i = 0; i < 2; ++i) { CK(out_sig[i].ensure((size_t)std::max<u32>(nrec, 1) * (D + 1))); CK(out_r[i].ensure((size_t)std::max<u32>(nrec, 1) * D)); }
         CK(key_top.ensure(std::max<u32>(nrec, 1))); CK(key_hi.ensure(std::max<u32>(nrec, 1))); CK(key_lo.ensure(std::max<u32>(nrec, 1)));
         int bits = id_bits();
         if (nrec > 0) {
+            // multi-GPU: only the vertices this rank owns; seed vertices (the caller's own) are not returned
+            const int world = std::max(1, prm.world), rank = std::min(std::max(0, prm.rank), world - 1);
+            const int lo = by_slab ? (int)(n * rank / world) : 0, hi = by_slab ? (int)(n * (rank + 1) / world) : 0;
             k_final_rows<D><<<blocks_for(nrec, 128), 128, 0, stream>>>(dv, perm.p, nrec, bits, out_sig[0].p, out_r[0].p, key_top.p, key_hi.p, key_lo.p,
-                                                                     &sc.p->out_count, &sc.p->max_var, 0, 0, 0u);
+                                                                     &sc.p->out_count, &sc.p->max_var, lo, hi, seed_prefix);
             ++launches;
         }
         if (nrays > 0) {
             CK(ray_edge.ensure((size_t)nrays * D)); CK(ray_base.ensure((size_t)nrays * D)); CK(ray_dir.ensure((size_t)nrays * D)); CK(ray_node.ensure(nrays));
             k_final_rays<D><<<blocks_for(nrays, 128), 128, 0, stream>>>(dv, perm.p, (u32)nrays, ray_edge.p, ray_base.p, ray_dir.p, ray_node.p);
-            ++launches;
-        }
-        int rc = read_scalars(); if (rc) return rc;
-        nvert = h_sc.p->out_count;
-        CK(cudaEventRecord(ev_rows, stream));            // the unsorted rows are complete: the neighbour build may start
-        if (second_pass) { res = 0; return HVB_OK; }     // a filtering pass follows (slab ownership / seed vertices): it sorts
-        return sort_rows((u32)nvert, bits);
-    }
-
-    // multi-GPU: keep only the vertices this rank owns (after the neighbour lists were built from ALL local rows)
-    int finalize_owned(bool by_slab) {
-        const int world = std::max(1, prm.world), rank = std::min(std::max(0, prm.rank), world - 1);
-        u32 nrec = std::min<u32>(h_sc.p->vcount, (u32)vcap);
-        int lo = by_slab ? (int)(n * rank / world) : 0, hi = by_slab ? (int)(n * (rank + 1) / world) : 0;
-        int bits = id_bits();
-        CK(cudaMemsetAsync(&sc.p->out_count, 0, sizeof(u32), stream));
-        if (nrec > 0) {
-            k_final_rows<D><<<blocks_for(nrec, 128), 128, 0, stream>>>(dv, perm.p, nrec, bits, out_sig[0].p, out_r[0].p, key_top.p, key_hi.p, key_lo.p,
-                                                                     &sc.p->out_count, &sc.p->max_var, lo, hi, seed_prefix);
             ++launches;
         }
         int rc = read_scalars(); if (rc) return rc;
@@ -986,54 +966,82 @@ struct Ctx : hvb_ctx {
         return HVB_OK;
     }
 
-    // neighbour lists from `rows` (nvert rows of sorted caller ids, in any order) on stream `ns`
-    int build_neighbors(cudaStream_t ns = nullptr, const long long* rows = nullptr) {
-        if (nb_total >= 0) return HVB_OK;
-        CK(cudaSetDevice(prm.device));
-        if (!ns) ns = stream;
-        if (!rows) rows = out_sig[res].p;
-        nb_staged = false;
+    // ---- neighbour lists (neighbors_of_cell_new, neighbors.jl:219-262) ------------------------------------------
+    // Two sources: the vertex records of the walk (raw: inside hvb_search, next to k_final_rows and the row sort) or
+    // the result rows (a request after the search, or after a multi-GPU merge installed other rows).
+    u64 nb_want = 0;
+    bool nb_raw = false;
+    const long long* nb_rows = nullptr;
+    int nb_prepare(bool raw, const long long* rows) {
+        nb_staged = false; nb_raw = raw; nb_rows = rows;
         CK(deg.ensure(n)); CK(ncur.ensure(n)); CK(nb_off.ensure(n + 1));
         static const double nb_est[7] = {0, 0, 8, 20, 48, 120, 320};
         // periodic contexts build the lists of the caller's cells only (n_user == n otherwise)
         const long long n_list = periodic ? n_user : n;
+        const double nrows = raw ? (double)std::min<u32>(h_sc.p->vcount, (u32)vcap) : (double)nvert;
         // unordered pairs: a list entry of an interior cell is stored once for two cells, so about n * nb_est / 2 pairs;
         // slots = 2 x that estimate (the estimate itself is ~1.3 x the Poisson-Voronoi mean): load <= 0.4, and the
         // memset + the fill pass touch a quarter of what an entry-per-list-element table would need
-        u64 want = next_pow2((u64)std::min((double)nvert * D * (D + 1) / 2.0 * 2.0, (double)n_list * nb_est[D]) + 1024);
-        long long total = 0;
+        nb_want = next_pow2((u64)std::min(nrows * D * (D + 1) / 2.0 * 2.0, (double)n_list * nb_est[D]) + 1024);
         size_t tmp_bytes = 0;
-        CK(cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, nb_off.p, nb_off.p, (int)(n + 1), ns));
+        CK(cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, nb_off.p, nb_off.p, (int)(n + 1), stream));
         CK(nb_cub_tmp.ensure(tmp_bytes));
-        for (int attempt = 0; attempt < 8; ++attempt) {
-            CK(ptab.ensure(want));
-            CK(cudaMemsetAsync(ptab.p, 0, want * sizeof(u64), ns));
-            CK(cudaMemsetAsync(deg.p, 0, n * sizeof(u32), ns));
-            CK(cudaMemsetAsync(nbsc.p, 0, sizeof(NbScalars), ns));
-            if (nvert > 0) { k_pairs<D><<<blocks_for(nvert, 128), 128, 0, ns>>>(rows, (u32)nvert, n_list, ptab.p, want - 1, deg.p, &nbsc.p->pflags); ++launches; }
-            // offsets = exclusive scan of the degrees (as int64); one host round trip brings the overflow flag and the total
-            k_u32_to_i64<<<blocks_for(n, 256), 256, 0, ns>>>(deg.p, nb_off.p, n); ++launches;
-            CK(cudaMemsetAsync(nb_off.p + n, 0, sizeof(long long), ns));
-            CK(cub::DeviceScan::ExclusiveSum(nb_cub_tmp.p, tmp_bytes, nb_off.p, nb_off.p, (int)(n + 1), ns));
-            k_publish<<<1, 32, 0, ns>>>((const u32*)nbsc.p, (u32*)h_nbsc.p, (int)(sizeof(NbScalars) / 4), nullptr, nullptr, 0, nb_off.p + n, h_nbtotal.p);
-            ++launches;
+        nb_tmp_bytes = tmp_bytes;
+        return HVB_OK;
+    }
+    size_t nb_tmp_bytes = 0;
+    // queues pair set + degrees + offsets + the publication of {overflow flag, total} on `ns`; no host wait
+    int nb_enqueue(cudaStream_t ns) {
+        const long long n_list = periodic ? n_user : n;
+        CK(ptab.ensure(nb_want));
+        CK(cudaMemsetAsync(ptab.p, 0, nb_want * sizeof(u64), ns));
+        CK(cudaMemsetAsync(deg.p, 0, n * sizeof(u32), ns));
+        CK(cudaMemsetAsync(nbsc.p, 0, sizeof(NbScalars), ns));
+        if (nb_raw) {
+            const u32 nrec = std::min<u32>(h_sc.p->vcount, (u32)vcap);
+            if (nrec > 0) { k_pairs_raw<D><<<blocks_for(nrec, 128), 128, 0, ns>>>(dv, perm.p, nrec, n_list, ptab.p, nb_want - 1, deg.p, &nbsc.p->pflags); ++launches; }
+        } else if (nvert > 0) {
+            k_pairs<D><<<blocks_for(nvert, 128), 128, 0, ns>>>(nb_rows, (u32)nvert, n_list, ptab.p, nb_want - 1, deg.p, &nbsc.p->pflags); ++launches;
+        }
+        // offsets = exclusive scan of the degrees (as int64); one host round trip brings the overflow flag and the total
+        k_u32_to_i64<<<blocks_for(n, 256), 256, 0, ns>>>(deg.p, nb_off.p, n); ++launches;
+        CK(cudaMemsetAsync(nb_off.p + n, 0, sizeof(long long), ns));
+        size_t tmp_bytes = nb_tmp_bytes;
+        CK(cub::DeviceScan::ExclusiveSum(nb_cub_tmp.p, tmp_bytes, nb_off.p, nb_off.p, (int)(n + 1), ns));
+        k_publish<<<1, 32, 0, ns>>>((const u32*)nbsc.p, (u32*)h_nbsc.p, (int)(sizeof(NbScalars) / 4), nullptr, nullptr, 0, nb_off.p + n, h_nbtotal.p);
+        ++launches;
+        return HVB_OK;
+    }
+    // waits for nb_enqueue, repeats it with a larger table if the pair set overflowed, then fills and sorts the lists
+    int nb_finish(cudaStream_t ns) {
+        const long long n_list = periodic ? n_user : n;
+        long long total = 0;
+        for (int attempt = 0;; ++attempt) {
             CK(cudaStreamSynchronize(ns));
             total = *h_nbtotal.p;
             if (!(h_nbsc.p->pflags & 8u)) break;
-            want *= 4;
             if (attempt == 7) { err = "neighbour pair table overflow"; return HVB_ENOMEM; }
+            nb_want *= 4;
+            int rc = nb_enqueue(ns); if (rc) return rc;
         }
         CK(nb_ids.ensure(std::max<long long>(total, 1)));
         CK(cudaMemsetAsync(ncur.p, 0, n * sizeof(u32), ns));
-        k_pair_fill<<<blocks_for((int64_t)want, 256), 256, 0, ns>>>(ptab.p, want, n_list, nb_off.p, ncur.p, nb_ids.p); ++launches;
+        k_pair_fill<<<blocks_for((int64_t)nb_want, 256), 256, 0, ns>>>(ptab.p, nb_want, n_list, nb_off.p, ncur.p, nb_ids.p); ++launches;
         k_sort_lists<<<blocks_for(n, 128), 128, 0, ns>>>(nb_off.p, nb_ids.p, n); ++launches;
         CK(cudaGetLastError());          // no host wait here: the staging copy / the fetch calls order themselves behind the stream
         CK(cudaEventRecord(ev_nb, ns));
         CK(cudaStreamWaitEvent(stream, ev_nb, 0));       // whatever the compute stream does next sees the lists
-        nb_ns = ns;
         nb_total = total;
         st.kernel_launches = launches;
         return HVB_OK;
+    }
+    // lists from the current result rows, on the compute stream (requests after the search)
+    int build_neighbors() {
+        if (nb_total >= 0) return HVB_OK;
+        CK(cudaSetDevice(prm.device));
+        int rc = nb_prepare(false, out_sig[res].p); if (rc) return rc;
+        rc = nb_enqueue(stream); if (rc) return rc;
+        return nb_finish(stream);
     }
     int neighbor_count(int64_t* total) override {
         if (!have_result) { err = "no search result"; return HVB_ESTATE; }

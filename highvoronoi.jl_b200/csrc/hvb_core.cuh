@@ -589,8 +589,8 @@ HVB_HD float upper_2t(double t) { return (float)(2.0 * t * (1.0 + 4.8e-7)) * 1.0
 // FP32 pass over the points [pa, pb) in chunks of four: all loads of a chunk are issued before any arithmetic.
 template <int D>
 HVB_HD void scan_points(const Dev<D>& dv, const RayQ<D>& q, const float (&uf)[D], const float (&w2f)[D], const float (&x0f)[D],
-                        Filt& flt, int pa, int pb, ScanState& st, Best& best, LocalStats& ls) {
-    ls.rows++;
+                        Filt& flt, int pa, int pb, ScanState& st, Best& best, LocalStats& ls, bool new_row = true) {
+    ls.rows += new_row ? 1u : 0u;
     ls.cand32 += (u32)(pb - pa);
     if (!dv.fp32_filter) {
         for (int p = pa; p < pb; ++p) verify64<D>(dv, q, p, best, ls);

@@ -576,14 +576,10 @@ __global__ void k_final_rays(Dev<D> dv, const int* __restrict__ perm, u32 nrays,
 // ------------------------------------------------------------------------------------------------------------
 // neighbour lists (neighbors_of_cell_new, neighbors.jl:219-262): set of unordered id pairs -> CSR
 // ------------------------------------------------------------------------------------------------------------
+// inserts the unordered pairs of one vertex (s ascending, 1-based caller ids, planes last) into the pair set
 template <int D>
-__global__ void k_pairs(const long long* __restrict__ sig, u32 nv, long long n, u64* __restrict__ ptab, u64 pmask,
-                        u32* __restrict__ deg, u32* __restrict__ flags) {
-    u32 v = blockIdx.x * blockDim.x + threadIdx.x;
-    if (v >= nv) return;
-    long long s[D + 1];
-#pragma unroll
-    for (int k = 0; k < D + 1; ++k) s[k] = sig[(size_t)v * (D + 1) + k];
+__device__ __forceinline__ void pairs_of_row(const long long (&s)[D + 1], long long n, u64* __restrict__ ptab, u64 pmask,
+                                             u32* __restrict__ deg, u32* __restrict__ flags) {
 #pragma unroll
     for (int i = 0; i < D + 1; ++i) {
 #pragma unroll
@@ -608,6 +604,38 @@ __global__ void k_pairs(const long long* __restrict__ sig, u32 nv, long long n, 
             }
         }
     }
+}
+
+template <int D>
+__global__ void k_pairs(const long long* __restrict__ sig, u32 nv, long long n, u64* __restrict__ ptab, u64 pmask,
+                        u32* __restrict__ deg, u32* __restrict__ flags) {
+    u32 v = blockIdx.x * blockDim.x + threadIdx.x;
+    if (v >= nv) return;
+    long long s[D + 1];
+#pragma unroll
+    for (int k = 0; k < D + 1; ++k) s[k] = sig[(size_t)v * (D + 1) + k];
+    pairs_of_row<D>(s, n, ptab, pmask, deg, flags);
+}
+
+// the same straight from the vertex records of the walk (internal ids; dead records skipped): the lists do not have to
+// wait for the result rows, so they are built next to k_final_rows and the row sort
+template <int D>
+__global__ void k_pairs_raw(Dev<D> dv, const int* __restrict__ perm, u32 nrec, long long n, u64* __restrict__ ptab, u64 pmask,
+                            u32* __restrict__ deg, u32* __restrict__ flags) {
+    u32 v = blockIdx.x * blockDim.x + threadIdx.x;
+    if (v >= nrec) return;
+    const int* sp = dv.vsig + (size_t)v * (D + 1);
+    if (sp[0] < 0) return;
+    long long s[D + 1];
+#pragma unroll
+    for (int k = 0; k < D + 1; ++k) { const int id = sp[k]; s[k] = ((id < dv.n) ? (long long)perm[id] : (long long)id) + 1; }
+#pragma unroll
+    for (int i = 1; i < D + 1; ++i) {
+#pragma unroll
+        for (int j = i; j > 0; --j)
+            if (s[j - 1] > s[j]) { const long long t = s[j]; s[j] = s[j - 1]; s[j - 1] = t; }
+    }
+    pairs_of_row<D>(s, n, ptab, pmask, deg, flags);
 }
 
 __global__ void k_pair_fill(const u64* __restrict__ ptab, u64 nslots, long long n, const long long* __restrict__ off,
