@@ -33,7 +33,7 @@ sys.path.insert(0, ROOT)
 # algorithmic bytes per vertex, SURVEY.md section 8(d) / BASELINE.md section 3
 B_ALG = {2: 240.0, 3: 429.0, 4: 740.0, 5: 1344.0, 6: 2755.0}
 WORKLOADS = {  # name -> (points per GPU, dim)
-    "C2": (100000, 3), "C1": (1000, 3), "C3": (1000000, 2), "C4": (50000, 5), "C4s": (20000, 5), "D4": (30000, 4), "D6": (4000, 6),
+    "C2": (100000, 3), "C2x4": (400000, 3), "C1": (1000, 3), "C3": (1000000, 2), "C4": (50000, 5), "C4s": (20000, 5), "D4": (30000, 4), "D6": (4000, 6),
     # periodic unit cube, cuboid(d) with every axis periodic (hvb_create_periodic): C5 = configs[4] of BASELINE.json
     "C5": (20000, 6), "C5s": (4000, 6), "P3": (100000, 3), "P2": (1000000, 2),
 }
@@ -117,7 +117,8 @@ def run_reference(args, n_per_gpu, d, rank, world):
             verts += len(o["sig"])
     T = sum(times)
     val = verts / T
-    sample = "first %d of the %d points of the workload (same density is not preserved: fewer, larger cells)" % (n_sample, n_per_gpu * world)
+    sample = ("the whole workload, %d points" % n_sample) if n_sample == n_per_gpu * world else \
+        "first %d of the %d points of the workload (same density is not preserved: fewer, larger cells)" % (n_sample, n_per_gpu * world)
     line = {"impl": "reference", "metric": "voronoi_vertices_per_sec", "value": val, "unit": "vertices/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * T / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
@@ -136,8 +137,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="C2", choices=sorted(WORKLOADS))
-    ap.add_argument("--ref-points", type=float, default=40000)
-    ap.add_argument("--cpu-points", type=int, default=25000)
+    ap.add_argument("--ref-points", type=float, default=100000)
+    ap.add_argument("--cpu-points", type=int, default=100000)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--setting", action="append", default=[], help="backend knob, e.g. tile_size=8")
     args = ap.parse_args()

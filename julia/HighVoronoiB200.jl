@@ -103,4 +103,46 @@ function _voronoi(mesh::AM, TODO, compact, v_offset, silence, iteration_reset, p
     return mesh, searcher
 end
 
+"""
+    periodic_tessellation(xs, domain; device = 0) -> (sig, r, canonical, origin, mult)
+
+Periodic boundaries (`Plane.BC > 0`, boundary.jl:15-29): the halo orchestration of `VoronoiGeometry`
+(Create_Discrete_Domain domain.jl:175-213, reflect_nodes :338-390, periodize! :139-166) runs on the device
+(`hvb_create_periodic`: halo copies, pushed planes, certificate with margin retry).  Rows are numbered caller 1..n,
+halo n+1..n+nhalo (`origin[k]`, `mult[:, k]` = generator and period multiplicities of halo node k, the reference's
+`references` / `reference_shifts`), plane n+nhalo+p; `canonical[v]` marks one image per periodic class.
+"""
+function periodic_tessellation(xs::Vector{P}, domain; device::Integer = 0) where {P}
+    d = size(P)[1]; n = length(xs)
+    planes = domain.planes; np = length(planes)
+    base = Matrix{Float64}(undef, d, np); normal = Matrix{Float64}(undef, d, np); bc = Vector{Int32}(undef, np)
+    for (k, pl) in enumerate(planes)
+        base[:, k] .= pl.base; normal[:, k] .= pl.normal; bc[k] = Int32(pl.BC)
+    end
+    prm = HvbParams(); ccall((:hvb_default_params, LIB), Cvoid, (Ref{HvbParams},), prm); prm.device = device
+    ctx = Ref{Ptr{Cvoid}}(C_NULL)
+    GC.@preserve xs base normal bc begin
+        check(ccall((:hvb_create_periodic, LIB), Cint,
+                    (Ref{Ptr{Cvoid}}, Cint, Int64, Ptr{Float64}, Cint, Ptr{Float64}, Ptr{Float64}, Ptr{Int32}, Ref{HvbParams}),
+                    ctx, d, n, pointer(reinterpret(Float64, xs)), np, base, normal, bc, prm))
+    end
+    c = ctx[]
+    try
+        check(ccall((:hvb_search, LIB), Cint, (Ptr{Cvoid}, Ptr{Int64}, Int64, Ptr{Int64}, Ptr{Float64}, Int64, Cint),
+                    c, C_NULL, 0, C_NULL, C_NULL, 0, 0), c)
+        nv = Ref{Int64}(0); nr = Ref{Int64}(0); ml = Ref{Int64}(0)
+        check(ccall((:hvb_counts, LIB), Cint, (Ptr{Cvoid}, Ref{Int64}, Ref{Int64}, Ref{Int64}), c, nv, nr, ml), c)
+        sig = Matrix{Int64}(undef, d + 1, nv[]); r = Matrix{Float64}(undef, d, nv[]); canonical = Vector{UInt8}(undef, nv[])
+        check(ccall((:hvb_fetch_vertices, LIB), Cint, (Ptr{Cvoid}, Ptr{Int64}, Ptr{Float64}), c, sig, r), c)
+        check(ccall((:hvb_fetch_vertex_flags, LIB), Cint, (Ptr{Cvoid}, Ptr{UInt8}), c, canonical), c)
+        nh = Ref{Int64}(0); npairs = Ref{Int32}(0); margin = Ref{Float64}(0)
+        check(ccall((:hvb_halo_count, LIB), Cint, (Ptr{Cvoid}, Ref{Int64}, Ref{Int32}, Ref{Float64}), c, nh, npairs, margin), c)
+        origin = Vector{Int64}(undef, nh[]); mult = Matrix{Int32}(undef, npairs[], nh[]); hxs = Matrix{Float64}(undef, d, nh[])
+        check(ccall((:hvb_fetch_halo, LIB), Cint, (Ptr{Cvoid}, Ptr{Int64}, Ptr{Int32}, Ptr{Float64}), c, origin, mult, hxs), c)
+        return sig, r, canonical, origin, mult
+    finally
+        ccall((:hvb_destroy, LIB), Cvoid, (Ptr{Cvoid},), c)
+    end
+end
+
 end # module

@@ -1,12 +1,12 @@
 """Aggregates an `ncu --page source --csv --print-source cuda,sass` dump by code region of hvb_core.cuh / hvb_kernels.cuh.
 usage: python tools/srcregions.py dump.csv   (line ranges below match the sources of the commit the dump was taken at)"""
 import csv, sys, collections
-REG = [("hvb_core.cuh", 200, 221, "load_x32"), ("hvb_core.cuh", 229, 248, "hash/edge_slot"), ("hvb_core.cuh", 252, 311, "ortho_direction/dot"),
-       ("hvb_core.cuh", 325, 378, "best/verify64"), ("hvb_core.cuh", 380, 401, "make_filter"), ("hvb_core.cuh", 407, 515, "row_range32/row_try32"),
-       ("hvb_core.cuh", 516, 559, "row_range(fp64)"), ("hvb_core.cuh", 560, 664, "scan_points"), ("hvb_core.cuh", 665, 676, "settle_stage"),
-       ("hvb_core.cuh", 677, 709, "query: planes"), ("hvb_core.cuh", 710, 782, "query: stage setup"), ("hvb_core.cuh", 783, 886, "query: row loop"),
-       ("hvb_core.cuh", 887, 933, "vertex_insert"), ("hvb_core.cuh", 934, 993, "edge_register"), ("hvb_core.cuh", 994, 1071, "commit_vertex"),
-       ("hvb_core.cuh", 1072, 1206, "ray_setup/ray_result"), ("hvb_kernels.cuh", 418, 473, "k_walk loop"),
+REG = [("hvb_core.cuh", 202, 223, "load_x32"), ("hvb_core.cuh", 231, 250, "hash/edge_slot"), ("hvb_core.cuh", 254, 313, "ortho_direction/dot"),
+       ("hvb_core.cuh", 327, 380, "best/verify64"), ("hvb_core.cuh", 382, 403, "make_filter"), ("hvb_core.cuh", 409, 517, "row_range32/row_try32"),
+       ("hvb_core.cuh", 518, 561, "row_range(fp64)"), ("hvb_core.cuh", 562, 666, "scan_points"), ("hvb_core.cuh", 667, 678, "settle_stage"),
+       ("hvb_core.cuh", 679, 711, "query: planes"), ("hvb_core.cuh", 712, 792, "query: stage setup"), ("hvb_core.cuh", 793, 896, "query: row loop"),
+       ("hvb_core.cuh", 897, 943, "vertex_insert"), ("hvb_core.cuh", 944, 1003, "edge_register"), ("hvb_core.cuh", 1004, 1081, "commit_vertex"),
+       ("hvb_core.cuh", 1082, 1216, "ray_setup/ray_result"), ("hvb_kernels.cuh", 418, 473, "k_walk loop"),
        ("hvb_coop.cuh", 40, 84, "coop: row geometry"), ("hvb_coop.cuh", 85, 139, "coop: next_row (task fetch)"), ("hvb_coop.cuh", 140, 206, "coop: scan chunk + survivors"),
        ("hvb_coop.cuh", 207, 326, "coop: stage setup / settle"), ("hvb_coop.cuh", 327, 462, "commit_vertex_warp"), ("hvb_coop.cuh", 463, 600, "k_walk_coop loop")]
 rows = list(csv.reader(open(sys.argv[1], newline='')))
