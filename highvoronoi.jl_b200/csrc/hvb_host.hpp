@@ -15,10 +15,14 @@ inline double simplices_per_point(int d) {
 }
 // measured on B200 (profiles/r1_tile_occupancy_sweep.md, knob sweeps): longer rows amortise the per-row geometry
 inline int default_points_per_cell(int d) {
-    static const int p[7] = {0, 0, 4, 5, 4, 3, 4};
+    static const int p[7] = {0, 0, 4, 5, 4, 4, 4};
     return p[d];
 }
-inline double default_probe_scale(int d) { return d <= 3 ? 1.5 : 1.3; }
+// first probe ball radius / circumradius of the origin vertex (re-tuned on the k_walk_coop kernel, profiles/r1_sweeps_session3.md)
+inline double default_probe_scale(int d) {
+    static const double s[7] = {0, 0, 1.7, 1.5, 1.3, 1.2, 1.2};
+    return s[d];
+}
 inline int tile_size_for_dim(int d) {
     static const int g[7] = {0, 0, 4, 8, 16, 32, 32};
     return g[d];

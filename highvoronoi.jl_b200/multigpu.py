@@ -78,10 +78,13 @@ def gather_and_merge(searcher, group=None, dedup=False, cache=None):
     bufcap = cache["cap"]
     got = ctypes.c_int64()
     _abi.check(L.hvb_export_device(ctx, cache["sig"].data_ptr(), cache["r"].data_ptr(), bufcap, ctypes.byref(got)), ctx)
-    # padded all-gather straight into one buffer per array; only the valid prefixes are copied out afterwards
-    dist.all_gather_into_tensor(cache["sig_all"].view(-1), cache["sig"].view(-1), group=group)
-    dist.all_gather_into_tensor(cache["r_all"].view(-1), cache["r"].view(-1), group=group)
+    # all-gather straight into one buffer per array, padded only to the largest count of THIS step (the buffers
+    # themselves keep 20 % headroom so that they are not re-allocated from step to step)
+    sig_out = cache["sig_all"].view(-1)[:world * cap * (d + 1)]
+    r_out = cache["r_all"].view(-1)[:world * cap * d]
+    dist.all_gather_into_tensor(sig_out, cache["sig"].view(-1)[:cap * (d + 1)], group=group)
+    dist.all_gather_into_tensor(r_out, cache["r"].view(-1)[:cap * d], group=group)
     torch.cuda.synchronize()
-    _abi.check(L.hvb_adopt_device_padded(ctx, cache["sig_all"].data_ptr(), cache["r_all"].data_ptr(), world, bufcap,
+    _abi.check(L.hvb_adopt_device_padded(ctx, sig_out.data_ptr(), r_out.data_ptr(), world, cap,
                                          cnts.ctypes.data_as(ctypes.c_void_p)), ctx)
-    return (cache["sig"].numel() + cache["r"].numel()) * 8
+    return cap * (2 * d + 1) * 8
