@@ -240,6 +240,14 @@ class VoronoiMesh:
         out[pl] = ids[pl] - self.n_halo
         return out
 
+    def volumes(self):
+        """volumes of the cells of the caller's generators (VoronoiData(...).volume, voronoidata.jl; computed on the device
+        from the vertex rows, hvb_cell_volumes); +inf for cells with an unbounded edge"""
+        L, ctx = _abi.lib(), self.searcher._ctx
+        vol = np.empty((getattr(self, "n_user", self.n),), dtype=np.float64)
+        _abi.check(L.hvb_cell_volumes(ctx, vol.ctypes.data_as(ctypes.c_void_p)), ctx)
+        return vol
+
     def neighbors(self):
         """CSR (offsets[n+1], ids) of neighbors_of_cell for every cell (neighbors.jl:214-262)."""
         if self._nb is None:
@@ -317,11 +325,13 @@ class VoronoiGeometry:
 
 
 class VoronoiData:
-    """VoronoiData(VG; getvertices, getneighbors) (voronoidata.jl:545-703), vertex / neighbour fields only."""
+    """VoronoiData(VG; getvertices, getneighbors, getvolume) (voronoidata.jl:545-703): vertex / neighbour / volume fields."""
 
-    def __init__(self, VG, getvertices=False, getneighbors=False, **_ignored):
+    def __init__(self, VG, getvertices=False, getneighbors=False, getvolume=False, **_ignored):
         self.nodes = VG.nodes
         m = VG.mesh
+        if getvolume:
+            self.volume = m.volumes()
         if getvertices:
             self.vertices = [list(m.vertices_iterator(i)) for i in range(1, getattr(m, "n_user", m.n) + 1)]
         nu = getattr(m, "n_user", m.n)

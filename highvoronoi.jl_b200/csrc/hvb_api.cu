@@ -118,6 +118,7 @@ struct hvb_ctx {
     virtual int halo_count(int64_t* nhalo, int32_t* npairs, double* margin) = 0;
     virtual int fetch_halo(int64_t* origin, int32_t* mult, double* xs) = 0;
     virtual int fetch_vertex_flags(uint8_t* flags) = 0;
+    virtual int cell_volumes(double* vol) = 0;
     virtual int set_points(int64_t n, const double* xs) = 0;
     virtual int search(const int64_t* cells, int64_t ncells, const int64_t* seed_sig, const double* seed_r, int64_t nseed, int stride) = 0;
     virtual int counts(int64_t* nv, int64_t* nr, int64_t* msl) = 0;
@@ -228,6 +229,7 @@ struct Ctx : hvb_ctx {
         if (sstream2) { cudaStreamSynchronize(sstream2); cudaStreamDestroy(sstream2); }
         if (ev_p0) cudaEventDestroy(ev_p0);
         if (ev_p1) cudaEventDestroy(ev_p1);
+        vol_acc.release(); vol_dev.release();
         halo_cnt.release(); halo_off.release(); halo_origin.release(); halo_mult.release(); vflags.release(); cert.release(); h_cert.release();
         if (sstream) { cudaStreamSynchronize(sstream); cudaStreamDestroy(sstream); }
         if (stream) cudaStreamDestroy(stream);
@@ -514,7 +516,8 @@ struct Ctx : hvb_ctx {
     }
 
     int alloc_tables(int64_t cap) {
-        if (cap > 0x7ffffff0LL) { err = "vertex capacity beyond 2^31"; return HVB_ENOMEM; }
+        // a queue entry carries the vertex index in 29 bits (frontier_entry): 5.3e8 records, more than 180 GB of HBM hold
+        if (cap >= (1LL << 29)) { err = "vertex capacity beyond 2^29"; return HVB_ENOMEM; }
         vcap = cap;
         CK(vsig.ensure((size_t)cap * (D + 1))); CK(vr.ensure((size_t)cap * D));
         u64 vts = next_pow2((u64)cap * 2);
@@ -640,6 +643,35 @@ struct Ctx : hvb_ctx {
         if (!periodic || !have_flags) { memset(flags, 1, (size_t)nvert); return HVB_OK; }   // without a halo every row is its own representative
         if (nvert > 0) CK(cudaMemcpyAsync(flags, vflags.p, (size_t)nvert, cudaMemcpyDeviceToHost, stream));
         CK(cudaStreamSynchronize(stream));
+        return HVB_OK;
+    }
+
+    // volumes of the cells of the caller's generators from the current result rows (hvb_geometry.cuh)
+    DBuf<long long> vol_acc;
+    DBuf<double> vol_dev;
+    int cell_volumes(double* vol) override {
+        if (!have_result) { err = "no search result"; return HVB_ESTATE; }
+        if (!vol) { err = "null output"; return HVB_EINVAL; }
+        if (seed_prefix > 0) { err = "cell volumes need all vertices of the cells: not available after a search with seed vertices"; return HVB_ESTATE; }
+        CK(cudaSetDevice(prm.device));
+        const long long n_list = periodic ? n_user : n;
+        CK(vol_acc.ensure(n_list)); CK(vol_dev.ensure(n_list));
+        CK(cudaMemsetAsync(vol_acc.p, 0, (size_t)n_list * sizeof(long long), stream));
+        double fact = 1.0;
+        for (int k = 2; k <= D; ++k) fact *= k;
+        // fixed point: 2^52 units per ext^D (the bounding box volume is at most ext^D); 1/d! is folded into the scale so
+        // that the accumulators hold volumes, with 11 bits of headroom for partial sums of either sign
+        const double scale = ldexp(1.0, 52) / (pow(dv.ext, (double)D) * fact);
+        if (nvert > 0) {
+            k_cell_volumes<D><<<blocks_for(nvert, 128), 128, 0, stream>>>(out_sig[res].p, (u32)nvert, xs_in.p, (long long)n, n_list, planes.p, scale, vol_acc.p);
+            ++launches;
+        }
+        k_volumes_finish<<<blocks_for(n_list, 256), 256, 0, stream>>>(vol_acc.p, 1.0 / (scale * fact), vol_dev.p, n_list); ++launches;
+        if (nrays > 0) { k_volumes_unbounded<<<blocks_for(nrays * D, 256), 256, 0, stream>>>(ray_edge.p, (long long)nrays * D, n_list, vol_dev.p); ++launches; }
+        CK(cudaMemcpyAsync(vol, vol_dev.p, (size_t)n_list * sizeof(double), cudaMemcpyDeviceToHost, stream));
+        CK(cudaStreamSynchronize(stream));
+        CK(cudaGetLastError());
+        st.kernel_launches = launches;
         return HVB_OK;
     }
 
@@ -1219,6 +1251,7 @@ int hvb_adopt_device(hvb_ctx* ctx, const void* sig_dev, const void* r_dev, int64
 int hvb_halo_count(hvb_ctx* ctx, int64_t* nhalo, int32_t* npairs, double* margin) { return ctx ? ctx->halo_count(nhalo, npairs, margin) : HVB_EINVAL; }
 int hvb_fetch_halo(hvb_ctx* ctx, int64_t* origin, int32_t* mult, double* xs) { return ctx ? ctx->fetch_halo(origin, mult, xs) : HVB_EINVAL; }
 int hvb_fetch_vertex_flags(hvb_ctx* ctx, uint8_t* flags) { return ctx ? ctx->fetch_vertex_flags(flags) : HVB_EINVAL; }
+int hvb_cell_volumes(hvb_ctx* ctx, double* vol) { return ctx ? ctx->cell_volumes(vol) : HVB_EINVAL; }
 int hvb_stats(hvb_ctx* ctx, hvb_stats_t* out) {
     if (!ctx || !out) return HVB_EINVAL;
     *out = ctx->st;

@@ -4,6 +4,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include "hvb_core.cuh"
+#include "hvb_geometry.cuh"
 
 namespace hvb {
 
@@ -664,6 +665,36 @@ __global__ void k_sort_lists(const long long* __restrict__ off, long long* __res
 __global__ void k_u32_to_i64(const u32* __restrict__ a, long long* __restrict__ b, long long n) {
     long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
     if (i < n) b[i] = a[i];
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// cell volumes from the result rows (hvb_geometry.cuh).  One thread per row; the d+1 contributions of a row are added
+// in 64-bit fixed point, so the sums do not depend on the order of the atomics (bitwise reproducible volumes).
+// ------------------------------------------------------------------------------------------------------------
+template <int D>
+__global__ void k_cell_volumes(const long long* __restrict__ sig, u32 nv, const double* __restrict__ xs, long long n, long long n_list,
+                               const PlaneSet* __restrict__ ps, double scale, long long* __restrict__ acc) {
+    u32 v = blockIdx.x * blockDim.x + threadIdx.x;
+    if (v >= nv) return;
+    long long s[D + 1];
+#pragma unroll
+    for (int k = 0; k < D + 1; ++k) s[k] = sig[(size_t)v * (D + 1) + k];
+    for (int k = 0; k < D + 1; ++k) {
+        if (s[k] > n_list) continue;                       // planes and halo generators have no cell of their own here
+        const double t = vertex_flag_sum<D>(xs, n, ps, s, k) * scale;
+        atomicAdd(reinterpret_cast<unsigned long long*>(acc + (s[k] - 1)), (unsigned long long)__double2ll_rn(t));
+    }
+}
+__global__ void k_volumes_finish(const long long* __restrict__ acc, double inv_scale, double* __restrict__ vol, long long n) {
+    long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (i < n) vol[i] = (double)acc[i] * inv_scale;
+}
+// cells with an unbounded edge have no finite volume
+__global__ void k_volumes_unbounded(const long long* __restrict__ ray_edge, long long nentries, long long n_list, double* __restrict__ vol) {
+    long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (i >= nentries) return;
+    const long long g = ray_edge[i];
+    if (g >= 1 && g <= n_list) vol[g - 1] = INFINITY;
 }
 
 // ------------------------------------------------------------------------------------------------------------

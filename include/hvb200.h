@@ -193,6 +193,16 @@ int hvb_adopt_device(hvb_ctx* ctx, const void* sig_dev, const void* r_dev, int64
 int hvb_adopt_device_padded(hvb_ctx* ctx, const void* sig_dev, const void* r_dev, int nseg, int64_t seg_cap, const int64_t* counts);
 
 /* rare_events / statistics.jl:132-143 analogue */
+/* Geometry product: volumes of the cells of the caller's generators, computed on the device from the
+ * current result rows by the signed flag decomposition of a simple polytope (hvb_geometry.cuh); replaces, for general
+ * position, the reference's VI_POLYGON volume pass (integrate.jl:33-53, polyintegrator.jl) behind VoronoiData(...).volume
+ * and is the quantity the reference's own tests check (sum of the volumes = volume of the domain, test/rcmethods.jl:8).
+ * vol: n doubles (periodic contexts: the n caller generators).  Cells with an unbounded edge get +inf.  Needs every
+ * vertex of a cell among the rows: all cells after hvb_search over all cells (after the merge in multi-GPU mode), the
+ * cells of Iter otherwise; HVB_ESTATE after a search with seed vertices.  Sums are accumulated in 64-bit fixed point:
+ * the result does not depend on the order of the atomics. */
+int hvb_cell_volumes(hvb_ctx* ctx, double* vol);
+
 int hvb_stats(hvb_ctx* ctx, hvb_stats_t* out);
 
 const char* hvb_last_error(hvb_ctx* ctx);   /* ctx may be NULL: message of the last failed hvb_create */

@@ -104,6 +104,18 @@ function _voronoi(mesh::AM, TODO, compact, v_offset, silence, iteration_reset, p
 end
 
 """
+    cell_volumes(ctx, n) -> Vector{Float64}
+
+Volumes of the cells from the vertex rows the context holds (`hvb_cell_volumes`): what `VoronoiData(VG, getvolume=true).volume`
+returns after the reference's `VI_POLYGON` pass (integrate.jl:33-53), for general position.
+"""
+function cell_volumes(ctx::Ptr{Cvoid}, n::Integer)
+    vol = Vector{Float64}(undef, n)
+    check(ccall((:hvb_cell_volumes, LIB), Cint, (Ptr{Cvoid}, Ptr{Float64}), ctx, vol), ctx)
+    return vol
+end
+
+"""
     periodic_tessellation(xs, domain; device = 0) -> (sig, r, canonical, origin, mult)
 
 Periodic boundaries (`Plane.BC > 0`, boundary.jl:15-29): the halo orchestration of `VoronoiGeometry`

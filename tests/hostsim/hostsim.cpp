@@ -8,6 +8,7 @@
 #include <vector>
 #include <algorithm>
 #include "../../highvoronoi.jl_b200/csrc/hvb_host.hpp"
+#include "../../highvoronoi.jl_b200/csrc/hvb_geometry.cuh"
 
 using namespace hvb;
 
@@ -110,6 +111,24 @@ static SimResult* run(int64_t n, const double* xs, int P, const double* base, co
     return R;
 }
 
+// cell volumes from vertex rows (vertex_flag_sum, hvb_geometry.cuh): sig [nv][dim+1] caller ids, 1-based, plane p = n + p
+template <int D>
+static void volumes(int64_t n, const double* xs, int P, const double* base, const double* normal, int64_t nv, const int64_t* sig, double* vol) {
+    PlaneSet ps; memset(&ps, 0, sizeof(ps)); ps.P = P;
+    for (int p = 0; p < P; ++p) {
+        double nr = 0; for (int k = 0; k < D; ++k) nr += normal[p * D + k] * normal[p * D + k];
+        nr = sqrt(nr); double off = 0;
+        for (int k = 0; k < D; ++k) { ps.normal[p * 6 + k] = normal[p * D + k] / nr; off += ps.normal[p * 6 + k] * base[p * D + k]; }
+        ps.off[p] = off;
+    }
+    double fact = 1; for (int k = 2; k <= D; ++k) fact *= k;
+    for (int64_t i = 0; i < n; ++i) vol[i] = 0;
+    for (int64_t v = 0; v < nv; ++v) {
+        long long s[D + 1];
+        for (int k = 0; k <= D; ++k) s[k] = sig[v * (D + 1) + k];
+        for (int k = 0; k <= D; ++k) if (s[k] <= n) vol[s[k] - 1] += vertex_flag_sum<D>(xs, n, &ps, s, k) / fact;
+    }
+}
 extern "C" {
 void* hostsim_run(int dim, int64_t n, const double* xs, int P, const double* base, const double* normal,
                   int ppc, double probe_scale, int fp32, int seed_stride) {
@@ -135,4 +154,14 @@ void hostsim_fetch(void* h, int64_t* sig, double* r, int64_t* ray_edge) {
     memcpy(ray_edge, R->ray_edge.data(), R->ray_edge.size() * 8);
 }
 void hostsim_free(void* h) { delete (SimResult*)h; }
+
+void hostsim_volumes(int dim, int64_t n, const double* xs, int P, const double* base, const double* normal, int64_t nv, const int64_t* sig, double* vol) {
+    switch (dim) {
+        case 2: volumes<2>(n, xs, P, base, normal, nv, sig, vol); break;
+        case 3: volumes<3>(n, xs, P, base, normal, nv, sig, vol); break;
+        case 4: volumes<4>(n, xs, P, base, normal, nv, sig, vol); break;
+        case 5: volumes<5>(n, xs, P, base, normal, nv, sig, vol); break;
+        case 6: volumes<6>(n, xs, P, base, normal, nv, sig, vol); break;
+    }
+}
 }

@@ -11,7 +11,8 @@ def build():
     src = os.path.join(_HERE, "hostsim.cpp")
     core = os.path.join(_HERE, "..", "..", "highvoronoi.jl_b200", "csrc", "hvb_core.cuh")
     host = os.path.join(_HERE, "..", "..", "highvoronoi.jl_b200", "csrc", "hvb_host.hpp")
-    newest = max(os.path.getmtime(f) for f in (src, core, host))
+    geom = os.path.join(_HERE, "..", "..", "highvoronoi.jl_b200", "csrc", "hvb_geometry.cuh")
+    newest = max(os.path.getmtime(f) for f in (src, core, host, geom))
     if not os.path.exists(_SO) or os.path.getmtime(_SO) < newest:
         subprocess.check_call(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-Wno-unknown-pragmas", "-o", _SO, src])
     return _SO
@@ -41,3 +42,21 @@ def run(xs, base=None, normal=None, ppc=0, probe_scale=0.0, fp32=1, seed_stride=
     L.hostsim_fetch(h, P(sig), P(r), P(re))
     L.hostsim_free(h)
     return dict(sig=sig, r=r, ray_edge=re, stats=dict(zip(CTR, ctr.tolist())))
+
+
+def volumes(xs, sig, base=None, normal=None):
+    """cell volumes from vertex rows with the product's own formula (vertex_flag_sum, hvb_geometry.cuh) on the host"""
+    L = ctypes.CDLL(build())
+    L.hostsim_volumes.restype = None
+    L.hostsim_volumes.argtypes = [ctypes.c_int, ctypes.c_int64, ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p,
+                                  ctypes.c_int64, ctypes.c_void_p, ctypes.c_void_p]
+    xs = np.ascontiguousarray(xs, dtype=np.float64)
+    n, d = xs.shape
+    if base is None:
+        base = np.zeros((0, d)); normal = np.zeros((0, d))
+    base = np.ascontiguousarray(base, dtype=np.float64); normal = np.ascontiguousarray(normal, dtype=np.float64)
+    sig = np.ascontiguousarray(sig, dtype=np.int64)
+    vol = np.zeros(n)
+    P = lambda a: a.ctypes.data_as(ctypes.c_void_p)
+    L.hostsim_volumes(d, n, P(xs), base.shape[0], P(base), P(normal), sig.shape[0], P(sig), P(vol))
+    return vol

@@ -30,6 +30,7 @@ def test_default_params_match_reference(hvb):
     # raycast-types.jl:226-230
     assert (p.variance_tol, p.break_tol, p.b_nodes_tol, p.plane_tolerance, p.ray_tol) == (1e-15, 1e-5, 1e-7, 1e-12, 1e-12)
     assert p.method == hvb.RCStandard == hvb.RCNonGeneralHP and p.world == 1 and p.fp32_filter == 1 and p.sort_output == 1
+    assert p.persistent == 3                  # the persistent walk with warp-aggregated atomics (include/hvb200.h)
     assert ctypes.sizeof(hvb._abi.hvb_params) == 5 * 8 + 12 * 4 + 8 + 8 + 8
     assert ctypes.sizeof(hvb._abi.hvb_stats_t) == 27 * 8
 

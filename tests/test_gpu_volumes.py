@@ -1,0 +1,78 @@
+"""Cell volumes on the device (hvb_cell_volumes).  The reference's own tests pin the raycast path through
+this product: sum of the cell volumes = volume of the domain (test/rcmethods.jl:8, test/multithread.jl:8,
+test/basics.jl:46); here additionally every single cell is compared with Qhull."""
+import numpy as np
+import pytest
+
+import qhull_oracle
+from util import points
+
+pytestmark = pytest.mark.gpu
+
+
+def run(hvb, xs, dom, periodic=False, **settings):
+    s = hvb.Raycast(xs, domain=dom, options=hvb.RaycastParameter(**settings), periodic=periodic)
+    mesh, _ = hvb.voronoi(xs, searcher=s)
+    return mesh, s
+
+
+@pytest.mark.parametrize("d,n", [(2, 5000), (3, 3000), (4, 1200), (5, 400), (6, 120)])
+def test_volumes_sum_to_the_domain(hvb, d, n):
+    """the reference's known-answer test: abs(sum(VoronoiData(vg).volume) - 1) < 1e-2 there, 1e-11 here"""
+    xs = points(n, d, 500 + d)
+    mesh, _ = run(hvb, xs, hvb.cuboid(d, periodic=[]))
+    vol = mesh.volumes()
+    assert vol.shape == (n,) and (vol > 0).all()
+    assert abs(vol.sum() - 1.0) < 1e-11
+
+
+@pytest.mark.parametrize("d,n", [(2, 600), (3, 400), (4, 150)])
+def test_every_cell_volume_matches_qhull(hvb, d, n):
+    from scipy.spatial import ConvexHull
+    xs = points(n, d, 510 + d)
+    mesh, _ = run(hvb, xs, hvb.cuboid(d, periodic=[]))
+    vol = mesh.volumes()
+    sig, r = np.array(mesh.sig), np.array(mesh.r)
+    for i in range(n):
+        rows = (sig == i + 1).any(axis=1)
+        assert abs(vol[i] / ConvexHull(r[rows]).volume - 1.0) < 1e-9, i
+
+
+def test_volumes_full_size_c2_and_reproducible(hvb):
+    xs = points(100000, 3, 0)
+    mesh, s = run(hvb, xs, hvb.cuboid(3, periodic=[]))
+    v1 = mesh.volumes()
+    v2 = mesh.volumes()
+    assert np.array_equal(v1, v2)                                   # fixed-point accumulation: independent of the atomics' order
+    assert abs(v1.sum() - 1.0) < 1e-9 and v1.min() > 0
+
+
+def test_unbounded_cells_have_infinite_volume(hvb):
+    xs = points(800, 3, 520)
+    mesh, _ = run(hvb, xs, hvb.Boundary())
+    vol = mesh.volumes()
+    open_cells = np.unique(mesh.ray_edge) - 1
+    assert len(open_cells) > 0 and np.isinf(vol[open_cells]).all()
+    closed = np.setdiff1d(np.arange(800), open_cells)
+    assert np.isfinite(vol[closed]).all() and (vol[closed] > 0).all()
+    # bounded cells do not depend on the domain: the same cells inside a cuboid that cuts none of them
+    from scipy.spatial import ConvexHull
+    sig, r = np.array(mesh.sig), np.array(mesh.r)
+    for i in closed[:50]:
+        rows = (sig == i + 1).any(axis=1)
+        assert abs(vol[i] / ConvexHull(r[rows]).volume - 1.0) < 1e-9
+
+
+@pytest.mark.parametrize("d,n", [(2, 3000), (3, 1500), (4, 500)])
+def test_periodic_volumes_sum_to_the_torus(hvb, d, n):
+    xs = points(n, d, 530 + d)
+    mesh, _ = run(hvb, xs, hvb.cuboid(d), periodic=True)
+    vol = mesh.volumes()
+    assert vol.shape == (n,) and (vol > 0).all()
+    assert abs(vol.sum() - 1.0) < 1e-11
+
+
+def test_voronoi_data_volume_front_end(hvb):
+    xs = points(2000, 3, 540)
+    vd = hvb.VoronoiData(hvb.VoronoiGeometry(xs, hvb.cuboid(3, periodic=[])), getvolume=True)
+    assert abs(vd.volume.sum() - 1.0) < 1e-11

@@ -58,3 +58,21 @@ def test_far_vertices_of_flat_hull_simplices(oracle, d, n, seed):
     o, s = oracle.run(xs), hostsim.run(xs)
     assert np.array_equal(s["sig"], o["sig"])
     assert sorted(map(tuple, s["ray_edge"].tolist())) == sorted(map(tuple, o["ray_edge"].tolist()))
+
+
+# ---- geometry product: the volume formula of hvb_geometry.cuh on the host, against Qhull ---------------------------
+@pytest.mark.parametrize("d,n", [(2, 400), (3, 300), (4, 120), (5, 50)])
+def test_cell_volume_formula_matches_qhull(d, n):
+    """vertex_flag_sum (the code the device kernel runs) on the oracle's vertex rows: every cell volume equals the volume
+    of the convex hull of the cell's vertices (Qhull), and the volumes add up to the domain (the reference's own
+    known-answer test of this path, test/rcmethods.jl:8)"""
+    from scipy.spatial import ConvexHull
+    import hv_oracle
+    xs = points(n, d, 70 + d)
+    base, normal = qhull_oracle.cuboid(d)
+    o = hv_oracle.run(xs, base, normal)
+    vol = hostsim.volumes(xs, o["sig"], base, normal)
+    assert abs(vol.sum() - 1.0) < 1e-12
+    for i in range(n):
+        rows = (o["sig"] == i + 1).any(axis=1)
+        assert abs(vol[i] / ConvexHull(o["r"][rows]).volume - 1.0) < 1e-10
