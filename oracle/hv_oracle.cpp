@@ -11,7 +11,11 @@
 // Julia is not installed in the build container, so this restatement could not be run
 // against the real package.  It is pinned instead against an independent Qhull oracle
 // (oracle/qhull_oracle.py) and the reference's own validity predicates (verify_vertex,
-// raycast.jl:477-502), see tests/test_oracle.py.
+// raycast.jl:477-502), see tests/test_oracle.py.  The one known-answer test the reference's
+// tests do hold for this path -- the cell volumes add up to the volume of the domain
+// (test/rcmethods.jl:8, test/multithread.jl:8, test/basics.jl:46) -- is run on this oracle's
+// rows in tests/test_hostsim.py::test_cell_volume_formula_matches_qhull and on the GPU result
+// in tests/test_gpu_volumes.py; exact values beyond that invariant stay unpinned.
 //
 // Every function cites the reference file:line (relative to /root/reference/src) it follows.
 // Deviations from the reference, all irrelevant for general-position input:
