@@ -248,6 +248,15 @@ class VoronoiMesh:
         _abi.check(L.hvb_cell_volumes(ctx, vol.ctypes.data_as(ctypes.c_void_p)), ctx)
         return vol
 
+    def areas(self):
+        """interface areas aligned with the ids of neighbors() (VoronoiData(...).area; hvb_cell_areas); +inf for facets
+        that hold an unbounded edge"""
+        L, ctx = _abi.lib(), self.searcher._ctx
+        off, ids = self.neighbors()
+        area = np.empty((ids.shape[0],), dtype=np.float64)
+        _abi.check(L.hvb_cell_areas(ctx, area.ctypes.data_as(ctypes.c_void_p)), ctx)
+        return area
+
     def neighbors(self):
         """CSR (offsets[n+1], ids) of neighbors_of_cell for every cell (neighbors.jl:214-262)."""
         if self._nb is None:
@@ -327,11 +336,15 @@ class VoronoiGeometry:
 class VoronoiData:
     """VoronoiData(VG; getvertices, getneighbors, getvolume) (voronoidata.jl:545-703): vertex / neighbour / volume fields."""
 
-    def __init__(self, VG, getvertices=False, getneighbors=False, getvolume=False, **_ignored):
+    def __init__(self, VG, getvertices=False, getneighbors=False, getvolume=False, getarea=False, **_ignored):
         self.nodes = VG.nodes
         m = VG.mesh
         if getvolume:
             self.volume = m.volumes()
+        if getarea:
+            off, _ids = m.neighbors()
+            a = m.areas()
+            self.area = [a[off[i]:off[i + 1]] for i in range(getattr(m, "n_user", m.n))]
         if getvertices:
             self.vertices = [list(m.vertices_iterator(i)) for i in range(1, getattr(m, "n_user", m.n) + 1)]
         nu = getattr(m, "n_user", m.n)

@@ -119,6 +119,7 @@ struct hvb_ctx {
     virtual int fetch_halo(int64_t* origin, int32_t* mult, double* xs) = 0;
     virtual int fetch_vertex_flags(uint8_t* flags) = 0;
     virtual int cell_volumes(double* vol) = 0;
+    virtual int cell_areas(double* area) = 0;
     virtual int set_points(int64_t n, const double* xs) = 0;
     virtual int search(const int64_t* cells, int64_t ncells, const int64_t* seed_sig, const double* seed_r, int64_t nseed, int stride) = 0;
     virtual int counts(int64_t* nv, int64_t* nr, int64_t* msl) = 0;
@@ -669,6 +670,37 @@ struct Ctx : hvb_ctx {
         k_volumes_finish<<<blocks_for(n_list, 256), 256, 0, stream>>>(vol_acc.p, 1.0 / (scale * fact), vol_dev.p, n_list); ++launches;
         if (nrays > 0) { k_volumes_unbounded<<<blocks_for(nrays * D, 256), 256, 0, stream>>>(ray_edge.p, (long long)nrays * D, n_list, vol_dev.p); ++launches; }
         CK(cudaMemcpyAsync(vol, vol_dev.p, (size_t)n_list * sizeof(double), cudaMemcpyDeviceToHost, stream));
+        CK(cudaStreamSynchronize(stream));
+        CK(cudaGetLastError());
+        st.kernel_launches = launches;
+        return HVB_OK;
+    }
+
+    // interface areas aligned with the neighbour lists (hvb_geometry.cuh, first facet fixed)
+    int cell_areas(double* area) override {
+        if (!have_result) { err = "no search result"; return HVB_ESTATE; }
+        if (!area) { err = "null output"; return HVB_EINVAL; }
+        if (seed_prefix > 0) { err = "interface areas need all vertices of the cells: not available after a search with seed vertices"; return HVB_ESTATE; }
+        int rc = build_neighbors(); if (rc) return rc;
+        CK(cudaSetDevice(prm.device));
+        const long long n_list = periodic ? n_user : n;
+        const long long tot = std::max<long long>(nb_total, 1);
+        CK(vol_acc.ensure(tot)); CK(vol_dev.ensure(tot));
+        CK(cudaMemsetAsync(vol_acc.p, 0, (size_t)tot * sizeof(long long), stream));
+        double fact = 1.0;
+        for (int k = 2; k <= D - 1; ++k) fact *= k;
+        const double scale = ldexp(1.0, 52) / (pow(dv.ext, (double)(D - 1)) * fact);
+        if (nvert > 0 && nb_total > 0) {
+            k_cell_areas<D><<<blocks_for(nvert, 128), 128, 0, stream>>>(out_sig[res].p, (u32)nvert, xs_in.p, (long long)n, n_list, planes.p,
+                                                                       nb_off.p, nb_ids.p, scale, vol_acc.p);
+            ++launches;
+        }
+        k_volumes_finish<<<blocks_for(tot, 256), 256, 0, stream>>>(vol_acc.p, 1.0 / (scale * fact), vol_dev.p, tot); ++launches;
+        if (nrays > 0 && nb_total > 0) {
+            k_areas_unbounded<<<blocks_for(nrays, 256), 256, 0, stream>>>(ray_edge.p, (long long)nrays, D, n_list, nb_off.p, nb_ids.p, vol_dev.p);
+            ++launches;
+        }
+        if (nb_total > 0) CK(cudaMemcpyAsync(area, vol_dev.p, (size_t)nb_total * sizeof(double), cudaMemcpyDeviceToHost, stream));
         CK(cudaStreamSynchronize(stream));
         CK(cudaGetLastError());
         st.kernel_launches = launches;
@@ -1252,6 +1284,7 @@ int hvb_halo_count(hvb_ctx* ctx, int64_t* nhalo, int32_t* npairs, double* margin
 int hvb_fetch_halo(hvb_ctx* ctx, int64_t* origin, int32_t* mult, double* xs) { return ctx ? ctx->fetch_halo(origin, mult, xs) : HVB_EINVAL; }
 int hvb_fetch_vertex_flags(hvb_ctx* ctx, uint8_t* flags) { return ctx ? ctx->fetch_vertex_flags(flags) : HVB_EINVAL; }
 int hvb_cell_volumes(hvb_ctx* ctx, double* vol) { return ctx ? ctx->cell_volumes(vol) : HVB_EINVAL; }
+int hvb_cell_areas(hvb_ctx* ctx, double* area) { return ctx ? ctx->cell_areas(area) : HVB_EINVAL; }
 int hvb_stats(hvb_ctx* ctx, hvb_stats_t* out) {
     if (!ctx || !out) return HVB_EINVAL;
     *out = ctx->st;

@@ -22,13 +22,17 @@ namespace hvb {
 // sum over the d! orders of the products of signed heights for the vertex with caller-numbered signature s[0..D]
 // (1-based, generators <= n, plane p = n + p) seen from the cell of the generator at position `pos`.
 // xs: generators in caller order [n][D].  Divide the sum over all vertices of the cell by d! for the volume.
+// `first` (a position of s other than pos, or -1): only the orders that impose that facet first are summed and its own
+// height is left out of the products -- the vertex's share of (d-1)! times the (d-1)-volume of the interface between
+// the cell and s[first] (VoronoiData(...).area of the reference).
 template <int D>
-HVB_HD double vertex_flag_sum(const double* xs, long long n, const PlaneSet* ps, const long long* s, int pos) {
+HVB_HD double vertex_flag_sum(const double* xs, long long n, const PlaneSet* ps, const long long* s, int pos, int first = -1) {
     double nrm[D][D], b[D];
     const double* xi = xs + (size_t)(s[pos] - 1) * D;
-    int cnt = 0;
+    int cnt = 0, jfirst = -1;
     for (int k = 0; k < D + 1; ++k) {
         if (k == pos) continue;
+        if (k == first) jfirst = cnt;
         const long long g = s[k];
         if (g <= n) {
             const double* xg = xs + (size_t)(g - 1) * D;
@@ -53,6 +57,7 @@ HVB_HD double vertex_flag_sum(const double* xs, long long n, const PlaneSet* ps,
     double total = 0.0;
     for (;;) {
         int j = it[depth] + 1;
+        if (depth == 0 && jfirst >= 0) j = (it[0] < jfirst) ? jfirst : D;      // one choice at the top level
         while (j < D && ((used >> j) & 1u)) ++j;
         if (j >= D) {                                   // this level is exhausted: back to the previous one
             if (depth == 0) break;
@@ -75,9 +80,10 @@ HVB_HD double vertex_flag_sum(const double* xs, long long n, const PlaneSet* ps,
         const double len = sqrt(len2);
         // moving along the unit direction m/len changes n_j.y by m.n_j/len = len: signed height of the facet over the foot
         const double h = (len > 0) ? (b[j] - nc) / len : 0.0;
-        if (depth + 1 == D) { total += prod[depth] * h; continue; }      // a vertex is reached: one flag
+        const double hf = (depth == 0 && jfirst >= 0) ? 1.0 : h;          // the interface's own height is not part of its area
+        if (depth + 1 == D) { total += prod[depth] * hf; continue; }     // a vertex is reached: one flag
         for (int a = 0; a < D; ++a) { Q[depth][a] = m[a] / len; c[depth + 1][a] = c[depth][a] + h * Q[depth][a]; }
-        prod[depth + 1] = prod[depth] * h;
+        prod[depth + 1] = prod[depth] * hf;
         used |= 1u << j;
         ++depth;
         it[depth] = -1;

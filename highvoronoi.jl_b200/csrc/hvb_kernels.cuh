@@ -689,6 +689,48 @@ __global__ void k_volumes_finish(const long long* __restrict__ acc, double inv_s
     long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
     if (i < n) vol[i] = (double)acc[i] * inv_scale;
 }
+// interface areas aligned with the CSR neighbour lists: entry k of cell i's list (ids ascending) receives the (d-1)-volume
+// of the facet between the cells of i and ids[k] (a generator, a halo generator or a boundary plane)
+__device__ __forceinline__ long long csr_find(const long long* __restrict__ off, const long long* __restrict__ ids, long long cell, long long id) {
+    long long lo = off[cell - 1], hi = off[cell];
+    while (lo < hi) { const long long mid = (lo + hi) >> 1; if (ids[mid] < id) lo = mid + 1; else hi = mid; }
+    return (lo < off[cell] && ids[lo] == id) ? lo : -1;
+}
+template <int D>
+__global__ void k_cell_areas(const long long* __restrict__ sig, u32 nv, const double* __restrict__ xs, long long n, long long n_list,
+                             const PlaneSet* __restrict__ ps, const long long* __restrict__ off, const long long* __restrict__ ids,
+                             double scale, long long* __restrict__ acc) {
+    u32 v = blockIdx.x * blockDim.x + threadIdx.x;
+    if (v >= nv) return;
+    long long s[D + 1];
+#pragma unroll
+    for (int k = 0; k < D + 1; ++k) s[k] = sig[(size_t)v * (D + 1) + k];
+    for (int k = 0; k < D + 1; ++k) {
+        if (s[k] > n_list) continue;
+        for (int q = 0; q < D + 1; ++q) {
+            if (q == k) continue;
+            const long long pos = csr_find(off, ids, s[k], s[q]);
+            if (pos < 0) continue;
+            const double t = vertex_flag_sum<D>(xs, n, ps, s, k, q) * scale;
+            atomicAdd(reinterpret_cast<unsigned long long*>(acc + pos), (unsigned long long)__double2ll_rn(t));
+        }
+    }
+}
+// facets that contain an unbounded edge have no finite area
+__global__ void k_areas_unbounded(const long long* __restrict__ ray_edge, long long nrays, int D, long long n_list,
+                                  const long long* __restrict__ off, const long long* __restrict__ ids, double* __restrict__ area) {
+    long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (i >= nrays) return;
+    const long long* e = ray_edge + i * D;
+    for (int a = 0; a < D; ++a) {
+        if (e[a] < 1 || e[a] > n_list) continue;
+        for (int b = 0; b < D; ++b) {
+            if (a == b) continue;
+            const long long pos = csr_find(off, ids, e[a], e[b]);
+            if (pos >= 0) area[pos] = INFINITY;
+        }
+    }
+}
 // cells with an unbounded edge have no finite volume
 __global__ void k_volumes_unbounded(const long long* __restrict__ ray_edge, long long nentries, long long n_list, double* __restrict__ vol) {
     long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;

@@ -202,6 +202,11 @@ int hvb_adopt_device_padded(hvb_ctx* ctx, const void* sig_dev, const void* r_dev
  * cells of Iter otherwise; HVB_ESTATE after a search with seed vertices.  Sums are accumulated in 64-bit fixed point:
  * the result does not depend on the order of the atomics. */
 int hvb_cell_volumes(hvb_ctx* ctx, double* vol);
+/* The same for the interfaces (VoronoiData(...).area): area[k] is the (d-1)-volume of the facet between cell i and
+ * ids[k] for every entry k of the CSR neighbour lists of hvb_fetch_neighbors (offsets[i-1] <= k < offsets[i]); the
+ * neighbour may be a generator, a halo generator or a boundary plane.  hvb_neighbor_count entries.  Facets that hold an
+ * unbounded edge get +inf.  Same completeness rule and the same fixed-point accumulation as hvb_cell_volumes. */
+int hvb_cell_areas(hvb_ctx* ctx, double* area);
 
 int hvb_stats(hvb_ctx* ctx, hvb_stats_t* out);
 

@@ -129,6 +129,35 @@ static void volumes(int64_t n, const double* xs, int P, const double* base, cons
         for (int k = 0; k <= D; ++k) if (s[k] <= n) vol[s[k] - 1] += vertex_flag_sum<D>(xs, n, &ps, s, k) / fact;
     }
 }
+// interface areas aligned with the CSR neighbour lists (off[n+1], ids ascending per cell)
+template <int D>
+static void areas(int64_t n, const double* xs, int P, const double* base, const double* normal, int64_t nv, const int64_t* sig,
+                  const int64_t* off, const int64_t* ids, double* area) {
+    PlaneSet ps; memset(&ps, 0, sizeof(ps)); ps.P = P;
+    for (int p = 0; p < P; ++p) {
+        double nr = 0; for (int k = 0; k < D; ++k) nr += normal[p * D + k] * normal[p * D + k];
+        nr = sqrt(nr); double o = 0;
+        for (int k = 0; k < D; ++k) { ps.normal[p * 6 + k] = normal[p * D + k] / nr; o += ps.normal[p * 6 + k] * base[p * D + k]; }
+        ps.off[p] = o;
+    }
+    double fact = 1; for (int k = 2; k <= D - 1; ++k) fact *= k;
+    for (int64_t i = 0; i < off[n]; ++i) area[i] = 0;
+    for (int64_t v = 0; v < nv; ++v) {
+        long long s[D + 1];
+        for (int k = 0; k <= D; ++k) s[k] = sig[v * (D + 1) + k];
+        for (int k = 0; k <= D; ++k) {
+            if (s[k] > n) continue;
+            for (int q = 0; q <= D; ++q) {
+                if (q == k) continue;
+                const int64_t* a = ids + off[s[k] - 1]; const int64_t* b = ids + off[s[k]];
+                const int64_t* it = std::lower_bound(a, b, (int64_t)s[q]);
+                if (it == b || *it != s[q]) continue;
+                area[it - ids] += vertex_flag_sum<D>(xs, n, &ps, s, k, q) / fact;
+            }
+        }
+    }
+}
+
 extern "C" {
 void* hostsim_run(int dim, int64_t n, const double* xs, int P, const double* base, const double* normal,
                   int ppc, double probe_scale, int fp32, int seed_stride) {
@@ -155,6 +184,16 @@ void hostsim_fetch(void* h, int64_t* sig, double* r, int64_t* ray_edge) {
 }
 void hostsim_free(void* h) { delete (SimResult*)h; }
 
+void hostsim_areas(int dim, int64_t n, const double* xs, int P, const double* base, const double* normal, int64_t nv, const int64_t* sig,
+                   const int64_t* off, const int64_t* ids, double* area) {
+    switch (dim) {
+        case 2: areas<2>(n, xs, P, base, normal, nv, sig, off, ids, area); break;
+        case 3: areas<3>(n, xs, P, base, normal, nv, sig, off, ids, area); break;
+        case 4: areas<4>(n, xs, P, base, normal, nv, sig, off, ids, area); break;
+        case 5: areas<5>(n, xs, P, base, normal, nv, sig, off, ids, area); break;
+        case 6: areas<6>(n, xs, P, base, normal, nv, sig, off, ids, area); break;
+    }
+}
 void hostsim_volumes(int dim, int64_t n, const double* xs, int P, const double* base, const double* normal, int64_t nv, const int64_t* sig, double* vol) {
     switch (dim) {
         case 2: volumes<2>(n, xs, P, base, normal, nv, sig, vol); break;

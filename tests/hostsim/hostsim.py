@@ -60,3 +60,21 @@ def volumes(xs, sig, base=None, normal=None):
     P = lambda a: a.ctypes.data_as(ctypes.c_void_p)
     L.hostsim_volumes(d, n, P(xs), base.shape[0], P(base), P(normal), sig.shape[0], P(sig), P(vol))
     return vol
+
+
+def areas(xs, sig, off, ids, base=None, normal=None):
+    """interface areas aligned with the CSR neighbour lists, with the product's own formula on the host"""
+    L = ctypes.CDLL(build())
+    L.hostsim_areas.restype = None
+    L.hostsim_areas.argtypes = [ctypes.c_int, ctypes.c_int64, ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p,
+                                ctypes.c_int64, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]
+    xs = np.ascontiguousarray(xs, dtype=np.float64)
+    n, d = xs.shape
+    if base is None:
+        base = np.zeros((0, d)); normal = np.zeros((0, d))
+    base = np.ascontiguousarray(base, dtype=np.float64); normal = np.ascontiguousarray(normal, dtype=np.float64)
+    sig = np.ascontiguousarray(sig, dtype=np.int64); off = np.ascontiguousarray(off, dtype=np.int64); ids = np.ascontiguousarray(ids, dtype=np.int64)
+    area = np.zeros(int(off[n]))
+    P = lambda a: a.ctypes.data_as(ctypes.c_void_p)
+    L.hostsim_areas(d, n, P(xs), base.shape[0], P(base), P(normal), sig.shape[0], P(sig), P(off), P(ids), P(area))
+    return area

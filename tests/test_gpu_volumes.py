@@ -76,3 +76,60 @@ def test_voronoi_data_volume_front_end(hvb):
     xs = points(2000, 3, 540)
     vd = hvb.VoronoiData(hvb.VoronoiGeometry(xs, hvb.cuboid(3, periodic=[])), getvolume=True)
     assert abs(vd.volume.sum() - 1.0) < 1e-11
+
+
+# ---- interface areas (hvb_cell_areas) ---------------------------------------------------------------------------
+@pytest.mark.parametrize("d,n", [(2, 2000), (3, 1200), (4, 400), (5, 120)])
+def test_areas_satisfy_volume_divergence_and_symmetry(hvb, d, n):
+    from util import area_invariants
+    xs = points(n, d, 550 + d)
+    mesh, _ = run(hvb, xs, hvb.cuboid(d, periodic=[]))
+    vol, area = mesh.volumes(), mesh.areas()
+    off, ids = mesh.neighbors()
+    off, ids = np.array(off), np.array(ids)
+    # fixed-point accumulation: 2^-52 (d-1)! of the unit face per term, so a facet smaller than ~1e-14 may read as 0
+    assert area.shape == ids.shape and (area > -1e-13).all() and (area > 0).mean() > 0.999
+    dv, dd, sym, face = area_invariants(xs, vol, off, ids, area, qhull_oracle.cuboid(d))
+    assert dv < 1e-10 and dd < 1e-10 and sym < 1e-10
+    assert np.abs(face - 1.0).max() < 1e-11                        # every face of the unit cube is tiled exactly once
+
+
+def test_areas_match_the_host_formula_and_are_reproducible(hvb):
+    import hostsim
+    xs = points(1500, 3, 560)
+    base, normal = qhull_oracle.cuboid(3)
+    mesh, _ = run(hvb, xs, hvb.cuboid(3, periodic=[]))
+    off, ids = mesh.neighbors()
+    a1, a2 = mesh.areas(), mesh.areas()
+    assert np.array_equal(a1, a2)
+    ref = hostsim.areas(xs, np.array(mesh.sig), np.array(off), np.array(ids), base, normal)
+    assert np.abs(a1 - ref).max() < 1e-12
+
+
+def test_unbounded_facets_have_infinite_area(hvb):
+    from util import area_invariants
+    xs = points(600, 3, 570)
+    mesh, _ = run(hvb, xs, hvb.Boundary())
+    vol, area = mesh.volumes(), mesh.areas()
+    off, ids = np.array(mesh.neighbors()[0]), np.array(mesh.neighbors()[1])
+    assert np.isinf(area).any() and (area[np.isfinite(area)] > 0).all()
+    # a cell is unbounded exactly if one of its facets is
+    cell_inf = np.array([np.isinf(area[off[i]:off[i + 1]]).any() for i in range(600)])
+    assert np.array_equal(cell_inf, np.isinf(vol))
+    dv, dd, sym, _ = area_invariants(xs, vol, off, ids, area)
+    assert dv < 1e-10 and dd < 1e-10 and sym < 1e-10               # the bounded cells
+
+
+def test_periodic_areas_close_every_cell(hvb):
+    xs = points(1500, 3, 580)
+    mesh, _ = run(hvb, xs, hvb.cuboid(3), periodic=True)
+    vol, area = mesh.volumes(), mesh.areas()
+    off, ids = np.array(mesh.neighbors()[0]), np.array(mesh.neighbors()[1])
+    ext = np.vstack([xs, mesh.halo_xs])
+    n = 1500
+    for i in range(n):
+        J, A = ids[off[i]:off[i + 1]], area[off[i]:off[i + 1]]
+        w = ext[J - 1] - xs[i]
+        L = np.linalg.norm(w, axis=1)
+        assert abs((A * L).sum() / 6 / vol[i] - 1.0) < 1e-10       # volume from the facets (d = 3: 1/d * area * |w|/2)
+        assert np.linalg.norm((A[:, None] * w / L[:, None]).sum(0)) / A.sum() < 1e-10

@@ -76,3 +76,20 @@ def test_cell_volume_formula_matches_qhull(d, n):
     for i in range(n):
         rows = (o["sig"] == i + 1).any(axis=1)
         assert abs(vol[i] / ConvexHull(o["r"][rows]).volume - 1.0) < 1e-10
+
+
+@pytest.mark.parametrize("d,n", [(2, 300), (3, 200), (4, 80), (5, 36)])
+def test_interface_area_formula_invariants(d, n):
+    """the area variant of vertex_flag_sum on the oracle's rows and neighbour lists: volume = 1/d sum area * height,
+    divergence theorem, symmetry, and the faces of the unit cube have area 1"""
+    import hv_oracle
+    from util import area_invariants
+    xs = points(n, d, 80 + d)
+    base, normal = qhull_oracle.cuboid(d)
+    o = hv_oracle.run(xs, base, normal)
+    vol = hostsim.volumes(xs, o["sig"], base, normal)
+    area = hostsim.areas(xs, o["sig"], o["nb_off"], o["nb_ids"], base, normal)
+    assert (area > 0).all()
+    dv, dd, sym, face = area_invariants(xs, vol, o["nb_off"], o["nb_ids"], area, (base, normal))
+    assert dv < 1e-11 and dd < 1e-11 and sym < 1e-11
+    assert np.abs(face - 1.0).max() < 1e-12

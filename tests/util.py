@@ -103,3 +103,37 @@ def empty_ball_violations(sig, r, xs, sample=2000, seed=0):
         if dev > 1e-9 * max(rad, 1e-12):
             bad += 1
     return bad
+
+
+def area_invariants(xs, vol, off, ids, area, planes=None):
+    """checks of interface areas that need no second implementation: (1) vol_i = 1/d * sum_j area_ij * height_ij,
+    (2) the divergence theorem sum_j area_ij * normal_ij = 0, (3) symmetry area_ij = area_ji between generators.
+    Returns (max relative volume defect, max |divergence| / surface, max symmetry defect relative to the largest area,
+    area per boundary plane).  Cells with an infinite entry are skipped."""
+    n, d = xs.shape
+    base, normal = planes if planes is not None else (np.zeros((0, d)), np.zeros((0, d)))
+    P = base.shape[0]
+    face = np.zeros(P)
+    dv = dd = 0.0
+    for i in range(n):
+        J, A = ids[off[i]:off[i + 1]], area[off[i]:off[i + 1]]
+        if not np.isfinite(A).all() or not np.isfinite(vol[i]):
+            continue
+        acc, div = 0.0, np.zeros(d)
+        for j, a in zip(J, A):
+            if j <= n:
+                w = xs[j - 1] - xs[i]; L = np.linalg.norm(w)
+                acc += a * L / 2 / d; div += a * w / L
+            elif j - n - 1 < P:
+                p = j - n - 1
+                nn = normal[p] / np.linalg.norm(normal[p])
+                acc += a * (nn @ (base[p] - xs[i])) / d; div += a * nn; face[p] += a
+        dv = max(dv, abs(acc / vol[i] - 1.0)); dd = max(dd, float(np.linalg.norm(div) / A.sum()))
+    sym, amax = 0.0, float(area[np.isfinite(area)].max())
+    for i in range(n):
+        for k in range(off[i], off[i + 1]):
+            j = ids[k]
+            if j <= n and np.isfinite(area[k]):
+                kk = off[j - 1] + np.searchsorted(ids[off[j - 1]:off[j]], i + 1)
+                sym = max(sym, abs(area[k] - area[kk]) / amax)
+    return dv, dd, sym, face
