@@ -12,7 +12,7 @@ ERROR_NAMES = {-1: "HVB_EINVAL", -2: "HVB_ECUDA", -3: "HVB_ENOGPU", -4: "HVB_ENO
 
 EXPORTS = ("hvb_default_params", "hvb_create", "hvb_set_points", "hvb_search", "hvb_counts", "hvb_fetch_vertices", "hvb_fetch_vertices_range", "hvb_fetch_rays",
            "hvb_neighbor_count", "hvb_fetch_neighbors", "hvb_view_vertices", "hvb_view_neighbors", "hvb_export_device", "hvb_merge_device", "hvb_adopt_device", "hvb_adopt_device_padded",
-           "hvb_stats", "hvb_last_error", "hvb_destroy", "hvb_version", "hvb_create_periodic", "hvb_halo_count", "hvb_fetch_halo", "hvb_fetch_vertex_flags", "hvb_cell_volumes", "hvb_cell_areas")
+           "hvb_stats", "hvb_last_error", "hvb_destroy", "hvb_version", "hvb_create_periodic", "hvb_halo_count", "hvb_fetch_halo", "hvb_fetch_vertex_flags", "hvb_cell_volumes", "hvb_cell_areas", "hvb_clean_affected")
 
 
 class hvb_params(ctypes.Structure):
@@ -63,6 +63,7 @@ def lib():
         L.hvb_fetch_vertex_flags.argtypes = [vp, vp]
         L.hvb_cell_volumes.argtypes = [vp, vp]
         L.hvb_cell_areas.argtypes = [vp, vp]
+        L.hvb_clean_affected.argtypes = [vp, vp, vp, i64, i32, i64, i64, vp, vp]
         L.hvb_set_points.argtypes = [vp, i64, vp]
         L.hvb_search.argtypes = [vp, vp, i64, vp, vp, i64, i32]
         L.hvb_counts.argtypes = [vp, ctypes.POINTER(i64), ctypes.POINTER(i64), ctypes.POINTER(i64)]
@@ -83,7 +84,7 @@ def lib():
         L.hvb_destroy.argtypes = [vp]
         L.hvb_destroy.restype = None
         L.hvb_version.restype = ctypes.c_char_p
-        for name in ("hvb_cell_volumes", "hvb_cell_areas", "hvb_create", "hvb_create_periodic", "hvb_halo_count", "hvb_fetch_halo", "hvb_fetch_vertex_flags", "hvb_set_points", "hvb_search", "hvb_counts", "hvb_fetch_vertices", "hvb_fetch_vertices_range", "hvb_fetch_rays", "hvb_neighbor_count",
+        for name in ("hvb_cell_volumes", "hvb_cell_areas", "hvb_clean_affected", "hvb_create", "hvb_create_periodic", "hvb_halo_count", "hvb_fetch_halo", "hvb_fetch_vertex_flags", "hvb_set_points", "hvb_search", "hvb_counts", "hvb_fetch_vertices", "hvb_fetch_vertices_range", "hvb_fetch_rays", "hvb_neighbor_count",
                      "hvb_fetch_neighbors", "hvb_view_vertices", "hvb_view_neighbors", "hvb_export_device", "hvb_merge_device", "hvb_adopt_device", "hvb_adopt_device_padded", "hvb_stats"):
             getattr(L, name).restype = i32
         _lib = L

@@ -318,6 +318,29 @@ def voronoi(xs, searcher=None, Iter=None, copy=False, known=None, **_ignored):
     return VoronoiMesh(searcher, copy=copy), searcher
 
 
+def refine(searcher, new_xs, old_xs, old_sig, old_r):
+    """systematic_refine! (meshrefine.jl:183-216) on the device: new_xs are PREPENDED to the generators as the reference does
+    (new ids 1..m, old ids shift by m, plane p = n + p), the old mesh (old_sig, old_r in the OLD numbering) loses the
+    vertices whose ball a new node invades (hvb_clean_affected), the new cells are explored (hvb_search with Iter = 1:m).
+    Returns (xs_all, sig, r, affected): the vertices of the refined mesh, sorted, and the 1-based ids of the affected cells."""
+    new_xs, old_xs = VoronoiNodes(new_xs), VoronoiNodes(old_xs)
+    m, n0 = new_xs.shape[0], old_xs.shape[0]
+    xs_all = np.ascontiguousarray(np.vstack([new_xs, old_xs]))
+    searcher.set_points(xs_all)
+    sig = np.ascontiguousarray(np.asarray(old_sig, dtype=np.int64) + m)          # generators and planes shift alike
+    r = np.ascontiguousarray(old_r, dtype=np.float64)
+    keep = np.zeros(sig.shape[0], dtype=np.uint8)
+    affected = np.zeros(n0 + m, dtype=np.uint8)
+    L, ctx = _abi.lib(), searcher._ctx
+    P = lambda a: a.ctypes.data_as(ctypes.c_void_p)
+    _abi.check(L.hvb_clean_affected(ctx, P(sig), P(r), sig.shape[0], sig.shape[1], 1, m, P(keep), P(affected)), ctx)
+    mesh, _ = voronoi(xs_all, searcher=searcher, Iter=range(1, m + 1), copy=True)
+    all_sig = np.vstack([sig[keep.astype(bool)], mesh.sig])
+    all_r = np.vstack([r[keep.astype(bool)], mesh.r])
+    order = np.lexsort(all_sig.T[::-1])
+    return xs_all, all_sig[order], all_r[order], np.nonzero(affected)[0] + 1
+
+
 class VoronoiGeometry:
     """VoronoiGeometry(xs, b; search_settings=(...)) (geometry.jl:139-201), restricted to what this path produces:
     the vertex database and the neighbour lists (integrate=false)."""

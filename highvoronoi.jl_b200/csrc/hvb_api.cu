@@ -120,6 +120,7 @@ struct hvb_ctx {
     virtual int fetch_vertex_flags(uint8_t* flags) = 0;
     virtual int cell_volumes(double* vol) = 0;
     virtual int cell_areas(double* area) = 0;
+    virtual int clean_affected(const int64_t* sig, const double* r, int64_t nv, int stride, int64_t first_new, int64_t n_new, uint8_t* keep, uint8_t* affected) = 0;
     virtual int set_points(int64_t n, const double* xs) = 0;
     virtual int search(const int64_t* cells, int64_t ncells, const int64_t* seed_sig, const double* seed_r, int64_t nseed, int stride) = 0;
     virtual int counts(int64_t* nv, int64_t* nr, int64_t* msl) = 0;
@@ -230,7 +231,7 @@ struct Ctx : hvb_ctx {
         if (sstream2) { cudaStreamSynchronize(sstream2); cudaStreamDestroy(sstream2); }
         if (ev_p0) cudaEventDestroy(ev_p0);
         if (ev_p1) cudaEventDestroy(ev_p1);
-        vol_acc.release(); vol_dev.release();
+        vol_acc.release(); vol_dev.release(); ca_keep.release(); ca_aff.release();
         halo_cnt.release(); halo_off.release(); halo_origin.release(); halo_mult.release(); vflags.release(); cert.release(); h_cert.release();
         if (sstream) { cudaStreamSynchronize(sstream); cudaStreamDestroy(sstream); }
         if (stream) cudaStreamDestroy(stream);
@@ -673,6 +674,33 @@ struct Ctx : hvb_ctx {
         CK(cudaStreamSynchronize(stream));
         CK(cudaGetLastError());
         st.kernel_launches = launches;
+        return HVB_OK;
+    }
+
+    // clean_affected! (meshrefine.jl:126-149): which vertices of the caller's old mesh survive the new generators
+    DBuf<unsigned char> ca_keep, ca_aff;
+    int clean_affected(const int64_t* sig, const double* r, int64_t nv, int stride, int64_t first_new, int64_t n_new, uint8_t* keep, uint8_t* affected) override {
+        if (periodic) { err = "refinement is not supported on a periodic context"; return HVB_EINVAL; }
+        if (nv < 0 || stride < 1 || (nv > 0 && (!sig || !r || !keep)) || !affected) { err = "bad arguments"; return HVB_EINVAL; }
+        if (first_new < 1 || n_new < 0 || first_new + n_new - 1 > n) { err = "the new generators must be a range of the context's ids"; return HVB_EINVAL; }
+        CK(cudaSetDevice(prm.device));
+        CK(seed_sig_dev.ensure((size_t)std::max<int64_t>(nv, 1) * stride)); CK(seed_r_dev.ensure((size_t)std::max<int64_t>(nv, 1) * D));
+        CK(ca_keep.ensure(std::max<int64_t>(nv, 1))); CK(ca_aff.ensure(n));
+        CK(cudaMemsetAsync(ca_aff.p, 0, n, stream));
+        CK(cudaMemsetAsync(&sc.p->pflags, 0, sizeof(u32), stream));
+        if (nv > 0) {
+            CK(cudaMemcpyAsync(seed_sig_dev.p, sig, (size_t)nv * stride * 8, cudaMemcpyHostToDevice, stream));
+            CK(cudaMemcpyAsync(seed_r_dev.p, r, (size_t)nv * D * 8, cudaMemcpyHostToDevice, stream));
+            k_clean_affected<D><<<blocks_for(nv, 128), 128, 0, stream>>>(dv, perm.p, seed_sig_dev.p, seed_r_dev.p, nv, stride, xs_in.p,
+                                                                        first_new - 1, first_new - 1 + n_new, ca_keep.p, ca_aff.p, &sc.p->pflags);
+            ++launches;
+            CK(cudaMemcpyAsync(keep, ca_keep.p, (size_t)nv, cudaMemcpyDeviceToHost, stream));
+        }
+        CK(cudaMemcpyAsync(affected, ca_aff.p, (size_t)n, cudaMemcpyDeviceToHost, stream));
+        int rc = read_scalars(); if (rc) return rc;
+        CK(cudaGetLastError());
+        if (h_sc.p->pflags) { err = "a vertex row without a generator id of this context"; return HVB_EINVAL; }
+        for (int64_t i = first_new - 1; i < first_new - 1 + n_new; ++i) affected[i] = 1;      // the new cells themselves
         return HVB_OK;
     }
 
@@ -1285,6 +1313,9 @@ int hvb_fetch_halo(hvb_ctx* ctx, int64_t* origin, int32_t* mult, double* xs) { r
 int hvb_fetch_vertex_flags(hvb_ctx* ctx, uint8_t* flags) { return ctx ? ctx->fetch_vertex_flags(flags) : HVB_EINVAL; }
 int hvb_cell_volumes(hvb_ctx* ctx, double* vol) { return ctx ? ctx->cell_volumes(vol) : HVB_EINVAL; }
 int hvb_cell_areas(hvb_ctx* ctx, double* area) { return ctx ? ctx->cell_areas(area) : HVB_EINVAL; }
+int hvb_clean_affected(hvb_ctx* ctx, const int64_t* sig, const double* r, int64_t nv, int sig_stride, int64_t first_new, int64_t n_new, uint8_t* keep, uint8_t* affected) {
+    return ctx ? ctx->clean_affected(sig, r, nv, sig_stride, first_new, n_new, keep, affected) : HVB_EINVAL;
+}
 int hvb_stats(hvb_ctx* ctx, hvb_stats_t* out) {
     if (!ctx || !out) return HVB_EINVAL;
     *out = ctx->st;

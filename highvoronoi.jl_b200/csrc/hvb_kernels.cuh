@@ -668,6 +668,56 @@ __global__ void k_u32_to_i64(const u32* __restrict__ a, long long* __restrict__ 
 }
 
 // ------------------------------------------------------------------------------------------------------------
+// refinement: clean_affected! (meshrefine.jl:126-149) on the device.  The context holds ALL generators
+// (old and new); a vertex of the old mesh survives iff no NEW generator lies inside its ball: the reference keeps
+// it iff |x_sig1 - r| <= (1 + 1e-7) * dist(r, nearest new node).  Generators of removed vertices are marked affected.
+// ------------------------------------------------------------------------------------------------------------
+template <int D>
+__global__ void k_clean_affected(Dev<D> dv, const int* __restrict__ perm, const long long* __restrict__ sig, const double* __restrict__ r,
+                                 long long nv, int stride, const double* __restrict__ xs, long long new_lo, long long new_hi,
+                                 unsigned char* __restrict__ keep, unsigned char* __restrict__ affected, u32* __restrict__ bad) {
+    long long v = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (v >= nv) return;
+    const long long* s = sig + v * stride;
+    long long g0 = 0;
+    for (int k = 0; k < stride && g0 == 0; ++k) if (s[k] >= 1 && s[k] <= dv.n) g0 = s[k];
+    if (g0 == 0) { atomicAdd(bad, 1u); keep[v] = 0; return; }        // a vertex names at least one generator
+    RayQ<D> q;
+    double cen[D], R2 = 0;
+#pragma unroll
+    for (int k = 0; k < D; ++k) { cen[k] = r[v * D + k]; const double t = xs[(size_t)(g0 - 1) * D + k] - cen[k]; R2 += t * t; q.u[k] = 0.0; q.x0[k] = cen[k]; }
+    const double rho = sqrt(R2);
+    int clo[D], chi[D], nrows = 1;
+    bool empty = false;
+#pragma unroll
+    for (int k = 0; k < D; ++k) {
+        const double gk = (double)dv.g[k];
+        const double vlo = fmin(fmax((cen[k] - rho - dv.lo[k]) * dv.inv_h[k] - 1e-9, 0.0), gk - 1.0);
+        const double vhi = fmin(fmax((cen[k] + rho - dv.lo[k]) * dv.inv_h[k] + 1e-9, -1.0), gk - 1.0);
+        clo[k] = (int)floor(vlo); chi[k] = (int)floor(vhi);
+        if (chi[k] < clo[k]) empty = true;
+        if (k < D - 1) nrows *= (chi[k] - clo[k] + 1);
+    }
+    bool invaded = false;
+    const double lim = R2 / ((1.0 + 1e-7) * (1.0 + 1e-7));
+    for (int j = 0; j < nrows && !empty && !invaded; ++j) {
+        int pa = 0, pb = 0;
+        if (!row_range<D>(dv, q, clo, chi, cen, R2 * (1.0 + 1e-12) + 1e-300, j, pa, pb)) continue;     // u = 0: no half-space clipping
+        for (int p = pa; p < pb && !invaded; ++p) {
+            const long long cid = perm[p];
+            if (cid < new_lo || cid >= new_hi) continue;
+            double d2 = 0;
+#pragma unroll
+            for (int k = 0; k < D; ++k) { const double t = dv.x64[(size_t)p * D + k] - cen[k]; d2 += t * t; }
+            invaded = d2 < lim;
+        }
+    }
+    keep[v] = invaded ? 0 : 1;
+    if (invaded)
+        for (int k = 0; k < stride; ++k) if (s[k] >= 1 && s[k] <= dv.n) affected[s[k] - 1] = 1;
+}
+
+// ------------------------------------------------------------------------------------------------------------
 // cell volumes from the result rows (hvb_geometry.cuh).  One thread per row; the d+1 contributions of a row are added
 // in 64-bit fixed point, so the sums do not depend on the order of the atomics (bitwise reproducible volumes).
 // ------------------------------------------------------------------------------------------------------------

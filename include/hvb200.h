@@ -193,6 +193,17 @@ int hvb_adopt_device(hvb_ctx* ctx, const void* sig_dev, const void* r_dev, int64
 int hvb_adopt_device_padded(hvb_ctx* ctx, const void* sig_dev, const void* r_dev, int nseg, int64_t seg_cap, const int64_t* counts);
 
 /* rare_events / statistics.jl:132-143 analogue */
+/* Refinement.  Replaces clean_affected! (src/meshrefine.jl:126-149) inside systematic_refine! (:183-216):
+ * the context holds ALL generators, old and new (hvb_set_points), the new ones being the id range
+ * [first_new, first_new + n_new) (the reference prepends them: first_new = 1); sig/r are the nv vertices of the caller's
+ * old mesh in the numbering of the context (sig_stride entries per row, 0 = unused, plane p = n + p).  keep[v] = 1 iff
+ * no new generator lies inside the ball of vertex v -- the reference's rule |x_sig1 - r| <= (1 + 1e-7) * dist(r, nearest
+ * new node); affected[i] = 1 (n entries) for the new cells and for every generator of a removed vertex.  The new mesh is
+ * the surviving rows plus the rows of hvb_search(ctx, new ids, n_new, ...): every vertex that is not an old one names
+ * a new generator, so exploring the new cells finds them all (the reference's 1st Voronoi pass, meshrefine.jl:199). */
+int hvb_clean_affected(hvb_ctx* ctx, const int64_t* sig, const double* r, int64_t nv, int sig_stride,
+                       int64_t first_new, int64_t n_new, uint8_t* keep, uint8_t* affected);
+
 /* Geometry product: volumes of the cells of the caller's generators, computed on the device from the
  * current result rows by the signed flag decomposition of a simple polytope (hvb_geometry.cuh); replaces, for general
  * position, the reference's VI_POLYGON volume pass (integrate.jl:33-53, polyintegrator.jl) behind VoronoiData(...).volume

@@ -104,6 +104,22 @@ function _voronoi(mesh::AM, TODO, compact, v_offset, silence, iteration_reset, p
 end
 
 """
+    clean_affected(ctx, sig, r, lnxs, n) -> (keep, affected)
+
+`clean_affected!` (meshrefine.jl:126-149) on the device: `sig` (d+1 x nv, ids of the context that already holds the
+prepended new nodes 1..lnxs) and `r` (d x nv) are the old mesh; `keep[v]` tells whether vertex v survives the new
+nodes, `affected[i]` marks the new cells and the generators of removed vertices.
+"""
+function clean_affected(ctx::Ptr{Cvoid}, sig::Matrix{Int64}, r::Matrix{Float64}, lnxs::Integer, n::Integer)
+    nv = size(sig, 2)
+    keep = Vector{UInt8}(undef, nv); affected = Vector{UInt8}(undef, n)
+    check(ccall((:hvb_clean_affected, LIB), Cint,
+                (Ptr{Cvoid}, Ptr{Int64}, Ptr{Float64}, Int64, Cint, Int64, Int64, Ptr{UInt8}, Ptr{UInt8}),
+                ctx, sig, r, nv, size(sig, 1), 1, lnxs, keep, affected), ctx)
+    return keep, affected
+end
+
+"""
     cell_volumes(ctx, n) -> Vector{Float64}
 
 Volumes of the cells from the vertex rows the context holds (`hvb_cell_volumes`): what `VoronoiData(VG, getvolume=true).volume`
