@@ -3,7 +3,7 @@
 The directory is called `highvoronoi.jl_b200`; because of the dot it is imported through the loader module
 `hvb200.py` at the repository root (`import hvb200`)."""
 from . import _abi  # noqa: F401
-from .api import (refine, B200Thread, Boundary, HVBError, Raycast, RaycastParameter, RCCombined, RCNonGeneral,  # noqa: F401
+from .api import (refine, ConvexHull, B200Thread, Boundary, HVBError, Raycast, RaycastParameter, RCCombined, RCNonGeneral,  # noqa: F401
                   RCNonGeneralFast, RCNonGeneralHP, RCOriginal, RCStandard, SingleThread, VoronoiData,
                   VoronoiGeometry, VoronoiMesh, VoronoiNodes, cuboid, voronoi)
 

@@ -341,6 +341,40 @@ def refine(searcher, new_xs, old_xs, old_sig, old_r):
     return xs_all, all_sig[order], all_r[order], np.nonzero(affected)[0] + 1
 
 
+class ConvexHull:
+    """ConvexHull(xs) (chull.jl:213-238, docs/src/man/convexhull.md): `len(cv)` surface elements, `cv[i] = (sig, r, u)` with
+    sig the d generating nodes (1-based, sorted), r a point of the facet's plane and u its outer unit normal.
+
+    General position only.  The reference walks the hull facets directly (systematic_chull, chull.jl:241-387); here the
+    facets are read off the search this backend already runs: a facet of the hull is the dual of an unbounded Voronoi edge
+    (the d generators of the edge, the edge's direction as outer normal), i.e. one row of hvb_fetch_rays on the unbounded
+    domain.  Same result, but the whole tessellation is computed to get it."""
+
+    def __init__(self, xs, intro="", nthreads=None, method=None, options=None):
+        xs = VoronoiNodes(xs)
+        s = Raycast(xs, domain=Boundary(), options=options or RaycastParameter())
+        try:
+            mesh, _ = voronoi(xs, searcher=s, copy=True)
+            order = np.lexsort(mesh.ray_edge.T[::-1]) if len(mesh.ray_edge) else np.zeros(0, dtype=np.int64)
+            self.sig = mesh.ray_edge[order]
+            self.u = mesh.ray_dir[order]
+            base = mesh.ray_base[order]
+        finally:
+            s.close()
+        self.xs = xs
+        # the reference projects the stored point onto the facet's plane (chull.jl:224-232)
+        self.r = base + self.u * ((xs[self.sig[:, 0] - 1] - base) * self.u).sum(axis=1)[:, None] if len(self.sig) else base
+
+    def __len__(self):
+        return self.sig.shape[0]
+
+    def __getitem__(self, i):
+        return self.sig[i].copy(), self.r[i].copy(), self.u[i].copy()
+
+    def __iter__(self):
+        return (self[i] for i in range(len(self)))
+
+
 class VoronoiGeometry:
     """VoronoiGeometry(xs, b; search_settings=(...)) (geometry.jl:139-201), restricted to what this path produces:
     the vertex database and the neighbour lists (integrate=false)."""
