@@ -31,7 +31,7 @@ class hvb_stats_t(ctypes.Structure):
                [(k, ctypes.c_double) for k in ("ms_build", "ms_search", "ms_finalize", "ms_expand_kernel")] + \
                [("expand_launches", ctypes.c_int64), ("expand_items", ctypes.c_int64)] + \
                [(k, ctypes.c_double) for k in ("ms_seed", "ms_neighbors", "ms_rows_sort")] + \
-               [(k, ctypes.c_int64) for k in ("halo_nodes", "unique_vertices", "periodic_retries")] + [("ms_stage_wait", ctypes.c_double)]
+               [(k, ctypes.c_int64) for k in ("halo_nodes", "unique_vertices", "periodic_retries")] + [("ms_stage_wait", ctypes.c_double), ("ms_upload", ctypes.c_double)]
 
     def as_dict(self):
         return {k: getattr(self, k) for k, _ in self._fields_}

@@ -100,6 +100,7 @@ typedef struct hvb_stats_t {
     int64_t periodic_retries; /* searches repeated because the periodic certificate asked for a larger margin */
     double  ms_stage_wait;    /* time hvb_search waited, after the result was complete in HBM (end of ms_finalize), for the
                                  page-locked staging copies (D2H) that overlap the neighbour build */
+    double  ms_upload;        /* part of ms_build: the host -> device copy of the generators (hvb_create / hvb_set_points) */
 } hvb_stats_t;
 
 /* fills *p with the reference's defaults (RaycastParameter(Float64), raycast-types.jl:312-324) */
