@@ -1,0 +1,48 @@
+"""The bench.py contract on the CPU: the reference arm runs without a GPU and prints one JSON line with the agreed keys;
+the committed GPU bench line (profiles/r1_bench_C2.json) carries every key the contract names."""
+import json
+import os
+import subprocess
+import sys
+
+from conftest import ROOT
+
+BASE_KEYS = {"metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "vs_baseline",
+             "dtype", "data", "config", "e2e", "cpu_baseline"}
+
+
+def last_json_line(text):
+    lines = [l for l in text.splitlines() if l.startswith("{")]
+    assert lines, text[-2000:]
+    return json.loads(lines[-1])
+
+
+def test_reference_arm_runs_on_the_cpu():
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "1",
+                          "--ref-points", "3000"], capture_output=True, text=True, timeout=300, cwd=ROOT)
+    assert out.returncode == 0, out.stderr[-2000:]
+    j = last_json_line(out.stdout)
+    assert BASE_KEYS <= set(j) and j["impl"] == "reference" and j["metric"] == "voronoi_vertices_per_sec"
+    assert j["value"] > 0 and j["unit"] == "vertices/s" and j["higher_is_better"] is True
+    assert j["cpu_baseline"]["kind"] == "port" and j["cpu_baseline"]["cores"] >= 1 and j["cpu_baseline"]["value"] == j["value"]
+    assert j["e2e"] == {"value": j["value"], "unit": "vertices/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    assert "workload" in j["config"] and "model" not in j["config"]
+
+
+def test_reference_arm_other_ranks_exit_silently():
+    env = dict(os.environ, RANK="1", WORLD_SIZE="2", LOCAL_RANK="1")
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2", "--steps", "1", "--warmup", "0"],
+                         capture_output=True, text=True, timeout=120, cwd=ROOT, env=env)
+    assert out.returncode == 0 and out.stdout.strip() == ""
+
+
+def test_committed_gpu_line_carries_the_contract_keys():
+    j = last_json_line(open(os.path.join(ROOT, "profiles", "r1_bench_C2.json")).read())
+    assert BASE_KEYS | {"roofline", "clocks", "gpu_launches"} <= set(j)
+    assert j["metric"] == "voronoi_vertices_per_sec" and j["n_gpus"] == 1 and j["warmup"] >= 3 and j["dtype"] == "f64"
+    r = j["roofline"]
+    assert r["bound"] == "hbm" and r["unit"] == "GB/s" and abs(r["frac"] - r["achieved"] / r["peak"]) < 1e-12 and r["traffic"]
+    assert {"value", "unit", "h2d_bytes_per_step", "d2h_bytes_per_step"} <= set(j["e2e"]) and j["e2e"]["h2d_bytes_per_step"] > 0
+    assert j["gpu_launches"] > 0 and j["clocks"]["sm_mhz"] and not j["clocks"]["reasons"]
+    assert {"value", "unit", "cores", "kind", "sample"} <= set(j["cpu_baseline"])
+    assert "workload" in j["config"] and j["vs_baseline"] is None
