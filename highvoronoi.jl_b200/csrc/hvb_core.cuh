@@ -817,7 +817,7 @@ HVB_HD Best min_t_query(const Dev<D>& dv, const T& tile, const RayQ<D>& q, Local
                     const float tsh = fminf((float)best.t * 1.0000002f, 0.5f * flt.tb2 * 1.000001f);
                     if (tsh < 0.92f * Ts32) {
                         Ts32 = tsh;
-    #pragma unroll
+#pragma unroll
                         for (int k = 0; k < D; ++k) b32.cen[k] = fmaf(Ts32, uf[k], r32[k]);
                         const float dT = fabsf(Ts32 - a32) + 4e-7f * (fabsf(a32) + Ts32);
                         b32.rho2 = fmaf(dT, dT, perp2f) * 1.00001f;
@@ -826,7 +826,7 @@ HVB_HD Best min_t_query(const Dev<D>& dv, const T& tile, const RayQ<D>& q, Local
                     const double Tshr = fmin(best.t, 0.5 * (double)flt.tb2);
                     if (Tshr < 0.92 * Ts) {
                         Ts = Tshr;
-    #pragma unroll
+#pragma unroll
                         for (int k = 0; k < D; ++k) cen[k] = q.r[k] + Ts * q.u[k];
                         rho2 = (q.R0sq - 2.0 * Ts * q.a + Ts * Ts) * (1.0 + 1e-12) + 1e-300;
                         rho = sqrt(rho2);
