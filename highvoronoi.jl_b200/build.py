@@ -5,7 +5,7 @@ import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 SRC = os.path.join(HERE, "csrc", "hvb_api.cu")
-DEPS = [os.path.join(HERE, "csrc", f) for f in ("hvb_api.cu", "hvb_core.cuh", "hvb_kernels.cuh", "hvb_host.hpp")] + \
+DEPS = [os.path.join(HERE, "csrc", f) for f in ("hvb_api.cu", "hvb_core.cuh", "hvb_kernels.cuh", "hvb_coop.cuh", "hvb_geometry.cuh", "hvb_host.hpp")] + \
        [os.path.join(HERE, "..", "include", "hvb200.h")]
 OUT = os.path.join(HERE, "lib", "libhvb200.so")
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
