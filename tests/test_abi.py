@@ -70,3 +70,27 @@ def test_product_does_not_touch_the_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".hpp", ".h")):
                 text = open(os.path.join(dirpath, f)).read()
                 assert "hv_oracle" not in text and "qhull_oracle" not in text and "hostsim" not in text.replace("tests/hostsim", ""), f
+
+
+def _c_struct_fields(src, name):
+    body = re.search(r"typedef struct %s \{(.*?)\} %s;" % (name, name), src, flags=re.S).group(1)
+    body = re.sub(r"/\*.*?\*/", "", body, flags=re.S)
+    return [m.group(2) for m in re.finditer(r"\b(double|int32_t|int64_t)\s+([a-z_0-9]+)\s*;", body)]
+
+
+def test_struct_layouts_agree_across_header_python_and_julia(hvb):
+    """hvb_params / hvb_stats_t are mirrored by hand in _abi.py and in the Julia shim: same fields, same order"""
+    hdr = open(os.path.join(ROOT, "include", "hvb200.h")).read()
+    hdr = hdr.replace("typedef struct hvb_params {", "typedef struct hvb_params {").replace("} hvb_params;", "} hvb_params;")
+    params = _c_struct_fields(hdr, "hvb_params")
+    assert params == [f[0] for f in hvb._abi.hvb_params._fields_]
+    stats_body = re.search(r"typedef struct \{(.*?)\} hvb_stats_t;", hdr, flags=re.S)
+    if stats_body is None:
+        stats_body = re.search(r"typedef struct hvb_stats_t \{(.*?)\} hvb_stats_t;", hdr, flags=re.S)
+    body = re.sub(r"/\*.*?\*/", "", stats_body.group(1), flags=re.S)
+    stats = [m.group(2) for m in re.finditer(r"\b(double|int32_t|int64_t)\s+([a-z_0-9]+)\s*;", body)]
+    assert stats == [f[0] for f in hvb._abi.hvb_stats_t._fields_]
+    jl = open(os.path.join(ROOT, "julia", "HighVoronoiB200.jl")).read()
+    jbody = re.search(r"mutable struct HvbParams(.*?)HvbParams\(\) = new\(\)", jl, flags=re.S).group(1)
+    jfields = re.findall(r"([a-z_0-9]+)::(?:Cdouble|Int32|Int64)", jbody)
+    assert jfields == params
