@@ -26,6 +26,11 @@
 #define HVB_D inline
 #endif
 
+// trace hook of the host build (tests/hostsim records per-ray row / point counts for tools/simt_model.py); nothing on the device
+#ifndef HVB_TRACE_EVENT
+#define HVB_TRACE_EVENT(kind, val)
+#endif
+
 #ifndef HVB_MAX_PLANES
 #define HVB_MAX_PLANES 32
 #endif
@@ -625,6 +630,7 @@ HVB_HD void scan_points(const Dev<D>& dv, const RayQ<D>& q, const float (&uf)[D]
         while (pmask) {
             const int i = lowest_bit(pmask);
             pmask &= pmask - 1u;
+            HVB_TRACE_EVENT(4, 0);
             float nm_i = nms[0], den_i = dens[0];
 #pragma unroll
             for (int b = 1; b < U; ++b) { nm_i = (i == b) ? nms[b] : nm_i; den_i = (i == b) ? dens[b] : den_i; }
@@ -706,6 +712,7 @@ HVB_HD Best min_t_query(const Dev<D>& dv, const T& tile, const RayQ<D>& q, Local
     best.t = INFINITY; best.id = -1; best.t2 = INFINITY;
     const int lane = tile.lane();
     ls.raycasts += (lane == 0);
+    HVB_TRACE_EVENT(0, 0);
 
     plane_candidates<D>(dv, q, best);
 
@@ -769,6 +776,7 @@ HVB_HD Best min_t_query(const Dev<D>& dv, const T& tile, const RayQ<D>& q, Local
             if (k < D - 1) nrows *= (chi[k] - clo[k] + 1);
         }
         if (empty) nrows = 0;
+        HVB_TRACE_EVENT(3, nrows);
         Filt flt = make_filter<D>(halfspace_mode ? INFINITY : Ts, rho, R0, dv.ext);
         // FP32 upper bounds certify validity only while the filter's denominator margin dominates the half-space slack
         if (!((float)(fabs(q.c) * 8e-12) < flt.ed)) st.tighten = false;
@@ -799,11 +807,13 @@ HVB_HD Best min_t_query(const Dev<D>& dv, const T& tile, const RayQ<D>& q, Local
                 while (j < nrows) {
                     int jn = use32 ? row_try32<D>(dv, uf, x0f, clo, chi, b32, j, pa, pb)
                                    : (row_range<D>(dv, q, clo, chi, cen, rho2, j, pa, pb) ? -1 : j + 1);
+                    HVB_TRACE_EVENT(1, 0);
                     if (jn < 0) { have = true; j += T::SIZE; break; }
                     j = (T::SIZE == 1) ? jn : jn + ((T::SIZE - ((jn - lane) % T::SIZE)) % T::SIZE);
                 }
                 if (T::SIZE > 1) { if (tile.ballot(have) == 0u) break; }
                 else if (!have) break;
+                HVB_TRACE_EVENT(2, (have && pb > pa) ? pb - pa : 0);
                 if (have && pb > pa) scan_points<D>(dv, q, uf, w2f, x0f, flt, pa, pb, st, best, ls);
                 if (T::SIZE > 1) {
                     best_reduce(tile, best);
@@ -844,6 +854,8 @@ HVB_HD Best min_t_query(const Dev<D>& dv, const T& tile, const RayQ<D>& q, Local
             int jn = (it + 1) * T::SIZE + lane;
             bool have_n = (jn < nrows) && (use32 ? row_range32<D>(dv, uf, x0f, clo, chi, b32, jn, pa_n, pb_n)
                                                  : row_range<D>(dv, q, clo, chi, cen, rho2, jn, pa_n, pb_n));
+            HVB_TRACE_EVENT(1, 0);
+            HVB_TRACE_EVENT(2, (have && pb > pa) ? pb - pa : 0);
             if (have && pb > pa) scan_points<D>(dv, q, uf, w2f, x0f, flt, pa, pb, st, best, ls);
             have = have_n; pa = pa_n; pb = pb_n;
             // share the best bound and shrink the ball

@@ -7,6 +7,10 @@
 #include <cstring>
 #include <vector>
 #include <algorithm>
+// per-ray trace of the query (kind: 0 ray, 1 row test, 2 row scanned with val points, 3 stage with val rows, 4 FP32 survivor)
+static std::vector<int>* g_trace = nullptr;
+static bool g_want_trace = false;
+#define HVB_TRACE_EVENT(kind, val) do { if (g_trace) { g_trace->push_back(kind); g_trace->push_back((int)(val)); } } while (0)
 #include "../../highvoronoi.jl_b200/csrc/hvb_host.hpp"
 #include "../../highvoronoi.jl_b200/csrc/hvb_geometry.cuh"
 
@@ -18,6 +22,7 @@ struct SimResult {
     std::vector<int64_t> ray_edge;
     Counters ctr;
     int rounds;
+    std::vector<int> trace;
 };
 
 template <int D>
@@ -64,6 +69,8 @@ static SimResult* run(int64_t n, const double* xs, int P, const double* base, co
     u32 na = 0, nb = 0;
     TileHost tile; LocalStats ls; memset(&ls, 0, sizeof(ls));
     if (seed_stride <= 0) seed_stride = 16;
+    std::vector<int> trace_buf;
+    if (g_want_trace) g_trace = &trace_buf;
     for (int64_t i = 0; i < n; i += seed_stride) seed_item<D, TileHost>(dv, tile, (int)i, qa.data(), &na, qcap, ls);
     int rounds = 0;
     for (;;) {
@@ -79,7 +86,9 @@ static SimResult* run(int64_t n, const double* xs, int P, const double* base, co
         for (int64_t i = 0; i < n; ++i) if (!hasv[i]) seed_item<D, TileHost>(dv, tile, (int)i, qa.data(), &na, qcap, ls);
         if (na == 0) break;
     }
+    g_trace = nullptr;
     SimResult* R = new SimResult(); R->d = D; R->rounds = rounds;
+    R->trace.swap(trace_buf);
     ctr.raycasts = ls.raycasts; ctr.dup_hits = ls.dup_hits; ctr.closed_skips = ls.closed_skips; ctr.cand32 = ls.cand32; ctr.cand64 = ls.cand64;
     ctr.rows = ls.rows; ctr.stages = ls.stages; ctr.seeds = ls.seeds; ctr.degenerate = ls.degenerate; ctr.seed_fail = ls.seed_fail; ctr.dead = ls.dead;
     R->ctr = ctr;
@@ -183,6 +192,9 @@ void hostsim_fetch(void* h, int64_t* sig, double* r, int64_t* ray_edge) {
     memcpy(ray_edge, R->ray_edge.data(), R->ray_edge.size() * 8);
 }
 void hostsim_free(void* h) { delete (SimResult*)h; }
+void hostsim_set_trace(int on) { g_want_trace = on != 0; }
+int64_t hostsim_trace_size(void* h) { return (int64_t)((SimResult*)h)->trace.size(); }
+void hostsim_trace_fetch(void* h, int* out) { SimResult* R = (SimResult*)h; memcpy(out, R->trace.data(), R->trace.size() * sizeof(int)); }
 
 void hostsim_areas(int dim, int64_t n, const double* xs, int P, const double* base, const double* normal, int64_t nv, const int64_t* sig,
                    const int64_t* off, const int64_t* ids, double* area) {

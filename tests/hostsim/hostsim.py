@@ -18,8 +18,9 @@ def build():
     return _SO
 
 
-def run(xs, base=None, normal=None, ppc=0, probe_scale=0.0, fp32=1, seed_stride=0):
+def run(xs, base=None, normal=None, ppc=0, probe_scale=0.0, fp32=1, seed_stride=0, trace=False):
     L = ctypes.CDLL(build())
+    L.hostsim_set_trace(1 if trace else 0)
     L.hostsim_run.restype = ctypes.c_void_p
     L.hostsim_run.argtypes = [ctypes.c_int, ctypes.c_int64, ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p,
                               ctypes.c_int, ctypes.c_double, ctypes.c_int, ctypes.c_int]
@@ -40,8 +41,19 @@ def run(xs, base=None, normal=None, ppc=0, probe_scale=0.0, fp32=1, seed_stride=
     L.hostsim_counts(h, ctypes.byref(nv), ctypes.byref(nr), P(ctr))
     sig = np.empty((nv.value, d + 1), dtype=np.int64); r = np.empty((nv.value, d)); re = np.empty((nr.value, d), dtype=np.int64)
     L.hostsim_fetch(h, P(sig), P(r), P(re))
+    out = dict(sig=sig, r=r, ray_edge=re, stats=dict(zip(CTR, ctr.tolist())))
+    if trace:
+        L.hostsim_trace_size.restype = ctypes.c_int64
+        L.hostsim_trace_size.argtypes = [ctypes.c_void_p]
+        L.hostsim_trace_fetch.argtypes = [ctypes.c_void_p, ctypes.c_void_p]
+        m = L.hostsim_trace_size(h)
+        tr = np.zeros(m, dtype=np.int32)
+        if m:
+            L.hostsim_trace_fetch(h, P(tr))
+        out["trace"] = tr.reshape(-1, 2)
     L.hostsim_free(h)
-    return dict(sig=sig, r=r, ray_edge=re, stats=dict(zip(CTR, ctr.tolist())))
+    L.hostsim_set_trace(0)
+    return out
 
 
 def volumes(xs, sig, base=None, normal=None):
