@@ -466,7 +466,7 @@ __device__ __forceinline__ void commit_vertex_warp(const Dev<D>& dv, bool has, c
 #define HVB_COOP_COMMIT 1         // 1: warp-aggregated commit (commit_vertex_warp), 0: the lane-per-ray commit_vertex
 #endif
 template <int D, bool COOPQ>
-__global__ void __launch_bounds__(128, HVB_COOP_MINB) k_walk_coop(Dev<D> dv, WalkQueue wq) {
+static __global__ void __launch_bounds__(128, HVB_COOP_MINB) k_walk_coop(Dev<D> dv, WalkQueue wq) {
     extern __shared__ __align__(16) unsigned char hvb_smem_raw[];
     CoopShared<D>& sh = reinterpret_cast<CoopShared<D>*>(hvb_smem_raw)[threadIdx.x >> 5];
     const unsigned FULL = 0xffffffffu;

@@ -30,7 +30,7 @@ __device__ __forceinline__ void flush_stats(const LocalStats& ls, Counters* c) {
 // the last block to finish.  out: [2*D] doubles (min, max), viol: smallest index of a generator outside a plane
 // (or non-finite), 0xffffffff if none
 template <int D>
-__global__ void k_bbox_check(const double* __restrict__ xs, int n, const PlaneSet* __restrict__ ps, double* __restrict__ partial,
+static __global__ void k_bbox_check(const double* __restrict__ xs, int n, const PlaneSet* __restrict__ ps, double* __restrict__ partial,
                              unsigned int* __restrict__ done, double* __restrict__ out, unsigned int* __restrict__ viol) {
     double mn[D], mx[D];
 #pragma unroll
@@ -104,7 +104,7 @@ __global__ void k_bbox_check(const double* __restrict__ xs, int n, const PlaneSe
 }
 
 template <int D>
-__global__ void k_cell_count(Dev<D> dv, const double* __restrict__ xs, int* __restrict__ cell_of, int* __restrict__ cell_cnt) {
+static __global__ void k_cell_count(Dev<D> dv, const double* __restrict__ xs, int* __restrict__ cell_of, int* __restrict__ cell_cnt) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= dv.n) return;
     double x[D];
@@ -116,7 +116,7 @@ __global__ void k_cell_count(Dev<D> dv, const double* __restrict__ xs, int* __re
 }
 
 template <int D>
-__global__ void k_scatter(Dev<D> dv, const double* __restrict__ xs, const int* __restrict__ cell_of,
+static __global__ void k_scatter(Dev<D> dv, const double* __restrict__ xs, const int* __restrict__ cell_of,
                           const int* __restrict__ cell_start, int* __restrict__ cursor,
                           double* __restrict__ x64, float* __restrict__ x32, int* __restrict__ perm) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -128,7 +128,7 @@ __global__ void k_scatter(Dev<D> dv, const double* __restrict__ xs, const int* _
 
 // deterministic order inside a cell: sort each cell's entries by caller id (cells hold a handful of points)
 template <int D>
-__global__ void k_cell_sort(Dev<D> dv, const double* __restrict__ xs, const int* __restrict__ cell_start, int ncells,
+static __global__ void k_cell_sort(Dev<D> dv, const double* __restrict__ xs, const int* __restrict__ cell_start, int ncells,
                             double* __restrict__ x64, float* __restrict__ x32, int* __restrict__ perm) {
     int c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= ncells) return;
@@ -151,15 +151,15 @@ __global__ void k_cell_sort(Dev<D> dv, const double* __restrict__ xs, const int*
 }
 
 // active[g] = 1 for the sorted positions of this context's slab (parallelmesh.jl:52-87) or of the Iter cells
-__global__ void k_fill_active_range(unsigned char* active, int n, int lo, int hi) {
+static __global__ void k_fill_active_range(unsigned char* active, int n, int lo, int hi) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) active[i] = (i >= lo && i < hi) ? 1 : 0;
 }
-__global__ void k_inverse_perm(const int* __restrict__ perm, int* __restrict__ inv, int n) {
+static __global__ void k_inverse_perm(const int* __restrict__ perm, int* __restrict__ inv, int n) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) inv[perm[i]] = i;
 }
-__global__ void k_mark_cells(const long long* __restrict__ cells, long long ncells, const int* __restrict__ inv,
+static __global__ void k_mark_cells(const long long* __restrict__ cells, long long ncells, const int* __restrict__ inv,
                              unsigned char* active, int n) {
     long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
     if (i < ncells) { long long c = cells[i] - 1; if (c >= 0 && c < n) active[inv[c]] = 1; }
@@ -185,7 +185,7 @@ struct HaloSpec {
 // one thread per caller generator, all shift codes in ascending order: deterministic halo numbering without atomics.
 // Pass 1 (xs_out == nullptr) counts the accepted copies of every generator, pass 2 writes them behind offs[i].
 template <int D>
-__global__ void k_halo(const double* xs, int n_user, HaloSpec hs, const PlaneSet* __restrict__ ps,
+static __global__ void k_halo(const double* xs, int n_user, HaloSpec hs, const PlaneSet* __restrict__ ps,
                        int* __restrict__ counts, const int* __restrict__ offs, double* xs_out,
                        int* __restrict__ origin, signed char* __restrict__ mult) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -235,7 +235,7 @@ __global__ void k_halo(const double* xs, int n_user, HaloSpec hs, const PlaneSet
 }
 
 // active[g] = 1 for the caller's own generators (not the halo) inside the slab of sorted positions [lo, hi)
-__global__ void k_fill_active_orig(unsigned char* active, const int* __restrict__ perm, int n, int n_user, int lo, int hi) {
+static __global__ void k_fill_active_orig(unsigned char* active, const int* __restrict__ perm, int n, int n_user, int lo, int hi) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) active[i] = (i >= lo && i < hi && perm[i] < n_user) ? 1 : 0;
 }
@@ -260,7 +260,7 @@ struct CertOut {
     unsigned int pad;
 };
 template <int D>
-__global__ void k_certify(const long long* __restrict__ sig, const double* __restrict__ r, u32 nv, long long n_user, long long n_ext,
+static __global__ void k_certify(const long long* __restrict__ sig, const double* __restrict__ r, u32 nv, long long n_user, long long n_ext,
                           const double* __restrict__ xs_ext, const int* __restrict__ halo_origin, const PlaneSet* __restrict__ ps,
                           PeriodicCert pc, unsigned char* __restrict__ vflags, CertOut* __restrict__ out) {
     u32 v = blockIdx.x * blockDim.x + threadIdx.x;
@@ -315,7 +315,7 @@ __global__ void k_certify(const long long* __restrict__ sig, const double* __res
 // seeding and frontier rounds
 // ------------------------------------------------------------------------------------------------------------
 template <int D, int G>
-__global__ void __launch_bounds__(128) k_seed(Dev<D> dv, const int* __restrict__ seeds, int nseeds, int stride,
+static __global__ void __launch_bounds__(128) k_seed(Dev<D> dv, const int* __restrict__ seeds, int nseeds, int stride,
                                               u64* q_out, u32* q_count, u32 q_cap) {
     TileDev<G> tile;
     LocalStats ls = {};
@@ -334,7 +334,7 @@ __global__ void __launch_bounds__(128) k_seed(Dev<D> dv, const int* __restrict__
 // Vertices the caller's mesh already holds (refinement callers, meshrefine.jl:199-215): converted to internal
 // numbering, stored and registered like found vertices, so that the walk continues from them and never returns them.
 template <int D>
-__global__ void k_insert_seeds(Dev<D> dv, const long long* __restrict__ sig_in, const double* __restrict__ r_in, long long nseed,
+static __global__ void k_insert_seeds(Dev<D> dv, const long long* __restrict__ sig_in, const double* __restrict__ r_in, long long nseed,
                                int stride, const int* __restrict__ inv, u64* q_out, u32* q_count, u32 q_cap, u32* bad) {
     long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
     if (i >= nseed) return;
@@ -370,7 +370,7 @@ __global__ void k_insert_seeds(Dev<D> dv, const long long* __restrict__ sig_in, 
 // One frontier round.  Tiles pull entries from a shared cursor and skip closed edges while acquiring, so that all
 // tiles of a warp enter the expensive part (direction, min-t query, commit) with live work.
 template <int D, int G>
-__global__ void __launch_bounds__(128, HVB_EXPAND_MINB) k_expand(Dev<D> dv, const u64* __restrict__ q_in, const u32* __restrict__ n_in_ptr,
+static __global__ void __launch_bounds__(128, HVB_EXPAND_MINB) k_expand(Dev<D> dv, const u64* __restrict__ q_in, const u32* __restrict__ n_in_ptr,
                                                                  u32* cursor, u64* q_out, u32* q_count, u32 q_cap) {
     TileDev<G> tile;
     LocalStats ls = {};
@@ -417,7 +417,7 @@ struct WalkQueue {
 #define HVB_Q_EMPTY 0xffffffffffffffffULL
 
 template <int D, int G>
-__global__ void __launch_bounds__(128, HVB_EXPAND_MINB) k_walk(Dev<D> dv, WalkQueue wq) {
+static __global__ void __launch_bounds__(128, HVB_EXPAND_MINB) k_walk(Dev<D> dv, WalkQueue wq) {
     TileDev<G> tile;
     LocalStats ls = {};
     u32 ticket = 0xffffffffu;          // held by lane 0 of the tile
@@ -474,7 +474,7 @@ __global__ void __launch_bounds__(128, HVB_EXPAND_MINB) k_walk(Dev<D> dv, WalkQu
 
 // cells of this context that still have no vertex (sysvoronoi.jl:416-429: they get their own descent)
 template <int D>
-__global__ void k_unseeded(Dev<D> dv, int* list, u32* count) {
+static __global__ void k_unseeded(Dev<D> dv, int* list, u32* count) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= dv.n) return;
     if (dv.active[i] && !dv.has_vertex[i]) list[atomicAdd(count, 1u)] = i;
@@ -485,7 +485,7 @@ __global__ void k_unseeded(Dev<D> dv, int* list, u32* count) {
 // ------------------------------------------------------------------------------------------------------------
 // one thread per stored record; dead records (lost insertion races) are skipped
 template <int D>
-__global__ void k_final_rows(Dev<D> dv, const int* __restrict__ perm, u32 nrec, int bits,
+static __global__ void k_final_rows(Dev<D> dv, const int* __restrict__ perm, u32 nrec, int bits,
                              long long* __restrict__ out_sig, double* __restrict__ out_r,
                              u64* __restrict__ key_top, u64* __restrict__ key_hi, u64* __restrict__ key_lo, u32* __restrict__ out_count,
                              double* __restrict__ max_var, int own_lo, int own_hi, u32 skip_below) {
@@ -530,16 +530,16 @@ __global__ void k_final_rows(Dev<D> dv, const int* __restrict__ perm, u32 nrec, 
     if (var > 1e-18) atomicMax(reinterpret_cast<unsigned long long*>(max_var), (unsigned long long)__double_as_longlong(var));
 }
 
-__global__ void k_iota(u32* a, u32 n) {
+static __global__ void k_iota(u32* a, u32 n) {
     u32 i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) a[i] = i;
 }
-__global__ void k_gather_u64(const u64* __restrict__ src, const u32* __restrict__ idx, u64* __restrict__ dst, u32 n) {
+static __global__ void k_gather_u64(const u64* __restrict__ src, const u32* __restrict__ idx, u64* __restrict__ dst, u32 n) {
     u32 i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) dst[i] = src[idx[i]];
 }
 template <int D>
-__global__ void k_gather_rows(const long long* __restrict__ sig_in, const double* __restrict__ r_in, const u32* __restrict__ idx,
+static __global__ void k_gather_rows(const long long* __restrict__ sig_in, const double* __restrict__ r_in, const u32* __restrict__ idx,
                               long long* __restrict__ sig_out, double* __restrict__ r_out, u32 n) {
     u32 i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
@@ -552,7 +552,7 @@ __global__ void k_gather_rows(const long long* __restrict__ sig_in, const double
 
 // unbounded edges in caller numbering (pushray!, abstractmesh.jl:191; node = exploring cell = smallest id of the edge)
 template <int D>
-__global__ void k_final_rays(Dev<D> dv, const int* __restrict__ perm, u32 nrays,
+static __global__ void k_final_rays(Dev<D> dv, const int* __restrict__ perm, u32 nrays,
                              long long* __restrict__ edge, double* __restrict__ base, double* __restrict__ dir, long long* __restrict__ node) {
     u32 i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= nrays) return;
@@ -608,7 +608,7 @@ __device__ __forceinline__ void pairs_of_row(const long long (&s)[D + 1], long l
 }
 
 template <int D>
-__global__ void k_pairs(const long long* __restrict__ sig, u32 nv, long long n, u64* __restrict__ ptab, u64 pmask,
+static __global__ void k_pairs(const long long* __restrict__ sig, u32 nv, long long n, u64* __restrict__ ptab, u64 pmask,
                         u32* __restrict__ deg, u32* __restrict__ flags) {
     u32 v = blockIdx.x * blockDim.x + threadIdx.x;
     if (v >= nv) return;
@@ -621,7 +621,7 @@ __global__ void k_pairs(const long long* __restrict__ sig, u32 nv, long long n, 
 // the same straight from the vertex records of the walk (internal ids; dead records skipped): the lists do not have to
 // wait for the result rows, so they are built next to k_final_rows and the row sort
 template <int D>
-__global__ void k_pairs_raw(Dev<D> dv, const int* __restrict__ perm, u32 nrec, long long n, u64* __restrict__ ptab, u64 pmask,
+static __global__ void k_pairs_raw(Dev<D> dv, const int* __restrict__ perm, u32 nrec, long long n, u64* __restrict__ ptab, u64 pmask,
                             u32* __restrict__ deg, u32* __restrict__ flags) {
     u32 v = blockIdx.x * blockDim.x + threadIdx.x;
     if (v >= nrec) return;
@@ -639,7 +639,7 @@ __global__ void k_pairs_raw(Dev<D> dv, const int* __restrict__ perm, u32 nrec, l
     pairs_of_row<D>(s, n, ptab, pmask, deg, flags);
 }
 
-__global__ void k_pair_fill(const u64* __restrict__ ptab, u64 nslots, long long n, const long long* __restrict__ off,
+static __global__ void k_pair_fill(const u64* __restrict__ ptab, u64 nslots, long long n, const long long* __restrict__ off,
                             u32* __restrict__ cursor, long long* __restrict__ ids) {
     u64 i = blockIdx.x * (u64)blockDim.x + threadIdx.x;
     if (i >= nslots) return;
@@ -650,7 +650,7 @@ __global__ void k_pair_fill(const u64* __restrict__ ptab, u64 nslots, long long 
     if (b <= n) ids[off[b - 1] + atomicAdd(cursor + (b - 1), 1u)] = a;
 }
 
-__global__ void k_sort_lists(const long long* __restrict__ off, long long* __restrict__ ids, long long n) {
+static __global__ void k_sort_lists(const long long* __restrict__ off, long long* __restrict__ ids, long long n) {
     long long c = blockIdx.x * (long long)blockDim.x + threadIdx.x;
     if (c >= n) return;
     long long a = off[c], b = off[c + 1];
@@ -662,7 +662,7 @@ __global__ void k_sort_lists(const long long* __restrict__ off, long long* __res
     }
 }
 
-__global__ void k_u32_to_i64(const u32* __restrict__ a, long long* __restrict__ b, long long n) {
+static __global__ void k_u32_to_i64(const u32* __restrict__ a, long long* __restrict__ b, long long n) {
     long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
     if (i < n) b[i] = a[i];
 }
@@ -673,7 +673,7 @@ __global__ void k_u32_to_i64(const u32* __restrict__ a, long long* __restrict__ 
 // it iff |x_sig1 - r| <= (1 + 1e-7) * dist(r, nearest new node).  Generators of removed vertices are marked affected.
 // ------------------------------------------------------------------------------------------------------------
 template <int D>
-__global__ void k_clean_affected(Dev<D> dv, const int* __restrict__ perm, const long long* __restrict__ sig, const double* __restrict__ r,
+static __global__ void k_clean_affected(Dev<D> dv, const int* __restrict__ perm, const long long* __restrict__ sig, const double* __restrict__ r,
                                  long long nv, int stride, const double* __restrict__ xs, long long new_lo, long long new_hi,
                                  unsigned char* __restrict__ keep, unsigned char* __restrict__ affected, u32* __restrict__ bad) {
     long long v = blockIdx.x * (long long)blockDim.x + threadIdx.x;
@@ -722,7 +722,7 @@ __global__ void k_clean_affected(Dev<D> dv, const int* __restrict__ perm, const 
 // in 64-bit fixed point, so the sums do not depend on the order of the atomics (bitwise reproducible volumes).
 // ------------------------------------------------------------------------------------------------------------
 template <int D>
-__global__ void k_cell_volumes(const long long* __restrict__ sig, u32 nv, const double* __restrict__ xs, long long n, long long n_list,
+static __global__ void k_cell_volumes(const long long* __restrict__ sig, u32 nv, const double* __restrict__ xs, long long n, long long n_list,
                                const PlaneSet* __restrict__ ps, double scale, long long* __restrict__ acc) {
     u32 v = blockIdx.x * blockDim.x + threadIdx.x;
     if (v >= nv) return;
@@ -735,7 +735,7 @@ __global__ void k_cell_volumes(const long long* __restrict__ sig, u32 nv, const 
         atomicAdd(reinterpret_cast<unsigned long long*>(acc + (s[k] - 1)), (unsigned long long)__double2ll_rn(t));
     }
 }
-__global__ void k_volumes_finish(const long long* __restrict__ acc, double inv_scale, double* __restrict__ vol, long long n) {
+static __global__ void k_volumes_finish(const long long* __restrict__ acc, double inv_scale, double* __restrict__ vol, long long n) {
     long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
     if (i < n) vol[i] = (double)acc[i] * inv_scale;
 }
@@ -747,7 +747,7 @@ __device__ __forceinline__ long long csr_find(const long long* __restrict__ off,
     return (lo < off[cell] && ids[lo] == id) ? lo : -1;
 }
 template <int D>
-__global__ void k_cell_areas(const long long* __restrict__ sig, u32 nv, const double* __restrict__ xs, long long n, long long n_list,
+static __global__ void k_cell_areas(const long long* __restrict__ sig, u32 nv, const double* __restrict__ xs, long long n, long long n_list,
                              const PlaneSet* __restrict__ ps, const long long* __restrict__ off, const long long* __restrict__ ids,
                              double scale, long long* __restrict__ acc) {
     u32 v = blockIdx.x * blockDim.x + threadIdx.x;
@@ -767,7 +767,7 @@ __global__ void k_cell_areas(const long long* __restrict__ sig, u32 nv, const do
     }
 }
 // facets that contain an unbounded edge have no finite area
-__global__ void k_areas_unbounded(const long long* __restrict__ ray_edge, long long nrays, int D, long long n_list,
+static __global__ void k_areas_unbounded(const long long* __restrict__ ray_edge, long long nrays, int D, long long n_list,
                                   const long long* __restrict__ off, const long long* __restrict__ ids, double* __restrict__ area) {
     long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
     if (i >= nrays) return;
@@ -782,7 +782,7 @@ __global__ void k_areas_unbounded(const long long* __restrict__ ray_edge, long l
     }
 }
 // cells with an unbounded edge have no finite volume
-__global__ void k_volumes_unbounded(const long long* __restrict__ ray_edge, long long nentries, long long n_list, double* __restrict__ vol) {
+static __global__ void k_volumes_unbounded(const long long* __restrict__ ray_edge, long long nentries, long long n_list, double* __restrict__ vol) {
     long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
     if (i >= nentries) return;
     const long long g = ray_edge[i];
@@ -793,7 +793,7 @@ __global__ void k_volumes_unbounded(const long long* __restrict__ ray_edge, long
 // multi-GPU merge: dedup of gathered rows (sorted caller ids, 1-based) by a row hash set
 // ------------------------------------------------------------------------------------------------------------
 template <int D>
-__global__ void k_merge_rows(const long long* __restrict__ sig_in, const double* __restrict__ r_in, u64 count, int bits,
+static __global__ void k_merge_rows(const long long* __restrict__ sig_in, const double* __restrict__ r_in, u64 count, int bits,
                              u64* __restrict__ tab, u64 mask, long long* __restrict__ sig_out, double* __restrict__ r_out,
                              u64* __restrict__ key_top, u64* __restrict__ key_hi, u64* __restrict__ key_lo, u32* __restrict__ out_count) {
     u64 i = blockIdx.x * (u64)blockDim.x + threadIdx.x;
