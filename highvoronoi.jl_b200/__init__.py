@@ -4,7 +4,7 @@ The directory is called `highvoronoi.jl_b200`; because of the dot it is imported
 `hvb200.py` at the repository root (`import hvb200`)."""
 from . import _abi  # noqa: F401
 from .api import (refine, ConvexHull, B200Thread, Boundary, HVBError, Raycast, RaycastParameter, RCCombined, RCNonGeneral,  # noqa: F401
-                  RCNonGeneralFast, RCNonGeneralHP, RCOriginal, RCStandard, SingleThread, VoronoiData,
+                  RCNonGeneralFast, RCNonGeneralHP, RCOriginal, RCStandard, RCOriginalSafety, RCNonGeneralSkip, RCOriginalHP, RCNonGeneralCutoff, SingleThread, VoronoiData,
                   VoronoiGeometry, VoronoiMesh, VoronoiNodes, cuboid, voronoi)
 
 __version__ = "0.1.0"

@@ -69,6 +69,7 @@ RCStandard = RCNonGeneral = RCNonGeneralHP = 0
 RCOriginal = 1
 RCCombined = 2
 RCNonGeneralFast = 3
+RCOriginalSafety, RCNonGeneralSkip, RCOriginalHP, RCNonGeneralCutoff = 4, 5, 6, 7
 
 
 class SingleThread:
@@ -162,6 +163,12 @@ class Raycast:
             self.close()
         except Exception:
             pass
+
+    def owned(self):
+        """bool mask over the caller's cells: True where this searcher's slab owns the cell (all True unless world > 1)"""
+        m = np.empty((self.n,), dtype=np.uint8)
+        _abi.check(_abi.lib().hvb_fetch_owned(self._ctx, m.ctypes.data_as(ctypes.c_void_p)), self._ctx)
+        return m.astype(bool)
 
     def stats(self):
         s = _abi.hvb_stats_t()

@@ -37,6 +37,10 @@ int hvb_create_periodic(hvb_ctx** out, int dim, int64_t n, const double* xs, int
     if (dim < 2 || dim > HVB_MAX_DIM) { g_create_error = "dimension must be 2..6"; return HVB_EINVAL; }
     if (n <= dim || !xs) { g_create_error = "There are not enough points to create a Voronoi tessellation"; return HVB_EINVAL; }   // sysvoronoi.jl:25-27
     if (n > 0x7ff00000LL) { g_create_error = "too many generators"; return HVB_EINVAL; }
+    if (prm.method < 0 || prm.method > 7) { g_create_error = "unknown raycast method (0..7, raycast-types.jl:244-284)"; return HVB_EINVAL; }
+    if (!(prm.variance_tol >= 0) || !(prm.break_tol > 0) || !(prm.b_nodes_tol > 0) || !(prm.plane_tolerance >= 0) || !(prm.ray_tol > 0)) {
+        g_create_error = "tolerances must be positive numbers (raycast-types.jl:226-230)"; return HVB_EINVAL;
+    }
     if (nplanes < 0 || nplanes > HVB_MAX_PLANES || (nplanes > 0 && (!plane_base || !plane_normal))) { g_create_error = "bad boundary planes"; return HVB_EINVAL; }
     int ndev = 0;
     cudaError_t ce = cudaGetDeviceCount(&ndev);
@@ -81,6 +85,7 @@ int hvb_adopt_device(hvb_ctx* ctx, const void* sig_dev, const void* r_dev, int64
 int hvb_halo_count(hvb_ctx* ctx, int64_t* nhalo, int32_t* npairs, double* margin) { return ctx ? ctx->halo_count(nhalo, npairs, margin) : HVB_EINVAL; }
 int hvb_fetch_halo(hvb_ctx* ctx, int64_t* origin, int32_t* mult, double* xs) { return ctx ? ctx->fetch_halo(origin, mult, xs) : HVB_EINVAL; }
 int hvb_fetch_vertex_flags(hvb_ctx* ctx, uint8_t* flags) { return ctx ? ctx->fetch_vertex_flags(flags) : HVB_EINVAL; }
+int hvb_fetch_owned(hvb_ctx* ctx, uint8_t* owned) { return ctx ? ctx->fetch_owned(owned) : HVB_EINVAL; }
 int hvb_cell_volumes(hvb_ctx* ctx, double* vol) { return ctx ? ctx->cell_volumes(vol) : HVB_EINVAL; }
 int hvb_cell_areas(hvb_ctx* ctx, double* area) { return ctx ? ctx->cell_areas(area) : HVB_EINVAL; }
 int hvb_clean_affected(hvb_ctx* ctx, const int64_t* sig, const double* r, int64_t nv, int sig_stride, int64_t first_new, int64_t n_new, uint8_t* keep, uint8_t* affected) {

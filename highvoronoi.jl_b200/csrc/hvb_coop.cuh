@@ -212,7 +212,7 @@ __device__ __forceinline__ Best coop_min_t(const Dev<D>& dv, CoopShared<D>& sh, 
     const int lane = threadIdx.x & 31;
     const int TA = CoopCfg<D>::TA, CAP = CoopCfg<D>::CAP;
     Best best;
-    best.t = INFINITY; best.id = -1; best.t2 = INFINITY;
+    best.t = INFINITY; best.id = -1; best.t2 = INFINITY; best.tw = 0.0;
     bool active = has_ray, serial = false, tighten = true, redone = false;
     double R0 = 0, R0p = 0, perp2 = 0, scale = dv.probe_scale;
     int stage = 0;
@@ -524,7 +524,7 @@ static __global__ void __launch_bounds__(128, HVB_COOP_MINB) k_walk_coop(Dev<D> 
             // and the commit are warp-aggregated)
             Best best;
             if (COOPQ) best = coop_min_t<D>(dv, sh, q, ok, ls);
-            else { best.t = INFINITY; best.id = -1; best.t2 = INFINITY; if (ok) best = min_t_query<D, TileDev<1> >(dv, tile, q, ls); }
+            else { best.t = INFINITY; best.id = -1; best.t2 = INFINITY; best.tw = 0.0; if (ok) best = min_t_query<D, TileDev<1> >(dv, tile, q, ls); }
 #if HVB_COOP_COMMIT
             int sig2[D + 1];
             double r2[D];

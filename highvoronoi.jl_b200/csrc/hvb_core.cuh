@@ -325,6 +325,7 @@ struct RayQ {
     double c;          // half-space threshold on u.x : candidates need u.x > c   (raycast.jl:802-805, myskips :385)
     double R0sq;       // |x0 - r|^2
     double a;          // u.(x0 - r)
+    double rnorm;      // |r| (scale of the reference's rounding estimate, get_t_hp_ raycast.jl:406)
     int excl[D + 1];   // ids that may not win (the origin vertex's generators)
     int nexcl;
 };
@@ -333,16 +334,25 @@ struct Best {
     double t;          // smallest ray parameter so far
     int id;            // its generator (>= n : boundary plane id - n), -1 none
     double t2;         // runner-up, for the general-position check
+    double tw;         // the reference's tie window on t for this winner (raycast.jl:902), see tie_window()
 };
 
-HVB_HD void best_offer(Best& b, double t, int id) {
-    if (t < b.t || (t == b.t && id < b.id)) { b.t2 = b.t; b.t = t; b.id = id; }
+// The reference treats every candidate with t <= t_min + min(1e-7, (10 + d) * full_error) as tied with the winner
+// (raycast.jl:902), full_error = (t * 1e-14 + |r| * 1e-15) / (u . normalize(x - x0)) (get_t_hp_, raycast.jl:399-407):
+// the window widens for grazing candidates.  `den` = u . (x - x0), `dx2` = |x - x0|^2.
+HVB_HD double tie_window(int D, double t, double rnorm, double den, double dx2) {
+    const double w = (10.0 + D) * (t * 1e-14 + rnorm * 1e-15) * sqrt(dx2) / den;
+    return fmin(1e-7, w);
+}
+
+HVB_HD void best_offer(Best& b, double t, int id, double tw) {
+    if (t < b.t || (t == b.t && id < b.id)) { b.t2 = b.t; b.t = t; b.id = id; b.tw = tw; }
     else if (id != b.id && t < b.t2) b.t2 = t;
 }
-HVB_HD void best_merge(Best& b, double t, int id, double t2) {
+HVB_HD void best_merge(Best& b, double t, int id, double t2, double tw) {
     if (t < b.t || (t == b.t && id < b.id)) {
         double o = (id != b.id) ? b.t : b.t2;
-        b.t2 = fmin(o, fmin(b.t2, t2)); b.t = t; b.id = id;
+        b.t2 = fmin(o, fmin(b.t2, t2)); b.t = t; b.id = id; b.tw = tw;
     } else {
         double o = (id != b.id) ? t : t2;
         b.t2 = fmin(b.t2, fmin(o, t2));
@@ -355,8 +365,14 @@ HVB_HD void best_reduce(const T& tile, Best& b) {
         double ot = tile.shfl_xor(b.t, m);
         int oid = tile.shfl_xor(b.id, m);
         double ot2 = tile.shfl_xor(b.t2, m);
-        best_merge(b, ot, oid, ot2);
+        double otw = tile.shfl_xor(b.tw, m);
+        best_merge(b, ot, oid, ot2, otw);
     }
+}
+// non-general position in the reference's sense: the runner-up lies inside the winner's tie window (the reference would
+// append it to the signature, raycast.jl:926-949), or within 1e-12 relative of it
+HVB_HD bool near_tie(const Best& b, double R0sq) {
+    return b.t2 - b.t <= fmax(1e-12 * fmax(b.t, sqrt(R0sq)), b.tw);
 }
 
 // FP64 evaluation of one generator: get_t_hp (raycast.jl:427-432) under the predicate of myskips (:385)
@@ -366,7 +382,7 @@ HVB_HD bool verify64(const Dev<D>& dv, const RayQ<D>& q, int j, Best& best, Loca
     for (int e = 0; e < D + 1; ++e)
         if (e < q.nexcl && q.excl[e] == j) return false;
     const double* x = dv.x64 + (size_t)j * D;
-    double ux = 0, num = 0, den = 0;
+    double ux = 0, num = 0, den = 0, dx2 = 0;
 #pragma unroll
     for (int k = 0; k < D; ++k) {
         double xk = x[k];
@@ -374,12 +390,13 @@ HVB_HD bool verify64(const Dev<D>& dv, const RayQ<D>& q, int j, Best& best, Loca
         ux += q.u[k] * xk;
         num += dx * (q.x0[k] + xk - 2.0 * q.r[k]);
         den += q.u[k] * dx;
+        dx2 += dx * dx;
     }
     ls.cand64++;
     if (!(ux > q.c) || !(den > 0)) return false;
     double t = num / (2.0 * den);
     if (!(t >= dv.plane_tol)) return false;           // raycast.jl:887-889
-    best_offer(best, t, j);
+    best_offer(best, t, j, tie_window(D, t, q.rnorm, den, dx2));
     return true;
 }
 
@@ -700,7 +717,8 @@ HVB_HD void plane_candidates(const Dev<D>& dv, const RayQ<D>& q, Best& best) {
         if (!(ux0 + 2.0 * s * nu > q.c) || !(nu > 0)) continue;
         double t = (ps->off[p] - nr) / nu;
         if (!(t >= dv.plane_tol)) continue;
-        best_offer(best, t, dv.n + p);
+        // a plane is the mirror image of x0: x - x0 = 2 s n, u . (x - x0) = 2 s nu
+        best_offer(best, t, dv.n + p, tie_window(D, t, q.rnorm, 2.0 * s * nu, 4.0 * s * s));
     }
 }
 
@@ -709,7 +727,7 @@ HVB_HD void plane_candidates(const Dev<D>& dv, const RayQ<D>& q, Best& best) {
 template <int D, class T>
 HVB_HD Best min_t_query(const Dev<D>& dv, const T& tile, const RayQ<D>& q, LocalStats& ls) {
     Best best;
-    best.t = INFINITY; best.id = -1; best.t2 = INFINITY;
+    best.t = INFINITY; best.id = -1; best.t2 = INFINITY; best.tw = 0.0;
     const int lane = tile.lane();
     ls.raycasts += (lane == 0);
     HVB_TRACE_EVENT(0, 0);
@@ -1160,6 +1178,7 @@ HVB_HD bool ray_setup(const Dev<D>& dv, u64 item, RayQ<D>& q, int (&sig)[D + 1],
         for (int k = 0; k < D; ++k) w[k] = q.x0[k] - q.r[k];
         q.R0sq = dotD<D>(w, w);
         q.a = dotD<D>(q.u, w);
+        q.rnorm = sqrt(dotD<D>(q.r, q.r));
     }
     return true;
 }
@@ -1180,7 +1199,7 @@ HVB_HD bool ray_result(const Dev<D>& dv, int lane, const RayQ<D>& q, const int (
         }
         return false;
     }
-    if (best.t2 - best.t <= 1e-12 * fmax(best.t, sqrt(q.R0sq))) { ls.degenerate += (lane == 0); if (lane == 0) atom_or(&dv.ctr->flags, (u32)FLAG_DEGEN); }
+    if (near_tie(best, q.R0sq)) { ls.degenerate += (lane == 0); if (lane == 0) atom_or(&dv.ctr->flags, (u32)FLAG_DEGEN); }
     // new vertex: (sig minus position kd) plus the winner, kept sorted with static indexing
     {
         int e[D];
@@ -1278,7 +1297,7 @@ HVB_HD void seed_item(const Dev<D>& dv, const T& tile, int start, u64* q_out, u3
             for (int k = 0; k < D; ++k) v[k] = unit_hash(rs);
             if (!ortho_direction<D>(V, vmask_, v)) { ok = false; break; }
             Best best;
-            best.id = -1; best.t = INFINITY; best.t2 = INFINITY;
+            best.id = -1; best.t = INFINITY; best.t2 = INFINITY; best.tw = 0.0;
             for (int dir = 0; dir < 2 && best.id < 0; ++dir) {
 #pragma unroll
                 for (int k = 0; k < D; ++k) q.u[k] = dir ? -v[k] : v[k];
@@ -1306,13 +1325,14 @@ HVB_HD void seed_item(const Dev<D>& dv, const T& tile, int start, u64* q_out, u3
                 for (int k = 0; k < D; ++k) w[k] = q.x0[k] - q.r[k];
                 q.R0sq = dotD<D>(w, w);
                 q.a = dotD<D>(q.u, w);
+                q.rnorm = sqrt(dotD<D>(q.r, q.r));
 #pragma unroll
                 for (int i = 0; i < D + 1; ++i) q.excl[i] = (i < cnt) ? sig[i] : -1;
                 q.nexcl = cnt;
                 best = min_t_query_call<D, T>(dv, tile, q, ls);
             }
             if (best.id < 0) { ok = false; break; }
-            if (best.t2 - best.t <= 1e-12 * fmax(best.t, sqrt(q.R0sq))) { ls.degenerate += (lane == 0); if (lane == 0) atom_or(&dv.ctr->flags, (u32)FLAG_DEGEN); }
+            if (near_tie(best, q.R0sq)) { ls.degenerate += (lane == 0); if (lane == 0) atom_or(&dv.ctr->flags, (u32)FLAG_DEGEN); }
 #pragma unroll
             for (int k = 0; k < D; ++k) q.r[k] += best.t * q.u[k];
             sig[cnt++] = best.id;

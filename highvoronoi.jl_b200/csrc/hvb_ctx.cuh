@@ -96,6 +96,7 @@ struct Scalars {            // small device-side words, mirrored into pinned hos
     u32 bbox_done;
     u32 bbox_viol;
     u32 pad2;
+    u32 tol_counts[2];                // vertices dropped (variance > break_tol) / kept above variance_tol (k_final_rows)
     double max_var;
     double bbox[12];
 };
@@ -174,6 +175,10 @@ struct Ctx : hvb_ctx {
     HBuf<long long> h_nb_off, h_nb_ids;
     bool nb_staged = false;
     int64_t nb_total = -1;
+    // multi-GPU slabs: byte mask over caller cells, 1 = this context owns the cell (its sorted position lies in the slab).
+    // Neighbour lists are built for owned cells only (complete there); null = every cell
+    DBuf<unsigned char> own_mask;
+    const unsigned char* own_ptr = nullptr;
     std::vector<cudaEvent_t> ev_pool;
     cudaEvent_t ev_up = nullptr;
     cudaEvent_t ev_a = nullptr, ev_b = nullptr, ev_c = nullptr, ev_d = nullptr, ev_s0 = nullptr, ev_s1 = nullptr, ev_n0 = nullptr, ev_n1 = nullptr;
@@ -203,7 +208,7 @@ struct Ctx : hvb_ctx {
         if (ev_n1) cudaEventDestroy(ev_n1);
         if (ev_stage) cudaEventDestroy(ev_stage);
         if (ev_nb) cudaEventDestroy(ev_nb);
-        nbsc.release(); h_nbsc.release(); h_nbtotal.release();
+        nbsc.release(); h_nbsc.release(); h_nbtotal.release(); own_mask.release();
         if (nstream) { cudaStreamSynchronize(nstream); cudaStreamDestroy(nstream); }
         if (sstream2) { cudaStreamSynchronize(sstream2); cudaStreamDestroy(sstream2); }
         if (ev_p0) cudaEventDestroy(ev_p0);
@@ -232,6 +237,7 @@ struct Ctx : hvb_ctx {
     DBuf<CertOut> cert;
     HBuf<CertOut> h_cert;
     bool have_flags = false;
+    double margin_spacing = 0, margin_rel_certified = 0;
     cudaEvent_t ev_p0 = nullptr, ev_p1 = nullptr;
 
     int init(const double* xs, const double* pbase, const double* pnormal, const int32_t* plane_bc) override {
@@ -365,6 +371,9 @@ struct Ctx : hvb_ctx {
             for (int k = 0; k < D; ++k) vol *= std::max(h_sc.p->bbox[D + k] - h_sc.p->bbox[k], 1e-300);
             const double spacing = pow(vol / (double)n_user, 1.0 / D);
             margin = prm.periodic_margin > 0 ? prm.periodic_margin : 2.0 * spacing * pow((double)D / cd[D], 1.0 / D) * allow[D];
+            // a margin the certificate had to enlarge on an earlier cloud of this context is not tried again
+            margin_spacing = spacing;
+            if (margin_rel_certified > 0) margin = std::max(margin, margin_rel_certified * spacing);
             rc = build_halo(); if (rc) return rc;
         }
         return build_index();
@@ -550,20 +559,39 @@ struct Ctx : hvb_ctx {
         if (cells) for (int64_t i = 0; i < ncells_in; ++i) if (cells[i] < 1 || cells[i] > n_user) { err = "Iter names a cell that is not a caller generator"; return HVB_EINVAL; }
         int64_t retries = 0;
         double ms_cert = 0;
+        // what the failed attempts cost (their searches, the halo + index rebuilds) stays in the statistics of this call:
+        // ms_search and the work counters are sums over all attempts
+        hvb_stats_t lost;
+        memset(&lost, 0, sizeof(lost));
         for (;;) {
             int rc = search_once(cells, ncells_in, nullptr, nullptr, 0, 0); if (rc) return rc;
             bool ok = false; double need = 0;
             rc = certify(&ok, &need, &ms_cert); if (rc) return rc;
             if (ok) break;
             if (++retries > 6) { err = "periodic certificate still fails after 6 margin increases"; return HVB_EINCOMPLETE; }
+            lost.ms_search += st.ms_search + st.ms_finalize; lost.ms_expand_kernel += st.ms_expand_kernel; lost.ms_seed += st.ms_seed;
+            lost.raycasts += st.raycasts; lost.duplicate_hits += st.duplicate_hits; lost.closed_skips += st.closed_skips;
+            lost.candidates_fp32 += st.candidates_fp32; lost.candidates_fp64 += st.candidates_fp64; lost.rows_scanned += st.rows_scanned;
+            lost.probe_stages += st.probe_stages; lost.rounds += st.rounds; lost.seeds += st.seeds; lost.kernel_launches += st.kernel_launches;
+            lost.expand_launches += st.expand_launches; lost.expand_items += st.expand_items; lost.capacity_retries += st.capacity_retries;
             margin = std::max(1.5 * margin, 1.1 * need);
             if (debug) fprintf(stderr, "[hvb] periodic certificate failed (needs margin %.4g): retry with margin %.4g\n", need, margin);
             CK(cudaEventRecord(ev_a, stream));
+            const double build0 = st.ms_build, upload0 = st.ms_upload;
             rc = build_halo(); if (rc) return rc;
             rc = build_index(); if (rc) return rc;
+            lost.ms_search += st.ms_build;                 // the rebuild happened inside this hvb_search
+            st.ms_build = build0; st.ms_upload = upload0;  // ms_build keeps describing hvb_create / hvb_set_points
         }
         st.periodic_retries = retries;
         st.ms_finalize += ms_cert;
+        st.ms_search += lost.ms_search; st.ms_expand_kernel += lost.ms_expand_kernel; st.ms_seed += lost.ms_seed;
+        st.raycasts += lost.raycasts; st.duplicate_hits += lost.duplicate_hits; st.closed_skips += lost.closed_skips;
+        st.candidates_fp32 += lost.candidates_fp32; st.candidates_fp64 += lost.candidates_fp64; st.rows_scanned += lost.rows_scanned;
+        st.probe_stages += lost.probe_stages; st.rounds += lost.rounds; st.seeds += lost.seeds; st.kernel_launches += lost.kernel_launches;
+        st.expand_launches += lost.expand_launches; st.expand_items += lost.expand_items; st.capacity_retries += lost.capacity_retries;
+        // the certified margin, in units of the generator spacing, is kept for the next cloud on this context
+        if (retries > 0 && margin_spacing > 0) margin_rel_certified = std::max(margin_rel_certified, margin / margin_spacing);
         return HVB_OK;
     }
 
@@ -625,6 +653,20 @@ struct Ctx : hvb_ctx {
         CK(cudaSetDevice(prm.device));
         if (!periodic || !have_flags) { memset(flags, 1, (size_t)nvert); return HVB_OK; }   // without a halo every row is its own representative
         if (nvert > 0) CK(cudaMemcpyAsync(flags, vflags.p, (size_t)nvert, cudaMemcpyDeviceToHost, stream));
+        CK(cudaStreamSynchronize(stream));
+        return HVB_OK;
+    }
+
+    // which caller cells this context owns (multi-GPU slabs; all of them otherwise)
+    int fetch_owned(uint8_t* owned) override {
+        if (!owned) { err = "null output"; return HVB_EINVAL; }
+        const int64_t n_list = periodic ? n_user : n;
+        const int world = std::max(1, prm.world), rank = std::min(std::max(0, prm.rank), world - 1);
+        if (world == 1) { memset(owned, 1, (size_t)n_list); return HVB_OK; }
+        CK(cudaSetDevice(prm.device));
+        CK(own_mask.ensure(n));
+        k_own_mask<<<blocks_for(n, 256), 256, 0, stream>>>(perm.p, (int)n, (int)(n * rank / world), (int)(n * (rank + 1) / world), own_mask.p); ++launches;
+        CK(cudaMemcpyAsync(owned, own_mask.p, (size_t)n_list, cudaMemcpyDeviceToHost, stream));
         CK(cudaStreamSynchronize(stream));
         return HVB_OK;
     }
@@ -864,8 +906,14 @@ struct Ctx : hvb_ctx {
             if (++retries > 6) { err = "capacity exhausted after 6 retries"; return HVB_ENOMEM; }
             cap = vcap * 2;
         }
-        CK(cudaEventRecord(ev_b, stream));
         const bool by_slab = world > 1 && cells == nullptr;
+        own_ptr = nullptr;
+        if (by_slab) {
+            CK(own_mask.ensure(n));
+            k_own_mask<<<blocks_for(n, 256), 256, 0, stream>>>(perm.p, (int)n, (int)(n * rank / world), (int)(n * (rank + 1) / world), own_mask.p); ++launches;
+            own_ptr = own_mask.p;
+        }
+        CK(cudaEventRecord(ev_b, stream));
         // The neighbour lists are built from the vertex records of the walk (a set of pairs needs neither the result rows
         // nor their order) on their own stream, next to k_final_rows and the radix sort of the rows.  With seed vertices
         // they must be built now: the caller's own vertices are part of the lists but not of the returned rows
@@ -959,7 +1007,8 @@ struct Ctx : hvb_ctx {
             const int world = std::max(1, prm.world), rank = std::min(std::max(0, prm.rank), world - 1);
             const int lo = by_slab ? (int)(n * rank / world) : 0, hi = by_slab ? (int)(n * (rank + 1) / world) : 0;
             k_final_rows<D><<<blocks_for(nrec, 128), 128, 0, stream>>>(dv, perm.p, nrec, bits, out_sig[0].p, out_r[0].p, key_top.p, key_hi.p, key_lo.p,
-                                                                     &sc.p->out_count, &sc.p->max_var, lo, hi, seed_prefix);
+                                                                     &sc.p->out_count, &sc.p->max_var, lo, hi, seed_prefix,
+                                                                     prm.variance_tol, prm.break_tol, sc.p->tol_counts);
             ++launches;
         }
         if (nrays > 0) {
@@ -969,6 +1018,7 @@ struct Ctx : hvb_ctx {
         }
         int rc = read_scalars(); if (rc) return rc;
         nvert = h_sc.p->out_count;
+        st.rejected = h_sc.p->tol_counts[0]; st.suboptimal = h_sc.p->tol_counts[1];
         return sort_rows((u32)nvert, bits);
     }
 
@@ -1072,9 +1122,9 @@ struct Ctx : hvb_ctx {
         CK(cudaMemsetAsync(nbsc.p, 0, sizeof(NbScalars), ns));
         if (nb_raw) {
             const u32 nrec = std::min<u32>(h_sc.p->vcount, (u32)vcap);
-            if (nrec > 0) { k_pairs_raw<D><<<blocks_for(nrec, 128), 128, 0, ns>>>(dv, perm.p, nrec, n_list, ptab.p, nb_want - 1, deg.p, &nbsc.p->pflags); ++launches; }
+            if (nrec > 0) { k_pairs_raw<D><<<blocks_for(nrec, 128), 128, 0, ns>>>(dv, perm.p, nrec, n_list, ptab.p, nb_want - 1, deg.p, &nbsc.p->pflags, own_ptr); ++launches; }
         } else if (nvert > 0) {
-            k_pairs<D><<<blocks_for(nvert, 128), 128, 0, ns>>>(nb_rows, (u32)nvert, n_list, ptab.p, nb_want - 1, deg.p, &nbsc.p->pflags); ++launches;
+            k_pairs<D><<<blocks_for(nvert, 128), 128, 0, ns>>>(nb_rows, (u32)nvert, n_list, ptab.p, nb_want - 1, deg.p, &nbsc.p->pflags, own_ptr); ++launches;
         }
         // offsets = exclusive scan of the degrees (as int64); one host round trip brings the overflow flag and the total
         k_u32_to_i64<<<blocks_for(n, 256), 256, 0, ns>>>(deg.p, nb_off.p, n); ++launches;
@@ -1099,7 +1149,7 @@ struct Ctx : hvb_ctx {
         }
         CK(nb_ids.ensure(std::max<long long>(total, 1)));
         CK(cudaMemsetAsync(ncur.p, 0, n * sizeof(u32), ns));
-        k_pair_fill<<<blocks_for((int64_t)nb_want, 256), 256, 0, ns>>>(ptab.p, nb_want, n_list, nb_off.p, ncur.p, nb_ids.p); ++launches;
+        k_pair_fill<<<blocks_for((int64_t)nb_want, 256), 256, 0, ns>>>(ptab.p, nb_want, n_list, nb_off.p, ncur.p, nb_ids.p, own_ptr); ++launches;
         k_sort_lists<<<blocks_for(n, 128), 128, 0, ns>>>(nb_off.p, nb_ids.p, n); ++launches;
         CK(cudaGetLastError());          // no host wait here: the staging copy / the fetch calls order themselves behind the stream
         CK(cudaEventRecord(ev_nb, ns));
@@ -1112,7 +1162,9 @@ struct Ctx : hvb_ctx {
     int build_neighbors() {
         if (nb_total >= 0) return HVB_OK;
         CK(cudaSetDevice(prm.device));
-        int rc = nb_prepare(false, out_sig[res].p); if (rc) return rc;
+        // a slab result holds only the rows this rank OWNS; the lists of its own cells need every vertex it FOUND, so
+        // they come from the vertex records of the walk (still intact: the next search / set_points drops the result)
+        int rc = nb_prepare(own_ptr != nullptr, out_sig[res].p); if (rc) return rc;
         rc = nb_enqueue(stream); if (rc) return rc;
         return nb_finish(stream);
     }
@@ -1170,7 +1222,7 @@ struct Ctx : hvb_ctx {
         }
         CK(cudaStreamSynchronize(stream));
         nvert = count; res = 0; staged = false; have_result = true;
-        if (!(prm.neighbors && std::max(1, prm.world) > 1)) nb_total = -1;
+        nb_total = -1; own_ptr = nullptr;         // the rows are global now: lists are rebuilt from them on request, for every cell
         st.vertices = nvert;
         return HVB_OK;
     }
@@ -1191,7 +1243,7 @@ struct Ctx : hvb_ctx {
         }
         CK(cudaStreamSynchronize(stream));
         nvert = total; res = 0; staged = false; have_result = true;
-        if (!(prm.neighbors && std::max(1, prm.world) > 1)) nb_total = -1;
+        nb_total = -1; own_ptr = nullptr;
         st.vertices = nvert;
         return HVB_OK;
     }
@@ -1212,7 +1264,7 @@ struct Ctx : hvb_ctx {
         int rc = read_scalars(); if (rc) return rc;
         nvert = h_sc.p->out_count;
         rc = sort_rows((u32)nvert, bits); if (rc) return rc;
-        if (!(prm.neighbors && std::max(1, prm.world) > 1)) nb_total = -1;   // slab-built lists stay: they are complete for the rank's own cells
+        nb_total = -1; own_ptr = nullptr;         // the rows are global now: lists are rebuilt from them on request
         staged = false;                      // staged on the first hvb_view_* / hvb_fetch_* (only ranks that read the result pay the D2H)
         CK(cudaStreamSynchronize(stream));
         CK(cudaGetLastError());

@@ -16,6 +16,7 @@ struct hvb_ctx {
     virtual int halo_count(int64_t* nhalo, int32_t* npairs, double* margin) = 0;
     virtual int fetch_halo(int64_t* origin, int32_t* mult, double* xs) = 0;
     virtual int fetch_vertex_flags(uint8_t* flags) = 0;
+    virtual int fetch_owned(uint8_t* owned) = 0;
     virtual int cell_volumes(double* vol) = 0;
     virtual int cell_areas(double* area) = 0;
     virtual int clean_affected(const int64_t* sig, const double* r, int64_t nv, int stride, int64_t first_new, int64_t n_new, uint8_t* keep, uint8_t* affected) = 0;

@@ -488,7 +488,8 @@ template <int D>
 static __global__ void k_final_rows(Dev<D> dv, const int* __restrict__ perm, u32 nrec, int bits,
                              long long* __restrict__ out_sig, double* __restrict__ out_r,
                              u64* __restrict__ key_top, u64* __restrict__ key_hi, u64* __restrict__ key_lo, u32* __restrict__ out_count,
-                             double* __restrict__ max_var, int own_lo, int own_hi, u32 skip_below) {
+                             double* __restrict__ max_var, int own_lo, int own_hi, u32 skip_below,
+                             double variance_tol, double break_tol, u32* __restrict__ tol_counts) {
     u32 v = blockIdx.x * blockDim.x + threadIdx.x;
     if (v >= nrec || v < skip_below) return;          // records below skip_below are the caller's own (seed) vertices
     const int* s = dv.vsig + (size_t)v * (D + 1);
@@ -514,6 +515,11 @@ static __global__ void k_final_rows(Dev<D> dv, const int* __restrict__ perm, u32
     }
     double r[D];
     double var = canonical_vertex<D>(dv, in, r);
+    // walkray_correct_vertex (raycast.jl:257-279): the relative variance of the squared radii AFTER the correction decides;
+    // above break_tol the vertex is irreparable and dropped (SRI_vertex_irreparable), above variance_tol it is kept
+    // and counted (SRI_vertex_suboptimal_correction).  NaN (a singular system) counts as irreparable.
+    if (!(var <= break_tol)) { atomicAdd(tol_counts + 0, 1u); return; }
+    if (var > variance_tol) atomicAdd(tol_counts + 1, 1u);
     u32 pos = atomicAdd(out_count, 1u);
     u64 top = 0, hi = 0, lo = 0;
 #pragma unroll
@@ -577,15 +583,21 @@ static __global__ void k_final_rays(Dev<D> dv, const int* __restrict__ perm, u32
 // ------------------------------------------------------------------------------------------------------------
 // neighbour lists (neighbors_of_cell_new, neighbors.jl:219-262): set of unordered id pairs -> CSR
 // ------------------------------------------------------------------------------------------------------------
-// inserts the unordered pairs of one vertex (s ascending, 1-based caller ids, planes last) into the pair set
+// inserts the unordered pairs of one vertex (s ascending, 1-based caller ids, planes last) into the pair set.
+// `own` (may be null = every cell): byte mask over caller cells; only lists of owned cells are built (multi-GPU slabs:
+// a rank finds every vertex of its own cells, so these lists are complete; the lists of other cells would be partial
+// and are left empty)
 template <int D>
 __device__ __forceinline__ void pairs_of_row(const long long (&s)[D + 1], long long n, u64* __restrict__ ptab, u64 pmask,
-                                             u32* __restrict__ deg, u32* __restrict__ flags) {
+                                             u32* __restrict__ deg, u32* __restrict__ flags, const unsigned char* __restrict__ own) {
+    bool ow[D + 1];
+#pragma unroll
+    for (int i = 0; i < D + 1; ++i) ow[i] = (s[i] <= n) && (!own || own[s[i] - 1]);
 #pragma unroll
     for (int i = 0; i < D + 1; ++i) {
 #pragma unroll
         for (int j = i + 1; j < D + 1; ++j) {
-            if (s[i] > n) continue;                       // neither is a cell whose list is built (ids ascend: both are planes, or halo / planes)
+            if (!(ow[i] || ow[j])) continue;              // neither is a cell whose list is built (ids ascend: planes / halo last)
             u64 key = ((u64)s[i] << 32) | (u64)s[j];      // 1-based ids: key != 0
             u64 slot = mix64(key) & pmask;
             for (u32 probe = 0;; ++probe) {
@@ -594,8 +606,8 @@ __device__ __forceinline__ void pairs_of_row(const long long (&s)[D + 1], long l
                 if (cur == 0) {
                     cur = atomicCAS(ptab + slot, 0ULL, key);
                     if (cur == 0) {
-                        atomicAdd(deg + (s[i] - 1), 1u);
-                        if (s[j] <= n) atomicAdd(deg + (s[j] - 1), 1u);
+                        if (ow[i]) atomicAdd(deg + (s[i] - 1), 1u);
+                        if (ow[j]) atomicAdd(deg + (s[j] - 1), 1u);
                         break;
                     }
                     if (cur == key) break;
@@ -609,20 +621,20 @@ __device__ __forceinline__ void pairs_of_row(const long long (&s)[D + 1], long l
 
 template <int D>
 static __global__ void k_pairs(const long long* __restrict__ sig, u32 nv, long long n, u64* __restrict__ ptab, u64 pmask,
-                        u32* __restrict__ deg, u32* __restrict__ flags) {
+                        u32* __restrict__ deg, u32* __restrict__ flags, const unsigned char* __restrict__ own) {
     u32 v = blockIdx.x * blockDim.x + threadIdx.x;
     if (v >= nv) return;
     long long s[D + 1];
 #pragma unroll
     for (int k = 0; k < D + 1; ++k) s[k] = sig[(size_t)v * (D + 1) + k];
-    pairs_of_row<D>(s, n, ptab, pmask, deg, flags);
+    pairs_of_row<D>(s, n, ptab, pmask, deg, flags, own);
 }
 
 // the same straight from the vertex records of the walk (internal ids; dead records skipped): the lists do not have to
 // wait for the result rows, so they are built next to k_final_rows and the row sort
 template <int D>
 static __global__ void k_pairs_raw(Dev<D> dv, const int* __restrict__ perm, u32 nrec, long long n, u64* __restrict__ ptab, u64 pmask,
-                            u32* __restrict__ deg, u32* __restrict__ flags) {
+                            u32* __restrict__ deg, u32* __restrict__ flags, const unsigned char* __restrict__ own) {
     u32 v = blockIdx.x * blockDim.x + threadIdx.x;
     if (v >= nrec) return;
     const int* sp = dv.vsig + (size_t)v * (D + 1);
@@ -636,18 +648,24 @@ static __global__ void k_pairs_raw(Dev<D> dv, const int* __restrict__ perm, u32 
         for (int j = i; j > 0; --j)
             if (s[j - 1] > s[j]) { const long long t = s[j]; s[j] = s[j - 1]; s[j - 1] = t; }
     }
-    pairs_of_row<D>(s, n, ptab, pmask, deg, flags);
+    pairs_of_row<D>(s, n, ptab, pmask, deg, flags, own);
 }
 
 static __global__ void k_pair_fill(const u64* __restrict__ ptab, u64 nslots, long long n, const long long* __restrict__ off,
-                            u32* __restrict__ cursor, long long* __restrict__ ids) {
+                            u32* __restrict__ cursor, long long* __restrict__ ids, const unsigned char* __restrict__ own) {
     u64 i = blockIdx.x * (u64)blockDim.x + threadIdx.x;
     if (i >= nslots) return;
     u64 key = ptab[i];
     if (key == 0) return;
     long long a = (long long)(key >> 32), b = (long long)(key & 0xffffffffULL);
-    ids[off[a - 1] + atomicAdd(cursor + (a - 1), 1u)] = b;
-    if (b <= n) ids[off[b - 1] + atomicAdd(cursor + (b - 1), 1u)] = a;
+    if (a <= n && (!own || own[a - 1])) ids[off[a - 1] + atomicAdd(cursor + (a - 1), 1u)] = b;
+    if (b <= n && (!own || own[b - 1])) ids[off[b - 1] + atomicAdd(cursor + (b - 1), 1u)] = a;
+}
+
+// own[c] = 1 for the caller cells whose sorted position lies in the slab [lo, hi) of this context
+static __global__ void k_own_mask(const int* __restrict__ perm, int n, int lo, int hi, unsigned char* __restrict__ own) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) own[perm[i]] = (i >= lo && i < hi) ? 1 : 0;
 }
 
 static __global__ void k_sort_lists(const long long* __restrict__ off, long long* __restrict__ ids, long long n) {

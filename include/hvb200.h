@@ -39,13 +39,24 @@ typedef struct hvb_ctx hvb_ctx;
 /* Search settings: RaycastParameter (src/raycast-types.jl:312-324) plus backend knobs. */
 typedef struct hvb_params {
     /* the five tolerances of the reference, defaults raycast-types.jl:226-230 */
-    double variance_tol;      /* 1e-15 : accepted relative variance of the d+1 squared radii */
-    double break_tol;         /* 1e-5  : above this a vertex is rejected                    */
-    double b_nodes_tol;       /* 1e-7                                                       */
-    double plane_tolerance;   /* 1e-12 : half-space slack  c = c1 + |c1| * plane_tolerance (raycast.jl:802-804) */
-    double ray_tol;           /* 1e-12                                                      */
-    int32_t method;           /* 0 RCStandard/RCNonGeneralHP, 1 RCOriginal, 2 RCCombined, 3 RCNonGeneralFast
-                                 (raycast-types.jl:244-284): every value runs the same exact min-t kernel */
+    double variance_tol;      /* 1e-15 : relative variance of the d+1 squared radii above which a vertex counts as
+                                 "suboptimal" (raycast.jl:275-277); coordinates always come from the direct solve +
+                                 refinement step that replaces the reference's CG correction (raycast.jl:257-261) */
+    double break_tol;         /* 1e-5  : above this a vertex is dropped and counted in hvb_stats_t.rejected (raycast.jl:271) */
+    double b_nodes_tol;       /* 1e-7  : in the reference only widens the in-range ball that collects cospherical generators
+                                 (raycast.jl:870; adjust_boundary_vertex boundary.jl:444 is a no-op).  Here: accepted and
+                                 validated (> 0); candidates inside the reference's tie window are REPORTED as non-general
+                                 position (HVB_EDEGENERATE), see on_degenerate */
+    double plane_tolerance;   /* 1e-12 : half-space slack  c = c1 + |c1| * plane_tolerance (raycast.jl:802-804) and smallest
+                                 accepted ray parameter t (raycast.jl:887-889) */
+    double ray_tol;           /* 1e-12 : used by the reference only inside FastEdgeIterator (edgeiterate.jl:199,435-460), the
+                                 enumeration of non-general vertices this backend reports instead; accepted and validated */
+    int32_t method;           /* 0 RCStandard/RCNonGeneral/RCNonGeneralHP, 1 RCOriginal, 2 RCCombined, 3 RCNonGeneralFast,
+                                 4 RCOriginalSafety, 5 RCNonGeneralSkip, 6 RCOriginalHP, 7 RCNonGeneralCutoff
+                                 (raycast-types.jl:244-284).  The methods differ in the PROCEDURE that finds the min-t
+                                 generator, not in the winner; every value runs the one exact min-t kernel.  Other values:
+                                 HVB_EINVAL.  (The RCOriginal family assumes general position; this backend still reports
+                                 a non-general vertex instead of picking one winner silently.) */
     int32_t device;           /* CUDA device ordinal */
     /* slab sharding (parallelmesh.jl:52-87): this context explores slab `rank` of `world` contiguous slabs of
        the spatially sorted generator order; rank=0, world=1 explores everything */
@@ -58,7 +69,7 @@ typedef struct hvb_params {
     int32_t sort_output;      /* 1: vertices are returned in lexicographic order of their signature (default) */
     int32_t tile_size;        /* lanes cooperating on one frontier entry: 1, 2, 4, 8, 16 or 32; 0 = auto by dimension */
     int32_t neighbors;        /* 1: hvb_search also builds and stages the neighbour lists (default 0: on first request);
-                                 with world > 1 they are built from the slab result: complete for the rank's own cells */
+                                 with world > 1 they cover the rank's OWN cells (hvb_fetch_owned), other cells get empty lists */
     int32_t persistent;       /* the frontier walk.  3 (default): one persistent launch with a device-side queue; a warp takes
                                  its tickets, vertex indices and queue slots with ONE atomic each, every lane runs the
                                  min-t query of its own ray (tile_size 1 only);
@@ -101,6 +112,9 @@ typedef struct hvb_stats_t {
     double  ms_stage_wait;    /* time hvb_search waited, after the result was complete in HBM (end of ms_finalize), for the
                                  page-locked staging copies (D2H) that overlap the neighbour build */
     double  ms_upload;        /* part of ms_build: the host -> device copy of the generators (hvb_create / hvb_set_points) */
+    int64_t rejected;         /* vertices dropped because the relative variance of their squared radii exceeds break_tol
+                                 (walkray_correct_vertex raycast.jl:271-273, SRI_vertex_irreparable) */
+    int64_t suboptimal;       /* vertices kept with a variance between variance_tol and break_tol (raycast.jl:275-277) */
 } hvb_stats_t;
 
 /* fills *p with the reference's defaults (RaycastParameter(Float64), raycast-types.jl:312-324) */
@@ -192,6 +206,13 @@ int hvb_merge_device(hvb_ctx* ctx, const void* sig_dev, const void* r_dev, int64
 int hvb_adopt_device(hvb_ctx* ctx, const void* sig_dev, const void* r_dev, int64_t count);
 /* same, for the raw output of a padded all-gather: nseg segments of seg_cap rows, counts[k] (host array) valid rows each */
 int hvb_adopt_device_padded(hvb_ctx* ctx, const void* sig_dev, const void* r_dev, int nseg, int64_t seg_cap, const int64_t* counts);
+
+/* owned[i] = 1 (n entries; periodic contexts: the n caller generators) iff cell i+1 belongs to this context's slab
+ * (world > 1: its position in the spatially sorted order lies in slab `rank`; the analogue of the index range a thread
+ * receives from partition_indices, parallelmesh.jl:52-87).  With world > 1 the neighbour lists are built for owned cells
+ * only -- the rank found every vertex of those cells, so they are complete; other cells get EMPTY lists -- until a
+ * merged result is installed (hvb_adopt_device*, hvb_merge_device, hvb_allgather), after which they cover every cell. */
+int hvb_fetch_owned(hvb_ctx* ctx, uint8_t* owned);
 
 /* rare_events / statistics.jl:132-143 analogue */
 /* Refinement.  Replaces clean_affected! (src/meshrefine.jl:126-149) inside systematic_refine! (:183-216):

@@ -104,19 +104,32 @@ def test_iter_subset_finds_all_vertices_of_the_cells(hvb, oracle):
     assert want <= got <= {tuple(r) for r in o["sig"].tolist()}
 
 
-def test_slab_union_equals_full(hvb, oracle):
-    """the multi-GPU decomposition on one device: the union of the slab searches is the full vertex set"""
+@pytest.mark.parametrize("nb_in_search", [1, 0])
+def test_slab_union_equals_full(hvb, oracle, nb_in_search):
+    """the multi-GPU decomposition on one device: the union of the slab searches is the full vertex set, and every rank
+    holds the complete neighbour lists of the cells it owns (empty lists elsewhere)"""
     xs = points(6000, 3, 10)
     base, normal = qhull_oracle.cuboid(3)
     o = oracle.run(xs, base, normal)
     rows, total = set(), 0
+    owned_by = np.zeros(6000, dtype=int)
     for rank in range(4):
-        s = hvb.Raycast(xs, domain=hvb.cuboid(3, periodic=[]), options=hvb.RaycastParameter(threading=hvb.B200Thread(0, rank, 4), neighbors=1))
+        s = hvb.Raycast(xs, domain=hvb.cuboid(3, periodic=[]), options=hvb.RaycastParameter(threading=hvb.B200Thread(0, rank, 4), neighbors=nb_in_search))
         mesh, _ = hvb.voronoi(xs, searcher=s)
         assert (np.diff(mesh.sig[:, 0]) >= 0).all()                      # each shard is sorted
         rows |= {tuple(r) for r in mesh.sig.tolist()}
         total += mesh.sig.shape[0]
         assert s.stats()["raycasts"] < 0.9 * len(o["sig"])               # a rank walks its slab (plus a halo) only
+        own = s.owned()
+        owned_by += own
+        off, ids = mesh.neighbors()
+        for c in range(6000):
+            mine, ref = ids[off[c]:off[c + 1]], o["nb_ids"][o["nb_off"][c]:o["nb_off"][c + 1]]
+            if own[c]:
+                assert np.array_equal(mine, ref), (rank, c)
+            else:
+                assert len(mine) == 0, (rank, c)
+    assert (owned_by == 1).all()                                         # the slabs partition the cells
     assert rows == {tuple(r) for r in o["sig"].tolist()}
     assert total == len(o["sig"])                                        # ownership rule: the shards are disjoint
 
@@ -208,6 +221,81 @@ def test_full_size_matches_oracle(hvb, oracle, d, n):
     assert_same_mesh(mesh.sig, mesh.r, o["sig"], o["r"], xs, COORD_TOL)
     off, ids = mesh.neighbors()
     assert np.array_equal(off, o["nb_off"]) and np.array_equal(ids, o["nb_ids"])
+
+
+# ---- every BASELINE.json config at its OWN size, exact parity against the 8-thread restatement ----------------------
+# C3 (1 000 000 points, d = 2), C4 (50 000 points, d = 5) and d = 6 at 2 000 points (C5's dimension; its periodic form is
+# covered in test_gpu_periodic.py).  The oracle needs 17 s / 110 s / 20 s on 8 host threads.
+@pytest.mark.parametrize("d,n", [(2, 1000000), (5, 50000), (6, 2000)])
+def test_config_size_matches_oracle(hvb, oracle, d, n):
+    xs = points(n, d, 0)
+    base, normal = qhull_oracle.cuboid(d)
+    o = oracle.run(xs, base, normal, nthreads=min(8, os.cpu_count() or 1))
+    mesh, s = run_gpu(hvb, xs, True)
+    assert_same_mesh(mesh.sig, mesh.r, o["sig"], o["r"], xs, COORD_TOL)
+    if d <= 5:
+        off, ids = mesh.neighbors()
+        assert np.array_equal(off, o["nb_off"]) and np.array_equal(ids, o["nb_ids"])
+    st = s.stats()
+    assert st["degenerate"] == 0 and st["rejected"] == 0 and st["vertices"] == len(o["sig"])
+
+
+# ---- the search_settings raycast methods (test/rcmethods.jl:4-13: d = 4, 1000 points, cuboid, |sum(volume) - 1| < 1e-3) ----
+@pytest.mark.parametrize("method", ["RCCombined", "RCOriginal", "RCNonGeneralFast", "RCNonGeneral", "RCOriginalHP", "RCNonGeneralSkip"])
+def test_rcmethods(hvb, oracle, method):
+    xs = points(1000, 4, 99)
+    base, normal = qhull_oracle.cuboid(4)
+    o = oracle.run(xs, base, normal)
+    mesh, s = run_gpu(hvb, xs, True, method=getattr(hvb, method))
+    assert s.parameters.method == getattr(hvb, method)
+    assert_same_mesh(mesh.sig, mesh.r, o["sig"], o["r"], xs, COORD_TOL)     # the winner does not depend on the procedure
+    vol = mesh.volumes()
+    assert abs(vol.sum() - 1.0) < 1e-3                                       # the reference's own bar
+    assert abs(vol.sum() - 1.0) < 1e-10
+
+
+def test_unknown_method_and_bad_tolerances_are_refused(hvb):
+    xs = points(100, 3, 0)
+    for kw in (dict(method=8), dict(method=-1), dict(break_tol=0.0), dict(variance_tol=-1.0), dict(ray_tol=float("nan"))):
+        with pytest.raises(hvb.HVBError) as e:
+            run_gpu(hvb, xs, True, **kw)
+        assert e.value.code == hvb._abi.HVB_EINVAL
+
+
+def test_break_tol_and_variance_tol_are_honoured(hvb):
+    """walkray_correct_vertex (raycast.jl:257-279): vertices whose squared radii vary by more than break_tol (relative
+    variance) are dropped and counted, those above variance_tol are kept and counted"""
+    xs = points(4000, 3, 21)
+    a, sa = run_gpu(hvb, xs, True)
+    assert sa.stats()["rejected"] == 0 and sa.stats()["suboptimal"] == 0
+    # canonical coordinates leave a relative variance of ~1e-31 .. 1e-28: thresholds inside that range split the rows
+    b, sb = run_gpu(hvb, xs, True, variance_tol=1e-40, break_tol=1e-5)
+    assert sb.stats()["rejected"] == 0 and sb.stats()["suboptimal"] > 0
+    assert np.array_equal(a.sig, b.sig)
+    c, sc = run_gpu(hvb, xs, True, variance_tol=1e-40, break_tol=1e-31)
+    rej = sc.stats()["rejected"]
+    assert 0 < rej < len(a.sig) and len(c.sig) == len(a.sig) - rej
+    assert {tuple(r) for r in c.sig.tolist()} <= {tuple(r) for r in a.sig.tolist()}
+
+
+@pytest.mark.parametrize("eps,degenerate", [(0.0, True), (1e-14, True), (1e-7, False)])
+def test_near_degenerate_input_is_reported_like_the_reference(hvb, eps, degenerate):
+    """five generators on a common sphere: the reference appends every candidate inside its tie window to the signature
+    (raycast.jl:902,926-949, a vertex with d + 2 generators); this backend reports exactly those inputs as non-general
+    position and treats a 1e-7 perturbation as general, as the reference does"""
+    rng = np.random.default_rng(5)
+    u = rng.normal(size=(5, 3)); u /= np.linalg.norm(u, axis=1)[:, None]
+    cos = 0.5 + 0.25 * u                                   # on the sphere of radius 0.25 around the centre of the cube
+    cos[4] = 0.5 + 0.25 * (1.0 + eps) * u[4]
+    far = 0.5 + 0.49 * np.sign(rng.normal(size=(40, 3))) * (0.8 + 0.2 * rng.random((40, 3)))   # keep the ball empty
+    xs = np.vstack([cos, far])
+    if degenerate:
+        with pytest.raises(hvb.HVBError) as e:
+            run_gpu(hvb, xs, True)
+        assert e.value.code == hvb._abi.HVB_EDEGENERATE
+    else:
+        mesh, s = run_gpu(hvb, xs, True)
+        assert s.stats()["degenerate"] == 0 and len(mesh.sig) > 0
 
 
 # ---- BASELINE.json full sizes: properties that need no oracle run --------------------------------------------
