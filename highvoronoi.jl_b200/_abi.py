@@ -6,13 +6,14 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("HVB_LIB") or os.path.join(_HERE, "lib", "libhvb200.so")   # HVB_LIB: tuning builds
 
-HVB_OK, HVB_EINVAL, HVB_ECUDA, HVB_ENOGPU, HVB_ENOMEM, HVB_EDEGENERATE, HVB_ESTATE, HVB_EINCOMPLETE = 0, -1, -2, -3, -4, -5, -6, -7
+HVB_OK, HVB_EINVAL, HVB_ECUDA, HVB_ENOGPU, HVB_ENOMEM, HVB_EDEGENERATE, HVB_ESTATE, HVB_EINCOMPLETE, HVB_ENCCL = 0, -1, -2, -3, -4, -5, -6, -7, -8
 ERROR_NAMES = {-1: "HVB_EINVAL", -2: "HVB_ECUDA", -3: "HVB_ENOGPU", -4: "HVB_ENOMEM", -5: "HVB_EDEGENERATE",
-               -6: "HVB_ESTATE", -7: "HVB_EINCOMPLETE"}
+               -6: "HVB_ESTATE", -7: "HVB_EINCOMPLETE", -8: "HVB_ENCCL"}
 
 EXPORTS = ("hvb_default_params", "hvb_create", "hvb_set_points", "hvb_search", "hvb_counts", "hvb_fetch_vertices", "hvb_fetch_vertices_range", "hvb_fetch_rays",
            "hvb_neighbor_count", "hvb_fetch_neighbors", "hvb_view_vertices", "hvb_view_neighbors", "hvb_export_device", "hvb_merge_device", "hvb_adopt_device", "hvb_adopt_device_padded",
-           "hvb_stats", "hvb_last_error", "hvb_destroy", "hvb_version", "hvb_create_periodic", "hvb_halo_count", "hvb_fetch_halo", "hvb_fetch_vertex_flags", "hvb_cell_volumes", "hvb_cell_areas", "hvb_clean_affected", "hvb_fetch_owned")
+           "hvb_stats", "hvb_last_error", "hvb_destroy", "hvb_version", "hvb_create_periodic", "hvb_halo_count", "hvb_fetch_halo", "hvb_fetch_vertex_flags", "hvb_cell_volumes", "hvb_cell_areas", "hvb_clean_affected", "hvb_fetch_owned",
+           "hvb_create_multi", "hvb_comm_unique_id", "hvb_comm_init", "hvb_exchange_counts", "hvb_allgather")
 
 
 class hvb_params(ctypes.Structure):
@@ -32,7 +33,7 @@ class hvb_stats_t(ctypes.Structure):
                [("expand_launches", ctypes.c_int64), ("expand_items", ctypes.c_int64)] + \
                [(k, ctypes.c_double) for k in ("ms_seed", "ms_neighbors", "ms_rows_sort")] + \
                [(k, ctypes.c_int64) for k in ("halo_nodes", "unique_vertices", "periodic_retries")] + [("ms_stage_wait", ctypes.c_double), ("ms_upload", ctypes.c_double)] + \
-               [("rejected", ctypes.c_int64), ("suboptimal", ctypes.c_int64)]
+               [("rejected", ctypes.c_int64), ("suboptimal", ctypes.c_int64), ("exchange_bytes", ctypes.c_int64)]
 
     def as_dict(self):
         return {k: getattr(self, k) for k, _ in self._fields_}
@@ -64,6 +65,11 @@ def lib():
         L.hvb_fetch_vertex_flags.argtypes = [vp, vp]
         L.hvb_cell_volumes.argtypes = [vp, vp]
         L.hvb_fetch_owned.argtypes = [vp, vp]
+        L.hvb_create_multi.argtypes = [ctypes.POINTER(vp), i32, i64, vp, i32, vp, vp, vp, ctypes.POINTER(hvb_params), i32, vp]
+        L.hvb_comm_unique_id.argtypes = [vp]
+        L.hvb_comm_init.argtypes = [vp, vp]
+        L.hvb_exchange_counts.argtypes = [vp, vp]
+        L.hvb_allgather.argtypes = [vp]
         L.hvb_cell_areas.argtypes = [vp, vp]
         L.hvb_clean_affected.argtypes = [vp, vp, vp, i64, i32, i64, i64, vp, vp]
         L.hvb_set_points.argtypes = [vp, i64, vp]
@@ -86,7 +92,7 @@ def lib():
         L.hvb_destroy.argtypes = [vp]
         L.hvb_destroy.restype = None
         L.hvb_version.restype = ctypes.c_char_p
-        for name in ("hvb_fetch_owned", "hvb_cell_volumes", "hvb_cell_areas", "hvb_clean_affected", "hvb_create", "hvb_create_periodic", "hvb_halo_count", "hvb_fetch_halo", "hvb_fetch_vertex_flags", "hvb_set_points", "hvb_search", "hvb_counts", "hvb_fetch_vertices", "hvb_fetch_vertices_range", "hvb_fetch_rays", "hvb_neighbor_count",
+        for name in ("hvb_create_multi", "hvb_comm_unique_id", "hvb_comm_init", "hvb_exchange_counts", "hvb_allgather", "hvb_fetch_owned", "hvb_cell_volumes", "hvb_cell_areas", "hvb_clean_affected", "hvb_create", "hvb_create_periodic", "hvb_halo_count", "hvb_fetch_halo", "hvb_fetch_vertex_flags", "hvb_set_points", "hvb_search", "hvb_counts", "hvb_fetch_vertices", "hvb_fetch_vertices_range", "hvb_fetch_rays", "hvb_neighbor_count",
                      "hvb_fetch_neighbors", "hvb_view_vertices", "hvb_view_neighbors", "hvb_export_device", "hvb_merge_device", "hvb_adopt_device", "hvb_adopt_device_padded", "hvb_stats"):
             getattr(L, name).restype = i32
         _lib = L

@@ -77,11 +77,15 @@ class SingleThread:
 
 
 class B200Thread:
-    """The new `threading` singleton the Julia shim adds: run the search on GPU `device`,
-    as slab `rank` of `world` GPUs."""
+    """The new `threading` singleton the Julia shim adds.
 
-    def __init__(self, device=0, rank=0, world=1):
+    B200Thread(ngpus=N[, devices=[...]]): ONE process drives N GPUs (hvb_create_multi) -- the analogue of the reference's
+    MultiThread(N, 1) (sysvoronoi.jl:50-82).  B200Thread(device, rank, world): this process is slab `rank` of `world`
+    processes, one per GPU (torchrun / MPI style); see hvb200.multigpu for the communicator."""
+
+    def __init__(self, device=0, rank=0, world=1, ngpus=1, devices=None):
         self.device, self.rank, self.world = device, rank, world
+        self.ngpus, self.devices = int(ngpus), (None if devices is None else [int(v) for v in devices])
 
 
 def RaycastParameter(variance_tol=1e-15, break_tol=1e-5, b_nodes_tol=1e-7, plane_tolerance=1e-12, ray_tol=1e-12,
@@ -94,6 +98,8 @@ def RaycastParameter(variance_tol=1e-15, break_tol=1e-5, b_nodes_tol=1e-7, plane
     p.method = int(method)
     if threading is not None and isinstance(threading, B200Thread):
         p.device, p.rank, p.world = threading.device, threading.rank, threading.world
+        if threading.ngpus > 1 or threading.devices is not None:
+            p._multi = (threading.ngpus if threading.devices is None else len(threading.devices), threading.devices)
     for k, v in backend.items():
         if not hasattr(p, k):
             raise TypeError("unknown search setting %r" % k)
@@ -120,7 +126,15 @@ class Raycast:
         base = self.domain.base.ctypes.data_as(ctypes.c_void_p) if P else None
         normal = self.domain.normal.ctypes.data_as(ctypes.c_void_p) if P else None
         self.periodic = bool(periodic) and len(self.domain.periodic) > 0
-        if self.periodic:
+        self.multi = getattr(self.parameters, "_multi", None)
+        if self.multi is not None:
+            ngpus, devices = self.multi
+            self._bc = self.domain.plane_bc() if self.periodic else None
+            dev = None if devices is None else np.ascontiguousarray(devices, dtype=np.int32)
+            rc = L.hvb_create_multi(ctypes.byref(self._ctx), d, n, self.xs.ctypes.data_as(ctypes.c_void_p), P, base, normal,
+                                    self._bc.ctypes.data_as(ctypes.c_void_p) if self.periodic else None,
+                                    ctypes.byref(self.parameters), ngpus, None if dev is None else dev.ctypes.data_as(ctypes.c_void_p))
+        elif self.periodic:
             self._bc = self.domain.plane_bc()
             rc = L.hvb_create_periodic(ctypes.byref(self._ctx), d, n, self.xs.ctypes.data_as(ctypes.c_void_p), P, base, normal,
                                        self._bc.ctypes.data_as(ctypes.c_void_p), ctypes.byref(self.parameters))
@@ -199,6 +213,7 @@ class VoronoiMesh:
 
     def __init__(self, searcher, copy=False):
         self.searcher = searcher
+        copy = bool(copy) or getattr(searcher, "multi", None) is not None     # shards of several GPUs have no common staging buffer
         self.copy = copy
         self.n, self.dim = searcher.n, searcher.dim
         L, ctx = _abi.lib(), searcher._ctx
@@ -302,8 +317,11 @@ class VoronoiMesh:
         return self.sig.shape[0]
 
 
-def voronoi(xs, searcher=None, Iter=None, copy=False, known=None, **_ignored):
+def voronoi(xs, searcher=None, Iter=None, copy=True, known=None, **_ignored):
     """voronoi(xs; searcher=Raycast(xs), Iter=1:length(xs)) (sysvoronoi.jl:7-39) -> (mesh, searcher).
+
+    copy=True (default): the mesh owns its arrays.  copy=False returns zero-copy views of the searcher's page-locked
+    staging memory, valid only until the next search / set_points / close on that searcher.
 
     known=(sig, r): vertices the mesh already holds (the reference passes a non-empty mesh in refinement,
     meshrefine.jl:199-215): the walk continues from them and only NEW vertices are returned."""

@@ -28,11 +28,11 @@ int hvb_create(hvb_ctx** out, int dim, int64_t n, const double* xs, int nplanes,
     return hvb_create_periodic(out, dim, n, xs, nplanes, plane_base, plane_normal, nullptr, params);
 }
 
-int hvb_create_periodic(hvb_ctx** out, int dim, int64_t n, const double* xs, int nplanes, const double* plane_base,
-                        const double* plane_normal, const int32_t* plane_bc, const hvb_params* params) {
+// argument checks shared by the create calls; fills `prm`
+static int check_create(hvb_ctx** out, int dim, int64_t n, const double* xs, int nplanes, const double* plane_base,
+                        const double* plane_normal, const hvb_params* params, hvb_params& prm, int* ndev_out) {
     if (!out) return HVB_EINVAL;
     *out = nullptr;
-    hvb_params prm;
     if (params) prm = *params; else hvb_default_params(&prm);
     if (dim < 2 || dim > HVB_MAX_DIM) { g_create_error = "dimension must be 2..6"; return HVB_EINVAL; }
     if (n <= dim || !xs) { g_create_error = "There are not enough points to create a Voronoi tessellation"; return HVB_EINVAL; }   // sysvoronoi.jl:25-27
@@ -48,6 +48,16 @@ int hvb_create_periodic(hvb_ctx** out, int dim, int64_t n, const double* xs, int
         g_create_error = std::string("no CUDA device available (") + cudaGetErrorString(ce) + "); libhvb200 has no host fallback";
         return HVB_ENOGPU;
     }
+    *ndev_out = ndev;
+    return HVB_OK;
+}
+
+int hvb_create_periodic(hvb_ctx** out, int dim, int64_t n, const double* xs, int nplanes, const double* plane_base,
+                        const double* plane_normal, const int32_t* plane_bc, const hvb_params* params) {
+    hvb_params prm;
+    int ndev = 0;
+    int rc = check_create(out, dim, n, xs, nplanes, plane_base, plane_normal, params, prm, &ndev);
+    if (rc != HVB_OK) return rc;
     if (prm.device < 0 || prm.device >= ndev) { g_create_error = "bad device ordinal"; return HVB_EINVAL; }
     hvb_ctx* c = nullptr;
     switch (dim) {
@@ -58,11 +68,32 @@ int hvb_create_periodic(hvb_ctx** out, int dim, int64_t n, const double* xs, int
         case 6: c = hvb_make_ctx_6(); break;
     }
     c->dim = dim; c->n = n; c->P = nplanes; c->prm = prm;
-    int rc = c->init(xs, plane_base, plane_normal, plane_bc);
+    rc = c->init(xs, plane_base, plane_normal, plane_bc);
     if (rc != HVB_OK) { g_create_error = c->err; delete c; return rc; }
     *out = c;
     return HVB_OK;
 }
+
+int hvb_create_multi(hvb_ctx** out, int dim, int64_t n, const double* xs, int nplanes, const double* plane_base,
+                     const double* plane_normal, const int32_t* plane_bc, const hvb_params* params, int ngpus, const int32_t* devices) {
+    hvb_params prm;
+    int ndev = 0;
+    int rc = check_create(out, dim, n, xs, nplanes, plane_base, plane_normal, params, prm, &ndev);
+    if (rc != HVB_OK) return rc;
+    if (ngpus < 1 || ngpus > ndev || ngpus > 64) { g_create_error = "ngpus must be between 1 and the number of visible CUDA devices"; return HVB_EINVAL; }
+    for (int k = 0; devices && k < ngpus; ++k) {
+        if (devices[k] < 0 || devices[k] >= ndev) { g_create_error = "bad device ordinal"; return HVB_EINVAL; }
+    }
+    hvb_ctx* c = hvb_make_multi(dim, n, xs, nplanes, plane_base, plane_normal, plane_bc, prm, ngpus, devices, &rc, &g_create_error);
+    if (!c) return rc;
+    *out = c;
+    return HVB_OK;
+}
+
+int hvb_comm_unique_id(void* id128) { return id128 ? hvb_nccl_unique_id(id128, &g_create_error) : HVB_EINVAL; }
+int hvb_comm_init(hvb_ctx* ctx, const void* id128) { return ctx ? ctx->comm_init(id128) : HVB_EINVAL; }
+int hvb_exchange_counts(hvb_ctx* ctx, int64_t* counts) { return ctx ? ctx->exchange_counts(counts) : HVB_EINVAL; }
+int hvb_allgather(hvb_ctx* ctx) { return ctx ? ctx->allgather() : HVB_EINVAL; }
 
 int hvb_set_points(hvb_ctx* ctx, int64_t n, const double* xs) { return ctx ? ctx->set_points(n, xs) : HVB_EINVAL; }
 

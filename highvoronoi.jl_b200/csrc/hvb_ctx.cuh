@@ -22,6 +22,7 @@
 #include "hvb_host.hpp"
 #include "hvb_ctx_base.hpp"
 #include "hvb_kernels.cuh"
+#include "hvb_nccl.hpp"
 
 using namespace hvb;
 
@@ -34,6 +35,17 @@ using namespace hvb;
             snprintf(buf_, sizeof(buf_), "%s failed at %s:%d: %s", #call, __FILE__, __LINE__, cudaGetErrorString(e_)); \
             this->err = buf_;                                                                            \
             return (e_ == cudaErrorMemoryAllocation) ? HVB_ENOMEM : HVB_ECUDA;                           \
+        }                                                                                                \
+    } while (0)
+
+#define NK(call)                                                                                         \
+    do {                                                                                                 \
+        ncclResult_t r_ = (call);                                                                        \
+        if (r_ != ncclSuccess) {                                                                         \
+            char buf_[512];                                                                              \
+            snprintf(buf_, sizeof(buf_), "%s failed at %s:%d: %s", #call, __FILE__, __LINE__, hvb::Nccl::get().GetErrorString(r_)); \
+            this->err = buf_;                                                                            \
+            return HVB_ENCCL;                                                                            \
         }                                                                                                \
     } while (0)
 
@@ -96,6 +108,8 @@ struct Scalars {            // small device-side words, mirrored into pinned hos
     u32 bbox_done;
     u32 bbox_viol;
     u32 pad2;
+    u32 ray_out;                      // unbounded edges this rank owns (k_final_rays with slabs)
+    u32 pad3;
     u32 tol_counts[2];                // vertices dropped (variance > break_tol) / kept above variance_tol (k_final_rows)
     double max_var;
     double bbox[12];
@@ -209,6 +223,8 @@ struct Ctx : hvb_ctx {
         if (ev_stage) cudaEventDestroy(ev_stage);
         if (ev_nb) cudaEventDestroy(ev_nb);
         nbsc.release(); h_nbsc.release(); h_nbtotal.release(); own_mask.release();
+        if (comm && comm_owned) Nccl::get().CommDestroy(comm);
+        xc_counts.release(); h_xc_counts.release(); xs_sig32.release(); xr_sig32.release(); xs_r.release(); xr_r.release(); xc_red.release(); h_xc_red.release();
         if (nstream) { cudaStreamSynchronize(nstream); cudaStreamDestroy(nstream); }
         if (sstream2) { cudaStreamSynchronize(sstream2); cudaStreamDestroy(sstream2); }
         if (ev_p0) cudaEventDestroy(ev_p0);
@@ -299,7 +315,6 @@ struct Ctx : hvb_ctx {
             }
             periodic = halo.npairs > 0;
         }
-        if (periodic && std::max(1, prm.world) > 1) { err = "periodic domains are not sharded across GPUs yet (world must be 1)"; return HVB_EINVAL; }
         CK(planes.ensure(1)); CK(ctr.ensure(1)); CK(sc.ensure(1)); CK(h_sc.ensure(1)); CK(h_ctr.ensure(1)); CK(h_extra.ensure(1));
         CK(cert.ensure(1)); CK(h_cert.ensure(1));
         CK(cudaMemcpyAsync(planes.p, &ps_orig, sizeof(ps_orig), cudaMemcpyHostToDevice, stream));
@@ -567,6 +582,11 @@ struct Ctx : hvb_ctx {
             int rc = search_once(cells, ncells_in, nullptr, nullptr, 0, 0); if (rc) return rc;
             bool ok = false; double need = 0;
             rc = certify(&ok, &need, &ms_cert); if (rc) return rc;
+            if (std::max(1, prm.world) > 1) {
+                // every rank must build the same halo (its numbering is part of the result): agree on the verdict
+                if (ok && !comm) { /* nothing to agree on for this rank; ranks that fail report the missing communicator */ }
+                else { double v[2] = {need, ok ? 0.0 : 1.0}; rc = allreduce_max(v, 2); if (rc) return rc; need = v[0]; ok = (v[1] == 0.0); }
+            }
             if (ok) break;
             if (++retries > 6) { err = "periodic certificate still fails after 6 margin increases"; return HVB_EINCOMPLETE; }
             lost.ms_search += st.ms_search + st.ms_finalize; lost.ms_expand_kernel += st.ms_expand_kernel; lost.ms_seed += st.ms_seed;
@@ -773,6 +793,7 @@ struct Ctx : hvb_ctx {
         if (nseed < 0 || (nseed > 0 && (!seed_sig || !seed_r || stride < D + 1))) { err = "bad seed vertex arguments"; return HVB_EINVAL; }
         CK(cudaSetDevice(prm.device));
         have_result = false; staged = false; nb_total = -1; have_flags = false;
+        st.exchange_bytes = 0;
         int64_t cap = prm.vertex_capacity > 0 ? prm.vertex_capacity
                       : (periodic ? (int64_t)(estimate_vertices(D, n_user, P) * periodic_versions()) : estimate_vertices(D, n, P));
         if (vcap >= cap) cap = vcap;
@@ -1008,16 +1029,20 @@ struct Ctx : hvb_ctx {
             const int lo = by_slab ? (int)(n * rank / world) : 0, hi = by_slab ? (int)(n * (rank + 1) / world) : 0;
             k_final_rows<D><<<blocks_for(nrec, 128), 128, 0, stream>>>(dv, perm.p, nrec, bits, out_sig[0].p, out_r[0].p, key_top.p, key_hi.p, key_lo.p,
                                                                      &sc.p->out_count, &sc.p->max_var, lo, hi, seed_prefix,
-                                                                     prm.variance_tol, prm.break_tol, sc.p->tol_counts);
+                                                                     prm.variance_tol, prm.break_tol, sc.p->tol_counts, (int)n_user);
             ++launches;
         }
         if (nrays > 0) {
             CK(ray_edge.ensure((size_t)nrays * D)); CK(ray_base.ensure((size_t)nrays * D)); CK(ray_dir.ensure((size_t)nrays * D)); CK(ray_node.ensure(nrays));
-            k_final_rays<D><<<blocks_for(nrays, 128), 128, 0, stream>>>(dv, perm.p, (u32)nrays, ray_edge.p, ray_base.p, ray_dir.p, ray_node.p);
+            const int world = std::max(1, prm.world), rank = std::min(std::max(0, prm.rank), world - 1);
+            const int lo = by_slab ? (int)(n * rank / world) : 0, hi = by_slab ? (int)(n * (rank + 1) / world) : 0;
+            k_final_rays<D><<<blocks_for(nrays, 128), 128, 0, stream>>>(dv, perm.p, (u32)nrays, ray_edge.p, ray_base.p, ray_dir.p, ray_node.p,
+                                                                     lo, hi, &sc.p->ray_out);
             ++launches;
         }
         int rc = read_scalars(); if (rc) return rc;
         nvert = h_sc.p->out_count;
+        if (by_slab) nrays = h_sc.p->ray_out;
         st.rejected = h_sc.p->tol_counts[0]; st.suboptimal = h_sc.p->tol_counts[1];
         return sort_rows((u32)nvert, bits);
     }
@@ -1185,6 +1210,7 @@ struct Ctx : hvb_ctx {
     }
     int view_neighbors(const int64_t** off, const int64_t** ids, int64_t* total) override {
         if (!have_result) { err = "no search result"; return HVB_ESTATE; }
+        CK(cudaSetDevice(prm.device));
         int rc = build_neighbors(); if (rc) return rc;
         rc = stage_neighbors(); if (rc) return rc;
         CK(cudaStreamSynchronize(stream));
@@ -1197,6 +1223,98 @@ struct Ctx : hvb_ctx {
         int rc = view_neighbors(&o, &i, &tot); if (rc) return rc;
         if (off) memcpy(off, o, (size_t)(n + 1) * 8);
         if (ids && tot > 0) memcpy(ids, i, (size_t)tot * 8);
+        return HVB_OK;
+    }
+
+    // ---- in-library collective: one NCCL communicator per context (process-per-GPU callers: hvb_comm_init; the
+    // single-process multi-GPU context of hvb_create_multi attaches communicators made by ncclCommInitAll) -------------
+    ncclComm_t comm = nullptr;
+    bool comm_owned = false;
+    DBuf<long long> xc_counts;
+    HBuf<long long> h_xc_counts;
+    DBuf<int> xs_sig32, xr_sig32;
+    DBuf<double> xs_r, xr_r, xc_red;
+    HBuf<double> h_xc_red;
+    int need_nccl() {
+        Nccl& N = Nccl::get();
+        if (!N.ok()) { err = "NCCL is not available: " + N.error; return HVB_ENCCL; }
+        return HVB_OK;
+    }
+    int comm_init(const void* id128) override {
+        if (!id128) { err = "null NCCL id"; return HVB_EINVAL; }
+        int rc = need_nccl(); if (rc) return rc;
+        CK(cudaSetDevice(prm.device));
+        const int world = std::max(1, prm.world), rank = std::min(std::max(0, prm.rank), world - 1);
+        if (comm && comm_owned) Nccl::get().CommDestroy(comm);
+        comm = nullptr;
+        ncclUniqueId id;
+        memcpy(&id, id128, sizeof(id));
+        NK(Nccl::get().CommInitRank(&comm, world, id, rank));
+        comm_owned = true;
+        return HVB_OK;
+    }
+    int comm_attach(void* c) override { comm = (ncclComm_t)c; comm_owned = false; return HVB_OK; }
+    // max over the ranks of a few doubles (periodic contexts agree on the next halo margin with this)
+    int allreduce_max(double* v, int cnt) {
+        const int world = std::max(1, prm.world);
+        if (world == 1) return HVB_OK;
+        if (!comm) { err = "a periodic search on several GPUs needs a communicator (hvb_comm_init / hvb_create_multi)"; return HVB_ENCCL; }
+        CK(xc_red.ensure(cnt)); CK(h_xc_red.ensure(cnt));
+        memcpy(h_xc_red.p, v, cnt * sizeof(double));
+        CK(cudaMemcpyAsync(xc_red.p, h_xc_red.p, cnt * sizeof(double), cudaMemcpyHostToDevice, stream));
+        NK(Nccl::get().AllReduce(xc_red.p, xc_red.p, cnt, ncclFloat64, ncclMax, comm, stream));
+        CK(cudaMemcpyAsync(h_xc_red.p, xc_red.p, cnt * sizeof(double), cudaMemcpyDeviceToHost, stream));
+        CK(cudaStreamSynchronize(stream));
+        memcpy(v, h_xc_red.p, cnt * sizeof(double));
+        return HVB_OK;
+    }
+    // counts[k] = rows rank k owns (all-gather of one word per rank; one host wait)
+    int exchange_counts(int64_t* counts) override {
+        if (!have_result) { err = "no search result"; return HVB_ESTATE; }
+        const int world = std::max(1, prm.world);
+        if (world == 1) { if (counts) counts[0] = nvert; return HVB_OK; }
+        if (!comm) { err = "no communicator: call hvb_comm_init first"; return HVB_ENCCL; }
+        CK(cudaSetDevice(prm.device));
+        CK(xc_counts.ensure(world + 1)); CK(h_xc_counts.ensure(world + 1));
+        h_xc_counts.p[world] = nvert;
+        CK(cudaMemcpyAsync(xc_counts.p + world, h_xc_counts.p + world, sizeof(long long), cudaMemcpyHostToDevice, stream));
+        NK(Nccl::get().AllGather(xc_counts.p + world, xc_counts.p, 1, ncclInt64, comm, stream));
+        CK(cudaMemcpyAsync(h_xc_counts.p, xc_counts.p, world * sizeof(long long), cudaMemcpyDeviceToHost, stream));
+        CK(cudaStreamSynchronize(stream));
+        if (counts) for (int k = 0; k < world; ++k) counts[k] = h_xc_counts.p[k];
+        return HVB_OK;
+    }
+    // Replaces this rank's owned rows by the rows of ALL ranks (parallelmesh.jl's shared store): the owned sets are
+    // disjoint and sorted, so the concatenation in rank order is the deduplicated global vertex list.  Wire format:
+    // (D + 1) int32 ids + D doubles per row, padded to the largest count, one fused NCCL group of two all-gathers.
+    int allgather() override {
+        const int world = std::max(1, prm.world);
+        if (world == 1) return have_result ? HVB_OK : (err = "no search result", HVB_ESTATE);
+        int rc = exchange_counts(nullptr); if (rc) return rc;
+        long long cap = 1, total = 0;
+        for (int k = 0; k < world; ++k) { cap = std::max(cap, h_xc_counts.p[k]); total += h_xc_counts.p[k]; }
+        if (total >= (1LL << 31)) { err = "merged vertex list beyond 2^31 rows"; return HVB_ENOMEM; }
+        CK(xs_sig32.ensure((size_t)cap * (D + 1))); CK(xs_r.ensure((size_t)cap * D));
+        CK(xr_sig32.ensure((size_t)world * cap * (D + 1))); CK(xr_r.ensure((size_t)world * cap * D));
+        if (nvert > 0) {
+            const size_t cnt = (size_t)nvert * (D + 1);
+            k_narrow_i64<<<blocks_for((int64_t)cnt, 256), 256, 0, stream>>>(out_sig[res].p, xs_sig32.p, cnt); ++launches;
+            CK(cudaMemcpyAsync(xs_r.p, out_r[res].p, (size_t)nvert * D * sizeof(double), cudaMemcpyDeviceToDevice, stream));
+        }
+        NK(Nccl::get().GroupStart());
+        NK(Nccl::get().AllGather(xs_sig32.p, xr_sig32.p, (size_t)cap * (D + 1), ncclInt32, comm, stream));
+        NK(Nccl::get().AllGather(xs_r.p, xr_r.p, (size_t)cap * D, ncclFloat64, comm, stream));
+        NK(Nccl::get().GroupEnd());
+        CK(out_sig[0].ensure((size_t)std::max<long long>(total, 1) * (D + 1))); CK(out_r[0].ensure((size_t)std::max<long long>(total, 1) * D));
+        k_unpack_segments<D><<<dim3((unsigned)blocks_for(cap, 128), (unsigned)world), 128, 0, stream>>>(xr_sig32.p, xr_r.p, world, (u32)cap, xc_counts.p,
+                                                                                                        out_sig[0].p, out_r[0].p);
+        ++launches;
+        CK(cudaStreamSynchronize(stream));
+        CK(cudaGetLastError());
+        st.exchange_bytes = (int64_t)((size_t)cap * ((D + 1) * 4 + D * 8) * (size_t)(world - 1));
+        nvert = total; res = 0; staged = false; have_result = true;
+        nb_total = -1; own_ptr = nullptr;         // the rows are global now: lists are rebuilt from them on request, for every cell
+        st.vertices = nvert; st.kernel_launches = launches;
         return HVB_OK;
     }
 

@@ -30,6 +30,10 @@ struct hvb_ctx {
     virtual int neighbor_count(int64_t* total) = 0;
     virtual int fetch_neighbors(int64_t* off, int64_t* ids) = 0;
     virtual int view_neighbors(const int64_t** off, const int64_t** ids, int64_t* total) = 0;
+    virtual int comm_init(const void* id128) = 0;
+    virtual int comm_attach(void* nccl_comm) = 0;
+    virtual int exchange_counts(int64_t* counts) = 0;
+    virtual int allgather() = 0;
     virtual int export_device(void* sig, void* r, int64_t cap, int64_t* count) = 0;
     virtual int merge_device(const void* sig, const void* r, int64_t count) = 0;
     virtual int adopt_device(const void* sig, const void* r, int64_t count) = 0;
@@ -42,3 +46,8 @@ hvb_ctx* hvb_make_ctx_3();
 hvb_ctx* hvb_make_ctx_4();
 hvb_ctx* hvb_make_ctx_5();
 hvb_ctx* hvb_make_ctx_6();
+
+// hvb_multi.cu
+hvb_ctx* hvb_make_multi(int dim, int64_t n, const double* xs, int nplanes, const double* plane_base, const double* plane_normal,
+                        const int32_t* plane_bc, const hvb_params& prm, int ngpus, const int32_t* devices, int* rc_out, std::string* err_out);
+int hvb_nccl_unique_id(void* id128, std::string* err_out);

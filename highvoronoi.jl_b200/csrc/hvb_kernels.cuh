@@ -489,7 +489,7 @@ static __global__ void k_final_rows(Dev<D> dv, const int* __restrict__ perm, u32
                              long long* __restrict__ out_sig, double* __restrict__ out_r,
                              u64* __restrict__ key_top, u64* __restrict__ key_hi, u64* __restrict__ key_lo, u32* __restrict__ out_count,
                              double* __restrict__ max_var, int own_lo, int own_hi, u32 skip_below,
-                             double variance_tol, double break_tol, u32* __restrict__ tol_counts) {
+                             double variance_tol, double break_tol, u32* __restrict__ tol_counts, int n_user) {
     u32 v = blockIdx.x * blockDim.x + threadIdx.x;
     if (v >= nrec || v < skip_below) return;          // records below skip_below are the caller's own (seed) vertices
     const int* s = dv.vsig + (size_t)v * (D + 1);
@@ -497,7 +497,13 @@ static __global__ void k_final_rows(Dev<D> dv, const int* __restrict__ perm, u32
     // multi-GPU ownership rule: a vertex belongs to the slab that holds its first generator in grid order (s is
     // sorted by internal = grid-order id); every rank finds all vertices it owns, so the owned sets are disjoint
     // and their union is the full set -- a deterministic dedup that needs no communication
-    if (own_hi > own_lo && (s[0] < own_lo || s[0] >= own_hi)) return;
+    // (periodic contexts: the first generator that is one of the CALLER's -- halo copies belong to no slab)
+    if (own_hi > own_lo) {
+        int first = -1;
+#pragma unroll
+        for (int k = D; k >= 0; --k) { const int id = s[k]; if (id < dv.n && perm[id] < n_user) first = id; }
+        if (first < own_lo || first >= own_hi) return;
+    }
     int in[D + 1];
     long long og[D + 1];
 #pragma unroll
@@ -559,25 +565,57 @@ static __global__ void k_gather_rows(const long long* __restrict__ sig_in, const
 // unbounded edges in caller numbering (pushray!, abstractmesh.jl:191; node = exploring cell = smallest id of the edge)
 template <int D>
 static __global__ void k_final_rays(Dev<D> dv, const int* __restrict__ perm, u32 nrays,
-                             long long* __restrict__ edge, double* __restrict__ base, double* __restrict__ dir, long long* __restrict__ node) {
+                             long long* __restrict__ edge, double* __restrict__ base, double* __restrict__ dir, long long* __restrict__ node,
+                             int own_lo, int own_hi, u32* __restrict__ out_count) {
     u32 i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= nrays) return;
     u32 it = dv.ray_item[i];
     u32 v = it >> 3; int kd = it & 7;
     long long e[D];
-    int c = 0;
+    int c = 0, first = 0x7fffffff;
     for (int k = 0; k < D + 1; ++k) {
         if (k == kd) continue;
         int id = dv.vsig[(size_t)v * (D + 1) + k];
+        first = min(first, id);
         e[c++] = ((id < dv.n) ? (long long)perm[id] : (long long)id) + 1;
+    }
+    // multi-GPU slabs: an unbounded edge belongs to the slab of its first generator in grid order (every rank whose
+    // slab touches the edge walks it)
+    u32 o = i;
+    if (own_hi > own_lo) {
+        if (first < own_lo || first >= own_hi) return;
+        o = atomicAdd(out_count, 1u);
     }
     for (int a = 1; a < D; ++a) { long long key = e[a]; int b = a - 1; while (b >= 0 && e[b] > key) { e[b + 1] = e[b]; --b; } e[b + 1] = key; }
     for (int k = 0; k < D; ++k) {
-        edge[(size_t)i * D + k] = e[k];
-        base[(size_t)i * D + k] = dv.vr[(size_t)v * D + k];
-        dir[(size_t)i * D + k] = dv.ray_u[(size_t)i * D + k];
+        edge[(size_t)o * D + k] = e[k];
+        base[(size_t)o * D + k] = dv.vr[(size_t)v * D + k];
+        dir[(size_t)o * D + k] = dv.ray_u[(size_t)i * D + k];
     }
-    node[i] = e[0];
+    node[o] = e[0];
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// wire format of the multi-GPU exchange and of the compact host interface: a row is (D + 1) int32 ids + D doubles
+// ------------------------------------------------------------------------------------------------------------
+static __global__ void k_narrow_i64(const long long* __restrict__ src, int* __restrict__ dst, size_t count) {
+    size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+    if (i < count) dst[i] = (int)src[i];
+}
+// gathered segments (nseg x cap rows, seg_count[k] valid rows each) -> one dense int64 / double row array
+template <int D>
+static __global__ void k_unpack_segments(const int* __restrict__ sig32, const double* __restrict__ r_in, int nseg, u32 cap,
+                                  const long long* __restrict__ seg_count, long long* __restrict__ sig_out, double* __restrict__ r_out) {
+    const u32 row = blockIdx.x * blockDim.x + threadIdx.x;
+    const int k = blockIdx.y;
+    if (row >= cap || row >= (u32)seg_count[k]) return;
+    long long at = 0;
+    for (int j = 0; j < k; ++j) at += seg_count[j];
+    const size_t src = (size_t)k * cap + row, dst = (size_t)at + row;
+#pragma unroll
+    for (int c = 0; c < D + 1; ++c) sig_out[dst * (D + 1) + c] = (long long)sig32[src * (D + 1) + c];
+#pragma unroll
+    for (int c = 0; c < D; ++c) r_out[dst * D + c] = r_in[src * D + c];
 }
 
 // ------------------------------------------------------------------------------------------------------------

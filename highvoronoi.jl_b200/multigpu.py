@@ -12,6 +12,35 @@ import torch.distributed as dist
 from . import _abi
 
 
+def init_comm(searcher, group=None):
+    """process-per-GPU mode: gives the searcher's context its NCCL communicator (hvb_comm_init).  Rank 0 draws the id
+    (hvb_comm_unique_id); torch.distributed only carries the 128 bytes -- every collective on the data path is issued
+    by the library itself."""
+    L, ctx = _abi.lib(), searcher._ctx
+    buf = ctypes.create_string_buffer(128)
+    if dist.get_rank(group) == 0:
+        _abi.check(L.hvb_comm_unique_id(buf), None)
+    box = [bytes(buf.raw)]
+    dist.broadcast_object_list(box, src=0, group=group)
+    _abi.check(L.hvb_comm_init(ctx, ctypes.create_string_buffer(box[0], 128)), ctx)
+
+
+def exchange_counts(searcher):
+    """rows owned by every rank (hvb_exchange_counts: ncclAllGather of one word inside the library)"""
+    import numpy as np
+    L, ctx = _abi.lib(), searcher._ctx
+    world = max(1, searcher.parameters.world)
+    cnt = np.zeros(world, dtype=np.int64)
+    _abi.check(L.hvb_exchange_counts(ctx, cnt.ctypes.data_as(ctypes.c_void_p)), ctx)
+    return cnt
+
+
+def allgather(searcher):
+    """replaces the rank's shard by the rows of all ranks (hvb_allgather: counts + compact rows, one fused NCCL group)"""
+    L, ctx = _abi.lib(), searcher._ctx
+    _abi.check(L.hvb_allgather(ctx), ctx)
+
+
 def slab_bounds(n, rank, world):
     """contiguous, near-equal index ranges of the spatially sorted order (partition_indices, parallelmesh.jl:52-87)"""
     return n * rank // world, n * (rank + 1) // world

@@ -30,6 +30,7 @@ extern "C" {
 #define HVB_EDEGENERATE  -5   /* a vertex with more than dim+1 cospherical generators was met (edgeiterate.jl path) */
 #define HVB_ESTATE       -6   /* call sequence error (fetch before search, ...) */
 #define HVB_EINCOMPLETE  -7   /* a descent failed: some cell has no vertex (raycast.jl:54-59 analogue) */
+#define HVB_ENCCL        -8   /* NCCL missing / a collective failed / no communicator on a multi-GPU call */
 
 #define HVB_MAX_DIM     6
 #define HVB_MAX_PLANES  32
@@ -115,6 +116,7 @@ typedef struct hvb_stats_t {
     int64_t rejected;         /* vertices dropped because the relative variance of their squared radii exceeds break_tol
                                  (walkray_correct_vertex raycast.jl:271-273, SRI_vertex_irreparable) */
     int64_t suboptimal;       /* vertices kept with a variance between variance_tol and break_tol (raycast.jl:275-277) */
+    int64_t exchange_bytes;   /* bytes this rank received in the last hvb_allgather (0 when the result stayed sharded) */
 } hvb_stats_t;
 
 /* fills *p with the reference's defaults (RaycastParameter(Float64), raycast-types.jl:312-324) */
@@ -192,7 +194,37 @@ int hvb_fetch_neighbors(hvb_ctx* ctx, int64_t* offsets, int64_t* ids);
 int hvb_view_vertices(hvb_ctx* ctx, const int64_t** sig, const double** r, int64_t* nvert);
 int hvb_view_neighbors(hvb_ctx* ctx, const int64_t** offsets, const int64_t** ids, int64_t* total);
 
-/* Multi-GPU exchange step (parallelmesh.jl's shared store becomes: local search -> all-gather -> merge).
+/* ---- Multi-GPU (replaces MultiThread(a,b): _voronoi sysvoronoi.jl:50-82, ParallelMesh / partition_indices
+ * parallelmesh.jl:52-87, getMultiThreadRaycasters raycast-types.jl:361-371) ------------------------------------------
+ * Generators and index are replicated on every GPU; GPU k explores slab k of the spatially sorted generator order and
+ * returns the vertices it OWNS (first caller generator in grid order inside the slab): owned sets are disjoint, their
+ * union is the full vertex set, so no deduplication traffic is needed.  Two ways to drive it:
+ *
+ * (1) ONE process, ONE call: hvb_create_multi builds one context per GPU (host thread per GPU, communicators from
+ *     ncclCommInitAll) behind a single hvb_ctx.  hvb_search runs the slab searches concurrently; hvb_counts,
+ *     hvb_fetch_vertices, hvb_fetch_rays, hvb_fetch_neighbors, hvb_cell_volumes, hvb_stats return the union (rows: the
+ *     shards in rank order, each shard sorted; every GPU copies its shard into the caller's buffer over its own PCIe link).
+ *     This is what the Julia shim binds for B200Thread(ngpus): the reference's model is one process
+ *     (Threads.@threads over slabs, sysvoronoi.jl:74), not one process per device.
+ *     devices == NULL: GPUs 0..ngpus-1.  params->rank / world / device are ignored.  (A device listed twice is shared by
+ *     two slabs: a way to exercise the decomposition on a one-GPU box; such a context has no communicator.)
+ * (2) one process per GPU (MPI / torchrun style): every rank creates its own context with params->rank / world / device,
+ *     rank 0 obtains an id with hvb_comm_unique_id and distributes the 128 bytes by whatever channel the host language
+ *     has, every rank calls hvb_comm_init.  After hvb_search each rank holds its shard; hvb_exchange_counts tells every
+ *     rank all shard sizes (ncclAllGather of one word); hvb_allgather replaces the shard by the rows of ALL ranks
+ *     (counts + rows in a compact wire format, (dim+1) int32 + dim doubles per row, one fused NCCL group; rank order,
+ *     each shard sorted -- identical on every rank, no dedup needed).  Periodic contexts use the communicator to agree on
+ *     the halo margin (ncclAllReduce max of the certificate's demand), so that every rank numbers the halo alike.
+ * NCCL is bound at run time (dlopen "libnccl.so.2"); without it these calls return HVB_ENCCL. */
+int hvb_create_multi(hvb_ctx** out, int dim, int64_t n, const double* xs,
+                     int nplanes, const double* plane_base, const double* plane_normal, const int32_t* plane_bc,
+                     const hvb_params* params, int ngpus, const int32_t* devices);
+int hvb_comm_unique_id(void* id128 /* out: 128 bytes */);
+int hvb_comm_init(hvb_ctx* ctx, const void* id128);
+int hvb_exchange_counts(hvb_ctx* ctx, int64_t* counts /* out: world entries */);
+int hvb_allgather(hvb_ctx* ctx);
+
+/* Exchange step with the collective issued by the HOST LANGUAGE (kept for callers that bring their own communicator).
  * hvb_export_device copies this rank's vertices (int64 sig rows of dim+1 sorted 1-based caller ids, double r rows)
  * into caller-provided DEVICE buffers of capacity `cap` rows; hvb_merge_device replaces the context's result
  * by the deduplicated, sorted union of `count` gathered rows (device pointers).  The collective itself

@@ -32,7 +32,7 @@ def test_default_params_match_reference(hvb):
     assert p.method == hvb.RCStandard == hvb.RCNonGeneralHP and p.world == 1 and p.fp32_filter == 1 and p.sort_output == 1
     assert p.persistent == 3                  # the persistent walk with warp-aggregated atomics (include/hvb200.h)
     assert ctypes.sizeof(hvb._abi.hvb_params) == 5 * 8 + 12 * 4 + 8 + 8 + 8
-    assert ctypes.sizeof(hvb._abi.hvb_stats_t) == 30 * 8
+    assert ctypes.sizeof(hvb._abi.hvb_stats_t) == 31 * 8
 
 
 def test_argument_errors(hvb):
