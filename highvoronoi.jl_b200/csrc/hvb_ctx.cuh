@@ -796,9 +796,12 @@ struct Ctx : hvb_ctx {
         st.exchange_bytes = 0;
         int64_t cap = prm.vertex_capacity > 0 ? prm.vertex_capacity
                       : (periodic ? (int64_t)(estimate_vertices(D, n_user, P) * periodic_versions()) : estimate_vertices(D, n, P));
+        const int world = std::max(1, prm.world), rank = std::min(std::max(0, prm.rank), world - 1);
+        // a slab context stores what touches its slab: 1/world of the vertices plus the layer both neighbours find too
+        // (tables are memset every search: over-sizing them by `world` is what made the replicated part of a step grow)
+        if (world > 1 && cells == nullptr && prm.vertex_capacity <= 0) cap = (int64_t)(cap * std::min(1.0, (D <= 3 ? 1.6 : 2.5) / world + 0.04)) + 4096;
         if (vcap >= cap) cap = vcap;
         int retries = 0;
-        const int world = std::max(1, prm.world), rank = std::min(std::max(0, prm.rank), world - 1);
         launches = 0;
         size_t n_ev = 0;
         int64_t rounds = 0, items = 0, expand_launches = 0;

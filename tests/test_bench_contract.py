@@ -27,6 +27,25 @@ def test_reference_arm_runs_on_the_cpu():
     assert j["cpu_baseline"]["kind"] == "port" and j["cpu_baseline"]["cores"] >= 1 and j["cpu_baseline"]["value"] == j["value"]
     assert j["e2e"] == {"value": j["value"], "unit": "vertices/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     assert "workload" in j["config"] and "model" not in j["config"]
+    assert "no julia binary" in j["cpu_baseline"]["note"]           # the probe ran and found none in this container
+
+
+def test_row_checksum_is_order_independent_and_bit_sensitive():
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("bench", os.path.join(ROOT, "bench.py"))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    import numpy as np
+    rng = np.random.default_rng(0)
+    sig = np.sort(rng.integers(1, 1000, size=(500, 4)), axis=1).astype(np.int64)
+    r = rng.random((500, 3))
+    a = bench.checksum(sig, r)
+    perm = rng.permutation(500)
+    assert bench.checksum(sig[perm], r[perm]) == a
+    r2 = r.copy(); r2[17, 1] = np.nextafter(r2[17, 1], 2.0)
+    assert bench.checksum(sig, r2) != a
+    s2 = sig.copy(); s2[3, 0] += 1
+    assert bench.checksum(s2, r) != a
 
 
 def test_reference_arm_other_ranks_exit_silently():
