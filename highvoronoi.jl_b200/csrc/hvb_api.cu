@@ -80,7 +80,7 @@ int hvb_create_multi(hvb_ctx** out, int dim, int64_t n, const double* xs, int np
     int ndev = 0;
     int rc = check_create(out, dim, n, xs, nplanes, plane_base, plane_normal, params, prm, &ndev);
     if (rc != HVB_OK) return rc;
-    if (ngpus < 1 || ngpus > ndev || ngpus > 64) { g_create_error = "ngpus must be between 1 and the number of visible CUDA devices"; return HVB_EINVAL; }
+    if (ngpus < 1 || ngpus > 64 || (!devices && ngpus > ndev)) { g_create_error = "ngpus must be between 1 and the number of visible CUDA devices"; return HVB_EINVAL; }
     for (int k = 0; devices && k < ngpus; ++k) {
         if (devices[k] < 0 || devices[k] >= ndev) { g_create_error = "bad device ordinal"; return HVB_EINVAL; }
     }

@@ -332,7 +332,7 @@ struct Ctx : hvb_ctx {
     // bounding box + domain check (check_boundary, boundary.jl:437) of `cnt` points against the planes on the device;
     // the box lands in h_sc.p->bbox.  `host_xs` (may be null) is only used to word the error message.
     int check_points(const double* dev_xs, int64_t cnt, const double* host_xs) {
-        const int bb_blocks = std::min(blocks_for(cnt, 256), sms);
+        const int bb_blocks = std::min(blocks_for(cnt, 256), sms * 8);
         CK(bbox_partial.ensure((size_t)bb_blocks * 2 * D));
         CK(cudaMemsetAsync(&sc.p->bbox_done, 0, sizeof(u32), stream));
         CK(cudaMemsetAsync(&sc.p->bbox_viol, 0xff, sizeof(u32), stream));
@@ -455,8 +455,8 @@ struct Ctx : hvb_ctx {
         CK(cub::DeviceScan::ExclusiveSum(cub_tmp.p, tmp_bytes, cell_cur.p, cell_start.p, (int)(ncells + 1), stream));
         CK(cudaMemsetAsync(cell_cur.p, 0, (size_t)(ncells + 1) * sizeof(int), stream));
         k_scatter<D><<<blocks_for(n, 256), 256, 0, stream>>>(dv, xs_in.p, cell_of.p, cell_start.p, cell_cur.p, x64.p, x32.p, perm.p); ++launches;
-        k_cell_sort<D><<<blocks_for(ncells, 256), 256, 0, stream>>>(dv, xs_in.p, cell_start.p, (int)ncells, x64.p, x32.p, perm.p); ++launches;
-        k_inverse_perm<<<blocks_for(n, 256), 256, 0, stream>>>(perm.p, inv.p, (int)n); ++launches;
+        k_cell_sort<<<blocks_for(ncells, 256), 256, 0, stream>>>(cell_start.p, (int)ncells, perm.p); ++launches;
+        k_gather_points<D><<<blocks_for(n, 256), 256, 0, stream>>>(dv, xs_in.p, perm.p, x64.p, x32.p, inv.p); ++launches;
         CK(cudaEventRecord(ev_b, stream));
         CK(cudaStreamSynchronize(stream));
         CK(cudaGetLastError());
@@ -1133,7 +1133,9 @@ struct Ctx : hvb_ctx {
         // unordered pairs: a list entry of an interior cell is stored once for two cells, so about n * nb_est / 2 pairs;
         // slots = 2 x that estimate (the estimate itself is ~1.3 x the Poisson-Voronoi mean): load <= 0.4, and the
         // memset + the fill pass touch a quarter of what an entry-per-list-element table would need
-        nb_want = next_pow2((u64)std::min(nrows * D * (D + 1) / 2.0 * 2.0, (double)n_list * nb_est[D]) + 1024);
+        // (slab contexts build the lists of their own cells only: 1/world of the cells plus the pairs that cross the slab faces)
+        const double own_frac = own_ptr ? std::min(1.0, 1.5 / std::max(1, prm.world) + 0.02) : 1.0;
+        nb_want = next_pow2((u64)std::min(nrows * D * (D + 1) / 2.0 * 2.0, (double)n_list * own_frac * nb_est[D]) + 1024);
         size_t tmp_bytes = 0;
         CK(cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, nb_off.p, nb_off.p, (int)(n + 1), stream));
         CK(nb_cub_tmp.ensure(tmp_bytes));

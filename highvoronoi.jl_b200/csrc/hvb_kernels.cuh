@@ -87,11 +87,13 @@ static __global__ void k_bbox_check(const double* __restrict__ xs, int n, const 
         last = (atomicAdd(done, 1u) == gridDim.x - 1);
     }
     __syncthreads();
-    if (last && threadIdx.x == 0) {
+    if (last) {
+        // the last block folds the per-block partials with all its threads (a serial loop of one thread over ~1000 partials
+        // was the longest part of this kernel)
         double r[2 * D];
 #pragma unroll
         for (int k = 0; k < D; ++k) { r[k] = 1e300; r[D + k] = -1e300; }
-        for (unsigned int b = 0; b < gridDim.x; ++b) {
+        for (unsigned int b = threadIdx.x; b < gridDim.x; b += blockDim.x) {
 #pragma unroll
             for (int k = 0; k < D; ++k) {
                 r[k] = fmin(r[k], __ldcg(partial + (size_t)b * 2 * D + k));
@@ -99,7 +101,28 @@ static __global__ void k_bbox_check(const double* __restrict__ xs, int n, const 
             }
         }
 #pragma unroll
-        for (int k = 0; k < 2 * D; ++k) out[k] = r[k];
+        for (int m = 16; m >= 1; m >>= 1) {
+#pragma unroll
+            for (int k = 0; k < D; ++k) {
+                r[k] = fmin(r[k], __shfl_xor_sync(0xffffffffu, r[k], m));
+                r[D + k] = fmax(r[D + k], __shfl_xor_sync(0xffffffffu, r[D + k], m));
+            }
+        }
+        __syncthreads();
+        if ((threadIdx.x & 31) == 0) {
+#pragma unroll
+            for (int k = 0; k < 2 * D; ++k) sm[w][k] = r[k];
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            const int nw = blockDim.x >> 5;
+            for (int j = 1; j < nw; ++j) {
+#pragma unroll
+                for (int k = 0; k < D; ++k) { sm[0][k] = fmin(sm[0][k], sm[j][k]); sm[0][D + k] = fmax(sm[0][D + k], sm[j][D + k]); }
+            }
+#pragma unroll
+            for (int k = 0; k < 2 * D; ++k) out[k] = sm[0][k];
+        }
     }
 }
 
@@ -127,9 +150,7 @@ static __global__ void k_scatter(Dev<D> dv, const double* __restrict__ xs, const
 }
 
 // deterministic order inside a cell: sort each cell's entries by caller id (cells hold a handful of points)
-template <int D>
-static __global__ void k_cell_sort(Dev<D> dv, const double* __restrict__ xs, const int* __restrict__ cell_start, int ncells,
-                            double* __restrict__ x64, float* __restrict__ x32, int* __restrict__ perm) {
+static __global__ void k_cell_sort(const int* __restrict__ cell_start, int ncells, int* __restrict__ perm) {
     int c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= ncells) return;
     int a = cell_start[c], b = cell_start[c + 1];
@@ -139,14 +160,21 @@ static __global__ void k_cell_sort(Dev<D> dv, const double* __restrict__ xs, con
         while (j >= a && perm[j] > key) { perm[j + 1] = perm[j]; --j; }
         perm[j + 1] = key;
     }
-    for (int i = a; i < b; ++i) {
-        int o = perm[i];
+}
+// coordinates in grid order (FP64 for verification, FP32 minus the grid origin for the filter) and the inverse
+// permutation; one thread per sorted position: the writes are coalesced
+template <int D>
+static __global__ void k_gather_points(Dev<D> dv, const double* __restrict__ xs, const int* __restrict__ perm,
+                                double* __restrict__ x64, float* __restrict__ x32, int* __restrict__ inv) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= dv.n) return;
+    const int o = perm[i];
+    inv[o] = i;
 #pragma unroll
-        for (int k = 0; k < X32<D>::STRIDE; ++k) {
-            double v = (k < D) ? xs[(size_t)o * D + (k < D ? k : 0)] : 0.0;
-            if (k < D) x64[(size_t)i * D + k] = v;
-            x32[(size_t)i * X32<D>::STRIDE + k] = (k < D) ? (float)(v - dv.lo[k < D ? k : 0]) : 0.f;
-        }
+    for (int k = 0; k < X32<D>::STRIDE; ++k) {
+        double v = (k < D) ? xs[(size_t)o * D + (k < D ? k : 0)] : 0.0;
+        if (k < D) x64[(size_t)i * D + k] = v;
+        x32[(size_t)i * X32<D>::STRIDE + k] = (k < D) ? (float)(v - dv.lo[k < D ? k : 0]) : 0.f;
     }
 }
 
