@@ -19,6 +19,7 @@ template <int D>
 struct CoopCfg {
     static const int TA = (D <= 3) ? D - 1 : D - 2;   // leading axes enumerated by the task index (d >= 4: a task loops over axis D-2)
     static const int CAP = 16;                        // survivor list entries per ray and stage
+    static const int MAXT = 384;                      // chunk tasks (of <= 4 points) a round can hold; the rest is scanned by the emitting lane
 };
 
 template <int D>
@@ -34,6 +35,9 @@ struct __align__(16) CoopShared {      // one warp's 32 rays, structure of array
     int ntask[32];                     // row tasks of the ray's current stage (0: none)
     int nexttask[32];                  // next task of the ray (atomicAdd; >= ntask: exhausted)
     int cnt[32];                       // survivors appended (may exceed CAP: overflow)
+    // ---- the statically scheduled pool (pool_scan) ----
+    int rbase[32], rcnt[32];           // this round's offer of the ray: first row task, number of row tasks
+    unsigned chunk[CoopCfg<D>::MAXT];  // chunk tasks of the round: {owner : 5, points - 1 : 2, first point : 25}
 };
 
 // point range of the row (leading cell coordinates folded into base / d2 / umax / uabs) along the last axis:
@@ -205,8 +209,191 @@ __device__ __forceinline__ void coop_scan(const Dev<D>& dv, CoopShared<D>& sh, L
     }
 }
 
-// The min-t query of up to 32 rays of a warp (lane l owns ray q iff has_ray).  Every lane of the warp must call.
+// ------------------------------------------------------------------------------------------------------------
+// pool_scan: the same stage scan with STATIC scheduling.  coop_scan hands out whole rows through shared-memory tickets:
+// the rows of a warp's rays differ in length, so its lanes diverge again inside the rows, and the ticket traffic costs
+// more than the row geometry it distributes.  Here nothing is fetched dynamically:
+//   round:  every ray that still has row tasks offers its next Kr of them (Kr a power of two chosen so that the offers
+//           of all active rays fill one or two warp steps);
+//   rows:   slot s of the round belongs to (s / Kr)-th active ray, task s % Kr: the lanes run the row geometry for the
+//           slots, whoever the ray belongs to, and turn every point range into chunk tasks of <= 4 points
+//           (a warp prefix sum places them in the round's task array);
+//   chunks: the lanes run the FP32 filter over the chunk tasks, 32 chunks per step, all lanes on the same instruction;
+//           survivors tighten the ray's bound (atomicMin in shared memory) and are appended to the ray's list.
+// The next round's rows see the tightened bounds, as the rows of the one-lane query do (in-flight shrink of the ball).
+// ------------------------------------------------------------------------------------------------------------
+#ifndef HVB_POOL_SLOTS
+#define HVB_POOL_SLOTS 64          // row slots a round aims at (d <= 3); d >= 4 uses half: its tasks loop over axis D-2
+#endif
 template <int D>
+__device__ __forceinline__ void pool_eval_chunk(const Dev<D>& dv, CoopShared<D>& sh, int o, int p0, int cnt) {
+    const int CAP = CoopCfg<D>::CAP;
+    const int U = 4;
+    float uf[D], w2f[D], x0f[D];
+#pragma unroll
+    for (int k = 0; k < D; ++k) { uf[k] = sh.uf[k][o]; w2f[k] = sh.w2f[k][o]; x0f[k] = sh.x0f[k][o]; }
+    const float en = sh.en[o], ed = sh.ed[o];
+    float x[U][D];
+#pragma unroll
+    for (int i = 0; i < U; ++i) load_x32<D>(dv.x32, p0 + (i < cnt ? i : cnt - 1), x[i]);
+    float tb2 = __uint_as_float(*(volatile unsigned*)&sh.tb2[o]);
+    float nm[U], den[U];
+    unsigned pmask = 0;
+#pragma unroll
+    for (int i = 0; i < U; ++i) {
+        float d_ = 0.f, n_ = 0.f;
+#pragma unroll
+        for (int k = 0; k < D; ++k) {
+            const float qk = x[i][k] - x0f[k];
+            d_ = fmaf(uf[k], qk, d_);
+            n_ = fmaf(qk, qk - w2f[k], n_);
+        }
+        nm[i] = n_; den[i] = d_;
+        const bool pass = (i < cnt) && (d_ + ed > 0.f) && (n_ - en <= tb2 * (d_ + ed));
+        pmask |= pass ? (1u << i) : 0u;
+    }
+    while (pmask) {
+        const int i = __ffs((int)pmask) - 1;
+        pmask &= pmask - 1u;
+        float nm_i = nm[0], den_i = den[0];
+#pragma unroll
+        for (int b = 1; b < U; ++b) { nm_i = (i == b) ? nm[b] : nm_i; den_i = (i == b) ? den[b] : den_i; }
+        const int id = p0 + i;
+        bool excluded = false;
+#pragma unroll
+        for (int e = 0; e < D + 1; ++e) excluded |= (sh.excl[e][o] == id);
+        if (excluded) continue;
+        const float nlo = nm_i - en, nhi = nm_i + en, dh = den_i + ed, dl = den_i - ed;
+        // an FP32 upper bound exists when the denominator is safely positive and t is safely > 0: such a
+        // candidate is valid in FP64 as well (u.x > c, den > 0, t >= plane_tol)
+        const bool bounded = sh.tighten[o] && dl > ed && nlo > 0.f;
+        float lo = 0.f;
+        if (bounded) {
+            lo = nlo / dh; lo -= fabsf(lo) * 4e-7f;
+            const float hi = nhi / dl * 1.000001f;
+            tb2 = __uint_as_float(*(volatile unsigned*)&sh.tb2[o]);
+            if (!(lo <= tb2)) continue;                                      // the bound tightened meanwhile
+            if (hi < tb2) atomicMin(&sh.tb2[o], __float_as_uint(hi));
+        }
+        const int pos = atomicAdd(&sh.cnt[o], 1);
+        if (pos < CAP) sh.surv[o][pos] = ((u64)__float_as_uint(lo) << 32) | (bounded ? 0x80000000ULL : 0ULL) | (u64)(u32)id;
+    }
+}
+
+template <int D>
+__device__ __forceinline__ void pool_scan(const Dev<D>& dv, CoopShared<D>& sh, LocalStats& ls) {
+    const unsigned FULL = 0xffffffffu;
+    const int lane = threadIdx.x & 31;
+    const int TA = CoopCfg<D>::TA, MAXT = CoopCfg<D>::MAXT;
+    const int mytasks = sh.ntask[lane];
+    int done = 0;                                   // row tasks of MY ray handed out so far
+    for (;;) {
+        const unsigned amask = __ballot_sync(FULL, done < mytasks);
+        if (!amask) break;
+        const int nact = __popc(amask);
+        // row tasks per ray and round: a power of two, so that the slots decode with shifts
+        const int want = ((D <= 3) ? HVB_POOL_SLOTS : HVB_POOL_SLOTS / 2) / nact;
+        int ke = 0;
+        while ((2 << ke) <= want && ke < 4) ++ke;
+        const int Kr = 1 << ke;
+        const int left = mytasks - done;
+        const int k = left > Kr ? Kr : (left > 0 ? left : 0);
+        sh.rbase[lane] = done; sh.rcnt[lane] = k;
+        done += k;
+        __syncwarp();
+        const int nslots = nact << ke;
+        int total = 0;                              // chunk tasks emitted in this round (warp-uniform)
+        for (int s0 = 0; s0 < nslots; s0 += 32) {
+            const int s = s0 + lane;
+            bool valid = s < nslots;
+            int o = 0, idx = 0;
+            if (valid) {
+                o = __fns(amask, 0, (s >> ke) + 1);           // lane of the (s >> ke)-th active ray
+                idx = s & (Kr - 1);
+                valid = idx < sh.rcnt[o];
+            }
+            // ---- row geometry of task (o, rbase + idx) ------------------------------------------------------
+            int c2 = 1, c2hi = 0, base_p = 0, pa = 0, pb = 0;
+            float d2_p = 0.f, umax_p = 0.f, uabs_p = 0.f, Ts = 0.f, rho2 = 0.f, m = 0.f;
+            bool have = false;
+            if (valid) {
+                int rem = sh.rbase[o] + idx;
+                // the ray's current ball: the bound may have tightened since the stage was set up
+                const float tb2 = __uint_as_float(*(volatile unsigned*)&sh.tb2[o]);
+                Ts = fminf(sh.ts0[o], 0.5f * tb2 * 1.000001f);
+                const float a = sh.a32[o];
+                const float dT = fabsf(Ts - a) + 4e-7f * (fabsf(a) + Ts);
+                rho2 = fmaf(dT, dT, sh.perp2[o]) * 1.00001f;
+                m = sh.m[o];
+                int cc[TA];
+#pragma unroll
+                for (int kk = TA - 1; kk >= 0; --kk) {
+                    const int e = sh.ext[kk][o];
+                    const int qd = (int)(((float)rem + 0.5f) * sh.re[kk][o]);     // rem / e without an integer division (rem < 2^22)
+                    cc[kk] = sh.clo[kk][o] + (rem - qd * e);
+                    rem = qd;
+                }
+                float d2 = 0.f, umax = 0.f, uabs = 0.f; int base = 0;
+#pragma unroll
+                for (int kk = 0; kk < TA; ++kk) coop_axis<D>(dv, sh, o, kk, cc[kk], Ts, m, d2, umax, uabs, base);
+                if (D <= 3) have = coop_zrange<D>(dv, sh, o, Ts, rho2, m, d2, umax, uabs, base, pa, pb);
+                else if (d2 <= rho2) {
+                    // cells of axis D-2 the ball's slice reaches, inside the stage's box
+                    const int A = D - 2;
+                    const float sq = sqrtf(rho2 - d2) * 1.000001f + m;
+                    const float cenA = fmaf(Ts, sh.uf[A][o], sh.r32[A][o]);
+                    const float iha = dv.inv_h32[A];
+                    const int blo = sh.clo[A][o], bhi = blo + sh.ext[A][o] - 1;
+                    const float vlo = fminf(fmaxf((cenA - sq) * iha - 2e-3f, (float)blo), (float)bhi);
+                    const float vhi = fminf(fmaxf((cenA + sq) * iha + 2e-3f, (float)blo - 1.f), (float)bhi);
+                    c2 = (int)floorf(vlo); c2hi = (int)floorf(vhi);
+                    d2_p = d2; umax_p = umax; uabs_p = uabs; base_p = base;
+                }
+            }
+            // ---- rows -> chunk tasks: d <= 3 one row per slot; d >= 4 the rows of the task along axis D-2 ------------
+            int span = (D <= 3) ? 1 : ((valid && c2hi >= c2) ? c2hi - c2 + 1 : 0);
+            if (D >= 4) {
+#pragma unroll
+                for (int mm = 16; mm >= 1; mm >>= 1) span = max(span, __shfl_xor_sync(FULL, span, mm));
+            }
+            for (int j = 0; j < span; ++j) {
+                if (D >= 4) {
+                    have = false;
+                    if (valid && c2 + j <= c2hi) {
+                        float d2 = d2_p, umax = umax_p, uabs = uabs_p; int base = base_p;
+                        coop_axis<D>(dv, sh, o, D - 2, c2 + j, Ts, m, d2, umax, uabs, base);
+                        have = coop_zrange<D>(dv, sh, o, Ts, rho2, m, d2, umax, uabs, base, pa, pb);
+                    }
+                }
+                const int len = (have && pb > pa) ? pb - pa : 0;
+                if (len) { ls.rows++; ls.cand32 += (u32)len; }
+                const int nch = (len + 3) >> 2;
+                int incl = nch;
+#pragma unroll
+                for (int dd = 1; dd < 32; dd <<= 1) { const int t_ = __shfl_up_sync(FULL, incl, dd); if (lane >= dd) incl += t_; }
+                int pos = total + incl - nch;
+                total += __shfl_sync(FULL, incl, 31);
+                for (int c = 0; c < nch; ++c, ++pos) {
+                    const int p = pa + 4 * c;
+                    const int cn = (pb - p < 4) ? pb - p : 4;
+                    if (pos < MAXT && p < (1 << 25)) sh.chunk[pos] = ((unsigned)o << 27) | ((unsigned)(cn - 1) << 25) | (unsigned)p;
+                    else pool_eval_chunk<D>(dv, sh, o, p, cn);            // no room in the round's array: scanned at once
+                }
+            }
+        }
+        __syncwarp();
+        // ---- chunks: 32 per step, every lane on the same instruction ---------------------------------------------
+        const int M = total < MAXT ? total : MAXT;
+        for (int c = lane; c < M; c += 32) {
+            const unsigned t_ = sh.chunk[c];
+            pool_eval_chunk<D>(dv, sh, (int)(t_ >> 27), (int)(t_ & 0x1ffffffu), (int)((t_ >> 25) & 3u) + 1);
+        }
+        __syncwarp();
+    }
+}
+
+// The min-t query of up to 32 rays of a warp (lane l owns ray q iff has_ray).  Every lane of the warp must call.
+template <int D, bool POOL>
 __device__ __forceinline__ Best coop_min_t(const Dev<D>& dv, CoopShared<D>& sh, const RayQ<D>& q, bool has_ray, LocalStats& ls) {
     const unsigned FULL = 0xffffffffu;
     const int lane = threadIdx.x & 31;
@@ -291,7 +478,7 @@ __device__ __forceinline__ Best coop_min_t(const Dev<D>& dv, CoopShared<D>& sh, 
         sh.ntask[lane] = ntask;
         sh.nexttask[lane] = 0;
         __syncwarp();
-        if (__any_sync(FULL, ntask > 0)) coop_scan<D>(dv, sh, ls);
+        if (__any_sync(FULL, ntask > 0)) { if (POOL) pool_scan<D>(dv, sh, ls); else coop_scan<D>(dv, sh, ls); }
         __syncwarp();
         // ---- settle: FP64 evaluation of everything that can be the winner or tie with it ------------------------
         if (active) {
@@ -465,7 +652,9 @@ __device__ __forceinline__ void commit_vertex_warp(const Dev<D>& dv, bool has, c
 #ifndef HVB_COOP_COMMIT
 #define HVB_COOP_COMMIT 1         // 1: warp-aggregated commit (commit_vertex_warp), 0: the lane-per-ray commit_vertex
 #endif
-template <int D, bool COOPQ>
+// QMODE 0: every lane runs the one-lane query of its own ray; 1: pooled query with dynamic row tickets (coop_scan);
+// 2: pooled query with static scheduling (pool_scan)
+template <int D, int QMODE>
 static __global__ void __launch_bounds__(128, HVB_COOP_MINB) k_walk_coop(Dev<D> dv, WalkQueue wq) {
     extern __shared__ __align__(16) unsigned char hvb_smem_raw[];
     CoopShared<D>& sh = reinterpret_cast<CoopShared<D>*>(hvb_smem_raw)[threadIdx.x >> 5];
@@ -523,7 +712,8 @@ static __global__ void __launch_bounds__(128, HVB_COOP_MINB) k_walk_coop(Dev<D> 
             // COOPQ: the pooled query; else every lane runs the one-lane query for its own ray (only the acquisition
             // and the commit are warp-aggregated)
             Best best;
-            if (COOPQ) best = coop_min_t<D>(dv, sh, q, ok, ls);
+            if (QMODE == 2) best = coop_min_t<D, true>(dv, sh, q, ok, ls);
+            else if (QMODE == 1) best = coop_min_t<D, false>(dv, sh, q, ok, ls);
             else { best.t = INFINITY; best.id = -1; best.t2 = INFINITY; best.tw = 0.0; if (ok) best = min_t_query<D, TileDev<1> >(dv, tile, q, ls); }
 #if HVB_COOP_COMMIT
             int sig2[D + 1];

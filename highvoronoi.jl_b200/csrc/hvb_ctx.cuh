@@ -224,7 +224,7 @@ struct Ctx : hvb_ctx {
         if (ev_nb) cudaEventDestroy(ev_nb);
         nbsc.release(); h_nbsc.release(); h_nbtotal.release(); own_mask.release();
         if (comm && comm_owned) Nccl::get().CommDestroy(comm);
-        xc_counts.release(); h_xc_counts.release(); xs_sig32.release(); xr_sig32.release(); xs_r.release(); xr_r.release(); xc_red.release(); h_xc_red.release();
+        xc_counts.release(); h_xc_counts.release(); xc_counts32.release(); h_xc_counts32.release(); xs_sig32.release(); xr_sig32.release(); xs_r.release(); xr_r.release(); xc_red.release(); h_xc_red.release();
         if (nstream) { cudaStreamSynchronize(nstream); cudaStreamDestroy(nstream); }
         if (sstream2) { cudaStreamSynchronize(sstream2); cudaStreamDestroy(sstream2); }
         if (ev_p0) cudaEventDestroy(ev_p0);
@@ -323,6 +323,7 @@ struct Ctx : hvb_ctx {
         dv.fp32_filter = prm.fp32_filter;
         if (prm.tile_size == 1 || prm.tile_size == 2 || prm.tile_size == 4 || prm.tile_size == 8 || prm.tile_size == 16 || prm.tile_size == 32) G = prm.tile_size;
         debug = getenv("HVB_DEBUG") != nullptr;
+        if (const char* e = getenv("HVB_PERSISTENT")) prm.persistent = atoi(e);      // tuning / test runs: force a walk variant
         persistent = prm.persistent != 0;
         coop = prm.persistent >= 2;
         setup_done = true;
@@ -490,7 +491,7 @@ struct Ctx : hvb_ctx {
         k_walk<D, GG><<<std::max(1, per_sm) * sms, 128, 0, stream>>>(dv, wq);
         return HVB_OK;
     }
-    template <bool COOPQ>
+    template <int COOPQ>
     int launch_walk_coop(const WalkQueue& wq) {
         const size_t smem = COOPQ ? 4 * sizeof(CoopShared<D>) : 16;
         CK(cudaFuncSetAttribute(k_walk_coop<D, COOPQ>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -501,7 +502,7 @@ struct Ctx : hvb_ctx {
         return HVB_OK;
     }
     int launch_walk(const WalkQueue& wq) {
-        if (coop && G == 1) return prm.persistent == 3 ? launch_walk_coop<false>(wq) : launch_walk_coop<true>(wq);
+        if (coop && G == 1) return prm.persistent == 3 ? launch_walk_coop<0>(wq) : (prm.persistent == 4 ? launch_walk_coop<2>(wq) : launch_walk_coop<1>(wq));
         switch (G) {
             case 1: return launch_walk_g<1>(wq);
             case 2: return launch_walk_g<2>(wq);
@@ -1043,6 +1044,16 @@ struct Ctx : hvb_ctx {
                                                                      lo, hi, &sc.p->ray_out);
             ++launches;
         }
+        // multi-GPU with a communicator: the shard sizes of all ranks travel now (ncclAllGather of one word, straight from
+        // the device counter) and are in host memory when this search returns: hvb_exchange_counts costs nothing
+        counts_cached = false;
+        if (by_slab && comm) {
+            const int world = std::max(1, prm.world);
+            CK(xc_counts32.ensure(world)); CK(h_xc_counts32.ensure(world));
+            NK(Nccl::get().AllGather(&sc.p->out_count, xc_counts32.p, 1, ncclUint32, comm, stream));
+            CK(cudaMemcpyAsync(h_xc_counts32.p, xc_counts32.p, world * sizeof(u32), cudaMemcpyDeviceToHost, stream));
+            counts_cached = true;
+        }
         int rc = read_scalars(); if (rc) return rc;
         nvert = h_sc.p->out_count;
         if (by_slab) nrays = h_sc.p->ray_out;
@@ -1237,6 +1248,9 @@ struct Ctx : hvb_ctx {
     bool comm_owned = false;
     DBuf<long long> xc_counts;
     HBuf<long long> h_xc_counts;
+    DBuf<u32> xc_counts32;
+    HBuf<u32> h_xc_counts32;
+    bool counts_cached = false;       // h_xc_counts32 holds the shard sizes of the current result (filled inside hvb_search)
     DBuf<int> xs_sig32, xr_sig32;
     DBuf<double> xs_r, xr_r, xc_red;
     HBuf<double> h_xc_red;
@@ -1281,6 +1295,13 @@ struct Ctx : hvb_ctx {
         if (!comm) { err = "no communicator: call hvb_comm_init first"; return HVB_ENCCL; }
         CK(cudaSetDevice(prm.device));
         CK(xc_counts.ensure(world + 1)); CK(h_xc_counts.ensure(world + 1));
+        if (counts_cached) {
+            // gathered inside hvb_search, next to the row sort; the device copy the unpack kernel reads is refreshed
+            for (int k = 0; k < world; ++k) h_xc_counts.p[k] = (long long)h_xc_counts32.p[k];
+            CK(cudaMemcpyAsync(xc_counts.p, h_xc_counts.p, world * sizeof(long long), cudaMemcpyHostToDevice, stream));
+            if (counts) for (int k = 0; k < world; ++k) counts[k] = h_xc_counts.p[k];
+            return HVB_OK;
+        }
         h_xc_counts.p[world] = nvert;
         CK(cudaMemcpyAsync(xc_counts.p + world, h_xc_counts.p + world, sizeof(long long), cudaMemcpyHostToDevice, stream));
         NK(Nccl::get().AllGather(xc_counts.p + world, xc_counts.p, 1, ncclInt64, comm, stream));
@@ -1317,9 +1338,23 @@ struct Ctx : hvb_ctx {
         CK(cudaStreamSynchronize(stream));
         CK(cudaGetLastError());
         st.exchange_bytes = (int64_t)((size_t)cap * ((D + 1) * 4 + D * 8) * (size_t)(world - 1));
-        nvert = total; res = 0; staged = false; have_result = true;
+        nvert = total; res = 0; staged = false; have_result = true; counts_cached = false;
         nb_total = -1; own_ptr = nullptr;         // the rows are global now: lists are rebuilt from them on request, for every cell
         st.vertices = nvert; st.kernel_launches = launches;
+        if (periodic) {
+            // the flags of the canonical images are a function of the rows: recomputed for the merged list
+            CK(vflags.ensure(std::max<int64_t>(nvert, 1)));
+            CK(cudaMemsetAsync(cert.p, 0, sizeof(CertOut), stream));
+            if (nvert > 0) {
+                k_certify<D><<<blocks_for(nvert, 128), 128, 0, stream>>>(out_sig[res].p, out_r[res].p, (u32)nvert, (long long)n_user, (long long)n,
+                                                                        xs_in.p, halo_origin.p, planes.p, pcert, vflags.p, cert.p);
+                ++launches;
+            }
+            k_publish<<<1, 64, 0, stream>>>((const u32*)cert.p, (u32*)h_cert.p, (int)(sizeof(CertOut) / 4), nullptr, nullptr, 0, nullptr, nullptr);
+            CK(cudaStreamSynchronize(stream));
+            st.unique_vertices = h_cert.p->canonical;
+            have_flags = true;
+        }
         return HVB_OK;
     }
 

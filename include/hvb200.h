@@ -74,7 +74,11 @@ typedef struct hvb_params {
     int32_t persistent;       /* the frontier walk.  3 (default): one persistent launch with a device-side queue; a warp takes
                                  its tickets, vertex indices and queue slots with ONE atomic each, every lane runs the
                                  min-t query of its own ray (tile_size 1 only);
-                                 2: the same launch with the warp-cooperative (pooled) query: correct, measured slower;
+                                 2: the same launch with the warp-cooperative (pooled) query, rows handed out through
+                                    shared-memory tickets: correct, measured slower;
+                                 4: the pooled query with static scheduling: per round the lanes of a warp run the row
+                                    geometry of all its rays' next rows, then the FP32 filter over the resulting chunks of
+                                    4 points, 32 chunks per step (hvb_coop.cuh, pool_scan);
                                  1: the persistent launch with one tile per ray from start to end (any tile_size);
                                  0: one launch per frontier round */
     int64_t vertex_capacity;  /* 0 = estimate from lowerbound(d,d) (edgeiteratebase.jl:151); grows on demand */

@@ -139,13 +139,13 @@ def test_capacity_retry_path(hvb, oracle):
     xs = points(3000, 3, 12)
     base, normal = qhull_oracle.cuboid(3)
     o = oracle.run(xs, base, normal)
-    for persistent in (3, 2, 1, 0):
+    for persistent in (4, 3, 2, 1, 0):
         mesh, s = run_gpu(hvb, xs, True, vertex_capacity=700, persistent=persistent)
         assert np.array_equal(mesh.sig, o["sig"])
         assert s.stats()["capacity_retries"] >= 3
 
 
-@pytest.mark.parametrize("persistent", [0, 1, 2, 3])
+@pytest.mark.parametrize("persistent", [0, 1, 2, 3, 4])
 @pytest.mark.parametrize("tile", [1, 2, 4, 8, 16, 32])
 def test_every_tile_size_and_both_walk_modes(hvb, oracle, tile, persistent):
     xs = points(4000, 3, 13)

@@ -20,7 +20,7 @@ def run_periodic(hvb, xs, axes, **settings):
 
 
 @pytest.mark.parametrize("d,n,axes", [(2, 2000, (1, 2)), (2, 1500, (2,)), (3, 800, (1, 2, 3)), (3, 800, (1, 3)), (4, 600, (1, 2, 3, 4)),
-                                      (5, 400, (1, 2)), (6, 200, (3,)), (6, 2000, (1,))])
+                                      (5, 400, (1, 2)), (5, 1500, (2, 5)), (6, 2000, (1,))])
 def test_periodic_matches_oracle_on_the_halo_problem(hvb, oracle, d, n, axes):
     xs = points(n, d, 300 + d)
     mesh, s = run_periodic(hvb, xs, axes)
