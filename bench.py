@@ -50,6 +50,7 @@ WORKLOADS = {  # name -> (points per GPU, dim)
     "C5": (20000, 6), "C5s": (4000, 6), "P3": (100000, 3), "P2": (1000000, 2),
 }
 PERIODIC = {"C5", "C5s", "P3", "P2"}
+DEFAULT_PERSISTENT = 3          # hvb_default_params: the walk variant behind persistent (include/hvb200.h)
 STRONG = {"C3"}                 # N > 1: the total stays fixed (BASELINE.json configs[2] names 1 000 000 points over all GPUs)
 
 
@@ -226,7 +227,9 @@ class Runner:
     def searcher(self, xs):
         hvb = self.hvb
         if self.s is None:                               # the context (device + page-locked buffers) is re-used
-            opts = hvb.RaycastParameter(threading=hvb.B200Thread(self.env["local_rank"], self.rank, self.world), neighbors=1, **self.settings)
+            kw = dict(neighbors=1, wire32=1)             # ids cross PCIe as int32 (hvb_view_vertices32 / hvb_view_neighbors32)
+            kw.update(self.settings)
+            opts = hvb.RaycastParameter(threading=hvb.B200Thread(self.env["local_rank"], self.rank, self.world), **kw)
             self.s = hvb.Raycast(xs, domain=self.dom, options=opts, periodic=self.periodic)
             if self.world > 1:
                 from hvb200 import multigpu
@@ -281,8 +284,8 @@ class Runner:
             sig_h, r_h = sig_h[:mine], r_h[:mine]
             t1c = time.perf_counter()
             po, pi, tot = ctypes.c_void_p(), ctypes.c_void_p(), ctypes.c_int64()
-            abi.check(L.hvb_view_neighbors(s._ctx, ctypes.byref(po), ctypes.byref(pi), ctypes.byref(tot)), s._ctx)
-            nb_bytes = (self.n_total + 1) * 8 + int(tot.value) * 8
+            abi.check(L.hvb_view_neighbors32(s._ctx, ctypes.byref(po), ctypes.byref(pi), ctypes.byref(tot)), s._ctx)
+            nb_bytes = (self.n_total + 1) * 8 + int(tot.value) * 4
         torch.cuda.synchronize()
         t2 = time.perf_counter()
         if timed:
@@ -313,12 +316,14 @@ class Runner:
         bytes_per_launch = B_ALG[d] * (v_rank * steps) / max(kern_launches, 1)
         avg_launch_s = kern_ms * 1e-3 / max(kern_launches, 1)
         achieved = bytes_per_launch / avg_launch_s / 1e9
-        kname = {0: "k_expand<%d>", 1: "k_walk<%d>", 2: "k_walk_coop<%d,pooled query>", 3: "k_walk_coop<%d>"}[self.settings.get("persistent", 3)] % d
+        kname = {0: "k_expand<%d>", 1: "k_walk<%d>", 2: "k_walk_coop<%d,1> (pooled query, row tickets)", 3: "k_walk_coop<%d,0>",
+                 4: "k_walk_coop<%d,2> (pooled query, static schedule)"}[int(os.environ.get("HVB_PERSISTENT", self.settings.get("persistent", DEFAULT_PERSISTENT)))] % d
         return {
             "value": verts / (dev_ms_tot * 1e-3), "unit": "vertices/s", "steps": steps, "warmup": warmup, "ms_per_step": dev_ms_tot / steps,
             "scaling": "strong" if self.strong else "weak",
             "config": {"workload": workload_text(self.name, self.n_per_gpu, self.n_total, d, self.periodic), "parallelism": "slab%d" % self.world,
-                       "l2": "256 MiB L2 flush before every step; steps timed one by one and summed", "settings": self.settings},
+                       "l2": "256 MiB L2 flush before every step; steps timed one by one and summed", "settings": self.settings,
+                       "wire": "ids cross PCIe as int32 (wire32), coordinates as f64"},
             "e2e": {"value": verts / e2e_tot, "unit": "vertices/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": 1e3 * e2e_tot / steps,
                     "phase_ms": dict(zip(("set_points", "search", "fetch_vertices", "neighbors"), (1e3 * self.phases / steps).round(3).tolist()))},
             "gpu_launches": launches,

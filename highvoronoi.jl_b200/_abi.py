@@ -13,7 +13,7 @@ ERROR_NAMES = {-1: "HVB_EINVAL", -2: "HVB_ECUDA", -3: "HVB_ENOGPU", -4: "HVB_ENO
 EXPORTS = ("hvb_default_params", "hvb_create", "hvb_set_points", "hvb_search", "hvb_counts", "hvb_fetch_vertices", "hvb_fetch_vertices_range", "hvb_fetch_rays",
            "hvb_neighbor_count", "hvb_fetch_neighbors", "hvb_view_vertices", "hvb_view_neighbors", "hvb_export_device", "hvb_merge_device", "hvb_adopt_device", "hvb_adopt_device_padded",
            "hvb_stats", "hvb_last_error", "hvb_destroy", "hvb_version", "hvb_create_periodic", "hvb_halo_count", "hvb_fetch_halo", "hvb_fetch_vertex_flags", "hvb_cell_volumes", "hvb_cell_areas", "hvb_clean_affected", "hvb_fetch_owned",
-           "hvb_create_multi", "hvb_comm_unique_id", "hvb_comm_init", "hvb_exchange_counts", "hvb_allgather")
+           "hvb_create_multi", "hvb_comm_unique_id", "hvb_comm_init", "hvb_exchange_counts", "hvb_allgather", "hvb_view_vertices32", "hvb_view_neighbors32")
 
 
 class hvb_params(ctypes.Structure):
@@ -22,7 +22,8 @@ class hvb_params(ctypes.Structure):
                 ("method", ctypes.c_int32), ("device", ctypes.c_int32), ("rank", ctypes.c_int32), ("world", ctypes.c_int32),
                 ("fp32_filter", ctypes.c_int32), ("on_degenerate", ctypes.c_int32), ("points_per_cell", ctypes.c_int32),
                 ("seed_stride", ctypes.c_int32), ("sort_output", ctypes.c_int32), ("tile_size", ctypes.c_int32), ("neighbors", ctypes.c_int32), ("persistent", ctypes.c_int32),
-                ("vertex_capacity", ctypes.c_int64), ("probe_scale", ctypes.c_double), ("periodic_margin", ctypes.c_double)]
+                ("vertex_capacity", ctypes.c_int64), ("probe_scale", ctypes.c_double), ("periodic_margin", ctypes.c_double),
+                ("wire32", ctypes.c_int32), ("reserved", ctypes.c_int32)]
 
 
 class hvb_stats_t(ctypes.Structure):
@@ -82,6 +83,8 @@ def lib():
         L.hvb_fetch_neighbors.argtypes = [vp, vp, vp]
         L.hvb_view_vertices.argtypes = [vp, ctypes.POINTER(vp), ctypes.POINTER(vp), ctypes.POINTER(i64)]
         L.hvb_view_neighbors.argtypes = [vp, ctypes.POINTER(vp), ctypes.POINTER(vp), ctypes.POINTER(i64)]
+        L.hvb_view_vertices32.argtypes = [vp, ctypes.POINTER(vp), ctypes.POINTER(vp), ctypes.POINTER(i64)]
+        L.hvb_view_neighbors32.argtypes = [vp, ctypes.POINTER(vp), ctypes.POINTER(vp), ctypes.POINTER(i64)]
         L.hvb_export_device.argtypes = [vp, vp, vp, i64, ctypes.POINTER(i64)]
         L.hvb_merge_device.argtypes = [vp, vp, vp, i64]
         L.hvb_adopt_device.argtypes = [vp, vp, vp, i64]
@@ -92,7 +95,7 @@ def lib():
         L.hvb_destroy.argtypes = [vp]
         L.hvb_destroy.restype = None
         L.hvb_version.restype = ctypes.c_char_p
-        for name in ("hvb_create_multi", "hvb_comm_unique_id", "hvb_comm_init", "hvb_exchange_counts", "hvb_allgather", "hvb_fetch_owned", "hvb_cell_volumes", "hvb_cell_areas", "hvb_clean_affected", "hvb_create", "hvb_create_periodic", "hvb_halo_count", "hvb_fetch_halo", "hvb_fetch_vertex_flags", "hvb_set_points", "hvb_search", "hvb_counts", "hvb_fetch_vertices", "hvb_fetch_vertices_range", "hvb_fetch_rays", "hvb_neighbor_count",
+        for name in ("hvb_view_vertices32", "hvb_view_neighbors32", "hvb_create_multi", "hvb_comm_unique_id", "hvb_comm_init", "hvb_exchange_counts", "hvb_allgather", "hvb_fetch_owned", "hvb_cell_volumes", "hvb_cell_areas", "hvb_clean_affected", "hvb_create", "hvb_create_periodic", "hvb_halo_count", "hvb_fetch_halo", "hvb_fetch_vertex_flags", "hvb_set_points", "hvb_search", "hvb_counts", "hvb_fetch_vertices", "hvb_fetch_vertices_range", "hvb_fetch_rays", "hvb_neighbor_count",
                      "hvb_fetch_neighbors", "hvb_view_vertices", "hvb_view_neighbors", "hvb_export_device", "hvb_merge_device", "hvb_adopt_device", "hvb_adopt_device_padded", "hvb_stats"):
             getattr(L, name).restype = i32
         _lib = L

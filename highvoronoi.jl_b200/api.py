@@ -226,8 +226,13 @@ class VoronoiMesh:
             _abi.check(L.hvb_fetch_vertices(ctx, self.sig.ctypes.data_as(ctypes.c_void_p), self.r.ctypes.data_as(ctypes.c_void_p)), ctx)
         else:
             ps, pr, cnt = ctypes.c_void_p(), ctypes.c_void_p(), ctypes.c_int64()
-            _abi.check(L.hvb_view_vertices(ctx, ctypes.byref(ps), ctypes.byref(pr), ctypes.byref(cnt)), ctx)
-            self.sig = _wrap(ps, (cnt.value, d + 1), ctypes.c_int64, searcher)
+            self.wire32 = bool(searcher.parameters.wire32)
+            if self.wire32:                 # compact wire format: int32 ids (hvb_view_vertices32)
+                _abi.check(L.hvb_view_vertices32(ctx, ctypes.byref(ps), ctypes.byref(pr), ctypes.byref(cnt)), ctx)
+                self.sig = _wrap(ps, (cnt.value, d + 1), ctypes.c_int32, searcher)
+            else:
+                _abi.check(L.hvb_view_vertices(ctx, ctypes.byref(ps), ctypes.byref(pr), ctypes.byref(cnt)), ctx)
+                self.sig = _wrap(ps, (cnt.value, d + 1), ctypes.c_int64, searcher)
             self.r = _wrap(pr, (cnt.value, d), ctypes.c_double, searcher)
         self.ray_edge = np.empty((nr.value, d), dtype=np.int64)
         self.ray_base = np.empty((nr.value, d))
@@ -291,9 +296,13 @@ class VoronoiMesh:
                 _abi.check(L.hvb_fetch_neighbors(ctx, off.ctypes.data_as(ctypes.c_void_p), ids.ctypes.data_as(ctypes.c_void_p)), ctx)
             else:
                 po, pi, tot = ctypes.c_void_p(), ctypes.c_void_p(), ctypes.c_int64()
-                _abi.check(L.hvb_view_neighbors(ctx, ctypes.byref(po), ctypes.byref(pi), ctypes.byref(tot)), ctx)
+                if getattr(self, "wire32", False):
+                    _abi.check(L.hvb_view_neighbors32(ctx, ctypes.byref(po), ctypes.byref(pi), ctypes.byref(tot)), ctx)
+                    ids = _wrap(pi, (tot.value,), ctypes.c_int32, self.searcher)
+                else:
+                    _abi.check(L.hvb_view_neighbors(ctx, ctypes.byref(po), ctypes.byref(pi), ctypes.byref(tot)), ctx)
+                    ids = _wrap(pi, (tot.value,), ctypes.c_int64, self.searcher)
                 off = _wrap(po, (self.n + 1,), ctypes.c_int64, self.searcher)
-                ids = _wrap(pi, (tot.value,), ctypes.c_int64, self.searcher)
             self._nb = (off, ids)
         return self._nb
 

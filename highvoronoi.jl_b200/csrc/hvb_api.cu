@@ -20,7 +20,7 @@ void hvb_default_params(hvb_params* p) {
     memset(p, 0, sizeof(*p));
     p->variance_tol = 1e-15; p->break_tol = 1e-5; p->b_nodes_tol = 1e-7; p->plane_tolerance = 1e-12; p->ray_tol = 1e-12;
     p->method = 0; p->device = 0; p->rank = 0; p->world = 1; p->fp32_filter = 1; p->on_degenerate = 0;
-    p->points_per_cell = 0; p->seed_stride = 0; p->sort_output = 1; p->neighbors = 0; p->persistent = 3; p->vertex_capacity = 0; p->probe_scale = 0.0; p->periodic_margin = 0.0;
+    p->points_per_cell = 0; p->seed_stride = 0; p->sort_output = 1; p->neighbors = 0; p->persistent = 3; p->vertex_capacity = 0; p->probe_scale = 0.0; p->periodic_margin = 0.0; p->wire32 = 0; p->reserved = 0;
 }
 
 int hvb_create(hvb_ctx** out, int dim, int64_t n, const double* xs, int nplanes, const double* plane_base,
@@ -105,6 +105,8 @@ int hvb_counts(hvb_ctx* ctx, int64_t* nvert, int64_t* nrays, int64_t* max_siglen
 int hvb_fetch_vertices(hvb_ctx* ctx, int64_t* sig, double* r) { return ctx ? ctx->fetch_vertices(sig, r) : HVB_EINVAL; }
 int hvb_fetch_vertices_range(hvb_ctx* ctx, int64_t first, int64_t count, int64_t* sig, double* r) { return ctx ? ctx->fetch_vertices_range(first, count, sig, r) : HVB_EINVAL; }
 int hvb_view_vertices(hvb_ctx* ctx, const int64_t** sig, const double** r, int64_t* nvert) { return (ctx && sig && r && nvert) ? ctx->view_vertices(sig, r, nvert) : HVB_EINVAL; }
+int hvb_view_vertices32(hvb_ctx* ctx, const int32_t** sig, const double** r, int64_t* nvert) { return (ctx && sig && r && nvert) ? ctx->view_vertices32(sig, r, nvert) : HVB_EINVAL; }
+int hvb_view_neighbors32(hvb_ctx* ctx, const int64_t** offsets, const int32_t** ids, int64_t* total) { return (ctx && offsets && ids && total) ? ctx->view_neighbors32(offsets, ids, total) : HVB_EINVAL; }
 int hvb_fetch_rays(hvb_ctx* ctx, int64_t* edge, double* base, double* dir, int64_t* node) { return ctx ? ctx->fetch_rays(edge, base, dir, node) : HVB_EINVAL; }
 int hvb_neighbor_count(hvb_ctx* ctx, int64_t* total) { return (ctx && total) ? ctx->neighbor_count(total) : HVB_EINVAL; }
 int hvb_fetch_neighbors(hvb_ctx* ctx, int64_t* offsets, int64_t* ids) { return ctx ? ctx->fetch_neighbors(offsets, ids) : HVB_EINVAL; }

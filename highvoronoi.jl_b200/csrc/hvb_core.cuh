@@ -345,8 +345,10 @@ HVB_HD double tie_window(int D, double t, double rnorm, double den, double dx2) 
     return fmin(1e-7, w);
 }
 
-HVB_HD void best_offer(Best& b, double t, int id, double tw) {
-    if (t < b.t || (t == b.t && id < b.id)) { b.t2 = b.t; b.t = t; b.id = id; b.tw = tw; }
+// the window is only needed for a candidate that becomes the winner: it is computed inside that branch (an FP64 square
+// root and a division per verified candidate otherwise)
+HVB_HD void best_offer(Best& b, double t, int id, int D, double rnorm, double den, double dx2) {
+    if (t < b.t || (t == b.t && id < b.id)) { b.t2 = b.t; b.t = t; b.id = id; b.tw = tie_window(D, t, rnorm, den, dx2); }
     else if (id != b.id && t < b.t2) b.t2 = t;
 }
 HVB_HD void best_merge(Best& b, double t, int id, double t2, double tw) {
@@ -396,7 +398,7 @@ HVB_HD bool verify64(const Dev<D>& dv, const RayQ<D>& q, int j, Best& best, Loca
     if (!(ux > q.c) || !(den > 0)) return false;
     double t = num / (2.0 * den);
     if (!(t >= dv.plane_tol)) return false;           // raycast.jl:887-889
-    best_offer(best, t, j, tie_window(D, t, q.rnorm, den, dx2));
+    best_offer(best, t, j, D, q.rnorm, den, dx2);
     return true;
 }
 
@@ -718,7 +720,7 @@ HVB_HD void plane_candidates(const Dev<D>& dv, const RayQ<D>& q, Best& best) {
         double t = (ps->off[p] - nr) / nu;
         if (!(t >= dv.plane_tol)) continue;
         // a plane is the mirror image of x0: x - x0 = 2 s n, u . (x - x0) = 2 s nu
-        best_offer(best, t, dv.n + p, tie_window(D, t, q.rnorm, 2.0 * s * nu, 4.0 * s * s));
+        best_offer(best, t, dv.n + p, D, q.rnorm, 2.0 * s * nu, 4.0 * s * s);
     }
 }
 

@@ -207,7 +207,7 @@ struct Ctx : hvb_ctx {
         ctr.release(); sc.release(); h_sc.release(); h_ctr.release(); h_extra.release(); cells_dev.release(); seed_sig_dev.release(); seed_r_dev.release();
         out_sig[0].release(); out_sig[1].release(); out_r[0].release(); out_r[1].release(); key_top.release(); key_hi.release(); key_lo.release(); key_tmp.release();
         idx[0].release(); idx[1].release(); ray_edge.release(); ray_node.release(); ray_base.release(); ray_dir.release();
-        h_sig.release(); h_r.release(); h_nb_off.release(); h_nb_ids.release(); ptab.release(); deg.release(); ncur.release(); nb_off.release(); nb_ids.release();
+        h_sig.release(); h_r.release(); sig32_dev.release(); ids32_dev.release(); h_sig32.release(); h_ids32.release(); h_nb_off.release(); h_nb_ids.release(); ptab.release(); deg.release(); ncur.release(); nb_off.release(); nb_ids.release();
         for (cudaEvent_t e : ev_pool) cudaEventDestroy(e);
         if (ev_up) cudaEventDestroy(ev_up);
         if (ev_a) cudaEventDestroy(ev_a);
@@ -369,7 +369,7 @@ struct Ctx : hvb_ctx {
         if (!setup_done) { err = "context not initialised"; return HVB_ESTATE; }
         if (n_new <= D || !xs) { err = "There are not enough points to create a Voronoi tessellation"; return HVB_EINVAL; }
         CK(cudaSetDevice(prm.device));
-        have_result = false; staged = false; nb_total = -1; have_flags = false;
+        have_result = false; staged = false; staged_r = staged_sig64 = staged_sig32 = false; nb_staged32 = false; nb_total = -1; have_flags = false;
         n_user = n_new; n = n_new; n_halo = 0;
         CK(cudaEventRecord(ev_a, stream));
         // upload, then bounding box + domain check on the device against the caller's planes
@@ -793,7 +793,7 @@ struct Ctx : hvb_ctx {
     int search_once(const int64_t* cells, int64_t ncells_in, const int64_t* seed_sig, const double* seed_r, int64_t nseed, int stride) {
         if (nseed < 0 || (nseed > 0 && (!seed_sig || !seed_r || stride < D + 1))) { err = "bad seed vertex arguments"; return HVB_EINVAL; }
         CK(cudaSetDevice(prm.device));
-        have_result = false; staged = false; nb_total = -1; have_flags = false;
+        have_result = false; staged = false; staged_r = staged_sig64 = staged_sig32 = false; nb_staged32 = false; nb_total = -1; have_flags = false;
         st.exchange_bytes = 0;
         int64_t cap = prm.vertex_capacity > 0 ? prm.vertex_capacity
                       : (periodic ? (int64_t)(estimate_vertices(D, n_user, P) * periodic_versions()) : estimate_vertices(D, n, P));
@@ -1061,19 +1061,34 @@ struct Ctx : hvb_ctx {
         return sort_rows((u32)nvert, bits);
     }
 
-    // device -> page-locked host staging (asynchronous; the fetch calls wait for it)
-    int stage() {
-        CK(h_sig.ensure((size_t)std::max<int64_t>(nvert, 1) * (D + 1))); CK(h_r.ensure((size_t)std::max<int64_t>(nvert, 1) * D));
+    // device -> page-locked host staging (asynchronous; the fetch calls wait for it).  Three pieces, staged on demand:
+    // coordinates, signatures as int64 (the reference's Int64 ids) and signatures as int32 (the compact wire format:
+    // prm.wire32 stages this one inside hvb_search instead of the int64 form, 4 (dim+1) bytes per row less over PCIe)
+    bool staged_r = false, staged_sig64 = false, staged_sig32 = false;
+    DBuf<int> sig32_dev, ids32_dev;
+    HBuf<int> h_sig32, h_ids32;
+    bool nb_staged32 = false;
+    int stage_rows(bool want64, bool want32) {
+        const size_t rows = (size_t)std::max<int64_t>(nvert, 1);
+        const bool do_r = !staged_r, do64 = want64 && !staged_sig64, do32 = want32 && !staged_sig32;
+        if (!(do_r || do64 || do32)) return HVB_OK;
+        if (do_r) CK(h_r.ensure(rows * D));
+        if (do64) CK(h_sig.ensure(rows * (D + 1)));
+        if (do32) { CK(h_sig32.ensure(rows * (D + 1))); CK(sig32_dev.ensure(rows * (D + 1))); }
         if (nvert > 0) {
+            if (do32) { const size_t cnt = (size_t)nvert * (D + 1); k_narrow_i64<<<blocks_for((int64_t)cnt, 256), 256, 0, stream>>>(out_sig[res].p, sig32_dev.p, cnt); ++launches; }
             // on the staging stream, so that the copy overlaps whatever the compute stream does next (neighbour lists)
             CK(cudaEventRecord(ev_stage, stream));
             CK(cudaStreamWaitEvent(sstream, ev_stage, 0));
-            CK(cudaMemcpyAsync(h_sig.p, out_sig[res].p, (size_t)nvert * (D + 1) * sizeof(long long), cudaMemcpyDeviceToHost, sstream));
-            CK(cudaMemcpyAsync(h_r.p, out_r[res].p, (size_t)nvert * D * sizeof(double), cudaMemcpyDeviceToHost, sstream));
+            if (do32) CK(cudaMemcpyAsync(h_sig32.p, sig32_dev.p, (size_t)nvert * (D + 1) * sizeof(int), cudaMemcpyDeviceToHost, sstream));
+            if (do64) CK(cudaMemcpyAsync(h_sig.p, out_sig[res].p, (size_t)nvert * (D + 1) * sizeof(long long), cudaMemcpyDeviceToHost, sstream));
+            if (do_r) CK(cudaMemcpyAsync(h_r.p, out_r[res].p, (size_t)nvert * D * sizeof(double), cudaMemcpyDeviceToHost, sstream));
         }
-        staged = true;
+        staged_r = true; staged_sig64 |= want64; staged_sig32 |= want32;
+        staged = staged_sig64;
         return HVB_OK;
     }
+    int stage() { return stage_rows(!prm.wire32, prm.wire32 != 0); }
 
     cudaEvent_t ev_sd = nullptr, ev_sd2 = nullptr;
     cudaEvent_t ev_stage_done() {          // an event on the staging stream that marks "everything staged so far is in host memory"
@@ -1091,10 +1106,20 @@ struct Ctx : hvb_ctx {
     int view_vertices(const int64_t** sig, const double** r, int64_t* nv) override {
         if (!have_result) { err = "no search result"; return HVB_ESTATE; }
         CK(cudaSetDevice(prm.device));
-        if (!staged) { int rc = stage(); if (rc) return rc; }
+        { int rc = stage_rows(true, false); if (rc) return rc; }
         CK(cudaStreamSynchronize(stream));
         CK(cudaStreamSynchronize(sstream));
         *sig = (const int64_t*)h_sig.p; *r = h_r.p; *nv = nvert;
+        return HVB_OK;
+    }
+    int view_vertices32(const int32_t** sig, const double** r, int64_t* nv) override {
+        if (!have_result) { err = "no search result"; return HVB_ESTATE; }
+        if (n + P >= 0x7fffffffLL) { err = "ids do not fit 32 bits"; return HVB_EINVAL; }
+        CK(cudaSetDevice(prm.device));
+        { int rc = stage_rows(false, true); if (rc) return rc; }
+        CK(cudaStreamSynchronize(stream));
+        CK(cudaStreamSynchronize(sstream));
+        *sig = (const int32_t*)h_sig32.p; *r = h_r.p; *nv = nvert;
         return HVB_OK;
     }
     int fetch_vertices(int64_t* sig, double* r) override {
@@ -1135,7 +1160,7 @@ struct Ctx : hvb_ctx {
     bool nb_raw = false;
     const long long* nb_rows = nullptr;
     int nb_prepare(bool raw, const long long* rows) {
-        nb_staged = false; nb_raw = raw; nb_rows = rows;
+        nb_staged = false; nb_staged32 = false; nb_off_staged = false; nb_raw = raw; nb_rows = rows;
         CK(deg.ensure(n)); CK(ncur.ensure(n)); CK(nb_off.ensure(n + 1));
         static const double nb_est[7] = {0, 0, 8, 20, 48, 120, 320};
         // periodic contexts build the lists of the caller's cells only (n_user == n otherwise)
@@ -1215,20 +1240,44 @@ struct Ctx : hvb_ctx {
         *total = nb_total;
         return HVB_OK;
     }
-    int stage_neighbors() {
-        if (nb_staged) return HVB_OK;
-        CK(h_nb_off.ensure(n + 1)); CK(h_nb_ids.ensure(std::max<int64_t>(nb_total, 1)));
+    bool nb_off_staged = false;
+    int stage_neighbors() { return stage_neighbors_as(!prm.wire32, prm.wire32 != 0); }
+    int stage_neighbors_as(bool want64, bool want32) {
+        const bool do64 = want64 && !nb_staged, do32 = want32 && !nb_staged32;
+        if (!(do64 || do32)) return HVB_OK;
+        CK(h_nb_off.ensure(n + 1));
+        if (do64) CK(h_nb_ids.ensure(std::max<int64_t>(nb_total, 1)));
+        if (do32) {
+            CK(h_ids32.ensure(std::max<int64_t>(nb_total, 1))); CK(ids32_dev.ensure(std::max<int64_t>(nb_total, 1)));
+            // the narrowing runs behind the list build, on the stream that built the lists last
+            if (nb_total > 0) {
+                CK(cudaStreamWaitEvent(sstream2, ev_nb, 0));
+                k_narrow_i64<<<blocks_for(nb_total, 256), 256, 0, sstream2>>>(nb_ids.p, ids32_dev.p, (size_t)nb_total); ++launches;
+            }
+        }
         CK(cudaStreamWaitEvent(sstream2, ev_nb, 0));
-        CK(cudaMemcpyAsync(h_nb_off.p, nb_off.p, (size_t)(n + 1) * 8, cudaMemcpyDeviceToHost, sstream2));
-        if (nb_total > 0) CK(cudaMemcpyAsync(h_nb_ids.p, nb_ids.p, (size_t)nb_total * 8, cudaMemcpyDeviceToHost, sstream2));
-        nb_staged = true;
+        if (!nb_off_staged) CK(cudaMemcpyAsync(h_nb_off.p, nb_off.p, (size_t)(n + 1) * 8, cudaMemcpyDeviceToHost, sstream2));
+        if (do64 && nb_total > 0) CK(cudaMemcpyAsync(h_nb_ids.p, nb_ids.p, (size_t)nb_total * 8, cudaMemcpyDeviceToHost, sstream2));
+        if (do32 && nb_total > 0) CK(cudaMemcpyAsync(h_ids32.p, ids32_dev.p, (size_t)nb_total * 4, cudaMemcpyDeviceToHost, sstream2));
+        nb_off_staged = true; nb_staged |= want64; nb_staged32 |= want32;
+        return HVB_OK;
+    }
+    int view_neighbors32(const int64_t** off, const int32_t** ids, int64_t* total) override {
+        if (!have_result) { err = "no search result"; return HVB_ESTATE; }
+        if (n + P >= 0x7fffffffLL) { err = "ids do not fit 32 bits"; return HVB_EINVAL; }
+        CK(cudaSetDevice(prm.device));
+        int rc = build_neighbors(); if (rc) return rc;
+        rc = stage_neighbors_as(false, true); if (rc) return rc;
+        CK(cudaStreamSynchronize(stream));
+        CK(cudaStreamSynchronize(sstream2));
+        *off = (const int64_t*)h_nb_off.p; *ids = (const int32_t*)h_ids32.p; *total = nb_total;
         return HVB_OK;
     }
     int view_neighbors(const int64_t** off, const int64_t** ids, int64_t* total) override {
         if (!have_result) { err = "no search result"; return HVB_ESTATE; }
         CK(cudaSetDevice(prm.device));
         int rc = build_neighbors(); if (rc) return rc;
-        rc = stage_neighbors(); if (rc) return rc;
+        rc = stage_neighbors_as(true, false); if (rc) return rc;
         CK(cudaStreamSynchronize(stream));
         CK(cudaStreamSynchronize(sstream2));
         *off = (const int64_t*)h_nb_off.p; *ids = (const int64_t*)h_nb_ids.p; *total = nb_total;
@@ -1338,7 +1387,7 @@ struct Ctx : hvb_ctx {
         CK(cudaStreamSynchronize(stream));
         CK(cudaGetLastError());
         st.exchange_bytes = (int64_t)((size_t)cap * ((D + 1) * 4 + D * 8) * (size_t)(world - 1));
-        nvert = total; res = 0; staged = false; have_result = true; counts_cached = false;
+        nvert = total; res = 0; staged = false; staged_r = staged_sig64 = staged_sig32 = false; nb_staged32 = false; have_result = true; counts_cached = false;
         nb_total = -1; own_ptr = nullptr;         // the rows are global now: lists are rebuilt from them on request, for every cell
         st.vertices = nvert; st.kernel_launches = launches;
         if (periodic) {
@@ -1379,7 +1428,7 @@ struct Ctx : hvb_ctx {
             CK(cudaMemcpyAsync(out_r[0].p, r, (size_t)count * D * 8, cudaMemcpyDeviceToDevice, stream));
         }
         CK(cudaStreamSynchronize(stream));
-        nvert = count; res = 0; staged = false; have_result = true;
+        nvert = count; res = 0; staged = false; staged_r = staged_sig64 = staged_sig32 = false; nb_staged32 = false; have_result = true;
         nb_total = -1; own_ptr = nullptr;         // the rows are global now: lists are rebuilt from them on request, for every cell
         st.vertices = nvert;
         return HVB_OK;
@@ -1400,7 +1449,7 @@ struct Ctx : hvb_ctx {
             at += counts[k];
         }
         CK(cudaStreamSynchronize(stream));
-        nvert = total; res = 0; staged = false; have_result = true;
+        nvert = total; res = 0; staged = false; staged_r = staged_sig64 = staged_sig32 = false; nb_staged32 = false; have_result = true;
         nb_total = -1; own_ptr = nullptr;
         st.vertices = nvert;
         return HVB_OK;
@@ -1423,7 +1472,7 @@ struct Ctx : hvb_ctx {
         nvert = h_sc.p->out_count;
         rc = sort_rows((u32)nvert, bits); if (rc) return rc;
         nb_total = -1; own_ptr = nullptr;         // the rows are global now: lists are rebuilt from them on request
-        staged = false;                      // staged on the first hvb_view_* / hvb_fetch_* (only ranks that read the result pay the D2H)
+        staged = false; staged_r = staged_sig64 = staged_sig32 = false; nb_staged32 = false;   // staged on the first hvb_view_* / hvb_fetch_*
         CK(cudaStreamSynchronize(stream));
         CK(cudaGetLastError());
         st.vertices = nvert; st.kernel_launches = launches;

@@ -25,6 +25,8 @@ struct hvb_ctx {
     virtual int counts(int64_t* nv, int64_t* nr, int64_t* msl) = 0;
     virtual int fetch_vertices(int64_t* sig, double* r) = 0;
     virtual int view_vertices(const int64_t** sig, const double** r, int64_t* nv) = 0;
+    virtual int view_vertices32(const int32_t** sig, const double** r, int64_t* nv) = 0;
+    virtual int view_neighbors32(const int64_t** off, const int32_t** ids, int64_t* total) = 0;
     virtual int fetch_vertices_range(int64_t first, int64_t count, int64_t* sig, double* r) = 0;
     virtual int fetch_rays(int64_t* edge, double* base, double* dir, int64_t* node) = 0;
     virtual int neighbor_count(int64_t* total) = 0;

@@ -184,6 +184,14 @@ struct MultiCtx : hvb_ctx {
         err = "zero-copy views exist per GPU only: use hvb_fetch_vertices on a multi-GPU context";
         return HVB_ESTATE;
     }
+    int view_vertices32(const int32_t**, const double**, int64_t*) override {
+        err = "zero-copy views exist per GPU only: use hvb_fetch_vertices on a multi-GPU context";
+        return HVB_ESTATE;
+    }
+    int view_neighbors32(const int64_t**, const int32_t**, int64_t*) override {
+        err = "zero-copy views exist per GPU only: use hvb_fetch_neighbors on a multi-GPU context";
+        return HVB_ESTATE;
+    }
     int view_neighbors(const int64_t**, const int64_t**, int64_t*) override {
         err = "zero-copy views exist per GPU only: use hvb_fetch_neighbors on a multi-GPU context";
         return HVB_ESTATE;

@@ -85,6 +85,10 @@ typedef struct hvb_params {
     double probe_scale;       /* first probe ball radius / circumradius of the origin vertex; 0 = auto */
     double periodic_margin;   /* hvb_create_periodic: first halo margin (distance outside the periodic planes); 0 = auto
                                  from the generator density.  The certificate enlarges it when it proves too small. */
+    int32_t wire32;           /* 1: hvb_search stages signatures and neighbour ids in page-locked memory as int32 (read them
+                                 with hvb_view_vertices32 / hvb_view_neighbors32): 4 bytes per id less over PCIe.  The int64
+                                 calls keep working (they stage the int64 form on first use).  Default 0. */
+    int32_t reserved;
 } hvb_params;
 
 typedef struct hvb_stats_t {
@@ -197,6 +201,10 @@ int hvb_fetch_neighbors(hvb_ctx* ctx, int64_t* offsets, int64_t* ids);
  * hvb_search / hvb_destroy.  Layout as in hvb_fetch_vertices. */
 int hvb_view_vertices(hvb_ctx* ctx, const int64_t** sig, const double** r, int64_t* nvert);
 int hvb_view_neighbors(hvb_ctx* ctx, const int64_t** offsets, const int64_t** ids, int64_t* total);
+/* The same with ids as int32 (needs n + nplanes < 2^31): the compact wire format.  A caller that wants Int64 widens on
+ * its side; the reference's replay loop (push!(mesh, sig => r), abstractmesh.jl:111) copies every signature anyway. */
+int hvb_view_vertices32(hvb_ctx* ctx, const int32_t** sig, const double** r, int64_t* nvert);
+int hvb_view_neighbors32(hvb_ctx* ctx, const int64_t** offsets, const int32_t** ids, int64_t* total);
 
 /* ---- Multi-GPU (replaces MultiThread(a,b): _voronoi sysvoronoi.jl:50-82, ParallelMesh / partition_indices
  * parallelmesh.jl:52-87, getMultiThreadRaycasters raycast-types.jl:361-371) ------------------------------------------

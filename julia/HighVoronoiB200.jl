@@ -1,23 +1,43 @@
-# HighVoronoiB200.jl -- the reference-side binding of libhvb200.so (NOT executed in the build container: Julia is not
-# installed there; the same C ABI is exercised by the Python ctypes mirror in highvoronoi.jl_b200/).
+# HighVoronoiB200.jl -- the reference-side binding of libhvb200.so.
 #
-# What a HighVoronoi.jl maintainer adds to select the B200 backend through the existing `search_settings` seam:
+# NOT EXECUTED in the build container or on its GPU boxes: no Julia is installed there.  The same C ABI is exercised by the
+# Python ctypes mirror in highvoronoi.jl_b200/ (tests/ call every entry point bound below).  tests/test_abi.py checks that
+# `HvbParams` mirrors `struct hvb_params` field by field.
 #
-#   1. one new threading singleton  `B200Thread(device, rank, world)`   (next to SingleThread/MultiThread/AutoThread,
-#      src/HighVoronoi.jl:60-81)
-#   2. one new method of `_voronoi(mesh, TODO, ..., threading::B200Thread)`   (next to src/sysvoronoi.jl:41 and :50)
+# What a HighVoronoi.jl maintainer adds to select the B200 backend through the existing `search_settings` seam -- the
+# complete list; each item names the reference line that makes it necessary:
 #
-# Everything else -- VoronoiGeometry / VoronoiData / refine! / ConvexHull -- is unchanged: they reach the search only
-# through `voronoi(mesh; Iter, searcher)` (sysvoronoi.jl:21), which dispatches on `searcher.parameters.threading`
-# (sysvoronoi.jl:38).
+#   1. a threading singleton  `B200Thread`                      next to SingleThread / MultiThread (src/HighVoronoi.jl:60-81).
+#      `RaycastParameter` is generic in `typeof(threading)` (raycast-types.jl:312-324), so no change there.
+#   2. `HighVoronoi.ThreadSafeDict(dict, ::B200Thread) = dict`  `Raycast(xs; options)` builds its `FEIStorage_global` with
+#      `ThreadSafeDict(dict, parameters.threading)` (raycast-types.jl:426), which has methods for SingleThread / MultiThread
+#      only (threaddict.jl:38-39): without this method the searcher cannot even be constructed.
+#   3. `HighVoronoi._voronoi(mesh, TODO, ..., ::B200Thread)`     next to sysvoronoi.jl:41 (SingleThread) and :50 (MultiThread);
+#      `voronoi` dispatches on `searcher.parameters.threading` at sysvoronoi.jl:38.
 #
-#   VG = VoronoiGeometry(xs, cuboid(3, periodic=[]); search_settings=(threading=B200Thread(0),), integrate=false)
+# No other dispatch on the threading object is reached from `voronoi()`: `myqht` / `locktype` (queues.jl:22-24) and
+# `MultyRaycast` (raycast-types.jl:298-307) are called inside the cell loop `__voronoi` that method 3 replaces;
+# `ThreadsafeProgressMeter(..., ::MultiThread)` (progress.jl:15) and `create_multithreads` (parallelmesh.jl:9) likewise;
+# `integrate_geo(::MultiThread, ...)` (geometry.jl:203) dispatches on the `integrate` keyword, not on `search_settings`.
+#
+# Everything above the seam -- VoronoiGeometry / VoronoiData / refine! / substitute! / ConvexHull -- is unchanged:
+#
+#   using HighVoronoi, HighVoronoiB200
+#   VG = VoronoiGeometry(xs, cuboid(3, periodic=[]); search_settings=(threading=B200Thread(),), integrate=false)
+#   VG = VoronoiGeometry(xs, cuboid(5, periodic=[]); search_settings=(threading=B200Thread(ngpus=8),), integrate=false)
+#
+# Periodic domains: at the `voronoi()` seam every plane is a mirror -- the reference periodises on the host around the search
+# (Create_Discrete_Domain domain.jl:175-213 calls voronoi() on generators + halo with a plain Boundary), so method 3 never
+# sees a periodic plane and works unchanged inside that orchestration.  `periodic_tessellation` below is the one-call
+# alternative that runs halo, search and certificate on the device (hvb_create_periodic).
 
 module HighVoronoiB200
 
 using HighVoronoi
 using StaticArrays
-import HighVoronoi: _voronoi, nodes, AbstractMesh, RaycastIncircleSkip
+import HighVoronoi: _voronoi, nodes, AbstractMesh, RaycastIncircleSkip, ThreadSafeDict
+
+export B200Thread, periodic_tessellation, release_contexts!
 
 const LIB = get(ENV, "HVB200_LIB", joinpath(@__DIR__, "..", "highvoronoi.jl_b200", "lib", "libhvb200.so"))
 
@@ -28,77 +48,157 @@ mutable struct HvbParams
     fp32_filter::Int32; on_degenerate::Int32; points_per_cell::Int32; seed_stride::Int32; sort_output::Int32
     tile_size::Int32; neighbors::Int32; persistent::Int32
     vertex_capacity::Int64; probe_scale::Cdouble; periodic_margin::Cdouble
+    wire32::Int32; reserved::Int32
     HvbParams() = new()
 end
 
-struct B200Thread            # <: the reference's threading singletons
+"""
+    B200Thread(; device = 0, ngpus = 1, devices = nothing)     one process drives `ngpus` GPUs (hvb_create_multi)
+    B200Thread(device, rank, world)                              this process is slab `rank` of `world` (one process per GPU)
+
+The threading singleton of the B200 backend (item 1).  `ngpus > 1` is the analogue of `MultiThread(ngpus, 1)`: contiguous
+slabs of the spatially sorted generator order, one per GPU (parallelmesh.jl:52-87).
+"""
+struct B200Thread
     device::Int32
     rank::Int32
     world::Int32
+    ngpus::Int32
+    devices::Vector{Int32}
 end
-B200Thread(device::Integer=0) = B200Thread(Int32(device), Int32(0), Int32(1))
+B200Thread(; device::Integer = 0, ngpus::Integer = 1, devices = nothing) =
+    B200Thread(Int32(device), Int32(0), Int32(1), Int32(devices === nothing ? ngpus : length(devices)),
+               devices === nothing ? Int32[] : Int32.(devices))
+B200Thread(device::Integer, rank::Integer, world::Integer) = B200Thread(Int32(device), Int32(rank), Int32(world), Int32(1), Int32[])
+
+# item 2 (raycast-types.jl:426, threaddict.jl:38-39): the search runs on the device, the host-side dictionary is never shared
+ThreadSafeDict(dict::ADKV, ::B200Thread) where {K, V, ADKV<:AbstractDict{K, V}} = dict
 
 last_error(ctx) = unsafe_string(ccall((:hvb_last_error, LIB), Cstring, (Ptr{Cvoid},), ctx))
 check(rc, ctx=C_NULL) = rc == 0 || error("libhvb200: code $rc: " * last_error(ctx))     # codes become Julia exceptions
 
-"""
-    _voronoi(mesh, TODO, ..., threading::B200Thread)
+# method singletons -> hvb_params.method (raycast-types.jl:244-284)
+method_code(::HighVoronoi.Raycast_Original) = Int32(1)
+method_code(::HighVoronoi.Raycast_Combined) = Int32(2)
+method_code(::HighVoronoi.Raycast_Non_General) = Int32(3)
+method_code(::HighVoronoi.Raycast_Original_Safety) = Int32(4)
+method_code(::HighVoronoi.Raycast_Non_General_Skip) = Int32(5)
+method_code(::HighVoronoi.Raycast_Original_HP) = Int32(6)
+method_code(::HighVoronoi.Raycast_Non_General_Asymptotic_General_HP) = Int32(7)
+method_code(_) = Int32(0)                                  # RCStandard = RCNonGeneral = RCNonGeneralHP
 
-Drop-in replacement of the cell loop (`__voronoi`, sysvoronoi.jl:152-215): flatten the generators and the boundary
-planes, run the search on the GPU, replay the result with the reference's own `push!(mesh, sig=>r)`
-(abstractmesh.jl:111) and `pushray!` (abstractmesh.jl:191).
-"""
-function _voronoi(mesh::AM, TODO, compact, v_offset, silence, iteration_reset, printsearcher,
-                  searcher::RaycastIncircleSkip, intro, threading::B200Thread) where {P, AM<:AbstractMesh{P}}
-    xs = nodes(mesh)                              # Vector{SVector{d,Float64}} == n x d row-major doubles (voronoinodes.jl:14)
-    d = size(P)[1]
-    n = length(xs)
+# ---- the device context lives with the searcher: created at the first voronoi() call, re-targeted with hvb_set_points when
+# the same searcher meets another generator set of the same dimension and domain, destroyed by release_contexts!() --------
+mutable struct Context
+    ptr::Ptr{Cvoid}
+    dim::Int
+    nplanes::Int
+    multi::Bool
+end
+const CONTEXTS = IdDict{Any, Context}()
+function release_contexts!()
+    for (_, c) in CONTEXTS
+        c.ptr != C_NULL && ccall((:hvb_destroy, LIB), Cvoid, (Ptr{Cvoid},), c.ptr)
+    end
+    empty!(CONTEXTS)
+end
+atexit(release_contexts!)
+
+function context_for(searcher, xs::Vector{P}, threading::B200Thread) where {P}
+    d = size(P)[1]; n = length(xs)
     planes = searcher.domain.planes               # boundary.jl:22-29
     np = length(planes)
-    base = Matrix{Float64}(undef, d, np)
-    normal = Matrix{Float64}(undef, d, np)
+    multi = threading.ngpus > 1
+    old = get(CONTEXTS, searcher, nothing)
+    if old !== nothing && old.dim == d && old.nplanes == np && old.multi == multi
+        GC.@preserve xs check(ccall((:hvb_set_points, LIB), Cint, (Ptr{Cvoid}, Int64, Ptr{Float64}), old.ptr, n, pointer(reinterpret(Float64, xs))), old.ptr)
+        return old.ptr
+    end
+    old !== nothing && ccall((:hvb_destroy, LIB), Cvoid, (Ptr{Cvoid},), old.ptr)
+    base = Matrix{Float64}(undef, d, np); normal = Matrix{Float64}(undef, d, np)
     for (k, pl) in enumerate(planes)
-        base[:, k] .= pl.base
-        normal[:, k] .= pl.normal
+        base[:, k] .= pl.base; normal[:, k] .= pl.normal
     end
     prm = HvbParams()
     ccall((:hvb_default_params, LIB), Cvoid, (Ref{HvbParams},), prm)
     par = searcher.parameters                     # raycast-types.jl:136-171
     prm.variance_tol = par.variance_tol; prm.break_tol = par.break_tol; prm.b_nodes_tol = par.b_nodes_tol
     prm.plane_tolerance = par.plane_tolerance; prm.ray_tol = par.ray_tol
+    prm.method = method_code(par.method)
     prm.device = threading.device; prm.rank = threading.rank; prm.world = threading.world
     ctx = Ref{Ptr{Cvoid}}(C_NULL)
     GC.@preserve xs base normal begin
-        check(ccall((:hvb_create, LIB), Cint,
-                    (Ref{Ptr{Cvoid}}, Cint, Int64, Ptr{Float64}, Cint, Ptr{Float64}, Ptr{Float64}, Ref{HvbParams}),
-                    ctx, d, n, pointer(reinterpret(Float64, xs)), np, base, normal, prm))
+        if multi
+            devs = threading.devices
+            check(ccall((:hvb_create_multi, LIB), Cint,
+                        (Ref{Ptr{Cvoid}}, Cint, Int64, Ptr{Float64}, Cint, Ptr{Float64}, Ptr{Float64}, Ptr{Int32}, Ref{HvbParams}, Cint, Ptr{Int32}),
+                        ctx, d, n, pointer(reinterpret(Float64, xs)), np, base, normal, C_NULL, prm, threading.ngpus,
+                        isempty(devs) ? Ptr{Int32}(C_NULL) : pointer(devs)))
+        else
+            check(ccall((:hvb_create, LIB), Cint,
+                        (Ref{Ptr{Cvoid}}, Cint, Int64, Ptr{Float64}, Cint, Ptr{Float64}, Ptr{Float64}, Ref{HvbParams}),
+                        ctx, d, n, pointer(reinterpret(Float64, xs)), np, base, normal, prm))
+        end
     end
-    c = ctx[]
-    try
-        cells = Int64.(TODO)                      # Iter (1-based)
-        all_cells = length(cells) == n
+    CONTEXTS[searcher] = Context(ctx[], d, np, multi)
+    return ctx[]
+end
+
+# the vertices a mesh already holds (refinement callers pass a non-empty mesh, meshrefine.jl:199-215): every vertex once,
+# at its owner cell sig[1] (abstractmesh.jl:111-125); plane ids in the external numbering n+p
+function known_vertices(mesh, n::Int, d::Int)
+    sigs = Int64[]; rs = Float64[]
+    for i in 1:n
+        for (sig, r) in HighVoronoi.vertices_iterator(mesh, i)
+            sig[1] == i || continue
+            length(sig) == d + 1 || error("HighVoronoiB200: the mesh holds a non-general vertex (more than dim+1 generators): not supported by the device search")
+            append!(sigs, sig); append!(rs, r)
+        end
+    end
+    return reshape(sigs, d + 1, :), reshape(rs, d, :)
+end
+
+"""
+    _voronoi(mesh, TODO, ..., threading::B200Thread)                                            (item 3)
+
+Drop-in replacement of the cell loop (`__voronoi`, sysvoronoi.jl:152-215): flatten the generators and the boundary
+planes, run the search on the GPU(s), replay the result with the reference's own `push!(mesh, sig=>r)`
+(abstractmesh.jl:111) and `pushray!` (abstractmesh.jl:191).  `TODO` is `Iter`; vertices the mesh already holds are
+passed as seed vertices, so that only NEW vertices come back (hvb_search).
+"""
+function _voronoi(mesh::AM, TODO, compact, v_offset, silence, iteration_reset, printsearcher,
+                  searcher::RaycastIncircleSkip, intro, threading::B200Thread) where {P, AM<:AbstractMesh{P}}
+    xs = nodes(mesh)                              # Vector{SVector{d,Float64}} == n x d row-major doubles (voronoinodes.jl:14)
+    d = size(P)[1]
+    n = length(xs)
+    c = context_for(searcher, xs, threading)
+    cells = Int64.(collect(TODO))                 # Iter (1-based)
+    all_cells = length(cells) == n
+    ksig, kr = all_cells && iteration_reset ? (Matrix{Int64}(undef, d + 1, 0), Matrix{Float64}(undef, d, 0)) : known_vertices(mesh, n, d)
+    nk = size(ksig, 2)
+    if threading.ngpus > 1 && (!all_cells || nk > 0)
+        error("HighVoronoiB200: Iter subsets / meshes that already hold vertices run on one GPU: use B200Thread() for refinement")
+    end
+    GC.@preserve cells ksig kr begin
         check(ccall((:hvb_search, LIB), Cint,
                     (Ptr{Cvoid}, Ptr{Int64}, Int64, Ptr{Int64}, Ptr{Float64}, Int64, Cint),
-                    c, all_cells ? C_NULL : cells, all_cells ? 0 : length(cells), C_NULL, C_NULL, 0, 0), c)
-        nv = Ref{Int64}(0); nr = Ref{Int64}(0); ml = Ref{Int64}(0)
-        check(ccall((:hvb_counts, LIB), Cint, (Ptr{Cvoid}, Ref{Int64}, Ref{Int64}, Ref{Int64}), c, nv, nr, ml), c)
-        # zero-copy view of the page-locked result (valid until the context is destroyed)
-        psig = Ref{Ptr{Int64}}(C_NULL); pr = Ref{Ptr{Float64}}(C_NULL); cnt = Ref{Int64}(0)
-        check(ccall((:hvb_view_vertices, LIB), Cint, (Ptr{Cvoid}, Ref{Ptr{Int64}}, Ref{Ptr{Float64}}, Ref{Int64}), c, psig, pr, cnt), c)
-        sig = unsafe_wrap(Array, psig[], (d + 1, cnt[]))
-        r = unsafe_wrap(Array, pr[], (d, cnt[]))
-        for v in 1:cnt[]
-            push!(mesh, Vector{Int64}(view(sig, :, v)) => P(view(r, :, v)))          # abstractmesh.jl:111
+                    c, all_cells ? Ptr{Int64}(C_NULL) : pointer(cells), all_cells ? 0 : length(cells),
+                    nk > 0 ? pointer(ksig) : Ptr{Int64}(C_NULL), nk > 0 ? pointer(kr) : Ptr{Float64}(C_NULL), nk, d + 1), c)
+    end
+    nv = Ref{Int64}(0); nr = Ref{Int64}(0); ml = Ref{Int64}(0)
+    check(ccall((:hvb_counts, LIB), Cint, (Ptr{Cvoid}, Ref{Int64}, Ref{Int64}, Ref{Int64}), c, nv, nr, ml), c)
+    # rows are copied out (hvb_fetch_vertices): push! keeps the signature vectors, they must not alias library memory
+    sig = Matrix{Int64}(undef, d + 1, nv[]); r = Matrix{Float64}(undef, d, nv[])
+    check(ccall((:hvb_fetch_vertices, LIB), Cint, (Ptr{Cvoid}, Ptr{Int64}, Ptr{Float64}), c, sig, r), c)
+    for v in 1:nv[]
+        push!(mesh, sig[:, v] => P(view(r, :, v)))                                     # abstractmesh.jl:111
+    end
+    if nr[] > 0
+        edge = Matrix{Int64}(undef, d, nr[]); rb = Matrix{Float64}(undef, d, nr[]); ru = similar(rb); node = Vector{Int64}(undef, nr[])
+        check(ccall((:hvb_fetch_rays, LIB), Cint, (Ptr{Cvoid}, Ptr{Int64}, Ptr{Float64}, Ptr{Float64}, Ptr{Int64}), c, edge, rb, ru, node), c)
+        for k in 1:nr[]
+            HighVoronoi.pushray!(mesh, edge[:, k], P(view(rb, :, k)), P(view(ru, :, k)), node[k])   # abstractmesh.jl:191
         end
-        if nr[] > 0
-            edge = Matrix{Int64}(undef, d, nr[]); rb = Matrix{Float64}(undef, d, nr[]); ru = similar(rb); node = Vector{Int64}(undef, nr[])
-            check(ccall((:hvb_fetch_rays, LIB), Cint, (Ptr{Cvoid}, Ptr{Int64}, Ptr{Float64}, Ptr{Float64}, Ptr{Int64}), c, edge, rb, ru, node), c)
-            for k in 1:nr[]
-                HighVoronoi.pushray!(mesh, Vector{Int64}(view(edge, :, k)), P(view(rb, :, k)), P(view(ru, :, k)), node[k])   # abstractmesh.jl:191
-            end
-        end
-    finally
-        ccall((:hvb_destroy, LIB), Cvoid, (Ptr{Cvoid},), c)
     end
     return mesh, searcher
 end

@@ -12,7 +12,7 @@ from conftest import ROOT, cuda_available
 def declared_symbols():
     src = open(os.path.join(ROOT, "include", "hvb200.h")).read()
     src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
-    return sorted(set(re.findall(r"\b(hvb_[a-z_]+)\s*\(", src)))
+    return sorted(set(re.findall(r"\b(hvb_[a-z_0-9]+)\s*\(", src)))
 
 
 def test_library_exports_every_declared_symbol(hvb):
@@ -31,7 +31,7 @@ def test_default_params_match_reference(hvb):
     assert (p.variance_tol, p.break_tol, p.b_nodes_tol, p.plane_tolerance, p.ray_tol) == (1e-15, 1e-5, 1e-7, 1e-12, 1e-12)
     assert p.method == hvb.RCStandard == hvb.RCNonGeneralHP and p.world == 1 and p.fp32_filter == 1 and p.sort_output == 1
     assert p.persistent == 3                  # the persistent walk with warp-aggregated atomics (include/hvb200.h)
-    assert ctypes.sizeof(hvb._abi.hvb_params) == 5 * 8 + 12 * 4 + 8 + 8 + 8
+    assert ctypes.sizeof(hvb._abi.hvb_params) == 5 * 8 + 12 * 4 + 8 + 8 + 8 + 8
     assert ctypes.sizeof(hvb._abi.hvb_stats_t) == 31 * 8
 
 

@@ -155,6 +155,24 @@ def test_every_tile_size_and_both_walk_modes(hvb, oracle, tile, persistent):
     assert_same_mesh(mesh.sig, mesh.r, o["sig"], o["r"], xs, COORD_TOL)
 
 
+def test_int32_wire_format_equals_int64(hvb):
+    """wire32: signatures and neighbour ids staged as int32 (hvb_view_vertices32 / hvb_view_neighbors32), same content;
+    the int64 calls keep working on the same context"""
+    xs = points(8000, 3, 17)
+    dom = hvb.cuboid(3, periodic=[])
+    a, _ = hvb.voronoi(xs, searcher=hvb.Raycast(xs, domain=dom, options=hvb.RaycastParameter(neighbors=1)))
+    s = hvb.Raycast(xs, domain=dom, options=hvb.RaycastParameter(wire32=1, neighbors=1))
+    b, _ = hvb.voronoi(xs, searcher=s, copy=False)
+    assert b.sig.dtype == np.int32 and np.array_equal(b.sig, a.sig) and np.array_equal(b.r, a.r)
+    off, ids = b.neighbors()
+    off0, ids0 = a.neighbors()
+    assert ids.dtype == np.int32 and np.array_equal(off, off0) and np.array_equal(ids, ids0)
+    c = hvb.VoronoiMesh(s, copy=True)                     # int64 fetch on the wire32 context
+    assert c.sig.dtype == np.int64 and np.array_equal(c.sig, a.sig)
+    off2, ids2 = c.neighbors()
+    assert np.array_equal(ids2, ids0)
+
+
 def test_context_reuse_set_points(hvb, oracle):
     """hvb_set_points: one context, several clouds of different sizes, results independent of the history"""
     base, normal = qhull_oracle.cuboid(3)

@@ -1,14 +1,16 @@
 """Aggregates an `ncu --page source --csv --print-source cuda,sass` dump by code region of hvb_core.cuh / hvb_kernels.cuh.
 usage: python tools/srcregions.py dump.csv   (line ranges below match the sources of the commit the dump was taken at)"""
 import csv, sys, collections
-REG = [("hvb_core.cuh", 202, 223, "load_x32"), ("hvb_core.cuh", 231, 250, "hash/edge_slot"), ("hvb_core.cuh", 254, 313, "ortho_direction/dot"),
-       ("hvb_core.cuh", 327, 380, "best/verify64"), ("hvb_core.cuh", 382, 403, "make_filter"), ("hvb_core.cuh", 409, 517, "row_range32/row_try32"),
-       ("hvb_core.cuh", 518, 561, "row_range(fp64)"), ("hvb_core.cuh", 562, 666, "scan_points"), ("hvb_core.cuh", 667, 678, "settle_stage"),
-       ("hvb_core.cuh", 679, 711, "query: planes"), ("hvb_core.cuh", 712, 792, "query: stage setup"), ("hvb_core.cuh", 793, 896, "query: row loop"),
-       ("hvb_core.cuh", 897, 943, "vertex_insert"), ("hvb_core.cuh", 944, 1003, "edge_register"), ("hvb_core.cuh", 1004, 1081, "commit_vertex"),
-       ("hvb_core.cuh", 1082, 1216, "ray_setup/ray_result"), ("hvb_kernels.cuh", 418, 473, "k_walk loop"),
-       ("hvb_coop.cuh", 40, 84, "coop: row geometry"), ("hvb_coop.cuh", 85, 139, "coop: next_row (task fetch)"), ("hvb_coop.cuh", 140, 206, "coop: scan chunk + survivors"),
-       ("hvb_coop.cuh", 207, 326, "coop: stage setup / settle"), ("hvb_coop.cuh", 327, 462, "commit_vertex_warp"), ("hvb_coop.cuh", 463, 600, "k_walk_coop loop")]
+REG = [("hvb_core.cuh", 203, 228, "load_x32"), ("hvb_core.cuh", 236, 258, "hash/edge_slot"), ("hvb_core.cuh", 259, 322, "ortho_direction/dot"),
+       ("hvb_core.cuh", 323, 403, "best/verify64/tie_window"), ("hvb_core.cuh", 404, 431, "make_filter"), ("hvb_core.cuh", 432, 542, "row_range32/row_try32"),
+       ("hvb_core.cuh", 543, 587, "row_range(fp64)"), ("hvb_core.cuh", 588, 691, "scan_points"), ("hvb_core.cuh", 692, 702, "settle_stage"),
+       ("hvb_core.cuh", 703, 727, "query: planes"), ("hvb_core.cuh", 728, 816, "query: stage setup"), ("hvb_core.cuh", 817, 929, "query: row loop"),
+       ("hvb_core.cuh", 930, 974, "vertex_insert"), ("hvb_core.cuh", 975, 1033, "edge_register"), ("hvb_core.cuh", 1034, 1104, "commit_vertex"),
+       ("hvb_core.cuh", 1105, 1255, "ray_setup/ray_result"),
+       ("hvb_coop.cuh", 40, 88, "coop: row geometry"), ("hvb_coop.cuh", 89, 215, "coop_scan (row tickets)"),
+       ("hvb_coop.cuh", 216, 283, "pool: chunk filter + survivors"), ("hvb_coop.cuh", 284, 368, "pool: round setup + row slots"),
+       ("hvb_coop.cuh", 369, 384, "pool: chunk task emission"), ("hvb_coop.cuh", 385, 396, "pool: chunk loop"),
+       ("hvb_coop.cuh", 397, 520, "coop: stage setup / settle"), ("hvb_coop.cuh", 521, 657, "commit_vertex_warp"), ("hvb_coop.cuh", 658, 800, "k_walk_coop loop")]
 rows = list(csv.reader(open(sys.argv[1], newline='')))
 agg = collections.OrderedDict(); cur = None; hdr = None
 for r in rows:
