@@ -310,6 +310,9 @@ class Runner:
             kern_ms += st["ms_expand_kernel"]
             kern_launches += st["expand_launches"]
             h2d, d2h, stats_last = hb, db, st
+        if os.environ.get("HVB_BENCH_ALLRANKS"):
+            sys.stderr.write("[rank %d] %s %s\n" % (self.rank, self.name, json.dumps({k: round(float(stats_last[k]), 3) for k in (
+                "ms_build", "ms_upload", "ms_search", "ms_finalize", "ms_seed", "ms_neighbors", "ms_rows_sort", "ms_expand_kernel", "raycasts", "vertices")})))
         peak, peak_src = measured_peak()
         # roofline of the dominant kernel (the walk): algorithmic bytes per launch / average launch duration, this rank
         v_rank = stats_last["raycasts"] - stats_last["duplicate_hits"] if self.world > 1 else stats_last["vertices"]

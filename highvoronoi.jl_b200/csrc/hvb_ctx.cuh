@@ -224,7 +224,8 @@ struct Ctx : hvb_ctx {
         if (ev_nb) cudaEventDestroy(ev_nb);
         nbsc.release(); h_nbsc.release(); h_nbtotal.release(); own_mask.release();
         if (comm && comm_owned) Nccl::get().CommDestroy(comm);
-        xc_counts.release(); h_xc_counts.release(); xc_counts32.release(); h_xc_counts32.release(); xs_sig32.release(); xr_sig32.release(); xs_r.release(); xr_r.release(); xc_red.release(); h_xc_red.release();
+        xc_counts.release(); h_xc_counts.release(); xc_counts32.release(); h_xc_counts32.release(); xc_pair.release(); h_xc_pair.release(); h_xc_mine.release();
+        if (xstream) { cudaStreamDestroy(xstream); cudaEventDestroy(ev_x0); cudaEventDestroy(ev_x1); } xs_sig32.release(); xr_sig32.release(); xs_r.release(); xr_r.release(); xc_red.release(); h_xc_red.release();
         if (nstream) { cudaStreamSynchronize(nstream); cudaStreamDestroy(nstream); }
         if (sstream2) { cudaStreamSynchronize(sstream2); cudaStreamDestroy(sstream2); }
         if (ev_p0) cudaEventDestroy(ev_p0);
@@ -686,7 +687,7 @@ struct Ctx : hvb_ctx {
         if (world == 1) { memset(owned, 1, (size_t)n_list); return HVB_OK; }
         CK(cudaSetDevice(prm.device));
         CK(own_mask.ensure(n));
-        k_own_mask<<<blocks_for(n, 256), 256, 0, stream>>>(perm.p, (int)n, (int)(n * rank / world), (int)(n * (rank + 1) / world), own_mask.p); ++launches;
+        k_own_mask<<<blocks_for(n, 256), 256, 0, stream>>>(perm.p, (int)n, (int)slab_bound(rank), (int)slab_bound(rank + 1), own_mask.p); ++launches;
         CK(cudaMemcpyAsync(owned, own_mask.p, (size_t)n_list, cudaMemcpyDeviceToHost, stream));
         CK(cudaStreamSynchronize(stream));
         return HVB_OK;
@@ -815,7 +816,7 @@ struct Ctx : hvb_ctx {
             CK(cudaMemsetAsync(ctr.p, 0, sizeof(Counters), stream));
             CK(cudaMemsetAsync(sc.p, 0, sizeof(Scalars), stream));
             if (cells == nullptr) {
-                int lo = (int)(n * rank / world), hi = (int)(n * (rank + 1) / world);
+                int lo = (int)slab_bound(rank), hi = (int)slab_bound(rank + 1);
                 if (periodic) k_fill_active_orig<<<blocks_for(n, 256), 256, 0, stream>>>(active.p, perm.p, (int)n, (int)n_user, lo, hi);
                 else k_fill_active_range<<<blocks_for(n, 256), 256, 0, stream>>>(active.p, (int)n, lo, hi);
                 ++launches;
@@ -935,7 +936,7 @@ struct Ctx : hvb_ctx {
         own_ptr = nullptr;
         if (by_slab) {
             CK(own_mask.ensure(n));
-            k_own_mask<<<blocks_for(n, 256), 256, 0, stream>>>(perm.p, (int)n, (int)(n * rank / world), (int)(n * (rank + 1) / world), own_mask.p); ++launches;
+            k_own_mask<<<blocks_for(n, 256), 256, 0, stream>>>(perm.p, (int)n, (int)slab_bound(rank), (int)slab_bound(rank + 1), own_mask.p); ++launches;
             own_ptr = own_mask.p;
         }
         CK(cudaEventRecord(ev_b, stream));
@@ -963,9 +964,14 @@ struct Ctx : hvb_ctx {
         if (!ev_sd2) CK(cudaEventCreateWithFlags(&ev_sd2, cudaEventDisableTiming));
         CK(cudaEventRecord(ev_sd2, sstream2));
         CK(cudaStreamWaitEvent(stream, ev_sd2, 0));
+        if (counts_cached) CK(cudaStreamWaitEvent(stream, ev_x1, 0));
         CK(cudaEventRecord(ev_p1, stream));
         CK(cudaStreamSynchronize(stream));
         CK(cudaGetLastError());
+        if (counts_cached) {
+            for (int k = 0; k < world; ++k) h_xc_counts32.p[k] = h_xc_pair.p[2 * k];
+            if (prm.balance) rebalance(world);
+        }
         float ms = 0;
         cudaEventElapsedTime(&ms, ev_d, ev_p1); st.ms_stage_wait = ms;
         cudaEventElapsedTime(&ms, ev_a, ev_b); st.ms_search = ms;
@@ -976,6 +982,7 @@ struct Ctx : hvb_ctx {
         double kms = 0;
         for (size_t i = 0; i + 1 < n_ev; i += 2) { cudaEventElapsedTime(&ms, ev_pool[i], ev_pool[i + 1]); kms += ms; }
         st.ms_expand_kernel = kms; st.expand_launches = expand_launches; st.expand_items = items;
+        last_walk_ms = kms;
         const Counters& c = *h_ctr.p;
         st.vertices = nvert; st.unique_vertices = nvert; st.periodic_retries = 0; st.rays = nrays; st.raycasts = (int64_t)c.raycasts; st.duplicate_hits = (int64_t)c.dup_hits;
         st.closed_skips = (int64_t)c.closed_skips; st.candidates_fp32 = (int64_t)c.cand32; st.candidates_fp64 = (int64_t)c.cand64;
@@ -1030,7 +1037,7 @@ struct Ctx : hvb_ctx {
         if (nrec > 0) {
             // multi-GPU: only the vertices this rank owns; seed vertices (the caller's own) are not returned
             const int world = std::max(1, prm.world), rank = std::min(std::max(0, prm.rank), world - 1);
-            const int lo = by_slab ? (int)(n * rank / world) : 0, hi = by_slab ? (int)(n * (rank + 1) / world) : 0;
+            const int lo = by_slab ? (int)slab_bound(rank) : 0, hi = by_slab ? (int)slab_bound(rank + 1) : 0;
             k_final_rows<D><<<blocks_for(nrec, 128), 128, 0, stream>>>(dv, perm.p, nrec, bits, out_sig[0].p, out_r[0].p, key_top.p, key_hi.p, key_lo.p,
                                                                      &sc.p->out_count, &sc.p->max_var, lo, hi, seed_prefix,
                                                                      prm.variance_tol, prm.break_tol, sc.p->tol_counts, (int)n_user);
@@ -1039,19 +1046,28 @@ struct Ctx : hvb_ctx {
         if (nrays > 0) {
             CK(ray_edge.ensure((size_t)nrays * D)); CK(ray_base.ensure((size_t)nrays * D)); CK(ray_dir.ensure((size_t)nrays * D)); CK(ray_node.ensure(nrays));
             const int world = std::max(1, prm.world), rank = std::min(std::max(0, prm.rank), world - 1);
-            const int lo = by_slab ? (int)(n * rank / world) : 0, hi = by_slab ? (int)(n * (rank + 1) / world) : 0;
+            const int lo = by_slab ? (int)slab_bound(rank) : 0, hi = by_slab ? (int)slab_bound(rank + 1) : 0;
             k_final_rays<D><<<blocks_for(nrays, 128), 128, 0, stream>>>(dv, perm.p, (u32)nrays, ray_edge.p, ray_base.p, ray_dir.p, ray_node.p,
                                                                      lo, hi, &sc.p->ray_out);
             ++launches;
         }
-        // multi-GPU with a communicator: the shard sizes of all ranks travel now (ncclAllGather of one word, straight from
-        // the device counter) and are in host memory when this search returns: hvb_exchange_counts costs nothing
+        // multi-GPU with a communicator: the shard sizes of all ranks (and the walk times of the previous search, for the
+        // slab balance) travel now -- one ncclAllGather of two words per rank, on its own stream: a collective makes the
+        // fast ranks wait for the slowest one, and that wait must overlap the row sort and the neighbour lists instead of
+        // standing in front of them.  The numbers are in host memory when this search returns.
         counts_cached = false;
-        if (by_slab && comm) {
+        if (by_slab && comm && !getenv("HVB_NO_COUNT_XCHG")) {
             const int world = std::max(1, prm.world);
-            CK(xc_counts32.ensure(world)); CK(h_xc_counts32.ensure(world));
-            NK(Nccl::get().AllGather(&sc.p->out_count, xc_counts32.p, 1, ncclUint32, comm, stream));
-            CK(cudaMemcpyAsync(h_xc_counts32.p, xc_counts32.p, world * sizeof(u32), cudaMemcpyDeviceToHost, stream));
+            if (!xstream) { CK(cudaStreamCreateWithFlags(&xstream, cudaStreamNonBlocking)); CK(cudaEventCreateWithFlags(&ev_x0, cudaEventDisableTiming)); CK(cudaEventCreateWithFlags(&ev_x1, cudaEventDisableTiming)); }
+            CK(xc_counts32.ensure(2)); CK(xc_pair.ensure(2 * world)); CK(h_xc_pair.ensure(2 * world)); CK(h_xc_mine.ensure(1)); CK(h_xc_counts32.ensure(world));
+            h_xc_mine.p[0] = (u32)std::min(4.0e9, last_walk_ms * 1000.0);
+            CK(cudaEventRecord(ev_x0, stream));
+            CK(cudaStreamWaitEvent(xstream, ev_x0, 0));
+            CK(cudaMemcpyAsync(xc_counts32.p, &sc.p->out_count, sizeof(u32), cudaMemcpyDeviceToDevice, xstream));
+            CK(cudaMemcpyAsync(xc_counts32.p + 1, h_xc_mine.p, sizeof(u32), cudaMemcpyHostToDevice, xstream));
+            NK(Nccl::get().AllGather(xc_counts32.p, xc_pair.p, 2, ncclUint32, comm, xstream));
+            CK(cudaMemcpyAsync(h_xc_pair.p, xc_pair.p, 2 * world * sizeof(u32), cudaMemcpyDeviceToHost, xstream));
+            CK(cudaEventRecord(ev_x1, xstream));
             counts_cached = true;
         }
         int rc = read_scalars(); if (rc) return rc;
@@ -1295,10 +1311,44 @@ struct Ctx : hvb_ctx {
     // single-process multi-GPU context of hvb_create_multi attaches communicators made by ncclCommInitAll) -------------
     ncclComm_t comm = nullptr;
     bool comm_owned = false;
+    // slab k = sorted positions [slab_bound(k), slab_bound(k + 1)).  Equal counts by default (partition_indices,
+    // parallelmesh.jl:52-87); with a communicator and prm.balance the widths follow the walk times the ranks measured on
+    // the previous search of this context (boundary slabs hold cheaper cells in high dimensions: equal counts left the
+    // inner ranks of C4 with almost twice the work of the outer ones).  Every rank derives the same boundaries from the
+    // same gathered numbers.
+    std::vector<double> slab_f;
+    int64_t slab_bound(int k) const {
+        const int world = std::max(1, prm.world);
+        if (k <= 0) return 0;
+        if (k >= world) return n;
+        if (slab_f.empty()) return n * k / world;
+        return std::min<int64_t>(n, std::max<int64_t>(0, (int64_t)((double)n * slab_f[k])));
+    }
+    double last_walk_ms = 0;
+    cudaStream_t xstream = nullptr;
+    cudaEvent_t ev_x0 = nullptr, ev_x1 = nullptr;
+    void rebalance(int world) {
+        // h_xc_pair: {rows owned, walk time of the PREVIOUS search in microseconds} per rank
+        std::vector<double> t(world);
+        for (int k = 0; k < world; ++k) { t[k] = (double)h_xc_pair.p[2 * k + 1]; if (!(t[k] > 0)) return; }
+        if (slab_f.empty()) { slab_f.resize(world + 1); for (int k = 0; k <= world; ++k) slab_f[k] = (double)k / world; }
+        std::vector<double> w(world);
+        double sum = 0;
+        for (int k = 0; k < world; ++k) { w[k] = (slab_f[k + 1] - slab_f[k]) / t[k]; sum += w[k]; }
+        double acc = 0;
+        std::vector<double> f(world + 1, 0.0);
+        for (int k = 0; k < world; ++k) {
+            const double old_w = slab_f[k + 1] - slab_f[k];
+            double nw = 0.5 * old_w + 0.5 * w[k] / sum;                    // damped: the cost model is local, the clouds change
+            nw = std::max(nw, 0.25 / world);
+            acc += nw; f[k + 1] = acc;
+        }
+        for (int k = 0; k <= world; ++k) slab_f[k] = f[k] / acc;
+    }
     DBuf<long long> xc_counts;
     HBuf<long long> h_xc_counts;
-    DBuf<u32> xc_counts32;
-    HBuf<u32> h_xc_counts32;
+    DBuf<u32> xc_counts32, xc_pair;
+    HBuf<u32> h_xc_counts32, h_xc_pair, h_xc_mine;
     bool counts_cached = false;       // h_xc_counts32 holds the shard sizes of the current result (filled inside hvb_search)
     DBuf<int> xs_sig32, xr_sig32;
     DBuf<double> xs_r, xr_r, xc_red;

@@ -1,0 +1,12 @@
+#!/bin/bash
+cd "$GRAFT_REPO_ROOT" 2>/dev/null || cd /root/repo
+mkdir -p gpurun_out
+export HVB_BENCH_ALLRANKS=1
+run() { # name N extra...
+  name=$1; N=$2; shift 2
+  ( time python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port $((29530+RANDOM%100)) bench.py --gpus $N --steps 20 --warmup 5 "$@" ) > gpurun_out/scale2_$name.log 2>&1
+  echo "$name rc=$?"
+}
+run N8_bal 8
+run N8_nobal 8 --setting balance=0 --no-parity
+run N4_bal 4 --no-parity
