@@ -23,7 +23,7 @@ class hvb_params(ctypes.Structure):
                 ("fp32_filter", ctypes.c_int32), ("on_degenerate", ctypes.c_int32), ("points_per_cell", ctypes.c_int32),
                 ("seed_stride", ctypes.c_int32), ("sort_output", ctypes.c_int32), ("tile_size", ctypes.c_int32), ("neighbors", ctypes.c_int32), ("persistent", ctypes.c_int32),
                 ("vertex_capacity", ctypes.c_int64), ("probe_scale", ctypes.c_double), ("periodic_margin", ctypes.c_double),
-                ("wire32", ctypes.c_int32), ("balance", ctypes.c_int32)]
+                ("wire32", ctypes.c_int32), ("decomposition", ctypes.c_int32)]
 
 
 class hvb_stats_t(ctypes.Structure):

@@ -20,7 +20,7 @@ void hvb_default_params(hvb_params* p) {
     memset(p, 0, sizeof(*p));
     p->variance_tol = 1e-15; p->break_tol = 1e-5; p->b_nodes_tol = 1e-7; p->plane_tolerance = 1e-12; p->ray_tol = 1e-12;
     p->method = 0; p->device = 0; p->rank = 0; p->world = 1; p->fp32_filter = 1; p->on_degenerate = 0;
-    p->points_per_cell = 0; p->seed_stride = 0; p->sort_output = 1; p->neighbors = 0; p->persistent = 3; p->vertex_capacity = 0; p->probe_scale = 0.0; p->periodic_margin = 0.0; p->wire32 = 0; p->balance = 1;
+    p->points_per_cell = 0; p->seed_stride = 0; p->sort_output = 1; p->neighbors = 0; p->persistent = 3; p->vertex_capacity = 0; p->probe_scale = 0.0; p->periodic_margin = 0.0; p->wire32 = 0; p->decomposition = 1;
 }
 
 int hvb_create(hvb_ctx** out, int dim, int64_t n, const double* xs, int nplanes, const double* plane_base,

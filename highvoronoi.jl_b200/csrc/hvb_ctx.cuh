@@ -193,6 +193,12 @@ struct Ctx : hvb_ctx {
     // Neighbour lists are built for owned cells only (complete there); null = every cell
     DBuf<unsigned char> own_mask;
     const unsigned char* own_ptr = nullptr;
+    // multi-GPU decomposition (hvb_kernels.cuh, BlockSpec): rank per sorted position, built with the index
+    DBuf<unsigned char> owner;
+    const unsigned char* owner_ptr = nullptr;          // null: world == 1
+    DBuf<unsigned int> marg;
+    HBuf<unsigned int> h_marg;
+    BlockSpec bspec;
     std::vector<cudaEvent_t> ev_pool;
     cudaEvent_t ev_up = nullptr;
     cudaEvent_t ev_a = nullptr, ev_b = nullptr, ev_c = nullptr, ev_d = nullptr, ev_s0 = nullptr, ev_s1 = nullptr, ev_n0 = nullptr, ev_n1 = nullptr;
@@ -222,9 +228,9 @@ struct Ctx : hvb_ctx {
         if (ev_n1) cudaEventDestroy(ev_n1);
         if (ev_stage) cudaEventDestroy(ev_stage);
         if (ev_nb) cudaEventDestroy(ev_nb);
-        nbsc.release(); h_nbsc.release(); h_nbtotal.release(); own_mask.release();
+        nbsc.release(); h_nbsc.release(); h_nbtotal.release(); own_mask.release(); owner.release(); marg.release(); h_marg.release();
         if (comm && comm_owned) Nccl::get().CommDestroy(comm);
-        xc_counts.release(); h_xc_counts.release(); xc_counts32.release(); h_xc_counts32.release(); xc_pair.release(); h_xc_pair.release(); h_xc_mine.release();
+        xc_counts.release(); h_xc_counts.release(); xc_counts32.release(); h_xc_counts32.release();
         if (xstream) { cudaStreamDestroy(xstream); cudaEventDestroy(ev_x0); cudaEventDestroy(ev_x1); } xs_sig32.release(); xr_sig32.release(); xs_r.release(); xr_r.release(); xc_red.release(); h_xc_red.release();
         if (nstream) { cudaStreamSynchronize(nstream); cudaStreamDestroy(nstream); }
         if (sstream2) { cudaStreamSynchronize(sstream2); cudaStreamDestroy(sstream2); }
@@ -459,6 +465,7 @@ struct Ctx : hvb_ctx {
         k_scatter<D><<<blocks_for(n, 256), 256, 0, stream>>>(dv, xs_in.p, cell_of.p, cell_start.p, cell_cur.p, x64.p, x32.p, perm.p); ++launches;
         k_cell_sort<<<blocks_for(ncells, 256), 256, 0, stream>>>(cell_start.p, (int)ncells, perm.p); ++launches;
         k_gather_points<D><<<blocks_for(n, 256), 256, 0, stream>>>(dv, xs_in.p, perm.p, x64.p, x32.p, inv.p); ++launches;
+        { int rc = assign_owners(); if (rc) return rc; }
         CK(cudaEventRecord(ev_b, stream));
         CK(cudaStreamSynchronize(stream));
         CK(cudaGetLastError());
@@ -468,6 +475,70 @@ struct Ctx : hvb_ctx {
         st.ms_upload = 0;                                 // (a periodic margin retry re-records ev_a: no upload in that build)
         if (cudaEventElapsedTime(&ms, ev_a, ev_up) == cudaSuccess && ms > 0 && ms <= st.ms_build) st.ms_upload = ms;
         st.halo_nodes = n_halo;
+        return HVB_OK;
+    }
+
+    // which rank explores which cell (world > 1): slabs of the sorted order or blocks of the grid, see BlockSpec
+    int assign_owners() {
+        const int world = std::max(1, prm.world);
+        owner_ptr = nullptr;
+        if (world == 1) return HVB_OK;
+        if (world > 64) { err = "at most 64 ranks"; return HVB_EINVAL; }
+        memset(&bspec, 0, sizeof(bspec));
+        bspec.world = world; bspec.mode = prm.decomposition ? 1 : 0;
+        for (int a = 0; a < 3; ++a) bspec.m[a] = 1;
+        if (bspec.mode == 1) {
+            // factorise world over the first min(D, 3) axes: every prime factor goes to the axis whose parts are still the
+            // thickest in cells (2 x 2 x 2 for 8 ranks in a cube)
+            int w = world;
+            const int A = std::min(D, 3);
+            for (int f = 2; w > 1; ) {
+                if (w % f) { ++f; continue; }
+                int best = 0; double thick = -1;
+                for (int a = 0; a < A; ++a) { const double t = (double)dv.g[a] / bspec.m[a]; if (t > thick) { thick = t; best = a; } }
+                bspec.m[best] *= f; w /= f;
+            }
+            bool ok = true;
+            for (int a = 0; a < A; ++a) ok &= (bspec.m[a] <= 16 && bspec.m[a] <= dv.g[a]);
+            if (!ok) bspec.mode = 0;                       // a grid too coarse to cut that way: slabs
+        }
+        if (bspec.mode == 1) {
+            // cuts at the quantiles of the marginal point counts (equal counts per part for product-like densities)
+            const int A = std::min(D, 3);
+            size_t tot = 0;
+            for (int a = 0; a < A; ++a) tot += (size_t)dv.g[a];
+            CK(marg.ensure(tot)); CK(h_marg.ensure(tot));
+            CK(cudaMemsetAsync(marg.p, 0, tot * sizeof(unsigned int), stream));
+            size_t off = 0; long long nprefix = 1;
+            for (int a = 0; a < A; ++a) {
+                nprefix *= dv.g[a];
+                if (bspec.m[a] > 1) {
+                    k_marginal<<<blocks_for(nprefix, 256), 256, 0, stream>>>(cell_start.p, nprefix, ncells / nprefix, dv.g[a], marg.p + off); ++launches;
+                }
+                off += dv.g[a];
+            }
+            CK(cudaMemcpyAsync(h_marg.p, marg.p, tot * sizeof(unsigned int), cudaMemcpyDeviceToHost, stream));
+            CK(cudaStreamSynchronize(stream));
+            off = 0;
+            for (int a = 0; a < A; ++a) {
+                const int m = bspec.m[a], g = dv.g[a];
+                bspec.cut[a][0] = 0; bspec.cut[a][m] = g;
+                if (m > 1) {
+                    long long acc = 0; int j = 1;
+                    for (int c = 0; c < g && j < m; ++c) {
+                        acc += h_marg.p[off + c];
+                        while (j < m && acc * m >= (long long)n * j) { bspec.cut[a][j] = std::min(g - (m - j), std::max(c + 1, bspec.cut[a][j - 1] + 1)); ++j; }
+                    }
+                    for (; j < m; ++j) bspec.cut[a][j] = std::min(g - (m - j), bspec.cut[a][j - 1] + 1);
+                }
+                off += g;
+            }
+        } else {
+            for (int k = 0; k <= world; ++k) bspec.bound[k] = n * k / world;       // partition_indices, parallelmesh.jl:52-87
+        }
+        CK(owner.ensure(n));
+        k_assign_owner<D><<<blocks_for(n, 256), 256, 0, stream>>>(dv, perm.p, cell_of.p, bspec, owner.p); ++launches;
+        owner_ptr = owner.p;
         return HVB_OK;
     }
 
@@ -687,7 +758,7 @@ struct Ctx : hvb_ctx {
         if (world == 1) { memset(owned, 1, (size_t)n_list); return HVB_OK; }
         CK(cudaSetDevice(prm.device));
         CK(own_mask.ensure(n));
-        k_own_mask<<<blocks_for(n, 256), 256, 0, stream>>>(perm.p, (int)n, (int)slab_bound(rank), (int)slab_bound(rank + 1), own_mask.p); ++launches;
+        k_own_mask<<<blocks_for(n, 256), 256, 0, stream>>>(perm.p, (int)n, owner_ptr, rank, own_mask.p); ++launches;
         CK(cudaMemcpyAsync(owned, own_mask.p, (size_t)n_list, cudaMemcpyDeviceToHost, stream));
         CK(cudaStreamSynchronize(stream));
         return HVB_OK;
@@ -801,7 +872,7 @@ struct Ctx : hvb_ctx {
         const int world = std::max(1, prm.world), rank = std::min(std::max(0, prm.rank), world - 1);
         // a slab context stores what touches its slab: 1/world of the vertices plus the layer both neighbours find too
         // (tables are memset every search: over-sizing them by `world` is what made the replicated part of a step grow)
-        if (world > 1 && cells == nullptr && prm.vertex_capacity <= 0) cap = (int64_t)(cap * std::min(1.0, (D <= 3 ? 1.6 : 2.5) / world + 0.04)) + 4096;
+        if (world > 1 && cells == nullptr && prm.vertex_capacity <= 0) cap = (int64_t)(cap * std::min(1.0, (D <= 3 ? 1.8 : 3.0) / world + 0.04)) + 4096;
         if (vcap >= cap) cap = vcap;
         int retries = 0;
         launches = 0;
@@ -816,9 +887,7 @@ struct Ctx : hvb_ctx {
             CK(cudaMemsetAsync(ctr.p, 0, sizeof(Counters), stream));
             CK(cudaMemsetAsync(sc.p, 0, sizeof(Scalars), stream));
             if (cells == nullptr) {
-                int lo = (int)slab_bound(rank), hi = (int)slab_bound(rank + 1);
-                if (periodic) k_fill_active_orig<<<blocks_for(n, 256), 256, 0, stream>>>(active.p, perm.p, (int)n, (int)n_user, lo, hi);
-                else k_fill_active_range<<<blocks_for(n, 256), 256, 0, stream>>>(active.p, (int)n, lo, hi);
+                k_fill_active_owner<<<blocks_for(n, 256), 256, 0, stream>>>(active.p, owner_ptr, perm.p, (int)n, (int)(periodic ? n_user : n), rank);
                 ++launches;
             } else {
                 CK(cells_dev.ensure(ncells_in));
@@ -936,7 +1005,7 @@ struct Ctx : hvb_ctx {
         own_ptr = nullptr;
         if (by_slab) {
             CK(own_mask.ensure(n));
-            k_own_mask<<<blocks_for(n, 256), 256, 0, stream>>>(perm.p, (int)n, (int)slab_bound(rank), (int)slab_bound(rank + 1), own_mask.p); ++launches;
+            k_own_mask<<<blocks_for(n, 256), 256, 0, stream>>>(perm.p, (int)n, owner_ptr, rank, own_mask.p); ++launches;
             own_ptr = own_mask.p;
         }
         CK(cudaEventRecord(ev_b, stream));
@@ -968,10 +1037,6 @@ struct Ctx : hvb_ctx {
         CK(cudaEventRecord(ev_p1, stream));
         CK(cudaStreamSynchronize(stream));
         CK(cudaGetLastError());
-        if (counts_cached) {
-            for (int k = 0; k < world; ++k) h_xc_counts32.p[k] = h_xc_pair.p[2 * k];
-            if (prm.balance) rebalance(world);
-        }
         float ms = 0;
         cudaEventElapsedTime(&ms, ev_d, ev_p1); st.ms_stage_wait = ms;
         cudaEventElapsedTime(&ms, ev_a, ev_b); st.ms_search = ms;
@@ -982,7 +1047,6 @@ struct Ctx : hvb_ctx {
         double kms = 0;
         for (size_t i = 0; i + 1 < n_ev; i += 2) { cudaEventElapsedTime(&ms, ev_pool[i], ev_pool[i + 1]); kms += ms; }
         st.ms_expand_kernel = kms; st.expand_launches = expand_launches; st.expand_items = items;
-        last_walk_ms = kms;
         const Counters& c = *h_ctr.p;
         st.vertices = nvert; st.unique_vertices = nvert; st.periodic_retries = 0; st.rays = nrays; st.raycasts = (int64_t)c.raycasts; st.duplicate_hits = (int64_t)c.dup_hits;
         st.closed_skips = (int64_t)c.closed_skips; st.candidates_fp32 = (int64_t)c.cand32; st.candidates_fp64 = (int64_t)c.cand64;
@@ -1037,36 +1101,31 @@ struct Ctx : hvb_ctx {
         if (nrec > 0) {
             // multi-GPU: only the vertices this rank owns; seed vertices (the caller's own) are not returned
             const int world = std::max(1, prm.world), rank = std::min(std::max(0, prm.rank), world - 1);
-            const int lo = by_slab ? (int)slab_bound(rank) : 0, hi = by_slab ? (int)slab_bound(rank + 1) : 0;
             k_final_rows<D><<<blocks_for(nrec, 128), 128, 0, stream>>>(dv, perm.p, nrec, bits, out_sig[0].p, out_r[0].p, key_top.p, key_hi.p, key_lo.p,
-                                                                     &sc.p->out_count, &sc.p->max_var, lo, hi, seed_prefix,
+                                                                     &sc.p->out_count, &sc.p->max_var, by_slab ? owner_ptr : nullptr, rank, seed_prefix,
                                                                      prm.variance_tol, prm.break_tol, sc.p->tol_counts, (int)n_user);
             ++launches;
         }
         if (nrays > 0) {
             CK(ray_edge.ensure((size_t)nrays * D)); CK(ray_base.ensure((size_t)nrays * D)); CK(ray_dir.ensure((size_t)nrays * D)); CK(ray_node.ensure(nrays));
             const int world = std::max(1, prm.world), rank = std::min(std::max(0, prm.rank), world - 1);
-            const int lo = by_slab ? (int)slab_bound(rank) : 0, hi = by_slab ? (int)slab_bound(rank + 1) : 0;
             k_final_rays<D><<<blocks_for(nrays, 128), 128, 0, stream>>>(dv, perm.p, (u32)nrays, ray_edge.p, ray_base.p, ray_dir.p, ray_node.p,
-                                                                     lo, hi, &sc.p->ray_out);
+                                                                     by_slab ? owner_ptr : nullptr, rank, &sc.p->ray_out);
             ++launches;
         }
-        // multi-GPU with a communicator: the shard sizes of all ranks (and the walk times of the previous search, for the
-        // slab balance) travel now -- one ncclAllGather of two words per rank, on its own stream: a collective makes the
+        // multi-GPU with a communicator: the shard sizes of all ranks travel now -- one ncclAllGather of one word per rank,
+        // straight from the device counter, on its own stream: a collective makes the
         // fast ranks wait for the slowest one, and that wait must overlap the row sort and the neighbour lists instead of
         // standing in front of them.  The numbers are in host memory when this search returns.
         counts_cached = false;
         if (by_slab && comm && !getenv("HVB_NO_COUNT_XCHG")) {
             const int world = std::max(1, prm.world);
             if (!xstream) { CK(cudaStreamCreateWithFlags(&xstream, cudaStreamNonBlocking)); CK(cudaEventCreateWithFlags(&ev_x0, cudaEventDisableTiming)); CK(cudaEventCreateWithFlags(&ev_x1, cudaEventDisableTiming)); }
-            CK(xc_counts32.ensure(2)); CK(xc_pair.ensure(2 * world)); CK(h_xc_pair.ensure(2 * world)); CK(h_xc_mine.ensure(1)); CK(h_xc_counts32.ensure(world));
-            h_xc_mine.p[0] = (u32)std::min(4.0e9, last_walk_ms * 1000.0);
+            CK(xc_counts32.ensure(world)); CK(h_xc_counts32.ensure(world));
             CK(cudaEventRecord(ev_x0, stream));
             CK(cudaStreamWaitEvent(xstream, ev_x0, 0));
-            CK(cudaMemcpyAsync(xc_counts32.p, &sc.p->out_count, sizeof(u32), cudaMemcpyDeviceToDevice, xstream));
-            CK(cudaMemcpyAsync(xc_counts32.p + 1, h_xc_mine.p, sizeof(u32), cudaMemcpyHostToDevice, xstream));
-            NK(Nccl::get().AllGather(xc_counts32.p, xc_pair.p, 2, ncclUint32, comm, xstream));
-            CK(cudaMemcpyAsync(h_xc_pair.p, xc_pair.p, 2 * world * sizeof(u32), cudaMemcpyDeviceToHost, xstream));
+            NK(Nccl::get().AllGather(&sc.p->out_count, xc_counts32.p, 1, ncclUint32, comm, xstream));
+            CK(cudaMemcpyAsync(h_xc_counts32.p, xc_counts32.p, world * sizeof(u32), cudaMemcpyDeviceToHost, xstream));
             CK(cudaEventRecord(ev_x1, xstream));
             counts_cached = true;
         }
@@ -1186,7 +1245,7 @@ struct Ctx : hvb_ctx {
         // slots = 2 x that estimate (the estimate itself is ~1.3 x the Poisson-Voronoi mean): load <= 0.4, and the
         // memset + the fill pass touch a quarter of what an entry-per-list-element table would need
         // (slab contexts build the lists of their own cells only: 1/world of the cells plus the pairs that cross the slab faces)
-        const double own_frac = own_ptr ? std::min(1.0, 1.5 / std::max(1, prm.world) + 0.02) : 1.0;
+        const double own_frac = own_ptr ? std::min(1.0, 1.7 / std::max(1, prm.world) + 0.03) : 1.0;
         nb_want = next_pow2((u64)std::min(nrows * D * (D + 1) / 2.0 * 2.0, (double)n_list * own_frac * nb_est[D]) + 1024);
         size_t tmp_bytes = 0;
         CK(cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, nb_off.p, nb_off.p, (int)(n + 1), stream));
@@ -1311,44 +1370,12 @@ struct Ctx : hvb_ctx {
     // single-process multi-GPU context of hvb_create_multi attaches communicators made by ncclCommInitAll) -------------
     ncclComm_t comm = nullptr;
     bool comm_owned = false;
-    // slab k = sorted positions [slab_bound(k), slab_bound(k + 1)).  Equal counts by default (partition_indices,
-    // parallelmesh.jl:52-87); with a communicator and prm.balance the widths follow the walk times the ranks measured on
-    // the previous search of this context (boundary slabs hold cheaper cells in high dimensions: equal counts left the
-    // inner ranks of C4 with almost twice the work of the outer ones).  Every rank derives the same boundaries from the
-    // same gathered numbers.
-    std::vector<double> slab_f;
-    int64_t slab_bound(int k) const {
-        const int world = std::max(1, prm.world);
-        if (k <= 0) return 0;
-        if (k >= world) return n;
-        if (slab_f.empty()) return n * k / world;
-        return std::min<int64_t>(n, std::max<int64_t>(0, (int64_t)((double)n * slab_f[k])));
-    }
-    double last_walk_ms = 0;
     cudaStream_t xstream = nullptr;
     cudaEvent_t ev_x0 = nullptr, ev_x1 = nullptr;
-    void rebalance(int world) {
-        // h_xc_pair: {rows owned, walk time of the PREVIOUS search in microseconds} per rank
-        std::vector<double> t(world);
-        for (int k = 0; k < world; ++k) { t[k] = (double)h_xc_pair.p[2 * k + 1]; if (!(t[k] > 0)) return; }
-        if (slab_f.empty()) { slab_f.resize(world + 1); for (int k = 0; k <= world; ++k) slab_f[k] = (double)k / world; }
-        std::vector<double> w(world);
-        double sum = 0;
-        for (int k = 0; k < world; ++k) { w[k] = (slab_f[k + 1] - slab_f[k]) / t[k]; sum += w[k]; }
-        double acc = 0;
-        std::vector<double> f(world + 1, 0.0);
-        for (int k = 0; k < world; ++k) {
-            const double old_w = slab_f[k + 1] - slab_f[k];
-            double nw = 0.5 * old_w + 0.5 * w[k] / sum;                    // damped: the cost model is local, the clouds change
-            nw = std::max(nw, 0.25 / world);
-            acc += nw; f[k + 1] = acc;
-        }
-        for (int k = 0; k <= world; ++k) slab_f[k] = f[k] / acc;
-    }
     DBuf<long long> xc_counts;
     HBuf<long long> h_xc_counts;
-    DBuf<u32> xc_counts32, xc_pair;
-    HBuf<u32> h_xc_counts32, h_xc_pair, h_xc_mine;
+    DBuf<u32> xc_counts32;
+    HBuf<u32> h_xc_counts32;
     bool counts_cached = false;       // h_xc_counts32 holds the shard sizes of the current result (filled inside hvb_search)
     DBuf<int> xs_sig32, xr_sig32;
     DBuf<double> xs_r, xr_r, xc_red;

@@ -179,9 +179,59 @@ static __global__ void k_gather_points(Dev<D> dv, const double* __restrict__ xs,
 }
 
 // active[g] = 1 for the sorted positions of this context's slab (parallelmesh.jl:52-87) or of the Iter cells
-static __global__ void k_fill_active_range(unsigned char* active, int n, int lo, int hi) {
+// ------------------------------------------------------------------------------------------------------------
+// multi-GPU decomposition: owner[p] = rank that explores the cell of sorted position p.
+//   slabs  (decomposition 0): contiguous ranges of the sorted order with equal counts -- partition_indices,
+//           parallelmesh.jl:52-87.  The order is cell-linear with axis 0 slowest, so these are slabs across axis 0.
+//   blocks (decomposition 1): the grid is cut along up to three axes (m[0] x m[1] x m[2] = world) at the quantiles of the
+//           marginal point counts.  A rank finds every vertex that touches its cells, so the layer of vertices two
+//           neighbouring ranks both find grows with the SURFACE of a part: 8 slabs have 14 faces of full cross-section,
+//           2 x 2 x 2 blocks have 6 -- and all blocks of a cube are corner blocks, alike in their share of cheap boundary
+//           cells (with slabs the two end ranks of C4 had 2/3 of the work of the inner ones).
+// ------------------------------------------------------------------------------------------------------------
+struct BlockSpec {
+    int mode;                 // 0 slabs, 1 blocks
+    int world;
+    int m[3];                 // parts along axes 0, 1, 2 (1 = axis not cut)
+    int cut[3][17];           // blocks: cell coordinate where part j of axis a begins (cut[a][0] = 0, cut[a][m] = g[a])
+    long long bound[65];      // slabs: sorted position where slab k begins (bound[world] = n)
+};
+// marginal point count along axis a: thread q runs over the cell prefixes (c_0 .. c_a); the cells behind one prefix
+// are a contiguous range of cell_start
+static __global__ void k_marginal(const int* __restrict__ cell_start, long long nprefix, long long stride, int ga, unsigned int* __restrict__ hist) {
+    long long q = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (q >= nprefix) return;
+    const int cnt = cell_start[(q + 1) * stride] - cell_start[q * stride];
+    if (cnt) atomicAdd(hist + (int)(q % ga), (unsigned int)cnt);
+}
+template <int D>
+static __global__ void k_assign_owner(Dev<D> dv, const int* __restrict__ perm, const int* __restrict__ cell_of, BlockSpec bs,
+                               unsigned char* __restrict__ owner) {
+    int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= dv.n) return;
+    int r = 0;
+    if (bs.mode == 0) {
+        while (r + 1 < bs.world && (long long)p >= bs.bound[r + 1]) ++r;
+    } else {
+        int c = cell_of[perm[p]];
+        int cc[D];
+#pragma unroll
+        for (int k = D - 1; k >= 0; --k) { cc[k] = c % dv.g[k]; c /= dv.g[k]; }
+#pragma unroll
+        for (int a = 0; a < 3; ++a) {
+            if (a >= D) break;
+            int b = 0;
+            while (b + 1 < bs.m[a] && cc[a] >= bs.cut[a][b + 1]) ++b;
+            r = r * bs.m[a] + b;
+        }
+    }
+    owner[p] = (unsigned char)r;
+}
+// active[p] = 1 for the sorted positions this rank explores (periodic contexts: the caller's own generators only)
+static __global__ void k_fill_active_owner(unsigned char* active, const unsigned char* __restrict__ owner, const int* __restrict__ perm,
+                                    int n, int n_user, int rank) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) active[i] = (i >= lo && i < hi) ? 1 : 0;
+    if (i < n) active[i] = ((owner ? owner[i] == rank : true) && perm[i] < n_user) ? 1 : 0;
 }
 static __global__ void k_inverse_perm(const int* __restrict__ perm, int* __restrict__ inv, int n) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -262,11 +312,7 @@ static __global__ void k_halo(const double* xs, int n_user, HaloSpec hs, const P
     if (!xs_out) counts[i] = cnt;
 }
 
-// active[g] = 1 for the caller's own generators (not the halo) inside the slab of sorted positions [lo, hi)
-static __global__ void k_fill_active_orig(unsigned char* active, const int* __restrict__ perm, int n, int n_user, int lo, int hi) {
-    int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) active[i] = (i >= lo && i < hi && perm[i] < n_user) ? 1 : 0;
-}
+
 
 // Certificate of a periodic result.  A vertex that touches one of the caller's generators is a vertex of the
 // periodic tessellation if its (empty) ball stays inside the pushed periodic planes: then no periodic image that was
@@ -516,21 +562,21 @@ template <int D>
 static __global__ void k_final_rows(Dev<D> dv, const int* __restrict__ perm, u32 nrec, int bits,
                              long long* __restrict__ out_sig, double* __restrict__ out_r,
                              u64* __restrict__ key_top, u64* __restrict__ key_hi, u64* __restrict__ key_lo, u32* __restrict__ out_count,
-                             double* __restrict__ max_var, int own_lo, int own_hi, u32 skip_below,
+                             double* __restrict__ max_var, const unsigned char* __restrict__ owner, int rank, u32 skip_below,
                              double variance_tol, double break_tol, u32* __restrict__ tol_counts, int n_user) {
     u32 v = blockIdx.x * blockDim.x + threadIdx.x;
     if (v >= nrec || v < skip_below) return;          // records below skip_below are the caller's own (seed) vertices
     const int* s = dv.vsig + (size_t)v * (D + 1);
     if (s[0] < 0) return;
-    // multi-GPU ownership rule: a vertex belongs to the slab that holds its first generator in grid order (s is
-    // sorted by internal = grid-order id); every rank finds all vertices it owns, so the owned sets are disjoint
-    // and their union is the full set -- a deterministic dedup that needs no communication
+    // multi-GPU ownership rule: a vertex belongs to the rank that explores the cell of its first generator in grid order
+    // (s is sorted by internal = grid-order id); every rank finds all vertices that touch its cells, so the owned sets
+    // are disjoint and their union is the full set -- a deterministic dedup that needs no communication
     // (periodic contexts: the first generator that is one of the CALLER's -- halo copies belong to no slab)
-    if (own_hi > own_lo) {
+    if (owner) {
         int first = -1;
 #pragma unroll
         for (int k = D; k >= 0; --k) { const int id = s[k]; if (id < dv.n && perm[id] < n_user) first = id; }
-        if (first < own_lo || first >= own_hi) return;
+        if (first < 0 || owner[first] != rank) return;
     }
     int in[D + 1];
     long long og[D + 1];
@@ -594,7 +640,7 @@ static __global__ void k_gather_rows(const long long* __restrict__ sig_in, const
 template <int D>
 static __global__ void k_final_rays(Dev<D> dv, const int* __restrict__ perm, u32 nrays,
                              long long* __restrict__ edge, double* __restrict__ base, double* __restrict__ dir, long long* __restrict__ node,
-                             int own_lo, int own_hi, u32* __restrict__ out_count) {
+                             const unsigned char* __restrict__ owner, int rank, u32* __restrict__ out_count) {
     u32 i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= nrays) return;
     u32 it = dv.ray_item[i];
@@ -607,11 +653,11 @@ static __global__ void k_final_rays(Dev<D> dv, const int* __restrict__ perm, u32
         first = min(first, id);
         e[c++] = ((id < dv.n) ? (long long)perm[id] : (long long)id) + 1;
     }
-    // multi-GPU slabs: an unbounded edge belongs to the slab of its first generator in grid order (every rank whose
-    // slab touches the edge walks it)
+    // multi-GPU: an unbounded edge belongs to the rank of its first generator in grid order (every rank whose cells
+    // touch the edge walks it)
     u32 o = i;
-    if (own_hi > own_lo) {
-        if (first < own_lo || first >= own_hi) return;
+    if (owner) {
+        if (owner[first] != rank) return;
         o = atomicAdd(out_count, 1u);
     }
     for (int a = 1; a < D; ++a) { long long key = e[a]; int b = a - 1; while (b >= 0 && e[b] > key) { e[b + 1] = e[b]; --b; } e[b + 1] = key; }
@@ -728,10 +774,10 @@ static __global__ void k_pair_fill(const u64* __restrict__ ptab, u64 nslots, lon
     if (b <= n && (!own || own[b - 1])) ids[off[b - 1] + atomicAdd(cursor + (b - 1), 1u)] = a;
 }
 
-// own[c] = 1 for the caller cells whose sorted position lies in the slab [lo, hi) of this context
-static __global__ void k_own_mask(const int* __restrict__ perm, int n, int lo, int hi, unsigned char* __restrict__ own) {
+// own[c] = 1 for the caller cells this context explores
+static __global__ void k_own_mask(const int* __restrict__ perm, int n, const unsigned char* __restrict__ owner, int rank, unsigned char* __restrict__ own) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) own[perm[i]] = (i >= lo && i < hi) ? 1 : 0;
+    if (i < n) own[perm[i]] = (!owner || owner[i] == rank) ? 1 : 0;
 }
 
 static __global__ void k_sort_lists(const long long* __restrict__ off, long long* __restrict__ ids, long long n) {

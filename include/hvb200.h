@@ -88,9 +88,11 @@ typedef struct hvb_params {
     int32_t wire32;           /* 1: hvb_search stages signatures and neighbour ids in page-locked memory as int32 (read them
                                  with hvb_view_vertices32 / hvb_view_neighbors32): 4 bytes per id less over PCIe.  The int64
                                  calls keep working (they stage the int64 form on first use).  Default 0. */
-    int32_t balance;          /* world > 1 with a communicator: 1 (default) = the slab widths follow the walk times the ranks
-                                 measured on the previous search of this context (all-gathered with the shard sizes);
-                                 0 = equal counts per slab, always (partition_indices, parallelmesh.jl:52-87) */
+    int32_t decomposition;    /* world > 1: which cells a rank explores.  0 = contiguous slabs of the spatially sorted order
+                                 with equal counts (partition_indices, parallelmesh.jl:52-87: slabs across axis 0);
+                                 1 (default) = blocks: the grid is cut along up to three axes (2 x 2 x 2 for 8 ranks) at the
+                                 quantiles of the marginal point counts -- less surface between ranks, hence fewer vertices
+                                 found twice, and equal shares of the cheap boundary cells.  Same result either way. */
 } hvb_params;
 
 typedef struct hvb_stats_t {

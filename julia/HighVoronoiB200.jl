@@ -48,7 +48,7 @@ mutable struct HvbParams
     fp32_filter::Int32; on_degenerate::Int32; points_per_cell::Int32; seed_stride::Int32; sort_output::Int32
     tile_size::Int32; neighbors::Int32; persistent::Int32
     vertex_capacity::Int64; probe_scale::Cdouble; periodic_margin::Cdouble
-    wire32::Int32; balance::Int32
+    wire32::Int32; decomposition::Int32
     HvbParams() = new()
 end
 

@@ -104,8 +104,8 @@ def test_iter_subset_finds_all_vertices_of_the_cells(hvb, oracle):
     assert want <= got <= {tuple(r) for r in o["sig"].tolist()}
 
 
-@pytest.mark.parametrize("nb_in_search", [1, 0])
-def test_slab_union_equals_full(hvb, oracle, nb_in_search):
+@pytest.mark.parametrize("nb_in_search,decomposition,world", [(1, 1, 4), (0, 1, 4), (1, 0, 4), (1, 1, 8), (1, 1, 6)])
+def test_slab_union_equals_full(hvb, oracle, nb_in_search, decomposition, world):
     """the multi-GPU decomposition on one device: the union of the slab searches is the full vertex set, and every rank
     holds the complete neighbour lists of the cells it owns (empty lists elsewhere)"""
     xs = points(6000, 3, 10)
@@ -113,14 +113,16 @@ def test_slab_union_equals_full(hvb, oracle, nb_in_search):
     o = oracle.run(xs, base, normal)
     rows, total = set(), 0
     owned_by = np.zeros(6000, dtype=int)
-    for rank in range(4):
-        s = hvb.Raycast(xs, domain=hvb.cuboid(3, periodic=[]), options=hvb.RaycastParameter(threading=hvb.B200Thread(0, rank, 4), neighbors=nb_in_search))
+    for rank in range(world):
+        s = hvb.Raycast(xs, domain=hvb.cuboid(3, periodic=[]),
+                        options=hvb.RaycastParameter(threading=hvb.B200Thread(0, rank, world), neighbors=nb_in_search, decomposition=decomposition))
         mesh, _ = hvb.voronoi(xs, searcher=s)
         assert (np.diff(mesh.sig[:, 0]) >= 0).all()                      # each shard is sorted
         rows |= {tuple(r) for r in mesh.sig.tolist()}
         total += mesh.sig.shape[0]
-        assert s.stats()["raycasts"] < 0.9 * len(o["sig"])               # a rank walks its slab (plus a halo) only
+        assert s.stats()["raycasts"] < 0.9 * len(o["sig"])               # a rank walks its part (plus a layer around it) only
         own = s.owned()
+        assert 0.6 * 6000 / world <= own.sum() <= 1.6 * 6000 / world      # equal counts per part (quantile cuts / equal slabs)
         owned_by += own
         off, ids = mesh.neighbors()
         for c in range(6000):
