@@ -524,12 +524,17 @@ struct Ctx : hvb_ctx {
                 const int m = bspec.m[a], g = dv.g[a];
                 bspec.cut[a][0] = 0; bspec.cut[a][m] = g;
                 if (m > 1) {
-                    long long acc = 0; int j = 1;
-                    for (int c = 0; c < g && j < m; ++c) {
-                        acc += h_marg.p[off + c];
-                        while (j < m && acc * m >= (long long)n * j) { bspec.cut[a][j] = std::min(g - (m - j), std::max(c + 1, bspec.cut[a][j - 1] + 1)); ++j; }
+                    // part j begins at the cell boundary whose cumulative count is NEAREST to j / m of the points (grids of
+                    // high dimensions have ~10 cells per axis: "first boundary past the quantile" is off by up to a cell, 10 %)
+                    std::vector<long long> cum(g + 1, 0);
+                    for (int c = 0; c < g; ++c) cum[c + 1] = cum[c] + h_marg.p[off + c];
+                    for (int j = 1; j < m; ++j) {
+                        const double target = (double)cum[g] * j / m;
+                        int best = bspec.cut[a][j - 1] + 1;
+                        for (int c = best; c <= g - (m - j); ++c)
+                            if (fabs((double)cum[c] - target) < fabs((double)cum[best] - target)) best = c;
+                        bspec.cut[a][j] = best;
                     }
-                    for (; j < m; ++j) bspec.cut[a][j] = std::min(g - (m - j), bspec.cut[a][j - 1] + 1);
                 }
                 off += g;
             }
@@ -1098,6 +1103,11 @@ struct Ctx : hvb_ctx {
         for (int i = 0; i < 2; ++i) { CK(out_sig[i].ensure((size_t)std::max<u32>(nrec, 1) * (D + 1))); CK(out_r[i].ensure((size_t)std::max<u32>(nrec, 1) * D)); }
         CK(key_top.ensure(std::max<u32>(nrec, 1))); CK(key_hi.ensure(std::max<u32>(nrec, 1))); CK(key_lo.ensure(std::max<u32>(nrec, 1)));
         int bits = id_bits();
+        if (nrec > 0 && prm.sort_output) {
+            CK(cudaMemsetAsync(key_top.p, 0xff, (size_t)nrec * sizeof(u64), stream));
+            CK(cudaMemsetAsync(key_hi.p, 0xff, (size_t)nrec * sizeof(u64), stream));
+            CK(cudaMemsetAsync(key_lo.p, 0xff, (size_t)nrec * sizeof(u64), stream));
+        }
         if (nrec > 0) {
             // multi-GPU: only the vertices this rank owns; seed vertices (the caller's own) are not returned
             const int world = std::max(1, prm.world), rank = std::min(std::max(0, prm.rank), world - 1);
@@ -1129,11 +1139,15 @@ struct Ctx : hvb_ctx {
             CK(cudaEventRecord(ev_x1, xstream));
             counts_cached = true;
         }
-        int rc = read_scalars(); if (rc) return rc;
+        // The sort is enqueued over ALL nrec records right behind k_final_rows -- rows it skipped (dead records, vertices
+        // of other ranks, rejected ones) keep the all-ones key the arrays were filled with and end up behind the result --
+        // so that no host round trip stands between the two: the row count is read while the sort runs.
+        int rc = sort_rows(nrec, bits); if (rc) return rc;
+        rc = read_scalars(); if (rc) return rc;
         nvert = h_sc.p->out_count;
         if (by_slab) nrays = h_sc.p->ray_out;
         st.rejected = h_sc.p->tol_counts[0]; st.suboptimal = h_sc.p->tol_counts[1];
-        return sort_rows((u32)nvert, bits);
+        return HVB_OK;
     }
 
     // device -> page-locked host staging (asynchronous; the fetch calls wait for it).  Three pieces, staged on demand:

@@ -7,6 +7,10 @@ run() { # name N extra...
   ( time python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port $((29530+RANDOM%100)) bench.py --gpus $N --steps 20 --warmup 5 "$@" ) > gpurun_out/scale2_$name.log 2>&1
   echo "$name rc=$?"
 }
-run N8_bal 8
-run N8_nobal 8 --setting balance=0 --no-parity
-run N4_bal 4 --no-parity
+run N8_blocks 8
+run N8_slabs 8 --setting decomposition=0 --no-parity
+run N4_blocks 4
+run N2_blocks 2
+( time python bench.py --gpus 1 --steps 20 --warmup 5 --no-cpu-baseline ) > gpurun_out/scale2_N1.log 2>&1
+( time timeout 600 python -m pytest tests/test_gpu_multi.py -q ) > gpurun_out/pytest_multi.log 2>&1
+tail -2 gpurun_out/pytest_multi.log
