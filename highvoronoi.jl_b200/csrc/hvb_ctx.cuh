@@ -1022,12 +1022,14 @@ struct Ctx : hvb_ctx {
         CK(cudaStreamWaitEvent(nstream, ev_b, 0));
         CK(cudaEventRecord(ev_n0, nstream));
         if (want_nb) { rc = nb_prepare(true, nullptr); if (rc) return rc; rc = nb_enqueue(nstream); if (rc) return rc; }
-        rc = finalize(by_slab); if (rc) return rc;
+        rc = finalize(by_slab); if (rc) return rc;             // rows + sort: enqueued, not waited for
         CK(cudaEventRecord(ev_c, stream));
+        // the lists are finished (one host wait on THEIR stream for the list sizes, then fill + sort) while the row sort runs
+        if (want_nb) { rc = nb_finish(nstream); if (rc) return rc; }
+        rc = finalize_collect(by_slab); if (rc) return rc;
         // a slab result is an intermediate: it is exported to the exchange step, not staged for the host
         if (world == 1) { rc = stage(); if (rc) return rc; }
         have_result = true;
-        if (want_nb) { rc = nb_finish(nstream); if (rc) return rc; }
         if (prm.neighbors) { rc = stage_neighbors(); if (rc) return rc; }
         CK(cudaEventRecord(ev_n1, nstream));
         CK(cudaStreamWaitEvent(stream, ev_n1, 0));
@@ -1142,8 +1144,11 @@ struct Ctx : hvb_ctx {
         // The sort is enqueued over ALL nrec records right behind k_final_rows -- rows it skipped (dead records, vertices
         // of other ranks, rejected ones) keep the all-ones key the arrays were filled with and end up behind the result --
         // so that no host round trip stands between the two: the row count is read while the sort runs.
-        int rc = sort_rows(nrec, bits); if (rc) return rc;
-        rc = read_scalars(); if (rc) return rc;
+        return sort_rows(nrec, bits);
+    }
+    // second half of finalize: waits for the row count (the neighbour lists were completed on their stream meanwhile)
+    int finalize_collect(bool by_slab) {
+        int rc = read_scalars(); if (rc) return rc;
         nvert = h_sc.p->out_count;
         if (by_slab) nrays = h_sc.p->ray_out;
         st.rejected = h_sc.p->tol_counts[0]; st.suboptimal = h_sc.p->tol_counts[1];
