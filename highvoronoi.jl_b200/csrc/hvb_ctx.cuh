@@ -499,50 +499,38 @@ struct Ctx : hvb_ctx {
                 bspec.m[best] *= f; w /= f;
             }
             bool ok = true;
-            for (int a = 0; a < A; ++a) ok &= (bspec.m[a] <= 16 && bspec.m[a] <= dv.g[a]);
-            if (!ok) bspec.mode = 0;                       // a grid too coarse to cut that way: slabs
+            for (int a = 0; a < A; ++a) ok &= (bspec.m[a] <= 16);
+            if (!ok) bspec.mode = 0;                       // more than 16 parts along one axis: slabs
         }
         if (bspec.mode == 1) {
-            // cuts at the quantiles of the marginal point counts (equal counts per part for product-like densities)
+            // cuts at the quantiles of the points' coordinates along the cut axes (1024-bin histograms over the bounding box)
             const int A = std::min(D, 3);
-            size_t tot = 0;
-            for (int a = 0; a < A; ++a) tot += (size_t)dv.g[a];
-            CK(marg.ensure(tot)); CK(h_marg.ensure(tot));
-            CK(cudaMemsetAsync(marg.p, 0, tot * sizeof(unsigned int), stream));
-            size_t off = 0; long long nprefix = 1;
+            CK(marg.ensure((size_t)A * HVB_CUT_BINS)); CK(h_marg.ensure((size_t)A * HVB_CUT_BINS));
+            CK(cudaMemsetAsync(marg.p, 0, (size_t)A * HVB_CUT_BINS * sizeof(unsigned int), stream));
             for (int a = 0; a < A; ++a) {
-                nprefix *= dv.g[a];
-                if (bspec.m[a] > 1) {
-                    k_marginal<<<blocks_for(nprefix, 256), 256, 0, stream>>>(cell_start.p, nprefix, ncells / nprefix, dv.g[a], marg.p + off); ++launches;
-                }
-                off += dv.g[a];
+                if (bspec.m[a] == 1) continue;
+                const double width = dv.g[a] * dv.h[a];
+                k_coord_hist<D><<<std::min(blocks_for(n, 256), sms * 4), 256, 0, stream>>>(x64.p, (int)n, a, dv.lo[a], 1.0 / width, marg.p + (size_t)a * HVB_CUT_BINS); ++launches;
             }
-            CK(cudaMemcpyAsync(h_marg.p, marg.p, tot * sizeof(unsigned int), cudaMemcpyDeviceToHost, stream));
+            CK(cudaMemcpyAsync(h_marg.p, marg.p, (size_t)A * HVB_CUT_BINS * sizeof(unsigned int), cudaMemcpyDeviceToHost, stream));
             CK(cudaStreamSynchronize(stream));
-            off = 0;
             for (int a = 0; a < A; ++a) {
-                const int m = bspec.m[a], g = dv.g[a];
-                bspec.cut[a][0] = 0; bspec.cut[a][m] = g;
-                if (m > 1) {
-                    // part j begins at the cell boundary whose cumulative count is NEAREST to j / m of the points (grids of
-                    // high dimensions have ~10 cells per axis: "first boundary past the quantile" is off by up to a cell, 10 %)
-                    std::vector<long long> cum(g + 1, 0);
-                    for (int c = 0; c < g; ++c) cum[c + 1] = cum[c] + h_marg.p[off + c];
-                    for (int j = 1; j < m; ++j) {
-                        const double target = (double)cum[g] * j / m;
-                        int best = bspec.cut[a][j - 1] + 1;
-                        for (int c = best; c <= g - (m - j); ++c)
-                            if (fabs((double)cum[c] - target) < fabs((double)cum[best] - target)) best = c;
-                        bspec.cut[a][j] = best;
-                    }
+                const int m = bspec.m[a];
+                if (m == 1) continue;
+                const double width = dv.g[a] * dv.h[a];
+                const unsigned int* hst = h_marg.p + (size_t)a * HVB_CUT_BINS;
+                long long acc = 0; int j = 1;
+                for (int c = 0; c < HVB_CUT_BINS && j < m; ++c) {
+                    acc += hst[c];
+                    while (j < m && acc * m >= (long long)n * j) { bspec.cut[a][j] = dv.lo[a] + width * (double)(c + 1) / HVB_CUT_BINS; ++j; }
                 }
-                off += g;
+                for (; j < m; ++j) bspec.cut[a][j] = dv.lo[a] + width;
             }
         } else {
             for (int k = 0; k <= world; ++k) bspec.bound[k] = n * k / world;       // partition_indices, parallelmesh.jl:52-87
         }
         CK(owner.ensure(n));
-        k_assign_owner<D><<<blocks_for(n, 256), 256, 0, stream>>>(dv, perm.p, cell_of.p, bspec, owner.p); ++launches;
+        k_assign_owner<D><<<blocks_for(n, 256), 256, 0, stream>>>(dv, bspec, owner.p); ++launches;
         owner_ptr = owner.p;
         return HVB_OK;
     }
@@ -1264,7 +1252,7 @@ struct Ctx : hvb_ctx {
         // slots = 2 x that estimate (the estimate itself is ~1.3 x the Poisson-Voronoi mean): load <= 0.4, and the
         // memset + the fill pass touch a quarter of what an entry-per-list-element table would need
         // (slab contexts build the lists of their own cells only: 1/world of the cells plus the pairs that cross the slab faces)
-        const double own_frac = own_ptr ? std::min(1.0, 1.7 / std::max(1, prm.world) + 0.03) : 1.0;
+        const double own_frac = own_ptr ? std::min(1.0, 2.2 / std::max(1, prm.world) + 0.05) : 1.0;
         nb_want = next_pow2((u64)std::min(nrows * D * (D + 1) / 2.0 * 2.0, (double)n_list * own_frac * nb_est[D]) + 1024);
         size_t tmp_bytes = 0;
         CK(cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, nb_off.p, nb_off.p, (int)(n + 1), stream));

@@ -183,8 +183,8 @@ static __global__ void k_gather_points(Dev<D> dv, const double* __restrict__ xs,
 // multi-GPU decomposition: owner[p] = rank that explores the cell of sorted position p.
 //   slabs  (decomposition 0): contiguous ranges of the sorted order with equal counts -- partition_indices,
 //           parallelmesh.jl:52-87.  The order is cell-linear with axis 0 slowest, so these are slabs across axis 0.
-//   blocks (decomposition 1): the grid is cut along up to three axes (m[0] x m[1] x m[2] = world) at the quantiles of the
-//           marginal point counts.  A rank finds every vertex that touches its cells, so the layer of vertices two
+//   blocks (decomposition 1): the domain is cut along up to three axes (m[0] x m[1] x m[2] = world) at the quantiles of the
+//           points' coordinates.  A rank finds every vertex that touches its cells, so the layer of vertices two
 //           neighbouring ranks both find grows with the SURFACE of a part: 8 slabs have 14 faces of full cross-section,
 //           2 x 2 x 2 blocks have 6 -- and all blocks of a cube are corner blocks, alike in their share of cheap boundary
 //           cells (with slabs the two end ranks of C4 had 2/3 of the work of the inner ones).
@@ -193,35 +193,40 @@ struct BlockSpec {
     int mode;                 // 0 slabs, 1 blocks
     int world;
     int m[3];                 // parts along axes 0, 1, 2 (1 = axis not cut)
-    int cut[3][17];           // blocks: cell coordinate where part j of axis a begins (cut[a][0] = 0, cut[a][m] = g[a])
+    double cut[3][17];        // blocks: coordinate where part j of axis a begins (j = 1 .. m - 1): a point with x_a >= cut belongs
+                              // to part j or a later one.  Quantiles of the points' coordinates (1024-bin histogram), NOT cell
+                              // boundaries: a grid of high dimension has ~10 cells per axis, far too coarse to halve evenly
     long long bound[65];      // slabs: sorted position where slab k begins (bound[world] = n)
 };
-// marginal point count along axis a: thread q runs over the cell prefixes (c_0 .. c_a); the cells behind one prefix
-// are a contiguous range of cell_start
-static __global__ void k_marginal(const int* __restrict__ cell_start, long long nprefix, long long stride, int ga, unsigned int* __restrict__ hist) {
-    long long q = blockIdx.x * (long long)blockDim.x + threadIdx.x;
-    if (q >= nprefix) return;
-    const int cnt = cell_start[(q + 1) * stride] - cell_start[q * stride];
-    if (cnt) atomicAdd(hist + (int)(q % ga), (unsigned int)cnt);
+// histogram of the points' coordinates along axis a (HVB_CUT_BINS bins over [lo, lo + width)), per-block in shared memory
+#define HVB_CUT_BINS 1024
+template <int D>
+static __global__ void k_coord_hist(const double* __restrict__ x64, int n, int a, double lo, double inv_w, unsigned int* __restrict__ hist) {
+    __shared__ unsigned int sh[HVB_CUT_BINS];
+    for (int i = threadIdx.x; i < HVB_CUT_BINS; i += blockDim.x) sh[i] = 0;
+    __syncthreads();
+    for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < n; p += gridDim.x * blockDim.x) {
+        int b = (int)((x64[(size_t)p * D + a] - lo) * inv_w * HVB_CUT_BINS);
+        b = b < 0 ? 0 : (b >= HVB_CUT_BINS ? HVB_CUT_BINS - 1 : b);
+        atomicAdd(sh + b, 1u);
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < HVB_CUT_BINS; i += blockDim.x) if (sh[i]) atomicAdd(hist + i, sh[i]);
 }
 template <int D>
-static __global__ void k_assign_owner(Dev<D> dv, const int* __restrict__ perm, const int* __restrict__ cell_of, BlockSpec bs,
-                               unsigned char* __restrict__ owner) {
+static __global__ void k_assign_owner(Dev<D> dv, BlockSpec bs, unsigned char* __restrict__ owner) {
     int p = blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= dv.n) return;
     int r = 0;
     if (bs.mode == 0) {
         while (r + 1 < bs.world && (long long)p >= bs.bound[r + 1]) ++r;
     } else {
-        int c = cell_of[perm[p]];
-        int cc[D];
-#pragma unroll
-        for (int k = D - 1; k >= 0; --k) { cc[k] = c % dv.g[k]; c /= dv.g[k]; }
 #pragma unroll
         for (int a = 0; a < 3; ++a) {
             if (a >= D) break;
+            const double x = dv.x64[(size_t)p * D + a];
             int b = 0;
-            while (b + 1 < bs.m[a] && cc[a] >= bs.cut[a][b + 1]) ++b;
+            while (b + 1 < bs.m[a] && x >= bs.cut[a][b + 1]) ++b;
             r = r * bs.m[a] + b;
         }
     }

@@ -90,8 +90,8 @@ typedef struct hvb_params {
                                  calls keep working (they stage the int64 form on first use).  Default 0. */
     int32_t decomposition;    /* world > 1: which cells a rank explores.  0 = contiguous slabs of the spatially sorted order
                                  with equal counts (partition_indices, parallelmesh.jl:52-87: slabs across axis 0);
-                                 1 (default) = blocks: the grid is cut along up to three axes (2 x 2 x 2 for 8 ranks) at the
-                                 quantiles of the marginal point counts -- less surface between ranks, hence fewer vertices
+                                 1 (default) = blocks: the domain is cut along up to three axes (2 x 2 x 2 for 8 ranks) at the
+                                 quantiles of the generators' coordinates -- less surface between ranks, hence fewer vertices
                                  found twice, and equal shares of the cheap boundary cells.  Same result either way. */
 } hvb_params;
 
