@@ -379,20 +379,35 @@ class ConvexHull:
     """ConvexHull(xs) (chull.jl:213-238, docs/src/man/convexhull.md): `len(cv)` surface elements, `cv[i] = (sig, r, u)` with
     sig the d generating nodes (1-based, sorted), r a point of the facet's plane and u its outer unit normal.
 
-    General position only.  The reference walks the hull facets directly (systematic_chull, chull.jl:241-387); here the
-    facets are read off the search this backend already runs: a facet of the hull is the dual of an unbounded Voronoi edge
-    (the d generators of the edge, the edge's direction as outer normal), i.e. one row of hvb_fetch_rays on the unbounded
-    domain.  Same result, but the whole tessellation is computed to get it."""
+    General position only.  The facets are walked directly on the device (hvb_convex_hull, csrc/hvb_hull.cuh: a hull facet is an
+    unbounded Voronoi edge, two facets that share a ridge are the two unbounded edges of one 2-face of the diagram, so the walk
+    goes around those 2-faces with ordinary min-t queries) -- the interior of the tessellation is never computed.
+    via="search" keeps round 1's way (a complete search on the unbounded domain, facets read off its unbounded edges): same
+    result, used by the tests as a cross-check."""
 
-    def __init__(self, xs, intro="", nthreads=None, method=None, options=None):
+    def __init__(self, xs, intro="", nthreads=None, method=None, options=None, via="walk"):
         xs = VoronoiNodes(xs)
         s = Raycast(xs, domain=Boundary(), options=options or RaycastParameter())
         try:
-            mesh, _ = voronoi(xs, searcher=s, copy=True)
-            order = np.lexsort(mesh.ray_edge.T[::-1]) if len(mesh.ray_edge) else np.zeros(0, dtype=np.int64)
-            self.sig = mesh.ray_edge[order]
-            self.u = mesh.ray_dir[order]
-            base = mesh.ray_base[order]
+            if via == "search":
+                mesh, _ = voronoi(xs, searcher=s, copy=True)
+                edge, udir, base = mesh.ray_edge, mesh.ray_dir, mesh.ray_base
+            else:
+                L, ctx = _abi.lib(), s._ctx
+                _abi.check(L.hvb_convex_hull(ctx), ctx)
+                nv, nr = ctypes.c_int64(), ctypes.c_int64()
+                _abi.check(L.hvb_counts(ctx, ctypes.byref(nv), ctypes.byref(nr), None), ctx)
+                d = xs.shape[1]
+                edge = np.empty((nr.value, d), dtype=np.int64); base = np.empty((nr.value, d)); udir = np.empty((nr.value, d))
+                node = np.empty((nr.value,), dtype=np.int64)
+                if nr.value:
+                    P = lambda a: a.ctypes.data_as(ctypes.c_void_p)
+                    _abi.check(L.hvb_fetch_rays(ctx, P(edge), P(base), P(udir), P(node)), ctx)
+            self.stats = s.stats()
+            order = np.lexsort(edge.T[::-1]) if len(edge) else np.zeros(0, dtype=np.int64)
+            self.sig = edge[order]
+            self.u = udir[order]
+            base = base[order]
         finally:
             s.close()
         self.xs = xs

@@ -213,7 +213,7 @@ struct Ctx : hvb_ctx {
         ctr.release(); sc.release(); h_sc.release(); h_ctr.release(); h_extra.release(); cells_dev.release(); seed_sig_dev.release(); seed_r_dev.release();
         out_sig[0].release(); out_sig[1].release(); out_r[0].release(); out_r[1].release(); key_top.release(); key_hi.release(); key_lo.release(); key_tmp.release();
         idx[0].release(); idx[1].release(); ray_edge.release(); ray_node.release(); ray_base.release(); ray_dir.release();
-        h_sig.release(); h_r.release(); sig32_dev.release(); ids32_dev.release(); h_sig32.release(); h_ids32.release(); h_nb_off.release(); h_nb_ids.release(); ptab.release(); deg.release(); ncur.release(); nb_off.release(); nb_ids.release();
+        h_sig.release(); h_r.release(); sig32_dev.release(); ids32_dev.release(); h_sig32.release(); h_ids32.release(); h_fsig.release(); h_fitem.release(); h_fu.release(); h_ftab.release(); h_rtab.release(); h_arg.release(); h_nb_off.release(); h_nb_ids.release(); ptab.release(); deg.release(); ncur.release(); nb_off.release(); nb_ids.release();
         for (cudaEvent_t e : ev_pool) cudaEventDestroy(e);
         if (ev_up) cudaEventDestroy(ev_up);
         if (ev_a) cudaEventDestroy(ev_a);
@@ -740,6 +740,85 @@ struct Ctx : hvb_ctx {
         if (!periodic || !have_flags) { memset(flags, 1, (size_t)nvert); return HVB_OK; }   // without a halo every row is its own representative
         if (nvert > 0) CK(cudaMemcpyAsync(flags, vflags.p, (size_t)nvert, cudaMemcpyDeviceToHost, stream));
         CK(cudaStreamSynchronize(stream));
+        return HVB_OK;
+    }
+
+    // ---- convex hull by the facet walk (hvb_hull.cuh; replaces systematic_chull, chull.jl:241-387) -------------------
+    DBuf<int> h_fsig; DBuf<u32> h_fitem; DBuf<double> h_fu; DBuf<u64> h_ftab, h_rtab; DBuf<unsigned long long> h_arg;
+    int convex_hull() override {
+        if (P != 0 || periodic) { err = "the convex hull is computed on the unbounded domain: create the context without planes"; return HVB_EINVAL; }
+        if (std::max(1, prm.world) > 1) { err = "the convex hull runs on one GPU"; return HVB_EINVAL; }
+        CK(cudaSetDevice(prm.device));
+        have_result = false; staged = false; staged_r = staged_sig64 = staged_sig32 = false; nb_staged32 = false; nb_total = -1; have_flags = false;
+        launches = 0;
+        int64_t cap = std::max<int64_t>(vcap, prm.vertex_capacity > 0 ? prm.vertex_capacity : estimate_vertices(D, n, 0));
+        CK(cudaEventRecord(ev_a, stream));
+        if (cap != vcap || !vsig.p) { int rc = alloc_tables(cap); if (rc) return rc; }
+        HullDev<D> hd;
+        const u32 fcap = (u32)std::min<int64_t>(vcap, 0x7fffffff);
+        const u64 fts = next_pow2(2 * (u64)fcap), rts = next_pow2(2 * (u64)fcap * D);
+        CK(h_fsig.ensure((size_t)fcap * D)); CK(h_fitem.ensure(fcap)); CK(h_fu.ensure((size_t)fcap * D)); CK(h_ftab.ensure(fts)); CK(h_rtab.ensure(rts)); CK(h_arg.ensure(1));
+        hd.fsig = h_fsig.p; hd.fitem = h_fitem.p; hd.fu = h_fu.p; hd.fcount = &sc.p->ray_count; hd.fcap = fcap;
+        hd.ftab = h_ftab.p; hd.fmask = fts - 1; hd.rtab = h_rtab.p; hd.rmask = rts - 1;
+        CK(cudaMemsetAsync(h_ftab.p, 0, fts * sizeof(u64), stream));
+        CK(cudaMemsetAsync(h_rtab.p, 0, rts * sizeof(u64), stream));
+        CK(cudaMemsetAsync(ctr.p, 0, sizeof(Counters), stream));
+        CK(cudaMemsetAsync(sc.p, 0, sizeof(Scalars), stream));
+        CK(cudaMemsetAsync(h_arg.p, 0, sizeof(unsigned long long), stream));
+        CK(cudaMemsetAsync(active.p, 1, n, stream));
+        const int axis = 0;
+        k_argmax_axis<D><<<std::min(blocks_for(n, 256), sms * 4), 256, 0, stream>>>(x64.p, (int)n, axis, h_arg.p); ++launches;
+        CK(cudaMemcpyAsync(h_extra.p, h_arg.p, sizeof(long long), cudaMemcpyDeviceToHost, stream));
+        CK(cudaStreamSynchronize(stream));
+        const int start = (int)((unsigned long long)*h_extra.p & 0xffffffffULL);
+        int cur = 0;
+        k_hull_seed<D><<<1, 32, 0, stream>>>(dv, hd, start, axis, q[cur].p, &sc.p->rnd[cur].qcount, qcap); ++launches;
+        int64_t rounds = 0, items = 0;
+        size_t n_ev = 0;
+        for (;;) {
+            int rc = read_scalars(); if (rc) return rc;
+            if (h_ctr.p->flags & FLAG_OVERFLOW_MASK) { err = "hull walk: capacity exhausted (raise vertex_capacity)"; return HVB_ENOMEM; }
+            if ((h_ctr.p->degenerate > 0 || (h_ctr.p->flags & FLAG_DEGEN)) && !prm.on_degenerate) {
+                st.degenerate = (int64_t)std::max<u64>(h_ctr.p->degenerate, 1);
+                err = "non-general position: a hull facet with more than dim generators was met";
+                return HVB_EDEGENERATE;
+            }
+            const u32 cnt = h_sc.p->rnd[cur].qcount;
+            if (cnt == 0) break;
+            const int nxt = 1 - cur;
+            CK(cudaMemsetAsync(&sc.p->rnd[nxt], 0, sizeof(Round), stream));
+            cudaEvent_t e0 = pool_event(n_ev++), e1 = pool_event(n_ev++);
+            CK(cudaEventRecord(e0, stream));
+            k_hull_expand<D><<<std::min(blocks_for(cnt, 128), sms * 16), 128, 0, stream>>>(dv, hd, q[cur].p, &sc.p->rnd[cur].qcount, &sc.p->rnd[cur].cursor,
+                                                                                       q[nxt].p, &sc.p->rnd[nxt].qcount, qcap);
+            CK(cudaEventRecord(e1, stream));
+            ++launches; ++rounds; items += cnt;
+            cur = nxt;
+            if (rounds > 100000) { err = "hull walk does not terminate"; return HVB_EINCOMPLETE; }
+        }
+        if (h_ctr.p->seed_fail > 0 && h_sc.p->ray_count == 0) { err = "hull walk: no first facet found"; return HVB_EINCOMPLETE; }
+        CK(cudaEventRecord(ev_b, stream));
+        const u32 nf = std::min<u32>(h_sc.p->ray_count, fcap);
+        nvert = 0; nrays = 0;
+        if (nf > 0) {
+            CK(ray_edge.ensure((size_t)nf * D)); CK(ray_base.ensure((size_t)nf * D)); CK(ray_dir.ensure((size_t)nf * D)); CK(ray_node.ensure(nf));
+            k_final_facets<D><<<blocks_for(nf, 128), 128, 0, stream>>>(dv, hd, perm.p, nf, ray_edge.p, ray_base.p, ray_dir.p, ray_node.p, &sc.p->ray_out); ++launches;
+        }
+        CK(cudaEventRecord(ev_d, stream));
+        int rc = read_scalars(); if (rc) return rc;
+        nrays = h_sc.p->ray_out;
+        float ms = 0;
+        cudaEventElapsedTime(&ms, ev_a, ev_b); st.ms_search = ms;
+        cudaEventElapsedTime(&ms, ev_b, ev_d); st.ms_finalize = ms;
+        double kms = 0;
+        for (size_t i = 0; i + 1 < n_ev; i += 2) { cudaEventElapsedTime(&ms, ev_pool[i], ev_pool[i + 1]); kms += ms; }
+        const Counters& c = *h_ctr.p;
+        st.ms_expand_kernel = kms; st.expand_launches = rounds; st.expand_items = items; st.rounds = rounds;
+        st.vertices = 0; st.unique_vertices = 0; st.rays = nrays; st.raycasts = (int64_t)c.raycasts; st.duplicate_hits = 0; st.closed_skips = 0;
+        st.candidates_fp32 = (int64_t)c.cand32; st.candidates_fp64 = (int64_t)c.cand64; st.rows_scanned = (int64_t)c.rows; st.probe_stages = (int64_t)c.stages;
+        st.seeds = 1; st.degenerate = (int64_t)c.degenerate; st.kernel_launches = launches; st.capacity_retries = 0; st.ms_seed = 0; st.ms_neighbors = 0;
+        st.ms_rows_sort = 0; st.ms_stage_wait = 0; st.rejected = 0; st.suboptimal = 0; st.exchange_bytes = 0; st.periodic_retries = 0;
+        have_result = true;
         return HVB_OK;
     }
 

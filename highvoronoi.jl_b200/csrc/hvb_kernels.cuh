@@ -5,6 +5,7 @@
 #include <cuda_runtime.h>
 #include "hvb_core.cuh"
 #include "hvb_geometry.cuh"
+#include "hvb_hull.cuh"
 
 namespace hvb {
 
@@ -557,6 +558,73 @@ static __global__ void k_unseeded(Dev<D> dv, int* list, u32* count) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= dv.n) return;
     if (dv.active[i] && !dv.has_vertex[i]) list[atomicAdd(count, 1u)] = i;
+}
+
+
+// ------------------------------------------------------------------------------------------------------------
+// convex hull by the facet walk (hvb_hull.cuh; replaces systematic_chull, chull.jl:241-387)
+// ------------------------------------------------------------------------------------------------------------
+// generator with the largest coordinate along `axis` (search_max, chull.jl:244): packed {ordered coordinate bits, position}
+template <int D>
+static __global__ void k_argmax_axis(const double* __restrict__ x64, int n, int axis, unsigned long long* __restrict__ out) {
+    unsigned long long best = 0;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const float v = (float)x64[(size_t)i * D + axis];
+        unsigned int b = __float_as_uint(v);
+        b = (b & 0x80000000u) ? ~b : (b | 0x80000000u);           // order-preserving map of float bits
+        const unsigned long long key = ((unsigned long long)b << 32) | (unsigned int)i;
+        best = key > best ? key : best;
+    }
+#pragma unroll
+    for (int m = 16; m >= 1; m >>= 1) { const unsigned long long o = __shfl_xor_sync(0xffffffffu, best, m); best = o > best ? o : best; }
+    if ((threadIdx.x & 31) == 0) atomicMax(out, best);
+}
+template <int D>
+static __global__ void k_hull_seed(Dev<D> dv, HullDev<D> hd, int start, int axis, u64* q_out, u32* q_count, u32 q_cap) {
+    TileDev<1> tile;
+    LocalStats ls = {};
+    if (threadIdx.x == 0) hull_seed<D, TileDev<1> >(dv, hd, tile, start, axis, q_out, q_count, q_cap, ls);
+    __syncwarp();
+    flush_stats(ls, dv.ctr);
+}
+// one round of walks: a lane per entry, entries pulled from a shared cursor (warp-uniform loop as in k_expand)
+template <int D>
+static __global__ void __launch_bounds__(128, HVB_EXPAND_MINB) k_hull_expand(Dev<D> dv, HullDev<D> hd, const u64* __restrict__ q_in, const u32* __restrict__ n_in_ptr,
+                                                                      u32* cursor, u64* q_out, u32* q_count, u32 q_cap) {
+    TileDev<1> tile;
+    LocalStats ls = {};
+    const u32 n_in = min(*n_in_ptr, q_cap);
+    for (;;) {
+        const u32 idx = atomicAdd(cursor, 1u);
+        const bool live = idx < n_in;
+        if (!__any_sync(0xffffffffu, live)) break;
+        if (live) hull_step<D, TileDev<1> >(dv, hd, tile, q_in[idx], q_out, q_count, q_cap, ls);
+        __syncwarp();
+    }
+    flush_stats(ls, dv.ctr);
+}
+// facets in caller numbering, into the arrays of the unbounded edges (a hull facet IS an unbounded edge): edge = the d
+// generators (sorted, 1-based), base = a point the edge starts at, dir = outward unit normal, node = smallest generator
+template <int D>
+static __global__ void k_final_facets(Dev<D> dv, HullDev<D> hd, const int* __restrict__ perm, u32 nf,
+                               long long* __restrict__ edge, double* __restrict__ base, double* __restrict__ dir, long long* __restrict__ node,
+                               u32* __restrict__ out_count) {
+    u32 f = blockIdx.x * blockDim.x + threadIdx.x;
+    if (f >= nf) return;
+    const int* fs = hd.fsig + (size_t)f * D;
+    if (fs[0] < 0) return;
+    const u32 o = atomicAdd(out_count, 1u);
+    long long e[D];
+#pragma unroll
+    for (int k = 0; k < D; ++k) e[k] = (long long)perm[fs[k]] + 1;
+    for (int a = 1; a < D; ++a) { long long key = e[a]; int b = a - 1; while (b >= 0 && e[b] > key) { e[b + 1] = e[b]; --b; } e[b + 1] = key; }
+    const u32 v = hd.fitem[f] >> 3;
+    for (int k = 0; k < D; ++k) {
+        edge[(size_t)o * D + k] = e[k];
+        base[(size_t)o * D + k] = dv.vr[(size_t)v * D + k];
+        dir[(size_t)o * D + k] = hd.fu[(size_t)f * D + k];
+    }
+    node[o] = e[0];
 }
 
 // ------------------------------------------------------------------------------------------------------------

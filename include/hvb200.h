@@ -183,6 +183,16 @@ int hvb_set_points(hvb_ctx* ctx, int64_t n, const double* xs);
 int hvb_search(hvb_ctx* ctx, const int64_t* cells, int64_t ncells,
                const int64_t* seed_sig, const double* seed_r, int64_t nseed, int sig_stride);
 
+/* Replaces ConvexHull(xs) = systematic_chull (src/chull.jl:238-387: search_max, descent_chull, a queue of facets whose
+ * sub-facets are explored by raycast_des3 :485-499, explore_chull_vertex :547) on a context created WITHOUT planes.
+ * A hull facet is an unbounded Voronoi edge; two facets that share a ridge are the two unbounded edges of one 2-face of the
+ * diagram, so the walk goes around those 2-faces with ordinary min-t queries and never visits the interior of the
+ * tessellation (csrc/hvb_hull.cuh).  Afterwards hvb_counts reports nvert = 0 and nrays = number of facets, and
+ * hvb_fetch_rays returns them: edge = the dim generators of the facet (sorted, 1-based), base = a point of the ray the
+ * facet is dual to, dir = outer unit normal, node = smallest generator.  General position only (a facet with more than dim
+ * generators: HVB_EDEGENERATE). */
+int hvb_convex_hull(hvb_ctx* ctx);
+
 /* sizes for the fetch calls; max_siglen is dim+1 (general position) */
 int hvb_counts(hvb_ctx* ctx, int64_t* nvert, int64_t* nrays, int64_t* max_siglen);
 

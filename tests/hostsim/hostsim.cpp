@@ -13,6 +13,7 @@ static bool g_want_trace = false;
 #define HVB_TRACE_EVENT(kind, val) do { if (g_trace) { g_trace->push_back(kind); g_trace->push_back((int)(val)); } } while (0)
 #include "../../highvoronoi.jl_b200/csrc/hvb_host.hpp"
 #include "../../highvoronoi.jl_b200/csrc/hvb_geometry.cuh"
+#include "../../highvoronoi.jl_b200/csrc/hvb_hull.cuh"
 
 using namespace hvb;
 
@@ -167,7 +168,83 @@ static void areas(int64_t n, const double* xs, int P, const double* base, const 
     }
 }
 
+// convex hull by the facet walk of hvb_hull.cuh, driven sequentially (unbounded domain)
+struct HullResult { int d; int64_t nf; std::vector<int64_t> facet; std::vector<double> normal; int64_t raycasts, records, rounds, degenerate; };
+template <int D>
+static HullResult* run_hull(int64_t n, const double* xs, int ppc) {
+    Dev<D> dv;
+    memset(&dv, 0, sizeof(dv));
+    dv.n = (int)n;
+    double blo[D], bhi[D];
+    for (int k = 0; k < D; ++k) { blo[k] = 1e300; bhi[k] = -1e300; }
+    for (int64_t i = 0; i < n; ++i)
+        for (int k = 0; k < D; ++k) { blo[k] = std::min(blo[k], xs[i * D + k]); bhi[k] = std::max(bhi[k], xs[i * D + k]); }
+    int64_t ncell = setup_grid<D>(dv, blo, bhi, n, ppc > 0 ? ppc : default_points_per_cell(D));
+    std::vector<int> cell(n), cstart(ncell + 1, 0), perm(n);
+    for (int64_t i = 0; i < n; ++i) { cell[i] = cell_index<D>(dv, xs + i * D); cstart[cell[i] + 1]++; }
+    for (int64_t c = 0; c < ncell; ++c) cstart[c + 1] += cstart[c];
+    { std::vector<int> cur(cstart.begin(), cstart.end() - 1); for (int64_t i = 0; i < n; ++i) perm[cur[cell[i]]++] = (int)i; }
+    std::vector<double> x64(n * D); std::vector<float> x32(n * X32<D>::STRIDE, 0.f);
+    for (int64_t i = 0; i < n; ++i)
+        for (int k = 0; k < D; ++k) { x64[i * D + k] = xs[(int64_t)perm[i] * D + k]; x32[i * X32<D>::STRIDE + k] = (float)(x64[i * D + k] - dv.lo[k]); }
+    PlaneSet ps; memset(&ps, 0, sizeof(ps));
+    std::vector<unsigned char> active(n, 1), hasv(n, 0);
+    dv.cell_start = cstart.data(); dv.x32 = x32.data(); dv.x64 = x64.data(); dv.planes = &ps; dv.active = active.data();
+    dv.plane_tol = 1e-12; dv.probe_scale = default_probe_scale(D); dv.fp32_filter = 1;
+    int64_t vcap = estimate_vertices(D, n, 0);
+    std::vector<int> vsig(vcap * (D + 1)); std::vector<double> vr(vcap * D);
+    u32 vcount = 0;
+    Counters ctr; memset(&ctr, 0, sizeof(ctr));
+    dv.vsig = vsig.data(); dv.vr = vr.data(); dv.vcount = &vcount; dv.vcap = (u32)vcap; dv.has_vertex = hasv.data(); dv.ctr = &ctr;
+    HullDev<D> hd;
+    u32 fcap = (u32)vcap, fcount = 0;
+    std::vector<int> fsig((size_t)fcap * D); std::vector<u32> fitem(fcap); std::vector<double> fu((size_t)fcap * D);
+    u64 fts = next_pow2(2 * (u64)fcap), rts = next_pow2(2 * (u64)fcap * D);
+    std::vector<u64> ftab(fts, 0), rtab(rts, 0);
+    hd.fsig = fsig.data(); hd.fitem = fitem.data(); hd.fu = fu.data(); hd.fcount = &fcount; hd.fcap = fcap;
+    hd.ftab = ftab.data(); hd.fmask = fts - 1; hd.rtab = rtab.data(); hd.rmask = rts - 1;
+    u32 qcap = (u32)(2 * (u64)fcap * D);
+    std::vector<u64> qa(qcap), qb(qcap);
+    u32 na = 0, nb = 0;
+    TileHost tile; LocalStats ls; memset(&ls, 0, sizeof(ls));
+    // the extreme generator along axis 0 (search_max, chull.jl:244)
+    int start = 0;
+    for (int64_t i = 1; i < n; ++i) if (x64[i * D] > x64[(size_t)start * D]) start = (int)i;
+    HullResult* R = new HullResult(); R->d = D; R->rounds = 0;
+    bool ok = hull_seed<D, TileHost>(dv, hd, tile, start, 0, qa.data(), &na, qcap, ls);
+    while (ok && na > 0) {
+        nb = 0;
+        for (u32 i = 0; i < na; ++i) hull_step<D, TileHost>(dv, hd, tile, qa[i], qb.data(), &nb, qcap, ls);
+        qa.swap(qb); na = nb; ++R->rounds;
+    }
+    R->raycasts = ls.raycasts; R->records = vcount; R->degenerate = ls.degenerate + ((ctr.flags & FLAG_OVERFLOW_MASK) ? 1000000 : 0);
+    R->nf = 0;
+    for (u32 f = 0; f < fcount; ++f) {
+        if (fsig[(size_t)f * D] < 0) continue;
+        std::vector<int64_t> e;
+        for (int k = 0; k < D; ++k) e.push_back((int64_t)perm[fsig[(size_t)f * D + k]] + 1);
+        std::sort(e.begin(), e.end());
+        R->facet.insert(R->facet.end(), e.begin(), e.end());
+        for (int k = 0; k < D; ++k) R->normal.push_back(fu[(size_t)f * D + k]);
+        ++R->nf;
+    }
+    return R;
+}
+
 extern "C" {
+void* hostsim_hull(int dim, int64_t n, const double* xs, int ppc) {
+    switch (dim) {
+        case 2: return run_hull<2>(n, xs, ppc);
+        case 3: return run_hull<3>(n, xs, ppc);
+        case 4: return run_hull<4>(n, xs, ppc);
+        case 5: return run_hull<5>(n, xs, ppc);
+        case 6: return run_hull<6>(n, xs, ppc);
+    }
+    return 0;
+}
+void hostsim_hull_counts(void* h, int64_t* out /*5*/) { HullResult* R = (HullResult*)h; out[0] = R->nf; out[1] = R->raycasts; out[2] = R->records; out[3] = R->rounds; out[4] = R->degenerate; }
+void hostsim_hull_fetch(void* h, int64_t* facet, double* normal) { HullResult* R = (HullResult*)h; memcpy(facet, R->facet.data(), R->facet.size() * 8); memcpy(normal, R->normal.data(), R->normal.size() * 8); }
+void hostsim_hull_free(void* h) { delete (HullResult*)h; }
 void* hostsim_run(int dim, int64_t n, const double* xs, int P, const double* base, const double* normal,
                   int ppc, double probe_scale, int fp32, int seed_stride) {
     switch (dim) {

@@ -12,7 +12,8 @@ def build():
     core = os.path.join(_HERE, "..", "..", "highvoronoi.jl_b200", "csrc", "hvb_core.cuh")
     host = os.path.join(_HERE, "..", "..", "highvoronoi.jl_b200", "csrc", "hvb_host.hpp")
     geom = os.path.join(_HERE, "..", "..", "highvoronoi.jl_b200", "csrc", "hvb_geometry.cuh")
-    newest = max(os.path.getmtime(f) for f in (src, core, host, geom))
+    hull = os.path.join(_HERE, "..", "..", "highvoronoi.jl_b200", "csrc", "hvb_hull.cuh")
+    newest = max(os.path.getmtime(f) for f in (src, core, host, geom, hull))
     if not os.path.exists(_SO) or os.path.getmtime(_SO) < newest:
         subprocess.check_call(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-Wno-unknown-pragmas", "-o", _SO, src])
     return _SO
@@ -90,3 +91,25 @@ def areas(xs, sig, off, ids, base=None, normal=None):
     P = lambda a: a.ctypes.data_as(ctypes.c_void_p)
     L.hostsim_areas(d, n, P(xs), base.shape[0], P(base), P(normal), sig.shape[0], P(sig), P(off), P(ids), P(area))
     return area
+
+
+def hull(xs, ppc=0):
+    """convex hull by the facet walk of hvb_hull.cuh on the host: (facets [F, d] sorted 1-based ids, normals [F, d], stats)"""
+    L = ctypes.CDLL(build())
+    L.hostsim_hull.restype = ctypes.c_void_p
+    L.hostsim_hull.argtypes = [ctypes.c_int, ctypes.c_int64, ctypes.c_void_p, ctypes.c_int]
+    for f in ("hostsim_hull_counts", "hostsim_hull_fetch", "hostsim_hull_free"):
+        getattr(L, f).restype = None
+    L.hostsim_hull_counts.argtypes = [ctypes.c_void_p, ctypes.c_void_p]
+    L.hostsim_hull_fetch.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]
+    L.hostsim_hull_free.argtypes = [ctypes.c_void_p]
+    xs = np.ascontiguousarray(xs, dtype=np.float64)
+    n, d = xs.shape
+    P = lambda a: a.ctypes.data_as(ctypes.c_void_p)
+    h = L.hostsim_hull(d, n, P(xs), ppc)
+    c = np.zeros(5, dtype=np.int64)
+    L.hostsim_hull_counts(h, P(c))
+    facets = np.empty((c[0], d), dtype=np.int64); normals = np.empty((c[0], d))
+    L.hostsim_hull_fetch(h, P(facets), P(normals))
+    L.hostsim_hull_free(h)
+    return facets, normals, dict(facets=int(c[0]), raycasts=int(c[1]), records=int(c[2]), rounds=int(c[3]), degenerate=int(c[4]))
