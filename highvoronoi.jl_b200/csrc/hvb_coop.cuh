@@ -429,7 +429,7 @@ __device__ __forceinline__ Best coop_min_t(const Dev<D>& dv, CoopShared<D>& sh, 
         if (active) {
             ls.stages++;
             const double rho_t = scale * R0p;
-            Tst = (rho_t > 1e4 * dv.diag) ? INFINITY : q.a + sqrt(fmax(rho_t * rho_t - perp2, 0.0));
+            Tst = (rho_t > 4.0 * dv.diag) ? INFINITY : q.a + sqrt(fmax(rho_t * rho_t - perp2, 0.0));
             const double Ts = fmin(Tst, best.t);
             if (!(Ts < INFINITY)) { serial = true; active = false; }      // half-space mode: the FP64 path
             else {

@@ -583,6 +583,63 @@ HVB_HD bool row_range(const Dev<D>& dv, const RayQ<D>& q, const int (&clo)[D], c
     return true;
 }
 
+// row_range with block pruning for the FP64 path (the huge balls and the half-spaces of unbounded edges, where the cell
+// box is the whole grid): returns -1 if row j is usable (pa, pb set), else the first row index that is not pruned by the
+// same test.  Two tests cut whole blocks of rows that share leading cell coordinates: the partial distance to the ball's
+// centre (as row_try32), and the half-space: if the best u.(x - x0) over the leading cells so far plus the best the
+// REMAINING axes can contribute anywhere in the grid (msuf) is not positive, no generator behind that cell prefix lies
+// beyond the edge's hyperplane.  An unbounded edge -- a facet of the convex hull -- must certify exactly that: an empty
+// half-space; without this test every such ray visited every row of the grid.
+template <int D>
+HVB_HD int row_try64(const Dev<D>& dv, const RayQ<D>& q, const int (&clo)[D], const int (&chi)[D], const double (&cen)[D],
+                     double rho2, const double (&msuf)[D], int j, int& pa, int& pb) {
+    int rem = j;
+    int dg[D], pv[D];
+    int place = 1;
+#pragma unroll
+    for (int k = D - 2; k >= 0; --k) {
+        const int e = chi[k] - clo[k] + 1;
+        const int qd = rem / e;
+        dg[k] = rem - qd * e;
+        rem = qd;
+        pv[k] = place;
+        place *= e;
+    }
+    const double slk = 4e-9 * dv.diag;
+    int base = 0, prefix = 0;
+    double d2 = 0, umax = 0;
+#pragma unroll
+    for (int k = 0; k < D - 1; ++k) {
+        const int e = chi[k] - clo[k] + 1;
+        const int c = clo[k] + dg[k];
+        prefix = prefix * e + dg[k];
+        const double blo = dv.lo[k] + c * dv.h[k] - 1e-9 * dv.h[k];
+        const double bhi = blo + dv.h[k] * (1.0 + 2e-9);
+        const double dd = fmax(0.0, fmax(blo - cen[k], cen[k] - bhi));
+        d2 += dd * dd;
+        if (!(d2 <= rho2)) return (prefix + 1) * pv[k];
+        umax += fmax(q.u[k] * (blo - q.x0[k]), q.u[k] * (bhi - q.x0[k]));
+        if (umax + msuf[k] + slk <= 0) return (prefix + 1) * pv[k];
+        base = base * dv.g[k] + c;
+    }
+    const int L = D - 1;
+    const double s = sqrt(rho2 - d2);
+    double zlo = cen[L] - s, zhi = cen[L] + s;
+    const double ul = q.u[L];
+    const double slack = 1e-9 * (dv.h[L] + fabs(umax));
+    if (ul > 1e-300) zlo = fmax(zlo, q.x0[L] - (umax + slack) / ul);
+    else if (ul < -1e-300) zhi = fmin(zhi, q.x0[L] - (umax + slack) / ul);
+    else if (umax + slack <= 0) return j + 1;
+    const double gl = (double)dv.g[L];
+    const double vlo = fmin(fmax((zlo - dv.lo[L]) * dv.inv_h[L] - 1e-9, 0.0), gl - 1.0);
+    const double vhi = fmin(fmax((zhi - dv.lo[L]) * dv.inv_h[L] + 1e-9, -1.0), gl - 1.0);
+    const int z0 = (int)floor(vlo), z1 = (int)floor(vhi);
+    if (z1 < z0) return j + 1;
+    const int* cs = dv.cell_start + (size_t)base * dv.g[L];
+    pa = cs[z0]; pb = cs[z1 + 1];
+    return -1;
+}
+
 // FP32 bookkeeping of a probe stage: the candidate with the smallest FP32 UPPER bound of 2t (`cb`) and at most one
 // rival whose FP32 interval overlaps it (`cr`).  Everything else is decided in FP32; the FP64 evaluation
 // (get_t_hp, raycast.jl:427) runs once per stage for cb -- all lanes of a warp reach it together -- and only in
@@ -767,7 +824,8 @@ HVB_HD Best min_t_query(const Dev<D>& dv, const T& tile, const RayQ<D>& q, Local
     for (int stage = 0; stage < 96; ++stage) {
         ls.stages += (lane == 0);
         double rho_t = scale * R0p;
-        double Tst = (rho_t > 1e4 * dv.diag) ? INFINITY : q.a + sqrt(fmax(rho_t * rho_t - perp2, 0.0));
+        // a probe ball several times the size of the cloud selects what the half-space does: go there at once (it is exact)
+        double Tst = (rho_t > 4.0 * dv.diag) ? INFINITY : q.a + sqrt(fmax(rho_t * rho_t - perp2, 0.0));
         double Ts = fmin(Tst, best.t);
         bool halfspace_mode = !(Ts < INFINITY);
         // current search ball
@@ -818,15 +876,26 @@ HVB_HD Best min_t_query(const Dev<D>& dv, const T& tile, const RayQ<D>& q, Local
             b32.rho2 = (float)(rho2 * (1.0 + 1e-5)) * 1.000001f;
         }
 
-        if (D >= 4) {
-            // d >= 4: walk the rows with block pruning (row_try32); a lane keeps its residue class lane mod G
+        if (D >= 4 || !use32) {
+            // d >= 4, and the FP64 path of every dimension: walk the rows with block pruning (row_try32 / row_try64); a lane
+            // keeps its residue class lane mod G
+            double msuf[D];                     // FP64 path: best u.(x - x0) the axes behind k can contribute anywhere in the grid
+            if (!use32) {
+                double acc = 0;
+#pragma unroll
+                for (int k = D - 1; k >= 0; --k) {
+                    msuf[k] = acc;
+                    const double glo = dv.lo[k] - 1e-9 * dv.h[k], ghi = dv.lo[k] + dv.g[k] * dv.h[k] * (1.0 + 1e-9);
+                    acc += fmax(q.u[k] * (glo - q.x0[k]), q.u[k] * (ghi - q.x0[k]));
+                }
+            }
             int j = lane;
             int pa = 0, pb = 0;
             for (;;) {
                 bool have = false;
                 while (j < nrows) {
                     int jn = use32 ? row_try32<D>(dv, uf, x0f, clo, chi, b32, j, pa, pb)
-                                   : (row_range<D>(dv, q, clo, chi, cen, rho2, j, pa, pb) ? -1 : j + 1);
+                                   : row_try64<D>(dv, q, clo, chi, cen, rho2, msuf, j, pa, pb);
                     HVB_TRACE_EVENT(1, 0);
                     if (jn < 0) { have = true; j += T::SIZE; break; }
                     j = (T::SIZE == 1) ? jn : jn + ((T::SIZE - ((jn - lane) % T::SIZE)) % T::SIZE);

@@ -789,7 +789,7 @@ struct Ctx : hvb_ctx {
             CK(cudaMemsetAsync(&sc.p->rnd[nxt], 0, sizeof(Round), stream));
             cudaEvent_t e0 = pool_event(n_ev++), e1 = pool_event(n_ev++);
             CK(cudaEventRecord(e0, stream));
-            k_hull_expand<D><<<std::min(blocks_for(cnt, 128), sms * 16), 128, 0, stream>>>(dv, hd, q[cur].p, &sc.p->rnd[cur].qcount, &sc.p->rnd[cur].cursor,
+            k_hull_expand<D><<<std::min(blocks_for((int64_t)cnt * 32, 128), sms * 16), 128, 0, stream>>>(dv, hd, q[cur].p, &sc.p->rnd[cur].qcount, &sc.p->rnd[cur].cursor,
                                                                                        q[nxt].p, &sc.p->rnd[nxt].qcount, qcap);
             CK(cudaEventRecord(e1, stream));
             ++launches; ++rounds; items += cnt;

@@ -166,8 +166,11 @@ HVB_HD void hull_step(const Dev<D>& dv, const HullDev<D>& hd, const T& tile, u64
     int sig[D + 1];
     RayQ<D> q;
     u32 v; int kd;
-    if (!ray_setup<D>(dv, ((u64)v0 << 3) | (u64)kd0, q, sig, v, kd)) { ls.seed_fail++; return; }
+    // the lanes of the tile build the same ray and share the rows of the query (the half-space of an unbounded edge spans
+    // the whole grid: one lane per ray is hopeless here); lane 0 alone touches the tables
+    if (!ray_setup<D>(dv, ((u64)v0 << 3) | (u64)kd0, q, sig, v, kd)) { ls.seed_fail += (tile.lane() == 0); return; }
     const Best best = min_t_query<D, T>(dv, tile, q, ls);
+    if (tile.lane() != 0) return;
     if (best.id < 0) { hull_facet_found<D>(dv, hd, sig, v, kd, q.u, q_out, q_count, q_cap); return; }
     if (near_tie(best, q.R0sq)) { ls.degenerate++; atom_or(&dv.ctr->flags, (u32)FLAG_DEGEN); }
     // the next vertex of the polygon: edge + winner; the walk goes on over (that vertex minus the pivot)
@@ -267,9 +270,13 @@ template <int D, class T>
 HVB_HD bool hull_seed(const Dev<D>& dv, const HullDev<D>& hd, const T& tile, int start, int axis, u64* q_out, u32* q_count, u32 q_cap, LocalStats& ls) {
     int sig[D + 1];
     double r[D];
-    if (!descent_vertex<D, T>(dv, tile, start, sig, r, ls)) { ls.seed_fail++; return false; }
+    const int lane = tile.lane();
+    if (!descent_vertex<D, T>(dv, tile, start, sig, r, ls)) { ls.seed_fail += (lane == 0); return false; }
     for (int step = 0; step < 100000; ++step) {
-        const u32 v = hull_new_vertex<D>(dv, sig, r);
+        // all lanes of the tile walk the same path (the queries are shared); lane 0 writes, the others read its record
+        u32 v = 0;
+        if (lane == 0) { v = hull_new_vertex<D>(dv, sig, r); mem_fence(); }
+        v = tile.shfl(v, 0);
         if (v == 0xffffffffu) return false;
         int bestk = -1;
         double bests = -INFINITY;
@@ -280,10 +287,10 @@ HVB_HD bool hull_seed(const Dev<D>& dv, const HullDev<D>& hd, const T& tile, int
             if (!ray_setup<D>(dv, ((u64)v << 3) | (u64)k, q, s2, vv, kk)) continue;
             if (q.u[axis] > bests) { bests = q.u[axis]; bestk = k; qb = q; }
         }
-        if (bestk < 0) { ls.seed_fail++; return false; }
+        if (bestk < 0) { ls.seed_fail += (lane == 0); return false; }
         const Best best = min_t_query_call<D, T>(dv, tile, qb, ls);
         if (best.id < 0) {
-            hull_facet_found<D>(dv, hd, sig, v, bestk, qb.u, q_out, q_count, q_cap);
+            if (lane == 0) hull_facet_found<D>(dv, hd, sig, v, bestk, qb.u, q_out, q_count, q_cap);
             return true;
         }
         int e[D];
@@ -292,7 +299,7 @@ HVB_HD bool hull_seed(const Dev<D>& dv, const HullDev<D>& hd, const T& tile, int
         sorted_insert(sig, D, best.id);
         for (int k = 0; k < D; ++k) r[k] = qb.r[k] + best.t * qb.u[k];
     }
-    ls.seed_fail++;
+    ls.seed_fail += (lane == 0);
     return false;
 }
 

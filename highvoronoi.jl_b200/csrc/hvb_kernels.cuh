@@ -581,24 +581,26 @@ static __global__ void k_argmax_axis(const double* __restrict__ x64, int n, int 
 }
 template <int D>
 static __global__ void k_hull_seed(Dev<D> dv, HullDev<D> hd, int start, int axis, u64* q_out, u32* q_count, u32 q_cap) {
-    TileDev<1> tile;
+    TileDev<32> tile;                    // one warp: the descent and the climb are a chain of queries, each shared by the lanes
     LocalStats ls = {};
-    if (threadIdx.x == 0) hull_seed<D, TileDev<1> >(dv, hd, tile, start, axis, q_out, q_count, q_cap, ls);
+    hull_seed<D, TileDev<32> >(dv, hd, tile, start, axis, q_out, q_count, q_cap, ls);
     __syncwarp();
     flush_stats(ls, dv.ctr);
 }
-// one round of walks: a lane per entry, entries pulled from a shared cursor (warp-uniform loop as in k_expand)
+// one round of walks: a warp per entry (the query of an unbounded edge scans a half-space of the grid), entries pulled from
+// a shared cursor
 template <int D>
 static __global__ void __launch_bounds__(128, HVB_EXPAND_MINB) k_hull_expand(Dev<D> dv, HullDev<D> hd, const u64* __restrict__ q_in, const u32* __restrict__ n_in_ptr,
                                                                       u32* cursor, u64* q_out, u32* q_count, u32 q_cap) {
-    TileDev<1> tile;
+    TileDev<32> tile;
     LocalStats ls = {};
     const u32 n_in = min(*n_in_ptr, q_cap);
     for (;;) {
-        const u32 idx = atomicAdd(cursor, 1u);
-        const bool live = idx < n_in;
-        if (!__any_sync(0xffffffffu, live)) break;
-        if (live) hull_step<D, TileDev<1> >(dv, hd, tile, q_in[idx], q_out, q_count, q_cap, ls);
+        u32 idx = 0;
+        if (tile.lane() == 0) idx = atomicAdd(cursor, 1u);
+        idx = tile.shfl(idx, 0);
+        if (idx >= n_in) break;
+        hull_step<D, TileDev<32> >(dv, hd, tile, q_in[idx], q_out, q_count, q_cap, ls);
         __syncwarp();
     }
     flush_stats(ls, dv.ctr);
