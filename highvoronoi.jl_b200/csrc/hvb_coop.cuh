@@ -500,7 +500,7 @@ __device__ __forceinline__ Best coop_min_t(const Dev<D>& dv, CoopShared<D>& sh, 
                 redone = true;
             }
             else if (best.t <= Ts0 || !(Tst < INFINITY)) active = false;
-            else { scale *= 2.0; redone = false; }
+            else { scale *= dv.probe_growth; redone = false; }
             if (++stage >= 96) active = false;
         }
     }

@@ -176,6 +176,7 @@ struct Dev {
     const unsigned char* active;       // [n] 1 = this context walks the edges of that cell (slab / Iter)
     double plane_tol;                  // raycast-types.jl:229
     double probe_scale;
+    double probe_growth;               // radius factor from one probe stage to the next (2; the hull walk jumps to the half-space)
     int fp32_filter;
     // ---- written during the search -------------------------------------------------------------------
     int* vsig;                         // [vcap][D+1] sorted internal ids; vsig[v][0] = -1 marks a dead record
@@ -989,7 +990,7 @@ HVB_HD Best min_t_query(const Dev<D>& dv, const T& tile, const RayQ<D>& q, Local
         }
         if (st.rejected) { st.rejected = false; st.tighten = false; continue; }     // redo this stage, FP64 decides everything
         if (best.t <= Ts0 || !(Tst < INFINITY)) break;
-        scale *= 2.0;
+        scale *= dv.probe_growth;
     }
     return best;
 }

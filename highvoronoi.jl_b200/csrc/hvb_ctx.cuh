@@ -328,6 +328,7 @@ struct Ctx : hvb_ctx {
         dv.plane_tol = prm.plane_tolerance;
         dv.probe_scale = prm.probe_scale > 1.0 ? prm.probe_scale : default_probe_scale(D);
         dv.fp32_filter = prm.fp32_filter;
+        dv.probe_growth = 2.0;
         if (prm.tile_size == 1 || prm.tile_size == 2 || prm.tile_size == 4 || prm.tile_size == 8 || prm.tile_size == 16 || prm.tile_size == 32) G = prm.tile_size;
         debug = getenv("HVB_DEBUG") != nullptr;
         if (const char* e = getenv("HVB_PERSISTENT")) prm.persistent = atoi(e);      // tuning / test runs: force a walk variant
@@ -772,7 +773,11 @@ struct Ctx : hvb_ctx {
         CK(cudaStreamSynchronize(stream));
         const int start = (int)((unsigned long long)*h_extra.p & 0xffffffffULL);
         int cur = 0;
-        k_hull_seed<D><<<1, 32, 0, stream>>>(dv, hd, start, axis, q[cur].p, &sc.p->rnd[cur].qcount, qcap); ++launches;
+        // most walks near the hull that find nothing in the first probe ball find nothing at all: the second stage is the
+        // half-space (exact; a candidate met on the way shrinks it to a ball again)
+        Dev<D> dh = dv;
+        dh.probe_growth = 1e9;
+        k_hull_seed<D><<<1, 32, 0, stream>>>(dh, hd, start, axis, q[cur].p, &sc.p->rnd[cur].qcount, qcap); ++launches;
         int64_t rounds = 0, items = 0;
         size_t n_ev = 0;
         for (;;) {
@@ -789,7 +794,7 @@ struct Ctx : hvb_ctx {
             CK(cudaMemsetAsync(&sc.p->rnd[nxt], 0, sizeof(Round), stream));
             cudaEvent_t e0 = pool_event(n_ev++), e1 = pool_event(n_ev++);
             CK(cudaEventRecord(e0, stream));
-            k_hull_expand<D><<<std::min(blocks_for((int64_t)cnt * 32, 128), sms * 16), 128, 0, stream>>>(dv, hd, q[cur].p, &sc.p->rnd[cur].qcount, &sc.p->rnd[cur].cursor,
+            k_hull_expand<D><<<std::min(blocks_for((int64_t)cnt * 32, 128), sms * 16), 128, 0, stream>>>(dh, hd, q[cur].p, &sc.p->rnd[cur].qcount, &sc.p->rnd[cur].cursor,
                                                                                        q[nxt].p, &sc.p->rnd[nxt].qcount, qcap);
             CK(cudaEventRecord(e1, stream));
             ++launches; ++rounds; items += cnt;
@@ -802,7 +807,7 @@ struct Ctx : hvb_ctx {
         nvert = 0; nrays = 0;
         if (nf > 0) {
             CK(ray_edge.ensure((size_t)nf * D)); CK(ray_base.ensure((size_t)nf * D)); CK(ray_dir.ensure((size_t)nf * D)); CK(ray_node.ensure(nf));
-            k_final_facets<D><<<blocks_for(nf, 128), 128, 0, stream>>>(dv, hd, perm.p, nf, ray_edge.p, ray_base.p, ray_dir.p, ray_node.p, &sc.p->ray_out); ++launches;
+            k_final_facets<D><<<blocks_for(nf, 128), 128, 0, stream>>>(dh, hd, perm.p, nf, ray_edge.p, ray_base.p, ray_dir.p, ray_node.p, &sc.p->ray_out); ++launches;
         }
         CK(cudaEventRecord(ev_d, stream));
         int rc = read_scalars(); if (rc) return rc;

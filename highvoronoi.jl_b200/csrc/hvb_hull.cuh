@@ -82,6 +82,27 @@ HVB_HD u32 facet_insert(const Dev<D>& dv, const HullDev<D>& hd, const int* E, u3
     }
 }
 
+// is facet E (D sorted ids) stored already?
+template <int D>
+HVB_HD bool facet_known(const HullDev<D>& hd, const int* E) {
+    const u64 h = hash_facet<D>(E, -1);
+    u64 fp = (h >> 32) << 32;
+    if (fp == 0) fp = 1ULL << 32;
+    u64 slot = h & hd.fmask;
+    for (;;) {
+        const u64 s = ld_cg(hd.ftab + slot);
+        if (s == 0) return false;
+        if ((s >> 32) == (fp >> 32)) {
+            const int* p = hd.fsig + (size_t)((u32)(s & 0xffffffffu) - 1u) * D;
+            bool eq = true;
+#pragma unroll
+            for (int k = 0; k < D; ++k) eq &= (ld_cg(p + k) == E[k]);
+            if (eq) return true;
+        }
+        slot = (slot + 1) & hd.fmask;
+    }
+}
+
 // registers ridge (E minus position j) of facet f: true = first facet at this ridge (a walk goes around it), false = the
 // ridge has both its facets now
 template <int D>
@@ -169,6 +190,14 @@ HVB_HD void hull_step(const Dev<D>& dv, const HullDev<D>& hd, const T& tile, u64
     // the lanes of the tile build the same ray and share the rows of the query (the half-space of an unbounded edge spans
     // the whole grid: one lane per ray is hopeless here); lane 0 alone touches the tables
     if (!ray_setup<D>(dv, ((u64)v0 << 3) | (u64)kd0, q, sig, v, kd)) { ls.seed_fail += (tile.lane() == 0); return; }
+    {
+        // a walk that arrives at a facet another walk has certified already ends here: certifying an unbounded edge means
+        // scanning a half-space of the grid, the most expensive query there is, and every facet is reached over several ridges
+        int E[D];
+#pragma unroll
+        for (int j = 0; j < D; ++j) E[j] = (j < kd) ? sig[j] : sig[j + 1];
+        if (facet_known<D>(hd, E)) return;
+    }
     const Best best = min_t_query<D, T>(dv, tile, q, ls);
     if (tile.lane() != 0) return;
     if (best.id < 0) { hull_facet_found<D>(dv, hd, sig, v, kd, q.u, q_out, q_count, q_cap); return; }

@@ -53,7 +53,7 @@ static SimResult* run(int64_t n, const double* xs, int P, const double* base, co
     }
     std::vector<unsigned char> active(n, 1), hasv(n, 0);
     dv.cell_start = cstart.data(); dv.x32 = x32.data(); dv.x64 = x64.data(); dv.planes = &ps; dv.active = active.data();
-    dv.plane_tol = 1e-12; dv.probe_scale = probe_scale > 1.0 ? probe_scale : 1.3; dv.fp32_filter = fp32;
+    dv.plane_tol = 1e-12; dv.probe_scale = probe_scale > 1.0 ? probe_scale : 1.3; dv.probe_growth = 2.0; dv.fp32_filter = fp32;
     int64_t vcap = estimate_vertices(D, n, P) * 2;
     std::vector<int> vsig(vcap * (D + 1)); std::vector<double> vr(vcap * D);
     u32 vcount = 0;
@@ -190,7 +190,7 @@ static HullResult* run_hull(int64_t n, const double* xs, int ppc) {
     PlaneSet ps; memset(&ps, 0, sizeof(ps));
     std::vector<unsigned char> active(n, 1), hasv(n, 0);
     dv.cell_start = cstart.data(); dv.x32 = x32.data(); dv.x64 = x64.data(); dv.planes = &ps; dv.active = active.data();
-    dv.plane_tol = 1e-12; dv.probe_scale = default_probe_scale(D); dv.fp32_filter = 1;
+    dv.plane_tol = 1e-12; dv.probe_scale = default_probe_scale(D); dv.probe_growth = 1e9; dv.fp32_filter = 1;
     int64_t vcap = estimate_vertices(D, n, 0);
     std::vector<int> vsig(vcap * (D + 1)); std::vector<double> vr(vcap * D);
     u32 vcount = 0;
