@@ -379,22 +379,23 @@ class ConvexHull:
     """ConvexHull(xs) (chull.jl:213-238, docs/src/man/convexhull.md): `len(cv)` surface elements, `cv[i] = (sig, r, u)` with
     sig the d generating nodes (1-based, sorted), r a point of the facet's plane and u its outer unit normal.
 
-    General position only.  The facets are walked directly on the device (hvb_convex_hull, csrc/hvb_hull.cuh: a hull facet is an
-    unbounded Voronoi edge, two facets that share a ridge are the two unbounded edges of one 2-face of the diagram, so the walk
-    goes around those 2-faces with ordinary min-t queries) -- the interior of the tessellation is never computed.
-    via="search" keeps round 1's way (a complete search on the unbounded domain, facets read off its unbounded edges): same
-    result, used by the tests as a cross-check."""
+    General position only.  The hull is wrapped facet by facet on the device (hvb_convex_hull, csrc/hvb_wrap.cuh: one query per
+    open ridge, a query streams all generators through shared memory) -- the interior of the tessellation is never computed.
+    via="walk": the first device version (around the unbounded 2-faces of the Voronoi diagram with ordinary min-t queries,
+    csrc/hvb_hull.cuh); via="search": round 1's way (a complete search on the unbounded domain, facets read off its unbounded
+    edges).  Same result all three ways; the tests use the other two as cross-checks."""
 
-    def __init__(self, xs, intro="", nthreads=None, method=None, options=None, via="walk"):
+    def __init__(self, xs, intro="", nthreads=None, method=None, options=None, via="wrap", searcher=None):
         xs = VoronoiNodes(xs)
-        s = Raycast(xs, domain=Boundary(), options=options or RaycastParameter())
+        # searcher: a Raycast(xs, domain=Boundary()) to reuse (a warm context allocates nothing); it stays open
+        s = searcher if searcher is not None else Raycast(xs, domain=Boundary(), options=options or RaycastParameter())
         try:
             if via == "search":
                 mesh, _ = voronoi(xs, searcher=s, copy=True)
                 edge, udir, base = mesh.ray_edge, mesh.ray_dir, mesh.ray_base
             else:
                 L, ctx = _abi.lib(), s._ctx
-                _abi.check(L.hvb_convex_hull(ctx), ctx)
+                _abi.check(L.hvb_convex_hull_via(ctx, {"wrap": 0, "walk": 1}[via]), ctx)
                 nv, nr = ctypes.c_int64(), ctypes.c_int64()
                 _abi.check(L.hvb_counts(ctx, ctypes.byref(nv), ctypes.byref(nr), None), ctx)
                 d = xs.shape[1]
@@ -409,7 +410,8 @@ class ConvexHull:
             self.u = udir[order]
             base = base[order]
         finally:
-            s.close()
+            if searcher is None:
+                s.close()
         self.xs = xs
         # the reference projects the stored point onto the facet's plane (chull.jl:224-232)
         self.r = base + self.u * ((xs[self.sig[:, 0] - 1] - base) * self.u).sum(axis=1)[:, None] if len(self.sig) else base

@@ -101,7 +101,8 @@ int hvb_search(hvb_ctx* ctx, const int64_t* cells, int64_t ncells, const int64_t
     if (!ctx) return HVB_EINVAL;
     return ctx->search(cells, ncells, seed_sig, seed_r, nseed, sig_stride);
 }
-int hvb_convex_hull(hvb_ctx* ctx) { return ctx ? ctx->convex_hull() : HVB_EINVAL; }
+int hvb_convex_hull(hvb_ctx* ctx) { return ctx ? ctx->convex_hull(0) : HVB_EINVAL; }
+int hvb_convex_hull_via(hvb_ctx* ctx, int method) { return ctx ? ctx->convex_hull(method) : HVB_EINVAL; }
 int hvb_counts(hvb_ctx* ctx, int64_t* nvert, int64_t* nrays, int64_t* max_siglen) { return ctx ? ctx->counts(nvert, nrays, max_siglen) : HVB_EINVAL; }
 int hvb_fetch_vertices(hvb_ctx* ctx, int64_t* sig, double* r) { return ctx ? ctx->fetch_vertices(sig, r) : HVB_EINVAL; }
 int hvb_fetch_vertices_range(hvb_ctx* ctx, int64_t first, int64_t count, int64_t* sig, double* r) { return ctx ? ctx->fetch_vertices_range(first, count, sig, r) : HVB_EINVAL; }

@@ -449,7 +449,7 @@ struct Ctx : hvb_ctx {
         for (int k = 0; k < D; ++k) { blo[k] = h_sc.p->bbox[k]; bhi[k] = h_sc.p->bbox[D + k]; }
         int ppc = prm.points_per_cell > 0 ? prm.points_per_cell : default_points_per_cell(D);
         ncells = setup_grid<D>(dv, blo, bhi, n, ppc);
-        CK(x64.ensure((size_t)n * D)); CK(x32.ensure((size_t)n * X32<D>::STRIDE));
+        CK(x64.ensure((size_t)n * D)); CK(x32.ensure((size_t)(n + 4) * X32<D>::STRIDE));      // + 4: the hull's bulk copies read whole groups of four generators
         CK(perm.ensure(n)); CK(inv.ensure(n)); CK(cell_of.ensure(n)); CK(unseeded_list.ensure(n));
         CK(cell_start.ensure(ncells + 1)); CK(cell_cur.ensure(ncells + 1));
         CK(active.ensure(n)); CK(has_vertex.ensure(n));
@@ -746,7 +746,110 @@ struct Ctx : hvb_ctx {
 
     // ---- convex hull by the facet walk (hvb_hull.cuh; replaces systematic_chull, chull.jl:241-387) -------------------
     DBuf<int> h_fsig; DBuf<u32> h_fitem; DBuf<double> h_fu; DBuf<u64> h_ftab, h_rtab; DBuf<unsigned long long> h_arg;
-    int convex_hull() override {
+    // ---- convex hull by gift wrapping (hvb_wrap.cuh): the default ----------------------------------------------------
+    DBuf<unsigned char> w_wq; DBuf<double> w_pc1, w_pc2; DBuf<int> w_pid; DBuf<u64> w_q[2]; DBuf<u32> w_words; DBuf<WrapSeed> w_seed;
+    HBuf<u32> hw_words;
+    int convex_hull(int method) override {
+        if (method == 1) return convex_hull_walk();
+        if (method != 0) { err = "hvb_convex_hull_via: method 0 (gift wrapping) or 1 (walk around the unbounded 2-faces)"; return HVB_EINVAL; }
+        if (P != 0 || periodic) { err = "the convex hull is computed on the unbounded domain: create the context without planes"; return HVB_EINVAL; }
+        if (std::max(1, prm.world) > 1) { err = "the convex hull runs on one GPU"; return HVB_EINVAL; }
+        if (n <= D) { err = "the convex hull needs more than dim generators"; return HVB_EINVAL; }
+        CK(cudaSetDevice(prm.device));
+        have_result = false; staged = false; staged_r = staged_sig64 = staged_sig32 = false; nb_staged32 = false; nb_total = -1; have_flags = false;
+        launches = 0;
+        CK(h_arg.ensure(16)); CK(w_words.ensure(32)); CK(hw_words.ensure(32)); CK(w_seed.ensure(16));
+        const int tb = sms * 4;
+        const int grid_small = sms * 2;
+        u32 fcap = (u32)std::min<int64_t>(std::max<int64_t>(prm.vertex_capacity > 0 ? prm.vertex_capacity : 0, 1 << 16), 0x07ffffff);
+        int64_t rounds = 0;
+        u32 nf = 0;
+        st.capacity_retries = 0;
+        for (int attempt = 0;; ++attempt) {
+            HullDev<D> hd;
+            WrapDev<D> wd;
+            const u64 fts = next_pow2(2 * (u64)fcap), rts = next_pow2(2 * (u64)fcap * D);
+            const u32 wq_cap = fcap, wqueue = (u32)std::min<u64>((u64)fcap * D, 0x7fffffffULL);
+            const u32 pcap = std::max<u32>(wq_cap, (u32)tb * 128u);
+            CK(h_fsig.ensure((size_t)fcap * D)); CK(h_fitem.ensure(fcap)); CK(h_fu.ensure((size_t)fcap * D)); CK(h_ftab.ensure(fts)); CK(h_rtab.ensure(rts));
+            CK(w_wq.ensure((size_t)wq_cap * sizeof(WrapQuery<D>))); CK(w_pc1.ensure(pcap)); CK(w_pc2.ensure(pcap)); CK(w_pid.ensure(pcap));
+            CK(w_q[0].ensure(wqueue)); CK(w_q[1].ensure(wqueue));
+            hd.fsig = h_fsig.p; hd.fitem = h_fitem.p; hd.fu = h_fu.p; hd.fcount = &sc.p->ray_count; hd.fcap = fcap;
+            hd.ftab = h_ftab.p; hd.fmask = fts - 1; hd.rtab = h_rtab.p; hd.rmask = rts - 1;
+            wd.wq = (WrapQuery<D>*)w_wq.p; wd.wq_cap = wq_cap; wd.pc1 = w_pc1.p; wd.pc2 = w_pc2.p; wd.pid = w_pid.p; wd.pcap = pcap;
+            wd.q[0] = w_q[0].p; wd.q[1] = w_q[1].p; wd.qcap = wqueue; wd.qcount = w_words.p; wd.nq = w_words.p + 2; wd.seed = w_seed.p;
+            wrap_tolerances<D>(dv.ext, wd.E32, wd.tinyA);
+            if (!prm.fp32_filter) wd.E32 = INFINITY;
+            CK(cudaEventRecord(ev_a, stream));            // device time of the walk: buffers exist (a warm context allocates nothing)
+            CK(cudaMemsetAsync(h_ftab.p, 0, fts * sizeof(u64), stream));
+            CK(cudaMemsetAsync(h_rtab.p, 0, rts * sizeof(u64), stream));
+            CK(cudaMemsetAsync(ctr.p, 0, sizeof(Counters), stream));
+            CK(cudaMemsetAsync(sc.p, 0, sizeof(Scalars), stream));
+            CK(cudaMemsetAsync(h_arg.p, 0, 16 * sizeof(unsigned long long), stream));
+            CK(cudaMemsetAsync(w_words.p, 0xff, 32 * sizeof(u32), stream));
+            k_wrap_extremes<D><<<std::min(blocks_for(n, 256), sms * 4), 256, 0, stream>>>(x64.p, (int)n, h_arg.p, 0, w_words.p + 8);
+            k_wrap_extremes<D><<<std::min(blocks_for(n, 256), sms * 4), 256, 0, stream>>>(x64.p, (int)n, h_arg.p, 1, w_words.p + 8);
+            k_wrap_init<D><<<1, 1, 0, stream>>>(wd, w_words.p + 8);
+            launches += 3;
+            int cur = 0;
+            rounds = 0;
+            bool overflow = false;
+            // the host enqueues `batch` rounds and only then looks at the queue: a round after the end is three empty launches
+            for (int batch = D + 3;; batch = 4) {
+                for (int b = 0; b < batch; ++b) {
+                    k_wrap_prepare<D><<<grid_small, 128, 0, stream>>>(dv, hd, wd, cur);
+                    k_wrap_scan<D><<<tb, 128, 0, stream>>>(dv, wd, cur, tb);
+                    k_wrap_commit<D><<<grid_small, 128, 0, stream>>>(dv, hd, wd, cur, tb);
+                    launches += 3; ++rounds;
+                    cur = 1 - cur;
+                }
+                CK(cudaMemcpyAsync(hw_words.p, w_words.p, 4 * sizeof(u32), cudaMemcpyDeviceToHost, stream));
+                int rc = read_scalars(); if (rc) return rc;
+                if (h_ctr.p->flags & FLAG_OVERFLOW_MASK) { overflow = true; break; }
+                if ((h_ctr.p->degenerate > 0 || (h_ctr.p->flags & FLAG_DEGEN)) && !prm.on_degenerate) {
+                    st.degenerate = (int64_t)std::max<u64>(h_ctr.p->degenerate, 1);
+                    err = "non-general position: a hull facet with more than dim generators was met";
+                    return HVB_EDEGENERATE;
+                }
+                if (hw_words.p[cur] == 0) break;
+                if (rounds > 1000000) { err = "hull walk does not terminate"; return HVB_EINCOMPLETE; }
+            }
+            CK(cudaEventRecord(ev_c, stream));
+            if (overflow) {
+                if (attempt >= 4 || fcap >= 0x07ffffff) { err = "hull walk: capacity exhausted (raise vertex_capacity)"; return HVB_ENOMEM; }
+                fcap = (u32)std::min<u64>((u64)fcap * 8, 0x07ffffff);
+                ++st.capacity_retries;
+                continue;
+            }
+            if (h_ctr.p->seed_fail > 0) { err = "hull walk: a query found no generator (fewer than dim + 1 generators in general position?)"; return HVB_EINCOMPLETE; }
+            nf = std::min<u32>(h_sc.p->ray_count, fcap);
+            nvert = 0; nrays = 0;
+            if (nf > 0) { CK(ray_edge.ensure((size_t)nf * D)); CK(ray_base.ensure((size_t)nf * D)); CK(ray_dir.ensure((size_t)nf * D)); CK(ray_node.ensure(nf)); }
+            CK(cudaEventRecord(ev_b, stream));
+            if (nf > 0) {
+                k_final_facets_wrap<D><<<blocks_for(nf, 128), 128, 0, stream>>>(dv, hd, perm.p, nf, ray_edge.p, ray_base.p, ray_dir.p, ray_node.p, &sc.p->ray_out, &sc.p->pflags); ++launches;
+            }
+            break;
+        }
+        CK(cudaEventRecord(ev_d, stream));
+        int rc = read_scalars(); if (rc) return rc;
+        nrays = h_sc.p->ray_out;
+        if (h_sc.p->pflags > 0 && !prm.on_degenerate) { err = "non-general position: a hull facet whose generators do not span a hyperplane"; return HVB_EDEGENERATE; }
+        float ms = 0;
+        cudaEventElapsedTime(&ms, ev_a, ev_c); st.ms_search = ms;
+        cudaEventElapsedTime(&ms, ev_b, ev_d); st.ms_finalize = ms;
+        const Counters& c = *h_ctr.p;
+        st.ms_expand_kernel = st.ms_search; st.expand_launches = rounds; st.expand_items = (int64_t)c.raycasts; st.rounds = rounds;
+        st.vertices = 0; st.unique_vertices = 0; st.rays = nrays; st.raycasts = (int64_t)c.raycasts; st.duplicate_hits = (int64_t)c.dup_hits; st.closed_skips = (int64_t)c.closed_skips;
+        st.candidates_fp32 = (int64_t)c.cand32; st.candidates_fp64 = (int64_t)c.cand64; st.rows_scanned = 0; st.probe_stages = (int64_t)c.stages;
+        st.seeds = 1; st.degenerate = (int64_t)c.degenerate; st.kernel_launches = launches; st.ms_seed = 0; st.ms_neighbors = 0;
+        st.ms_rows_sort = 0; st.ms_stage_wait = 0; st.rejected = 0; st.suboptimal = 0; st.exchange_bytes = 0; st.periodic_retries = 0;
+        have_result = true;
+        return HVB_OK;
+    }
+    // the first device hull walk (hvb_hull.cuh): around the unbounded 2-faces of the diagram with min-t queries.  Kept as
+    // hvb_convex_hull_via(ctx, 1): same facets, a cross-check of the wrapping on the Voronoi side
+    int convex_hull_walk() {
         if (P != 0 || periodic) { err = "the convex hull is computed on the unbounded domain: create the context without planes"; return HVB_EINVAL; }
         if (std::max(1, prm.world) > 1) { err = "the convex hull runs on one GPU"; return HVB_EINVAL; }
         CK(cudaSetDevice(prm.device));

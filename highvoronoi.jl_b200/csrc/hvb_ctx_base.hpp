@@ -22,7 +22,7 @@ struct hvb_ctx {
     virtual int clean_affected(const int64_t* sig, const double* r, int64_t nv, int stride, int64_t first_new, int64_t n_new, uint8_t* keep, uint8_t* affected) = 0;
     virtual int set_points(int64_t n, const double* xs) = 0;
     virtual int search(const int64_t* cells, int64_t ncells, const int64_t* seed_sig, const double* seed_r, int64_t nseed, int stride) = 0;
-    virtual int convex_hull() = 0;
+    virtual int convex_hull(int method) = 0;
     virtual int counts(int64_t* nv, int64_t* nr, int64_t* msl) = 0;
     virtual int fetch_vertices(int64_t* sig, double* r) = 0;
     virtual int view_vertices(const int64_t** sig, const double** r, int64_t* nv) = 0;

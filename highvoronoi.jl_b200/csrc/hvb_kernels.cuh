@@ -6,6 +6,7 @@
 #include "hvb_core.cuh"
 #include "hvb_geometry.cuh"
 #include "hvb_hull.cuh"
+#include "hvb_wrap.cuh"
 
 namespace hvb {
 
@@ -625,6 +626,253 @@ static __global__ void k_final_facets(Dev<D> dv, HullDev<D> hd, const int* __res
         edge[(size_t)o * D + k] = e[k];
         base[(size_t)o * D + k] = dv.vr[(size_t)v * D + k];
         dir[(size_t)o * D + k] = hd.fu[(size_t)f * D + k];
+    }
+    node[o] = e[0];
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// convex hull by gift wrapping (hvb_wrap.cuh): three kernels per round, all sized by device-side counts so that the host
+// enqueues rounds back to back and looks at the queue only every few rounds
+// ------------------------------------------------------------------------------------------------------------
+// extreme generators along every axis (search_max, chull.jl:244), exact in FP64: pass 0 the extreme values (order-preserving
+// map of the double's bits; slot 2 k: largest along axis k, slot 2 k + 1: smallest), pass 1 the smallest position that
+// holds each
+template <int D>
+static __global__ void k_wrap_extremes(const double* __restrict__ x64, int n, unsigned long long* __restrict__ best_val, int pass,
+                                       unsigned int* __restrict__ best_pos) {
+    unsigned long long best[2 * D];
+    unsigned int pos[2 * D];
+#pragma unroll
+    for (int a = 0; a < 2 * D; ++a) { best[a] = pass ? __ldcg(best_val + a) : 0ULL; pos[a] = 0xffffffffu; }
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+#pragma unroll
+        for (int k = 0; k < D; ++k) {
+            unsigned long long b = (unsigned long long)__double_as_longlong(x64[(size_t)i * D + k]);
+            b = (b & 0x8000000000000000ULL) ? ~b : (b | 0x8000000000000000ULL);
+            const unsigned long long nb = ~b;
+            if (!pass) { best[2 * k] = b > best[2 * k] ? b : best[2 * k]; best[2 * k + 1] = nb > best[2 * k + 1] ? nb : best[2 * k + 1]; }
+            else {
+                if (b == best[2 * k]) pos[2 * k] = min(pos[2 * k], (unsigned int)i);
+                if (nb == best[2 * k + 1]) pos[2 * k + 1] = min(pos[2 * k + 1], (unsigned int)i);
+            }
+        }
+    }
+#pragma unroll
+    for (int a = 0; a < 2 * D; ++a) {
+        if (!pass) {
+            unsigned long long v = best[a];
+#pragma unroll
+            for (int m = 16; m >= 1; m >>= 1) { const unsigned long long o = __shfl_xor_sync(0xffffffffu, v, m); v = o > v ? o : v; }
+            if ((threadIdx.x & 31) == 0) atomicMax(best_val + a, v);
+        } else {
+            unsigned int v = pos[a];
+#pragma unroll
+            for (int m = 16; m >= 1; m >>= 1) v = min(v, __shfl_xor_sync(0xffffffffu, v, m));
+            if ((threadIdx.x & 31) == 0 && v != 0xffffffffu) atomicMin(best_pos + a, v);
+        }
+    }
+}
+// the first seed steps: rotate the hyperplanes {x_k = max} and {x_k = min} about the extreme generators
+template <int D>
+static __global__ void k_wrap_init(WrapDev<D> wd, const unsigned int* __restrict__ start) {
+    for (int a = 0; a < 2 * D; ++a) {
+        WrapSeed& sd = wd.seed[a];
+        sd.ids[0] = (int)start[a]; sd.cnt = 1;
+        for (int k = 0; k < D; ++k) sd.u[k] = (k == (a >> 1)) ? ((a & 1) ? -1.0 : 1.0) : 0.0;
+        wd.q[0][a] = WRAP_SEED_ENTRY + (u64)a;
+    }
+    wd.qcount[0] = 2 * D; wd.qcount[1] = 0; wd.nq[0] = 0; wd.nq[1] = 0;
+}
+template <int D>
+static __global__ void __launch_bounds__(128) k_wrap_prepare(Dev<D> dv, HullDev<D> hd, WrapDev<D> wd, int cur) {
+    LocalStats ls = {};
+    const u32 cnt = min(__ldcg(wd.qcount + cur), wd.qcap);
+    if (blockIdx.x == 0 && threadIdx.x == 0) { wd.qcount[1 - cur] = 0; wd.nq[1 - cur] = 0; }
+    for (u32 i = blockIdx.x * blockDim.x + threadIdx.x; i < cnt; i += gridDim.x * blockDim.x) {
+        WrapQuery<D> w;
+        if (!wrap_prepare<D>(dv, hd, wd, wd.q[cur][i], w, ls)) continue;
+        const u32 qi = atomicAdd(wd.nq + cur, 1u);
+        if (qi < wd.wq_cap) wd.wq[qi] = w;
+        else atomicOr(&dv.ctr->flags, (u32)FLAG_QFULL);
+    }
+    __syncwarp();
+    flush_stats(ls, dv.ctr);
+}
+
+__device__ __forceinline__ u32 wrap_smem(const void* p) { return (u32)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void wrap_mbar_init(void* bar, u32 count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(wrap_smem(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void wrap_mbar_expect(void* bar, u32 bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(wrap_smem(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void wrap_bulk_load(void* dst, const void* src, u32 bytes, void* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(wrap_smem(dst)), "l"(src), "r"(bytes), "r"(wrap_smem(bar)) : "memory");
+}
+__device__ __forceinline__ void wrap_mbar_wait(void* bar, u32 parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WRAP_WAIT:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra WRAP_DONE;\n"
+        "bra WRAP_WAIT;\n"
+        "WRAP_DONE:\n"
+        "}\n" ::"r"(wrap_smem(bar)), "r"(parity) : "memory");
+}
+
+// The stream.  A block of 4 warps takes work items (query tile, chunk of the generators): QW of its warps own 32 queries
+// each (one per lane), the other PW = 4 / QW split every staged tile among them.  The FP32 coordinates of the chunk travel
+// through a ring of HVB_WRAP_NS shared-memory tiles filled by the TMA unit (one elected thread issues cp.async.bulk, the
+// bytes arrive on the tile's mbarrier); all lanes of a warp read the same staged generator, so a tile is read once per
+// warp and broadcast.  Partial results (best, runner-up, id per query and slot) go to global memory; k_wrap_commit merges.
+template <int D>
+static __global__ void __launch_bounds__(128) k_wrap_scan(Dev<D> dv, WrapDev<D> wd, int cur, int tb) {
+    constexpr int S = X32<D>::STRIDE, TP = HVB_WRAP_TP, NS = HVB_WRAP_NS;
+    __shared__ __align__(128) float tile[NS][TP * S];
+    __shared__ __align__(8) unsigned long long full[NS];
+    __shared__ double m_c1[4][32], m_c2[4][32];
+    __shared__ int m_id[4][32];
+    const u32 nq = min(__ldcg(wd.nq + cur), wd.wq_cap);
+    if (nq == 0) return;
+    const WrapShape sh = wrap_shape(nq, dv.n, tb, wd.pcap);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int qw = warp % sh.QW, part = warp / sh.QW;
+    if (threadIdx.x == 0) {
+#pragma unroll
+        for (int s = 0; s < NS; ++s) wrap_mbar_init(&full[s], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    LocalStats ls = {};
+    u32 it = 0;                                       // tiles this block has consumed: stage = it % NS, parity = (it / NS) & 1
+    const int nwork = sh.ntile * sh.PCH;
+    for (int wk = blockIdx.x; wk < nwork; wk += gridDim.x) {
+        const int qt = wk / sh.PCH, ch = wk - qt * sh.PCH;
+        const int p0 = ch * sh.chunk;
+        const int npts = max(min(p0 + sh.chunk, dv.n) - p0, 0);
+        const int ntl = (npts + TP - 1) / TP;
+        const u32 q = (u32)(qt * 32 * sh.QW + qw * 32 + lane);
+        const bool live = q < nq;
+        const WrapQuery<D>& w = wd.wq[live ? q : 0];
+        WrapLane<D> s;
+        wrap_lane_init<D>(w, s);
+        if (threadIdx.x == 0) {
+            for (int t = 0; t < NS && t < ntl; ++t) {
+                const int c4 = (min(TP, npts - t * TP) + 3) & ~3;
+                const u32 bytes = (u32)(c4 * S * sizeof(float));
+                const int st = (int)((it + t) % NS);
+                wrap_mbar_expect(&full[st], bytes);
+                wrap_bulk_load(tile[st], dv.x32 + (size_t)(p0 + t * TP) * S, bytes, &full[st]);
+            }
+        }
+        for (int t = 0; t < ntl; ++t) {
+            const int st = (int)((it + t) % NS);
+            wrap_mbar_wait(&full[st], ((it + t) / NS) & 1u);
+            const int cnt_t = min(TP, npts - t * TP);
+            const int per = ((cnt_t + sh.PW * 4 - 1) / (sh.PW * 4)) * 4;
+            const int a = part * per, b = min(a + per, cnt_t);
+            if (live && b > a) wrap_scan<D>(dv, w, tile[st] + a * S, p0 + t * TP + a, b - a, wd.tinyA, wd.E32, s, ls);
+            __syncthreads();                          // everyone is done with this tile
+            if (threadIdx.x == 0 && t + NS < ntl) {
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                const int c4 = (min(TP, npts - (t + NS) * TP) + 3) & ~3;
+                const u32 bytes = (u32)(c4 * S * sizeof(float));
+                wrap_mbar_expect(&full[st], bytes);
+                wrap_bulk_load(tile[st], dv.x32 + (size_t)(p0 + (t + NS) * TP) * S, bytes, &full[st]);
+            }
+        }
+        it += (u32)ntl;
+        if (live) wrap_settle<D>(dv, w, wd.tinyA, wd.E32, s, ls);
+        // the warps that shared the tiles of these queries merge in shared memory: one partial result per (chunk, query)
+        if (part > 0) { m_c1[warp][lane] = s.c1; m_c2[warp][lane] = s.c2; m_id[warp][lane] = s.id1; }
+        __syncthreads();
+        if (part == 0 && live) {
+            for (int pp = 1; pp < sh.PW; ++pp) {
+                const int ow = pp * sh.QW + qw;
+                wrap_merge(s.c1, s.id1, s.c2, m_c1[ow][lane], m_id[ow][lane], m_c2[ow][lane]);
+            }
+            const size_t idx = (size_t)ch * nq + q;
+            wd.pc1[idx] = s.c1; wd.pc2[idx] = s.c2; wd.pid[idx] = s.id1;
+        }
+        __syncthreads();
+    }
+    __syncwarp();
+    flush_stats(ls, dv.ctr);
+}
+
+// a warp per query: merge of the partial results, then lane 0 builds the new facet
+template <int D>
+static __global__ void __launch_bounds__(128) k_wrap_commit(Dev<D> dv, HullDev<D> hd, WrapDev<D> wd, int cur, int tb) {
+    LocalStats ls = {};
+    const u32 nq = min(__ldcg(wd.nq + cur), wd.wq_cap);
+    const WrapShape sh = wrap_shape(nq, dv.n, tb, wd.pcap);
+    const int slots = sh.PCH;
+    const int lane = threadIdx.x & 31;
+    const u32 nwarps = (gridDim.x * blockDim.x) >> 5;
+    for (u32 q = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; q < nq; q += nwarps) {
+        double c1 = -INFINITY, c2 = -INFINITY;
+        int g = -1;
+        for (int sl = lane; sl < slots; sl += 128) {
+            // four independent loads in flight per lane (the loop is a chain of memory round trips otherwise)
+            double a1[4], a2[4]; int ai[4];
+#pragma unroll
+            for (int r = 0; r < 4; ++r) {
+                const bool in = sl + 32 * r < slots;
+                const size_t idx = (size_t)(in ? sl + 32 * r : sl) * nq + q;
+                a1[r] = __ldcg(wd.pc1 + idx); a2[r] = __ldcg(wd.pc2 + idx); ai[r] = in ? __ldcg(wd.pid + idx) : -1;
+                if (!in) { a1[r] = -INFINITY; a2[r] = -INFINITY; }
+            }
+#pragma unroll
+            for (int r = 0; r < 4; ++r) wrap_merge(c1, g, c2, a1[r], ai[r], a2[r]);
+        }
+#pragma unroll
+        for (int m = 16; m >= 1; m >>= 1) {
+            const double oc1 = __shfl_xor_sync(0xffffffffu, c1, m), oc2 = __shfl_xor_sync(0xffffffffu, c2, m);
+            const int og = __shfl_xor_sync(0xffffffffu, g, m);
+            wrap_merge(c1, g, c2, oc1, og, oc2);
+        }
+        if (lane == 0) wrap_commit<D>(dv, hd, wd, wd.wq[q], c1, g, c2, 1 - cur, ls);
+        __syncwarp();
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0 && nq > 0) {
+        atomicAdd((u64*)&dv.ctr->raycasts, (u64)nq);
+        atomicAdd((u64*)&dv.ctr->cand32, (u64)nq * (u64)dv.n);
+        atomicAdd((u64*)&dv.ctr->stages, 1ULL);
+    }
+    flush_stats(ls, dv.ctr);
+}
+// facets in caller numbering: edge = the d generators (sorted, 1-based), base = circumcentre of the generators in the
+// facet's hyperplane, dir = outward unit normal -- both recomputed from the generators in ascending caller order, so
+// that the output does not depend on the path that found the facet
+template <int D>
+static __global__ void k_final_facets_wrap(Dev<D> dv, HullDev<D> hd, const int* __restrict__ perm, u32 nf,
+                               long long* __restrict__ edge, double* __restrict__ base, double* __restrict__ dir, long long* __restrict__ node,
+                               u32* __restrict__ out_count, u32* __restrict__ bad) {
+    u32 f = blockIdx.x * blockDim.x + threadIdx.x;
+    if (f >= nf) return;
+    const int* fs = hd.fsig + (size_t)f * D;
+    if (fs[0] < 0) return;
+    const u32 o = atomicAdd(out_count, 1u);
+    long long e[D];
+    int in[D];
+#pragma unroll
+    for (int k = 0; k < D; ++k) { in[k] = fs[k]; e[k] = (long long)perm[in[k]] + 1; }
+    for (int a = 1; a < D; ++a) {
+        const long long key = e[a]; const int ki = in[a];
+        int b = a - 1;
+        while (b >= 0 && e[b] > key) { e[b + 1] = e[b]; in[b + 1] = in[b]; --b; }
+        e[b + 1] = key; in[b + 1] = ki;
+    }
+    double P[D][D], nrm[D], cen[D];
+    for (int i = 0; i < D; ++i)
+        for (int k = 0; k < D; ++k) P[i][k] = dv.x64[(size_t)in[i] * D + k];
+    if (!wrap_facet_geometry<D>(P, hd.fu + (size_t)f * D, nrm, cen)) atomicAdd(bad, 1u);
+    for (int k = 0; k < D; ++k) {
+        edge[(size_t)o * D + k] = e[k];
+        base[(size_t)o * D + k] = cen[k];
+        dir[(size_t)o * D + k] = nrm[k];
     }
     node[o] = e[0];
 }

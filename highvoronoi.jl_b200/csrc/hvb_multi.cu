@@ -282,7 +282,7 @@ struct MultiCtx : hvb_ctx {
     int clean_affected(const int64_t*, const double*, int64_t, int, int64_t, int64_t, uint8_t*, uint8_t*) override {
         err = "refinement runs on a single-GPU context (hvb_create)"; return HVB_EINVAL;
     }
-    int convex_hull() override { err = "the convex hull runs on a single-GPU context (hvb_create)"; return HVB_EINVAL; }
+    int convex_hull(int) override { err = "the convex hull runs on a single-GPU context (hvb_create)"; return HVB_EINVAL; }
     int allgather() override {
         int rc = need_result(); if (rc) return rc;
         rc = each([&](int k) { return sub[k]->allgather(); });

@@ -184,14 +184,19 @@ int hvb_search(hvb_ctx* ctx, const int64_t* cells, int64_t ncells,
                const int64_t* seed_sig, const double* seed_r, int64_t nseed, int sig_stride);
 
 /* Replaces ConvexHull(xs) = systematic_chull (src/chull.jl:238-387: search_max, descent_chull, a queue of facets whose
- * sub-facets are explored by raycast_des3 :485-499, explore_chull_vertex :547) on a context created WITHOUT planes.
- * A hull facet is an unbounded Voronoi edge; two facets that share a ridge are the two unbounded edges of one 2-face of the
- * diagram, so the walk goes around those 2-faces with ordinary min-t queries and never visits the interior of the
- * tessellation (csrc/hvb_hull.cuh).  Afterwards hvb_counts reports nvert = 0 and nrays = number of facets, and
- * hvb_fetch_rays returns them: edge = the dim generators of the facet (sorted, 1-based), base = a point of the ray the
- * facet is dual to, dir = outer unit normal, node = smallest generator.  General position only (a facet with more than dim
- * generators: HVB_EDEGENERATE). */
+ * sub-facets are explored by raycast_des3 :485-499 / peak_direction kd_tree.jl:369-420, explore_chull_vertex :547) on a
+ * context created WITHOUT planes.  The interior of the tessellation is never computed: the hull is wrapped facet by facet
+ * (csrc/hvb_wrap.cuh): one query per open ridge, the query being a stream of all generators through shared memory (TMA
+ * staged) with an FP32 filter and FP64 verification.  Afterwards hvb_counts reports nvert = 0 and nrays = number of facets,
+ * and hvb_fetch_rays returns them: edge = the dim generators of the facet (sorted, 1-based), base = the circumcentre of
+ * those generators inside the facet's hyperplane (the point the reference stores, chull.jl:224-232), dir = outer unit
+ * normal, node = smallest generator; base and dir depend on the facet's generators alone (bitwise reproducible).
+ * General position only (a facet with more than dim generators: HVB_EDEGENERATE). */
 int hvb_convex_hull(hvb_ctx* ctx);
+/* method 0: as hvb_convex_hull; method 1: the walk around the unbounded 2-faces of the Voronoi diagram with the min-t
+ * query of the search (csrc/hvb_hull.cuh; base = a point of the unbounded edge the facet is dual to) -- same facets,
+ * kept as a cross-check of the wrapping on the Voronoi side, much slower. */
+int hvb_convex_hull_via(hvb_ctx* ctx, int method);
 
 /* sizes for the fetch calls; max_siglen is dim+1 (general position) */
 int hvb_counts(hvb_ctx* ctx, int64_t* nvert, int64_t* nrays, int64_t* max_siglen);

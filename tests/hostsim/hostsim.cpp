@@ -14,6 +14,7 @@ static bool g_want_trace = false;
 #include "../../highvoronoi.jl_b200/csrc/hvb_host.hpp"
 #include "../../highvoronoi.jl_b200/csrc/hvb_geometry.cuh"
 #include "../../highvoronoi.jl_b200/csrc/hvb_hull.cuh"
+#include "../../highvoronoi.jl_b200/csrc/hvb_wrap.cuh"
 
 using namespace hvb;
 
@@ -169,7 +170,7 @@ static void areas(int64_t n, const double* xs, int P, const double* base, const 
 }
 
 // convex hull by the facet walk of hvb_hull.cuh, driven sequentially (unbounded domain)
-struct HullResult { int d; int64_t nf; std::vector<int64_t> facet; std::vector<double> normal; int64_t raycasts, records, rounds, degenerate; };
+struct HullResult { int d; int64_t nf; std::vector<int64_t> facet; std::vector<double> normal, centre; int64_t raycasts, records, rounds, degenerate; };
 template <int D>
 static HullResult* run_hull(int64_t n, const double* xs, int ppc) {
     Dev<D> dv;
@@ -231,7 +232,111 @@ static HullResult* run_hull(int64_t n, const double* xs, int ppc) {
     return R;
 }
 
+// convex hull by gift wrapping (hvb_wrap.cuh), driven sequentially: per round prepare -> scan -> commit, as the three kernels
+// of the device do; `slots` cuts the generators into that many pieces whose partial results are merged (the device's chunks)
+template <int D>
+static HullResult* run_wrap(int64_t n, const double* xs, int slots, int fp32) {
+    Dev<D> dv;
+    memset(&dv, 0, sizeof(dv));
+    dv.n = (int)n;
+    double blo[D], bhi[D];
+    for (int k = 0; k < D; ++k) { blo[k] = 1e300; bhi[k] = -1e300; }
+    for (int64_t i = 0; i < n; ++i)
+        for (int k = 0; k < D; ++k) { blo[k] = std::min(blo[k], xs[i * D + k]); bhi[k] = std::max(bhi[k], xs[i * D + k]); }
+    int64_t ncell = setup_grid<D>(dv, blo, bhi, n, default_points_per_cell(D));
+    std::vector<int> cell(n), cstart(ncell + 1, 0), perm(n);
+    for (int64_t i = 0; i < n; ++i) { cell[i] = cell_index<D>(dv, xs + i * D); cstart[cell[i] + 1]++; }
+    for (int64_t c = 0; c < ncell; ++c) cstart[c + 1] += cstart[c];
+    { std::vector<int> cur(cstart.begin(), cstart.end() - 1); for (int64_t i = 0; i < n; ++i) perm[cur[cell[i]]++] = (int)i; }
+    std::vector<double> x64(n * D); std::vector<float> x32((n + 8) * X32<D>::STRIDE, 0.f);
+    for (int64_t i = 0; i < n; ++i)
+        for (int k = 0; k < D; ++k) { x64[i * D + k] = xs[(int64_t)perm[i] * D + k]; x32[i * X32<D>::STRIDE + k] = (float)(x64[i * D + k] - dv.lo[k]); }
+    Counters ctr; memset(&ctr, 0, sizeof(ctr));
+    dv.x32 = x32.data(); dv.x64 = x64.data(); dv.ctr = &ctr;
+    HullDev<D> hd;
+    u32 fcap = (u32)std::max<int64_t>(1 << 12, 64 * n), fcount = 0;
+    std::vector<int> fsig((size_t)fcap * D); std::vector<u32> fitem(fcap); std::vector<double> fu((size_t)fcap * D);
+    u64 fts = next_pow2(2 * (u64)fcap), rts = next_pow2(2 * (u64)fcap * D);
+    std::vector<u64> ftab(fts, 0), rtab(rts, 0);
+    hd.fsig = fsig.data(); hd.fitem = fitem.data(); hd.fu = fu.data(); hd.fcount = &fcount; hd.fcap = fcap;
+    hd.ftab = ftab.data(); hd.fmask = fts - 1; hd.rtab = rtab.data(); hd.rmask = rts - 1;
+    WrapDev<D> wd;
+    memset(&wd, 0, sizeof(wd));
+    u32 qcap = fcap * D;
+    std::vector<u64> qa(qcap), qb(qcap);
+    std::vector<WrapQuery<D> > wq(qcap);
+    u32 qcount[2] = {0, 0}, nqv[2] = {0, 0};
+    WrapSeed seed[16]; memset(seed, 0, sizeof(seed));
+    wd.wq = wq.data(); wd.wq_cap = qcap; wd.q[0] = qa.data(); wd.q[1] = qb.data(); wd.qcap = qcap; wd.qcount = qcount; wd.nq = nqv; wd.seed = seed;
+    wrap_tolerances<D>(dv.ext, wd.E32, wd.tinyA);
+    if (!fp32) wd.E32 = INFINITY;                 // every generator goes through the FP64 evaluation
+    LocalStats ls; memset(&ls, 0, sizeof(ls));
+    // the extreme generators along the axes (search_max, chull.jl:244): 2 D first facets
+    for (int a = 0; a < 2 * D; ++a) {
+        const int axis = a >> 1; const double sg = (a & 1) ? -1.0 : 1.0;
+        int start = 0;
+        for (int64_t i = 1; i < n; ++i) if (sg * x64[i * D + axis] > sg * x64[(size_t)start * D + axis]) start = (int)i;
+        seed[a].ids[0] = start; seed[a].cnt = 1;
+        for (int k = 0; k < D; ++k) seed[a].u[k] = (k == axis) ? sg : 0.0;
+        qa[a] = WRAP_SEED_ENTRY + (u64)a;
+    }
+    qcount[0] = 2 * D;
+    HullResult* R = new HullResult(); R->d = D; R->rounds = 0; R->raycasts = 0;
+    int cur = 0;
+    if (slots < 1) slots = 1;
+    while (qcount[cur] > 0 && R->rounds < 1000000) {
+        const int nxt = 1 - cur;
+        qcount[nxt] = 0; nqv[cur] = 0;
+        for (u32 i = 0; i < qcount[cur]; ++i) {
+            WrapQuery<D> w;
+            if (wrap_prepare<D>(dv, hd, wd, wd.q[cur][i], w, ls)) wq[nqv[cur]++] = w;
+        }
+        for (u32 q = 0; q < nqv[cur]; ++q) {
+            double c1 = -INFINITY, c2 = -INFINITY; int g = -1;
+            const int64_t chunk = (((n + slots - 1) / slots) + 3) & ~3LL;
+            for (int s = 0; s < slots; ++s) {
+                const int64_t p0 = s * chunk, p1 = std::min<int64_t>(p0 + chunk, n);
+                WrapLane<D> lane;
+                wrap_lane_init<D>(wq[q], lane);
+                if (p1 > p0) wrap_scan<D>(dv, wq[q], x32.data() + (size_t)p0 * X32<D>::STRIDE, (int)p0, (int)(p1 - p0), wd.tinyA, wd.E32, lane, ls);
+                wrap_settle<D>(dv, wq[q], wd.tinyA, wd.E32, lane, ls);
+                wrap_merge(c1, g, c2, lane.c1, lane.id1, lane.c2);
+            }
+            wrap_commit<D>(dv, hd, wd, wq[q], c1, g, c2, nxt, ls);
+            ++R->raycasts;
+        }
+        cur = nxt; ++R->rounds;
+    }
+    R->records = ls.cand64; R->degenerate = ls.degenerate + ls.seed_fail + ((ctr.flags & FLAG_OVERFLOW_MASK) ? 1000000 : 0);
+    R->nf = 0;
+    for (u32 f = 0; f < fcount; ++f) {
+        if (fsig[(size_t)f * D] < 0) continue;
+        std::vector<std::pair<int64_t, int> > e;
+        for (int k = 0; k < D; ++k) e.push_back(std::make_pair((int64_t)perm[fsig[(size_t)f * D + k]] + 1, fsig[(size_t)f * D + k]));
+        std::sort(e.begin(), e.end());
+        double P[D][D], nrm[D], cen[D];
+        for (int i = 0; i < D; ++i) for (int k = 0; k < D; ++k) P[i][k] = x64[(size_t)e[i].second * D + k];
+        if (!wrap_facet_geometry<D>(P, &fu[(size_t)f * D], nrm, cen)) R->degenerate += 1;
+        for (int k = 0; k < D; ++k) R->facet.push_back(e[k].first);
+        for (int k = 0; k < D; ++k) R->normal.push_back(nrm[k]);
+        for (int k = 0; k < D; ++k) R->centre.push_back(cen[k]);
+        ++R->nf;
+    }
+    return R;
+}
+
 extern "C" {
+void* hostsim_wrap(int dim, int64_t n, const double* xs, int slots, int fp32) {
+    switch (dim) {
+        case 2: return run_wrap<2>(n, xs, slots, fp32);
+        case 3: return run_wrap<3>(n, xs, slots, fp32);
+        case 4: return run_wrap<4>(n, xs, slots, fp32);
+        case 5: return run_wrap<5>(n, xs, slots, fp32);
+        case 6: return run_wrap<6>(n, xs, slots, fp32);
+    }
+    return 0;
+}
+void hostsim_wrap_centres(void* h, double* centre) { HullResult* R = (HullResult*)h; memcpy(centre, R->centre.data(), R->centre.size() * 8); }
 void* hostsim_hull(int dim, int64_t n, const double* xs, int ppc) {
     switch (dim) {
         case 2: return run_hull<2>(n, xs, ppc);

@@ -13,7 +13,8 @@ def build():
     host = os.path.join(_HERE, "..", "..", "highvoronoi.jl_b200", "csrc", "hvb_host.hpp")
     geom = os.path.join(_HERE, "..", "..", "highvoronoi.jl_b200", "csrc", "hvb_geometry.cuh")
     hull = os.path.join(_HERE, "..", "..", "highvoronoi.jl_b200", "csrc", "hvb_hull.cuh")
-    newest = max(os.path.getmtime(f) for f in (src, core, host, geom, hull))
+    wrap = os.path.join(_HERE, "..", "..", "highvoronoi.jl_b200", "csrc", "hvb_wrap.cuh")
+    newest = max(os.path.getmtime(f) for f in (src, core, host, geom, hull, wrap))
     if not os.path.exists(_SO) or os.path.getmtime(_SO) < newest:
         subprocess.check_call(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-Wno-unknown-pragmas", "-o", _SO, src])
     return _SO
@@ -113,3 +114,28 @@ def hull(xs, ppc=0):
     L.hostsim_hull_fetch(h, P(facets), P(normals))
     L.hostsim_hull_free(h)
     return facets, normals, dict(facets=int(c[0]), raycasts=int(c[1]), records=int(c[2]), rounds=int(c[3]), degenerate=int(c[4]))
+
+
+def wrap(xs, slots=1, fp32=1):
+    """convex hull by gift wrapping (hvb_wrap.cuh) on the host: (facets [F, d] sorted 1-based ids, normals [F, d], centres [F, d], stats);
+    `records` counts the FP64 evaluations"""
+    L = ctypes.CDLL(build())
+    L.hostsim_wrap.restype = ctypes.c_void_p
+    L.hostsim_wrap.argtypes = [ctypes.c_int, ctypes.c_int64, ctypes.c_void_p, ctypes.c_int, ctypes.c_int]
+    for f in ("hostsim_hull_counts", "hostsim_hull_fetch", "hostsim_hull_free", "hostsim_wrap_centres"):
+        getattr(L, f).restype = None
+    L.hostsim_hull_counts.argtypes = [ctypes.c_void_p, ctypes.c_void_p]
+    L.hostsim_hull_fetch.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]
+    L.hostsim_wrap_centres.argtypes = [ctypes.c_void_p, ctypes.c_void_p]
+    L.hostsim_hull_free.argtypes = [ctypes.c_void_p]
+    xs = np.ascontiguousarray(xs, dtype=np.float64)
+    n, d = xs.shape
+    P = lambda a: a.ctypes.data_as(ctypes.c_void_p)
+    h = L.hostsim_wrap(d, n, P(xs), slots, fp32)
+    c = np.zeros(5, dtype=np.int64)
+    L.hostsim_hull_counts(h, P(c))
+    facets = np.empty((c[0], d), dtype=np.int64); normals = np.empty((c[0], d)); centres = np.empty((c[0], d))
+    L.hostsim_hull_fetch(h, P(facets), P(normals))
+    L.hostsim_wrap_centres(h, P(centres))
+    L.hostsim_hull_free(h)
+    return facets, normals, centres, dict(facets=int(c[0]), raycasts=int(c[1]), fp64=int(c[2]), rounds=int(c[3]), degenerate=int(c[4]))

@@ -1,5 +1,6 @@
-"""ConvexHull(xs) (chull.jl:213-238) by the device facet walk (hvb_convex_hull, csrc/hvb_hull.cuh), against Qhull's hull and
-against round 1's way (facets read off the unbounded edges of a complete search)."""
+"""ConvexHull(xs) (chull.jl:213-238) by gift wrapping on the device (hvb_convex_hull, csrc/hvb_wrap.cuh), against Qhull's hull,
+against the walk around the unbounded 2-faces (hvb_convex_hull_via(ctx, 1), csrc/hvb_hull.cuh) and against round 1's way (facets
+read off the unbounded edges of a complete search)."""
 import numpy as np
 import pytest
 
@@ -22,7 +23,7 @@ def check_against_qhull(cv, xs):
         assert ((xs - r) @ u).max() < 1e-10                                            # every node behind the plane
 
 
-@pytest.mark.parametrize("via", ["walk", "search"])
+@pytest.mark.parametrize("via", ["wrap", "walk", "search"])
 @pytest.mark.parametrize("d,n", [(2, 3000), (3, 2000), (4, 600), (5, 200), (6, 100)])
 def test_convex_hull_matches_qhull(hvb, d, n, via):
     xs = points(n, d, 700 + d)
@@ -36,12 +37,46 @@ def test_facet_walk_never_visits_the_interior(hvb, d, n):
     xs = points(n, d, 710 + d)
     a = hvb.ConvexHull(xs)
     b = hvb.ConvexHull(xs, via="search")
-    assert np.array_equal(a.sig, b.sig)
-    assert np.abs(a.u - b.u).max() < 1e-9 and np.abs(a.r - b.r).max() < 1e-9
-    assert a.stats["vertices"] == 0 and a.stats["rays"] == len(a)
-    assert a.stats["raycasts"] < {3: 0.02, 4: 0.2, 5: 0.6}[d] * b.stats["raycasts"]
+    w = hvb.ConvexHull(xs, via="walk")
+    for c in (a, w):
+        assert np.array_equal(c.sig, b.sig)
+        assert np.abs(c.u - b.u).max() < 1e-9 and np.abs(c.r - b.r).max() < 1e-8
+        assert c.stats["vertices"] == 0 and c.stats["rays"] == len(c)
+    assert w.stats["raycasts"] < {3: 0.02, 4: 0.2, 5: 0.6}[d] * b.stats["raycasts"]
+    # one query per ridge at most: d / 2 per facet (+ the d - 1 seed steps)
+    assert a.stats["raycasts"] <= len(a) * d / 2 + d
     if d == 3:
         check_against_qhull(a, xs)
+
+
+def test_wrapping_is_reproducible_and_filter_independent(hvb):
+    """normals and centres come from the facet's generators alone: bitwise equal from run to run and with the FP32 filter off"""
+    xs = points(4000, 4, 77)
+    a = hvb.ConvexHull(xs)
+    b = hvb.ConvexHull(xs)
+    c = hvb.ConvexHull(xs, options=hvb.RaycastParameter(fp32_filter=0))
+    for o in (b, c):
+        assert np.array_equal(a.sig, o.sig) and np.array_equal(a.u, o.u) and np.array_equal(a.r, o.r)
+    assert c.stats["candidates_fp64"] > 100 * a.stats["candidates_fp64"]
+
+
+@pytest.mark.parametrize("d,n", [(5, 50000), (2, 1000000), (6, 3000)])
+def test_wrapping_at_config_size(hvb, d, n):
+    """the hull of BASELINE's C4 / C3 clouds (and a d = 6 cloud): every generator behind every facet, every ridge shared by
+    exactly two facets (a closed surface), Euler-Poincare for d = 2, 3 is implied by the comparison with Qhull above"""
+    xs = points(n, d, 720 + d)
+    cv = hvb.ConvexHull(xs)
+    assert len(cv) > 0 and np.abs(np.linalg.norm(cv.u, axis=1) - 1.0).max() < 1e-12
+    off = (cv.u * cv.r).sum(axis=1)
+    step = max(1, len(cv) // 2000)
+    for i in range(0, len(cv), step):
+        assert (xs @ cv.u[i] - off[i]).max() < 1e-10
+    ridges = {}
+    for f in cv.sig:
+        for j in range(d):
+            key = tuple(np.delete(f, j))
+            ridges[key] = ridges.get(key, 0) + 1
+    assert set(ridges.values()) == {2}
 
 
 def test_hull_needs_the_unbounded_domain(hvb):
