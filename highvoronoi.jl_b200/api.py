@@ -220,7 +220,20 @@ class VoronoiMesh:
         nv, nr, ml = ctypes.c_int64(), ctypes.c_int64(), ctypes.c_int64()
         _abi.check(L.hvb_counts(ctx, ctypes.byref(nv), ctypes.byref(nr), ctypes.byref(ml)), ctx)
         d = self.dim
-        if copy:
+        self.max_siglen = ml.value
+        self.sig_off = self.sig_ids = None
+        if ml.value > d + 1:
+            # non-general position resolved by the backend (on_degenerate = 2): vertices with more than d + 1 generators, the
+            # reference's variable-length sig vectors (raycast.jl:926-949).  `sig` does not exist; use sigs() / sig_off, sig_ids
+            P = lambda a: a.ctypes.data_as(ctypes.c_void_p)
+            self.copy = copy = True
+            self.sig_off = np.empty((nv.value + 1,), dtype=np.int64)
+            _abi.check(L.hvb_fetch_vertices_var(ctx, P(self.sig_off), None, None), ctx)
+            self.sig_ids = np.empty((int(self.sig_off[-1]),), dtype=np.int64)
+            self.r = np.empty((nv.value, d), dtype=np.float64)
+            _abi.check(L.hvb_fetch_vertices_var(ctx, P(self.sig_off), P(self.sig_ids), P(self.r)), ctx)
+            self.sig = None
+        elif copy:
             self.sig = np.empty((nv.value, d + 1), dtype=np.int64)
             self.r = np.empty((nv.value, d), dtype=np.float64)
             _abi.check(L.hvb_fetch_vertices(ctx, self.sig.ctypes.data_as(ctypes.c_void_p), self.r.ctypes.data_as(ctypes.c_void_p)), ctx)
@@ -254,6 +267,12 @@ class VoronoiMesh:
             if nv.value:
                 _abi.check(L.hvb_fetch_vertex_flags(ctx, self.canonical.ctypes.data_as(ctypes.c_void_p)), ctx)
             self.canonical = self.canonical.astype(bool)
+
+    def sigs(self):
+        """the signatures as a list of sorted 1-based id arrays, whatever their lengths (general position: d + 1 each)"""
+        if self.sig_off is None:
+            return [row for row in np.asarray(self.sig)]
+        return [self.sig_ids[self.sig_off[v]:self.sig_off[v + 1]] for v in range(len(self.sig_off) - 1)]
 
     def origin_of(self, ids):
         """folds extended ids back to caller ids (halo -> the generator it copies; planes -> n_user + p)"""
@@ -312,6 +331,11 @@ class VoronoiMesh:
 
     def vertices_iterator(self, i):
         """all (sig, r) of cell i (1-based), like vertices_iterator(mesh, i) (abstractmesh.jl:179)."""
+        if self.sig_off is not None:
+            for sg, rr in zip(self.sigs(), self.r):
+                if i in sg:
+                    yield sg, rr
+            return
         if self._cell_index is None:
             real = self.sig <= self.n
             rows = np.repeat(np.arange(self.sig.shape[0]), self.dim + 1)[real.ravel()]
@@ -323,7 +347,7 @@ class VoronoiMesh:
             yield self.sig[v], self.r[v]
 
     def number_of_vertices(self):
-        return self.sig.shape[0]
+        return self.r.shape[0]
 
 
 def voronoi(xs, searcher=None, Iter=None, copy=True, known=None, **_ignored):

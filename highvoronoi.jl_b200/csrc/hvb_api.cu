@@ -19,7 +19,7 @@ extern "C" {
 void hvb_default_params(hvb_params* p) {
     memset(p, 0, sizeof(*p));
     p->variance_tol = 1e-15; p->break_tol = 1e-5; p->b_nodes_tol = 1e-7; p->plane_tolerance = 1e-12; p->ray_tol = 1e-12;
-    p->method = 0; p->device = 0; p->rank = 0; p->world = 1; p->fp32_filter = 1; p->on_degenerate = 0;
+    p->method = 0; p->device = 0; p->rank = 0; p->world = 1; p->fp32_filter = 1; p->on_degenerate = 2;
     p->points_per_cell = 0; p->seed_stride = 0; p->sort_output = 1; p->neighbors = 0; p->persistent = 3; p->vertex_capacity = 0; p->probe_scale = 0.0; p->periodic_margin = 0.0; p->wire32 = 0; p->decomposition = 1;
 }
 
@@ -105,6 +105,7 @@ int hvb_convex_hull(hvb_ctx* ctx) { return ctx ? ctx->convex_hull(0) : HVB_EINVA
 int hvb_convex_hull_via(hvb_ctx* ctx, int method) { return ctx ? ctx->convex_hull(method) : HVB_EINVAL; }
 int hvb_counts(hvb_ctx* ctx, int64_t* nvert, int64_t* nrays, int64_t* max_siglen) { return ctx ? ctx->counts(nvert, nrays, max_siglen) : HVB_EINVAL; }
 int hvb_fetch_vertices(hvb_ctx* ctx, int64_t* sig, double* r) { return ctx ? ctx->fetch_vertices(sig, r) : HVB_EINVAL; }
+int hvb_fetch_vertices_var(hvb_ctx* ctx, int64_t* off, int64_t* ids, double* r) { return ctx ? ctx->fetch_vertices_var(off, ids, r) : HVB_EINVAL; }
 int hvb_fetch_vertices_range(hvb_ctx* ctx, int64_t first, int64_t count, int64_t* sig, double* r) { return ctx ? ctx->fetch_vertices_range(first, count, sig, r) : HVB_EINVAL; }
 int hvb_view_vertices(hvb_ctx* ctx, const int64_t** sig, const double** r, int64_t* nvert) { return (ctx && sig && r && nvert) ? ctx->view_vertices(sig, r, nvert) : HVB_EINVAL; }
 int hvb_view_vertices32(hvb_ctx* ctx, const int32_t** sig, const double** r, int64_t* nvert) { return (ctx && sig && r && nvert) ? ctx->view_vertices32(sig, r, nvert) : HVB_EINVAL; }

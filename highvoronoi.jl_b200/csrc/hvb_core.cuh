@@ -172,9 +172,14 @@ struct Dev {
     const int* cell_start;             // [ncells + 1]
     const float* x32;                  // [n][X32<D>::STRIDE]  coordinates minus lo, FP32, padded (filter)
     const double* x64;                 // [n][D]  coordinates, FP64 (verification)
+    const double* xcan;                // [n][D]  coordinates the returned vertex coordinates are solved from: x64, except when the
+                                       //         search runs on perturbed generators (non-general position resolved, hvb_ctx.cuh)
     const PlaneSet* planes;
     const unsigned char* active;       // [n] 1 = this context walks the edges of that cell (slab / Iter)
     double plane_tol;                  // raycast-types.jl:229
+    double t_min;                      // smallest accepted ray parameter: plane_tol (raycast.jl:887-889), except on a perturbed cloud
+                                       // (non-general position resolved): there the true winner of a walk inside a cospherical set
+                                       // sits at t ~ 1e-9 of the extent and must not be refused
     double probe_scale;
     double probe_growth;               // radius factor from one probe stage to the next (2; the hull walk jumps to the half-space)
     int fp32_filter;
@@ -398,7 +403,7 @@ HVB_HD bool verify64(const Dev<D>& dv, const RayQ<D>& q, int j, Best& best, Loca
     ls.cand64++;
     if (!(ux > q.c) || !(den > 0)) return false;
     double t = num / (2.0 * den);
-    if (!(t >= dv.plane_tol)) return false;           // raycast.jl:887-889
+    if (!(t >= dv.t_min)) return false;               // raycast.jl:887-889
     best_offer(best, t, j, D, q.rnorm, den, dx2);
     return true;
 }
@@ -776,7 +781,7 @@ HVB_HD void plane_candidates(const Dev<D>& dv, const RayQ<D>& q, Best& best) {
         double s = ps->off[p] - nx0;                       // distance of x0 to the plane (> 0 inside)
         if (!(ux0 + 2.0 * s * nu > q.c) || !(nu > 0)) continue;
         double t = (ps->off[p] - nr) / nu;
-        if (!(t >= dv.plane_tol)) continue;
+        if (!(t >= dv.t_min)) continue;
         // a plane is the mirror image of x0: x - x0 = 2 s n, u . (x - x0) = 2 s nu
         best_offer(best, t, dv.n + p, D, q.rnorm, 2.0 * s * nu, 4.0 * s * s);
     }
@@ -1426,20 +1431,22 @@ HVB_HD void seed_item(const Dev<D>& dv, const T& tile, int start, u64* q_out, u3
 // radii over the real generators (vertex_variance, raycast.jl:320-329).
 // ------------------------------------------------------------------------------------------------------------
 template <int D>
-HVB_HD double canonical_vertex(const Dev<D>& dv, const int* sig, double* r) {
+HVB_HD double canonical_vertex(const Dev<D>& dv, const int* sig, double* r, double* flatness = nullptr) {
     const PlaneSet* ps = dv.planes;
     double x0[D];
 #pragma unroll
-    for (int k = 0; k < D; ++k) x0[k] = dv.x64[(size_t)sig[0] * D + k];
+    for (int k = 0; k < D; ++k) x0[k] = dv.xcan[(size_t)sig[0] * D + k];
     double A[D][D], b[D], z[D];
+    double rownorm2 = 1.0;             // product of the squared row norms
 #pragma unroll
     for (int i = 0; i < D; ++i) {
         int id = sig[i + 1];
         if (id < dv.n) {
             double s = 0;
 #pragma unroll
-            for (int k = 0; k < D; ++k) { A[i][k] = dv.x64[(size_t)id * D + k] - x0[k]; s += A[i][k] * A[i][k]; }
+            for (int k = 0; k < D; ++k) { A[i][k] = dv.xcan[(size_t)id * D + k] - x0[k]; s += A[i][k] * A[i][k]; }
             b[i] = 0.5 * s;
+            rownorm2 *= s;
         } else {
             double s = 0;
 #pragma unroll
@@ -1447,6 +1454,7 @@ HVB_HD double canonical_vertex(const Dev<D>& dv, const int* sig, double* r) {
             b[i] = ps->off[id - dv.n] - s;
         }
     }
+    double pivprod = 1.0;              // |det A| = product of the pivots of the first elimination
 #pragma unroll
     for (int k = 0; k < D; ++k) z[k] = 0.0;
     // direct solve of A z = b plus one step of iterative refinement (Gaussian elimination with partial pivoting);
@@ -1474,6 +1482,7 @@ HVB_HD double canonical_vertex(const Dev<D>& dv, const int* sig, double* r) {
                     for (int k = 0; k < D + 1; ++k) { double tmp = M[c][k]; M[c][k] = M[i][k]; M[i][k] = tmp; }
                 }
             double inv = (M[c][c] != 0.0) ? 1.0 / M[c][c] : 0.0;
+            if (rep == 0) pivprod *= fabs(M[c][c]);
 #pragma unroll
             for (int i = 0; i < D; ++i)
                 if (i > c) {
@@ -1497,6 +1506,8 @@ HVB_HD double canonical_vertex(const Dev<D>& dv, const int* sig, double* r) {
     }
 #pragma unroll
     for (int k = 0; k < D; ++k) r[k] = x0[k] + z[k];
+    // how far the d + 1 generators are from lying in one hyperplane: |det| of the unit row vectors (1 for an orthogonal corner)
+    if (flatness) *flatness = (rownorm2 > 0) ? pivprod / sqrt(rownorm2) : 0.0;
     // variance over the real generators
     double dist[D + 1], mean = 0;
     int cnt = 0;
@@ -1506,7 +1517,7 @@ HVB_HD double canonical_vertex(const Dev<D>& dv, const int* sig, double* r) {
         if (sig[i] < dv.n) {
             double s = 0;
 #pragma unroll
-            for (int k = 0; k < D; ++k) { double t = dv.x64[(size_t)sig[i] * D + k] - r[k]; s += t * t; }
+            for (int k = 0; k < D; ++k) { double t = dv.xcan[(size_t)sig[i] * D + k] - r[k]; s += t * t; }
             dist[i] = s; mean += s; ++cnt;
         }
     }

@@ -16,6 +16,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <string>
+#include <unordered_map>
 #include <vector>
 
 #include "../../include/hvb200.h"
@@ -95,6 +96,17 @@ struct HBuf {   // page-locked host memory
     }
     void release() { if (p) cudaFreeHost(p); p = nullptr; cap = 0; }
 };
+
+// non-general position resolved by perturbation (Ctx::resolve_degenerate)
+#ifndef HVB_PERTURB_REL
+#define HVB_PERTURB_REL 1e-9      // offset of a generator / extent of the cloud
+#endif
+#ifndef HVB_MERGE_REL
+#define HVB_MERGE_REL 1e-8        // rows closer than this (times the extent, per coordinate) are one vertex
+#endif
+#ifndef HVB_FLAT_TOL
+#define HVB_FLAT_TOL 1e-7         // |det| of the unit edge vectors of a simplex below which its generators count as coplanar
+#endif
 
 struct Round { u32 qcount; u32 cursor; };   // frontier length and the work cursor of the round that consumes it
 struct Scalars {            // small device-side words, mirrored into pinned host memory after every round
@@ -325,7 +337,7 @@ struct Ctx : hvb_ctx {
         CK(planes.ensure(1)); CK(ctr.ensure(1)); CK(sc.ensure(1)); CK(h_sc.ensure(1)); CK(h_ctr.ensure(1)); CK(h_extra.ensure(1));
         CK(cert.ensure(1)); CK(h_cert.ensure(1));
         CK(cudaMemcpyAsync(planes.p, &ps_orig, sizeof(ps_orig), cudaMemcpyHostToDevice, stream));
-        dv.plane_tol = prm.plane_tolerance;
+        dv.plane_tol = prm.plane_tolerance; dv.t_min = prm.plane_tolerance;
         dv.probe_scale = prm.probe_scale > 1.0 ? prm.probe_scale : default_probe_scale(D);
         dv.fp32_filter = prm.fp32_filter;
         dv.probe_growth = 2.0;
@@ -379,6 +391,8 @@ struct Ctx : hvb_ctx {
         CK(cudaSetDevice(prm.device));
         have_result = false; staged = false; staged_r = staged_sig64 = staged_sig32 = false; nb_staged32 = false; nb_total = -1; have_flags = false;
         n_user = n_new; n = n_new; n_halo = 0;
+        perturbed = false; merged = false; m_nb_built = false;
+        dv.t_min = prm.plane_tolerance;
         CK(cudaEventRecord(ev_a, stream));
         // upload, then bounding box + domain check on the device against the caller's planes
         CK(xs_in.ensure((size_t)n * D));
@@ -453,7 +467,7 @@ struct Ctx : hvb_ctx {
         CK(perm.ensure(n)); CK(inv.ensure(n)); CK(cell_of.ensure(n)); CK(unseeded_list.ensure(n));
         CK(cell_start.ensure(ncells + 1)); CK(cell_cur.ensure(ncells + 1));
         CK(active.ensure(n)); CK(has_vertex.ensure(n));
-        dv.cell_start = cell_start.p; dv.x32 = x32.p; dv.x64 = x64.p; dv.planes = planes.p; dv.active = active.p;
+        dv.cell_start = cell_start.p; dv.x32 = x32.p; dv.x64 = x64.p; dv.xcan = x64.p; dv.planes = planes.p; dv.active = active.p;
         dv.has_vertex = has_vertex.p; dv.ctr = ctr.p;
         // counting sort into cells
         CK(cudaMemsetAsync(cell_cur.p, 0, (size_t)(ncells + 1) * sizeof(int), stream));
@@ -636,6 +650,14 @@ struct Ctx : hvb_ctx {
     // (the reference repeats its halo step a fixed number of times instead: Create_Discrete_Domain domain.jl:175-213,
     // periodize! :139-166).
     int search(const int64_t* cells, int64_t ncells_in, const int64_t* seed_sig, const double* seed_r, int64_t nseed, int stride) override {
+        merged = false; m_nb_built = false;
+        // a cloud that turned out to be in non-general position is searched in its perturbed form from then on
+        if (perturbed) return resolve_degenerate(cells, ncells_in, nseed);
+        int rc = search_general(cells, ncells_in, seed_sig, seed_r, nseed, stride);
+        if (rc == HVB_EDEGENERATE && prm.on_degenerate == 2) return resolve_degenerate(cells, ncells_in, nseed);
+        return rc;
+    }
+    int search_general(const int64_t* cells, int64_t ncells_in, const int64_t* seed_sig, const double* seed_r, int64_t nseed, int stride) {
         if (!periodic) return search_once(cells, ncells_in, seed_sig, seed_r, nseed, stride);
         if (nseed > 0) { err = "seed vertices are not supported on a periodic context"; return HVB_EINVAL; }
         if (cells) for (int64_t i = 0; i < ncells_in; ++i) if (cells[i] < 1 || cells[i] > n_user) { err = "Iter names a cell that is not a caller generator"; return HVB_EINVAL; }
@@ -744,6 +766,188 @@ struct Ctx : hvb_ctx {
         return HVB_OK;
     }
 
+    // ---- non-general position: resolved by perturbation + merge ----------------------------------------
+    // The reference enumerates the edges of a vertex with more than d + 1 cospherical generators by linear algebra on the
+    // cone of the vertex (FastEdgeIterator, edgeiterate.jl:82-780) and returns ONE vertex whose signature lists all of them
+    // (raycast.jl:870-969).  A cone enumeration is branchy, variable-length, sequential work -- the opposite of what the
+    // walk kernel is good at.  This backend gets the same RESULT from the general-position machinery:
+    //   1. the generators are moved by a deterministic pseudo-random offset of relative size HVB_PERTURB_REL (an explicit
+    //      simulation of simplicity): the perturbed cloud is in general position and its Delaunay triangulation restricted
+    //      to a cospherical set S is a triangulation of conv(S);
+    //   2. the search runs on the perturbed cloud unchanged;
+    //   3. coordinates are solved from the CALLER's generators (canonical_vertex on dv.xcan): every simplex of the
+    //      triangulation of conv(S) gets the circumcentre of S, identical up to rounding; simplices whose d + 1 generators
+    //      lie in one hyperplane of the caller's cloud are slivers between two cospherical cells and are dropped (k_final_rows);
+    //   4. rows with equal coordinates are merged (host, rare path): the union of their signatures is S.
+    // Checked against Qhull's Voronoi diagram of the same cloud (which merges cospherical facets), tests/test_gpu_degenerate.py.
+    DBuf<double> xs_orig, xcan;
+    bool perturbed = false;              // xs_in / x64 / x32 hold perturbed generators, xs_orig / xcan the caller's
+    bool merged = false;                 // the result of the last search are the variable-length rows below
+    bool m_nb_built = false;
+    std::vector<int64_t> m_off, m_ids, m_nb_off, m_nb_ids;
+    std::vector<double> m_r;
+    int64_t m_nvert = 0, m_maxlen = 0, m_degenerate = 0;
+    bool report_degenerate() const { return prm.on_degenerate == 0 || (prm.on_degenerate == 2 && !perturbed); }
+
+    int resolve_degenerate(const int64_t* cells, int64_t ncells_in, int64_t nseed) {
+        // unbounded domains: the hull of such a cloud (the faces of a lattice) has coplanar generators whose perturbed
+        // simplices have balls of arbitrary size; telling a generator ON such a ball from one inside it is beyond FP64
+        if (periodic || std::max(1, prm.world) > 1 || nseed > 0 || P == 0) {
+            err = "non-general position: a vertex with more than dim+1 cospherical generators was met (resolving it is available on bounded, non-periodic domains, one GPU, unseeded searches)";
+            return HVB_EDEGENERATE;
+        }
+        CK(cudaSetDevice(prm.device));
+        if (!perturbed) {
+            const double build0 = st.ms_build, upload0 = st.ms_upload;
+            CK(xs_orig.ensure((size_t)n * D));
+            CK(cudaMemcpyAsync(xs_orig.p, xs_in.p, (size_t)n * D * sizeof(double), cudaMemcpyDeviceToDevice, stream));
+            k_perturb<<<blocks_for(n * D, 256), 256, 0, stream>>>(xs_orig.p, xs_in.p, (size_t)n * D, D, HVB_PERTURB_REL * dv.ext); ++launches;
+            CK(cudaEventRecord(ev_a, stream));
+            int rc = check_points(xs_in.p, n, nullptr);
+            if (rc) {
+                CK(cudaMemcpyAsync(xs_in.p, xs_orig.p, (size_t)n * D * sizeof(double), cudaMemcpyDeviceToDevice, stream));
+                CK(cudaStreamSynchronize(stream));
+                err = "non-general position: a generator lies too close to the boundary for the perturbation that resolves it";
+                return HVB_EDEGENERATE;
+            }
+            rc = build_index(); if (rc) return rc;
+            CK(xcan.ensure((size_t)n * D));
+            k_gather_canon<D><<<blocks_for(n, 256), 256, 0, stream>>>(xs_orig.p, perm.p, (int)n, xcan.p); ++launches;
+            dv.xcan = xcan.p;
+            dv.t_min = -1e-13 * dv.ext;
+            perturbed = true;
+            st.ms_build = build0; st.ms_upload = upload0;
+        }
+        const int nb_save = prm.neighbors;
+        prm.neighbors = 0;                       // the lists of a merged mesh are built from the merged rows (build_merged_neighbors)
+        int rc = search_once(cells, ncells_in, nullptr, nullptr, 0, 0);
+        prm.neighbors = nb_save;
+        if (rc) return rc;
+        return merge_result();
+    }
+
+    // step 4: rows with equal coordinates -> one vertex with the union of the signatures
+    int merge_result() {
+        const int64_t* sig; const double* r; int64_t nrow;
+        int rc = view_vertices(&sig, &r, &nrow); if (rc) return rc;
+        const double eps = HVB_MERGE_REL * dv.ext;
+        std::vector<int> parent((size_t)nrow);
+        for (int64_t i = 0; i < nrow; ++i) parent[i] = (int)i;
+        auto find = [&](int x) { while (parent[x] != x) { parent[x] = parent[parent[x]]; x = parent[x]; } return x; };
+        auto unite = [&](int a, int b) { a = find(a); b = find(b); if (a != b) { if (a < b) parent[b] = a; else parent[a] = b; } };
+        // two grids of cell size eps, shifted by half a cell: members of a cluster agree to ~1e-13 of the extent, so they share
+        // a cell of at least one grid unless they straddle a boundary of both (probability ~ (d 1e-13 / eps)^2)
+        for (int pass = 0; pass < 2; ++pass) {
+            std::unordered_map<u64, int> first;
+            first.reserve((size_t)nrow * 2);
+            for (int64_t i = 0; i < nrow; ++i) {
+                u64 h = 0x9ae16a3b2f90404fULL + (u64)pass;
+                for (int k = 0; k < D; ++k) {
+                    const long long c = (long long)floor(r[i * D + k] / eps + 0.5 * pass);
+                    h = mix64(h ^ ((u64)c + 0x9e3779b97f4a7c15ULL * (u64)(k + 1)));
+                }
+                auto it = first.find(h);
+                if (it == first.end()) { first.emplace(h, (int)i); continue; }
+                const int j = it->second;
+                double dmax = 0;
+                for (int k = 0; k < D; ++k) dmax = std::max(dmax, fabs(r[i * D + k] - r[(size_t)j * D + k]));
+                if (dmax <= eps) unite((int)i, j);
+            }
+        }
+        // clusters in the order of their first row (rows are sorted by signature: the first row is the smallest one)
+        std::vector<int> cluster_of((size_t)nrow, -1), head;
+        for (int64_t i = 0; i < nrow; ++i) { const int rt = find((int)i); if (cluster_of[rt] < 0) { cluster_of[rt] = (int)head.size(); head.push_back(rt); } cluster_of[i] = cluster_of[rt]; }
+        const size_t nc = head.size();
+        std::vector<std::vector<int64_t> > sets(nc);
+        for (int64_t i = 0; i < nrow; ++i) { auto& v = sets[cluster_of[i]]; v.insert(v.end(), sig + i * (D + 1), sig + (i + 1) * (D + 1)); }
+        m_maxlen = D + 1; m_degenerate = 0;
+        for (auto& v : sets) { std::sort(v.begin(), v.end()); v.erase(std::unique(v.begin(), v.end()), v.end()); m_maxlen = std::max<int64_t>(m_maxlen, (int64_t)v.size()); if ((int64_t)v.size() > D + 1) ++m_degenerate; }
+        std::vector<int> order(nc);
+        for (size_t c = 0; c < nc; ++c) order[c] = (int)c;
+        if (prm.sort_output) std::sort(order.begin(), order.end(), [&](int a, int b) { return sets[a] < sets[b]; });
+        m_off.assign(nc + 1, 0); m_ids.clear(); m_r.resize(nc * D);
+        for (size_t o = 0; o < nc; ++o) {
+            const int c = order[o];
+            m_ids.insert(m_ids.end(), sets[c].begin(), sets[c].end());
+            m_off[o + 1] = (int64_t)m_ids.size();
+            for (int k = 0; k < D; ++k) m_r[o * D + k] = r[(size_t)head[c] * D + k];
+        }
+        m_nvert = (int64_t)nc;
+        merged = true; m_nb_built = false;
+        st.vertices = m_nvert; st.unique_vertices = m_nvert; st.degenerate = m_degenerate;
+        return HVB_OK;
+    }
+
+    // neighbour lists of a merged mesh: i and j are neighbours if they share a FULL interface (neighbors.jl:205-212; the
+    // reference's NeighborFinder removes cells that only share a lower-dimensional face of a non-general vertex): the
+    // vertices (and unbounded edges) both belong to span an affine space of dimension d - 1
+    int build_merged_neighbors() {
+        if (m_nb_built) return HVB_OK;
+        struct Item { int64_t i, j; int64_t v; };            // v >= 0: merged vertex; v < 0: unbounded edge -v - 1
+        std::vector<Item> items;
+        for (int64_t v = 0; v < m_nvert; ++v)
+            for (int64_t a = m_off[v]; a < m_off[v + 1]; ++a)
+                for (int64_t b = a + 1; b < m_off[v + 1]; ++b) items.push_back({m_ids[a], m_ids[b], v});
+        std::vector<int64_t> redge; std::vector<double> rdir;
+        if (nrays > 0) {
+            redge.resize((size_t)nrays * D); rdir.resize((size_t)nrays * D);
+            int rc = fetch_rays(redge.data(), nullptr, rdir.data(), nullptr); if (rc) return rc;
+            for (int64_t q = 0; q < nrays; ++q)
+                for (int a = 0; a < D; ++a)
+                    for (int b = a + 1; b < D; ++b) items.push_back({redge[q * D + a], redge[q * D + b], -q - 1});
+        }
+        std::sort(items.begin(), items.end(), [](const Item& x, const Item& y) { return x.i != y.i ? x.i < y.i : (x.j != y.j ? x.j < y.j : x.v < y.v); });
+        std::vector<std::pair<int64_t, int64_t> > adj;      // (cell, neighbour)
+        const double tol = 1e-6;
+        for (size_t a = 0; a < items.size();) {
+            size_t b = a;
+            while (b < items.size() && items[b].i == items[a].i && items[b].j == items[a].j) ++b;
+            // rank of the span: Gram-Schmidt over the differences to the first vertex and the directions of the unbounded edges
+            double basis[HVB_MAX_DIM][HVB_MAX_DIM];
+            int rank = 0;
+            const double* p0 = nullptr;
+            double scale = 0;
+            for (size_t t = a; t < b && !p0; ++t) if (items[t].v >= 0) p0 = &m_r[(size_t)items[t].v * D];
+            for (size_t t = a; t < b; ++t) if (items[t].v >= 0 && p0) { double s2 = 0; for (int k = 0; k < D; ++k) { const double dd = m_r[(size_t)items[t].v * D + k] - p0[k]; s2 += dd * dd; } scale = std::max(scale, sqrt(s2)); }
+            for (size_t t = a; t < b && rank < D - 1; ++t) {
+                double w[HVB_MAX_DIM];
+                double ref;
+                if (items[t].v >= 0) { if (!p0) continue; for (int k = 0; k < D; ++k) w[k] = m_r[(size_t)items[t].v * D + k] - p0[k]; ref = scale; }
+                else { for (int k = 0; k < D; ++k) w[k] = rdir[(size_t)(-items[t].v - 1) * D + k]; ref = 1.0; }
+                for (int rep = 0; rep < 2; ++rep)
+                    for (int q = 0; q < rank; ++q) { double sdot = 0; for (int k = 0; k < D; ++k) sdot += w[k] * basis[q][k]; for (int k = 0; k < D; ++k) w[k] -= sdot * basis[q][k]; }
+                double nw = 0; for (int k = 0; k < D; ++k) nw += w[k] * w[k];
+                nw = sqrt(nw);
+                if (ref > 0 && nw > tol * ref) { for (int k = 0; k < D; ++k) basis[rank][k] = w[k] / nw; ++rank; }
+            }
+            if (rank >= D - 1) {
+                const int64_t i = items[a].i, j = items[a].j;
+                if (i <= n) adj.emplace_back(i, j);
+                if (j <= n) adj.emplace_back(j, i);
+            }
+            a = b;
+        }
+        std::sort(adj.begin(), adj.end());
+        m_nb_off.assign((size_t)n + 1, 0); m_nb_ids.clear(); m_nb_ids.reserve(adj.size());
+        for (auto& pr : adj) { m_nb_off[pr.first]++; m_nb_ids.push_back(pr.second); }
+        for (int64_t i = 0; i < n; ++i) m_nb_off[i + 1] += m_nb_off[i];
+        m_nb_built = true;
+        return HVB_OK;
+    }
+
+    // variable-length rows (hvb_fetch_vertices_var): works for every result; general position gives off[v] = v (dim + 1)
+    int fetch_vertices_var(int64_t* off, int64_t* ids, double* r) override {
+        if (!have_result) { err = "no search result"; return HVB_ESTATE; }
+        if (merged) {
+            if (off) memcpy(off, m_off.data(), m_off.size() * sizeof(int64_t));
+            if (ids && !m_ids.empty()) memcpy(ids, m_ids.data(), m_ids.size() * sizeof(int64_t));
+            if (r && !m_r.empty()) memcpy(r, m_r.data(), m_r.size() * sizeof(double));
+            return HVB_OK;
+        }
+        if (off) for (int64_t v = 0; v <= nvert; ++v) off[v] = v * (D + 1);
+        return fetch_vertices(ids, r);
+    }
+
     // ---- convex hull by the facet walk (hvb_hull.cuh; replaces systematic_chull, chull.jl:241-387) -------------------
     DBuf<int> h_fsig; DBuf<u32> h_fitem; DBuf<double> h_fu; DBuf<u64> h_ftab, h_rtab; DBuf<unsigned long long> h_arg;
     // ---- convex hull by gift wrapping (hvb_wrap.cuh): the default ----------------------------------------------------
@@ -806,7 +1010,7 @@ struct Ctx : hvb_ctx {
                 CK(cudaMemcpyAsync(hw_words.p, w_words.p, 4 * sizeof(u32), cudaMemcpyDeviceToHost, stream));
                 int rc = read_scalars(); if (rc) return rc;
                 if (h_ctr.p->flags & FLAG_OVERFLOW_MASK) { overflow = true; break; }
-                if ((h_ctr.p->degenerate > 0 || (h_ctr.p->flags & FLAG_DEGEN)) && !prm.on_degenerate) {
+                if ((h_ctr.p->degenerate > 0 || (h_ctr.p->flags & FLAG_DEGEN)) && prm.on_degenerate != 1) {
                     st.degenerate = (int64_t)std::max<u64>(h_ctr.p->degenerate, 1);
                     err = "non-general position: a hull facet with more than dim generators was met";
                     return HVB_EDEGENERATE;
@@ -834,7 +1038,7 @@ struct Ctx : hvb_ctx {
         CK(cudaEventRecord(ev_d, stream));
         int rc = read_scalars(); if (rc) return rc;
         nrays = h_sc.p->ray_out;
-        if (h_sc.p->pflags > 0 && !prm.on_degenerate) { err = "non-general position: a hull facet whose generators do not span a hyperplane"; return HVB_EDEGENERATE; }
+        if (h_sc.p->pflags > 0 && prm.on_degenerate != 1) { err = "non-general position: a hull facet whose generators do not span a hyperplane"; return HVB_EDEGENERATE; }
         float ms = 0;
         cudaEventElapsedTime(&ms, ev_a, ev_c); st.ms_search = ms;
         cudaEventElapsedTime(&ms, ev_b, ev_d); st.ms_finalize = ms;
@@ -886,7 +1090,7 @@ struct Ctx : hvb_ctx {
         for (;;) {
             int rc = read_scalars(); if (rc) return rc;
             if (h_ctr.p->flags & FLAG_OVERFLOW_MASK) { err = "hull walk: capacity exhausted (raise vertex_capacity)"; return HVB_ENOMEM; }
-            if ((h_ctr.p->degenerate > 0 || (h_ctr.p->flags & FLAG_DEGEN)) && !prm.on_degenerate) {
+            if ((h_ctr.p->degenerate > 0 || (h_ctr.p->flags & FLAG_DEGEN)) && prm.on_degenerate != 1) {
                 st.degenerate = (int64_t)std::max<u64>(h_ctr.p->degenerate, 1);
                 err = "non-general position: a hull facet with more than dim generators was met";
                 return HVB_EDEGENERATE;
@@ -960,6 +1164,19 @@ struct Ctx : hvb_ctx {
         // fixed point: 2^52 units per ext^D (the bounding box volume is at most ext^D); 1/d! is folded into the scale so
         // that the accumulators hold volumes, with 11 bits of headroom for partial sums of either sign
         const double scale = ldexp(1.0, 52) / (pow(dv.ext, (double)D) * fact);
+        if (perturbed) {
+            // a mesh resolved from non-general position: the volumes of the PERTURBED cells (the perturbed diagram is simple,
+            // which is what the flag formula needs; they differ from the caller's by O(HVB_PERTURB_REL)), from every vertex
+            // record of the walk -- the slivers the result rows leave out are vertices of that diagram too
+            const u32 nrec = std::min<u32>(h_sc.p->vcount, (u32)vcap);
+            long long* rows = out_sig[1 - res].p;
+            CK(cudaMemsetAsync(&sc.p->pad2, 0, sizeof(u32), stream));
+            k_rows_from_records<D><<<blocks_for(nrec, 128), 128, 0, stream>>>(dv, perm.p, nrec, rows, &sc.p->pad2); ++launches;
+            CK(cudaMemcpyAsync(h_extra.p, &sc.p->pad2, sizeof(u32), cudaMemcpyDeviceToHost, stream));
+            CK(cudaStreamSynchronize(stream));
+            const u32 cnt = *(const u32*)h_extra.p;
+            if (cnt > 0) { k_cell_volumes<D><<<blocks_for(cnt, 128), 128, 0, stream>>>(rows, cnt, xs_in.p, (long long)n, n_list, planes.p, scale, vol_acc.p); ++launches; }
+        } else
         if (nvert > 0) {
             k_cell_volumes<D><<<blocks_for(nvert, 128), 128, 0, stream>>>(out_sig[res].p, (u32)nvert, xs_in.p, (long long)n, n_list, planes.p, scale, vol_acc.p);
             ++launches;
@@ -976,6 +1193,7 @@ struct Ctx : hvb_ctx {
     // clean_affected! (meshrefine.jl:126-149): which vertices of the caller's old mesh survive the new generators
     DBuf<unsigned char> ca_keep, ca_aff;
     int clean_affected(const int64_t* sig, const double* r, int64_t nv, int stride, int64_t first_new, int64_t n_new, uint8_t* keep, uint8_t* affected) override {
+        if (merged || perturbed) { err = "hvb_clean_affected: not available on a context whose cloud was resolved from non-general position"; return HVB_ESTATE; }
         if (periodic) { err = "refinement is not supported on a periodic context"; return HVB_EINVAL; }
         if (nv < 0 || stride < 1 || (nv > 0 && (!sig || !r || !keep)) || !affected) { err = "bad arguments"; return HVB_EINVAL; }
         if (first_new < 1 || n_new < 0 || first_new + n_new - 1 > n) { err = "the new generators must be a range of the context's ids"; return HVB_EINVAL; }
@@ -1002,6 +1220,7 @@ struct Ctx : hvb_ctx {
 
     // interface areas aligned with the neighbour lists (hvb_geometry.cuh, first facet fixed)
     int cell_areas(double* area) override {
+        if (merged || perturbed) { err = "hvb_cell_areas: not available on a context whose cloud was resolved from non-general position"; return HVB_ESTATE; }
         if (!have_result) { err = "no search result"; return HVB_ESTATE; }
         if (!area) { err = "null output"; return HVB_EINVAL; }
         if (seed_prefix > 0) { err = "interface areas need all vertices of the cells: not available after a search with seed vertices"; return HVB_ESTATE; }
@@ -1110,7 +1329,7 @@ struct Ctx : hvb_ctx {
                 // ---- single-launch walk: seeds were appended to q[0]; k_walk drains and extends it ----------------
                 WalkQueue wq;
                 wq.q = q[0].p; wq.tail = &sc.p->rnd[0].qcount; wq.head = &sc.p->q_head; wq.done = &sc.p->q_done;
-                wq.abort = &sc.p->q_abort; wq.cap = qcap; wq.stop_on_degenerate = prm.on_degenerate ? 0u : 1u;
+                wq.abort = &sc.p->q_abort; wq.cap = qcap; wq.stop_on_degenerate = report_degenerate() ? 1u : 0u;
                 for (;;) {
                     cudaEvent_t e0 = pool_event(n_ev++), e1 = pool_event(n_ev++);
                     CK(cudaEventRecord(e0, stream));
@@ -1123,7 +1342,7 @@ struct Ctx : hvb_ctx {
                     int rc = read_scalars(); if (rc) return rc;
                     items = h_sc.p->q_done;
                     if (h_sc.p->q_abort) { err = "walk kernel timed out (internal error)"; return HVB_ECUDA; }
-                    if ((h_ctr.p->degenerate > 0 || (h_ctr.p->flags & FLAG_DEGEN)) && !prm.on_degenerate) {
+                    if ((h_ctr.p->degenerate > 0 || (h_ctr.p->flags & FLAG_DEGEN)) && report_degenerate()) {
                         st.degenerate = (int64_t)std::max<u64>(h_ctr.p->degenerate, 1);
                         err = "non-general position: a vertex with more than dim+1 cospherical generators was met";
                         return HVB_EDEGENERATE;
@@ -1144,7 +1363,7 @@ struct Ctx : hvb_ctx {
             for (;;) {
                 int rc = read_scalars(); if (rc) return rc;
                 if (h_sc.p->pflags || (h_ctr.p->flags & FLAG_OVERFLOW_MASK)) { overflow = true; break; }
-                if (h_ctr.p->degenerate > 0 && !prm.on_degenerate) {
+                if (h_ctr.p->degenerate > 0 && report_degenerate()) {
                     // non-general position (edgeiterate.jl territory): stop at once instead of walking a corrupt frontier
                     st.degenerate = (int64_t)h_ctr.p->degenerate;
                     err = "non-general position: a vertex with more than dim+1 cospherical generators was met";
@@ -1235,7 +1454,7 @@ struct Ctx : hvb_ctx {
         st.rows_scanned = (int64_t)c.rows; st.probe_stages = (int64_t)c.stages; st.rounds = rounds; st.seeds = (int64_t)c.seeds;
         st.degenerate = (int64_t)c.degenerate; st.kernel_launches = launches; st.capacity_retries = retries;
         have_result = true;
-        if (c.degenerate > 0 && !prm.on_degenerate) {
+        if (c.degenerate > 0 && report_degenerate()) {
             err = "non-general position: a vertex with more than dim+1 cospherical generators was met"; return HVB_EDEGENERATE;
         }
         if (c.seed_fail > 0 && h_sc.p->unseeded > 0) { err = "descent failed for some cells"; return HVB_EINCOMPLETE; }
@@ -1290,7 +1509,8 @@ struct Ctx : hvb_ctx {
             const int world = std::max(1, prm.world), rank = std::min(std::max(0, prm.rank), world - 1);
             k_final_rows<D><<<blocks_for(nrec, 128), 128, 0, stream>>>(dv, perm.p, nrec, bits, out_sig[0].p, out_r[0].p, key_top.p, key_hi.p, key_lo.p,
                                                                      &sc.p->out_count, &sc.p->max_var, by_slab ? owner_ptr : nullptr, rank, seed_prefix,
-                                                                     prm.variance_tol, prm.break_tol, sc.p->tol_counts, (int)n_user);
+                                                                     prm.variance_tol, prm.break_tol, sc.p->tol_counts, (int)n_user,
+                                                                     perturbed ? HVB_FLAT_TOL : 0.0, &sc.p->pad3);
             ++launches;
         }
         if (nrays > 0) {
@@ -1367,13 +1587,22 @@ struct Ctx : hvb_ctx {
     }
     int counts(int64_t* nv, int64_t* nr, int64_t* msl) override {
         if (!have_result) { err = "no search result"; return HVB_ESTATE; }
-        if (nv) *nv = nvert;
+        if (nv) *nv = merged ? m_nvert : nvert;
         if (nr) *nr = nrays;
-        if (msl) *msl = D + 1;
+        if (msl) *msl = merged ? m_maxlen : D + 1;
+        return HVB_OK;
+    }
+    // fixed-width calls on a merged result: fine while every vertex still has dim + 1 generators
+    int merged_fixed(const char* what) {
+        if (merged && m_maxlen > D + 1) {
+            err = std::string(what) + ": the mesh holds vertices with more than dim+1 generators (non-general position): use hvb_fetch_vertices_var";
+            return HVB_ESTATE;
+        }
         return HVB_OK;
     }
     int view_vertices(const int64_t** sig, const double** r, int64_t* nv) override {
         if (!have_result) { err = "no search result"; return HVB_ESTATE; }
+        { int rcm = merged_fixed("hvb_view_vertices"); if (rcm) return rcm; }
         CK(cudaSetDevice(prm.device));
         { int rc = stage_rows(true, false); if (rc) return rc; }
         CK(cudaStreamSynchronize(stream));
@@ -1383,6 +1612,7 @@ struct Ctx : hvb_ctx {
     }
     int view_vertices32(const int32_t** sig, const double** r, int64_t* nv) override {
         if (!have_result) { err = "no search result"; return HVB_ESTATE; }
+        { int rcm = merged_fixed("hvb_view_vertices32"); if (rcm) return rcm; }
         if (n + P >= 0x7fffffffLL) { err = "ids do not fit 32 bits"; return HVB_EINVAL; }
         CK(cudaSetDevice(prm.device));
         { int rc = stage_rows(false, true); if (rc) return rc; }
@@ -1392,6 +1622,12 @@ struct Ctx : hvb_ctx {
         return HVB_OK;
     }
     int fetch_vertices(int64_t* sig, double* r) override {
+        if (merged) {
+            int rcm = merged_fixed("hvb_fetch_vertices"); if (rcm) return rcm;
+            if (sig && !m_ids.empty()) memcpy(sig, m_ids.data(), m_ids.size() * sizeof(int64_t));
+            if (r && !m_r.empty()) memcpy(r, m_r.data(), m_r.size() * sizeof(double));
+            return HVB_OK;
+        }
         const int64_t* s; const double* rr; int64_t nv;
         int rc = view_vertices(&s, &rr, &nv); if (rc) return rc;
         if (sig) memcpy(sig, s, (size_t)nv * (D + 1) * sizeof(int64_t));
@@ -1505,6 +1741,7 @@ struct Ctx : hvb_ctx {
     }
     int neighbor_count(int64_t* total) override {
         if (!have_result) { err = "no search result"; return HVB_ESTATE; }
+        if (merged) { int rcm = build_merged_neighbors(); if (rcm) return rcm; *total = (int64_t)m_nb_ids.size(); return HVB_OK; }
         int rc = build_neighbors(); if (rc) return rc;
         *total = nb_total;
         return HVB_OK;
@@ -1533,6 +1770,7 @@ struct Ctx : hvb_ctx {
     }
     int view_neighbors32(const int64_t** off, const int32_t** ids, int64_t* total) override {
         if (!have_result) { err = "no search result"; return HVB_ESTATE; }
+        if (merged) { err = "hvb_view_neighbors32: not available for a mesh resolved from non-general position (use hvb_view_neighbors)"; return HVB_ESTATE; }
         if (n + P >= 0x7fffffffLL) { err = "ids do not fit 32 bits"; return HVB_EINVAL; }
         CK(cudaSetDevice(prm.device));
         int rc = build_neighbors(); if (rc) return rc;
@@ -1544,6 +1782,11 @@ struct Ctx : hvb_ctx {
     }
     int view_neighbors(const int64_t** off, const int64_t** ids, int64_t* total) override {
         if (!have_result) { err = "no search result"; return HVB_ESTATE; }
+        if (merged) {
+            int rcm = build_merged_neighbors(); if (rcm) return rcm;
+            *off = m_nb_off.data(); *ids = m_nb_ids.data(); *total = (int64_t)m_nb_ids.size();
+            return HVB_OK;
+        }
         CK(cudaSetDevice(prm.device));
         int rc = build_neighbors(); if (rc) return rc;
         rc = stage_neighbors_as(true, false); if (rc) return rc;
@@ -1679,6 +1922,7 @@ struct Ctx : hvb_ctx {
     }
 
     int export_device(void* sig, void* r, int64_t cap, int64_t* count) override {
+        if (merged || perturbed) { err = "hvb_export_device: not available on a context whose cloud was resolved from non-general position"; return HVB_ESTATE; }
         if (!have_result) { err = "no search result"; return HVB_ESTATE; }
         CK(cudaSetDevice(prm.device));
         if (count) *count = nvert;

@@ -25,6 +25,7 @@ struct hvb_ctx {
     virtual int convex_hull(int method) = 0;
     virtual int counts(int64_t* nv, int64_t* nr, int64_t* msl) = 0;
     virtual int fetch_vertices(int64_t* sig, double* r) = 0;
+    virtual int fetch_vertices_var(int64_t* off, int64_t* ids, double* r) = 0;
     virtual int view_vertices(const int64_t** sig, const double** r, int64_t* nv) = 0;
     virtual int view_vertices32(const int32_t** sig, const double** r, int64_t* nv) = 0;
     virtual int view_neighbors32(const int64_t** off, const int32_t** ids, int64_t* total) = 0;

@@ -165,6 +165,25 @@ static __global__ void k_cell_sort(const int* __restrict__ cell_start, int ncell
 }
 // coordinates in grid order (FP64 for verification, FP32 minus the grid origin for the filter) and the inverse
 // permutation; one thread per sorted position: the writes are coalesced
+// Non-general position (Ctx::resolve_degenerate): the generators are moved by a deterministic pseudo-random offset of relative
+// size `rel` (times the extent of the cloud) -- an explicit simulation of simplicity.  The offset depends on the caller's id
+// and the axis alone.
+static __global__ void k_perturb(const double* __restrict__ src, double* __restrict__ dst, size_t count, int dim, double amp) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= count) return;
+    u64 h = mix64((u64)i * 0x9e3779b97f4a7c15ULL + 0x243f6a8885a308d3ULL);
+    const double u = ((double)(h >> 11) + 0.5) * (1.0 / 9007199254740992.0) * 2.0 - 1.0;
+    dst[i] = src[i] + amp * u;
+}
+// caller coordinates in grid order (the coordinates canonical_vertex solves from when the search ran on perturbed ones)
+template <int D>
+static __global__ void k_gather_canon(const double* __restrict__ xs, const int* __restrict__ perm, int n, double* __restrict__ out) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int o = perm[i];
+#pragma unroll
+    for (int k = 0; k < D; ++k) out[(size_t)i * D + k] = xs[(size_t)o * D + k];
+}
 template <int D>
 static __global__ void k_gather_points(Dev<D> dv, const double* __restrict__ xs, const int* __restrict__ perm,
                                 double* __restrict__ x64, float* __restrict__ x32, int* __restrict__ inv) {
@@ -886,7 +905,8 @@ static __global__ void k_final_rows(Dev<D> dv, const int* __restrict__ perm, u32
                              long long* __restrict__ out_sig, double* __restrict__ out_r,
                              u64* __restrict__ key_top, u64* __restrict__ key_hi, u64* __restrict__ key_lo, u32* __restrict__ out_count,
                              double* __restrict__ max_var, const unsigned char* __restrict__ owner, int rank, u32 skip_below,
-                             double variance_tol, double break_tol, u32* __restrict__ tol_counts, int n_user) {
+                             double variance_tol, double break_tol, u32* __restrict__ tol_counts, int n_user,
+                             double flat_tol, u32* __restrict__ flat_count) {
     u32 v = blockIdx.x * blockDim.x + threadIdx.x;
     if (v >= nrec || v < skip_below) return;          // records below skip_below are the caller's own (seed) vertices
     const int* s = dv.vsig + (size_t)v * (D + 1);
@@ -917,7 +937,12 @@ static __global__ void k_final_rows(Dev<D> dv, const int* __restrict__ perm, u32
         }
     }
     double r[D];
-    double var = canonical_vertex<D>(dv, in, r);
+    double flat = 1.0;
+    double var = canonical_vertex<D>(dv, in, r, &flat);
+    // Non-general position resolved by perturbation (Ctx::resolve_degenerate): the search ran on perturbed generators, the
+    // coordinates are solved from the caller's.  A simplex whose d + 1 generators lie in one hyperplane there is a sliver of
+    // the perturbed triangulation between two cospherical cells, not a vertex of the caller's diagram: dropped
+    if (flat_tol > 0 && !(flat > flat_tol)) { atomicAdd(flat_count, 1u); return; }
     // walkray_correct_vertex (raycast.jl:257-279): the relative variance of the squared radii AFTER the correction decides;
     // above break_tol the vertex is irreparable and dropped (SRI_vertex_irreparable), above variance_tol it is kept
     // and counted (SRI_vertex_suboptimal_correction).  NaN (a singular system) counts as irreparable.
@@ -939,6 +964,21 @@ static __global__ void k_final_rows(Dev<D> dv, const int* __restrict__ perm, u32
     if (var > 1e-18) atomicMax(reinterpret_cast<unsigned long long*>(max_var), (unsigned long long)__double_as_longlong(var));
 }
 
+// every live vertex record of the walk as a row of sorted 1-based caller ids (no filter, no order among rows): the
+// complete simplicial vertex set of a perturbed cloud, for the cell volumes of a mesh resolved from non-general position
+template <int D>
+static __global__ void k_rows_from_records(Dev<D> dv, const int* __restrict__ perm, u32 nrec, long long* __restrict__ out, u32* __restrict__ count) {
+    u32 v = blockIdx.x * blockDim.x + threadIdx.x;
+    if (v >= nrec) return;
+    const int* s = dv.vsig + (size_t)v * (D + 1);
+    if (s[0] < 0) return;
+    long long og[D + 1];
+#pragma unroll
+    for (int k = 0; k < D + 1; ++k) og[k] = ((s[k] < dv.n) ? (long long)perm[s[k]] : (long long)s[k]) + 1;
+    for (int a = 1; a < D + 1; ++a) { const long long key = og[a]; int b = a - 1; while (b >= 0 && og[b] > key) { og[b + 1] = og[b]; --b; } og[b + 1] = key; }
+    const u32 pos = atomicAdd(count, 1u);
+    for (int k = 0; k < D + 1; ++k) out[(size_t)pos * (D + 1) + k] = og[k];
+}
 static __global__ void k_iota(u32* a, u32 n) {
     u32 i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) a[i] = i;

@@ -164,6 +164,11 @@ struct MultiCtx : hvb_ctx {
             return sub[k]->fetch_vertices_range(0, cnt_v[k], sig ? sig + at[k] * (dim + 1) : nullptr, r ? r + at[k] * dim : nullptr);
         });
     }
+    int fetch_vertices_var(int64_t* off, int64_t* ids, double* r) override {
+        int64_t nv = 0; int rc = counts(&nv, nullptr, nullptr); if (rc) return rc;
+        if (off) for (int64_t v = 0; v <= nv; ++v) off[v] = v * (dim + 1);
+        return fetch_vertices(ids, r);
+    }
     int fetch_vertices_range(int64_t first, int64_t count, int64_t* sig, double* r) override {
         int rc = need_result(); if (rc) return rc;
         int64_t tot = 0;

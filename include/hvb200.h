@@ -27,7 +27,7 @@ extern "C" {
 #define HVB_ECUDA        -2   /* CUDA runtime error */
 #define HVB_ENOGPU       -3   /* no CUDA device: the library never computes on the host */
 #define HVB_ENOMEM       -4   /* device allocation failed / capacity exhausted after retries */
-#define HVB_EDEGENERATE  -5   /* a vertex with more than dim+1 cospherical generators was met (edgeiterate.jl path) */
+#define HVB_EDEGENERATE  -5   /* a vertex with more than dim+1 cospherical generators was met and on_degenerate did not ask to resolve it */
 #define HVB_ESTATE       -6   /* call sequence error (fetch before search, ...) */
 #define HVB_EINCOMPLETE  -7   /* a descent failed: some cell has no vertex (raycast.jl:54-59 analogue) */
 #define HVB_ENCCL        -8   /* NCCL missing / a collective failed / no communicator on a multi-GPU call */
@@ -64,7 +64,17 @@ typedef struct hvb_params {
     int32_t rank;
     int32_t world;
     int32_t fp32_filter;      /* 1: FP32 candidate filter + FP64 verification (default); 0: FP64 only */
-    int32_t on_degenerate;    /* 0: hvb_search returns HVB_EDEGENERATE (default); 1: count and continue */
+    int32_t on_degenerate;    /* what hvb_search does when it meets a vertex with more than dim+1 cospherical generators
+                                 (non-general position: cubic grids, ...; the reference enumerates such vertices with its
+                                 FastEdgeIterator, edgeiterate.jl:82-780, and returns ONE vertex listing all generators):
+                                 2 (default): resolve it -- the search is repeated on generators moved by a deterministic
+                                    offset of 1e-9 of the cloud's extent (general position), coordinates are solved from the
+                                    caller's generators, slivers are dropped and rows with equal coordinates merged into one
+                                    vertex with the union of the signatures: the reference's result, variable-length rows
+                                    (hvb_counts max_siglen > dim+1, hvb_fetch_vertices_var).  Bounded non-periodic domains,
+                                    one GPU, unseeded searches; elsewhere as 0;
+                                 0: return HVB_EDEGENERATE;
+                                 1: count and continue with one arbitrary winner (unsafe: the mesh may be wrong) */
     int32_t points_per_cell;  /* target occupancy of a uniform-grid cell; 0 = auto */
     int32_t seed_stride;      /* one descent seed every `seed_stride` generators; 0 = auto */
     int32_t sort_output;      /* 1: vertices are returned in lexicographic order of their signature (default) */
@@ -198,8 +208,17 @@ int hvb_convex_hull(hvb_ctx* ctx);
  * kept as a cross-check of the wrapping on the Voronoi side, much slower. */
 int hvb_convex_hull_via(hvb_ctx* ctx, int method);
 
-/* sizes for the fetch calls; max_siglen is dim+1 (general position) */
+/* sizes for the fetch calls; max_siglen is dim+1 unless the cloud was in non-general position and on_degenerate = 2
+ * resolved it (then: the largest number of generators of a vertex) */
 int hvb_counts(hvb_ctx* ctx, int64_t* nvert, int64_t* nrays, int64_t* max_siglen);
+
+/* Variable-length form of hvb_fetch_vertices, for meshes with vertices of more than dim+1 generators (the reference's
+ * sig vectors of non-general vertices, raycast.jl:926-949): vertex v has the sorted 1-based ids ids[off[v] .. off[v+1])
+ * (off: nvert+1 entries, ids: off[nvert] entries -- query off first with ids = r = NULL) and coordinates r[v*dim ..].
+ * Rows are in lexicographic order.  Works for every result; the fixed-width calls (hvb_fetch_vertices, hvb_view_vertices*)
+ * return HVB_ESTATE when max_siglen > dim+1.  On such a mesh the neighbour lists hold the cells that share a FULL
+ * interface (neighbors.jl:205-212), and hvb_cell_volumes / hvb_cell_areas / hvb_clean_affected are not available. */
+int hvb_fetch_vertices_var(hvb_ctx* ctx, int64_t* off, int64_t* ids, double* r);
 
 /* Replaces the replay target push!(mesh, sig=>r) (src/abstractmesh.jl:111): sig = nvert x (dim+1) sorted
  * 1-based ids, r = nvert x dim. */

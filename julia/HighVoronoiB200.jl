@@ -37,7 +37,7 @@ using HighVoronoi
 using StaticArrays
 import HighVoronoi: _voronoi, nodes, AbstractMesh, RaycastIncircleSkip, ThreadSafeDict
 
-export B200Thread, periodic_tessellation, release_contexts!
+export B200Thread, periodic_tessellation, release_contexts!, B200ConvexHull
 
 const LIB = get(ENV, "HVB200_LIB", joinpath(@__DIR__, "..", "highvoronoi.jl_b200", "lib", "libhvb200.so"))
 
@@ -188,10 +188,22 @@ function _voronoi(mesh::AM, TODO, compact, v_offset, silence, iteration_reset, p
     nv = Ref{Int64}(0); nr = Ref{Int64}(0); ml = Ref{Int64}(0)
     check(ccall((:hvb_counts, LIB), Cint, (Ptr{Cvoid}, Ref{Int64}, Ref{Int64}, Ref{Int64}), c, nv, nr, ml), c)
     # rows are copied out (hvb_fetch_vertices): push! keeps the signature vectors, they must not alias library memory
-    sig = Matrix{Int64}(undef, d + 1, nv[]); r = Matrix{Float64}(undef, d, nv[])
-    check(ccall((:hvb_fetch_vertices, LIB), Cint, (Ptr{Cvoid}, Ptr{Int64}, Ptr{Float64}), c, sig, r), c)
-    for v in 1:nv[]
-        push!(mesh, sig[:, v] => P(view(r, :, v)))                                     # abstractmesh.jl:111
+    if ml[] > d + 1
+        # non-general position (cubic grids, ...): the backend resolved it (hvb_params.on_degenerate = 2) and returns the
+        # reference's variable-length signatures -- one vertex per cospherical set, all its generators (raycast.jl:926-949)
+        off = Vector{Int64}(undef, nv[] + 1)
+        check(ccall((:hvb_fetch_vertices_var, LIB), Cint, (Ptr{Cvoid}, Ptr{Int64}, Ptr{Int64}, Ptr{Float64}), c, off, C_NULL, C_NULL), c)
+        ids = Vector{Int64}(undef, off[end]); r = Matrix{Float64}(undef, d, nv[])
+        check(ccall((:hvb_fetch_vertices_var, LIB), Cint, (Ptr{Cvoid}, Ptr{Int64}, Ptr{Int64}, Ptr{Float64}), c, off, ids, r), c)
+        for v in 1:nv[]
+            push!(mesh, ids[off[v]+1:off[v+1]] => P(view(r, :, v)))                    # abstractmesh.jl:111
+        end
+    else
+        sig = Matrix{Int64}(undef, d + 1, nv[]); r = Matrix{Float64}(undef, d, nv[])
+        check(ccall((:hvb_fetch_vertices, LIB), Cint, (Ptr{Cvoid}, Ptr{Int64}, Ptr{Float64}), c, sig, r), c)
+        for v in 1:nv[]
+            push!(mesh, sig[:, v] => P(view(r, :, v)))                                 # abstractmesh.jl:111
+        end
     end
     if nr[] > 0
         edge = Matrix{Int64}(undef, d, nr[]); rb = Matrix{Float64}(undef, d, nr[]); ru = similar(rb); node = Vector{Int64}(undef, nr[])
@@ -202,6 +214,45 @@ function _voronoi(mesh::AM, TODO, compact, v_offset, silence, iteration_reset, p
     end
     return mesh, searcher
 end
+
+"""
+    B200ConvexHull(xs; device = 0)
+
+`ConvexHull(xs)` (chull.jl:213-238) on the device (hvb_convex_hull: gift wrapping, the interior of the tessellation is never
+computed).  Same surface as the reference's `ConvexHull`: `length(cv)` facets, `cv[i] == (sig, r, u)` with `sig` the `d`
+generating nodes (sorted), `r` a point of the facet's hyperplane (the circumcentre of the nodes inside it -- the point the
+reference's projection chull.jl:224-232 yields) and `u` the outer unit normal; iterable.
+"""
+struct B200ConvexHull{P}
+    sig::Matrix{Int64}
+    r::Matrix{Float64}
+    u::Matrix{Float64}
+end
+function B200ConvexHull(xs::Vector{P}; device::Integer = 0) where {P}
+    d = size(P)[1]; n = length(xs)
+    prm = HvbParams()
+    ccall((:hvb_default_params, LIB), Cvoid, (Ref{HvbParams},), prm)
+    prm.device = device
+    ctx = Ref{Ptr{Cvoid}}(C_NULL)
+    GC.@preserve xs check(ccall((:hvb_create, LIB), Cint,
+                (Ref{Ptr{Cvoid}}, Cint, Int64, Ptr{Float64}, Cint, Ptr{Float64}, Ptr{Float64}, Ref{HvbParams}),
+                ctx, d, n, pointer(reinterpret(Float64, xs)), 0, C_NULL, C_NULL, prm))
+    c = ctx[]
+    try
+        check(ccall((:hvb_convex_hull, LIB), Cint, (Ptr{Cvoid},), c), c)
+        nv = Ref{Int64}(0); nr = Ref{Int64}(0); ml = Ref{Int64}(0)
+        check(ccall((:hvb_counts, LIB), Cint, (Ptr{Cvoid}, Ref{Int64}, Ref{Int64}, Ref{Int64}), c, nv, nr, ml), c)
+        edge = Matrix{Int64}(undef, d, nr[]); rb = Matrix{Float64}(undef, d, nr[]); ru = similar(rb); node = Vector{Int64}(undef, nr[])
+        nr[] > 0 && check(ccall((:hvb_fetch_rays, LIB), Cint, (Ptr{Cvoid}, Ptr{Int64}, Ptr{Float64}, Ptr{Float64}, Ptr{Int64}), c, edge, rb, ru, node), c)
+        order = sortperm(collect(eachcol(edge)))
+        return B200ConvexHull{P}(edge[:, order], rb[:, order], ru[:, order])
+    finally
+        ccall((:hvb_destroy, LIB), Cvoid, (Ptr{Cvoid},), c)
+    end
+end
+Base.length(c::B200ConvexHull) = size(c.sig, 2)
+Base.getindex(c::B200ConvexHull{P}, i::Int) where {P} = (c.sig[:, i], P(view(c.r, :, i)), P(view(c.u, :, i)))
+Base.iterate(c::B200ConvexHull, state = 1) = state > length(c) ? nothing : (c[state], state + 1)
 
 """
     clean_affected(ctx, sig, r, lnxs, n) -> (keep, affected)

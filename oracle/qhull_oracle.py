@@ -62,3 +62,40 @@ def bounded(X, base, normal):
             sig = tuple(sorted(ids + [i + 1]))
             verts.setdefault(sig, pt + xi)
     return verts
+
+
+def voronoi_nongeneral(X, base=None, normal=None, tol=1e-9):
+    """Truth for clouds in NON-general position (cubic grids, ...): Qhull's Voronoi diagram of the generators plus their mirror
+    images at the planes (scipy.spatial.Voronoi merges cospherical Delaunay facets into one Voronoi vertex).  Returns
+    {frozenset of 1-based ids (plane p = n + p): coordinates} for the vertices inside the domain -- what the reference
+    returns for such input: one vertex per cospherical set, listing ALL its generators (raycast.jl:926-949).
+    TEST INFRASTRUCTURE ONLY."""
+    from scipy.spatial import Voronoi
+    X = np.asarray(X, dtype=np.float64)
+    n, d = X.shape
+    P = 0 if base is None else len(base)
+    pts = [X]
+    for p in range(P):
+        s = ((base[p] - X) * normal[p]).sum(1)
+        pts.append(X + 2.0 * s[:, None] * normal[p])
+    allp = np.vstack(pts)
+    vor = Voronoi(allp)
+    v2p = {}
+    for pi, ri in enumerate(vor.point_region):
+        for v in vor.regions[ri]:
+            if v >= 0:
+                v2p.setdefault(v, set()).add(pi)
+    out = {}
+    for v, ps in v2p.items():
+        c = vor.vertices[v]
+        if P and not all(((c - base[p]) @ normal[p]) <= tol for p in range(P)):
+            continue
+        real = {p for p in ps if p < n}
+        if not real:
+            continue
+        ids = {p + 1 for p in real}
+        for p in ps:
+            if p >= n and (p - n) % n in real:            # the mirror image of one of the vertex's own generators: a plane
+                ids.add(n + (p - n) // n + 1)
+        out[frozenset(ids)] = c
+    return out

@@ -53,8 +53,8 @@ static SimResult* run(int64_t n, const double* xs, int P, const double* base, co
         ps.off[p] = off;
     }
     std::vector<unsigned char> active(n, 1), hasv(n, 0);
-    dv.cell_start = cstart.data(); dv.x32 = x32.data(); dv.x64 = x64.data(); dv.planes = &ps; dv.active = active.data();
-    dv.plane_tol = 1e-12; dv.probe_scale = probe_scale > 1.0 ? probe_scale : 1.3; dv.probe_growth = 2.0; dv.fp32_filter = fp32;
+    dv.cell_start = cstart.data(); dv.x32 = x32.data(); dv.x64 = x64.data(); dv.xcan = x64.data(); dv.planes = &ps; dv.active = active.data();
+    dv.plane_tol = 1e-12; dv.t_min = 1e-12; dv.probe_scale = probe_scale > 1.0 ? probe_scale : 1.3; dv.probe_growth = 2.0; dv.fp32_filter = fp32;
     int64_t vcap = estimate_vertices(D, n, P) * 2;
     std::vector<int> vsig(vcap * (D + 1)); std::vector<double> vr(vcap * D);
     u32 vcount = 0;
@@ -190,8 +190,8 @@ static HullResult* run_hull(int64_t n, const double* xs, int ppc) {
         for (int k = 0; k < D; ++k) { x64[i * D + k] = xs[(int64_t)perm[i] * D + k]; x32[i * X32<D>::STRIDE + k] = (float)(x64[i * D + k] - dv.lo[k]); }
     PlaneSet ps; memset(&ps, 0, sizeof(ps));
     std::vector<unsigned char> active(n, 1), hasv(n, 0);
-    dv.cell_start = cstart.data(); dv.x32 = x32.data(); dv.x64 = x64.data(); dv.planes = &ps; dv.active = active.data();
-    dv.plane_tol = 1e-12; dv.probe_scale = default_probe_scale(D); dv.probe_growth = 1e9; dv.fp32_filter = 1;
+    dv.cell_start = cstart.data(); dv.x32 = x32.data(); dv.x64 = x64.data(); dv.xcan = x64.data(); dv.planes = &ps; dv.active = active.data();
+    dv.plane_tol = 1e-12; dv.t_min = 1e-12; dv.probe_scale = default_probe_scale(D); dv.probe_growth = 1e9; dv.fp32_filter = 1;
     int64_t vcap = estimate_vertices(D, n, 0);
     std::vector<int> vsig(vcap * (D + 1)); std::vector<double> vr(vcap * D);
     u32 vcount = 0;
@@ -252,7 +252,7 @@ static HullResult* run_wrap(int64_t n, const double* xs, int slots, int fp32) {
     for (int64_t i = 0; i < n; ++i)
         for (int k = 0; k < D; ++k) { x64[i * D + k] = xs[(int64_t)perm[i] * D + k]; x32[i * X32<D>::STRIDE + k] = (float)(x64[i * D + k] - dv.lo[k]); }
     Counters ctr; memset(&ctr, 0, sizeof(ctr));
-    dv.x32 = x32.data(); dv.x64 = x64.data(); dv.ctr = &ctr;
+    dv.x32 = x32.data(); dv.x64 = x64.data(); dv.xcan = x64.data(); dv.ctr = &ctr;
     HullDev<D> hd;
     u32 fcap = (u32)std::max<int64_t>(1 << 12, 64 * n), fcount = 0;
     std::vector<int> fsig((size_t)fcap * D); std::vector<u32> fitem(fcap); std::vector<double> fu((size_t)fcap * D);
