@@ -906,7 +906,7 @@ static __global__ void k_final_rows(Dev<D> dv, const int* __restrict__ perm, u32
                              u64* __restrict__ key_top, u64* __restrict__ key_hi, u64* __restrict__ key_lo, u32* __restrict__ out_count,
                              double* __restrict__ max_var, const unsigned char* __restrict__ owner, int rank, u32 skip_below,
                              double variance_tol, double break_tol, u32* __restrict__ tol_counts, int n_user,
-                             double flat_tol, u32* __restrict__ flat_count) {
+                             double flat_tol, u32* __restrict__ flat_count, int* __restrict__ bucket_count) {
     u32 v = blockIdx.x * blockDim.x + threadIdx.x;
     if (v >= nrec || v < skip_below) return;          // records below skip_below are the caller's own (seed) vertices
     const int* s = dv.vsig + (size_t)v * (D + 1);
@@ -949,6 +949,7 @@ static __global__ void k_final_rows(Dev<D> dv, const int* __restrict__ perm, u32
     if (!(var <= break_tol)) { atomicAdd(tol_counts + 0, 1u); return; }
     if (var > variance_tol) atomicAdd(tol_counts + 1, 1u);
     u32 pos = atomicAdd(out_count, 1u);
+    if (bucket_count) atomicAdd(bucket_count + (int)og[0], 1);     // rows per first (smallest) generator: sort_rows_bucket
     u64 top = 0, hi = 0, lo = 0;
 #pragma unroll
     for (int k = 0; k < D + 1; ++k) {
@@ -987,10 +988,49 @@ static __global__ void k_gather_u64(const u64* __restrict__ src, const u32* __re
     u32 i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) dst[i] = src[idx[i]];
 }
+// Lexicographic order of the rows for d <= 3 (Ctx::sort_rows_bucket): a counting sort on the first id (always a generator, the
+// smallest id of the row) and an insertion sort inside each bucket (6.6 rows on average at d = 3) replace the nine radix passes
+// over 68-bit keys.  The row count is a device word: nothing here waits for the host.
+static __global__ void k_bucket_scatter(const long long* __restrict__ sig, int stride, const u32* __restrict__ count_ptr, const int* __restrict__ start,
+                                        int* __restrict__ cursor, u32* __restrict__ idx) {
+    u32 i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= *count_ptr) return;
+    const int b = (int)(sig[(size_t)i * stride] - 1);
+    idx[start[b] + atomicAdd(cursor + b, 1)] = i;
+}
+// inside a bucket the rows share their first id, so the low 64 bits of the packed sort key (the remaining d ids, d * bits <= 64)
+// order them: keys and row numbers of a bucket are sorted in thread-local arrays (buckets of up to 48 rows; larger ones in place)
+static __global__ void k_bucket_sort(const u64* __restrict__ key, const int* __restrict__ start, int nb, u32* __restrict__ idx) {
+    int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= nb) return;
+    const int lo = start[b], m = start[b + 1] - lo;
+    if (m <= 1) return;
+    if (m <= 48) {
+        u64 k[48];
+        u32 v[48];
+        for (int a = 0; a < m; ++a) { v[a] = idx[lo + a]; k[a] = key[v[a]]; }
+        for (int a = 1; a < m; ++a) {
+            const u64 kk = k[a]; const u32 vv = v[a];
+            int j = a - 1;
+            while (j >= 0 && k[j] > kk) { k[j + 1] = k[j]; v[j + 1] = v[j]; --j; }
+            k[j + 1] = kk; v[j + 1] = vv;
+        }
+        for (int a = 0; a < m; ++a) idx[lo + a] = v[a];
+        return;
+    }
+    for (int a = 1; a < m; ++a) {
+        const u32 vv = idx[lo + a];
+        const u64 kk = key[vv];
+        int j = a - 1;
+        while (j >= 0 && key[idx[lo + j]] > kk) { idx[lo + j + 1] = idx[lo + j]; --j; }
+        idx[lo + j + 1] = vv;
+    }
+}
 template <int D>
 static __global__ void k_gather_rows(const long long* __restrict__ sig_in, const double* __restrict__ r_in, const u32* __restrict__ idx,
-                              long long* __restrict__ sig_out, double* __restrict__ r_out, u32 n) {
+                              long long* __restrict__ sig_out, double* __restrict__ r_out, u32 n, const u32* __restrict__ n_ptr = nullptr) {
     u32 i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (n_ptr) n = *n_ptr;
     if (i >= n) return;
     u32 s = idx[i];
 #pragma unroll
@@ -1225,6 +1265,9 @@ static __global__ void k_cell_volumes(const long long* __restrict__ sig, u32 nv,
     for (int k = 0; k < D + 1; ++k) {
         if (s[k] > n_list) continue;                       // planes and halo generators have no cell of their own here
         const double t = vertex_flag_sum<D>(xs, n, ps, s, k) * scale;
+        // a single term beyond 2^62 units would saturate the conversion silently (a foot point far outside the cloud:
+        // nearly parallel facets): flagged in the word behind the accumulators, the host reports it
+        if (!(fabs(t) < 4.6e18)) atomicOr(reinterpret_cast<unsigned long long*>(acc + n_list), 1ULL);
         atomicAdd(reinterpret_cast<unsigned long long*>(acc + (s[k] - 1)), (unsigned long long)__double2ll_rn(t));
     }
 }
@@ -1242,7 +1285,7 @@ __device__ __forceinline__ long long csr_find(const long long* __restrict__ off,
 template <int D>
 static __global__ void k_cell_areas(const long long* __restrict__ sig, u32 nv, const double* __restrict__ xs, long long n, long long n_list,
                              const PlaneSet* __restrict__ ps, const long long* __restrict__ off, const long long* __restrict__ ids,
-                             double scale, long long* __restrict__ acc) {
+                             double scale, long long* __restrict__ acc, long long* __restrict__ sat) {
     u32 v = blockIdx.x * blockDim.x + threadIdx.x;
     if (v >= nv) return;
     long long s[D + 1];
@@ -1255,6 +1298,7 @@ static __global__ void k_cell_areas(const long long* __restrict__ sig, u32 nv, c
             const long long pos = csr_find(off, ids, s[k], s[q]);
             if (pos < 0) continue;
             const double t = vertex_flag_sum<D>(xs, n, ps, s, k, q) * scale;
+            if (!(fabs(t) < 4.6e18)) atomicOr(reinterpret_cast<unsigned long long*>(sat), 1ULL);
             atomicAdd(reinterpret_cast<unsigned long long*>(acc + pos), (unsigned long long)__double2ll_rn(t));
         }
     }
