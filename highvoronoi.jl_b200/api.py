@@ -294,6 +294,21 @@ class VoronoiMesh:
         _abi.check(L.hvb_cell_volumes(ctx, vol.ctypes.data_as(ctypes.c_void_p)), ctx)
         return vol
 
+    def moments(self):
+        """(vol [n], first [n, d], second [n, d, d]): the integrals of 1, x_a and x_a x_b over every cell, exact
+        (VoronoiData(...).bulk_integral for polynomial integrands up to degree two; hvb_cell_moments)"""
+        L, ctx = _abi.lib(), self.searcher._ctx
+        n, d = getattr(self, "n_user", self.n), self.dim
+        vol = np.empty((n,)); first = np.empty((n, d)); second = np.empty((n, d, d))
+        P = lambda a: a.ctypes.data_as(ctypes.c_void_p)
+        _abi.check(L.hvb_cell_moments(ctx, P(vol), P(first), P(second)), ctx)
+        return vol, first, second
+
+    def centroids(self):
+        """centres of mass of the cells (first moment / volume): the update of a Lloyd step"""
+        vol, first, _ = self.moments()
+        return first / vol[:, None]
+
     def areas(self):
         """interface areas aligned with the ids of neighbors() (VoronoiData(...).area; hvb_cell_areas); +inf for facets
         that hold an unbounded edge"""

@@ -250,7 +250,7 @@ struct Ctx : hvb_ctx {
         if (sstream2) { cudaStreamSynchronize(sstream2); cudaStreamDestroy(sstream2); }
         if (ev_p0) cudaEventDestroy(ev_p0);
         if (ev_p1) cudaEventDestroy(ev_p1);
-        vol_acc.release(); vol_dev.release(); ca_keep.release(); ca_aff.release();
+        vol_acc.release(); vol_dev.release(); mom_dev.release(); vol_sat.release(); ca_keep.release(); ca_aff.release();
         halo_cnt.release(); halo_off.release(); halo_origin.release(); halo_mult.release(); vflags.release(); cert.release(); h_cert.release();
         if (sstream) { cudaStreamSynchronize(sstream); cudaStreamDestroy(sstream); }
         if (stream) cudaStreamDestroy(stream);
@@ -1161,8 +1161,9 @@ struct Ctx : hvb_ctx {
         if (seed_prefix > 0) { err = "cell volumes need all vertices of the cells: not available after a search with seed vertices"; return HVB_ESTATE; }
         CK(cudaSetDevice(prm.device));
         const long long n_list = periodic ? n_user : n;
-        CK(vol_acc.ensure(n_list + 1)); CK(vol_dev.ensure(n_list));
-        CK(cudaMemsetAsync(vol_acc.p, 0, (size_t)(n_list + 1) * sizeof(long long), stream));
+        CK(vol_acc.ensure(n_list)); CK(vol_dev.ensure(n_list)); CK(vol_sat.ensure(n_list));
+        CK(cudaMemsetAsync(vol_acc.p, 0, (size_t)n_list * sizeof(long long), stream));
+        CK(cudaMemsetAsync(vol_sat.p, 0, (size_t)n_list, stream));
         double fact = 1.0;
         for (int k = 2; k <= D; ++k) fact *= k;
         // fixed point: 2^52 units per ext^D (the bounding box volume is at most ext^D); 1/d! is folded into the scale so
@@ -1179,20 +1180,60 @@ struct Ctx : hvb_ctx {
             CK(cudaMemcpyAsync(h_extra.p, &sc.p->pad2, sizeof(u32), cudaMemcpyDeviceToHost, stream));
             CK(cudaStreamSynchronize(stream));
             const u32 cnt = *(const u32*)h_extra.p;
-            if (cnt > 0) { k_cell_volumes<D><<<blocks_for(cnt, 128), 128, 0, stream>>>(rows, cnt, xs_in.p, (long long)n, n_list, planes.p, scale, vol_acc.p); ++launches; }
+            if (cnt > 0) { k_cell_volumes<D><<<blocks_for(cnt, 128), 128, 0, stream>>>(rows, cnt, xs_in.p, (long long)n, n_list, planes.p, scale, vol_acc.p, vol_sat.p); ++launches; }
         } else
         if (nvert > 0) {
-            k_cell_volumes<D><<<blocks_for(nvert, 128), 128, 0, stream>>>(out_sig[res].p, (u32)nvert, xs_in.p, (long long)n, n_list, planes.p, scale, vol_acc.p);
+            k_cell_volumes<D><<<blocks_for(nvert, 128), 128, 0, stream>>>(out_sig[res].p, (u32)nvert, xs_in.p, (long long)n, n_list, planes.p, scale, vol_acc.p, vol_sat.p);
             ++launches;
         }
-        k_volumes_finish<<<blocks_for(n_list, 256), 256, 0, stream>>>(vol_acc.p, 1.0 / (scale * fact), vol_dev.p, n_list); ++launches;
+        k_volumes_finish<<<blocks_for(n_list, 256), 256, 0, stream>>>(vol_acc.p, 1.0 / (scale * fact), vol_dev.p, n_list, vol_sat.p); ++launches;
         if (nrays > 0) { k_volumes_unbounded<<<blocks_for(nrays * D, 256), 256, 0, stream>>>(ray_edge.p, (long long)nrays * D, n_list, vol_dev.p); ++launches; }
         CK(cudaMemcpyAsync(vol, vol_dev.p, (size_t)n_list * sizeof(double), cudaMemcpyDeviceToHost, stream));
-        CK(cudaMemcpyAsync(h_extra.p, vol_acc.p + n_list, sizeof(long long), cudaMemcpyDeviceToHost, stream));
         CK(cudaStreamSynchronize(stream));
         CK(cudaGetLastError());
         st.kernel_launches = launches;
-        if (*h_extra.p != 0) { err = "hvb_cell_volumes: a term of the fixed-point sum left its range (nearly parallel facets: a foot point far outside the cloud); the volumes are not reliable"; return HVB_EINCOMPLETE; }
+        return HVB_OK;
+    }
+
+    // integrals of 1, x_a and x_a x_b over every cell (hvb_cell_moments): same rows, same completeness rule, same fixed-point
+    // accumulation as the volumes
+    DBuf<double> mom_dev;
+    DBuf<unsigned char> vol_sat;           // cells (or list entries) one of whose terms left the fixed-point range: they get NaN
+    int cell_moments(double* vol, double* first, double* second) override {
+        if (!have_result) { err = "no search result"; return HVB_ESTATE; }
+        if (seed_prefix > 0) { err = "cell moments need all vertices of the cells: not available after a search with seed vertices"; return HVB_ESTATE; }
+        if (std::max(1, prm.world) > 1) { err = "hvb_cell_moments runs on a single-GPU context"; return HVB_EINVAL; }
+        CK(cudaSetDevice(prm.device));
+        const int NM = 1 + D + D * (D + 1) / 2;
+        const long long n_list = periodic ? n_user : n;
+        CK(vol_acc.ensure((size_t)n_list * NM)); CK(mom_dev.ensure((size_t)n_list * (1 + D + D * D))); CK(vol_sat.ensure(n_list));
+        CK(cudaMemsetAsync(vol_acc.p, 0, (size_t)n_list * NM * sizeof(long long), stream));
+        CK(cudaMemsetAsync(vol_sat.p, 0, (size_t)n_list, stream));
+        double fact = 1.0;
+        for (int k = 2; k <= D; ++k) fact *= k;
+        // one fixed-point scale per degree: 2^52 units per ext^(D + degree) (local coordinates are bounded by the cell's diameter)
+        const double s0 = ldexp(1.0, 52) / (pow(dv.ext, (double)D) * fact), s1 = s0 / dv.ext, s2 = s1 / dv.ext;
+        const long long* rows = out_sig[res].p;
+        u32 cnt = (u32)nvert;
+        if (perturbed) {
+            const u32 nrec = std::min<u32>(h_sc.p->vcount, (u32)vcap);
+            long long* tmp = out_sig[1 - res].p;
+            CK(cudaMemsetAsync(&sc.p->pad2, 0, sizeof(u32), stream));
+            k_rows_from_records<D><<<blocks_for(nrec, 128), 128, 0, stream>>>(dv, perm.p, nrec, tmp, &sc.p->pad2); ++launches;
+            CK(cudaMemcpyAsync(h_extra.p, &sc.p->pad2, sizeof(u32), cudaMemcpyDeviceToHost, stream));
+            CK(cudaStreamSynchronize(stream));
+            cnt = *(const u32*)h_extra.p; rows = tmp;
+        }
+        if (cnt > 0) { k_cell_moments<D><<<blocks_for(cnt, 128), 128, 0, stream>>>(rows, cnt, xs_in.p, (long long)n, n_list, planes.p, s0, s1, s2, vol_acc.p, vol_sat.p); ++launches; }
+        double* dvol = mom_dev.p; double* dfirst = mom_dev.p + n_list; double* dsecond = mom_dev.p + n_list * (1 + D);
+        k_moments_finish<D><<<blocks_for(n_list, 128), 128, 0, stream>>>(vol_acc.p, xs_in.p, n_list, 1.0 / (s0 * fact), 1.0 / (s1 * fact), 1.0 / (s2 * fact), dvol, dfirst, dsecond, vol_sat.p); ++launches;
+        if (nrays > 0) { k_moments_unbounded<<<blocks_for(nrays * D, 256), 256, 0, stream>>>(ray_edge.p, (long long)nrays * D, n_list, D, dvol, dfirst, dsecond); ++launches; }
+        if (vol) CK(cudaMemcpyAsync(vol, dvol, (size_t)n_list * sizeof(double), cudaMemcpyDeviceToHost, stream));
+        if (first) CK(cudaMemcpyAsync(first, dfirst, (size_t)n_list * D * sizeof(double), cudaMemcpyDeviceToHost, stream));
+        if (second) CK(cudaMemcpyAsync(second, dsecond, (size_t)n_list * D * D * sizeof(double), cudaMemcpyDeviceToHost, stream));
+        CK(cudaStreamSynchronize(stream));
+        CK(cudaGetLastError());
+        st.kernel_launches = launches;
         return HVB_OK;
     }
 
@@ -1234,27 +1275,26 @@ struct Ctx : hvb_ctx {
         CK(cudaSetDevice(prm.device));
         const long long n_list = periodic ? n_user : n;
         const long long tot = std::max<long long>(nb_total, 1);
-        CK(vol_acc.ensure(tot + 1)); CK(vol_dev.ensure(tot));
-        CK(cudaMemsetAsync(vol_acc.p, 0, (size_t)(tot + 1) * sizeof(long long), stream));
+        CK(vol_acc.ensure(tot)); CK(vol_dev.ensure(tot)); CK(vol_sat.ensure(tot));
+        CK(cudaMemsetAsync(vol_acc.p, 0, (size_t)tot * sizeof(long long), stream));
+        CK(cudaMemsetAsync(vol_sat.p, 0, (size_t)tot, stream));
         double fact = 1.0;
         for (int k = 2; k <= D - 1; ++k) fact *= k;
         const double scale = ldexp(1.0, 52) / (pow(dv.ext, (double)(D - 1)) * fact);
         if (nvert > 0 && nb_total > 0) {
             k_cell_areas<D><<<blocks_for(nvert, 128), 128, 0, stream>>>(out_sig[res].p, (u32)nvert, xs_in.p, (long long)n, n_list, planes.p,
-                                                                       nb_off.p, nb_ids.p, scale, vol_acc.p, vol_acc.p + tot);
+                                                                       nb_off.p, nb_ids.p, scale, vol_acc.p, vol_sat.p);
             ++launches;
         }
-        k_volumes_finish<<<blocks_for(tot, 256), 256, 0, stream>>>(vol_acc.p, 1.0 / (scale * fact), vol_dev.p, tot); ++launches;
+        k_volumes_finish<<<blocks_for(tot, 256), 256, 0, stream>>>(vol_acc.p, 1.0 / (scale * fact), vol_dev.p, tot, vol_sat.p); ++launches;
         if (nrays > 0 && nb_total > 0) {
             k_areas_unbounded<<<blocks_for(nrays, 256), 256, 0, stream>>>(ray_edge.p, (long long)nrays, D, n_list, nb_off.p, nb_ids.p, vol_dev.p);
             ++launches;
         }
         if (nb_total > 0) CK(cudaMemcpyAsync(area, vol_dev.p, (size_t)nb_total * sizeof(double), cudaMemcpyDeviceToHost, stream));
-        CK(cudaMemcpyAsync(h_extra.p, vol_acc.p + tot, sizeof(long long), cudaMemcpyDeviceToHost, stream));
         CK(cudaStreamSynchronize(stream));
         CK(cudaGetLastError());
         st.kernel_launches = launches;
-        if (*h_extra.p != 0) { err = "hvb_cell_areas: a term of the fixed-point sum left its range (nearly parallel facets); the areas are not reliable"; return HVB_EINCOMPLETE; }
         return HVB_OK;
     }
 

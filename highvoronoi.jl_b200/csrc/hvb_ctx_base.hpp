@@ -18,6 +18,7 @@ struct hvb_ctx {
     virtual int fetch_vertex_flags(uint8_t* flags) = 0;
     virtual int fetch_owned(uint8_t* owned) = 0;
     virtual int cell_volumes(double* vol) = 0;
+    virtual int cell_moments(double* vol, double* first, double* second) = 0;
     virtual int cell_areas(double* area) = 0;
     virtual int clean_affected(const int64_t* sig, const double* r, int64_t nv, int stride, int64_t first_new, int64_t n_new, uint8_t* keep, uint8_t* affected) = 0;
     virtual int set_points(int64_t n, const double* xs) = 0;

@@ -91,4 +91,88 @@ HVB_HD double vertex_flag_sum(const double* xs, long long n, const PlaneSet* ps,
     return total;
 }
 
+// Integrals of 1, y_a and y_a y_b over the cell, y = x - x_i (the bulk integrals of VoronoiData for polynomial
+// integrands up to degree two, integrate.jl:33-53 / polyintegrator.jl -- the reference's own tests integrate x -> [1, x1^2, x2^2],
+// test/periodicgrids.jl).  Every flag of the decomposition above is an orthoscheme: the simplex with the vertices
+// c_0 = x_i, c_1 (foot on the first facet), ..., c_d (the Voronoi vertex) and signed volume prod(h) / d!.  Over a simplex with
+// vertices p_0..p_d:  int y_a = vol * S_a / (d + 1),  int y_a y_b = vol * (S_a S_b + T_ab) / ((d + 1)(d + 2)),  S = sum p_k,
+// T_ab = sum p_k,a p_k,b.  The running sums S, T travel down the recursion with the foot points.
+// out[0] += sum prod(h);  out[1 + a] += sum prod(h) S_a / (d+1);  out[1 + D + idx(a,b)] += sum prod(h) (S_a S_b + T_ab) / ((d+1)(d+2)),
+// idx over a <= b row by row.  Divide by d! for the integrals.
+template <int D>
+HVB_HD void vertex_flag_moments(const double* xs, long long n, const PlaneSet* ps, const long long* s, int pos, double* out) {
+    const int NM = 1 + D + D * (D + 1) / 2;
+    for (int a = 0; a < NM; ++a) out[a] = 0.0;
+    double nrm[D][D], b[D];
+    const double* xi = xs + (size_t)(s[pos] - 1) * D;
+    int cnt = 0;
+    for (int k = 0; k < D + 1; ++k) {
+        if (k == pos) continue;
+        const long long g = s[k];
+        if (g <= n) {
+            const double* xg = xs + (size_t)(g - 1) * D;
+            double q = 0;
+            for (int a = 0; a < D; ++a) { nrm[cnt][a] = xg[a] - xi[a]; q += nrm[cnt][a] * nrm[cnt][a]; }
+            b[cnt] = 0.5 * q;
+        } else {
+            const int p = (int)(g - n - 1);
+            double q = 0;
+            for (int a = 0; a < D; ++a) { nrm[cnt][a] = ps->normal[p * 6 + a]; q += nrm[cnt][a] * xi[a]; }
+            b[cnt] = ps->off[p] - q;
+        }
+        ++cnt;
+    }
+    double Q[D][D], c[D + 1][D], prod[D + 1];
+    double S[D + 1][D], T[D + 1][D * (D + 1) / 2];          // sums over the chain c_0..c_depth (c_0 = 0 contributes nothing)
+    int it[D];
+    unsigned used = 0;
+    for (int a = 0; a < D; ++a) { c[0][a] = 0.0; S[0][a] = 0.0; }
+    for (int a = 0; a < D * (D + 1) / 2; ++a) T[0][a] = 0.0;
+    prod[0] = 1.0;
+    int depth = 0;
+    it[0] = -1;
+    for (;;) {
+        int j = it[depth] + 1;
+        while (j < D && ((used >> j) & 1u)) ++j;
+        if (j >= D) {
+            if (depth == 0) break;
+            --depth;
+            used &= ~(1u << it[depth]);
+            continue;
+        }
+        it[depth] = j;
+        double m[D];
+        for (int a = 0; a < D; ++a) m[a] = nrm[j][a];
+        for (int rep = 0; rep < 2; ++rep)
+            for (int q = 0; q < depth; ++q) {
+                double sp = 0;
+                for (int a = 0; a < D; ++a) sp += Q[q][a] * m[a];
+                for (int a = 0; a < D; ++a) m[a] -= sp * Q[q][a];
+            }
+        double len2 = 0, nc = 0;
+        for (int a = 0; a < D; ++a) { len2 += m[a] * m[a]; nc += nrm[j][a] * c[depth][a]; }
+        const double len = sqrt(len2);
+        const double h = (len > 0) ? (b[j] - nc) / len : 0.0;
+        double cn[D];                                    // the next point of the chain: foot on facet j (the vertex at the last level)
+        for (int a = 0; a < D; ++a) cn[a] = c[depth][a] + ((len > 0) ? h * m[a] / len : 0.0);
+        if (depth + 1 == D) {
+            const double w = prod[depth] * h;
+            out[0] += w;
+            double Sa[D];
+            for (int a = 0; a < D; ++a) { Sa[a] = S[depth][a] + cn[a]; out[1 + a] += w * Sa[a] / (D + 1); }
+            int q = 0;
+            for (int a = 0; a < D; ++a)
+                for (int bb = a; bb < D; ++bb, ++q)
+                    out[1 + D + q] += w * (Sa[a] * Sa[bb] + T[depth][q] + cn[a] * cn[bb]) / ((D + 1) * (D + 2));
+            continue;
+        }
+        for (int a = 0; a < D; ++a) { Q[depth][a] = m[a] / len; c[depth + 1][a] = cn[a]; S[depth + 1][a] = S[depth][a] + cn[a]; }
+        { int q = 0; for (int a = 0; a < D; ++a) for (int bb = a; bb < D; ++bb, ++q) T[depth + 1][q] = T[depth][q] + cn[a] * cn[bb]; }
+        prod[depth + 1] = prod[depth] * h;
+        used |= 1u << j;
+        ++depth;
+        it[depth] = -1;
+    }
+}
+
 }  // namespace hvb

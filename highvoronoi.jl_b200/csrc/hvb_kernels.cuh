@@ -1256,7 +1256,7 @@ static __global__ void k_clean_affected(Dev<D> dv, const int* __restrict__ perm,
 // ------------------------------------------------------------------------------------------------------------
 template <int D>
 static __global__ void k_cell_volumes(const long long* __restrict__ sig, u32 nv, const double* __restrict__ xs, long long n, long long n_list,
-                               const PlaneSet* __restrict__ ps, double scale, long long* __restrict__ acc) {
+                               const PlaneSet* __restrict__ ps, double scale, long long* __restrict__ acc, unsigned char* __restrict__ sat) {
     u32 v = blockIdx.x * blockDim.x + threadIdx.x;
     if (v >= nv) return;
     long long s[D + 1];
@@ -1266,14 +1266,15 @@ static __global__ void k_cell_volumes(const long long* __restrict__ sig, u32 nv,
         if (s[k] > n_list) continue;                       // planes and halo generators have no cell of their own here
         const double t = vertex_flag_sum<D>(xs, n, ps, s, k) * scale;
         // a single term beyond 2^62 units would saturate the conversion silently (a foot point far outside the cloud:
-        // nearly parallel facets): flagged in the word behind the accumulators, the host reports it
-        if (!(fabs(t) < 4.6e18)) atomicOr(reinterpret_cast<unsigned long long*>(acc + n_list), 1ULL);
+        // nearly parallel facets, a bounded cell of an unbounded domain): the cell is marked and gets NaN
+        if (!(fabs(t) < 4.6e18)) sat[s[k] - 1] = 1;
         atomicAdd(reinterpret_cast<unsigned long long*>(acc + (s[k] - 1)), (unsigned long long)__double2ll_rn(t));
     }
 }
-static __global__ void k_volumes_finish(const long long* __restrict__ acc, double inv_scale, double* __restrict__ vol, long long n) {
+static __global__ void k_volumes_finish(const long long* __restrict__ acc, double inv_scale, double* __restrict__ vol, long long n,
+                                 const unsigned char* __restrict__ sat) {
     long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
-    if (i < n) vol[i] = (double)acc[i] * inv_scale;
+    if (i < n) vol[i] = sat[i] ? __longlong_as_double(0x7ff8000000000000LL) : (double)acc[i] * inv_scale;
 }
 // interface areas aligned with the CSR neighbour lists: entry k of cell i's list (ids ascending) receives the (d-1)-volume
 // of the facet between the cells of i and ids[k] (a generator, a halo generator or a boundary plane)
@@ -1285,7 +1286,7 @@ __device__ __forceinline__ long long csr_find(const long long* __restrict__ off,
 template <int D>
 static __global__ void k_cell_areas(const long long* __restrict__ sig, u32 nv, const double* __restrict__ xs, long long n, long long n_list,
                              const PlaneSet* __restrict__ ps, const long long* __restrict__ off, const long long* __restrict__ ids,
-                             double scale, long long* __restrict__ acc, long long* __restrict__ sat) {
+                             double scale, long long* __restrict__ acc, unsigned char* __restrict__ sat) {
     u32 v = blockIdx.x * blockDim.x + threadIdx.x;
     if (v >= nv) return;
     long long s[D + 1];
@@ -1298,7 +1299,7 @@ static __global__ void k_cell_areas(const long long* __restrict__ sig, u32 nv, c
             const long long pos = csr_find(off, ids, s[k], s[q]);
             if (pos < 0) continue;
             const double t = vertex_flag_sum<D>(xs, n, ps, s, k, q) * scale;
-            if (!(fabs(t) < 4.6e18)) atomicOr(reinterpret_cast<unsigned long long*>(sat), 1ULL);
+            if (!(fabs(t) < 4.6e18)) sat[pos] = 1;
             atomicAdd(reinterpret_cast<unsigned long long*>(acc + pos), (unsigned long long)__double2ll_rn(t));
         }
     }
@@ -1317,6 +1318,73 @@ static __global__ void k_areas_unbounded(const long long* __restrict__ ray_edge,
             if (pos >= 0) area[pos] = INFINITY;
         }
     }
+}
+// integrals of 1, x_a, x_a x_b over the cells (vertex_flag_moments, hvb_geometry.cuh): acc[cell][NM] in fixed point (one scale per
+// degree); sat[cell] = a term left the fixed-point range
+template <int D>
+static __global__ void k_cell_moments(const long long* __restrict__ sig, u32 nv, const double* __restrict__ xs, long long n, long long n_list,
+                               const PlaneSet* __restrict__ ps, double s0, double s1, double s2, long long* __restrict__ acc,
+                               unsigned char* __restrict__ sat) {
+    const int NM = 1 + D + D * (D + 1) / 2;
+    u32 v = blockIdx.x * blockDim.x + threadIdx.x;
+    if (v >= nv) return;
+    long long s[D + 1];
+#pragma unroll
+    for (int k = 0; k < D + 1; ++k) s[k] = sig[(size_t)v * (D + 1) + k];
+    for (int k = 0; k < D + 1; ++k) {
+        if (s[k] > n_list) continue;
+        double m[NM];
+        vertex_flag_moments<D>(xs, n, ps, s, k, m);
+        for (int a = 0; a < NM; ++a) {
+            const double t = m[a] * (a == 0 ? s0 : (a < 1 + D ? s1 : s2));
+            if (!(fabs(t) < 4.6e18)) sat[s[k] - 1] = 1;
+            atomicAdd(reinterpret_cast<unsigned long long*>(acc + (s[k] - 1) * NM + a), (unsigned long long)__double2ll_rn(t));
+        }
+    }
+}
+// local (y = x - x_i) -> global coordinates:  int x_a = x_i,a V + M_a,  int x_a x_b = x_i,a x_i,b V + x_i,a M_b + x_i,b M_a + M_ab
+template <int D>
+static __global__ void k_moments_finish(const long long* __restrict__ acc, const double* __restrict__ xs, long long n_list,
+                                 double i0, double i1, double i2, double* __restrict__ vol, double* __restrict__ first, double* __restrict__ second,
+                                 const unsigned char* __restrict__ sat) {
+    const int NM = 1 + D + D * (D + 1) / 2;
+    long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (i >= n_list) return;
+    if (sat[i]) {
+        const double nan = __longlong_as_double(0x7ff8000000000000LL);
+        if (vol) vol[i] = nan;
+        if (first) for (int k = 0; k < D; ++k) first[(size_t)i * D + k] = nan;
+        if (second) for (int k = 0; k < D * D; ++k) second[(size_t)i * D * D + k] = nan;
+        return;
+    }
+    const long long* a = acc + i * NM;
+    const double V = (double)a[0] * i0;
+    double x[D], m1[D];
+#pragma unroll
+    for (int k = 0; k < D; ++k) { x[k] = xs[(size_t)i * D + k]; m1[k] = (double)a[1 + k] * i1; }
+    if (vol) vol[i] = V;
+    if (first) for (int k = 0; k < D; ++k) first[(size_t)i * D + k] = x[k] * V + m1[k];
+    if (second) {
+        int q = 0;
+        for (int k = 0; k < D; ++k)
+            for (int l = k; l < D; ++l, ++q) {
+                const double val = x[k] * x[l] * V + x[k] * m1[l] + x[l] * m1[k] + (double)a[1 + D + q] * i2;
+                second[(size_t)i * D * D + k * D + l] = val;
+                second[(size_t)i * D * D + l * D + k] = val;
+            }
+    }
+}
+// cells with an unbounded edge: volume +inf, moments undefined (NaN)
+static __global__ void k_moments_unbounded(const long long* __restrict__ ray_edge, long long nentries, long long n_list, int dim,
+                                    double* __restrict__ vol, double* __restrict__ first, double* __restrict__ second) {
+    long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (i >= nentries) return;
+    const long long g = ray_edge[i];
+    if (g < 1 || g > n_list) return;
+    const double nan = __longlong_as_double(0x7ff8000000000000LL);
+    if (vol) vol[g - 1] = INFINITY;
+    if (first) for (int k = 0; k < dim; ++k) first[(size_t)(g - 1) * dim + k] = nan;
+    if (second) for (int k = 0; k < dim * dim; ++k) second[(size_t)(g - 1) * dim * dim + k] = nan;
 }
 // cells with an unbounded edge have no finite volume
 static __global__ void k_volumes_unbounded(const long long* __restrict__ ray_edge, long long nentries, long long n_list, double* __restrict__ vol) {

@@ -315,8 +315,17 @@ int hvb_clean_affected(hvb_ctx* ctx, const int64_t* sig, const double* r, int64_
  * vol: n doubles (periodic contexts: the n caller generators).  Cells with an unbounded edge get +inf.  Needs every
  * vertex of a cell among the rows: all cells after hvb_search over all cells (after the merge in multi-GPU mode), the
  * cells of Iter otherwise; HVB_ESTATE after a search with seed vertices.  Sums are accumulated in 64-bit fixed point:
- * the result does not depend on the order of the atomics. */
+ * the result does not depend on the order of the atomics.  A cell one of whose terms leaves the fixed-point range (a vertex
+ * far outside the cloud: a bounded cell at the hull of an unbounded domain, nearly parallel facets) gets NaN, not a wrong sum. */
 int hvb_cell_volumes(hvb_ctx* ctx, double* vol);
+/* Integrals of polynomials up to degree two over every cell, exactly (what VoronoiData(...).bulk_integral holds for
+ * such integrands, integrate.jl:33-53 / polyintegrator.jl; the reference's own tests integrate x -> [1, x1^2, x2^2],
+ * test/periodicgrids.jl): vol[i] = int 1, first[i*dim + a] = int x_a (centroid = first / vol), second[i*dim*dim + a*dim + b] =
+ * int x_a x_b over the cell of generator i.  Any pointer may be NULL.  Every flag of the decomposition behind hvb_cell_volumes
+ * is an orthoscheme whose vertices the recursion knows, so the moments of a simplex apply term by term (hvb_geometry.cuh,
+ * vertex_flag_moments).  Cells with an unbounded edge: vol = +inf, moments NaN; cells whose sums leave the fixed-point range: NaN.
+ * Same completeness rule and fixed-point accumulation as hvb_cell_volumes; single-GPU contexts. */
+int hvb_cell_moments(hvb_ctx* ctx, double* vol, double* first, double* second);
 /* The same for the interfaces (VoronoiData(...).area): area[k] is the (d-1)-volume of the facet between cell i and
  * ids[k] for every entry k of the CSR neighbour lists of hvb_fetch_neighbors (offsets[i-1] <= k < offsets[i]); the
  * neighbour may be a generator, a halo generator or a boundary plane.  hvb_neighbor_count entries.  Facets that hold an

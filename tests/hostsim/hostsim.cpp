@@ -140,6 +140,37 @@ static void volumes(int64_t n, const double* xs, int P, const double* base, cons
         for (int k = 0; k <= D; ++k) if (s[k] <= n) vol[s[k] - 1] += vertex_flag_sum<D>(xs, n, &ps, s, k) / fact;
     }
 }
+// integrals of 1, x_a, x_a x_b over the cells (global coordinates) from vertex rows: out[n][1 + D + D(D+1)/2]
+template <int D>
+static void moments(int64_t n, const double* xs, int P, const double* base, const double* normal, int64_t nv, const int64_t* sig, double* out) {
+    PlaneSet ps; memset(&ps, 0, sizeof(ps)); ps.P = P;
+    for (int p = 0; p < P; ++p) {
+        double nn = 0; for (int k = 0; k < D; ++k) nn += normal[p * D + k] * normal[p * D + k];
+        nn = sqrt(nn); double off = 0;
+        for (int k = 0; k < D; ++k) { ps.normal[p * 6 + k] = normal[p * D + k] / nn; off += ps.normal[p * 6 + k] * base[p * D + k]; }
+        ps.off[p] = off;
+    }
+    const int NM = 1 + D + D * (D + 1) / 2;
+    double fact = 1.0; for (int k = 2; k <= D; ++k) fact *= k;
+    std::vector<double> loc((size_t)n * NM, 0.0);
+    for (int64_t v = 0; v < nv; ++v) {
+        const int64_t* s = sig + v * (D + 1);
+        long long ss[D + 1]; for (int k = 0; k < D + 1; ++k) ss[k] = s[k];
+        for (int k = 0; k < D + 1; ++k) {
+            if (ss[k] > n) continue;
+            double m[NM];
+            vertex_flag_moments<D>(xs, n, &ps, ss, k, m);
+            for (int a = 0; a < NM; ++a) loc[(size_t)(ss[k] - 1) * NM + a] += m[a] / fact;
+        }
+    }
+    for (int64_t i = 0; i < n; ++i) {
+        const double* l = &loc[(size_t)i * NM]; const double* x = xs + i * D; double* o = out + i * NM;
+        o[0] = l[0];
+        for (int a = 0; a < D; ++a) o[1 + a] = x[a] * l[0] + l[1 + a];
+        int q = 0;
+        for (int a = 0; a < D; ++a) for (int b = a; b < D; ++b, ++q) o[1 + D + q] = x[a] * x[b] * l[0] + x[a] * l[1 + b] + x[b] * l[1 + a] + l[1 + D + q];
+    }
+}
 // interface areas aligned with the CSR neighbour lists (off[n+1], ids ascending per cell)
 template <int D>
 static void areas(int64_t n, const double* xs, int P, const double* base, const double* normal, int64_t nv, const int64_t* sig,
@@ -386,6 +417,15 @@ void hostsim_areas(int dim, int64_t n, const double* xs, int P, const double* ba
         case 4: areas<4>(n, xs, P, base, normal, nv, sig, off, ids, area); break;
         case 5: areas<5>(n, xs, P, base, normal, nv, sig, off, ids, area); break;
         case 6: areas<6>(n, xs, P, base, normal, nv, sig, off, ids, area); break;
+    }
+}
+void hostsim_moments(int dim, int64_t n, const double* xs, int P, const double* base, const double* normal, int64_t nv, const int64_t* sig, double* out) {
+    switch (dim) {
+        case 2: moments<2>(n, xs, P, base, normal, nv, sig, out); break;
+        case 3: moments<3>(n, xs, P, base, normal, nv, sig, out); break;
+        case 4: moments<4>(n, xs, P, base, normal, nv, sig, out); break;
+        case 5: moments<5>(n, xs, P, base, normal, nv, sig, out); break;
+        case 6: moments<6>(n, xs, P, base, normal, nv, sig, out); break;
     }
 }
 void hostsim_volumes(int dim, int64_t n, const double* xs, int P, const double* base, const double* normal, int64_t nv, const int64_t* sig, double* vol) {

@@ -139,3 +139,22 @@ def wrap(xs, slots=1, fp32=1):
     L.hostsim_wrap_centres(h, P(centres))
     L.hostsim_hull_free(h)
     return facets, normals, centres, dict(facets=int(c[0]), raycasts=int(c[1]), fp64=int(c[2]), rounds=int(c[3]), degenerate=int(c[4]))
+
+
+def moments(xs, sig, base=None, normal=None):
+    """integrals of 1, x_a and x_a x_b (a <= b, row by row) over every cell from vertex rows, with the product's own formula
+    (vertex_flag_moments, hvb_geometry.cuh) on the host: [n, 1 + d + d (d + 1) / 2]"""
+    L = ctypes.CDLL(build())
+    L.hostsim_moments.restype = None
+    L.hostsim_moments.argtypes = [ctypes.c_int, ctypes.c_int64, ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p,
+                                  ctypes.c_int64, ctypes.c_void_p, ctypes.c_void_p]
+    xs = np.ascontiguousarray(xs, dtype=np.float64)
+    n, d = xs.shape
+    if base is None:
+        base = np.zeros((0, d)); normal = np.zeros((0, d))
+    base = np.ascontiguousarray(base, dtype=np.float64); normal = np.ascontiguousarray(normal, dtype=np.float64)
+    sig = np.ascontiguousarray(sig, dtype=np.int64)
+    out = np.zeros((n, 1 + d + d * (d + 1) // 2))
+    P = lambda a: a.ctypes.data_as(ctypes.c_void_p)
+    L.hostsim_moments(d, n, P(xs), base.shape[0], P(base), P(normal), sig.shape[0], P(sig), P(out))
+    return out

@@ -133,3 +133,45 @@ def test_periodic_areas_close_every_cell(hvb):
         L = np.linalg.norm(w, axis=1)
         assert abs((A * L).sum() / 6 / vol[i] - 1.0) < 1e-10       # volume from the facets (d = 3: 1/d * area * |w|/2)
         assert np.linalg.norm((A[:, None] * w / L[:, None]).sum(0)) / A.sum() < 1e-10
+
+
+@pytest.mark.parametrize("d,n", [(2, 4000), (3, 3000), (4, 1000), (5, 400), (6, 120)])
+def test_moments_add_up_to_the_domain(hvb, d, n):
+    """hvb_cell_moments: the integrals of 1, x_a, x_a x_b over the cells add up to the unit cube's (1, 1/2, 1/3 on the diagonal,
+    1/4 off it); the volumes are those of hvb_cell_volumes; every centroid lies in its cell (closer to its generator than to any
+    other)"""
+    xs = points(n, d, 60 + d)
+    s = hvb.Raycast(xs, domain=hvb.cuboid(d, periodic=[]))
+    mesh, _ = hvb.voronoi(xs, searcher=s)
+    vol, first, second = mesh.moments()
+    assert np.abs(vol - mesh.volumes()).max() < 1e-14
+    assert abs(vol.sum() - 1.0) < 1e-11 and np.abs(first.sum(0) - 0.5).max() < 1e-11
+    tot = second.sum(0)
+    assert np.abs(tot - (np.full((d, d), 0.25) + np.eye(d) / 12.0)).max() < 1e-11 and np.array_equal(second, second.transpose(0, 2, 1))
+    c = mesh.centroids()
+    from scipy.spatial import cKDTree
+    assert np.array_equal(cKDTree(xs).query(c)[1], np.arange(n))
+
+
+def test_moments_against_the_host_formula_and_on_a_lattice(hvb):
+    import hostsim
+    import qhull_oracle
+    xs = points(500, 3, 71)
+    s = hvb.Raycast(xs, domain=hvb.cuboid(3, periodic=[]))
+    mesh, _ = hvb.voronoi(xs, searcher=s)
+    vol, first, second = mesh.moments()
+    base, normal = qhull_oracle.cuboid(3)
+    M = hostsim.moments(xs, np.asarray(mesh.sig), base, normal)
+    assert np.abs(M[:, 0] - vol).max() < 1e-13 and np.abs(M[:, 1:4] - first).max() < 1e-13
+    assert np.abs(M[:, 4:] - second[:, [0, 0, 0, 1, 1, 2], [0, 1, 2, 1, 2, 2]]).max() < 1e-13
+    # a lattice (non-general position, resolved): every cell is a cube around its generator
+    m = 5
+    g = (np.stack(np.meshgrid(*[np.arange(m)] * 3, indexing="ij"), -1).reshape(-1, 3) + 0.5) / m
+    s2 = hvb.Raycast(g, domain=hvb.cuboid(3, periodic=[]))
+    mesh2, _ = hvb.voronoi(g, searcher=s2)
+    assert np.abs(mesh2.centroids() - g).max() < 1e-7
+    # unbounded cells: +inf volume, undefined moments
+    s3 = hvb.Raycast(xs, domain=hvb.Boundary())
+    mesh3, _ = hvb.voronoi(xs, searcher=s3)
+    v3, f3, _ = mesh3.moments()
+    assert np.isinf(v3).any() and np.all(np.isnan(f3[np.isinf(v3), 0])) and np.isfinite(f3[np.isfinite(v3)]).all()

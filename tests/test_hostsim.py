@@ -93,3 +93,42 @@ def test_interface_area_formula_invariants(d, n):
     dv, dd, sym, face = area_invariants(xs, vol, o["nb_off"], o["nb_ids"], area, (base, normal))
     assert dv < 1e-11 and dd < 1e-11 and sym < 1e-11
     assert np.abs(face - 1.0).max() < 1e-12
+
+
+@pytest.mark.parametrize("d,n", [(2, 80), (3, 100), (4, 70), (5, 40)])
+def test_cell_moment_formula_matches_triangulated_cells(d, n):
+    """vertex_flag_moments (hvb_geometry.cuh, behind hvb_cell_moments) compiled on the host, on the oracle's rows: the integrals
+    of 1, x_a and x_a x_b over every cell against the same integrals summed over a Delaunay triangulation of the cell's vertices,
+    and their sums over the cells against the unit cube's (1, 1/2, 1/3 and 1/4)"""
+    import math
+    from scipy.spatial import Delaunay
+    import hv_oracle
+    import qhull_oracle
+    xs = points(n, d, 40 + d)
+    base, normal = qhull_oracle.cuboid(d)
+    o = hv_oracle.run(xs, base, normal)
+    M = hostsim.moments(xs, o["sig"], base, normal)
+    assert abs(M[:, 0].sum() - 1.0) < 1e-12 and np.abs(M[:, 1:1 + d].sum(0) - 0.5).max() < 1e-12
+    q = 0
+    for a in range(d):
+        for b in range(a, d):
+            assert abs(M[:, 1 + d + q].sum() - (1.0 / 3.0 if a == b else 0.25)) < 1e-12
+            q += 1
+    cellv = {}
+    for row, r in zip(o["sig"], o["r"]):
+        for g in row:
+            if g <= n:
+                cellv.setdefault(int(g), []).append(r)
+    for i in range(1, min(n, 30) + 1):
+        V = np.array(cellv[i])
+        m0, m1, m2 = 0.0, np.zeros(d), np.zeros((d, d))
+        for simp in Delaunay(V).simplices:
+            P = V[simp]
+            vol = abs(np.linalg.det(P[1:] - P[0])) / math.factorial(d)
+            S = P.sum(0)
+            m0 += vol; m1 += vol * S / (d + 1); m2 += vol * (np.outer(S, S) + P.T @ P) / ((d + 1) * (d + 2))
+        got2 = np.zeros((d, d)); q = 0
+        for a in range(d):
+            for b in range(a, d):
+                got2[a, b] = got2[b, a] = M[i - 1, 1 + d + q]; q += 1
+        assert abs(m0 - M[i - 1, 0]) < 1e-12 and np.abs(m1 - M[i - 1, 1:1 + d]).max() < 1e-12 and np.abs(m2 - got2).max() < 1e-12
