@@ -409,6 +409,35 @@ def parity_n(env, name, settings):
                                                   "allgather_ms": ms_gather, "allgather_bytes_received_per_rank": xbytes}}
 
 
+def products():
+    """Other products of the same backend, timed once each on a warm context (not part of `value`): the convex hull of the C4
+    cloud by gift wrapping (hvb_convex_hull; compare workloads.C4.ms_per_step = the complete search the hull used to cost) and a
+    40^3 lattice, a cloud in non-general position (resolved by perturbation + merge)."""
+    import hvb200
+    out = {}
+    try:
+        xs = cloud(50000, 5, 0)
+        s = hvb200.Raycast(xs, domain=hvb200.Boundary())
+        for _ in range(3):
+            t0 = time.perf_counter(); cv = hvb200.ConvexHull(xs, searcher=s); wall = time.perf_counter() - t0
+        st = cv.stats
+        out["convex_hull_C4"] = {"facets": len(cv), "queries": st["raycasts"], "rounds": st["rounds"], "ms_device": st["ms_search"] + st["ms_finalize"],
+                                 "ms_wall": wall * 1e3, "pairs_fp32": st["candidates_fp32"], "fp64_evaluations": st["candidates_fp64"]}
+        s.close()
+        m = 40
+        g = (np.stack(np.meshgrid(*[np.arange(m)] * 3, indexing="ij"), -1).reshape(-1, 3) + 0.5) / m
+        s = hvb200.Raycast(g, domain=hvb200.cuboid(3, periodic=[]))
+        for _ in range(2):
+            t0 = time.perf_counter(); mesh, _s = hvb200.voronoi(g, searcher=s); wall = time.perf_counter() - t0
+        st = s.stats()
+        out["lattice_40^3"] = {"vertices": mesh.number_of_vertices(), "with_8_generators": int((np.diff(mesh.sig_off) == 8).sum()), "max_siglen": mesh.max_siglen,
+                               "ms_wall": wall * 1e3, "ms_search": st["ms_search"], "ms_finalize": st["ms_finalize"]}
+        s.close()
+    except Exception as e:                                   # a product must not take the bench line down
+        out["error"] = repr(e)
+    return out
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -418,6 +447,7 @@ def main():
     ap.add_argument("--workload", default="C2", choices=sorted(WORKLOADS))
     ap.add_argument("--extra", default="C4,C3", help="workloads reported under `workloads` in the same line ('' = none)")
     ap.add_argument("--extra-steps", type=int, default=3)
+    ap.add_argument("--no-products", action="store_true", help="skip the `products` timings (convex hull, lattice)")
     ap.add_argument("--ref-points", type=float, default=100000)
     ap.add_argument("--cpu-points", type=int, default=100000)
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -488,6 +518,8 @@ def main():
     if extras:
         line["workloads"] = {k: {kk: v[kk] for kk in ("value", "unit", "steps", "warmup", "ms_per_step", "scaling", "config", "e2e", "roofline", "vertices_per_step",
                                                       "stats_last_step")} for k, v in extras.items()}
+    if world == 1 and not args.no_products:
+        line["products"] = products()
     if not args.no_cpu_baseline and world == 1:
         sys.path.insert(0, os.path.join(ROOT, "oracle"))
         import hv_oracle
