@@ -21,6 +21,7 @@
 
 #include "../../include/hvb200.h"
 #include "hvb_host.hpp"
+#include "hvb_nongeneral.hpp"
 #include "hvb_ctx_base.hpp"
 #include "hvb_kernels.cuh"
 #include "hvb_nccl.hpp"
@@ -96,17 +97,6 @@ struct HBuf {   // page-locked host memory
     }
     void release() { if (p) cudaFreeHost(p); p = nullptr; cap = 0; }
 };
-
-// non-general position resolved by perturbation (Ctx::resolve_degenerate)
-#ifndef HVB_PERTURB_REL
-#define HVB_PERTURB_REL 1e-9      // offset of a generator / extent of the cloud
-#endif
-#ifndef HVB_MERGE_REL
-#define HVB_MERGE_REL 1e-8        // rows closer than this (times the extent, per coordinate) are one vertex
-#endif
-#ifndef HVB_FLAT_TOL
-#define HVB_FLAT_TOL 1e-7         // |det| of the unit edge vectors of a simplex below which its generators count as coplanar
-#endif
 
 struct Round { u32 qcount; u32 cursor; };   // frontier length and the work cursor of the round that consumes it
 struct Scalars {            // small device-side words, mirrored into pinned host memory after every round
@@ -764,7 +754,7 @@ struct Ctx : hvb_ctx {
         if (!have_result) { err = "no search result"; return HVB_ESTATE; }
         if (!flags) { err = "null output"; return HVB_EINVAL; }
         CK(cudaSetDevice(prm.device));
-        if (!periodic || !have_flags) { memset(flags, 1, (size_t)nvert); return HVB_OK; }   // without a halo every row is its own representative
+        if (!periodic || !have_flags) { memset(flags, 1, (size_t)(merged ? m_nvert : nvert)); return HVB_OK; }   // without a halo every row is its own representative
         if (nvert > 0) CK(cudaMemcpyAsync(flags, vflags.p, (size_t)nvert, cudaMemcpyDeviceToHost, stream));
         CK(cudaStreamSynchronize(stream));
         return HVB_OK;
@@ -818,7 +808,7 @@ struct Ctx : hvb_ctx {
             CK(xcan.ensure((size_t)n * D));
             k_gather_canon<D><<<blocks_for(n, 256), 256, 0, stream>>>(xs_orig.p, perm.p, (int)n, xcan.p); ++launches;
             dv.xcan = xcan.p;
-            dv.t_min = -1e-13 * dv.ext;
+            dv.t_min = HVB_TMIN_REL * dv.ext;
             perturbed = true;
             st.ms_build = build0; st.ms_upload = upload0;
         }
@@ -830,111 +820,26 @@ struct Ctx : hvb_ctx {
         return merge_result();
     }
 
-    // step 4: rows with equal coordinates -> one vertex with the union of the signatures
+    // step 4: rows with equal coordinates -> one vertex with the union of the signatures (hvb_nongeneral.hpp)
     int merge_result() {
         const int64_t* sig; const double* r; int64_t nrow;
         int rc = view_vertices(&sig, &r, &nrow); if (rc) return rc;
-        const double eps = HVB_MERGE_REL * dv.ext;
-        std::vector<int> parent((size_t)nrow);
-        for (int64_t i = 0; i < nrow; ++i) parent[i] = (int)i;
-        auto find = [&](int x) { while (parent[x] != x) { parent[x] = parent[parent[x]]; x = parent[x]; } return x; };
-        auto unite = [&](int a, int b) { a = find(a); b = find(b); if (a != b) { if (a < b) parent[b] = a; else parent[a] = b; } };
-        // two grids of cell size eps, shifted by half a cell: members of a cluster agree to ~1e-13 of the extent, so they share
-        // a cell of at least one grid unless they straddle a boundary of both (probability ~ (d 1e-13 / eps)^2)
-        for (int pass = 0; pass < 2; ++pass) {
-            std::unordered_map<u64, int> first;
-            first.reserve((size_t)nrow * 2);
-            for (int64_t i = 0; i < nrow; ++i) {
-                u64 h = 0x9ae16a3b2f90404fULL + (u64)pass;
-                for (int k = 0; k < D; ++k) {
-                    const long long c = (long long)floor(r[i * D + k] / eps + 0.5 * pass);
-                    h = mix64(h ^ ((u64)c + 0x9e3779b97f4a7c15ULL * (u64)(k + 1)));
-                }
-                auto it = first.find(h);
-                if (it == first.end()) { first.emplace(h, (int)i); continue; }
-                const int j = it->second;
-                double dmax = 0;
-                for (int k = 0; k < D; ++k) dmax = std::max(dmax, fabs(r[i * D + k] - r[(size_t)j * D + k]));
-                if (dmax <= eps) unite((int)i, j);
-            }
-        }
-        // clusters in the order of their first row (rows are sorted by signature: the first row is the smallest one)
-        std::vector<int> cluster_of((size_t)nrow, -1), head;
-        for (int64_t i = 0; i < nrow; ++i) { const int rt = find((int)i); if (cluster_of[rt] < 0) { cluster_of[rt] = (int)head.size(); head.push_back(rt); } cluster_of[i] = cluster_of[rt]; }
-        const size_t nc = head.size();
-        std::vector<std::vector<int64_t> > sets(nc);
-        for (int64_t i = 0; i < nrow; ++i) { auto& v = sets[cluster_of[i]]; v.insert(v.end(), sig + i * (D + 1), sig + (i + 1) * (D + 1)); }
-        m_maxlen = D + 1; m_degenerate = 0;
-        for (auto& v : sets) { std::sort(v.begin(), v.end()); v.erase(std::unique(v.begin(), v.end()), v.end()); m_maxlen = std::max<int64_t>(m_maxlen, (int64_t)v.size()); if ((int64_t)v.size() > D + 1) ++m_degenerate; }
-        std::vector<int> order(nc);
-        for (size_t c = 0; c < nc; ++c) order[c] = (int)c;
-        if (prm.sort_output) std::sort(order.begin(), order.end(), [&](int a, int b) { return sets[a] < sets[b]; });
-        m_off.assign(nc + 1, 0); m_ids.clear(); m_r.resize(nc * D);
-        for (size_t o = 0; o < nc; ++o) {
-            const int c = order[o];
-            m_ids.insert(m_ids.end(), sets[c].begin(), sets[c].end());
-            m_off[o + 1] = (int64_t)m_ids.size();
-            for (int k = 0; k < D; ++k) m_r[o * D + k] = r[(size_t)head[c] * D + k];
-        }
-        m_nvert = (int64_t)nc;
+        merge_rows(D, nrow, sig, r, HVB_MERGE_REL * dv.ext, prm.sort_output != 0, m_off, m_ids, m_r, m_maxlen, m_degenerate);
+        m_nvert = (int64_t)m_off.size() - 1;
         merged = true; m_nb_built = false;
         st.vertices = m_nvert; st.unique_vertices = m_nvert; st.degenerate = m_degenerate;
         return HVB_OK;
     }
 
-    // neighbour lists of a merged mesh: i and j are neighbours if they share a FULL interface (neighbors.jl:205-212; the
-    // reference's NeighborFinder removes cells that only share a lower-dimensional face of a non-general vertex): the
-    // vertices (and unbounded edges) both belong to span an affine space of dimension d - 1
+    // neighbour lists of a merged mesh: cells that share a FULL interface (merged_neighbors, hvb_nongeneral.hpp)
     int build_merged_neighbors() {
         if (m_nb_built) return HVB_OK;
-        struct Item { int64_t i, j; int64_t v; };            // v >= 0: merged vertex; v < 0: unbounded edge -v - 1
-        std::vector<Item> items;
-        for (int64_t v = 0; v < m_nvert; ++v)
-            for (int64_t a = m_off[v]; a < m_off[v + 1]; ++a)
-                for (int64_t b = a + 1; b < m_off[v + 1]; ++b) items.push_back({m_ids[a], m_ids[b], v});
         std::vector<int64_t> redge; std::vector<double> rdir;
         if (nrays > 0) {
             redge.resize((size_t)nrays * D); rdir.resize((size_t)nrays * D);
             int rc = fetch_rays(redge.data(), nullptr, rdir.data(), nullptr); if (rc) return rc;
-            for (int64_t q = 0; q < nrays; ++q)
-                for (int a = 0; a < D; ++a)
-                    for (int b = a + 1; b < D; ++b) items.push_back({redge[q * D + a], redge[q * D + b], -q - 1});
         }
-        std::sort(items.begin(), items.end(), [](const Item& x, const Item& y) { return x.i != y.i ? x.i < y.i : (x.j != y.j ? x.j < y.j : x.v < y.v); });
-        std::vector<std::pair<int64_t, int64_t> > adj;      // (cell, neighbour)
-        const double tol = 1e-6;
-        for (size_t a = 0; a < items.size();) {
-            size_t b = a;
-            while (b < items.size() && items[b].i == items[a].i && items[b].j == items[a].j) ++b;
-            // rank of the span: Gram-Schmidt over the differences to the first vertex and the directions of the unbounded edges
-            double basis[HVB_MAX_DIM][HVB_MAX_DIM];
-            int rank = 0;
-            const double* p0 = nullptr;
-            double scale = 0;
-            for (size_t t = a; t < b && !p0; ++t) if (items[t].v >= 0) p0 = &m_r[(size_t)items[t].v * D];
-            for (size_t t = a; t < b; ++t) if (items[t].v >= 0 && p0) { double s2 = 0; for (int k = 0; k < D; ++k) { const double dd = m_r[(size_t)items[t].v * D + k] - p0[k]; s2 += dd * dd; } scale = std::max(scale, sqrt(s2)); }
-            for (size_t t = a; t < b && rank < D - 1; ++t) {
-                double w[HVB_MAX_DIM];
-                double ref;
-                if (items[t].v >= 0) { if (!p0) continue; for (int k = 0; k < D; ++k) w[k] = m_r[(size_t)items[t].v * D + k] - p0[k]; ref = scale; }
-                else { for (int k = 0; k < D; ++k) w[k] = rdir[(size_t)(-items[t].v - 1) * D + k]; ref = 1.0; }
-                for (int rep = 0; rep < 2; ++rep)
-                    for (int q = 0; q < rank; ++q) { double sdot = 0; for (int k = 0; k < D; ++k) sdot += w[k] * basis[q][k]; for (int k = 0; k < D; ++k) w[k] -= sdot * basis[q][k]; }
-                double nw = 0; for (int k = 0; k < D; ++k) nw += w[k] * w[k];
-                nw = sqrt(nw);
-                if (ref > 0 && nw > tol * ref) { for (int k = 0; k < D; ++k) basis[rank][k] = w[k] / nw; ++rank; }
-            }
-            if (rank >= D - 1) {
-                const int64_t i = items[a].i, j = items[a].j;
-                if (i <= n) adj.emplace_back(i, j);
-                if (j <= n) adj.emplace_back(j, i);
-            }
-            a = b;
-        }
-        std::sort(adj.begin(), adj.end());
-        m_nb_off.assign((size_t)n + 1, 0); m_nb_ids.clear(); m_nb_ids.reserve(adj.size());
-        for (auto& pr : adj) { m_nb_off[pr.first]++; m_nb_ids.push_back(pr.second); }
-        for (int64_t i = 0; i < n; ++i) m_nb_off[i + 1] += m_nb_off[i];
+        merged_neighbors(D, n, m_nvert, m_off.data(), m_ids.data(), m_r.data(), nrays, redge.data(), rdir.data(), m_nb_off, m_nb_ids);
         m_nb_built = true;
         return HVB_OK;
     }
@@ -1709,6 +1614,7 @@ struct Ctx : hvb_ctx {
     // rows [first, first + count) straight from the device (no staging of the whole result): the shard of a rank
     int fetch_vertices_range(int64_t first, int64_t count, int64_t* sig, double* r) override {
         if (!have_result) { err = "no search result"; return HVB_ESTATE; }
+        { int rcm = merged_fixed("hvb_fetch_vertices_range"); if (rcm) return rcm; }
         if (first < 0 || count < 0 || first + count > nvert) { err = "row range out of bounds"; return HVB_EINVAL; }
         CK(cudaSetDevice(prm.device));
         if (count > 0) {

@@ -7,6 +7,7 @@
 #include "hvb_geometry.cuh"
 #include "hvb_hull.cuh"
 #include "hvb_wrap.cuh"
+#include "hvb_nongeneral.hpp"
 
 namespace hvb {
 
@@ -171,9 +172,7 @@ static __global__ void k_cell_sort(const int* __restrict__ cell_start, int ncell
 static __global__ void k_perturb(const double* __restrict__ src, double* __restrict__ dst, size_t count, int dim, double amp) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= count) return;
-    u64 h = mix64((u64)i * 0x9e3779b97f4a7c15ULL + 0x243f6a8885a308d3ULL);
-    const double u = ((double)(h >> 11) + 0.5) * (1.0 / 9007199254740992.0) * 2.0 - 1.0;
-    dst[i] = src[i] + amp * u;
+    dst[i] = src[i] + amp * perturb_unit((u64)i);
 }
 // caller coordinates in grid order (the coordinates canonical_vertex solves from when the search ran on perturbed ones)
 template <int D>

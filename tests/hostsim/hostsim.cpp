@@ -15,6 +15,7 @@ static bool g_want_trace = false;
 #include "../../highvoronoi.jl_b200/csrc/hvb_geometry.cuh"
 #include "../../highvoronoi.jl_b200/csrc/hvb_hull.cuh"
 #include "../../highvoronoi.jl_b200/csrc/hvb_wrap.cuh"
+#include "../../highvoronoi.jl_b200/csrc/hvb_nongeneral.hpp"
 
 using namespace hvb;
 
@@ -29,7 +30,10 @@ struct SimResult {
 
 template <int D>
 static SimResult* run(int64_t n, const double* xs, int P, const double* base, const double* normal,
-                      int ppc, double probe_scale, int fp32, int seed_stride) {
+                      int ppc, double probe_scale, int fp32, int seed_stride,
+                      const double* xs_canon = nullptr, double t_min = 1e-12, double flat_tol = 0.0) {
+    // xs_canon / t_min / flat_tol: the search of a PERTURBED cloud (resolve_degenerate): coordinates are solved from the
+    // caller's generators xs_canon, the smallest ray parameter is t_min, simplices flat in xs_canon are dropped
     Dev<D> dv;
     memset(&dv, 0, sizeof(dv));
     dv.n = (int)n;
@@ -53,8 +57,10 @@ static SimResult* run(int64_t n, const double* xs, int P, const double* base, co
         ps.off[p] = off;
     }
     std::vector<unsigned char> active(n, 1), hasv(n, 0);
-    dv.cell_start = cstart.data(); dv.x32 = x32.data(); dv.x64 = x64.data(); dv.xcan = x64.data(); dv.planes = &ps; dv.active = active.data();
-    dv.plane_tol = 1e-12; dv.t_min = 1e-12; dv.probe_scale = probe_scale > 1.0 ? probe_scale : 1.3; dv.probe_growth = 2.0; dv.fp32_filter = fp32;
+    std::vector<double> xcan;
+    if (xs_canon) { xcan.resize(n * D); for (int64_t i = 0; i < n; ++i) for (int k = 0; k < D; ++k) xcan[i * D + k] = xs_canon[(int64_t)perm[i] * D + k]; }
+    dv.cell_start = cstart.data(); dv.x32 = x32.data(); dv.x64 = x64.data(); dv.xcan = xs_canon ? xcan.data() : x64.data(); dv.planes = &ps; dv.active = active.data();
+    dv.plane_tol = 1e-12; dv.t_min = t_min; dv.probe_scale = probe_scale > 1.0 ? probe_scale : 1.3; dv.probe_growth = 2.0; dv.fp32_filter = fp32;
     int64_t vcap = estimate_vertices(D, n, P) * 2;
     std::vector<int> vsig(vcap * (D + 1)); std::vector<double> vr(vcap * D);
     u32 vcount = 0;
@@ -105,7 +111,9 @@ static SimResult* run(int64_t n, const double* xs, int P, const double* base, co
         std::sort(o, o + D + 1);
         int cs[D + 1]; Row row;
         for (int k = 0; k <= D; ++k) { cs[k] = o[k].second; row.sig[k] = o[k].first + 1; }
-        canonical_vertex<D>(dv, cs, row.r);
+        double flat = 1.0;
+        canonical_vertex<D>(dv, cs, row.r, &flat);
+        if (flat_tol > 0 && !(flat > flat_tol)) continue;            // a sliver of the perturbed triangulation (k_final_rows)
         rows.push_back(row);
     }
     std::sort(rows.begin(), rows.end(), [](const Row& a, const Row& b) { return std::lexicographical_compare(a.sig, a.sig + D + 1, b.sig, b.sig + D + 1); });
@@ -119,6 +127,24 @@ static SimResult* run(int64_t n, const double* xs, int P, const double* base, co
         std::sort(e.begin(), e.end());
         R->ray_edge.insert(R->ray_edge.end(), e.begin(), e.end());
     }
+    return R;
+}
+
+// Non-general position resolved as Ctx::resolve_degenerate does it (hvb_ctx.cuh): perturb, search, coordinates from the caller's
+// generators, slivers dropped, rows merged, neighbour lists by full interfaces -- with the library's own host functions
+struct ResolveResult { std::vector<int64_t> off, ids, nb_off, nb_ids; std::vector<double> r; int64_t maxlen, ndeg, nsimplicial; };
+template <int D>
+static ResolveResult* run_resolve(int64_t n, const double* xs, int P, const double* base, const double* normal) {
+    double ext = 0;
+    for (int k = 0; k < D; ++k) { double lo = 1e300, hi = -1e300; for (int64_t i = 0; i < n; ++i) { lo = std::min(lo, xs[i * D + k]); hi = std::max(hi, xs[i * D + k]); } ext = std::max(ext, hi - lo); }
+    std::vector<double> xp(n * D);
+    for (int64_t i = 0; i < n * D; ++i) xp[i] = xs[i] + HVB_PERTURB_REL * ext * perturb_unit((u64)i);
+    SimResult* S = run<D>(n, xp.data(), P, base, normal, 0, 0.0, 1, 0, xs, HVB_TMIN_REL * ext, HVB_FLAT_TOL);
+    ResolveResult* R = new ResolveResult();
+    R->nsimplicial = S->nv;
+    merge_rows(D, S->nv, S->sig.data(), S->r.data(), HVB_MERGE_REL * ext, true, R->off, R->ids, R->r, R->maxlen, R->ndeg);
+    merged_neighbors(D, n, (int64_t)R->off.size() - 1, R->off.data(), R->ids.data(), R->r.data(), 0, nullptr, nullptr, R->nb_off, R->nb_ids);
+    delete S;
     return R;
 }
 
@@ -419,6 +445,26 @@ void hostsim_areas(int dim, int64_t n, const double* xs, int P, const double* ba
         case 6: areas<6>(n, xs, P, base, normal, nv, sig, off, ids, area); break;
     }
 }
+void* hostsim_resolve(int dim, int64_t n, const double* xs, int P, const double* base, const double* normal) {
+    switch (dim) {
+        case 2: return run_resolve<2>(n, xs, P, base, normal);
+        case 3: return run_resolve<3>(n, xs, P, base, normal);
+        case 4: return run_resolve<4>(n, xs, P, base, normal);
+        case 5: return run_resolve<5>(n, xs, P, base, normal);
+        case 6: return run_resolve<6>(n, xs, P, base, normal);
+    }
+    return 0;
+}
+void hostsim_resolve_counts(void* h, int64_t* out /*5*/) {
+    ResolveResult* R = (ResolveResult*)h;
+    out[0] = (int64_t)R->off.size() - 1; out[1] = (int64_t)R->ids.size(); out[2] = (int64_t)R->nb_ids.size(); out[3] = R->maxlen; out[4] = R->nsimplicial;
+}
+void hostsim_resolve_fetch(void* h, int64_t* off, int64_t* ids, double* r, int64_t* nb_off, int64_t* nb_ids) {
+    ResolveResult* R = (ResolveResult*)h;
+    memcpy(off, R->off.data(), R->off.size() * 8); memcpy(ids, R->ids.data(), R->ids.size() * 8); memcpy(r, R->r.data(), R->r.size() * 8);
+    memcpy(nb_off, R->nb_off.data(), R->nb_off.size() * 8); if (!R->nb_ids.empty()) memcpy(nb_ids, R->nb_ids.data(), R->nb_ids.size() * 8);
+}
+void hostsim_resolve_free(void* h) { delete (ResolveResult*)h; }
 void hostsim_moments(int dim, int64_t n, const double* xs, int P, const double* base, const double* normal, int64_t nv, const int64_t* sig, double* out) {
     switch (dim) {
         case 2: moments<2>(n, xs, P, base, normal, nv, sig, out); break;

@@ -14,7 +14,8 @@ def build():
     geom = os.path.join(_HERE, "..", "..", "highvoronoi.jl_b200", "csrc", "hvb_geometry.cuh")
     hull = os.path.join(_HERE, "..", "..", "highvoronoi.jl_b200", "csrc", "hvb_hull.cuh")
     wrap = os.path.join(_HERE, "..", "..", "highvoronoi.jl_b200", "csrc", "hvb_wrap.cuh")
-    newest = max(os.path.getmtime(f) for f in (src, core, host, geom, hull, wrap))
+    nong = os.path.join(_HERE, "..", "..", "highvoronoi.jl_b200", "csrc", "hvb_nongeneral.hpp")
+    newest = max(os.path.getmtime(f) for f in (src, core, host, geom, hull, wrap, nong))
     if not os.path.exists(_SO) or os.path.getmtime(_SO) < newest:
         subprocess.check_call(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-Wno-unknown-pragmas", "-o", _SO, src])
     return _SO
@@ -158,3 +159,31 @@ def moments(xs, sig, base=None, normal=None):
     P = lambda a: a.ctypes.data_as(ctypes.c_void_p)
     L.hostsim_moments(d, n, P(xs), base.shape[0], P(base), P(normal), sig.shape[0], P(sig), P(out))
     return out
+
+
+def resolve(xs, base=None, normal=None):
+    """a cloud in non-general position resolved as the library does it (perturbation + merge, csrc/hvb_ctx.cuh resolve_degenerate):
+    the search on the host build, the merge and the neighbour lists with the library's own host functions (hvb_nongeneral.hpp).
+    -> dict(off, ids, r, nb_off, nb_ids, max_siglen, simplicial)"""
+    L = ctypes.CDLL(build())
+    L.hostsim_resolve.restype = ctypes.c_void_p
+    L.hostsim_resolve.argtypes = [ctypes.c_int, ctypes.c_int64, ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p]
+    for f in ("hostsim_resolve_counts", "hostsim_resolve_fetch", "hostsim_resolve_free"):
+        getattr(L, f).restype = None
+    L.hostsim_resolve_counts.argtypes = [ctypes.c_void_p, ctypes.c_void_p]
+    L.hostsim_resolve_fetch.argtypes = [ctypes.c_void_p] * 6
+    L.hostsim_resolve_free.argtypes = [ctypes.c_void_p]
+    xs = np.ascontiguousarray(xs, dtype=np.float64)
+    n, d = xs.shape
+    if base is None:
+        base = np.zeros((0, d)); normal = np.zeros((0, d))
+    base = np.ascontiguousarray(base, dtype=np.float64); normal = np.ascontiguousarray(normal, dtype=np.float64)
+    P = lambda a: a.ctypes.data_as(ctypes.c_void_p)
+    h = L.hostsim_resolve(d, n, P(xs), base.shape[0], P(base), P(normal))
+    c = np.zeros(5, dtype=np.int64)
+    L.hostsim_resolve_counts(h, P(c))
+    off = np.empty(c[0] + 1, dtype=np.int64); ids = np.empty(c[1], dtype=np.int64); r = np.empty((c[0], d))
+    nb_off = np.empty(n + 1, dtype=np.int64); nb_ids = np.empty(c[2], dtype=np.int64)
+    L.hostsim_resolve_fetch(h, P(off), P(ids), P(r), P(nb_off), P(nb_ids))
+    L.hostsim_resolve_free(h)
+    return dict(off=off, ids=ids, r=r, nb_off=nb_off, nb_ids=nb_ids, max_siglen=int(c[3]), simplicial=int(c[4]))
