@@ -60,3 +60,19 @@ def test_gift_wrapping_filter_is_sound():
 def test_gift_wrapping_reports_coplanar_generators():
     g = np.stack(np.meshgrid(*[np.arange(4.0)] * 3, indexing="ij"), -1).reshape(-1, 3)          # cube grid: square facets
     assert hostsim.wrap(g)[3]["degenerate"] > 0
+
+
+@pytest.mark.parametrize("d", [2, 3, 4, 5, 6])
+def test_gift_wrapping_of_tiny_clouds_and_spheres(d):
+    """edge cases: a simplex (d + 1 generators: every seed step and no wrap), d + 2 generators, and a cloud whose generators are
+    all hull vertices (a sphere)"""
+    from scipy.spatial import ConvexHull as QHull
+    rng = np.random.default_rng(100 + d)
+    clouds = [rng.random((d + 1, d)), rng.random((d + 2, d))]
+    if d <= 4:
+        u = rng.normal(size=(200, d))
+        clouds.append(u / np.linalg.norm(u, axis=1)[:, None])
+    for xs in clouds:
+        F, N, C, st = hostsim.wrap(xs, slots=2)
+        want = {tuple(sorted(int(v) + 1 for v in f)) for f in QHull(xs).simplices}
+        assert {tuple(f) for f in F.tolist()} == want and st["degenerate"] == 0
