@@ -157,3 +157,33 @@ def test_volumes_of_a_grid(hvb, d, m):
     vol = mesh.volumes()
     assert abs(vol.sum() - 1.0) < 1e-7
     assert np.abs(vol * m ** d - 1.0).max() < 1e-6
+
+
+@pytest.mark.parametrize("d,m", [(2, 6), (3, 4)])
+def test_periodic_lattice_through_the_host_side_halo(hvb, d, m):
+    """test/periodicgrids.jl style input the way the reference itself periodises (Create_Discrete_Domain, domain.jl:175-213: halo
+    generators on the host, then voronoi() on generators + halo with a plain Boundary -- the seam the Julia shim replaces): a lattice
+    on the unit torus, its periodic copies within a margin, mirror planes pushed out by that margin.  Every vertex in [0, 1)^d is a
+    corner of the lattice of cubes with 2^d generators, one per class of the torus: m^d of them."""
+    import itertools
+    g = grid(m, d)
+    margin = 1.5 / m
+    pts = [g]
+    for shift in itertools.product((-1, 0, 1), repeat=d):
+        if any(shift):
+            c = g + np.array(shift, dtype=float)
+            pts.append(c[np.all((c > -margin) & (c < 1 + margin), axis=1)])
+    xs = np.vstack(pts)
+    dom = hvb.cuboid(d, dimensions=np.full(d, 1 + 2 * margin), periodic=[], offset=np.full(d, -margin))
+    s = hvb.Raycast(xs, domain=dom)
+    mesh, _ = hvb.voronoi(xs, searcher=s)
+    inside = np.all((mesh.r > -1e-9) & (mesh.r < 1 - 1e-9), axis=1)
+    lens = np.diff(mesh.sig_off)
+    assert int(inside.sum()) == m ** d and np.all(lens[inside] == 2 ** d)
+    assert np.abs(mesh.r[inside] * m - np.round(mesh.r[inside] * m)).max() < 1e-9
+    # folded to the torus every such vertex names 2^d DIFFERENT caller generators (m >= 3)
+    origin = np.concatenate([np.arange(len(g))] + [np.flatnonzero(np.all((g + np.array(sh, dtype=float) > -margin) & (g + np.array(sh, dtype=float) < 1 + margin), axis=1))
+                                                   for sh in itertools.product((-1, 0, 1), repeat=d) if any(sh)])
+    for v in np.flatnonzero(inside):
+        ids = mesh.sig_ids[mesh.sig_off[v]:mesh.sig_off[v + 1]]
+        assert ids.max() <= len(xs) and len(set(origin[ids - 1].tolist())) == 2 ** d

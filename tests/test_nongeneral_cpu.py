@@ -66,3 +66,27 @@ def test_perturbation_is_a_function_of_the_index_alone():
     base, normal = qhull_oracle.cuboid(3)
     a, b = hostsim.resolve(xs, base, normal), hostsim.resolve(xs, base, normal)
     assert np.array_equal(a["ids"], b["ids"]) and np.array_equal(a["r"], b["r"]) and np.array_equal(a["nb_ids"], b["nb_ids"])
+
+
+@pytest.mark.parametrize("d,m", [(2, 6), (3, 4)])
+def test_periodic_lattice_through_the_host_side_halo_on_the_host(d, m):
+    """a lattice on the unit torus the way the reference periodises (halo generators made by the caller, mirror planes pushed out
+    by the margin; domain.jl:175-213): in [0, 1)^d one vertex per class of the torus, m^d of them, each with 2^d generators"""
+    import itertools
+    g = grid(m, d)
+    margin = 1.5 / m
+    pts = [g]
+    for shift in itertools.product((-1, 0, 1), repeat=d):
+        if any(shift):
+            c = g + np.array(shift, dtype=float)
+            pts.append(c[np.all((c > -margin) & (c < 1 + margin), axis=1)])
+    xs = np.vstack(pts)
+    base = np.zeros((2 * d, d)); normal = np.zeros((2 * d, d))
+    for i in range(d):
+        base[2 * i] = -margin; base[2 * i, i] += 1 + 2 * margin; normal[2 * i, i] = 1.0
+        base[2 * i + 1] = -margin; normal[2 * i + 1, i] = -1.0
+    o = hostsim.resolve(xs, base, normal)
+    inside = np.all((o["r"] > -1e-9) & (o["r"] < 1 - 1e-9), axis=1)
+    lens = np.diff(o["off"])
+    assert int(inside.sum()) == m ** d and np.all(lens[inside] == 2 ** d)
+    assert np.abs(o["r"][inside] * m - np.round(o["r"][inside] * m)).max() < 1e-9
