@@ -9,3 +9,6 @@ python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/smoke.log 2>&1
 echo "smoke rc=$?" >> gpurun_out/smoke.log
 grep -E "passed|failed" gpurun_out/pytest_gpu.log | tail -3
 tail -2 gpurun_out/smoke.log
+( timeout 150 compute-sanitizer --tool memcheck --error-exitcode 7 python tools/sanitize_check.py r2 ) > gpurun_out/sanitize.log 2>&1
+echo "sanitize rc=$?" >> gpurun_out/sanitize.log
+tail -4 gpurun_out/sanitize.log
