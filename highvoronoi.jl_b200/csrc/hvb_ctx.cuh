@@ -786,8 +786,10 @@ struct Ctx : hvb_ctx {
     int resolve_degenerate(const int64_t* cells, int64_t ncells_in, int64_t nseed) {
         // unbounded domains: the hull of such a cloud (the faces of a lattice) has coplanar generators whose perturbed
         // simplices have balls of arbitrary size; telling a generator ON such a ball from one inside it is beyond FP64
-        if (periodic || std::max(1, prm.world) > 1 || nseed > 0 || P == 0) {
-            err = "non-general position: a vertex with more than dim+1 cospherical generators was met (resolving it is available on bounded, non-periodic domains, one GPU, unseeded searches)";
+        // Iter subsets: the simplices of a cospherical set that touch none of the explored cells are not found, their
+        // generators would be missing from the merged signature
+        if (periodic || std::max(1, prm.world) > 1 || nseed > 0 || P == 0 || cells != nullptr) {
+            err = "non-general position: a vertex with more than dim+1 cospherical generators was met (resolving it is available on bounded, non-periodic domains, one GPU, searches over all cells without seed vertices)";
             return HVB_EDEGENERATE;
         }
         CK(cudaSetDevice(prm.device));

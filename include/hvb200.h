@@ -72,7 +72,7 @@ typedef struct hvb_params {
                                     caller's generators, slivers are dropped and rows with equal coordinates merged into one
                                     vertex with the union of the signatures: the reference's result, variable-length rows
                                     (hvb_counts max_siglen > dim+1, hvb_fetch_vertices_var).  Bounded non-periodic domains,
-                                    one GPU, unseeded searches; elsewhere as 0;
+                                    one GPU, searches over all cells without seed vertices; elsewhere as 0;
                                  0: return HVB_EDEGENERATE;
                                  1: count and continue with one arbitrary winner (unsafe: the mesh may be wrong) */
     int32_t points_per_cell;  /* target occupancy of a uniform-grid cell; 0 = auto */

@@ -126,6 +126,10 @@ def test_reporting_is_still_available_and_fixed_width_calls_refuse(hvb):
     # a second search on the same context goes straight to the resolved form; new points reset it
     mesh2, _ = hvb.voronoi(xs, searcher=s)
     assert [tuple(a) for a in mesh2.sigs()] == [tuple(a) for a in mesh.sigs()]
+    # an Iter subset would lose generators of a cospherical set: reported, not resolved
+    with pytest.raises(hvb.HVBError) as e:
+        hvb.voronoi(xs, searcher=s, Iter=range(1, 11))
+    assert e.value.code == hvb._abi.HVB_EDEGENERATE
 
 
 def test_general_position_is_untouched(hvb):
