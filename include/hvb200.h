@@ -12,6 +12,15 @@
  *  - every call returns 0 or a negative HVB_E* code; hvb_last_error() gives the message;
  *  - there is NO CPU fallback: without a usable CUDA device hvb_create fails with HVB_ENOGPU;
  *  - a context is single-caller; distinct contexts are independent.
+ *
+ * Limits (checked, reported as HVB_EINVAL / HVB_ENOMEM, never silent)
+ *  - dimension 2..6; at most HVB_MAX_PLANES boundary planes;
+ *  - generators (+ halo generators of a periodic context) + planes < 2^31, and (dim+1) x bits(ids) <= 192 for the
+ *    lexicographic row order (only d = 6 with more than 2^27 generators is refused);
+ *  - vertices found by ONE context (one GPU's share) < 2^29: a frontier entry carries the vertex index in 29 bits
+ *    (5.3e8 vertex records are more than 180 GB of HBM hold); edge-table slots and queue entries are 32-bit indexed;
+ *  - int32 views (hvb_view_vertices32 / hvb_view_neighbors32, wire32) need ids < 2^31 - 1;
+ *  - the convex hull: facets < 2^27 (facet index in a ridge slot).
  */
 #ifndef HVB200_H
 #define HVB200_H
