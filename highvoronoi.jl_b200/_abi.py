@@ -12,7 +12,7 @@ ERROR_NAMES = {-1: "HVB_EINVAL", -2: "HVB_ECUDA", -3: "HVB_ENOGPU", -4: "HVB_ENO
 
 EXPORTS = ("hvb_default_params", "hvb_create", "hvb_set_points", "hvb_search", "hvb_counts", "hvb_fetch_vertices", "hvb_fetch_vertices_range", "hvb_fetch_rays",
            "hvb_neighbor_count", "hvb_fetch_neighbors", "hvb_view_vertices", "hvb_view_neighbors", "hvb_export_device", "hvb_merge_device", "hvb_adopt_device", "hvb_adopt_device_padded",
-           "hvb_stats", "hvb_last_error", "hvb_destroy", "hvb_version", "hvb_create_periodic", "hvb_halo_count", "hvb_fetch_halo", "hvb_fetch_vertex_flags", "hvb_cell_volumes", "hvb_cell_moments", "hvb_cell_areas", "hvb_clean_affected", "hvb_fetch_owned",
+           "hvb_stats", "hvb_last_error", "hvb_destroy", "hvb_version", "hvb_create_periodic", "hvb_halo_count", "hvb_fetch_halo", "hvb_fetch_vertex_flags", "hvb_cell_volumes", "hvb_cell_moments", "hvb_cell_areas", "hvb_cell_area_moments", "hvb_cell_area_moments", "hvb_clean_affected", "hvb_fetch_owned",
            "hvb_create_multi", "hvb_comm_unique_id", "hvb_comm_init", "hvb_exchange_counts", "hvb_allgather", "hvb_view_vertices32", "hvb_view_neighbors32", "hvb_convex_hull", "hvb_convex_hull_via", "hvb_fetch_vertices_var")
 
 
@@ -66,6 +66,7 @@ def lib():
         L.hvb_fetch_vertex_flags.argtypes = [vp, vp]
         L.hvb_cell_volumes.argtypes = [vp, vp]
         L.hvb_cell_moments.argtypes = [vp, vp, vp, vp]
+        L.hvb_cell_area_moments.argtypes = [vp, vp, vp]
         L.hvb_fetch_owned.argtypes = [vp, vp]
         L.hvb_create_multi.argtypes = [ctypes.POINTER(vp), i32, i64, vp, i32, vp, vp, vp, ctypes.POINTER(hvb_params), i32, vp]
         L.hvb_comm_unique_id.argtypes = [vp]
@@ -99,7 +100,7 @@ def lib():
         L.hvb_destroy.argtypes = [vp]
         L.hvb_destroy.restype = None
         L.hvb_version.restype = ctypes.c_char_p
-        for name in ("hvb_convex_hull", "hvb_convex_hull_via", "hvb_fetch_vertices_var", "hvb_view_vertices32", "hvb_view_neighbors32", "hvb_create_multi", "hvb_comm_unique_id", "hvb_comm_init", "hvb_exchange_counts", "hvb_allgather", "hvb_fetch_owned", "hvb_cell_volumes", "hvb_cell_moments", "hvb_cell_areas", "hvb_clean_affected", "hvb_create", "hvb_create_periodic", "hvb_halo_count", "hvb_fetch_halo", "hvb_fetch_vertex_flags", "hvb_set_points", "hvb_search", "hvb_counts", "hvb_fetch_vertices", "hvb_fetch_vertices_range", "hvb_fetch_rays", "hvb_neighbor_count",
+        for name in ("hvb_convex_hull", "hvb_convex_hull_via", "hvb_fetch_vertices_var", "hvb_view_vertices32", "hvb_view_neighbors32", "hvb_create_multi", "hvb_comm_unique_id", "hvb_comm_init", "hvb_exchange_counts", "hvb_allgather", "hvb_fetch_owned", "hvb_cell_volumes", "hvb_cell_moments", "hvb_cell_areas", "hvb_cell_area_moments", "hvb_clean_affected", "hvb_create", "hvb_create_periodic", "hvb_halo_count", "hvb_fetch_halo", "hvb_fetch_vertex_flags", "hvb_set_points", "hvb_search", "hvb_counts", "hvb_fetch_vertices", "hvb_fetch_vertices_range", "hvb_fetch_rays", "hvb_neighbor_count",
                      "hvb_fetch_neighbors", "hvb_view_vertices", "hvb_view_neighbors", "hvb_export_device", "hvb_merge_device", "hvb_adopt_device", "hvb_adopt_device_padded", "hvb_stats"):
             getattr(L, name).restype = i32
         _lib = L

@@ -318,6 +318,16 @@ class VoronoiMesh:
         _abi.check(L.hvb_cell_areas(ctx, area.ctypes.data_as(ctypes.c_void_p)), ctx)
         return area
 
+    def area_moments(self):
+        """(area [m], first [m, d]) aligned with the ids of neighbors(): the integrals of 1 and x_a over every interface
+        (VoronoiData(...).interface_integral for integrands up to degree one; hvb_cell_area_moments)"""
+        L, ctx = _abi.lib(), self.searcher._ctx
+        off, ids = self.neighbors()
+        area = np.empty((ids.shape[0],)); first = np.empty((ids.shape[0], self.dim))
+        P = lambda a: a.ctypes.data_as(ctypes.c_void_p)
+        _abi.check(L.hvb_cell_area_moments(ctx, P(area), P(first)), ctx)
+        return area, first
+
     def neighbors(self):
         """CSR (offsets[n+1], ids) of neighbors_of_cell for every cell (neighbors.jl:214-262)."""
         if self._nb is None:

@@ -125,6 +125,7 @@ int hvb_fetch_owned(hvb_ctx* ctx, uint8_t* owned) { return ctx ? ctx->fetch_owne
 int hvb_cell_volumes(hvb_ctx* ctx, double* vol) { return ctx ? ctx->cell_volumes(vol) : HVB_EINVAL; }
 int hvb_cell_moments(hvb_ctx* ctx, double* vol, double* first, double* second) { return ctx ? ctx->cell_moments(vol, first, second) : HVB_EINVAL; }
 int hvb_cell_areas(hvb_ctx* ctx, double* area) { return ctx ? ctx->cell_areas(area) : HVB_EINVAL; }
+int hvb_cell_area_moments(hvb_ctx* ctx, double* area, double* first) { return ctx ? ctx->cell_area_moments(area, first) : HVB_EINVAL; }
 int hvb_clean_affected(hvb_ctx* ctx, const int64_t* sig, const double* r, int64_t nv, int sig_stride, int64_t first_new, int64_t n_new, uint8_t* keep, uint8_t* affected) {
     return ctx ? ctx->clean_affected(sig, r, nv, sig_stride, first_new, n_new, keep, affected) : HVB_EINVAL;
 }

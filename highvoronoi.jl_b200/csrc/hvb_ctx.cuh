@@ -1205,6 +1205,41 @@ struct Ctx : hvb_ctx {
         return HVB_OK;
     }
 
+    // area and first moment of every interface, aligned with the neighbour lists (hvb_cell_area_moments)
+    int cell_area_moments(double* area, double* first) override {
+        if (merged || perturbed) { err = "hvb_cell_area_moments: not available on a context whose cloud was resolved from non-general position"; return HVB_ESTATE; }
+        if (!have_result) { err = "no search result"; return HVB_ESTATE; }
+        if (seed_prefix > 0) { err = "interface integrals need all vertices of the cells: not available after a search with seed vertices"; return HVB_ESTATE; }
+        if (std::max(1, prm.world) > 1) { err = "hvb_cell_area_moments runs on a single-GPU context"; return HVB_EINVAL; }
+        int rc = build_neighbors(); if (rc) return rc;
+        CK(cudaSetDevice(prm.device));
+        const long long n_list = periodic ? n_user : n;
+        const long long tot = std::max<long long>(nb_total, 1);
+        CK(vol_acc.ensure((size_t)tot * (1 + D))); CK(mom_dev.ensure((size_t)tot * (1 + D))); CK(vol_sat.ensure(tot));
+        CK(cudaMemsetAsync(vol_acc.p, 0, (size_t)tot * (1 + D) * sizeof(long long), stream));
+        CK(cudaMemsetAsync(vol_sat.p, 0, (size_t)tot, stream));
+        double fact = 1.0;
+        for (int k = 2; k <= D - 1; ++k) fact *= k;
+        const double s0 = ldexp(1.0, 52) / (pow(dv.ext, (double)(D - 1)) * fact), s1 = s0 / dv.ext;
+        if (nvert > 0 && nb_total > 0) {
+            k_cell_area_moments<D><<<blocks_for(nvert, 128), 128, 0, stream>>>(out_sig[res].p, (u32)nvert, xs_in.p, (long long)n, n_list, planes.p,
+                                                                              nb_off.p, nb_ids.p, s0, s1, vol_acc.p, vol_sat.p);
+            ++launches;
+        }
+        double* darea = mom_dev.p; double* dfirst = mom_dev.p + tot;
+        k_area_moments_finish<D><<<blocks_for(tot, 128), 128, 0, stream>>>(vol_acc.p, xs_in.p, nb_off.p, n_list, (long long)nb_total, 1.0 / (s0 * fact), 1.0 / (s1 * fact), darea, dfirst, vol_sat.p); ++launches;
+        if (nrays > 0 && nb_total > 0) {
+            k_area_moments_unbounded<<<blocks_for(nrays, 256), 256, 0, stream>>>(ray_edge.p, (long long)nrays, D, n_list, nb_off.p, nb_ids.p, darea, dfirst);
+            ++launches;
+        }
+        if (nb_total > 0 && area) CK(cudaMemcpyAsync(area, darea, (size_t)nb_total * sizeof(double), cudaMemcpyDeviceToHost, stream));
+        if (nb_total > 0 && first) CK(cudaMemcpyAsync(first, dfirst, (size_t)nb_total * D * sizeof(double), cudaMemcpyDeviceToHost, stream));
+        CK(cudaStreamSynchronize(stream));
+        CK(cudaGetLastError());
+        st.kernel_launches = launches;
+        return HVB_OK;
+    }
+
     // expected number of periodic images of a vertex that touch caller generators (capacity estimate only)
     double periodic_versions() const {
         static const double cd[7] = {0, 0, 3.14159265358979, 4.18879020478639, 4.93480220054468, 5.26378901391432, 5.16771278004997};

@@ -20,6 +20,7 @@ struct hvb_ctx {
     virtual int cell_volumes(double* vol) = 0;
     virtual int cell_moments(double* vol, double* first, double* second) = 0;
     virtual int cell_areas(double* area) = 0;
+    virtual int cell_area_moments(double* area, double* first) = 0;
     virtual int clean_affected(const int64_t* sig, const double* r, int64_t nv, int stride, int64_t first_new, int64_t n_new, uint8_t* keep, uint8_t* affected) = 0;
     virtual int set_points(int64_t n, const double* xs) = 0;
     virtual int search(const int64_t* cells, int64_t ncells, const int64_t* seed_sig, const double* seed_r, int64_t nseed, int stride) = 0;

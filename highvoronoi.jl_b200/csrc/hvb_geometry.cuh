@@ -99,15 +99,21 @@ HVB_HD double vertex_flag_sum(const double* xs, long long n, const PlaneSet* ps,
 // T_ab = sum p_k,a p_k,b.  The running sums S, T travel down the recursion with the foot points.
 // out[0] += sum prod(h);  out[1 + a] += sum prod(h) S_a / (d+1);  out[1 + D + idx(a,b)] += sum prod(h) (S_a S_b + T_ab) / ((d+1)(d+2)),
 // idx over a <= b row by row.  Divide by d! for the integrals.
+//
+// `first` (a position of s other than pos, or -1): the interface between the cell and s[first] instead of the cell -- only the
+// orders that impose that facet first, its own height left out: the (d-1)-simplices c_1..c_d inside the facet.
+// out[0] += sum prod'(h) (divide by (d-1)! for the area), out[1 + a] += sum prod'(h) S'_a / d with S' = c_1 + ... + c_d
+// (the first moment of the interface in local coordinates, (d-1)! times); second moments are not accumulated.
 template <int D>
-HVB_HD void vertex_flag_moments(const double* xs, long long n, const PlaneSet* ps, const long long* s, int pos, double* out) {
+HVB_HD void vertex_flag_moments(const double* xs, long long n, const PlaneSet* ps, const long long* s, int pos, double* out, int first = -1) {
     const int NM = 1 + D + D * (D + 1) / 2;
     for (int a = 0; a < NM; ++a) out[a] = 0.0;
     double nrm[D][D], b[D];
     const double* xi = xs + (size_t)(s[pos] - 1) * D;
-    int cnt = 0;
+    int cnt = 0, jfirst = -1;
     for (int k = 0; k < D + 1; ++k) {
         if (k == pos) continue;
+        if (k == first) jfirst = cnt;
         const long long g = s[k];
         if (g <= n) {
             const double* xg = xs + (size_t)(g - 1) * D;
@@ -133,6 +139,7 @@ HVB_HD void vertex_flag_moments(const double* xs, long long n, const PlaneSet* p
     it[0] = -1;
     for (;;) {
         int j = it[depth] + 1;
+        if (depth == 0 && jfirst >= 0) j = (it[0] < jfirst) ? jfirst : D;      // one choice at the top level
         while (j < D && ((used >> j) & 1u)) ++j;
         if (j >= D) {
             if (depth == 0) break;
@@ -155,20 +162,24 @@ HVB_HD void vertex_flag_moments(const double* xs, long long n, const PlaneSet* p
         const double h = (len > 0) ? (b[j] - nc) / len : 0.0;
         double cn[D];                                    // the next point of the chain: foot on facet j (the vertex at the last level)
         for (int a = 0; a < D; ++a) cn[a] = c[depth][a] + ((len > 0) ? h * m[a] / len : 0.0);
+        const double hf = (depth == 0 && jfirst >= 0) ? 1.0 : h;          // the interface's own height is not part of its area
         if (depth + 1 == D) {
-            const double w = prod[depth] * h;
+            const double w = prod[depth] * hf;
             out[0] += w;
             double Sa[D];
-            for (int a = 0; a < D; ++a) { Sa[a] = S[depth][a] + cn[a]; out[1 + a] += w * Sa[a] / (D + 1); }
-            int q = 0;
-            for (int a = 0; a < D; ++a)
-                for (int bb = a; bb < D; ++bb, ++q)
-                    out[1 + D + q] += w * (Sa[a] * Sa[bb] + T[depth][q] + cn[a] * cn[bb]) / ((D + 1) * (D + 2));
+            // c_0 = 0 adds nothing to S: the same sum serves the d + 1 vertices of the cell's orthoscheme and the d of the facet's
+            for (int a = 0; a < D; ++a) { Sa[a] = S[depth][a] + cn[a]; out[1 + a] += w * Sa[a] / (jfirst >= 0 ? D : D + 1); }
+            if (jfirst < 0) {
+                int q = 0;
+                for (int a = 0; a < D; ++a)
+                    for (int bb = a; bb < D; ++bb, ++q)
+                        out[1 + D + q] += w * (Sa[a] * Sa[bb] + T[depth][q] + cn[a] * cn[bb]) / ((D + 1) * (D + 2));
+            }
             continue;
         }
         for (int a = 0; a < D; ++a) { Q[depth][a] = m[a] / len; c[depth + 1][a] = cn[a]; S[depth + 1][a] = S[depth][a] + cn[a]; }
         { int q = 0; for (int a = 0; a < D; ++a) for (int bb = a; bb < D; ++bb, ++q) T[depth + 1][q] = T[depth][q] + cn[a] * cn[bb]; }
-        prod[depth + 1] = prod[depth] * h;
+        prod[depth + 1] = prod[depth] * hf;
         used |= 1u << j;
         ++depth;
         it[depth] = -1;

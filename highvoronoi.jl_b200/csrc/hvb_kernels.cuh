@@ -1373,6 +1373,67 @@ static __global__ void k_moments_finish(const long long* __restrict__ acc, const
             }
     }
 }
+// area and first moment of every interface, aligned with the CSR neighbour lists (vertex_flag_moments with `first`):
+// acc[entry][1 + D] in fixed point, sat[entry] = a term left the range
+template <int D>
+static __global__ void k_cell_area_moments(const long long* __restrict__ sig, u32 nv, const double* __restrict__ xs, long long n, long long n_list,
+                                    const PlaneSet* __restrict__ ps, const long long* __restrict__ off, const long long* __restrict__ ids,
+                                    double s0, double s1, long long* __restrict__ acc, unsigned char* __restrict__ sat) {
+    const int NM = 1 + D + D * (D + 1) / 2;
+    u32 v = blockIdx.x * blockDim.x + threadIdx.x;
+    if (v >= nv) return;
+    long long s[D + 1];
+#pragma unroll
+    for (int k = 0; k < D + 1; ++k) s[k] = sig[(size_t)v * (D + 1) + k];
+    for (int k = 0; k < D + 1; ++k) {
+        if (s[k] > n_list) continue;
+        for (int q = 0; q < D + 1; ++q) {
+            if (q == k) continue;
+            const long long pos = csr_find(off, ids, s[k], s[q]);
+            if (pos < 0) continue;
+            double m[NM];
+            vertex_flag_moments<D>(xs, n, ps, s, k, m, q);
+            for (int a = 0; a < 1 + D; ++a) {
+                const double t = m[a] * (a == 0 ? s0 : s1);
+                if (!(fabs(t) < 4.6e18)) sat[pos] = 1;
+                atomicAdd(reinterpret_cast<unsigned long long*>(acc + pos * (1 + D) + a), (unsigned long long)__double2ll_rn(t));
+            }
+        }
+    }
+}
+// local -> global: int x_a over the interface = x_i,a area + M_a; `cell_of[entry]` is the cell whose list holds the entry
+template <int D>
+static __global__ void k_area_moments_finish(const long long* __restrict__ acc, const double* __restrict__ xs, const long long* __restrict__ off,
+                                      long long n_list, long long tot, double i0, double i1, double* __restrict__ area, double* __restrict__ first,
+                                      const unsigned char* __restrict__ sat) {
+    long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (e >= tot) return;
+    // the cell of entry e: the last offset <= e
+    long long lo = 0, hi = n_list;
+    while (lo < hi) { const long long mid = (lo + hi + 1) >> 1; if (off[mid] <= e) lo = mid; else hi = mid - 1; }
+    const long long i = lo;                                   // 0-based cell
+    const double nan = __longlong_as_double(0x7ff8000000000000LL);
+    const double A = (double)acc[e * (1 + D)] * i0;
+    if (area) area[e] = sat[e] ? nan : A;
+    if (first) for (int k = 0; k < D; ++k) first[(size_t)e * D + k] = sat[e] ? nan : xs[(size_t)i * D + k] * A + (double)acc[e * (1 + D) + 1 + k] * i1;
+}
+static __global__ void k_area_moments_unbounded(const long long* __restrict__ ray_edge, long long nrays, int D, long long n_list,
+                                         const long long* __restrict__ off, const long long* __restrict__ ids, double* __restrict__ area, double* __restrict__ first) {
+    long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (i >= nrays) return;
+    const long long* e = ray_edge + i * D;
+    const double nan = __longlong_as_double(0x7ff8000000000000LL);
+    for (int a = 0; a < D; ++a) {
+        if (e[a] < 1 || e[a] > n_list) continue;
+        for (int b = 0; b < D; ++b) {
+            if (a == b) continue;
+            const long long pos = csr_find(off, ids, e[a], e[b]);
+            if (pos < 0) continue;
+            if (area) area[pos] = INFINITY;
+            if (first) for (int k = 0; k < D; ++k) first[(size_t)pos * D + k] = nan;
+        }
+    }
+}
 // cells with an unbounded edge: volume +inf, moments undefined (NaN)
 static __global__ void k_moments_unbounded(const long long* __restrict__ ray_edge, long long nentries, long long n_list, int dim,
                                     double* __restrict__ vol, double* __restrict__ first, double* __restrict__ second) {

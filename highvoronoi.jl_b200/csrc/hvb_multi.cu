@@ -280,6 +280,7 @@ struct MultiCtx : hvb_ctx {
         for (size_t i = 0; i < m; ++i) { double s = 0; for (size_t k = 0; k < sub.size(); ++k) s += part[k][i]; vol[i] = s; }
         return HVB_OK;
     }
+    int cell_area_moments(double*, double*) override { err = "hvb_cell_area_moments runs on a single-GPU context (hvb_create)"; return HVB_EINVAL; }
     int cell_moments(double*, double*, double*) override { err = "hvb_cell_moments runs on a single-GPU context (hvb_create)"; return HVB_EINVAL; }
     int cell_areas(double* area) override {
         if (gathered) return fwd(sub[0]->cell_areas(area));

@@ -126,7 +126,7 @@ typedef struct hvb_stats_t {
     int64_t probe_stages;     /* probe balls grown                                        */
     int64_t rounds;           /* frontier rounds                                          */
     int64_t seeds;            /* descents                                                 */
-    int64_t degenerate;       /* near-tie winners (non-general position)                  */
+    int64_t degenerate;       /* near-tie winners (non-general position); after on_degenerate = 2 resolved the cloud: vertices with more than dim+1 generators */
     int64_t kernel_launches;  /* kernels of this library launched by the last hvb_search  */
     int64_t capacity_retries;
     double  ms_build;         /* H2D + grid build                                         */
@@ -340,6 +340,13 @@ int hvb_cell_moments(hvb_ctx* ctx, double* vol, double* first, double* second);
  * neighbour may be a generator, a halo generator or a boundary plane.  hvb_neighbor_count entries.  Facets that hold an
  * unbounded edge get +inf.  Same completeness rule and the same fixed-point accumulation as hvb_cell_volumes. */
 int hvb_cell_areas(hvb_ctx* ctx, double* area);
+/* Area and first moment of every interface (VoronoiData(...).interface_integral for integrands up to degree one,
+ * integrate.jl:33-53): for entry k of the CSR neighbour lists area[k] = int 1 and first[k*dim + a] = int x_a over the facet between
+ * cell i and ids[k] (its centroid = first / area: what a finite-volume flux needs).  The orthoschemes of the flag decomposition
+ * restricted to the facet (vertex_flag_moments with `first`).  Either pointer may be NULL.  Unbounded facets: +inf / NaN;
+ * entries whose sums leave the fixed-point range: NaN.  Same completeness rule as hvb_cell_areas; single-GPU contexts,
+ * general position. */
+int hvb_cell_area_moments(hvb_ctx* ctx, double* area, double* first);
 
 int hvb_stats(hvb_ctx* ctx, hvb_stats_t* out);
 

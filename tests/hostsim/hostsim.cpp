@@ -226,6 +226,41 @@ static void areas(int64_t n, const double* xs, int P, const double* base, const 
     }
 }
 
+// area and first moment (global coordinates) of every interface, aligned with the CSR neighbour lists: out[off[n]][1 + D]
+template <int D>
+static void area_moments(int64_t n, const double* xs, int P, const double* base, const double* normal, int64_t nv, const int64_t* sig,
+                         const int64_t* off, const int64_t* ids, double* out) {
+    PlaneSet ps; memset(&ps, 0, sizeof(ps)); ps.P = P;
+    for (int p = 0; p < P; ++p) {
+        double nr = 0; for (int k = 0; k < D; ++k) nr += normal[p * D + k] * normal[p * D + k];
+        nr = sqrt(nr); double o = 0;
+        for (int k = 0; k < D; ++k) { ps.normal[p * 6 + k] = normal[p * D + k] / nr; o += ps.normal[p * 6 + k] * base[p * D + k]; }
+        ps.off[p] = o;
+    }
+    const int NM = 1 + D + D * (D + 1) / 2;
+    double fact = 1; for (int k = 2; k <= D - 1; ++k) fact *= k;
+    for (int64_t i = 0; i < off[n] * (1 + D); ++i) out[i] = 0;
+    for (int64_t v = 0; v < nv; ++v) {
+        long long s[D + 1];
+        for (int k = 0; k <= D; ++k) s[k] = sig[v * (D + 1) + k];
+        for (int k = 0; k <= D; ++k) {
+            if (s[k] > n) continue;
+            for (int q = 0; q <= D; ++q) {
+                if (q == k) continue;
+                const int64_t* a = ids + off[s[k] - 1]; const int64_t* b = ids + off[s[k]];
+                const int64_t* it = std::lower_bound(a, b, (int64_t)s[q]);
+                if (it == b || *it != s[q]) continue;
+                double m[NM];
+                vertex_flag_moments<D>(xs, n, &ps, s, k, m, q);
+                double* o = out + (it - ids) * (1 + D);
+                const double* x = xs + (s[k] - 1) * D;
+                o[0] += m[0] / fact;
+                for (int c = 0; c < D; ++c) o[1 + c] += (x[c] * m[0] + m[1 + c]) / fact;
+            }
+        }
+    }
+}
+
 // convex hull by the facet walk of hvb_hull.cuh, driven sequentially (unbounded domain)
 struct HullResult { int d; int64_t nf; std::vector<int64_t> facet; std::vector<double> normal, centre; int64_t raycasts, records, rounds, degenerate; };
 template <int D>
@@ -443,6 +478,16 @@ void hostsim_areas(int dim, int64_t n, const double* xs, int P, const double* ba
         case 4: areas<4>(n, xs, P, base, normal, nv, sig, off, ids, area); break;
         case 5: areas<5>(n, xs, P, base, normal, nv, sig, off, ids, area); break;
         case 6: areas<6>(n, xs, P, base, normal, nv, sig, off, ids, area); break;
+    }
+}
+void hostsim_area_moments(int dim, int64_t n, const double* xs, int P, const double* base, const double* normal, int64_t nv, const int64_t* sig,
+                          const int64_t* off, const int64_t* ids, double* out) {
+    switch (dim) {
+        case 2: area_moments<2>(n, xs, P, base, normal, nv, sig, off, ids, out); break;
+        case 3: area_moments<3>(n, xs, P, base, normal, nv, sig, off, ids, out); break;
+        case 4: area_moments<4>(n, xs, P, base, normal, nv, sig, off, ids, out); break;
+        case 5: area_moments<5>(n, xs, P, base, normal, nv, sig, off, ids, out); break;
+        case 6: area_moments<6>(n, xs, P, base, normal, nv, sig, off, ids, out); break;
     }
 }
 void* hostsim_resolve(int dim, int64_t n, const double* xs, int P, const double* base, const double* normal) {

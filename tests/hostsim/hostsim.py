@@ -187,3 +187,22 @@ def resolve(xs, base=None, normal=None):
     L.hostsim_resolve_fetch(h, P(off), P(ids), P(r), P(nb_off), P(nb_ids))
     L.hostsim_resolve_free(h)
     return dict(off=off, ids=ids, r=r, nb_off=nb_off, nb_ids=nb_ids, max_siglen=int(c[3]), simplicial=int(c[4]))
+
+
+def area_moments(xs, sig, off, ids, base=None, normal=None):
+    """area and first moment (global coordinates) of every interface aligned with the CSR neighbour lists, with the product's
+    own formula on the host: [off[n], 1 + d]"""
+    L = ctypes.CDLL(build())
+    L.hostsim_area_moments.restype = None
+    L.hostsim_area_moments.argtypes = [ctypes.c_int, ctypes.c_int64, ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p,
+                                       ctypes.c_int64, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]
+    xs = np.ascontiguousarray(xs, dtype=np.float64)
+    n, d = xs.shape
+    if base is None:
+        base = np.zeros((0, d)); normal = np.zeros((0, d))
+    base = np.ascontiguousarray(base, dtype=np.float64); normal = np.ascontiguousarray(normal, dtype=np.float64)
+    sig = np.ascontiguousarray(sig, dtype=np.int64); off = np.ascontiguousarray(off, dtype=np.int64); ids = np.ascontiguousarray(ids, dtype=np.int64)
+    out = np.zeros((int(off[n]), 1 + d))
+    P = lambda a: a.ctypes.data_as(ctypes.c_void_p)
+    L.hostsim_area_moments(d, n, P(xs), base.shape[0], P(base), P(normal), sig.shape[0], P(sig), P(off), P(ids), P(out))
+    return out

@@ -175,3 +175,28 @@ def test_moments_against_the_host_formula_and_on_a_lattice(hvb):
     mesh3, _ = hvb.voronoi(xs, searcher=s3)
     v3, f3, _ = mesh3.moments()
     assert np.isinf(v3).any() and np.all(np.isnan(f3[np.isinf(v3), 0])) and np.isfinite(f3[np.isfinite(v3)]).all()
+
+
+@pytest.mark.parametrize("d,n", [(2, 3000), (3, 2000), (4, 600), (5, 200)])
+def test_interface_moments(hvb, d, n):
+    """hvb_cell_area_moments: the areas are those of hvb_cell_areas; sum_j n_ij . (int_F x) = d vol_i for every cell (divergence
+    theorem, planes included); both cells see the same interface"""
+    xs = points(n, d, 90 + d)
+    s = hvb.Raycast(xs, domain=hvb.cuboid(d, periodic=[]))
+    mesh, _ = hvb.voronoi(xs, searcher=s)
+    off, ids = mesh.neighbors()
+    area, first = mesh.area_moments()
+    assert np.abs(area - mesh.areas()).max() < 1e-13
+    vol = mesh.volumes()
+    normal = s.domain.normal / np.linalg.norm(s.domain.normal, axis=1)[:, None]
+    cell = np.repeat(np.arange(n), np.diff(off))
+    real = np.asarray(ids) <= n
+    nij = np.empty((len(ids), d))
+    nij[real] = xs[np.asarray(ids)[real] - 1] - xs[cell[real]]
+    nij[real] /= np.linalg.norm(nij[real], axis=1)[:, None]
+    nij[~real] = normal[np.asarray(ids)[~real] - n - 1]
+    flux = np.bincount(cell, weights=(nij * first).sum(axis=1), minlength=n)
+    assert np.abs(flux - d * vol).max() < 1e-11
+    pair = {(int(c) + 1, int(j)): k for k, (c, j) in enumerate(zip(cell, ids)) if j <= n}
+    ks = np.array([[k, pair[(j, i)]] for (i, j), k in pair.items()])
+    assert np.abs(first[ks[:, 0]] - first[ks[:, 1]]).max() < 1e-13

@@ -132,3 +132,36 @@ def test_cell_moment_formula_matches_triangulated_cells(d, n):
             for b in range(a, d):
                 got2[a, b] = got2[b, a] = M[i - 1, 1 + d + q]; q += 1
         assert abs(m0 - M[i - 1, 0]) < 1e-12 and np.abs(m1 - M[i - 1, 1:1 + d]).max() < 1e-12 and np.abs(m2 - got2).max() < 1e-12
+
+
+@pytest.mark.parametrize("d,n", [(2, 80), (3, 100), (4, 70), (5, 40)])
+def test_interface_moment_formula(d, n):
+    """vertex_flag_moments restricted to a facet (behind hvb_cell_area_moments) on the host: the areas are those of the area formula,
+    the divergence theorem links the first moments of a cell's interfaces to its volume (sum_j n_ij . int_F x = d vol_i), both cells
+    see the same interface, and its centroid lies on the bisector"""
+    import hv_oracle
+    import qhull_oracle
+    xs = points(n, d, 80 + d)
+    base, normal = qhull_oracle.cuboid(d)
+    o = hv_oracle.run(xs, base, normal)
+    off, ids = o["nb_off"], o["nb_ids"]
+    AM = hostsim.area_moments(xs, o["sig"], off, ids, base, normal)
+    assert np.abs(AM[:, 0] - hostsim.areas(xs, o["sig"], off, ids, base, normal)).max() < 1e-13
+    vol = hostsim.volumes(xs, o["sig"], base, normal)
+    nrm = normal / np.linalg.norm(normal, axis=1)[:, None]
+    seen = {}
+    for i in range(1, n + 1):
+        tot = 0.0
+        for k in range(off[i - 1], off[i]):
+            j = int(ids[k])
+            if j <= n:
+                nij = xs[j - 1] - xs[i - 1]
+                nij /= np.linalg.norm(nij)
+                if AM[k, 0] > 1e-6:
+                    assert abs((AM[k, 1:] / AM[k, 0] - 0.5 * (xs[i - 1] + xs[j - 1])) @ nij) < 1e-9
+                seen[(i, j)] = AM[k]
+            else:
+                nij = nrm[j - n - 1]
+            tot += nij @ AM[k, 1:]
+        assert abs(tot - d * vol[i - 1]) < 1e-12
+    assert max(np.abs(v - seen[(j, i)]).max() for (i, j), v in seen.items()) < 1e-13
