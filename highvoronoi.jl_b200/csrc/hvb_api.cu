@@ -136,6 +136,6 @@ int hvb_stats(hvb_ctx* ctx, hvb_stats_t* out) {
 }
 const char* hvb_last_error(hvb_ctx* ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
 void hvb_destroy(hvb_ctx* ctx) { delete ctx; }
-const char* hvb_version(void) { return "hvb200 0.1.0 sm_100a"; }
+const char* hvb_version(void) { return "hvb200 0.2.0 sm_100a"; }
 
 }  // extern "C"
