@@ -7,4 +7,4 @@ from .api import (refine, ConvexHull, B200Thread, Boundary, HVBError, Raycast, R
                   RCNonGeneralFast, RCNonGeneralHP, RCOriginal, RCStandard, RCOriginalSafety, RCNonGeneralSkip, RCOriginalHP, RCNonGeneralCutoff, SingleThread, VoronoiData,
                   VoronoiGeometry, VoronoiMesh, VoronoiNodes, cuboid, voronoi)
 
-__version__ = "0.1.0"
+__version__ = "0.2.0"
