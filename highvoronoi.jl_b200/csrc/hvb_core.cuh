@@ -789,6 +789,35 @@ HVB_HD void plane_candidates(const Dev<D>& dv, const RayQ<D>& q, Best& best) {
 
 // Smallest t > 0 at which the ball centred at r + t u through x0 touches another generator or boundary plane.
 // All lanes of the tile call this with identical q; all return the same Best.
+// Shrinks the search ball of a probe stage to the best bound so far (tb2 / 2 bounds the winner once a candidate tightened
+// it).  With the FP32 row geometry this is FP32 arithmetic on rounded-up quantities (the ball only selects cells, a superset
+// is all it has to be); the filter constants of the larger ball stay valid bounds.
+template <int D>
+HVB_HD void shrink_ball(const Dev<D>& dv, const RayQ<D>& q, bool use32, const Best& best, Filt& flt, const float (&uf)[D],
+                        const float (&r32)[D], float a32, float perp2f, float& Ts32, Ball32<D>& b32, double& Ts, double (&cen)[D],
+                        double& rho2, double& rho, double R0) {
+    if (use32) {
+        const float tsh = fminf((float)best.t * 1.0000002f, 0.5f * flt.tb2 * 1.000001f);
+        if (tsh < 0.92f * Ts32) {
+            Ts32 = tsh;
+#pragma unroll
+            for (int k = 0; k < D; ++k) b32.cen[k] = fmaf(Ts32, uf[k], r32[k]);
+            const float dT = fabsf(Ts32 - a32) + 4e-7f * (fabsf(a32) + Ts32);
+            b32.rho2 = fmaf(dT, dT, perp2f) * 1.00001f;
+        }
+    } else {
+        const double Tshr = fmin(best.t, 0.5 * (double)flt.tb2);
+        if (Tshr < 0.92 * Ts) {
+            Ts = Tshr;
+#pragma unroll
+            for (int k = 0; k < D; ++k) cen[k] = q.r[k] + Ts * q.u[k];
+            rho2 = (q.R0sq - 2.0 * Ts * q.a + Ts * Ts) * (1.0 + 1e-12) + 1e-300;
+            rho = sqrt(rho2);
+            { float keep = flt.tb2; flt = make_filter<D>(Ts, rho, R0, dv.ext); flt.tb2 = fminf(flt.tb2, keep); }
+        }
+    }
+}
+
 template <int D, class T>
 HVB_HD Best min_t_query(const Dev<D>& dv, const T& tile, const RayQ<D>& q, LocalStats& ls) {
     Best best;
@@ -915,29 +944,7 @@ HVB_HD Best min_t_query(const Dev<D>& dv, const T& tile, const RayQ<D>& q, Local
 #pragma unroll
                     for (int m = T::SIZE / 2; m >= 1; m >>= 1) flt.tb2 = fminf(flt.tb2, tile.shfl_xor(flt.tb2, m));
                 }
-                // shrink the ball to the best bound so far (tb2 / 2 bounds the winner once a candidate tightened it).  With
-                // the FP32 row geometry this is FP32 arithmetic on rounded-up quantities (the ball only selects cells, a
-                // superset is all it has to be); the filter constants of the larger ball stay valid bounds
-                if (use32) {
-                    const float tsh = fminf((float)best.t * 1.0000002f, 0.5f * flt.tb2 * 1.000001f);
-                    if (tsh < 0.92f * Ts32) {
-                        Ts32 = tsh;
-#pragma unroll
-                        for (int k = 0; k < D; ++k) b32.cen[k] = fmaf(Ts32, uf[k], r32[k]);
-                        const float dT = fabsf(Ts32 - a32) + 4e-7f * (fabsf(a32) + Ts32);
-                        b32.rho2 = fmaf(dT, dT, perp2f) * 1.00001f;
-                    }
-                } else {
-                    const double Tshr = fmin(best.t, 0.5 * (double)flt.tb2);
-                    if (Tshr < 0.92 * Ts) {
-                        Ts = Tshr;
-#pragma unroll
-                        for (int k = 0; k < D; ++k) cen[k] = q.r[k] + Ts * q.u[k];
-                        rho2 = (q.R0sq - 2.0 * Ts * q.a + Ts * Ts) * (1.0 + 1e-12) + 1e-300;
-                        rho = sqrt(rho2);
-                        { float keep = flt.tb2; flt = make_filter<D>(Ts, rho, R0, dv.ext); flt.tb2 = fminf(flt.tb2, keep); }
-                    }
-                }
+                shrink_ball<D>(dv, q, use32, best, flt, uf, r32, a32, perp2f, Ts32, b32, Ts, cen, rho2, rho, R0);
             }
         } else {
         // rows lane, lane + G, ... ; the next row's range is requested before the current one is scanned
@@ -959,29 +966,7 @@ HVB_HD Best min_t_query(const Dev<D>& dv, const T& tile, const RayQ<D>& q, Local
 #pragma unroll
                 for (int m = T::SIZE / 2; m >= 1; m >>= 1) flt.tb2 = fminf(flt.tb2, tile.shfl_xor(flt.tb2, m));
             }
-            // shrink the ball to the best bound so far (tb2 / 2 bounds the winner once a candidate tightened it).  With
-            // the FP32 row geometry this is FP32 arithmetic on rounded-up quantities (the ball only selects cells, a
-            // superset is all it has to be); the filter constants of the larger ball stay valid bounds
-            if (use32) {
-                const float tsh = fminf((float)best.t * 1.0000002f, 0.5f * flt.tb2 * 1.000001f);
-                if (tsh < 0.92f * Ts32) {
-                    Ts32 = tsh;
-#pragma unroll
-                    for (int k = 0; k < D; ++k) b32.cen[k] = fmaf(Ts32, uf[k], r32[k]);
-                    const float dT = fabsf(Ts32 - a32) + 4e-7f * (fabsf(a32) + Ts32);
-                    b32.rho2 = fmaf(dT, dT, perp2f) * 1.00001f;
-                }
-            } else {
-                const double Tshr = fmin(best.t, 0.5 * (double)flt.tb2);
-                if (Tshr < 0.92 * Ts) {
-                    Ts = Tshr;
-#pragma unroll
-                    for (int k = 0; k < D; ++k) cen[k] = q.r[k] + Ts * q.u[k];
-                    rho2 = (q.R0sq - 2.0 * Ts * q.a + Ts * Ts) * (1.0 + 1e-12) + 1e-300;
-                    rho = sqrt(rho2);
-                    { float keep = flt.tb2; flt = make_filter<D>(Ts, rho, R0, dv.ext); flt.tb2 = fminf(flt.tb2, keep); }
-                }
-            }
+            shrink_ball<D>(dv, q, use32, best, flt, uf, r32, a32, perp2f, Ts32, b32, Ts, cen, rho2, rho, R0);
         }
         }
         if (T::SIZE > 1) {
