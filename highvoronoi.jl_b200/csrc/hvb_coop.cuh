@@ -408,7 +408,7 @@ __device__ __forceinline__ Best coop_min_t(const Dev<D>& dv, CoopShared<D>& sh, 
         plane_candidates<D>(dv, q, best);
         R0 = sqrt(q.R0sq);
         R0p = fmax(R0, 0.5 * dv.hmin);
-        perp2 = fmax(q.R0sq - q.a * q.a, 0.0);                    // squared distance of x0 to the ray's line
+        perp2 = ray_perp2<D>(q);                                  // squared distance of x0 to the ray's line
 #pragma unroll
         for (int k = 0; k < D; ++k) {
             sh.uf[k][lane] = (float)q.u[k];
@@ -433,8 +433,8 @@ __device__ __forceinline__ Best coop_min_t(const Dev<D>& dv, CoopShared<D>& sh, 
             const double Ts = fmin(Tst, best.t);
             if (!(Ts < INFINITY)) { serial = true; active = false; }      // half-space mode: the FP64 path
             else {
-                const double rho2 = (q.R0sq - 2.0 * Ts * q.a + Ts * Ts) * (1.0 + 1e-12) + 1e-300;
-                const double rho = sqrt(rho2);
+                double rho, rho2;
+                ray_ball<D>(q, perp2, R0, Ts, rho, rho2);
                 int clo[D], chi[D];
                 long long nrows = 1; int nt = 1;
                 bool empty = false;

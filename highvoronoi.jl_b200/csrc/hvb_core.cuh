@@ -789,13 +789,33 @@ HVB_HD void plane_candidates(const Dev<D>& dv, const RayQ<D>& q, Best& best) {
 
 // Smallest t > 0 at which the ball centred at r + t u through x0 touches another generator or boundary plane.
 // All lanes of the tile call this with identical q; all return the same Best.
+// Squared distance of x0 to the ray's line, and the ball centred at r + T u through x0 (radius, squared radius with the
+// row selection's safety factor).  Both come from the part of x0 - r perpendicular to u: the textbook forms R0^2 - a^2
+// and R0^2 - 2 T a + T^2 cancel catastrophically when the origin vertex lies far outside the cloud (a flat simplex on
+// the hull of an unbounded cloud has R0 ~ 1e7 cloud diameters, and the ball shrinks to the size of the cloud with the
+// first candidate): the rounding of R0^2 then exceeded the whole radius and rows that held the winner were pruned.
+// The absolute term covers the rounding of r + T u, of a and of the perpendicular part (a few ulp of |r| + R0 + |T|).
+template <int D>
+HVB_HD double ray_perp2(const RayQ<D>& q) {
+    double s = 0;
+#pragma unroll
+    for (int k = 0; k < D; ++k) { const double p = (q.x0[k] - q.r[k]) - q.a * q.u[k]; s += p * p; }
+    return s;
+}
+template <int D>
+HVB_HD void ray_ball(const RayQ<D>& q, double perp2, double R0, double T, double& rho, double& rho2) {
+    const double dT = T - q.a;
+    rho = sqrt(perp2 + dT * dT) + 1.5e-14 * (q.rnorm + R0 + fabs(T));
+    rho2 = rho * rho * (1.0 + 1e-12) + 1e-300;
+}
+
 // Shrinks the search ball of a probe stage to the best bound so far (tb2 / 2 bounds the winner once a candidate tightened
 // it).  With the FP32 row geometry this is FP32 arithmetic on rounded-up quantities (the ball only selects cells, a superset
 // is all it has to be); the filter constants of the larger ball stay valid bounds.
 template <int D>
 HVB_HD void shrink_ball(const Dev<D>& dv, const RayQ<D>& q, bool use32, const Best& best, Filt& flt, const float (&uf)[D],
                         const float (&r32)[D], float a32, float perp2f, float& Ts32, Ball32<D>& b32, double& Ts, double (&cen)[D],
-                        double& rho2, double& rho, double R0) {
+                        double& rho2, double& rho, double R0, double perp2) {
     if (use32) {
         const float tsh = fminf((float)best.t * 1.0000002f, 0.5f * flt.tb2 * 1.000001f);
         if (tsh < 0.92f * Ts32) {
@@ -811,8 +831,7 @@ HVB_HD void shrink_ball(const Dev<D>& dv, const RayQ<D>& q, bool use32, const Be
             Ts = Tshr;
 #pragma unroll
             for (int k = 0; k < D; ++k) cen[k] = q.r[k] + Ts * q.u[k];
-            rho2 = (q.R0sq - 2.0 * Ts * q.a + Ts * Ts) * (1.0 + 1e-12) + 1e-300;
-            rho = sqrt(rho2);
+            ray_ball<D>(q, perp2, R0, Ts, rho, rho2);
             { float keep = flt.tb2; flt = make_filter<D>(Ts, rho, R0, dv.ext); flt.tb2 = fminf(flt.tb2, keep); }
         }
     }
@@ -839,7 +858,7 @@ HVB_HD Best min_t_query(const Dev<D>& dv, const T& tile, const RayQ<D>& q, Local
     }
     const double R0 = sqrt(q.R0sq);
     const double R0p = fmax(R0, 0.5 * dv.hmin);
-    const double perp2 = fmax(q.R0sq - q.a * q.a, 0.0);       // squared distance of x0 to the ray's line
+    const double perp2 = ray_perp2<D>(q);                     // squared distance of x0 to the ray's line
     float a32 = (float)q.a;
     float perp2f = (float)(perp2 * (1.0 + 1e-6)) * 1.000001f;
 #if defined(__CUDA_ARCH__)
@@ -872,8 +891,7 @@ HVB_HD Best min_t_query(const Dev<D>& dv, const T& tile, const RayQ<D>& q, Local
         } else {
 #pragma unroll
             for (int k = 0; k < D; ++k) cen[k] = q.r[k] + Ts * q.u[k];
-            rho2 = (q.R0sq - 2.0 * Ts * q.a + Ts * Ts) * (1.0 + 1e-12) + 1e-300;
-            rho = sqrt(rho2);
+            ray_ball<D>(q, perp2, R0, Ts, rho, rho2);
         }
         // cell box of the ball
         int clo[D], chi[D];
@@ -944,7 +962,7 @@ HVB_HD Best min_t_query(const Dev<D>& dv, const T& tile, const RayQ<D>& q, Local
 #pragma unroll
                     for (int m = T::SIZE / 2; m >= 1; m >>= 1) flt.tb2 = fminf(flt.tb2, tile.shfl_xor(flt.tb2, m));
                 }
-                shrink_ball<D>(dv, q, use32, best, flt, uf, r32, a32, perp2f, Ts32, b32, Ts, cen, rho2, rho, R0);
+                shrink_ball<D>(dv, q, use32, best, flt, uf, r32, a32, perp2f, Ts32, b32, Ts, cen, rho2, rho, R0, perp2);
             }
         } else {
         // rows lane, lane + G, ... ; the next row's range is requested before the current one is scanned
@@ -966,7 +984,7 @@ HVB_HD Best min_t_query(const Dev<D>& dv, const T& tile, const RayQ<D>& q, Local
 #pragma unroll
                 for (int m = T::SIZE / 2; m >= 1; m >>= 1) flt.tb2 = fminf(flt.tb2, tile.shfl_xor(flt.tb2, m));
             }
-            shrink_ball<D>(dv, q, use32, best, flt, uf, r32, a32, perp2f, Ts32, b32, Ts, cen, rho2, rho, R0);
+            shrink_ball<D>(dv, q, use32, best, flt, uf, r32, a32, perp2f, Ts32, b32, Ts, cen, rho2, rho, R0, perp2);
         }
         }
         if (T::SIZE > 1) {

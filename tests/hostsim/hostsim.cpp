@@ -79,14 +79,55 @@ static SimResult* run(int64_t n, const double* xs, int P, const double* base, co
     if (seed_stride <= 0) seed_stride = 16;
     std::vector<int> trace_buf;
     if (g_want_trace) g_trace = &trace_buf;
-    for (int64_t i = 0; i < n; i += seed_stride) seed_item<D, TileHost>(dv, tile, (int)i, qa.data(), &na, qcap, ls);
+    int64_t watch[D + 1]; int watch_n = 0;
+    const bool watch_all = getenv("HOSTSIM_WATCH") && !strcmp(getenv("HOSTSIM_WATCH"), "all");
+    if (const char* w = watch_all ? nullptr : getenv("HOSTSIM_WATCH")) {
+        for (const char* c = w; *c && watch_n <= D; ) { watch[watch_n++] = strtoll(c, (char**)&c, 10); if (*c == ',') ++c; }
+        std::sort(watch, watch + watch_n);
+        g_trace = &trace_buf;
+    }
+    if (watch_all) g_trace = &trace_buf;
+    for (int64_t i = 0; i < n; i += seed_stride) {
+        const u32 v_before = vcount;
+        seed_item<D, TileHost>(dv, tile, (int)i, qa.data(), &na, qcap, ls);
+        if (watch_all && vcount > v_before) {
+            fprintf(stderr, "[seed] start %lld -> (", (long long)perm[i] + 1);
+            for (int k = 0; k <= D; ++k) { int id = vsig[(size_t)v_before * (D + 1) + k]; fprintf(stderr, "%lld ", (long long)((id < n ? perm[id] : id) + 1)); }
+            fprintf(stderr, ")\n");
+        }
+    }
     int rounds = 0;
     for (;;) {
         while (na > 0) {
             nb = 0;
             for (u32 i = 0; i < na; ++i) {
                 if (etab[(u32)(qa[i] >> 32)] & EDGE_CLOSED) { ls.closed_skips++; continue; }   // as in k_expand
+                const u32 v_before = vcount;
+                const size_t tr_before = trace_buf.size();
                 expand_item<D, TileHost>(dv, tile, qa[i], qb.data(), &nb, qcap, ls);
+                if ((watch_n == D + 1 || watch_all) && vcount > v_before) {
+                    // HOSTSIM_WATCH=id,id,...: report the walk that produced this vertex (caller ids, 1-based)
+                    int64_t s[D + 1];
+                    for (int k = 0; k <= D; ++k) { int id = vsig[(size_t)v_before * (D + 1) + k]; s[k] = (id < n ? perm[id] : id) + 1; }
+                    std::sort(s, s + D + 1);
+                    bool same = true; for (int k = 0; k <= D; ++k) same &= (s[k] == watch[k]);
+                    if (same || watch_all) {
+                        const u32 vo = (u32)(qa[i] & 0xffffffffu) >> 3; const int kd = (int)(qa[i] & 7);
+                        fprintf(stderr, "[watch] (");
+                        for (int k = 0; k <= D; ++k) fprintf(stderr, "%lld ", (long long)s[k]);
+                        fprintf(stderr, ") found from vertex (");
+                        for (int k = 0; k <= D; ++k) { int id = vsig[(size_t)vo * (D + 1) + k]; fprintf(stderr, "%lld%s", (long long)((id < n ? perm[id] : id) + 1), k == kd ? "* " : " "); }
+                        fprintf(stderr, ") r = (");
+                        for (int k = 0; k < D; ++k) fprintf(stderr, "%.17g ", vr[(size_t)vo * D + k]);
+                        fprintf(stderr, ")  grid g = (");
+                        for (int k = 0; k < D; ++k) fprintf(stderr, "%d ", dv.g[k]);
+                        fprintf(stderr, ") h = (");
+                        for (int k = 0; k < D; ++k) fprintf(stderr, "%.4g ", dv.h[k]);
+                        fprintf(stderr, ")\n[watch] trace:");
+                        for (size_t t = tr_before; t + 1 < trace_buf.size(); t += 2) fprintf(stderr, " %d:%d", trace_buf[t], trace_buf[t + 1]);
+                        fprintf(stderr, "\n");
+                    }
+                }
             }
             qa.swap(qb); na = nb; ++rounds;
         }

@@ -75,6 +75,17 @@ def test_matches_qhull_directly(hvb):
     assert max(np.abs(mesh.r[k] - q[s]).max() for k, s in enumerate(got)) < 1e-11
 
 
+@pytest.mark.parametrize("key", ["xs_1161", "xs_1282"])
+def test_walks_from_vertices_1e7_diameters_away(hvb, key):
+    """unbounded clouds whose density varies by ten orders of magnitude along one axis: flat hull simplices put vertices
+    1e7 ... 1e10 cloud diameters away (tests/test_hostsim.py has the story of the regression); against Qhull"""
+    xs = np.load(os.path.join(os.path.dirname(__file__), "golden", "clouds", "far_vertices.npz"))[key]
+    truth, rays = qhull_oracle.unbounded(xs)
+    mesh, s = run_gpu(hvb, xs, False)
+    assert {tuple(r) for r in mesh.sig.tolist()} == set(truth) and len(mesh.sig) == len(truth)
+    assert {tuple(r) for r in mesh.ray_edge.tolist()} == rays
+
+
 def test_fp32_filter_equals_fp64_only(hvb):
     xs = points(30000, 3, 3)
     a, sa = run_gpu(hvb, xs, True, fp32_filter=1)

@@ -60,6 +60,21 @@ def test_far_vertices_of_flat_hull_simplices(oracle, d, n, seed):
     assert sorted(map(tuple, s["ray_edge"].tolist())) == sorted(map(tuple, o["ray_edge"].tolist()))
 
 
+@pytest.mark.parametrize("key", ["xs_1161", "xs_1282"])
+def test_walks_from_vertices_1e7_diameters_away(key):
+    """clouds whose density varies by ten orders of magnitude along one axis (found by tools/fuzz_hostsim.py): a flat hull
+    simplex puts a vertex 1e7 ... 1e10 cloud diameters away, and the walk back from it shrinks its ball to the size of the
+    cloud with the first candidate.  Regression: the squared radius was formed as R0^2 - 2 T a + T^2, whose rounding error
+    exceeded the radius; rows holding the winner were pruned and vertices with non-empty balls were returned"""
+    import os
+    xs = np.load(os.path.join(os.path.dirname(__file__), "golden", "clouds", "far_vertices.npz"))[key]
+    truth, rays = qhull_oracle.unbounded(xs)
+    s = hostsim.run(xs)
+    assert {tuple(r) for r in s["sig"].tolist()} == set(truth)
+    assert {tuple(r) for r in s["ray_edge"].tolist()} == rays
+    assert s["stats"]["degenerate"] == 0 and s["stats"]["seed_fail"] == 0
+
+
 # ---- geometry product: the volume formula of hvb_geometry.cuh on the host, against Qhull ---------------------------
 @pytest.mark.parametrize("d,n", [(2, 400), (3, 300), (4, 120), (5, 50)])
 def test_cell_volume_formula_matches_qhull(d, n):
