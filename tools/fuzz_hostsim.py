@@ -197,6 +197,12 @@ def one(seed):
     tag = "seed=%d d=%d n=%d %s %s %s" % (seed, d, n, kind, "bounded" if bounded else "unbounded", knobs)
     if bounded:
         base, normal = qhull_oracle.cuboid(d)
+        if rng.integers(0, 2):
+            # the same cube somewhere else, at another size: plane offsets and the grid origin stop being 0 and 1
+            lo_, w_ = float(rng.uniform(-1, 1) * 10.0 ** rng.uniform(0, 3)), float(10.0 ** rng.uniform(-3, 3))
+            xs = lo_ + w_ * xs
+            base, normal = qhull_oracle.cuboid(d, lo_, lo_ + w_)
+            tag += " cube [%.6g, %.6g]" % (lo_, lo_ + w_)
         try:
             truth = qhull_oracle.bounded(xs, base, normal)
         except Exception as e:                              # Qhull refuses (nearly) degenerate input: not a finding
@@ -207,6 +213,11 @@ def one(seed):
         # stretched and offset clouds (the FP32 filter stores coordinates relative to the bounding box)
         if rng.integers(0, 2):
             xs = xs * 10.0 ** rng.uniform(-2, 2, size=d) + rng.uniform(-1, 1, size=d) * 10.0 ** rng.uniform(0, 3)
+        # generators that share an extreme coordinate exactly (x**4 underflows below the offset's ulp) are collinear points of the
+        # hull: non-general position that no in-sphere tie reveals -- outside the contract of the unbounded search
+        tolk = 1e-11 * np.abs(xs).max(axis=0)                     # ... or within the reference's relative tolerance of it
+        if any((xs[:, k] - xs[:, k].min() <= tolk[k]).sum() > 1 or (xs[:, k].max() - xs[:, k] <= tolk[k]).sum() > 1 for k in range(d)):
+            return ("skip", tag + " collinear hull points")
         try:
             truth, rays = qhull_oracle.unbounded(xs)
         except Exception as e:
@@ -240,6 +251,13 @@ def one(seed):
             cnt[e] = cnt.get(e, 0) + 1
         if all(c == 2 for c in cnt.values()) and all(ball_is_empty(xs, k) is not False for k in got):
             return ("skip", tag + " qhull wrong on %d vertices (result is a closed complex of empty balls)" % len(got ^ want))
+    if got != want and bounded and not s["stats"]["seed_fail"]:
+        # a small cube far from the origin: Qhull's neighbour lists lose vertices.  The result stands on its own if every ball
+        # is empty (exact) and the cell volumes computed from the rows fill the domain
+        dom = float(np.prod([base[2 * k, k] - base[2 * k + 1, k] for k in range(d)]))
+        if abs(hostsim.volumes(xs, s["sig"], base, normal).sum() / dom - 1.0) < 1e-9 and \
+                all(ball_is_empty(xs, k, (base, normal)) is not False for k in got):
+            return ("skip", tag + " qhull wrong on %d vertices (empty balls, volumes fill the domain)" % len(got ^ want))
     if (got != want or not rays_ok) and not s["stats"]["seed_fail"]:
         # near-degenerate input decided by the reference's own tolerances (u.x > c (1 + 1e-12), t >= 1e-12): parity is with the
         # restated reference, not with Qhull
@@ -261,15 +279,16 @@ def one(seed):
         # equal the volume of the convex hull of the cell's vertices
         from scipy.spatial import ConvexHull
         vol = hostsim.volumes(xs, s["sig"], base, normal)
-        if not abs(vol.sum() - 1.0) < 1e-9:
-            return ("FAIL", tag + " sum of cell volumes - 1 = %.3e" % (vol.sum() - 1.0))
+        dom = float(np.prod([base[2 * k, k] - base[2 * k + 1, k] for k in range(d)]))
+        if not abs(vol.sum() / dom - 1.0) < 1e-8:
+            return ("FAIL", tag + " sum of cell volumes / domain - 1 = %.3e" % (vol.sum() / dom - 1.0))
         for i in rng.integers(0, n, size=min(n, 12)):
             rows = (s["sig"] == i + 1).any(axis=1)
             try:
                 ref = ConvexHull(s["r"][rows]).volume
             except Exception:
                 continue
-            if not abs(vol[i] - ref) <= 1e-7 * ref + 1e-13:
+            if not abs(vol[i] - ref) <= 1e-7 * ref + 1e-13 * dom:
                 return ("FAIL", tag + " volume of cell %d: %.12e, Qhull %.12e" % (i + 1, vol[i], ref))
     # coordinates against Qhull's circumcentres, relative to the circumradius
     sig = s["sig"]
