@@ -17,6 +17,10 @@
 // rows in tests/test_hostsim.py::test_cell_volume_formula_matches_qhull and on the GPU result
 // in tests/test_gpu_volumes.py; exact values beyond that invariant stay unpinned.
 //
+// Methods: the default RCNonGeneralHP (raycast.jl:794-970) and, selected with hvo_set_method, RCOriginal (:972-1012) and
+// RCNonGeneralFast (:542-631) -- three of the four that test/rcmethods.jl:10-13 runs; RCCombined's nested KD traversal
+// (extended.jl:155-176, kd_tree.jl:210-336) is not restated.  tests/test_oracle.py checks that they return the same mesh.
+//
 // Every function cites the reference file:line (relative to /root/reference/src) it follows.
 // Deviations from the reference, all irrelevant for general-position input:
 //  * Double64 "full_mode" re-orthogonalised correction (raycast.jl:633-707) is not restated;
@@ -200,6 +204,9 @@ struct Problem {
     std::vector<double> pbase, pnormal;         // P*d
     KDTree tree;
     double variance_tol = 1e-15, break_tol = 1e-5, b_nodes_tol = 1e-7, plane_tol = 1e-12;   // raycast-types.jl:226-230
+    // search_settings = (method = ...,): 0 RCNonGeneralHP (RCStandard), 1 RCOriginal, 3 RCNonGeneralFast -- the numbering of
+    // hvb_params.method (include/hvb200.h)
+    int method = 0;
 };
 
 // Shared vertex store: hvdatabase.jl:94-116 (heap + key set), vdbdatabaseref.jl:118-143 (per-cell
@@ -424,9 +431,119 @@ struct Searcher {
     // sig: generators the ray is equidistant to (full_edge, or the partial simplex in descent);
     // origin: ids that may not be returned (the origin vertex's sig).  On success the new
     // generator(s) are appended to sig (sorted).  Returns generator or -1; t = INF if none.
+    // raycast.jl:394 get_t: the plain (cancellation-prone) form the FP64-only methods use
+    double get_t(const double* r, const double* u, const double* x0, const double* xn) const {
+        double den = 0;
+        for (int k = 0; k < d; ++k) den += u[k] * (xn[k] - x0[k]);
+        return (dist2(r, xn, d) - dist2(r, x0, d)) / (2 * den);
+    }
+
+    // raycast.jl:972-1012 raycast_des2(::Raycast_Original): the classic incircle iteration -- nearest neighbour of the foot
+    // point under the half-space predicate, then nearest neighbours of r + t u WITHOUT predicate until the answer is a
+    // generator of the edge or repeats.  General position only (one generator is appended).  `full_mode` (correct_cast on
+    // ill-conditioned rays, :990,999) re-solves the candidate centre; it does not change which generator wins and is left out.
+    i64 raycast_original(std::vector<i64>& sig, const double* r, const double* u, const std::vector<i64>& edge, double& t, double* r2) {
+        const double* x0 = X(edge[0]);
+        double c1 = -INF;
+        for (i64 g : sig) c1 = std::max(c1, dot(X(g), u, d));
+        const double c = c1 + std::fabs(c1) * pb.plane_tol;
+        auto skip = [&](i64 i) { return dot(X(i), u, d) <= c; };
+        auto noskip = [](i64) { return false; };
+        double vvv[MAXD], a = 0;
+        for (int k = 0; k < d; ++k) a += u[k] * (x0[k] - r[k]);
+        for (int k = 0; k < d; ++k) vvv[k] = r[k] + u[k] * a;
+        std::pair<i64, double> res = nn(vvv, skip);
+        t = INF;
+        if (res.first < 0) { std::memcpy(r2, r, sizeof(double) * d); return -1; }
+        i64 i = res.first, i2 = res.first;
+        double current_t = INF;
+        while (i >= 0) {
+            const double tt = get_t_hp(r, u, x0, X(i));
+            if (tt >= current_t) break;
+            current_t = tt;
+            for (int k = 0; k < d; ++k) vvv[k] = r[k] + tt * u[k];
+            i = nn(vvv, noskip).first;
+            if (i == i2 || std::find(sig.begin(), sig.end(), i) != sig.end()) i = -1;
+            if (i >= 0) i2 = i;
+        }
+        t = get_t_hp(r, u, x0, X(i2));
+        for (int k = 0; k < d; ++k) r2[k] = r[k] + t * u[k];
+        sig.push_back(i2);
+        std::sort(sig.begin(), sig.end());
+        return i2;
+    }
+
+    // raycast.jl:542-631 raycast_des2(::Raycast_Non_General): two predicate nearest-neighbour steps, one in-range ball, the
+    // smallest t with the tie rule (largest u.(x - x0) within 1e-7), everything in plain FP64 (get_t)
+    i64 raycast_nongeneral_fast(std::vector<i64>& sig, const double* r, const double* u, const std::vector<i64>& edge,
+                                const std::vector<i64>& origin, double& t, double* r2) {
+        const double* x0 = X(edge[0]);
+        double c1 = -INF;
+        for (i64 g : sig) c1 = std::max(c1, dot(X(g), u, d));
+        const double c = c1 + std::fabs(c1) * pb.plane_tol;
+        auto skip = [&](i64 i) { return dot(X(i), u, d) <= c; };
+        double vvv[MAXD], _vvv[MAXD], _r[MAXD], a = 0;
+        for (int k = 0; k < d; ++k) a += u[k] * (x0[k] - r[k]);
+        for (int k = 0; k < d; ++k) vvv[k] = r[k] + u[k] * a;                               // :552
+        std::pair<i64, double> res = nn(vvv, skip);
+        t = INF;
+        if (res.first < 0) { std::memcpy(r2, r, sizeof(double) * d); return -1; }
+        double tt = get_t(r, u, x0, X(res.first));                                          // :557
+        for (int k = 0; k < d; ++k) _vvv[k] = r[k] + tt * u[k];
+        tt = get_t(_vvv, u, x0, X(res.first));
+        for (int k = 0; k < d; ++k) vvv[k] = _vvv[k] + tt * u[k];
+        res = nn(vvv, skip);                                                                 // :561
+        if (res.first >= 0) tt = get_t(r, u, x0, X(res.first));
+        for (int k = 0; k < d; ++k) _r[k] = r[k] + tt * u[k];
+        double measure = 0;
+        for (i64 g : sig) measure = std::max(measure, std::sqrt(dist2(X(g), _r, d)));
+        double upper_t = tt + 2 * measure;
+        const double scale = get_scale(u, x0, _r);
+        std::vector<i64> idss;
+        inrange(_r, (1 + std::max(1e-12, pb.b_nodes_tol * 100 * scale)) * measure, idss);   // :573
+        if (idss.empty()) { std::memcpy(r2, r, sizeof(double) * d); return -1; }
+        const i64 MAXI = std::numeric_limits<i64>::max();
+        std::vector<double> ts(idss.size());
+        for (size_t k = 0; k < idss.size(); ++k) {
+            const bool in_origin = std::find(origin.begin(), origin.end(), idss[k]) != origin.end();
+            ts[k] = in_origin ? 0.0 : get_t(r, u, x0, X(idss[k]));                          // :579
+            if (ts[k] < pb.plane_tol) { idss[k] = MAXI; ts[k] = 0.0; }
+            else if (ts[k] < upper_t) upper_t = ts[k];
+        }
+        upper_t += 10e-8;                                                                    // :594
+        double max_dist = 0; i64 generator = -1;
+        for (size_t k = 0; k < idss.size(); ++k) {
+            if (ts[k] > upper_t) ts[k] = 0.0;
+            else if (idss[k] < MAXI) {
+                double v = 0; const double* xk = X(idss[k]);
+                for (int q = 0; q < d; ++q) v += u[q] * (xk[q] - x0[q]);
+                ts[k] = v;
+                if (v > max_dist) { max_dist = v; generator = idss[k]; }
+            }
+        }
+        if (generator < 0) { std::memcpy(r2, r, sizeof(double) * d); return -1; }
+        t = get_t(r, u, x0, X(generator));                                                   // :611
+        for (int k = 0; k < d; ++k) r2[k] = r[k] + t * u[k];
+        // correct_cast(::Raycast_By_Walkray) (:443-447) = walkray_correct_vertex, which walkray applies again to the result
+        double measure2 = std::sqrt(dist2(X(generator), r2, d));
+        for (i64 g : sig) measure2 = std::max(measure2, std::sqrt(dist2(X(g), r2, d)));
+        measure2 *= (1 + 0.1 * pb.b_nodes_tol);                                              // :616
+        const size_t before = sig.size();
+        for (size_t k = 0; k < idss.size(); ++k) {
+            if (idss[k] == MAXI || std::sqrt(dist2(X(idss[k]), r2, d)) > measure2) continue;
+            if (std::find(sig.begin(), sig.end(), idss[k]) == sig.end()) sig.push_back(idss[k]);
+        }
+        if (std::find(sig.begin(), sig.end(), generator) == sig.end()) sig.push_back(generator);
+        if (sig.size() > before + 1) ++stats.degenerate;
+        std::sort(sig.begin(), sig.end());
+        return generator;
+    }
+
     i64 raycast(std::vector<i64>& sig, const double* r, const double* u, const std::vector<i64>& edge,
                 const std::vector<i64>& origin, double& t, double* r2) {
         ++stats.raycasts;
+        if (pb.method == 1) return raycast_original(sig, r, u, edge, t, r2);
+        if (pb.method == 3) return raycast_nongeneral_fast(sig, r, u, edge, origin, t, r2);
         const double* x0 = X(edge[0]);
         double c1 = -INF;
         for (i64 g : sig) c1 = std::max(c1, dot(X(g), u, d));             // :802-804
@@ -723,13 +840,20 @@ extern "C" {
 // Runs voronoi(mesh; searcher=Raycast(xs; domain)) (sysvoronoi.jl:21-39,152-215).
 // nthreads == 1: SingleThread path (:41).  nthreads > 1: MultiThread(nthreads,1) path (:50-82):
 // contiguous index slabs (parallelmesh.jl:52-87), one searcher per thread, one shared store.
+static int g_method = 0;
+// search_settings = (method = ...,) of the next hvo_run calls: 0 default (RCNonGeneralHP), 1 RCOriginal, 3 RCNonGeneralFast
+int hvo_set_method(int method) {
+    if (method != 0 && method != 1 && method != 3) return -1;
+    g_method = method;
+    return 0;
+}
 void* hvo_run(int dim, int64_t n, const double* xs, int nplanes, const double* plane_base, const double* plane_normal,
               int nthreads, uint64_t seed) {
     Result* res = new Result();
     res->d = dim; res->N = n; res->P = nplanes;
     if (dim < 2 || dim > 6 || n <= dim) { res->error = "not enough points / bad dimension"; return res; }
     Problem pb;
-    pb.d = dim; pb.N = n; pb.P = nplanes;
+    pb.d = dim; pb.N = n; pb.P = nplanes; pb.method = g_method;
     pb.xs.assign(xs, xs + (size_t)n * dim);
     pb.pbase.assign(plane_base, plane_base + (size_t)nplanes * dim);
     pb.pnormal.assign(plane_normal, plane_normal + (size_t)nplanes * dim);

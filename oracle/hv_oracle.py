@@ -34,6 +34,8 @@ def _load():
         L.hvo_run.restype = ctypes.c_void_p
         L.hvo_run.argtypes = [ctypes.c_int, ctypes.c_int64, ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p,
                               ctypes.c_void_p, ctypes.c_int, ctypes.c_uint64]
+        L.hvo_set_method.restype = ctypes.c_int
+        L.hvo_set_method.argtypes = [ctypes.c_int]
         L.hvo_error.restype = ctypes.c_char_p
         L.hvo_error.argtypes = [ctypes.c_void_p]
         for name in ("hvo_counts", "hvo_fetch_vertices", "hvo_fetch_rays", "hvo_fetch_neighbors", "hvo_stats", "hvo_free"):
@@ -52,8 +54,13 @@ def _p(a):
     return a.ctypes.data_as(ctypes.c_void_p)
 
 
-def run(xs, plane_base=None, plane_normal=None, nthreads=1, seed=0):
-    """voronoi(xs; searcher=Raycast(xs; domain)) restated on the CPU.
+METHODS = {"RCNonGeneral": 0, "RCNonGeneralHP": 0, "RCStandard": 0, "RCOriginal": 1, "RCNonGeneralFast": 3}
+
+
+def run(xs, plane_base=None, plane_normal=None, nthreads=1, seed=0, method=0):
+    """voronoi(xs; searcher=Raycast(xs; domain, options=RaycastParameter(method=...))) restated on the CPU.
+
+    method: 0 / "RCNonGeneral" (the default, raycast.jl:794-970), 1 / "RCOriginal" (:972-1012), 3 / "RCNonGeneralFast" (:542-631).
 
     Returns dict(sig[V,d+1] int64 1-based sorted rows in lexicographic order, r[V,d], ray_edge, ray_base,
     ray_dir, ray_node, nb_off[n+1], nb_ids, stats)."""
@@ -65,7 +72,12 @@ def run(xs, plane_base=None, plane_normal=None, nthreads=1, seed=0):
         plane_normal = np.zeros((0, d))
     pb = np.ascontiguousarray(plane_base, dtype=np.float64).reshape(-1, d)
     pn = np.ascontiguousarray(plane_normal, dtype=np.float64).reshape(-1, d)
-    h = L.hvo_run(d, n, _p(xs), pb.shape[0], _p(pb), _p(pn), int(nthreads), int(seed))
+    if L.hvo_set_method(int(METHODS.get(method, method))) != 0:
+        raise ValueError("the restatement has methods 0 (RCNonGeneral), 1 (RCOriginal) and 3 (RCNonGeneralFast)")
+    try:
+        h = L.hvo_run(d, n, _p(xs), pb.shape[0], _p(pb), _p(pn), int(nthreads), int(seed))
+    finally:
+        L.hvo_set_method(0)
     try:
         err = L.hvo_error(h)
         if err:

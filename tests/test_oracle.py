@@ -63,6 +63,31 @@ def test_oracle_multithread_equals_singlethread(oracle):
     assert np.abs(a["r"] - b["r"]).max() < 1e-11
 
 
+# ---- the other search_settings methods restated (raycast.jl:972-1012 RCOriginal, :542-631 RCNonGeneralFast) -----------------
+@pytest.mark.parametrize("method", ["RCOriginal", "RCNonGeneralFast"])
+@pytest.mark.parametrize("d,n", [(2, 1500), (3, 800), (4, 300), (5, 100)])
+def test_oracle_methods_find_the_same_mesh(oracle, method, d, n):
+    """test/rcmethods.jl:10-13 runs the four methods and checks sum(volume) = 1 for each; restated, they return the same
+    vertex set for a cloud in general position -- which is what lets the device map every `method` value onto one exact
+    min-t kernel.  Checked against the default method, against Qhull, bounded and unbounded."""
+    xs = points(n, d, 500 + d)
+    base, normal = qhull_oracle.cuboid(d)
+    a, b = oracle.run(xs, base, normal), oracle.run(xs, base, normal, method=method)
+    assert np.array_equal(a["sig"], b["sig"]) and np.abs(a["r"] - b["r"]).max() < 1e-11
+    assert np.array_equal(a["nb_ids"], b["nb_ids"]) and b["stats"]["degenerate"] == 0
+    assert {tuple(s) for s in b["sig"].tolist()} == set(qhull_oracle.bounded(xs, base, normal))
+    ua, ub = oracle.run(xs), oracle.run(xs, method=method)
+    assert np.array_equal(ua["sig"], ub["sig"])
+    assert sorted(map(tuple, ua["ray_edge"].tolist())) == sorted(map(tuple, ub["ray_edge"].tolist()))
+    # the procedures differ: the default method spends 2.6 nn + 1 inrange per ray (docs/src/index.md:93), these fewer
+    assert b["stats"]["nn_calls"] < a["stats"]["nn_calls"]
+
+
+def test_oracle_refuses_a_method_it_does_not_restate(oracle):
+    with pytest.raises(ValueError):
+        oracle.run(points(50, 3, 1), method=2)          # RCCombined: the nested KD traversal is not restated
+
+
 def test_oracle_rejects_too_few_points(oracle):
     with pytest.raises(RuntimeError):
         oracle.run(np.random.default_rng(0).random((3, 3)))

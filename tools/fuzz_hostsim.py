@@ -290,6 +290,11 @@ def one(seed):
                 continue
             if not abs(vol[i] - ref) <= 1e-7 * ref + 1e-13 * dom:
                 return ("FAIL", tag + " volume of cell %d: %.12e, Qhull %.12e" % (i + 1, vol[i], ref))
+    if seed % 2 == 0:
+        # the FP32 filter may only drop candidates that cannot win: without it the rows are the same, bit for bit
+        s64 = hostsim.run(xs, base, normal, fp32=0, **knobs) if bounded else hostsim.run(xs, fp32=0, **knobs)
+        if not (np.array_equal(s64["sig"], s["sig"]) and np.array_equal(s64["r"], s["r"]) and np.array_equal(s64["ray_edge"], s["ray_edge"])):
+            return ("FAIL", tag + " FP32 filter changes the result")
     # coordinates against Qhull's circumcentres, relative to the circumradius
     sig = s["sig"]
     ref = np.array([truth[tuple(r)] for r in sig.tolist()])
