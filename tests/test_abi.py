@@ -94,3 +94,85 @@ def test_struct_layouts_agree_across_header_python_and_julia(hvb):
     jbody = re.search(r"mutable struct HvbParams(.*?)HvbParams\(\) = new\(\)", jl, flags=re.S).group(1)
     jfields = re.findall(r"([a-z_0-9]+)::(?:Cdouble|Int32|Int64)", jbody)
     assert jfields == params
+
+
+# ---- the ccalls of the Julia shim against the C prototypes ---------------------------------------------------------------
+def _split_top(s):
+    """split at commas that are not nested in (), {} or []"""
+    out, depth, cur = [], 0, ""
+    for ch in s:
+        if ch in "({[":
+            depth += 1
+        elif ch in ")}]":
+            depth -= 1
+        if ch == "," and depth == 0:
+            out.append(cur.strip()); cur = ""
+        else:
+            cur += ch
+    if cur.strip():
+        out.append(cur.strip())
+    return out
+
+
+def _balanced(s, start):
+    """the text between the parenthesis at s[start] and its partner"""
+    depth = 0
+    for i in range(start, len(s)):
+        depth += s[i] == "("
+        depth -= s[i] == ")"
+        if depth == 0:
+            return s[start + 1:i]
+    raise ValueError("unbalanced")
+
+
+def c_prototypes():
+    src = open(os.path.join(ROOT, "include", "hvb200.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    protos = {}
+    for m in re.finditer(r"\b(int|void|const char\s*\*)\s+(hvb_[a-z_0-9]+)\s*\(", src):
+        args = _balanced(src, m.end() - 1)
+        protos[m.group(2)] = (m.group(1).replace(" ", ""), [] if args.strip() == "void" else [" ".join(a.split()) for a in _split_top(args)])
+    return protos
+
+
+def c_kind(arg):
+    """pointer class or scalar type of a C parameter declaration"""
+    if "*" in arg:
+        base = arg.replace("const", "").split("*")[0].strip()
+        return "ptr:" + base + ("*" if arg.count("*") > 1 else "")
+    return arg.replace("const", "").split()[0]
+
+
+JL_SCALAR = {"Cint": "int", "Int32": "int", "Int64": "int64_t", "Cdouble": "double", "Float64": "double"}
+JL_POINTEE = {"Cvoid": {"hvb_ctx", "void"}, "Float64": {"double"}, "Int64": {"int64_t"}, "Int32": {"int32_t", "int"}, "UInt8": {"uint8_t"},
+              "HvbParams": {"hvb_params"}, "Ptr{Cvoid}": {"hvb_ctx*"}}
+
+
+def test_every_ccall_of_the_julia_shim_matches_its_c_prototype():
+    """the shim cannot be executed here (no Julia): what CAN be checked is that every ccall names an exported function and
+    passes the number and kinds of arguments the header declares -- the mistakes an unexecuted binding typically carries"""
+    jl = open(os.path.join(ROOT, "julia", "HighVoronoiB200.jl")).read()
+    jl = "\n".join(l.split("#")[0] if not l.lstrip().startswith("#") else "" for l in jl.split("\n"))
+    protos = c_prototypes()
+    seen = set()
+    for m in re.finditer(r"ccall\(", jl):
+        parts = _split_top(_balanced(jl, m.end() - 1))
+        name = re.match(r"\(:(hvb_[a-z_0-9]+),\s*LIB\)", parts[0]).group(1)
+        assert name in protos, name
+        ret, cargs = protos[name]
+        seen.add(name)
+        assert {"int": "Cint", "void": "Cvoid", "constchar*": "Cstring"}[ret] == parts[1], (name, parts[1])
+        types = _split_top(parts[2].strip()[1:-1].rstrip(","))
+        values = parts[3:]
+        assert len(types) == len(cargs) == len(values), (name, types, cargs, values)
+        for jt, ca in zip(types, cargs):
+            ck = c_kind(ca)
+            if jt in JL_SCALAR:
+                assert ck == JL_SCALAR[jt], (name, jt, ca)
+            else:
+                inner = re.match(r"(?:Ptr|Ref)\{(.*)\}$", jt)
+                assert inner and ck.startswith("ptr:"), (name, jt, ca)
+                assert ck[4:] in JL_POINTEE[inner.group(1)], (name, jt, ca)
+    # the entry points the seam needs are all bound
+    assert {"hvb_create", "hvb_create_multi", "hvb_create_periodic", "hvb_set_points", "hvb_search", "hvb_counts", "hvb_fetch_vertices",
+            "hvb_fetch_vertices_var", "hvb_fetch_rays", "hvb_last_error", "hvb_destroy", "hvb_default_params", "hvb_convex_hull"} <= seen
