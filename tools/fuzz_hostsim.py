@@ -318,6 +318,8 @@ def main():
         cnt[res[0]] += 1
         if res[0] == "FAIL":
             print("FAIL", res[1], flush=True)
+        if sum(cnt.values()) % 500 == 0:
+            print("... %s after %.0f s" % (cnt, time.time() - t0), flush=True)
         elif res[0] == "ok" and res[2] > worst[0]:
             worst = (res[2], res[1])
     print("cases: %s; worst relative coordinate difference to Qhull %.2e (%s); next seed %d" % (cnt, worst[0], worst[1], seed))
