@@ -313,9 +313,9 @@ def one(seed):
             e = float(np.linalg.norm(s["r"][k] - ex) / max(np.linalg.norm(ex - x0[k]), 1e-300))
             if e > 1e-10 and not bounded:
                 # a simplex with condition number 1e11 (a vertex 1e10 cloud diameters away): FP64 cannot hold 1e-10 there; the
-                # canonical solve stays near cond * 1e-19, the restated reference near cond * 1e-18
+                # canonical solve and the restated reference both stay below cond * 2^-52
                 A = xs[sig[k][1:] - 1] - xs[sig[k][0] - 1]
-                if e <= 1e-17 * np.linalg.cond(A):
+                if e <= 2.2e-16 * np.linalg.cond(A):
                     continue
             err = max(err, e)
         if err > 1e-10:
