@@ -46,7 +46,7 @@ def cloud(rng, kind, n, d):
 
 
 KINDS = ("uniform", "clusters", "shell", "density", "slab")
-SIZES = {2: (5, 3000), 3: (6, 1500), 4: (7, 500), 5: (8, 160)}
+SIZES = {2: (5, 3000), 3: (6, 1500), 4: (7, 500), 5: (8, 160), 6: (9, 60)}
 
 
 def ball_is_empty(xs, row, planes=None):
@@ -181,7 +181,7 @@ def one(seed):
     if seed % 8 == 5:
         return nongeneral_case(seed)
     rng = np.random.default_rng(seed)
-    d = int(rng.integers(2, 6))
+    d = int(rng.integers(2, 7)) if seed >= 50000000 else int(rng.integers(2, 6))      # d = 6 from seed 5e7 on (earlier seeds reproduce)
     lo, hi = SIZES[d]
     n = int(np.exp(rng.uniform(np.log(lo), np.log(hi))))
     kind = KINDS[int(rng.integers(0, len(KINDS)))]
