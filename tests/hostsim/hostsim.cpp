@@ -503,8 +503,8 @@ void hostsim_counts(void* h, int64_t* nv, int64_t* nr, int64_t* ctr /*12*/) {
 }
 void hostsim_fetch(void* h, int64_t* sig, double* r, int64_t* ray_edge) {
     SimResult* R = (SimResult*)h;
-    memcpy(sig, R->sig.data(), R->sig.size() * 8); memcpy(r, R->r.data(), R->r.size() * 8);
-    memcpy(ray_edge, R->ray_edge.data(), R->ray_edge.size() * 8);
+    if (!R->sig.empty()) { memcpy(sig, R->sig.data(), R->sig.size() * 8); memcpy(r, R->r.data(), R->r.size() * 8); }
+    if (!R->ray_edge.empty()) memcpy(ray_edge, R->ray_edge.data(), R->ray_edge.size() * 8);
 }
 void hostsim_free(void* h) { delete (SimResult*)h; }
 void hostsim_set_trace(int on) { g_want_trace = on != 0; }
