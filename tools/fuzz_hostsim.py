@@ -290,6 +290,34 @@ def one(seed):
                 continue
             if not abs(vol[i] - ref) <= 1e-7 * ref + 1e-13 * dom:
                 return ("FAIL", tag + " volume of cell %d: %.12e, Qhull %.12e" % (i + 1, vol[i], ref))
+    if bounded and d <= 4 and seed % 2 == 1:
+        # interface areas (the formula the device kernel runs) on the same rows: the cone formula vol_i = (1/d) sum_j A_ij h_ij
+        # over the interfaces of a cell (h = distance of the generator to the interface's hyperplane) and A_ij = A_ji
+        from util import neighbors_from_sig
+        off, ids = neighbors_from_sig(s["sig"], n)
+        area = hostsim.areas(xs, s["sig"], off, ids, base, normal)
+        vol = hostsim.volumes(xs, s["sig"], base, normal)
+        cone = np.zeros(n)
+        amap = {}
+        for i in range(n):
+            for q in range(off[i], off[i + 1]):
+                j = int(ids[q])
+                if j <= n:
+                    h = 0.5 * np.linalg.norm(xs[j - 1] - xs[i])
+                    amap[(i + 1, j)] = area[q]
+                else:
+                    h = abs((base[j - n - 1] - xs[i]) @ normal[j - n - 1]) / np.linalg.norm(normal[j - n - 1])
+                cone[i] += area[q] * h / d
+        dom = float(np.prod([base[2 * k, k] - base[2 * k + 1, k] for k in range(d)]))
+        bad = np.abs(cone - vol) > 1e-8 * vol + 1e-13 * dom
+        if bad.any():
+            i = int(np.argmax(np.abs(cone - vol) / np.maximum(vol, 1e-300)))
+            return ("FAIL", tag + " cone formula: cell %d volume %.12e, (1/d) sum A h = %.12e" % (i + 1, vol[i], cone[i]))
+        # (slivers of interfaces 1e-12 of a cell's surface carry the rounding of their neighbours: compared on the scale of the cell)
+        scale = {i + 1: max(vol[i], 1e-300) ** ((d - 1.0) / d) for i in range(n)}
+        asym = max((abs(a - amap.get((j, i), a)) / max(a, 1e-6 * scale[i]) for (i, j), a in amap.items()), default=0.0)
+        if asym > 1e-8:
+            return ("FAIL", tag + " interface areas not symmetric: %.2e" % asym)
     if seed % 2 == 0:
         # the FP32 filter may only drop candidates that cannot win: without it the rows are the same, bit for bit
         s64 = hostsim.run(xs, base, normal, fp32=0, **knobs) if bounded else hostsim.run(xs, fp32=0, **knobs)
