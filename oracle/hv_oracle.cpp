@@ -17,9 +17,10 @@
 // rows in tests/test_hostsim.py::test_cell_volume_formula_matches_qhull and on the GPU result
 // in tests/test_gpu_volumes.py; exact values beyond that invariant stay unpinned.
 //
-// Methods: the default RCNonGeneralHP (raycast.jl:794-970) and, selected with hvo_set_method, RCOriginal (:972-1012) and
-// RCNonGeneralFast (:542-631) -- three of the four that test/rcmethods.jl:10-13 runs; RCCombined's nested KD traversal
-// (extended.jl:155-176, kd_tree.jl:210-336) is not restated.  tests/test_oracle.py checks that they return the same mesh.
+// Methods: the default RCNonGeneralHP (raycast.jl:794-970) and, selected with hvo_set_method, RCOriginal (:972-1012),
+// RCCombined (:504-528 with the nested KD traversal of extended.jl:155-176, kd_tree.jl:210-336, searchtrees.jl:50-194) and
+// RCNonGeneralFast (:542-631) -- the four that test/rcmethods.jl:10-13 runs.  tests/test_oracle.py checks that they return the
+// same mesh.
 //
 // Every function cites the reference file:line (relative to /root/reference/src) it follows.
 // Deviations from the reference, all irrelevant for general-position input:
@@ -88,6 +89,7 @@ struct SigHash {
 // :683-743 (inrange kernel), tree_ops.jl:134-154,183-195 (leaf scans).
 // ---------------------------------------------------------------------------------------------
 struct KDTree {
+    static const int MAXD_ = 6;
     int d = 0;
     i64 n = 0;
     static const int LEAF = 10;                 // kd_tree.jl:29 leafsize = 10
@@ -167,6 +169,68 @@ struct KDTree {
         if (n > 0) nn_rec(0, p, min_dist2_box(p), best, best_d2, skip, visits);
         return std::make_pair(best, best < 0 ? INF : std::sqrt(best_d2));
     }
+    // kd_tree.jl:210-336 _knn_flex / knn_kernel_flex!: the nested traversal of RCCombined.  `data` is the NNSearchData of
+    // searchtrees.jl:50-108 (see CombinedData below); a leaf that improves the candidate moves the query point and ends the pass
+    // (returns false), the next pass skips the nodes already marked.
+    template <class Data>
+    bool flex_rec(i64 ni, double min_d2, Data& dt, i64& visits) const {
+        const Node& nd = nodes[ni];
+        if (nd.left < 0) {
+            double old_r[MAXD_];
+            std::memcpy(old_r, dt.new_r, sizeof(double) * d);
+            dt.visited_nodes[ni] = 1;
+            for (i64 i = nd.lo_i; i < nd.hi_i; ++i) {                 // tree_ops.jl:113-128 add_points_knn_flex!
+                ++visits;
+                const double dd = dist2(&pts[i * d], dt.new_r, d);
+                const double correction = dt.dist_new_r_x0_2 * 1000 * dt.plane_tol;
+                if (dd <= dt.dist_new_r_x0_2 + correction) dt.offer(&pts[i * d], idx[i], dd);
+            }
+            if (std::memcmp(old_r, dt.new_r, sizeof(double) * d) != 0) {
+                std::memcpy(dt.r, dt.new_r, sizeof(double) * d);
+                dt.bestdist = dist2(dt.x0, dt.new_r, d) * (1 + 1000 * dt.plane_tol);
+                dt.dist_r_x0_2 = dt.bestdist;
+                return false;
+            }
+            return true;
+        }
+        const int sd = nd.split_dim;
+        const double pd = dt.r[sd], sdiff = pd - nd.split_val;
+        i64 close, far; double ddiff; bool right;
+        if (sdiff > 0) { close = nd.right; far = nd.left; ddiff = std::max(0.0, pd - nd.hi); right = true; }
+        else { close = nd.left; far = nd.right; ddiff = std::max(0.0, nd.lo - pd); right = false; }
+        auto valid_leaf = [&](bool rgt, double& old_val) {            // kd_tree.jl:241-267 switch_leaf / valid_leaf
+            double& slot = rgt ? dt.mins[sd] : dt.maxs[sd];
+            old_val = slot; slot = nd.split_val;
+            double max_dot = 0;
+            for (int k = 0; k < d; ++k) max_dot += (dt.u[k] > 0 ? dt.maxs[k] : dt.mins[k]) * dt.u[k];
+            return max_dot > dt.c;
+        };
+        double old_val;
+        bool valid = valid_leaf(right, old_val);
+        if (!valid) dt.visited_nodes[close] = 1;
+        if (!dt.visited_nodes[close]) {
+            if (!flex_rec(close, min_d2, dt, visits)) return false;
+        }
+        (right ? dt.mins[sd] : dt.maxs[sd]) = old_val;
+        const double new_min = min_d2 + sdiff * sdiff - ddiff * ddiff;
+        valid = valid_leaf(!right, old_val);
+        if (!valid) dt.visited_nodes[far] = 1;
+        if (new_min < dt.bestdist && !dt.visited_nodes[far]) {
+            if (!flex_rec(far, new_min, dt, visits)) return false;
+        }
+        (!right ? dt.mins[sd] : dt.maxs[sd]) = old_val;
+        dt.visited_nodes[ni] = 1;
+        return true;
+    }
+    template <class Data>
+    void knn_flex(Data& dt, i64& visits) const {
+        dt.visited_nodes.assign(nodes.size(), 0);
+        const double init_min = min_dist2_box(dt.r);
+        for (;;) {
+            for (int k = 0; k < d; ++k) { dt.mins[k] = bmin[k]; dt.maxs[k] = bmax[k]; }
+            if (n == 0 || flex_rec(0, init_min, dt, visits)) break;
+        }
+    }
     void inrange_rec(i64 ni, const double* p, double r2, double min_d2, std::vector<i64>& out, i64& visits) const {
         if (min_d2 > r2) return;                                     // kd_tree.jl:700-703
         const Node& nd = nodes[ni];
@@ -204,7 +268,7 @@ struct Problem {
     std::vector<double> pbase, pnormal;         // P*d
     KDTree tree;
     double variance_tol = 1e-15, break_tol = 1e-5, b_nodes_tol = 1e-7, plane_tol = 1e-12;   // raycast-types.jl:226-230
-    // search_settings = (method = ...,): 0 RCNonGeneralHP (RCStandard), 1 RCOriginal, 3 RCNonGeneralFast -- the numbering of
+    // search_settings = (method = ...,): 0 RCNonGeneralHP (RCStandard), 1 RCOriginal, 2 RCCombined, 3 RCNonGeneralFast -- the numbering of
     // hvb_params.method (include/hvb200.h)
     int method = 0;
 };
@@ -438,6 +502,86 @@ struct Searcher {
         return (dist2(r, xn, d) - dist2(r, x0, d)) / (2 * den);
     }
 
+    // searchtrees.jl:50-108 NNSearchData / reset! and :125-194 skip_nodes_on_search: the state of RCCombined's nested search
+    struct CombinedData {
+        int d; double plane_tol;
+        std::vector<i64> sigma, taboo;
+        double bestdist; i64 bestnode;
+        double c, main_c, current_c, dist_r_x0_2, dist_new_r_x0_2;
+        double u[MAXD], r[MAXD], x0[MAXD], new_r[MAXD], mins[MAXD], maxs[MAXD];
+        i64 lt, visited;
+        std::vector<char> visited_nodes;
+        void offer(const double* x_new, i64 i, double dist) {           // skip_nodes_on_search
+            if (visited < lt && std::binary_search(taboo.begin(), taboo.end(), i)) { ++visited; return; }
+            const double dn = dist_new_r_x0_2, correction = dn * 10 * plane_tol;
+            if (dist > dn + correction) return;                           // by no means a better candidate
+            double c_new = 0, abs_dx = 0;
+            for (int k = 0; k < d; ++k) { c_new += x_new[k] * u[k]; abs_dx += (x_new[k] - x0[k]) * (x_new[k] - x0[k]); }
+            if (c_new <= c) return;                                       // original raycast exclusion principle
+            if (std::fabs(dist - dn) < correction) {                      // as good as the current candidate
+                if (abs_dx / dist < 100 * correction) return;
+                sigma.push_back(i);
+                if (c_new > current_c) { bestnode = i; current_c = c_new; }
+                return;
+            }
+            double rx2 = 0;
+            for (int k = 0; k < d; ++k) rx2 += (r[k] - x_new[k]) * (r[k] - x_new[k]);
+            const double new_t = (rx2 - dist_r_x0_2) / (2 * (c_new - main_c));
+            if (abs_dx / (new_t * new_t) < plane_tol) return;
+            double nr[MAXD], a = 0, b = 0, den = 0;
+            for (int k = 0; k < d; ++k) nr[k] = r[k] + new_t * u[k];
+            for (int k = 0; k < d; ++k) { a += (nr[k] - x_new[k]) * (nr[k] - x_new[k]); b += (nr[k] - x0[k]) * (nr[k] - x0[k]); den += u[k] * (x_new[k] - x0[k]); }
+            const double t2 = (a - b) / (2 * den);                        // second order correction: get_t(new_r, u, x0, x_new)
+            double dr = 0, dx0 = 0;
+            for (int k = 0; k < d; ++k) { nr[k] += t2 * u[k]; new_r[k] = nr[k]; dr += (r[k] - nr[k]) * (r[k] - nr[k]); dx0 += (nr[k] - x0[k]) * (nr[k] - x0[k]); }
+            dist_new_r_x0_2 = dx0;
+            bestdist = (std::sqrt(dr) + std::sqrt(dx0)) * (std::sqrt(dr) + std::sqrt(dx0)) * (1 + 10000 * plane_tol);
+            bestnode = i; current_c = c_new;
+            sigma.assign(1, i);
+        }
+    };
+
+    // raycast.jl:504-528 raycast_des2(::Raycast_Combined) with search_vertex2 (extended.jl:155-176): ONE nested traversal of the
+    // tree in which every point inside the current candidate ball either replaces the candidate (the ball shrinks, the query
+    // point moves to the new centre and the traversal restarts) or joins it (a tie).  The reference returns the dummy t = 1.0.
+    i64 raycast_combined(std::vector<i64>& sig, const double* old_r, const double* u, const std::vector<i64>& edge,
+                         const std::vector<i64>& origin, double& t, double* r2) {
+        const double* x0 = X(edge[0]);
+        CombinedData dt;
+        dt.d = d; dt.plane_tol = pb.plane_tol;
+        double a = 0, rr[MAXD];
+        for (int k = 0; k < d; ++k) a += u[k] * (x0[k] - old_r[k]);
+        for (int k = 0; k < d; ++k) rr[k] = old_r[k] + u[k] * a;                             // :508
+        a = 0;
+        for (int k = 0; k < d; ++k) a += u[k] * (x0[k] - rr[k]);
+        for (int k = 0; k < d; ++k) rr[k] += u[k] * a;                                       // :509
+        dt.taboo = origin; std::sort(dt.taboo.begin(), dt.taboo.end());                      // reset!(data, origin, r, x0, u, ...)
+        dt.lt = (i64)dt.taboo.size(); dt.visited = 0;
+        dt.bestdist = INF; dt.bestnode = -1;
+        double c1 = -INF;
+        for (i64 g : origin) c1 = std::max(c1, dot(X(g), u, d));
+        dt.c = c1 + std::fabs(c1) * pb.plane_tol;
+        dt.main_c = dot(x0, u, d); dt.current_c = dt.main_c;
+        dt.dist_r_x0_2 = dist2(rr, x0, d); dt.dist_new_r_x0_2 = INF;
+        for (int k = 0; k < d; ++k) { dt.u[k] = u[k]; dt.r[k] = rr[k]; dt.new_r[k] = rr[k]; dt.x0[k] = x0[k]; }
+        for (int m = 0; m < P; ++m) {                                                        // search_vertex2: the mirrors first
+            if (!active[m]) continue;
+            dt.offer(&mirror[m * d], N + m, dist2(dt.new_r, &mirror[m * d], d));
+        }
+        ++stats.nn_calls;
+        pb.tree.knn_flex(dt, stats.points_visited);
+        t = INF;
+        if (dt.bestnode < 0) { std::memcpy(r2, old_r, sizeof(double) * d); return -1; }
+        const size_t before = sig.size();
+        for (i64 g : dt.sigma) sig.push_back(g);
+        std::sort(sig.begin(), sig.end());
+        sig.erase(std::unique(sig.begin(), sig.end()), sig.end());
+        if (sig.size() > before + 1) ++stats.degenerate;
+        std::memcpy(r2, dt.new_r, sizeof(double) * d);
+        t = 1.0;                                                                             // :517
+        return dt.bestnode;
+    }
+
     // raycast.jl:972-1012 raycast_des2(::Raycast_Original): the classic incircle iteration -- nearest neighbour of the foot
     // point under the half-space predicate, then nearest neighbours of r + t u WITHOUT predicate until the answer is a
     // generator of the edge or repeats.  General position only (one generator is appended).  `full_mode` (correct_cast on
@@ -543,6 +687,7 @@ struct Searcher {
                 const std::vector<i64>& origin, double& t, double* r2) {
         ++stats.raycasts;
         if (pb.method == 1) return raycast_original(sig, r, u, edge, t, r2);
+        if (pb.method == 2) return raycast_combined(sig, r, u, edge, origin, t, r2);
         if (pb.method == 3) return raycast_nongeneral_fast(sig, r, u, edge, origin, t, r2);
         const double* x0 = X(edge[0]);
         double c1 = -INF;
@@ -841,9 +986,9 @@ extern "C" {
 // nthreads == 1: SingleThread path (:41).  nthreads > 1: MultiThread(nthreads,1) path (:50-82):
 // contiguous index slabs (parallelmesh.jl:52-87), one searcher per thread, one shared store.
 static int g_method = 0;
-// search_settings = (method = ...,) of the next hvo_run calls: 0 default (RCNonGeneralHP), 1 RCOriginal, 3 RCNonGeneralFast
+// search_settings = (method = ...,) of the next hvo_run calls: 0 default (RCNonGeneralHP), 1 RCOriginal, 2 RCCombined, 3 RCNonGeneralFast
 int hvo_set_method(int method) {
-    if (method != 0 && method != 1 && method != 3) return -1;
+    if (method < 0 || method > 3) return -1;
     g_method = method;
     return 0;
 }

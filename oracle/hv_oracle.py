@@ -54,13 +54,14 @@ def _p(a):
     return a.ctypes.data_as(ctypes.c_void_p)
 
 
-METHODS = {"RCNonGeneral": 0, "RCNonGeneralHP": 0, "RCStandard": 0, "RCOriginal": 1, "RCNonGeneralFast": 3}
+METHODS = {"RCNonGeneral": 0, "RCNonGeneralHP": 0, "RCStandard": 0, "RCOriginal": 1, "RCCombined": 2, "RCNonGeneralFast": 3}
 
 
 def run(xs, plane_base=None, plane_normal=None, nthreads=1, seed=0, method=0):
     """voronoi(xs; searcher=Raycast(xs; domain, options=RaycastParameter(method=...))) restated on the CPU.
 
-    method: 0 / "RCNonGeneral" (the default, raycast.jl:794-970), 1 / "RCOriginal" (:972-1012), 3 / "RCNonGeneralFast" (:542-631).
+    method: 0 / "RCNonGeneral" (the default, raycast.jl:794-970), 1 / "RCOriginal" (:972-1012), 2 / "RCCombined" (:504-528),
+    3 / "RCNonGeneralFast" (:542-631) -- the four methods of test/rcmethods.jl.
 
     Returns dict(sig[V,d+1] int64 1-based sorted rows in lexicographic order, r[V,d], ray_edge, ray_base,
     ray_dir, ray_node, nb_off[n+1], nb_ids, stats)."""
@@ -73,7 +74,7 @@ def run(xs, plane_base=None, plane_normal=None, nthreads=1, seed=0, method=0):
     pb = np.ascontiguousarray(plane_base, dtype=np.float64).reshape(-1, d)
     pn = np.ascontiguousarray(plane_normal, dtype=np.float64).reshape(-1, d)
     if L.hvo_set_method(int(METHODS.get(method, method))) != 0:
-        raise ValueError("the restatement has methods 0 (RCNonGeneral), 1 (RCOriginal) and 3 (RCNonGeneralFast)")
+        raise ValueError("the restatement has methods 0 (RCNonGeneral), 1 (RCOriginal), 2 (RCCombined) and 3 (RCNonGeneralFast)")
     try:
         h = L.hvo_run(d, n, _p(xs), pb.shape[0], _p(pb), _p(pn), int(nthreads), int(seed))
     finally:

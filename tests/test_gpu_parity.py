@@ -276,8 +276,8 @@ def test_config_size_matches_oracle(hvb, oracle, d, n):
 def test_rcmethods(hvb, oracle, method):
     xs = points(1000, 4, 99)
     base, normal = qhull_oracle.cuboid(4)
-    # against the same method of the restated reference where it restates it (RCOriginal, RCNonGeneralFast), else the default
-    o = oracle.run(xs, base, normal, method=method if method in ("RCOriginal", "RCNonGeneralFast") else 0)
+    # against the same method of the restated reference where it restates it (the four of test/rcmethods.jl), else the default
+    o = oracle.run(xs, base, normal, method=method if method in oracle.METHODS else 0)
     mesh, s = run_gpu(hvb, xs, True, method=getattr(hvb, method))
     assert s.parameters.method == getattr(hvb, method)
     assert_same_mesh(mesh.sig, mesh.r, o["sig"], o["r"], xs, COORD_TOL)     # the winner does not depend on the procedure

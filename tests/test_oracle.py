@@ -63,8 +63,8 @@ def test_oracle_multithread_equals_singlethread(oracle):
     assert np.abs(a["r"] - b["r"]).max() < 1e-11
 
 
-# ---- the other search_settings methods restated (raycast.jl:972-1012 RCOriginal, :542-631 RCNonGeneralFast) -----------------
-@pytest.mark.parametrize("method", ["RCOriginal", "RCNonGeneralFast"])
+# ---- the other search_settings methods restated (raycast.jl:972-1012 RCOriginal, :504-528 RCCombined, :542-631 RCNonGeneralFast)
+@pytest.mark.parametrize("method", ["RCOriginal", "RCCombined", "RCNonGeneralFast"])
 @pytest.mark.parametrize("d,n", [(2, 1500), (3, 800), (4, 300), (5, 100)])
 def test_oracle_methods_find_the_same_mesh(oracle, method, d, n):
     """test/rcmethods.jl:10-13 runs the four methods and checks sum(volume) = 1 for each; restated, they return the same
@@ -85,7 +85,7 @@ def test_oracle_methods_find_the_same_mesh(oracle, method, d, n):
 
 def test_oracle_refuses_a_method_it_does_not_restate(oracle):
     with pytest.raises(ValueError):
-        oracle.run(points(50, 3, 1), method=2)          # RCCombined: the nested KD traversal is not restated
+        oracle.run(points(50, 3, 1), method=6)          # RCOriginalHP (hull walks only) is not restated
 
 
 def test_oracle_rejects_too_few_points(oracle):
