@@ -9,6 +9,8 @@
 #include <algorithm>
 // per-ray trace of the query (kind: 0 ray, 1 row test, 2 row scanned with val points, 3 stage with val rows, 4 FP32 survivor)
 static std::vector<int>* g_trace = nullptr;
+// Iter subset / slab of a multi-GPU run: cells (caller order) the next run explores; empty = all (hostsim_set_active)
+static std::vector<unsigned char> g_active;
 static bool g_want_trace = false;
 #define HVB_TRACE_EVENT(kind, val) do { if (g_trace) { g_trace->push_back(kind); g_trace->push_back((int)(val)); } } while (0)
 #include "../../highvoronoi.jl_b200/csrc/hvb_host.hpp"
@@ -57,6 +59,7 @@ static SimResult* run(int64_t n, const double* xs, int P, const double* base, co
         ps.off[p] = off;
     }
     std::vector<unsigned char> active(n, 1), hasv(n, 0);
+    if ((int64_t)g_active.size() == n) for (int64_t i = 0; i < n; ++i) active[i] = g_active[perm[i]];   // grid order
     std::vector<double> xcan;
     if (xs_canon) { xcan.resize(n * D); for (int64_t i = 0; i < n; ++i) for (int k = 0; k < D; ++k) xcan[i * D + k] = xs_canon[(int64_t)perm[i] * D + k]; }
     dv.cell_start = cstart.data(); dv.x32 = x32.data(); dv.x64 = x64.data(); dv.xcan = xs_canon ? xcan.data() : x64.data(); dv.planes = &ps; dv.active = active.data();
@@ -89,6 +92,7 @@ static SimResult* run(int64_t n, const double* xs, int P, const double* base, co
     if (watch_all) g_trace = &trace_buf;
     for (int64_t i = 0; i < n; i += seed_stride) {
         const u32 v_before = vcount;
+        if (!active[i]) continue;                          // k_seed: descents start from cells this context explores
         seed_item<D, TileHost>(dv, tile, (int)i, qa.data(), &na, qcap, ls);
         if (watch_all && vcount > v_before) {
             fprintf(stderr, "[seed] start %lld -> (", (long long)perm[i] + 1);
@@ -132,7 +136,7 @@ static SimResult* run(int64_t n, const double* xs, int P, const double* base, co
             qa.swap(qb); na = nb; ++rounds;
         }
         // cells without any vertex get their own descent (sysvoronoi.jl:416-429)
-        for (int64_t i = 0; i < n; ++i) if (!hasv[i]) seed_item<D, TileHost>(dv, tile, (int)i, qa.data(), &na, qcap, ls);
+        for (int64_t i = 0; i < n; ++i) if (active[i] && !hasv[i]) seed_item<D, TileHost>(dv, tile, (int)i, qa.data(), &na, qcap, ls);
         if (na == 0) break;
     }
     g_trace = nullptr;
@@ -508,6 +512,7 @@ void hostsim_fetch(void* h, int64_t* sig, double* r, int64_t* ray_edge) {
 }
 void hostsim_free(void* h) { delete (SimResult*)h; }
 void hostsim_set_trace(int on) { g_want_trace = on != 0; }
+void hostsim_set_active(int64_t n, const unsigned char* active) { g_active.assign(active, active + (active ? n : 0)); }
 int64_t hostsim_trace_size(void* h) { return (int64_t)((SimResult*)h)->trace.size(); }
 void hostsim_trace_fetch(void* h, int* out) { SimResult* R = (SimResult*)h; memcpy(out, R->trace.data(), R->trace.size() * sizeof(int)); }
 

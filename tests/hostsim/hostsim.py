@@ -21,9 +21,18 @@ def build():
     return _SO
 
 
-def run(xs, base=None, normal=None, ppc=0, probe_scale=0.0, fp32=1, seed_stride=0, trace=False):
+def run(xs, base=None, normal=None, ppc=0, probe_scale=0.0, fp32=1, seed_stride=0, trace=False, cells=None):
+    """cells: 1-based ids of the cells to explore (Iter / the slab of a rank); None = all"""
     L = ctypes.CDLL(build())
     L.hostsim_set_trace(1 if trace else 0)
+    L.hostsim_set_active.restype = None
+    L.hostsim_set_active.argtypes = [ctypes.c_int64, ctypes.c_void_p]
+    if cells is None:
+        L.hostsim_set_active(0, None)
+    else:
+        act = np.zeros(len(xs), dtype=np.uint8)
+        act[np.asarray(cells, dtype=np.int64) - 1] = 1
+        L.hostsim_set_active(len(act), act.ctypes.data_as(ctypes.c_void_p))
     L.hostsim_run.restype = ctypes.c_void_p
     L.hostsim_run.argtypes = [ctypes.c_int, ctypes.c_int64, ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p,
                               ctypes.c_int, ctypes.c_double, ctypes.c_int, ctypes.c_int]
@@ -56,6 +65,7 @@ def run(xs, base=None, normal=None, ppc=0, probe_scale=0.0, fp32=1, seed_stride=
         out["trace"] = tr.reshape(-1, 2)
     L.hostsim_free(h)
     L.hostsim_set_trace(0)
+    L.hostsim_set_active(0, None)
     return out
 
 

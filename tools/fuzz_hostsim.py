@@ -313,11 +313,31 @@ def one(seed):
         if bad.any():
             i = int(np.argmax(np.abs(cone - vol) / np.maximum(vol, 1e-300)))
             return ("FAIL", tag + " cone formula: cell %d volume %.12e, (1/d) sum A h = %.12e" % (i + 1, vol[i], cone[i]))
-        # (slivers of interfaces 1e-12 of a cell's surface carry the rounding of their neighbours: compared on the scale of the cell)
-        scale = {i + 1: max(vol[i], 1e-300) ** ((d - 1.0) / d) for i in range(n)}
-        asym = max((abs(a - amap.get((j, i), a)) / max(a, 1e-6 * scale[i]) for (i, j), a in amap.items()), default=0.0)
+        # (an interface that is 1e-9 of a cell's surface carries the rounding of the cell's other flags: compared on that scale)
+        surf = {i + 1: float(area[off[i]:off[i + 1]].sum()) for i in range(n)}
+        asym = max((abs(a - amap.get((j, i), a)) / (a + 1e-4 * max(surf[i], surf[j])) for (i, j), a in amap.items()), default=0.0)
         if asym > 1e-8:
             return ("FAIL", tag + " interface areas not symmetric: %.2e" % asym)
+    if seed % 4 == 1:
+        # Iter subsets / the slab of a rank (the `active` set of the walk): exploring a subset of the cells returns every vertex
+        # that touches one of them and nothing that is not a vertex of the full mesh; the slabs' union is the full mesh
+        full = got
+        k = int(rng.integers(1, 5))
+        order = np.argsort(xs[:, int(rng.integers(0, d))]) if rng.integers(0, 2) else rng.permutation(n)
+        union = set()
+        for part in np.array_split(order, k):
+            if len(part) == 0:
+                continue
+            cells = part + 1
+            sp = hostsim.run(xs, base, normal, cells=cells, **knobs) if bounded else hostsim.run(xs, cells=cells, **knobs)
+            gp = {tuple(r) for r in sp["sig"].tolist()}
+            cs = set(int(c) for c in cells)
+            need = {r for r in full if any(g in cs for g in r)}
+            if not (need <= gp <= full) or sp["stats"]["seed_fail"]:
+                return ("FAIL", tag + " Iter subset of %d cells: missing=%d extra=%d" % (len(cells), len(need - gp), len(gp - full)))
+            union |= gp
+        if union != full:
+            return ("FAIL", tag + " union of %d slabs misses %d vertices" % (k, len(full - union)))
     if seed % 2 == 0:
         # the FP32 filter may only drop candidates that cannot win: without it the rows are the same, bit for bit
         s64 = hostsim.run(xs, base, normal, fp32=0, **knobs) if bounded else hostsim.run(xs, fp32=0, **knobs)
