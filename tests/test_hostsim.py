@@ -75,6 +75,24 @@ def test_walks_from_vertices_1e7_diameters_away(key):
     assert s["stats"]["degenerate"] == 0 and s["stats"]["seed_fail"] == 0
 
 
+@pytest.mark.parametrize("d,n,world", [(2, 2000, 4), (3, 1500, 8), (4, 400, 3)])
+def test_iter_subsets_and_slab_union_on_the_host(oracle, d, n, world):
+    """the `active` set of the walk (Iter of voronoi(), the slab of a rank; parallelmesh.jl:52-87): exploring a subset of the
+    cells returns every vertex that touches one of them and only vertices of the full mesh; the union over the slabs is the
+    full mesh (the CPU counterpart of test_gpu_parity.py::test_iter_subset... / test_slab_union_equals_full)"""
+    xs = points(n, d, 600 + d)
+    base, normal = qhull_oracle.cuboid(d)
+    full = {tuple(r) for r in oracle.run(xs, base, normal)["sig"].tolist()}
+    union = set()
+    for part in np.array_split(np.argsort(xs[:, 0]), world):
+        cells = part + 1
+        got = {tuple(r) for r in hostsim.run(xs, base, normal, cells=cells)["sig"].tolist()}
+        cs = set(cells.tolist())
+        assert {r for r in full if cs & set(r)} <= got <= full
+        union |= got
+    assert union == full
+
+
 # ---- geometry product: the volume formula of hvb_geometry.cuh on the host, against Qhull ---------------------------
 @pytest.mark.parametrize("d,n", [(2, 400), (3, 300), (4, 120), (5, 50)])
 def test_cell_volume_formula_matches_qhull(d, n):
