@@ -43,7 +43,9 @@ static SimResult* run(int64_t n, const double* xs, int P, const double* base, co
     for (int k = 0; k < D; ++k) { blo[k] = 1e300; bhi[k] = -1e300; }
     for (int64_t i = 0; i < n; ++i)
         for (int k = 0; k < D; ++k) { blo[k] = std::min(blo[k], xs[i * D + k]); bhi[k] = std::max(bhi[k], xs[i * D + k]); }
-    int64_t ncell = setup_grid<D>(dv, blo, bhi, n, ppc > 0 ? ppc : default_points_per_cell(D));
+    // HOSTSIM_CELLS_MULT: experiments with finer grids than one cell per `ppc` points (clustered clouds)
+    const double cells_mult = getenv("HOSTSIM_CELLS_MULT") ? atof(getenv("HOSTSIM_CELLS_MULT")) : 1.0;
+    int64_t ncell = setup_grid<D>(dv, blo, bhi, (int64_t)(n * cells_mult), ppc > 0 ? ppc : default_points_per_cell(D));
     std::vector<int> cell(n), cstart(ncell + 1, 0), perm(n);
     for (int64_t i = 0; i < n; ++i) { cell[i] = cell_index<D>(dv, xs + i * D); cstart[cell[i] + 1]++; }
     for (int64_t c = 0; c < ncell; ++c) cstart[c + 1] += cstart[c];
