@@ -145,12 +145,13 @@ function context_for(searcher, xs::Vector{P}, threading::B200Thread) where {P}
 end
 
 # the vertices a mesh already holds (refinement callers pass a non-empty mesh, meshrefine.jl:199-215): every vertex once,
-# at its owner cell sig[1] (abstractmesh.jl:111-125); plane ids in the external numbering n+p
+# through the iterator over the vertices stored primarily at a cell, in external numbering (all_vertices_iterator,
+# abstractmesh.jl:176,183-187 -- a view may permute the ids, so "sig[1] == i" is not a test for the owner cell; the library
+# orders every seed row itself); plane ids in the external numbering n+p
 function known_vertices(mesh, n::Int, d::Int)
     sigs = Int64[]; rs = Float64[]
     for i in 1:n
-        for (sig, r) in HighVoronoi.vertices_iterator(mesh, i)
-            sig[1] == i || continue
+        for (sig, r) in HighVoronoi.all_vertices_iterator(mesh, i)
             length(sig) == d + 1 || error("HighVoronoiB200: the mesh holds a non-general vertex (more than dim+1 generators): not supported by the device search")
             append!(sigs, sig); append!(rs, r)
         end
