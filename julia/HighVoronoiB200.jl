@@ -175,7 +175,9 @@ function _voronoi(mesh::AM, TODO, compact, v_offset, silence, iteration_reset, p
     c = context_for(searcher, xs, threading)
     cells = Int64.(collect(TODO))                 # Iter (1-based)
     all_cells = length(cells) == n
-    ksig, kr = all_cells && iteration_reset ? (Matrix{Int64}(undef, d + 1, 0), Matrix{Float64}(undef, d, 0)) : known_vertices(mesh, n, d)
+    # `iteration_reset` only steers the progress output (sysvoronoi.jl:171-204), it says nothing about the mesh: whether the mesh
+    # already holds vertices is read off the mesh itself (n empty iterators for a fresh one)
+    ksig, kr = known_vertices(mesh, n, d)
     nk = size(ksig, 2)
     if threading.ngpus > 1 && (!all_cells || nk > 0)
         error("HighVoronoiB200: Iter subsets / meshes that already hold vertices run on one GPU: use B200Thread() for refinement")
