@@ -490,22 +490,126 @@ class VoronoiGeometry:
         self.domain = b
 
 
-class VoronoiData:
-    """VoronoiData(VG; getvertices, getneighbors, getvolume) (voronoidata.jl:545-703): vertex / neighbour / volume fields."""
+def _split(a, off, n):
+    return [a[off[i]:off[i + 1]] for i in range(n)]
 
-    def __init__(self, VG, getvertices=False, getneighbors=False, getvolume=False, getarea=False, **_ignored):
+
+def orientations_of(xs, off, ids, n_user, halo_xs, base, normal):
+    """`orientations` of VoronoiData (voronoidata.jl:593-594): for every neighbour ids[k] of cell i the vector from generator i
+    to that neighbour -- the generator itself, the periodic IMAGE the cell really touches (halo ids n_user+1..n_user+n_halo: the
+    case the reference's docstring calls tricky by hand), or the mirror image of x_i behind a boundary plane (reflect,
+    boundary.jl:206-211) -- so that x_i + orientation / 2 lies on the interface (voronoidata.jl:788).  [m, d], aligned with ids."""
+    xs = np.asarray(xs)
+    ids = np.asarray(ids, dtype=np.int64)
+    off = np.asarray(off, dtype=np.int64)
+    d = xs.shape[1]
+    n_halo = 0 if halo_xs is None else len(halo_xs)
+    cell = np.repeat(np.arange(n_user), np.diff(off[:n_user + 1]))
+    ids = ids[off[0]:off[n_user]]
+    x0 = xs[cell]
+    out = np.empty((ids.shape[0], d))
+    g = ids <= n_user
+    out[g] = xs[ids[g] - 1] - x0[g]
+    h = (ids > n_user) & (ids <= n_user + n_halo)
+    if h.any():
+        out[h] = np.asarray(halo_xs)[ids[h] - n_user - 1] - x0[h]
+    pl = ids > n_user + n_halo
+    if pl.any():
+        p = ids[pl] - n_user - n_halo - 1
+        nrm = np.asarray(normal)[p]
+        nrm = nrm / np.linalg.norm(nrm, axis=1, keepdims=True)
+        dist = ((np.asarray(base)[p] - x0[pl]) * nrm).sum(1)
+        out[pl] = 2.0 * dist[:, None] * nrm
+    return out
+
+
+def boundary_nodes_of(xs, off, ids, n_user, n_halo, base, normal, onboundary=False):
+    """`boundary_nodes` of VoronoiData (voronoidata.jl:596-598): {i: {p: mirrored generator i}} for every cell i (1-based) that
+    touches boundary plane p (1-based); onboundary=True gives the projection of x_i onto the plane instead."""
+    ori = orientations_of(xs, off, ids, n_user, np.zeros((n_halo, np.asarray(xs).shape[1])), base, normal)
+    out = {}
+    ids = np.asarray(ids, dtype=np.int64)
+    for i in range(n_user):
+        for k in range(int(off[i]), int(off[i + 1])):
+            if ids[k] > n_user + n_halo:
+                out.setdefault(i + 1, {})[int(ids[k] - n_user - n_halo)] = np.asarray(xs)[i] + (0.5 if onboundary else 1.0) * ori[k - int(off[0])]
+    return out
+
+
+class VoronoiData:
+    """VoronoiData(VG; getFIELD...) (voronoidata.jl:545-703, docstring :571-620): the fields of the reference's data view that
+    this path and its geometry products fill.  Every field is a hard copy (the reference's `getFIELD=true`).
+
+    nodes, vertices, boundary_vertices (edge => (base, direction, node), voronoidata.jl:580-582), neighbors, orientations, volume,
+    area, boundary_nodes, bulk_integral, interface_integral, references / reference_shifts / offset (reduce_to_periodic=False).
+
+    Integrals: the reference integrates a Julia closure; across the C ABI the integrands are the monomials up to degree two
+    (bulk: 1, x_a, x_a x_b -> bulk_integral[i] of length 1 + d + d*d) and up to degree one on interfaces (1, x_a ->
+    interface_integral[i][k] of length 1 + d), exact (hvb_cell_moments, hvb_cell_area_moments).
+
+    Periodic domains, reduce_to_periodic=True (default, as in the reference): neighbours are folded back to the caller's ids, a
+    node may appear several times (voronoidata.jl:589), sorted=True orders them with their areas / integrals / orientations.
+    reduce_to_periodic=False shows the halo: ids n+1..n+offset are the periodic copies (the reference numbers them 1..offset IN
+    FRONT of the official nodes; here they stay behind them, as the backend numbers them), references[k] is the official node
+    halo node k copies and reference_shifts[k] the shift: node[n + k] = node[references[k]] + reference_shifts[k]."""
+
+    def __init__(self, VG, getvertices=False, getneighbors=False, getvolume=False, getarea=False, getorientations=False,
+                 getboundary_vertices=False, getboundary_nodes=False, getbulk_integral=False, getinterface_integral=False,
+                 getreferences=False, getreference_shifts=False, copyall=False, reduce_to_periodic=True, onboundary=False,
+                 sorted=False, **_ignored):
         self.nodes = VG.nodes
+        self.geometry = VG
         m = VG.mesh
-        if getvolume:
-            self.volume = m.volumes()
-        if getarea:
-            off, _ids = m.neighbors()
-            a = m.areas()
-            self.area = [a[off[i]:off[i + 1]] for i in range(getattr(m, "n_user", m.n))]
-        if getvertices:
-            self.vertices = [list(m.vertices_iterator(i)) for i in range(1, getattr(m, "n_user", m.n) + 1)]
         nu = getattr(m, "n_user", m.n)
-        if getneighbors:
-            off, ids = m.neighbors()
-            # periodic domains: neighbours folded back to the caller's ids (reduce_to_periodic, voronoidata.jl:623)
-            self.neighbors = [np.unique(m.origin_of(ids[off[i]:off[i + 1]])) for i in range(nu)]
+        n_halo = getattr(m, "n_halo", 0)
+        dom = VG.domain
+        want = lambda f: bool(f) or bool(copyall)
+        self.boundary = dom
+        self.boundary_nodes_on_boundary = bool(onboundary)
+        self.offset = 0 if reduce_to_periodic else n_halo
+        if want(getvolume):
+            self.volume = m.volumes()
+        if want(getvertices):
+            self.vertices = [list(m.vertices_iterator(i)) for i in range(1, nu + 1)]
+        if want(getboundary_vertices):
+            self.boundary_vertices = {tuple(int(g) for g in e): (np.array(b), np.array(u), int(nd))
+                                      for e, b, u, nd in zip(m.ray_edge, m.ray_base, m.ray_dir, m.ray_node)}
+        if n_halo and (want(getreferences) or want(getreference_shifts)):
+            self.references = np.array(m.halo_origin)
+            self.reference_shifts = np.asarray(m.halo_xs) - np.asarray(VG.nodes)[np.asarray(m.halo_origin) - 1]
+        if want(getbulk_integral):
+            vol, first, second = m.moments()
+            self.bulk_integral = np.concatenate([vol[:, None], first, second.reshape(len(vol), -1)], axis=1)
+            if want(getvolume):
+                self.volume = vol
+        per_nb = [want(getneighbors), want(getarea), want(getorientations), want(getinterface_integral), want(getboundary_nodes)]
+        if not any(per_nb):
+            return
+        off, ids = m.neighbors()
+        off = np.asarray(off, dtype=np.int64); ids = np.asarray(ids, dtype=np.int64)
+        lo, hi = int(off[0]), int(off[nu])
+        shown = ids[lo:hi]
+        if reduce_to_periodic and n_halo:
+            # periodic copies fold back to the node they copy, planes follow the official nodes (voronoidata.jl:623)
+            shown = m.origin_of(shown)
+        order = None
+        if sorted and reduce_to_periodic and n_halo:
+            cell = np.repeat(np.arange(nu), np.diff(off[:nu + 1]))
+            order = np.lexsort((shown, cell))
+            shown = shown[order]
+        pick = (lambda a: a[order]) if order is not None else (lambda a: a)
+        loc = off[:nu + 1] - lo
+        if want(getneighbors):
+            self.neighbors = _split(shown, loc, nu)
+        if want(getarea) and not want(getinterface_integral):
+            self.area = _split(pick(np.asarray(m.areas())[lo:hi]), loc, nu)
+        if want(getinterface_integral):
+            a, first = m.area_moments()
+            if want(getarea):
+                self.area = _split(pick(np.asarray(a)[lo:hi]), loc, nu)
+            self.interface_integral = _split(pick(np.concatenate([np.asarray(a)[lo:hi, None], np.asarray(first)[lo:hi]], axis=1)), loc, nu)
+        halo_xs = getattr(m, "halo_xs", None) if n_halo else None
+        if want(getorientations):
+            self.orientations = _split(pick(orientations_of(VG.nodes, off, ids, nu, halo_xs, dom.base, dom.normal)), loc, nu)
+        if want(getboundary_nodes):
+            self.boundary_nodes = boundary_nodes_of(VG.nodes, off, ids, nu, n_halo, dom.base, dom.normal, onboundary)

@@ -200,3 +200,34 @@ def test_interface_moments(hvb, d, n):
     pair = {(int(c) + 1, int(j)): k for k, (c, j) in enumerate(zip(cell, ids)) if j <= n}
     ks = np.array([[k, pair[(j, i)]] for (i, j), k in pair.items()])
     assert np.abs(first[ks[:, 0]] - first[ks[:, 1]]).max() < 1e-13
+
+
+# ---- the VoronoiData view (voronoidata.jl:571-620) on the device result; the assembly itself is checked on the CPU in
+# tests/test_voronoidata_cpu.py on a stand-in mesh ------------------------------------------------------------------------
+def test_voronoi_data_fields(hvb):
+    d, n = 3, 1500
+    xs = points(n, d, 590)
+    dom = hvb.cuboid(d, periodic=[])
+    vd = hvb.VoronoiData(hvb.VoronoiGeometry(xs, dom), copyall=True)
+    assert abs(vd.volume.sum() - 1.0) < 1e-11 and np.abs(vd.bulk_integral[:, 1:1 + d].sum(0) - 0.5).max() < 1e-11
+    assert len(vd.neighbors) == len(vd.orientations) == len(vd.area) == len(vd.interface_integral) == n
+    for i in range(n):
+        ori, area = vd.orientations[i], vd.area[i]
+        L = np.linalg.norm(ori, axis=1)
+        assert abs((area * L).sum() / (2 * d) / vd.volume[i] - 1.0) < 1e-10
+        assert np.linalg.norm((area[:, None] * ori / L[:, None]).sum(0)) / area.sum() < 1e-10
+        for k, j in enumerate(vd.neighbors[i]):
+            if j > n:
+                assert np.allclose(vd.boundary_nodes[i + 1][int(j) - n], xs[i] + ori[k], rtol=0, atol=1e-15)
+    # periodic: neighbours folded to the caller's ids, orientations point to the image the cell touches
+    vp = hvb.VoronoiData(hvb.VoronoiGeometry(xs, hvb.cuboid(d)), getneighbors=True, getorientations=True, getarea=True, getvolume=True,
+                         sorted=True)
+    assert abs(vp.volume.sum() - 1.0) < 1e-11
+    for i in range(n):
+        nb, ori, area = vp.neighbors[i], vp.orientations[i], vp.area[i]
+        assert int(nb.max()) <= n and list(nb) == sorted(nb)
+        L = np.linalg.norm(ori, axis=1)
+        assert abs((area * L).sum() / (2 * d) / vp.volume[i] - 1.0) < 1e-10
+        assert np.linalg.norm((area[:, None] * ori / L[:, None]).sum(0)) / area.sum() < 1e-10
+        shift = ori - (xs[nb - 1] - xs[i])                                  # a whole number of periods
+        assert np.abs(shift - np.round(shift)).max() < 1e-12
