@@ -144,3 +144,33 @@ def test_periodic_view_folds_and_sorts(hvb):
     assert raw.offset == 3 and list(raw.neighbors[0]) == [2, 3, 5, 6]
     assert np.array_equal(raw.references, halo_origin) and np.array_equal(raw.reference_shifts, shifts)
     assert np.array_equal(allx[4:], xs[raw.references - 1] + raw.reference_shifts)
+
+
+@pytest.mark.parametrize("d,n,margin", [(2, 300, 0.35), (3, 150, 0.75)])
+def test_periodic_view_on_the_explicit_halo_problem(hvb, oracle, d, n, margin):
+    """the assertions of tests/test_gpu_volumes.py::test_voronoi_data_fields (periodic part) on the halo problem solved by the
+    restated reference: halo copies within `margin`, periodic planes pushed out by it, the backend's numbering
+    (caller 1..n, halo n+1..n+nh, planes behind)"""
+    import periodic_oracle as po
+    xs = points(n, d, 960 + d)
+    axes = tuple(range(1, d + 1))
+    origin, mult, hxs = po.halo(xs, axes, margin)
+    ext = np.vstack([xs, hxs])
+    base, normal = po.pushed_cuboid(d, axes, margin)
+    o = oracle.run(ext, base, normal)
+    mesh = StandInMesh(ext, o["sig"], o["r"], o["nb_off"], o["nb_ids"], base, normal, halo=(origin, hxs))
+    mesh.volumes = lambda: hostsim.volumes(ext, o["sig"], base, normal)[:n]
+    vp = hvb.VoronoiData(StandInGeometry(xs, mesh, hvb.cuboid(d)), getneighbors=True, getorientations=True, getarea=True, getvolume=True,
+                         sorted=True)
+    assert abs(vp.volume.sum() - 1.0) < 1e-11
+    for i in range(n):
+        nb, ori, area = vp.neighbors[i], vp.orientations[i], vp.area[i]
+        assert int(nb.max()) <= n and list(nb) == sorted(nb)
+        L = np.linalg.norm(ori, axis=1)
+        assert abs((area * L).sum() / (2 * d) / vp.volume[i] - 1.0) < 1e-10
+        assert np.linalg.norm((area[:, None] * ori / L[:, None]).sum(0)) / area.sum() < 1e-10
+        shift = ori - (xs[nb - 1] - xs[i])                                  # a whole number of periods
+        assert np.abs(shift - np.round(shift)).max() < 1e-12
+    raw = hvb.VoronoiData(StandInGeometry(xs, mesh, hvb.cuboid(d)), getneighbors=True, getreferences=True, reduce_to_periodic=False)
+    assert raw.offset == len(origin) and max(int(nb.max()) for nb in raw.neighbors) > n
+    assert np.allclose(ext[n:], xs[raw.references - 1] + raw.reference_shifts, rtol=0, atol=0)
