@@ -95,10 +95,19 @@ mutable struct Context
     nplanes::Int
     multi::Bool
 end
-const CONTEXTS = IdDict{Any, Context}()
+# weak keys: a searcher that is garbage-collected takes its device context with it (finalizer below), so a session that
+# builds many geometries does not accumulate GPU memory
+const CONTEXTS = WeakKeyDict{Any, Context}()
+function destroy!(c::Context)
+    if c.ptr != C_NULL
+        ccall((:hvb_destroy, LIB), Cvoid, (Ptr{Cvoid},), c.ptr)
+        c.ptr = C_NULL
+    end
+    return nothing
+end
 function release_contexts!()
     for (_, c) in CONTEXTS
-        c.ptr != C_NULL && ccall((:hvb_destroy, LIB), Cvoid, (Ptr{Cvoid},), c.ptr)
+        destroy!(c)
     end
     empty!(CONTEXTS)
 end
@@ -110,11 +119,11 @@ function context_for(searcher, xs::Vector{P}, threading::B200Thread) where {P}
     np = length(planes)
     multi = threading.ngpus > 1
     old = get(CONTEXTS, searcher, nothing)
-    if old !== nothing && old.dim == d && old.nplanes == np && old.multi == multi
+    if old !== nothing && old.ptr != C_NULL && old.dim == d && old.nplanes == np && old.multi == multi
         GC.@preserve xs check(ccall((:hvb_set_points, LIB), Cint, (Ptr{Cvoid}, Int64, Ptr{Float64}), old.ptr, n, pointer(reinterpret(Float64, xs))), old.ptr)
         return old.ptr
     end
-    old !== nothing && ccall((:hvb_destroy, LIB), Cvoid, (Ptr{Cvoid},), old.ptr)
+    old !== nothing && destroy!(old)
     base = Matrix{Float64}(undef, d, np); normal = Matrix{Float64}(undef, d, np)
     for (k, pl) in enumerate(planes)
         base[:, k] .= pl.base; normal[:, k] .= pl.normal
@@ -140,7 +149,9 @@ function context_for(searcher, xs::Vector{P}, threading::B200Thread) where {P}
                         ctx, d, n, pointer(reinterpret(Float64, xs)), np, base, normal, prm))
         end
     end
-    CONTEXTS[searcher] = Context(ctx[], d, np, multi)
+    c = Context(ctx[], d, np, multi)
+    CONTEXTS[searcher] = c
+    finalizer(_ -> destroy!(c), searcher)          # RaycastIncircleSkip is a mutable struct (raycast-types.jl:372)
     return ctx[]
 end
 
