@@ -460,6 +460,18 @@ def main():
     n_per_gpu, d = WORKLOADS[args.workload]
     if args.impl == "reference":
         return run_reference(args, args.workload, n_per_gpu, d, rank, world)
+    if args.gpus > 1 and "WORLD_SIZE" not in os.environ:
+        # `python bench.py --gpus N` outside torchrun: one rank per GPU is the contract, so launch the ranks here instead of
+        # printing an N-GPU line measured on one GPU
+        import socket
+        with socket.socket() as sk:
+            sk.bind(("127.0.0.1", 0))
+            port = sk.getsockname()[1]
+        cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(args.gpus), "--master-addr", "127.0.0.1",
+               "--master-port", str(port), os.path.abspath(__file__)] + sys.argv[1:]
+        os.execv(sys.executable, cmd)
+    if args.gpus != world:
+        raise SystemExit("bench.py: --gpus %d but WORLD_SIZE=%d" % (args.gpus, world))
 
     import torch
     import hvb200  # noqa: F401

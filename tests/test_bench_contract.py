@@ -65,3 +65,11 @@ def test_committed_gpu_line_carries_the_contract_keys():
     assert j["gpu_launches"] > 0 and j["clocks"]["sm_mhz"] and not j["clocks"]["reasons"]
     assert {"value", "unit", "cores", "kind", "sample"} <= set(j["cpu_baseline"])
     assert "workload" in j["config"] and j["vs_baseline"] is None
+
+
+def test_gpus_must_match_the_launch():
+    """an N-GPU line is never printed from a different number of ranks"""
+    env = dict(os.environ, RANK="0", WORLD_SIZE="2", LOCAL_RANK="0")
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--gpus", "4", "--steps", "1", "--warmup", "0"],
+                         capture_output=True, text=True, timeout=120, cwd=ROOT, env=env)
+    assert out.returncode != 0 and "WORLD_SIZE=2" in out.stderr and out.stdout.strip() == ""
