@@ -213,9 +213,11 @@ class Runner:
         self.abi = hvb200._abi
         n_per_gpu, self.d = WORKLOADS[name]
         self.world, self.rank = env["world"], env["rank"]
-        self.strong = name in STRONG and self.world > 1
-        self.n_total = n_per_gpu if self.strong or self.world == 1 else n_per_gpu * self.world
-        self.n_per_gpu = self.n_total // self.world if self.strong else n_per_gpu
+        self.ngpus = env.get("ngpus", 1)                 # > 1: ONE process drives the GPUs through hvb_create_multi (--single-process)
+        parts = self.world * self.ngpus
+        self.strong = name in STRONG and parts > 1
+        self.n_total = n_per_gpu if self.strong or parts == 1 else n_per_gpu * parts
+        self.n_per_gpu = self.n_total // parts if self.strong else n_per_gpu
         self.periodic = name in PERIODIC
         self.settings = settings
         self.dom = hvb200.cuboid(self.d) if self.periodic else hvb200.cuboid(self.d, periodic=[])
@@ -229,7 +231,12 @@ class Runner:
         if self.s is None:                               # the context (device + page-locked buffers) is re-used
             kw = dict(neighbors=1, wire32=1)             # ids cross PCIe as int32 (hvb_view_vertices32 / hvb_view_neighbors32)
             kw.update(self.settings)
-            opts = hvb.RaycastParameter(threading=hvb.B200Thread(self.env["local_rank"], self.rank, self.world), **kw)
+            if self.ngpus > 1:
+                kw["wire32"] = 0                         # the shards of several GPUs are copied into the caller's int64 buffers
+                thr = hvb.B200Thread(ngpus=self.ngpus)
+            else:
+                thr = hvb.B200Thread(self.env["local_rank"], self.rank, self.world)
+            opts = hvb.RaycastParameter(threading=thr, **kw)
             self.s = hvb.Raycast(xs, domain=self.dom, options=opts, periodic=self.periodic)
             if self.world > 1:
                 from hvb200 import multigpu
@@ -252,7 +259,8 @@ class Runner:
         torch, L, abi, d = self.torch, self.L, self.abi, self.d
         xs = self.xs_pin.numpy()
         xs[:] = cloud(self.n_total, d, it)               # new synthetic cloud every step (identical on every rank)
-        self.env["flush"].fill_(it & 0xff)
+        for buf in self.env["flush"] if isinstance(self.env["flush"], list) else [self.env["flush"]]:
+            buf.fill_(it & 0xff)
         self.env["barrier"]()
         t0 = time.perf_counter()
         s = self.searcher(xs)
@@ -316,6 +324,8 @@ class Runner:
         peak, peak_src = measured_peak()
         # roofline of the dominant kernel (the walk): algorithmic bytes per launch / average launch duration, this rank
         v_rank = stats_last["raycasts"] - stats_last["duplicate_hits"] if self.world > 1 else stats_last["vertices"]
+        if self.ngpus > 1:                               # counters are summed over the GPUs, the kernel time is the slowest GPU's
+            v_rank = (stats_last["raycasts"] - stats_last["duplicate_hits"]) / self.ngpus
         bytes_per_launch = B_ALG[d] * (v_rank * steps) / max(kern_launches, 1)
         avg_launch_s = kern_ms * 1e-3 / max(kern_launches, 1)
         achieved = bytes_per_launch / avg_launch_s / 1e9
@@ -324,14 +334,14 @@ class Runner:
         return {
             "value": verts / (dev_ms_tot * 1e-3), "unit": "vertices/s", "steps": steps, "warmup": warmup, "ms_per_step": dev_ms_tot / steps,
             "scaling": "strong" if self.strong else "weak",
-            "config": {"workload": workload_text(self.name, self.n_per_gpu, self.n_total, d, self.periodic), "parallelism": "slab%d" % self.world,
+            "config": {"workload": workload_text(self.name, self.n_per_gpu, self.n_total, d, self.periodic), "parallelism": ("one process, %d GPUs (hvb_create_multi)" % self.ngpus) if self.ngpus > 1 else "slab%d" % self.world,
                        "l2": "256 MiB L2 flush before every step; steps timed one by one and summed", "settings": self.settings,
                        "wire": "ids cross PCIe as int32 (wire32), coordinates as f64"},
             "e2e": {"value": verts / e2e_tot, "unit": "vertices/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": 1e3 * e2e_tot / steps,
                     "phase_ms": dict(zip(("set_points", "search", "fetch_vertices", "neighbors"), (1e3 * self.phases / steps).round(3).tolist()))},
             "gpu_launches": launches,
             "roofline": {"bound": "hbm", "kernel": kname, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": measured_traffic(self.name) if self.world == 1 else None, "peak_source": peak_src, "bytes_per_vertex": B_ALG[d],
+                         "traffic": measured_traffic(self.name) if self.world == 1 and self.ngpus == 1 else None, "peak_source": peak_src, "bytes_per_vertex": B_ALG[d],
                          "vertices_per_launch": v_rank * steps / max(kern_launches, 1), "launches_per_step": kern_launches / steps,
                          "kernel_ms_per_step": kern_ms / steps},
             "vertices_per_step": verts / steps,
@@ -452,6 +462,9 @@ def main():
     ap.add_argument("--cpu-points", type=int, default=100000)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-parity", action="store_true")
+    ap.add_argument("--single-process", action="store_true",
+                    help="--gpus N in ONE process without torch.distributed: the library drives the GPUs (hvb_create_multi, one host thread + "
+                         "context per GPU, ncclCommInitAll) -- the model of a Julia caller (INTEGRATION.md)")
     ap.add_argument("--setting", action="append", default=[], help="backend knob, e.g. tile_size=8")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
@@ -460,7 +473,10 @@ def main():
     n_per_gpu, d = WORKLOADS[args.workload]
     if args.impl == "reference":
         return run_reference(args, args.workload, n_per_gpu, d, rank, world)
-    if args.gpus > 1 and "WORLD_SIZE" not in os.environ:
+    single = args.single_process and args.gpus > 1
+    if single and world > 1:
+        raise SystemExit("bench.py: --single-process is not launched under torchrun")
+    if args.gpus > 1 and "WORLD_SIZE" not in os.environ and not single:
         # `python bench.py --gpus N` outside torchrun: one rank per GPU is the contract, so launch the ranks here instead of
         # printing an N-GPU line measured on one GPU
         import socket
@@ -470,7 +486,7 @@ def main():
         cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(args.gpus), "--master-addr", "127.0.0.1",
                "--master-port", str(port), os.path.abspath(__file__)] + sys.argv[1:]
         os.execv(sys.executable, cmd)
-    if args.gpus != world:
+    if args.gpus != world and not single:
         raise SystemExit("bench.py: --gpus %d but WORLD_SIZE=%d" % (args.gpus, world))
 
     import torch
@@ -502,6 +518,14 @@ def main():
 
     env = {"rank": rank, "local_rank": local_rank, "world": world, "dist": dist, "torch": torch, "barrier": barrier, "all_max": all_max,
            "flush": torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device="cuda")}      # > 126 MB L2
+    if single:
+        env["ngpus"] = args.gpus
+        env["flush"] = [torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device="cuda:%d" % k) for k in range(args.gpus)]
+
+        def barrier():                                    # noqa: F811  (every device, not only the current one)
+            for k in range(args.gpus):
+                torch.cuda.synchronize(k)
+        env["barrier"] = barrier
 
     par = {}
     if world > 1 and not args.no_parity and args.workload not in PERIODIC:
