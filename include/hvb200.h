@@ -55,12 +55,13 @@ typedef struct hvb_params {
     double break_tol;         /* 1e-5  : above this a vertex is dropped and counted in hvb_stats_t.rejected (raycast.jl:271) */
     double b_nodes_tol;       /* 1e-7  : in the reference only widens the in-range ball that collects cospherical generators
                                  (raycast.jl:870; adjust_boundary_vertex boundary.jl:444 is a no-op).  Here: accepted and
-                                 validated (> 0); candidates inside the reference's tie window are REPORTED as non-general
-                                 position (HVB_EDEGENERATE), see on_degenerate */
+                                 validated (> 0); candidates inside the reference's tie window mark the cloud as being in
+                                 non-general position: resolved or reported, see on_degenerate */
     double plane_tolerance;   /* 1e-12 : half-space slack  c = c1 + |c1| * plane_tolerance (raycast.jl:802-804) and smallest
                                  accepted ray parameter t (raycast.jl:887-889) */
-    double ray_tol;           /* 1e-12 : used by the reference only inside FastEdgeIterator (edgeiterate.jl:199,435-460), the
-                                 enumeration of non-general vertices this backend reports instead; accepted and validated */
+    double ray_tol;           /* 1e-12 : used by the reference only inside FastEdgeIterator (edgeiterate.jl:199,435-460), its
+                                 enumeration of non-general vertices; this backend resolves or reports such vertices differently
+                                 (on_degenerate); accepted and validated */
     int32_t method;           /* 0 RCStandard/RCNonGeneral/RCNonGeneralHP, 1 RCOriginal, 2 RCCombined, 3 RCNonGeneralFast,
                                  4 RCOriginalSafety, 5 RCNonGeneralSkip, 6 RCOriginalHP, 7 RCNonGeneralCutoff
                                  (raycast-types.jl:244-284).  The methods differ in the PROCEDURE that finds the min-t
@@ -176,7 +177,9 @@ int hvb_create(hvb_ctx** out, int dim, int64_t n, const double* xs,
  * domain appears once per image that touches caller generators (each caller cell needs its own image, as in the
  * reference's mesh); hvb_fetch_vertex_flags marks one canonical image per class (hvb_stats_t.unique_vertices).
  * Neighbour lists have n+nhalo+1 offsets; they are built for the caller generators (halo cells get empty lists).
- * plane_bc == NULL is hvb_create.  world > 1 and seed vertices are not supported on periodic contexts yet. */
+ * plane_bc == NULL is hvb_create.  world > 1 shards a periodic context like any other (the ranks agree on the halo margin by one
+ * ncclAllReduce through the context's communicator, hvb_comm_init / hvb_create_multi); seed vertices and hvb_clean_affected are
+ * not supported on periodic contexts yet. */
 int hvb_create_periodic(hvb_ctx** out, int dim, int64_t n, const double* xs,
                         int nplanes, const double* plane_base, const double* plane_normal, const int32_t* plane_bc,
                         const hvb_params* params);
