@@ -308,7 +308,6 @@ int hvb_adopt_device_padded(hvb_ctx* ctx, const void* sig_dev, const void* r_dev
  * merged result is installed (hvb_adopt_device*, hvb_merge_device, hvb_allgather), after which they cover every cell. */
 int hvb_fetch_owned(hvb_ctx* ctx, uint8_t* owned);
 
-/* rare_events / statistics.jl:132-143 analogue */
 /* Refinement.  Replaces clean_affected! (src/meshrefine.jl:126-149) inside systematic_refine! (:183-216):
  * the context holds ALL generators, old and new (hvb_set_points), the new ones being the id range
  * [first_new, first_new + n_new) (the reference prepends them: first_new = 1); sig/r are the nv vertices of the caller's
@@ -351,6 +350,8 @@ int hvb_cell_areas(hvb_ctx* ctx, double* area);
  * general position. */
 int hvb_cell_area_moments(hvb_ctx* ctx, double* area, double* first);
 
+/* counters and device times of the last hvb_create / hvb_set_points / hvb_search: the analogue of the searcher's rare_events and
+ * of the counters statistics.jl:132-143 reports (raycasts, nn / inrange work per vertex) */
 int hvb_stats(hvb_ctx* ctx, hvb_stats_t* out);
 
 const char* hvb_last_error(hvb_ctx* ctx);   /* ctx may be NULL: message of the last failed hvb_create */
