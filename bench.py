@@ -336,7 +336,7 @@ class Runner:
             "scaling": "strong" if self.strong else "weak",
             "config": {"workload": workload_text(self.name, self.n_per_gpu, self.n_total, d, self.periodic), "parallelism": ("one process, %d GPUs (hvb_create_multi)" % self.ngpus) if self.ngpus > 1 else "slab%d" % self.world,
                        "l2": "256 MiB L2 flush before every step; steps timed one by one and summed", "settings": self.settings,
-                       "wire": "ids cross PCIe as int32 (wire32), coordinates as f64"},
+                       "wire": "ids cross PCIe as int64, coordinates as f64" if self.ngpus > 1 else "ids cross PCIe as int32 (wire32), coordinates as f64"},
             "e2e": {"value": verts / e2e_tot, "unit": "vertices/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": 1e3 * e2e_tot / steps,
                     "phase_ms": dict(zip(("set_points", "search", "fetch_vertices", "neighbors"), (1e3 * self.phases / steps).round(3).tolist()))},
             "gpu_launches": launches,

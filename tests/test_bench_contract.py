@@ -73,3 +73,36 @@ def test_gpus_must_match_the_launch():
     out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--gpus", "4", "--steps", "1", "--warmup", "0"],
                          capture_output=True, text=True, timeout=120, cwd=ROOT, env=env)
     assert out.returncode != 0 and "WORLD_SIZE=2" in out.stderr and out.stdout.strip() == ""
+
+
+def run_mock(*args):
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "mock_backend.py"), "--no-products"] + list(args),
+                         capture_output=True, text=True, timeout=600, cwd=ROOT)
+    assert out.returncode == 0, out.stderr[-2000:]
+    lines = [ln for ln in out.stdout.splitlines() if ln.startswith("{")]
+    assert len(lines) == 1                                  # ONE JSON line
+    return json.loads(lines[0])
+
+
+def test_own_arm_python_logic_against_a_mock_backend():
+    """bench.py's step loop, workload bookkeeping and JSON line without a GPU: `torch` and the `hvb200` host API are stood in for
+    by tests/mock_backend.py (the oracle behind the API's names); the numbers mean nothing (data = MOCK), the keys do"""
+    j = run_mock("--steps", "2", "--warmup", "3", "--cpu-points", "1500")
+    assert BASE_KEYS | {"roofline", "clocks", "gpu_launches", "e2e", "cpu_baseline", "workloads"} <= set(j)
+    assert j["data"] == "MOCK" and j["n_gpus"] == 1 and j["steps"] == 2 and j["warmup"] == 3 and j["vs_baseline"] is None
+    assert j["config"]["workload"].startswith("C2:") and j["config"]["parallelism"] == "slab1" and "model" not in j["config"]
+    r = j["roofline"]
+    assert r["bound"] == "hbm" and abs(r["frac"] - r["achieved"] / r["peak"]) < 1e-12 and r["bytes_per_vertex"] == 429.0
+    assert j["e2e"]["h2d_bytes_per_step"] == 1500 * 3 * 8 and j["e2e"]["d2h_bytes_per_step"] > 0
+    assert set(j["workloads"]) == {"C4", "C3"}
+    for w in j["workloads"].values():
+        assert {"value", "e2e", "roofline", "config"} <= set(w)
+    cb = j["cpu_baseline"]
+    assert cb["kind"] == "port" and cb["cores"] == 1 and cb["value"] > 0
+
+
+def test_single_process_mode_python_logic_against_a_mock_backend():
+    j = run_mock("--gpus", "2", "--single-process", "--steps", "1", "--warmup", "3", "--no-cpu-baseline", "--extra", "C3")
+    assert j["n_gpus"] == 2 and "hvb_create_multi" in j["config"]["parallelism"] and "(3000 total)" in j["config"]["workload"]
+    assert j["scaling"] == "weak" and j["workloads"]["C3"]["scaling"] == "strong"        # C3 keeps its total (BASELINE configs[2])
+    assert j["roofline"]["traffic"] is None
