@@ -176,3 +176,25 @@ def test_every_ccall_of_the_julia_shim_matches_its_c_prototype():
     # the entry points the seam needs are all bound
     assert {"hvb_create", "hvb_create_multi", "hvb_create_periodic", "hvb_set_points", "hvb_search", "hvb_counts", "hvb_fetch_vertices",
             "hvb_fetch_vertices_var", "hvb_fetch_rays", "hvb_last_error", "hvb_destroy", "hvb_default_params", "hvb_convex_hull"} <= seen
+
+
+def test_header_is_plain_c_and_the_c_example_links(tmp_path):
+    """include/hvb200.h compiles as C99 (no C++ types at the boundary), examples/c_example.c links against libhvb200.so, and on a
+    box without a GPU the run ends at hvb_create with HVB_ENOGPU -- never with a result"""
+    import shutil
+    import subprocess
+    import hvb200
+    hvb200._abi.lib()
+    if shutil.which("gcc") is None:
+        pytest.skip("no gcc")
+    libdir = os.path.join(ROOT, "highvoronoi.jl_b200", "lib")
+    exe = str(tmp_path / "c_example")
+    cc = subprocess.run(["gcc", "-std=c99", "-Wall", "-Wextra", "-Werror", "-pedantic", "-I" + os.path.join(ROOT, "include"),
+                         os.path.join(ROOT, "examples", "c_example.c"), "-L" + libdir, "-lhvb200", "-Wl,-rpath," + libdir, "-lm", "-o", exe],
+                        capture_output=True, text=True)
+    assert cc.returncode == 0, cc.stderr
+    from conftest import cuda_available
+    if cuda_available():
+        return                                              # the run itself belongs to the GPU suite (test_gpu_parity.py)
+    run = subprocess.run([exe, "500", "3"], capture_output=True, text=True)
+    assert run.returncode == 3 and "no host fallback" in run.stderr and "vertices" not in run.stdout

@@ -231,3 +231,21 @@ def test_voronoi_data_fields(hvb):
         assert np.linalg.norm((area[:, None] * ori / L[:, None]).sum(0)) / area.sum() < 1e-10
         shift = ori - (xs[nb - 1] - xs[i])                                  # a whole number of periods
         assert np.abs(shift - np.round(shift)).max() < 1e-12
+
+
+def test_c_example_runs_against_the_library(tmp_path):
+    """the C ABI from plain C (examples/c_example.c): create, search, fetch, neighbour lists, volumes -- the reference's
+    known-answer test (sum of the volumes = 1) is the program's exit code"""
+    import os
+    import shutil
+    import subprocess
+    from conftest import ROOT
+    if shutil.which("gcc") is None:
+        pytest.skip("no gcc")
+    libdir = os.path.join(ROOT, "highvoronoi.jl_b200", "lib")
+    exe = str(tmp_path / "c_example")
+    subprocess.run(["gcc", "-std=c99", "-I" + os.path.join(ROOT, "include"), os.path.join(ROOT, "examples", "c_example.c"),
+                    "-L" + libdir, "-lhvb200", "-Wl,-rpath," + libdir, "-lm", "-o", exe], check=True)
+    run = subprocess.run([exe, "20000", "3"], capture_output=True, text=True, timeout=120)
+    assert run.returncode == 0, run.stdout + run.stderr
+    assert "20000 generators, d = 3" in run.stdout and "sum of the cell volumes - 1" in run.stdout
