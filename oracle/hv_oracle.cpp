@@ -15,7 +15,13 @@
 // tests do hold for this path -- the cell volumes add up to the volume of the domain
 // (test/rcmethods.jl:8, test/multithread.jl:8, test/basics.jl:46) -- is run on this oracle's
 // rows in tests/test_hostsim.py::test_cell_volume_formula_matches_qhull and on the GPU result
-// in tests/test_gpu_volumes.py; exact values beyond that invariant stay unpinned.
+// in tests/test_gpu_volumes.py.  The reference also PUBLISHES outputs of this path: docs/src/index.md:93,96 print the matrices
+// its own harness (statistics.jl:98-143) produced with the real package -- vertices, boundary vertices, walks and nn-searches per
+// walk for N uniform points in the unit cube, d = 4 and 5, means over 4 unseeded clouds.  tests/golden/ref_published holds them and
+// tests/test_oracle.py::test_published_statistics_of_the_reference / test_published_vertex_count_at_30000_nodes hold this
+// restatement to them statistically (841 395.0 published vertices at d = 4, N = 30 000: +0.012 % here; 2 687 943.75 at d = 5,
+// N = 20 000: -0.042 %; descents 36.0 against 39.5; nn-searches per walk of RCOriginal 2.60 against 2.61).  Bit-level values
+// (signature by signature) stay unpinned until oracle/make_reference_fixtures.jl has been run by someone who has Julia.
 //
 // Methods: the default RCNonGeneralHP (raycast.jl:794-970) and, selected with hvo_set_method, RCOriginal (:972-1012),
 // RCCombined (:504-528 with the nested KD traversal of extended.jl:155-176, kd_tree.jl:210-336, searchtrees.jl:50-194) and
