@@ -118,7 +118,7 @@ if __name__ == "__main__":
     spec = importlib.util.spec_from_file_location("bench", os.path.join(ROOT, "bench.py"))
     bench = importlib.util.module_from_spec(spec)
     spec.loader.exec_module(bench)
-    bench.WORKLOADS.update({"C2": (1500, 3), "C4": (150, 5), "C3": (3000, 2)})     # the workload NAMES of the line, oracle-sized
+    bench.WORKLOADS.update({"C2": (1500, 3), "C4": (150, 5), "C3": (3000, 2), "D4": (400, 4)})     # the workload NAMES of the line, oracle-sized
     bench.cloud.__globals__["ROOT"] = ROOT
     _dumps = bench.json.dumps
     bench.json = types.SimpleNamespace(**{k: getattr(bench.json, k) for k in ("load", "loads")},

@@ -94,7 +94,9 @@ def test_own_arm_python_logic_against_a_mock_backend():
     r = j["roofline"]
     assert r["bound"] == "hbm" and abs(r["frac"] - r["achieved"] / r["peak"]) < 1e-12 and r["bytes_per_vertex"] == 429.0
     assert j["e2e"]["h2d_bytes_per_step"] == 1500 * 3 * 8 and j["e2e"]["d2h_bytes_per_step"] > 0
-    assert set(j["workloads"]) == {"C4", "C3"}
+    assert set(j["workloads"]) == {"C4", "C3", "D4"}
+    pb = j["workloads"]["D4"]["published_by_the_reference"]            # docs/src/index.md:93: 841 395.0 vertices in 14.37 s
+    assert abs(pb["vertices_per_s"] - 58557.6) < 0.1 and pb["value_over_published"] > 0 and pb["e2e_over_published"] > 0
     for w in j["workloads"].values():
         assert {"value", "e2e", "roofline", "config"} <= set(w)
     cb = j["cpu_baseline"]
