@@ -280,3 +280,22 @@ def test_published_vertex_counts_of_the_reference(hvb, d, n):
     assert tuple(V) == PUBLISHED_SCALE_CLOUDS[(d, n)]
     assert abs(np.mean(V) / pub["vertices"][c] - 1.0) < 0.0025
     assert abs(np.mean(B) / pub["boundary_vertices"][c] - 1.0) < 0.016
+
+
+def test_published_curves_of_the_reference(hvb):
+    """every entry of the matrices the reference publishes (docs/src/index.md:93,96) up to 30 000 (d = 4) / 20 000 (d = 5) nodes, 4 seeded
+    clouds each: the device returns exactly the restated reference's vertex and boundary-vertex counts (golden/ref_published/
+    seeded_counts.json), whose means follow the published curves (tests/test_oracle.py::test_seeded_counts_follow_the_published_curves)"""
+    from test_oracle import seeded_counts
+    searcher = {}
+    for (d, n), g in sorted(seeded_counts().items()):
+        for k in range(4):
+            xs = points(n, d, 8000 + 1000 * d + 10 * g["column"] + k)
+            if d not in searcher:
+                searcher[d] = hvb.Raycast(xs, domain=hvb.cuboid(d, periodic=[]))
+            else:
+                searcher[d].set_points(xs)
+            mesh, _ = hvb.voronoi(xs, searcher=searcher[d])
+            sig = np.asarray(mesh.sig)
+            assert sig.shape[0] == g["vertices"][k], (d, n, k)
+            assert int((sig > n).any(axis=1).sum()) == g["boundary_vertices"][k], (d, n, k)

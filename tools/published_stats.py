@@ -56,5 +56,29 @@ def big():
             d, n, np.mean(V), pv, 100 * (np.mean(V) / pv - 1), np.mean(B), pb, 100 * (np.mean(B) / pb - 1)))
 
 
+def counts():
+    """every entry of both matrices up to 30 000 (d = 4) / 20 000 (d = 5) nodes on 4 seeded clouds points(n, d, 8000 + 1000 d + 10 c + k),
+    c = column of the matrix, k = 0..3: the restatement's vertex / boundary-vertex counts -> tests/golden/ref_published/seeded_counts.json
+    (the counts the device path has to return for the same clouds, tests/test_gpu_volumes.py)"""
+    out = {}
+    for d, maxn in ((4, 30000), (5, 20000)):
+        base, normal = qhull_oracle.cuboid(d)
+        p = PUB[d]
+        for c, n in enumerate(p["nodes"]):
+            if n > maxn:
+                continue
+            V, B = [], []
+            for k in range(4):
+                xs = np.random.default_rng(8000 + 1000 * d + 10 * c + k).random((n, d))
+                r = hv_oracle.run(xs, base, normal, nthreads=min(8, os.cpu_count() or 1))
+                V.append(len(r["sig"])); B.append(int((r["sig"] > n).any(axis=1).sum()))
+            out["%d,%d" % (d, n)] = {"column": c, "vertices": V, "boundary_vertices": B}
+            print("d=%d N=%5d  vertices %+.4f  boundary %+.4f  (ours / published - 1; times sqrt(N): %+.2f, %+.2f)" % (
+                d, n, np.mean(V) / p["vertices"][c] - 1, np.mean(B) / p["boundary_vertices"][c] - 1,
+                np.sqrt(n) * (np.mean(V) / p["vertices"][c] - 1), np.sqrt(n) * (np.mean(B) / p["boundary_vertices"][c] - 1)), flush=True)
+    with open(os.path.join(ROOT, "tests", "golden", "ref_published", "seeded_counts.json"), "w") as f:
+        json.dump(out, f)
+
+
 if __name__ == "__main__":
-    big() if len(sys.argv) > 1 and sys.argv[1] == "big" else small()
+    {"big": big, "counts": counts}.get(sys.argv[1] if len(sys.argv) > 1 else "", small)()
