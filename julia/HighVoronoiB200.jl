@@ -155,14 +155,16 @@ function context_for(searcher, xs::Vector{P}, threading::B200Thread) where {P}
     return ctx[]
 end
 
-# the vertices a mesh already holds (refinement callers pass a non-empty mesh, meshrefine.jl:199-215): every vertex once,
-# through the iterator over the vertices stored primarily at a cell, in external numbering (all_vertices_iterator,
-# abstractmesh.jl:176,183-187 -- a view may permute the ids, so "sig[1] == i" is not a test for the owner cell; the library
-# orders every seed row itself); plane ids in the external numbering n+p
+# the vertices a mesh already holds (refinement callers pass a non-empty mesh, meshrefine.jl:199-215): every vertex once.
+# `vertices_iterator(mesh, i)` is the one iterator EVERY mesh type that reaches this seam implements -- RefineMesh forwards it
+# (meshrefine.jl:58-59) but not `all_vertices_iterator` -- and it lists a vertex at each of its cells, in external numbering; a
+# view may permute the ids, so the owner is not "sig[1]" but the smallest generator: the vertex is taken at cell minimum(sig)
+# (plane ids n+p are larger than every generator).  The library orders every seed row itself.
 function known_vertices(mesh, n::Int, d::Int)
     sigs = Int64[]; rs = Float64[]
     for i in 1:n
-        for (sig, r) in HighVoronoi.all_vertices_iterator(mesh, i)
+        for (sig, r) in HighVoronoi.vertices_iterator(mesh, i)
+            minimum(sig) == i || continue
             length(sig) == d + 1 || error("HighVoronoiB200: the mesh holds a non-general vertex (more than dim+1 generators): not supported by the device search")
             append!(sigs, sig); append!(rs, r)
         end

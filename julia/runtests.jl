@@ -17,7 +17,7 @@ using .HighVoronoiB200
 function vertex_dict(mesh, n)
     out = Dict{Vector{Int64}, Vector{Float64}}()
     for i in 1:n
-        for (sig, r) in HighVoronoi.all_vertices_iterator(mesh, i)
+        for (sig, r) in HighVoronoi.vertices_iterator(mesh, i)      # implemented by every mesh type; lists a vertex at each of its cells
             out[sort(collect(sig))] = collect(r)
         end
     end

@@ -31,8 +31,8 @@ function fixture(path, dim, n, seed; bounded = true)
     HighVoronoi.voronoi(mesh, searcher = searcher, silence = true)
     rows = Tuple{Vector{Int64}, Vector{Float64}}[]
     for i in 1:n
-        for (sig, r) in HighVoronoi.all_vertices_iterator(mesh, i)      # stored primarily at cell i: every vertex once
-            push!(rows, (external_sig(sig, n, length(dom)), collect(r)))
+        for (sig, r) in HighVoronoi.vertices_iterator(mesh, i)          # lists a vertex at each of its cells: taken at its smallest generator
+            minimum(sig) == i && push!(rows, (external_sig(sig, n, length(dom)), collect(r)))
         end
     end
     sort!(rows, by = x -> x[1])

@@ -5,7 +5,7 @@
 #
 # Protocol of the reference's own harness (src/statistics.jl:98-126): uniform rand(dim, N) in the unit cube, domain
 # cuboid(dim, periodic=[]), search only: Raycast(xs; domain) + voronoi(), with threading switched on as the docs describe
-# (docs/src/man/multithread.md:18-22).  Vertices are counted once (at their owner cell, all_vertices_iterator abstractmesh.jl:176,183-187).
+# (docs/src/man/multithread.md:18-22).  Vertices are counted once (at the cell of their smallest generator; vertices_iterator, abstractmesh.jl:175-182).
 #
 # usage: julia run_reference.jl <dim> <npoints> <steps> <warmup> <threads>
 # prints one JSON line: {"vertices": total over the timed steps, "seconds": total, "threads": t, "julia": version}
@@ -15,8 +15,8 @@ using Random
 function count_vertices(mesh, n)
     c = 0
     for i in 1:n
-        for _ in HighVoronoi.all_vertices_iterator(mesh, i)      # the vertices stored primarily at cell i: every vertex once
-            c += 1
+        for (sig, _) in HighVoronoi.vertices_iterator(mesh, i)   # lists a vertex at each of its cells: counted at its smallest generator
+            minimum(sig) == i && (c += 1)
         end
     end
     return c
