@@ -51,6 +51,7 @@ WORKLOADS = {  # name -> (points per GPU, dim)
 }
 PERIODIC = {"C5", "C5s", "P3", "P2"}
 DEFAULT_PERSISTENT = 3          # hvb_default_params: the walk variant behind persistent (include/hvb200.h)
+DEFAULT_EXTRA = "C4,C3,D4"     # side workloads of the default line (D4 at N = 1 only: it carries the reference's one-thread figure)
 STRONG = {"C3"}                 # N > 1: the total stays fixed (BASELINE.json configs[2] names 1 000 000 points over all GPUs)
 
 
@@ -455,7 +456,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="C2", choices=sorted(WORKLOADS))
-    ap.add_argument("--extra", default="C4,C3,D4", help="workloads reported under `workloads` in the same line ('' = none)")
+    ap.add_argument("--extra", default=DEFAULT_EXTRA, help="workloads reported under `workloads` in the same line ('' = none)")
     ap.add_argument("--extra-steps", type=int, default=3)
     ap.add_argument("--no-products", action="store_true", help="skip the `products` timings (convex hull, lattice)")
     ap.add_argument("--ref-points", type=float, default=100000)
@@ -536,11 +537,18 @@ def main():
     res = main_run.run(args.steps, args.warmup)
     clocks = sampler.stop() if sampler else None
     main_run.close()
-    extras = {}
+    extras, extra_errors = {}, {}
     for name in [w for w in args.extra.split(",") if w and w != args.workload]:
-        r = Runner(name, env, settings)
-        extras[name] = r.run(max(1, min(args.extra_steps, args.steps)), 1)
-        r.close()
+        if name == "D4" and world > 1 and args.extra == DEFAULT_EXTRA:
+            continue                                      # the published number is a one-thread figure: reported at N = 1 only
+        try:
+            r = Runner(name, env, settings)
+            extras[name] = r.run(max(1, min(args.extra_steps, args.steps)), 1)
+            r.close()
+        except Exception as e:                            # noqa: BLE001
+            if world > 1:
+                raise                                     # ranks must not part ways in front of a collective
+            extra_errors[name] = repr(e)                  # a side workload must not take the headline line down
     if rank != 0:
         if dist is not None:
             dist.destroy_process_group()
@@ -554,6 +562,8 @@ def main():
     if extras:
         line["workloads"] = {k: {kk: v[kk] for kk in ("value", "unit", "steps", "warmup", "ms_per_step", "scaling", "config", "e2e", "roofline", "vertices_per_step",
                                                       "stats_last_step")} for k, v in extras.items()}
+    if extra_errors:
+        line["workload_errors"] = extra_errors
     if "D4" in extras and world == 1:
         # the one workload of this bench the reference publishes a number for (docs/src/index.md:93): 30 000
         # uniform points in the unit cube, d = 4 -- 841 395.0 vertices in 14.37 s on one thread of the author's PC
